@@ -1,0 +1,810 @@
+// csgpu.cu — C ABI (include/csgpu.h) + index lifecycle + kernel dispatch.
+//
+// Mirrors the state machine of /root/reference/src/vectordb/store.rs:
+//   insert (store.rs:618-686) / delete (:548-610) flip indexed=false; build_index (:386-430)
+//   flips it back; search on a dirty index is an error (:440-444); clear (:690-706) empties.
+// There is no CPU fallback anywhere in this file: every search is a CUDA kernel launch.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+
+#include "index.h"
+#include "scan.cuh"
+#include "synth.cuh"
+
+namespace csgpu {
+
+static thread_local std::string t_error;
+std::atomic<uint64_t> g_kernel_launches{0};
+
+void set_error(const std::string &msg) { t_error = msg; }
+int fail(int code, const std::string &msg) { t_error = msg; return code; }
+int fail_cuda(cudaError_t e, const char *what, const char *file, int line)
+{
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    t_error = buf;
+    cudaGetLastError();  // clear sticky-less errors
+    return (e == cudaErrorMemoryAllocation) ? CSGPU_ERR_OOM : CSGPU_ERR_CUDA;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int d) { cudaGetDevice(&prev); if (prev != d) cudaSetDevice(d); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+static inline void count_launch(uint64_t n = 1) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---------------------------------------------------------------------------------------
+// contexts
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t MAX_GRID = 148 * 4;   // upper bound on persistent grid size we ever launch
+constexpr uint32_t MAX_BATCH = 16;       // queries per multi-query scan
+
+static int ctx_create(const csgpu_index *ix, Shard *sh, SearchCtx **out)
+{
+    DeviceGuard g(sh->device);
+    SearchCtx *c = new SearchCtx();
+    c->device = sh->device;
+    CS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CS_CUDA(cudaEventCreate(&c->ev0));
+    CS_CUDA(cudaEventCreate(&c->ev1));
+    CS_CUDA(cudaMalloc(&c->q_dev, (size_t)MAX_BATCH * ix->dim_pad * sizeof(float)));
+    CS_CUDA(cudaHostAlloc(&c->q_pin, (size_t)MAX_BATCH * ix->dim_pad * sizeof(float), cudaHostAllocDefault));
+    c->cand_cap = (size_t)MAX_GRID * CSGPU_MAX_K;
+    CS_CUDA(cudaMalloc(&c->cand, c->cand_cap * sizeof(uint64_t)));
+    CS_CUDA(cudaMalloc(&c->gather, (size_t)8 * CSGPU_MAX_K * sizeof(uint64_t)));
+    CS_CUDA(cudaMalloc(&c->ticket, 64 * sizeof(unsigned)));
+    CS_CUDA(cudaMemset(c->ticket, 0, 64 * sizeof(unsigned)));
+    CS_CUDA(cudaMalloc(&c->out_dev, (size_t)MAX_BATCH * CSGPU_MAX_K * sizeof(uint64_t)));
+    CS_CUDA(cudaHostAlloc(&c->out_pin, (size_t)MAX_BATCH * CSGPU_MAX_K * sizeof(uint64_t),
+                          cudaHostAllocMapped | cudaHostAllocPortable));
+    *out = c;
+    return CSGPU_OK;
+}
+
+static void ctx_destroy(SearchCtx *c)
+{
+    if (!c) return;
+    DeviceGuard g(c->device);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    cudaFree(c->q_dev); cudaFreeHost(c->q_pin); cudaFree(c->cand); cudaFree(c->gather); cudaFree(c->ticket);
+    cudaFree(c->out_dev); cudaFreeHost(c->out_pin); cudaFree(c->bitmap_dev);
+    delete c;
+}
+
+static int ctx_acquire(const csgpu_index *ix, Shard *sh, SearchCtx **out)
+{
+    {
+        std::lock_guard<std::mutex> lk(sh->ctx_mu);
+        if (!sh->free_ctx.empty()) { *out = sh->free_ctx.back(); sh->free_ctx.pop_back(); return CSGPU_OK; }
+    }
+    SearchCtx *c = nullptr;
+    int rc = ctx_create(ix, sh, &c);
+    if (rc) { ctx_destroy(c); return rc; }
+    std::lock_guard<std::mutex> lk(sh->ctx_mu);
+    sh->all_ctx.push_back(c);
+    *out = c;
+    return CSGPU_OK;
+}
+
+static void ctx_release(Shard *sh, SearchCtx *c)
+{
+    std::lock_guard<std::mutex> lk(sh->ctx_mu);
+    sh->free_ctx.push_back(c);
+}
+
+// ---------------------------------------------------------------------------------------
+// scan dispatch
+// ---------------------------------------------------------------------------------------
+template <int V, bool EXACT, bool BIG>
+static cudaError_t launch_scan_v(const ScanArgs &a, uint32_t grid, size_t smem, cudaStream_t st)
+{
+    constexpr int R = (V <= 2) ? 8 : (V <= 4 ? 4 : 2);
+    auto kern = scan_topk_kernel<V, EXACT, R, BIG>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<grid, SCAN_THREADS, smem, st>>>(a);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <bool BIG>
+static cudaError_t launch_scan_b(const ScanArgs &a, uint32_t grid, size_t smem, cudaStream_t st)
+{
+    const uint32_t V = (a.dim4 + 31) / 32;
+    const bool exact = (a.dim4 % 32) == 0;
+#define CS_CASE(v)                                                                    \
+    case v: return exact ? launch_scan_v<v, true, BIG>(a, grid, smem, st)              \
+                         : launch_scan_v<v, false, BIG>(a, grid, smem, st);
+    switch (V) {
+        CS_CASE(1) CS_CASE(2) CS_CASE(3) CS_CASE(4) CS_CASE(5) CS_CASE(6) CS_CASE(7) CS_CASE(8)
+        default: return cudaErrorInvalidValue;
+    }
+#undef CS_CASE
+}
+
+static uint32_t rows_in_flight(uint32_t dim4)
+{
+    const uint32_t V = (dim4 + 31) / 32;
+    return (V <= 2) ? 8 : (V <= 4 ? 4 : 2);
+}
+
+// Enqueue one single-query scan of `sh` on `st`. q_dev: [dim_pad] on the shard's device.
+static int enqueue_scan(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const float *q_dev, uint32_t k,
+                        const uint64_t *bitmap_dev, uint64_t n_bits, bool with_zero_ids, uint64_t *out_keys,
+                        cudaStream_t st)
+{
+    ScanArgs a;
+    a.rows = reinterpret_cast<const float4 *>(sh->rows);
+    a.ids = sh->ids;
+    a.n_rows = sh->n_built;
+    a.dim4 = ix->dim4;
+    a.q = q_dev;
+    a.k = k;
+    const bool big = k > 32;
+    a.kpad = big ? pow2_at_least(k, 64) : 32;
+    a.bitmap = bitmap_dev;
+    a.n_bits = n_bits;
+    a.zero_ids = with_zero_ids ? ix->zero_ids_dev : nullptr;
+    a.n_zero = with_zero_ids ? (uint32_t)ix->zero_ids.size() : 0;
+    a.cand = c->cand;
+    a.ticket = c->ticket;
+    a.out_keys = out_keys;
+    const uint32_t per_cta_rows = SCAN_WARPS * rows_in_flight(ix->dim4);
+    uint64_t want = (sh->n_built + per_cta_rows - 1) / per_cta_rows;
+    uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sh->sm_count * (big ? 1 : 2), std::max<uint64_t>(want, 1));
+    if (grid > MAX_GRID) grid = MAX_GRID;
+    const size_t smem = big ? (size_t)2 * SCAN_WARPS * a.kpad * sizeof(uint64_t) : (size_t)SCAN_WARPS * 32 * sizeof(uint64_t);
+    cudaError_t e = big ? launch_scan_b<true>(a, grid, smem, st) : launch_scan_b<false>(a, grid, smem, st);
+    if (e != cudaSuccess) return fail_cuda(e, "scan_topk_kernel launch", __FILE__, __LINE__);
+    return CSGPU_OK;
+}
+
+static int enqueue_merge(const uint64_t *keys_dev, uint64_t total, uint32_t k, uint64_t *out, cudaStream_t st)
+{
+    const bool big = k > 32;
+    const uint32_t kpad = big ? pow2_at_least(k, 64) : 32;
+    const size_t smem = big ? (size_t)2 * SCAN_WARPS * kpad * sizeof(uint64_t) : (size_t)SCAN_WARPS * 32 * sizeof(uint64_t);
+    cudaError_t e;
+    if (big) {
+        if (smem > 48 * 1024) {
+            e = cudaFuncSetAttribute(merge_keys_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return fail_cuda(e, "merge attr", __FILE__, __LINE__);
+        }
+        merge_keys_kernel<true><<<1, SCAN_THREADS, smem, st>>>(keys_dev, total, k, kpad, out);
+    } else {
+        merge_keys_kernel<false><<<1, SCAN_THREADS, smem, st>>>(keys_dev, total, k, kpad, out);
+    }
+    count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(e, "merge_keys_kernel launch", __FILE__, __LINE__);
+    return CSGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// storage
+// ---------------------------------------------------------------------------------------
+static int shard_reserve(const csgpu_index *ix, Shard *sh, uint64_t rows)
+{
+    if (rows <= sh->cap) return CSGPU_OK;
+    DeviceGuard g(sh->device);
+    uint64_t ncap = std::max<uint64_t>(rows, sh->cap + sh->cap / 2);
+    ncap = std::max<uint64_t>(ncap, 1024);
+    float *nrows = nullptr; uint32_t *nids = nullptr; uint8_t *nst = nullptr;
+    const size_t row_bytes = (size_t)ix->dim_pad * sizeof(float);
+    cudaError_t e = cudaMalloc(&nrows, ncap * row_bytes);
+    if (e != cudaSuccess && ncap > rows) {  // retry with the exact size before giving up
+        cudaGetLastError();
+        ncap = rows;
+        e = cudaMalloc(&nrows, ncap * row_bytes);
+    }
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(rows)", __FILE__, __LINE__);
+    if ((e = cudaMalloc(&nids, ncap * sizeof(uint32_t))) != cudaSuccess) { cudaFree(nrows); return fail_cuda(e, "cudaMalloc(ids)", __FILE__, __LINE__); }
+    if ((e = cudaMalloc(&nst, ncap)) != cudaSuccess) { cudaFree(nrows); cudaFree(nids); return fail_cuda(e, "cudaMalloc(status)", __FILE__, __LINE__); }
+    CS_CUDA(cudaMemsetAsync(nst, 0, ncap, sh->stream));
+    if (sh->n_total) {
+        CS_CUDA(cudaMemcpyAsync(nrows, sh->rows, sh->n_total * row_bytes, cudaMemcpyDeviceToDevice, sh->stream));
+        CS_CUDA(cudaMemcpyAsync(nids, sh->ids, sh->n_total * sizeof(uint32_t), cudaMemcpyDeviceToDevice, sh->stream));
+        CS_CUDA(cudaMemcpyAsync(nst, sh->status, sh->n_total, cudaMemcpyDeviceToDevice, sh->stream));
+    }
+    CS_CUDA(cudaStreamSynchronize(sh->stream));
+    cudaFree(sh->rows); cudaFree(sh->ids); cudaFree(sh->status);
+    sh->rows = nrows; sh->ids = nids; sh->status = nst; sh->cap = ncap;
+    return CSGPU_OK;
+}
+
+// Kill rows (all shards) whose id is in `ids` (any order). Returns rows killed (+ zero-norm ids dropped).
+static int kill_ids(csgpu_index *ix, const uint32_t *ids, uint64_t n, uint64_t *killed)
+{
+    *killed = 0;
+    if (n == 0) return CSGPU_OK;
+    std::vector<uint32_t> sorted(ids, ids + n);
+    std::sort(sorted.begin(), sorted.end());
+    sorted.erase(std::unique(sorted.begin(), sorted.end()), sorted.end());
+    // zero-norm rows live on the host list only
+    if (!ix->zero_ids.empty()) {
+        std::vector<uint32_t> keep;
+        keep.reserve(ix->zero_ids.size());
+        for (uint32_t z : ix->zero_ids) {
+            if (std::binary_search(sorted.begin(), sorted.end(), z)) ++*killed; else keep.push_back(z);
+        }
+        ix->zero_ids.swap(keep);
+    }
+    for (Shard *sh : ix->shards) {
+        if (sh->n_total == 0) continue;
+        DeviceGuard g(sh->device);
+        uint32_t *kill_dev = nullptr;
+        unsigned long long *cnt_dev = nullptr;
+        CS_CUDA(cudaMalloc(&kill_dev, sorted.size() * sizeof(uint32_t)));
+        CS_CUDA(cudaMalloc(&cnt_dev, sizeof(unsigned long long)));
+        CS_CUDA(cudaMemsetAsync(cnt_dev, 0, sizeof(unsigned long long), sh->stream));
+        CS_CUDA(cudaMemcpyAsync(kill_dev, sorted.data(), sorted.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, sh->stream));
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((sh->n_total + 255) / 256, (uint64_t)sh->sm_count * 8);
+        mark_dead_kernel<<<grid, 256, 0, sh->stream>>>(sh->ids, sh->status, sh->n_total, kill_dev, (uint32_t)sorted.size(), cnt_dev);
+        count_launch();
+        unsigned long long cnt = 0;
+        CS_CUDA(cudaMemcpyAsync(&cnt, cnt_dev, sizeof cnt, cudaMemcpyDeviceToHost, sh->stream));
+        CS_CUDA(cudaStreamSynchronize(sh->stream));
+        cudaFree(kill_dev); cudaFree(cnt_dev);
+        *killed += cnt;
+    }
+    return CSGPU_OK;
+}
+
+static Shard *least_loaded(csgpu_index *ix)
+{
+    Shard *best = ix->shards[0];
+    for (Shard *s : ix->shards) if (s->n_total < best->n_total) best = s;
+    return best;
+}
+
+static int upload_zero_ids(csgpu_index *ix)
+{
+    Shard *s0 = ix->shards[0];
+    DeviceGuard g(s0->device);
+    cudaFree(ix->zero_ids_dev);
+    ix->zero_ids_dev = nullptr;
+    if (!ix->zero_ids.empty()) {
+        CS_CUDA(cudaMalloc(&ix->zero_ids_dev, ix->zero_ids.size() * sizeof(uint32_t)));
+        CS_CUDA(cudaMemcpy(ix->zero_ids_dev, ix->zero_ids.data(), ix->zero_ids.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    return CSGPU_OK;
+}
+
+__global__ void gather_rows_bounce_kernel(const float4 *__restrict__ rows, float4 *__restrict__ bounce,
+                                          const uint32_t *__restrict__ keep_src, uint64_t n, uint32_t dim4)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t w0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t i = w0; i < n; i += nw) {
+        const float4 *s = rows + (uint64_t)keep_src[i] * dim4;
+        float4 *o = bounce + i * dim4;
+        for (uint32_t c = lane; c < dim4; c += 32) o[c] = s[c];
+    }
+}
+__global__ void gather_u32_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
+                                  const uint32_t *__restrict__ keep_src, uint64_t n)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        out[i] = in[keep_src[i]];
+}
+
+// Normalise pending rows, drop dead/zero/non-finite rows (stable), leave [0, n_built) all live.
+static int shard_build(csgpu_index *ix, Shard *sh, std::vector<uint32_t> &new_zero_ids)
+{
+    DeviceGuard g(sh->device);
+    const uint64_t n = sh->n_total;
+    if (n == 0) { sh->n_built = 0; return CSGPU_OK; }
+    const uint64_t pending = n - sh->n_built;
+    if (pending) {
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((pending + 7) / 8, (uint64_t)sh->sm_count * 8);
+        normalise_rows_kernel<<<grid, 256, 0, sh->stream>>>(reinterpret_cast<float4 *>(sh->rows), sh->status, sh->n_built, pending, ix->dim4);
+        count_launch();
+        CS_CUDA(cudaGetLastError());
+    }
+    std::vector<uint8_t> st(n);
+    CS_CUDA(cudaMemcpyAsync(st.data(), sh->status, n, cudaMemcpyDeviceToHost, sh->stream));
+    CS_CUDA(cudaStreamSynchronize(sh->stream));
+    uint64_t first_bad = n;
+    for (uint64_t i = 0; i < n; ++i) if (st[i] != ROW_OK) { first_bad = i; break; }
+    if (first_bad == n) { sh->n_built = n; return CSGPU_OK; }
+
+    // ids of zero-norm rows go to the host list; count non-finite
+    std::vector<uint32_t> keep_src;
+    keep_src.reserve(n - first_bad);
+    std::vector<uint64_t> zero_rows;
+    for (uint64_t i = first_bad; i < n; ++i) {
+        if (st[i] == ROW_OK) keep_src.push_back((uint32_t)i);
+        else if (st[i] == ROW_ZERO) zero_rows.push_back(i);
+        else if (st[i] == ROW_NONFINITE) ix->nonfinite_rows++;
+    }
+    for (uint64_t r : zero_rows) {
+        uint32_t id;
+        CS_CUDA(cudaMemcpy(&id, sh->ids + r, sizeof id, cudaMemcpyDeviceToHost));
+        new_zero_ids.push_back(id);
+    }
+    const uint64_t moved = keep_src.size();
+    if (moved) {
+        const uint64_t CH = 65536;  // rows per bounce chunk
+        uint32_t *keep_dev = nullptr; float *bounce = nullptr; uint32_t *bounce_ids = nullptr;
+        CS_CUDA(cudaMalloc(&keep_dev, moved * sizeof(uint32_t)));
+        CS_CUDA(cudaMalloc(&bounce, std::min(CH, moved) * (size_t)ix->dim_pad * sizeof(float)));
+        CS_CUDA(cudaMalloc(&bounce_ids, std::min(CH, moved) * sizeof(uint32_t)));
+        CS_CUDA(cudaMemcpyAsync(keep_dev, keep_src.data(), moved * sizeof(uint32_t), cudaMemcpyHostToDevice, sh->stream));
+        for (uint64_t c0 = 0; c0 < moved; c0 += CH) {
+            const uint64_t cn = std::min(CH, moved - c0);
+            const uint32_t grid = (uint32_t)std::min<uint64_t>((cn + 7) / 8, (uint64_t)sh->sm_count * 8);
+            gather_rows_bounce_kernel<<<grid, 256, 0, sh->stream>>>(reinterpret_cast<const float4 *>(sh->rows),
+                                                                     reinterpret_cast<float4 *>(bounce), keep_dev + c0, cn, ix->dim4);
+            gather_u32_kernel<<<(uint32_t)((cn + 255) / 256), 256, 0, sh->stream>>>(sh->ids, bounce_ids, keep_dev + c0, cn);
+            count_launch(2);
+            CS_CUDA(cudaMemcpyAsync(sh->rows + (first_bad + c0) * ix->dim_pad, bounce, cn * (size_t)ix->dim_pad * sizeof(float), cudaMemcpyDeviceToDevice, sh->stream));
+            CS_CUDA(cudaMemcpyAsync(sh->ids + first_bad + c0, bounce_ids, cn * sizeof(uint32_t), cudaMemcpyDeviceToDevice, sh->stream));
+        }
+        CS_CUDA(cudaStreamSynchronize(sh->stream));
+        cudaFree(keep_dev); cudaFree(bounce); cudaFree(bounce_ids);
+    }
+    sh->n_built = sh->n_total = first_bad + moved;
+    CS_CUDA(cudaMemsetAsync(sh->status, 0, sh->cap, sh->stream));
+    CS_CUDA(cudaStreamSynchronize(sh->stream));
+    return CSGPU_OK;
+}
+
+static bool all_finite(const float *q, uint32_t n)
+{
+    for (uint32_t i = 0; i < n; ++i) if (!std::isfinite(q[i])) return false;
+    return true;
+}
+
+static int check_search_args(const csgpu_index *ix, const float *q, uint32_t q_len, uint32_t k)
+{
+    if (!ix) return fail(CSGPU_ERR_ARG, "null index");
+    if (q_len != ix->dim) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "Query embedding dimension mismatch: expected %u, got %u", ix->dim, q_len);
+        return fail(CSGPU_ERR_DIM, buf);
+    }
+    if (!ix->built) return fail(CSGPU_ERR_NOT_BUILT, "Index not built. Call build_index() after inserting chunks.");
+    if (!q) return fail(CSGPU_ERR_ARG, "null query");
+    if (k > CSGPU_MAX_K) return fail(CSGPU_ERR_ARG, "k exceeds CSGPU_MAX_K (1024)");
+    return CSGPU_OK;
+}
+
+static void decode_keys(const uint64_t *keys, uint32_t k, uint32_t *out_ids, float *out_dist, uint32_t *out_n)
+{
+    uint32_t m = 0;
+    for (uint32_t i = 0; i < k; ++i) {
+        if (keys[i] == KEY_EMPTY) break;
+        const uint32_t bits = bits_from_okey((uint32_t)(keys[i] >> 32));
+        float d;
+        memcpy(&d, &bits, sizeof d);
+        if (out_ids) out_ids[m] = (uint32_t)keys[i];
+        if (out_dist) out_dist[m] = d;
+        ++m;
+    }
+    if (out_n) *out_n = m;
+}
+
+// One query (optionally filtered) through every shard; result keys land in ctx0->out_pin[0..k).
+static int search_one(const csgpu_index *ix, const float *q, uint32_t k, const uint64_t *bitmap, uint64_t n_bits,
+                      uint32_t *out_ids, float *out_dist, uint32_t *out_n)
+{
+    const size_t G = ix->shards.size();
+    std::vector<SearchCtx *> ctx(G, nullptr);
+    int rc = CSGPU_OK;
+    auto release_all = [&]() { for (size_t g = 0; g < G; ++g) if (ctx[g]) ctx_release(ix->shards[g], ctx[g]); };
+    for (size_t g = 0; g < G && !rc; ++g) rc = ctx_acquire(ix, ix->shards[g], &ctx[g]);
+    if (rc) { release_all(); return rc; }
+    const size_t qbytes = (size_t)ix->dim_pad * sizeof(float);
+    const size_t bm_words = bitmap ? (size_t)((n_bits + 63) / 64) : 0;
+
+    auto body = [&]() -> int {
+        for (size_t g = 0; g < G; ++g) {
+            Shard *sh = ix->shards[g];
+            SearchCtx *c = ctx[g];
+            DeviceGuard dg(sh->device);
+            memset(c->q_pin, 0, qbytes);
+            memcpy(c->q_pin, q, (size_t)ix->dim * sizeof(float));
+            CS_CUDA(cudaMemcpyAsync(c->q_dev, c->q_pin, qbytes, cudaMemcpyHostToDevice, c->stream));
+            const uint64_t *bm_dev = nullptr;
+            if (bitmap) {
+                if (c->bitmap_cap < bm_words) {
+                    CS_CUDA(cudaStreamSynchronize(c->stream));
+                    cudaFree(c->bitmap_dev); c->bitmap_dev = nullptr; c->bitmap_cap = 0;
+                    CS_CUDA(cudaMalloc(&c->bitmap_dev, std::max<size_t>(bm_words, 1) * sizeof(uint64_t)));
+                    c->bitmap_cap = std::max<size_t>(bm_words, 1);
+                }
+                if (bm_words) CS_CUDA(cudaMemcpyAsync(c->bitmap_dev, bitmap, bm_words * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+                bm_dev = c->bitmap_dev;
+            }
+            if (g == 0) CS_CUDA(cudaEventRecord(c->ev0, c->stream));
+            uint64_t *dst = (G == 1) ? c->out_pin : c->out_dev;
+            int r = enqueue_scan(ix, sh, c, c->q_dev, k, bm_dev, n_bits, /*with_zero_ids=*/g == 0, dst, c->stream);
+            if (r) return r;
+        }
+        SearchCtx *c0 = ctx[0];
+        if (G > 1) {
+            // gather every shard's k keys on shard 0 (peer copies over NVLink), merge there
+            DeviceGuard dg(ix->shards[0]->device);
+            uint64_t *gather = c0->gather;
+            for (size_t g = 1; g < G; ++g) {
+                DeviceGuard dg2(ix->shards[g]->device);
+                CS_CUDA(cudaMemcpyPeerAsync(gather + g * k, ix->shards[0]->device,
+                                            ctx[g]->out_dev, ix->shards[g]->device, (size_t)k * sizeof(uint64_t), ctx[g]->stream));
+                CS_CUDA(cudaEventRecord(ctx[g]->ev1, ctx[g]->stream));
+            }
+            for (size_t g = 1; g < G; ++g) CS_CUDA(cudaStreamWaitEvent(c0->stream, ctx[g]->ev1, 0));
+            CS_CUDA(cudaMemcpyAsync(gather, c0->out_dev, (size_t)k * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c0->stream));
+            int r = enqueue_merge(gather, (uint64_t)G * k, k, c0->out_pin, c0->stream);
+            if (r) return r;
+        }
+        {
+            DeviceGuard dg(ix->shards[0]->device);
+            CS_CUDA(cudaEventRecord(c0->ev1, c0->stream));
+            CS_CUDA(cudaStreamSynchronize(c0->stream));
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, c0->ev0, c0->ev1) == cudaSuccess) ix->last_search_us.store(ms * 1000.f);
+        }
+        decode_keys(c0->out_pin, k, out_ids, out_dist, out_n);
+        return CSGPU_OK;
+    };
+    rc = body();
+    if (rc) for (size_t g = 0; g < G; ++g) { DeviceGuard dg(ix->shards[g]->device); cudaStreamSynchronize(ctx[g]->stream); }
+    release_all();
+    return rc;
+}
+
+}  // namespace csgpu
+
+using namespace csgpu;
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+uint32_t csgpu_abi_version(void) { return CSGPU_ABI_VERSION; }
+const char *csgpu_last_error(void) { return t_error.c_str(); }
+uint64_t csgpu_kernel_launches(void) { return g_kernel_launches.load(); }
+
+int csgpu_create(csgpu_index **out, uint32_t dim, uint32_t dtype, const int32_t *devices, uint32_t n_devices)
+{
+    if (!out) return fail(CSGPU_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (dim == 0 || dim > CSGPU_MAX_DIM) return fail(CSGPU_ERR_ARG, "dim must be in [1, 4096]");
+    if (((dim + 3) / 4 + 31) / 32 > 8) return fail(CSGPU_ERR_ARG, "dim > 1024 is not supported by the scan kernels yet");
+    if (dtype != CSGPU_DTYPE_F32) return fail(CSGPU_ERR_ARG, "only CSGPU_DTYPE_F32 is implemented (bf16 index: planned)");
+    if (n_devices == 0) n_devices = 1;
+    if (n_devices > 8) return fail(CSGPU_ERR_ARG, "n_devices must be <= 8");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(CSGPU_ERR_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    }
+    csgpu_index *ix = new csgpu_index();
+    ix->dim = dim;
+    ix->dim_pad = (dim + 3) & ~3u;
+    ix->dim4 = ix->dim_pad / 4;
+    ix->dtype = dtype;
+    for (uint32_t g = 0; g < n_devices; ++g) {
+        const int dev = devices ? devices[g] : (int)g;
+        if (dev < 0 || dev >= count) { csgpu_destroy(ix); return fail(CSGPU_ERR_ARG, "device ordinal out of range"); }
+        cudaDeviceProp prop;
+        if ((e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess) { csgpu_destroy(ix); return fail_cuda(e, "cudaGetDeviceProperties", __FILE__, __LINE__); }
+        if (prop.major != 10) {
+            csgpu_destroy(ix);
+            return fail(CSGPU_ERR_CUDA, std::string("device is not sm_100 (Blackwell B200); this library ships sm_100a code only: ") + prop.name);
+        }
+        Shard *sh = new Shard();
+        sh->device = dev;
+        sh->sm_count = prop.multiProcessorCount;
+        ix->shards.push_back(sh);
+        DeviceGuard dg(dev);
+        if ((e = cudaStreamCreateWithFlags(&sh->stream, cudaStreamNonBlocking)) != cudaSuccess) { csgpu_destroy(ix); return fail_cuda(e, "cudaStreamCreate", __FILE__, __LINE__); }
+    }
+    // peer access for the in-process multi-GPU gather
+    for (size_t a = 0; a < ix->shards.size(); ++a)
+        for (size_t b = 0; b < ix->shards.size(); ++b) {
+            if (a == b) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, ix->shards[a]->device, ix->shards[b]->device);
+            if (can) { DeviceGuard dg(ix->shards[a]->device); cudaError_t pe = cudaDeviceEnablePeerAccess(ix->shards[b]->device, 0); if (pe != cudaSuccess) cudaGetLastError(); }
+        }
+    *out = ix;
+    return CSGPU_OK;
+}
+
+void csgpu_destroy(csgpu_index *ix)
+{
+    if (!ix) return;
+    for (Shard *sh : ix->shards) {
+        DeviceGuard dg(sh->device);
+        for (SearchCtx *c : sh->all_ctx) ctx_destroy(c);
+        cudaFree(sh->rows); cudaFree(sh->ids); cudaFree(sh->status);
+        if (sh->stream) cudaStreamDestroy(sh->stream);
+        delete sh;
+    }
+    if (ix->zero_ids_dev && !ix->shards.empty()) { cudaFree(ix->zero_ids_dev); }
+    delete ix;
+}
+
+int csgpu_reserve(csgpu_index *ix, uint64_t total_rows)
+{
+    if (!ix) return fail(CSGPU_ERR_ARG, "null index");
+    const uint64_t G = ix->shards.size();
+    for (Shard *sh : ix->shards) {
+        int rc = shard_reserve(ix, sh, (total_rows + G - 1) / G);
+        if (rc) return rc;
+    }
+    return CSGPU_OK;
+}
+
+int csgpu_append(csgpu_index *ix, const float *rows, const uint32_t *ids, uint64_t n)
+{
+    if (!ix) return fail(CSGPU_ERR_ARG, "null index");
+    if (n == 0) return CSGPU_OK;
+    if (!rows || !ids) return fail(CSGPU_ERR_ARG, "rows/ids is null");
+    // replace semantics (LMDB put): an id that is already present dies; within the batch the last wins
+    {
+        uint64_t killed = 0;
+        bool any_rows = !ix->zero_ids.empty();
+        for (Shard *sh : ix->shards) any_rows = any_rows || sh->n_total;
+        if (any_rows) { int rc = kill_ids(ix, ids, n, &killed); if (rc) return rc; }
+    }
+    std::vector<uint8_t> dup;  // rows of this batch superseded by a later row with the same id
+    {
+        bool increasing = true;
+        for (uint64_t i = 1; i < n && increasing; ++i) increasing = ids[i] > ids[i - 1];
+        if (!increasing) {
+            std::vector<uint64_t> order(n);
+            std::iota(order.begin(), order.end(), 0);
+            std::stable_sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return ids[a] < ids[b]; });
+            for (uint64_t i = 0; i + 1 < n; ++i)
+                if (ids[order[i]] == ids[order[i + 1]]) { if (dup.empty()) dup.assign(n, 0); dup[order[i]] = ROW_DEAD; }
+        }
+    }
+    const uint64_t G = ix->shards.size();
+    // big batches are split evenly; small ones go to the least-loaded shard
+    std::vector<std::pair<Shard *, std::pair<uint64_t, uint64_t>>> parts;
+    if (G > 1 && n >= 4096 * G) {
+        for (uint64_t g = 0; g < G; ++g) parts.push_back({ix->shards[g], {n * g / G, n * (g + 1) / G}});
+    } else {
+        parts.push_back({least_loaded(ix), {0, n}});
+    }
+    std::vector<float> padded;
+    for (auto &p : parts) {
+        Shard *sh = p.first;
+        const uint64_t a = p.second.first, b = p.second.second, m = b - a;
+        if (!m) continue;
+        int rc = shard_reserve(ix, sh, sh->n_total + m);
+        if (rc) return rc;
+        DeviceGuard dg(sh->device);
+        float *dst = sh->rows + sh->n_total * ix->dim_pad;
+        if (ix->dim_pad == ix->dim) {
+            CS_CUDA(cudaMemcpyAsync(dst, rows + a * ix->dim, m * (size_t)ix->dim * sizeof(float), cudaMemcpyHostToDevice, sh->stream));
+        } else {
+            CS_CUDA(cudaMemsetAsync(dst, 0, m * (size_t)ix->dim_pad * sizeof(float), sh->stream));
+            CS_CUDA(cudaMemcpy2DAsync(dst, (size_t)ix->dim_pad * sizeof(float), rows + a * ix->dim, (size_t)ix->dim * sizeof(float),
+                                      (size_t)ix->dim * sizeof(float), m, cudaMemcpyHostToDevice, sh->stream));
+        }
+        CS_CUDA(cudaMemcpyAsync(sh->ids + sh->n_total, ids + a, m * sizeof(uint32_t), cudaMemcpyHostToDevice, sh->stream));
+        if (!dup.empty()) CS_CUDA(cudaMemcpyAsync(sh->status + sh->n_total, dup.data() + a, m, cudaMemcpyHostToDevice, sh->stream));
+        else CS_CUDA(cudaMemsetAsync(sh->status + sh->n_total, 0, m, sh->stream));
+        CS_CUDA(cudaStreamSynchronize(sh->stream));
+        sh->n_total += m;
+    }
+    ix->built = false;
+    return CSGPU_OK;
+}
+
+int csgpu_append_synthetic(csgpu_index *ix, uint64_t seed, uint64_t first_row, uint64_t n, uint32_t id_base)
+{
+    if (!ix) return fail(CSGPU_ERR_ARG, "null index");
+    if (n == 0) return CSGPU_OK;
+    if (ix->dim != ix->dim_pad) return fail(CSGPU_ERR_ARG, "synthetic rows need dim % 4 == 0");
+    const uint64_t G = ix->shards.size();
+    for (uint64_t g = 0; g < G; ++g) {
+        Shard *sh = ix->shards[g];
+        const uint64_t a = n * g / G, b = n * (g + 1) / G, m = b - a;
+        if (!m) continue;
+        int rc = shard_reserve(ix, sh, sh->n_total + m);
+        if (rc) return rc;
+        DeviceGuard dg(sh->device);
+        const uint64_t total = m * ix->dim4;
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((total + 255) / 256, (uint64_t)sh->sm_count * 16);
+        synth_rows_kernel<<<grid, 256, 0, sh->stream>>>(reinterpret_cast<float4 *>(sh->rows) + sh->n_total * ix->dim4,
+                                                        sh->ids + sh->n_total, seed, first_row + a, m, ix->dim4, id_base);
+        count_launch();
+        CS_CUDA(cudaGetLastError());
+        CS_CUDA(cudaMemsetAsync(sh->status + sh->n_total, 0, m, sh->stream));
+        CS_CUDA(cudaStreamSynchronize(sh->stream));
+        sh->n_total += m;
+    }
+    ix->built = false;
+    return CSGPU_OK;
+}
+
+int csgpu_synth_rows_host(const csgpu_index *ix, uint64_t seed, uint64_t first_row, uint64_t n, float *out_rows)
+{
+    if (!ix || !out_rows) return fail(CSGPU_ERR_ARG, "null argument");
+    if (ix->dim != ix->dim_pad) return fail(CSGPU_ERR_ARG, "synthetic rows need dim % 4 == 0");
+    if (n == 0) return CSGPU_OK;
+    Shard *sh = ix->shards[0];
+    DeviceGuard dg(sh->device);
+    float *tmp = nullptr;
+    CS_CUDA(cudaMalloc(&tmp, n * (size_t)ix->dim_pad * sizeof(float)));
+    const uint64_t total = n * ix->dim4;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((total + 255) / 256, (uint64_t)sh->sm_count * 16);
+    synth_rows_kernel<<<grid, 256, 0, sh->stream>>>(reinterpret_cast<float4 *>(tmp), nullptr, seed, first_row, n, ix->dim4, 0);
+    count_launch();
+    cudaError_t e = cudaMemcpyAsync(out_rows, tmp, n * (size_t)ix->dim_pad * sizeof(float), cudaMemcpyDeviceToHost, sh->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(sh->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail_cuda(e, "synth_rows_host", __FILE__, __LINE__);
+    return CSGPU_OK;
+}
+
+int csgpu_remove(csgpu_index *ix, const uint32_t *ids, uint64_t n, uint64_t *n_removed)
+{
+    if (!ix) return fail(CSGPU_ERR_ARG, "null index");
+    if (n_removed) *n_removed = 0;
+    if (n == 0) return CSGPU_OK;
+    if (!ids) return fail(CSGPU_ERR_ARG, "ids is null");
+    uint64_t killed = 0;
+    int rc = kill_ids(ix, ids, n, &killed);
+    if (rc) return rc;
+    if (n_removed) *n_removed = killed;
+    ix->tombstones += killed;
+    ix->built = false;  // store.rs:605-607 — even a no-op delete leaves the index needing a rebuild
+    return CSGPU_OK;
+}
+
+int csgpu_build(csgpu_index *ix)
+{
+    if (!ix) return fail(CSGPU_ERR_ARG, "null index");
+    std::vector<uint32_t> new_zero;
+    for (Shard *sh : ix->shards) {
+        int rc = shard_build(ix, sh, new_zero);
+        if (rc) return rc;
+    }
+    if (!new_zero.empty()) {
+        ix->zero_ids.insert(ix->zero_ids.end(), new_zero.begin(), new_zero.end());
+        std::sort(ix->zero_ids.begin(), ix->zero_ids.end());
+        ix->zero_ids.erase(std::unique(ix->zero_ids.begin(), ix->zero_ids.end()), ix->zero_ids.end());
+    }
+    int rc = upload_zero_ids(ix);
+    if (rc) return rc;
+    ix->tombstones = 0;
+    ix->built = true;
+    return CSGPU_OK;
+}
+
+int csgpu_clear(csgpu_index *ix)
+{
+    if (!ix) return fail(CSGPU_ERR_ARG, "null index");
+    for (Shard *sh : ix->shards) {
+        DeviceGuard dg(sh->device);
+        cudaFree(sh->rows); cudaFree(sh->ids); cudaFree(sh->status);
+        sh->rows = nullptr; sh->ids = nullptr; sh->status = nullptr;
+        sh->n_built = sh->n_total = sh->cap = 0;
+    }
+    ix->zero_ids.clear();
+    upload_zero_ids(ix);
+    ix->nonfinite_rows = 0;
+    ix->tombstones = 0;
+    ix->built = false;
+    return CSGPU_OK;
+}
+
+int csgpu_search(const csgpu_index *ix, const float *q, uint32_t q_len, uint32_t k,
+                 uint32_t *out_ids, float *out_dist, uint32_t *out_n)
+{
+    if (out_n) *out_n = 0;
+    int rc = check_search_args(ix, q, q_len, k);
+    if (rc) return rc;
+    if (!all_finite(q, q_len)) return fail(CSGPU_ERR_ARG, "query contains NaN/Inf");
+    if (k == 0) return CSGPU_OK;
+    return search_one(ix, q, k, nullptr, 0, out_ids, out_dist, out_n);
+}
+
+int csgpu_search_filtered(const csgpu_index *ix, const float *q, uint32_t q_len, uint32_t k,
+                          const uint64_t *id_bitmap, uint64_t n_bits,
+                          uint32_t *out_ids, float *out_dist, uint32_t *out_n)
+{
+    if (out_n) *out_n = 0;
+    int rc = check_search_args(ix, q, q_len, k);
+    if (rc) return rc;
+    if (!id_bitmap && n_bits) return fail(CSGPU_ERR_ARG, "id_bitmap is null");
+    if (!all_finite(q, q_len)) return fail(CSGPU_ERR_ARG, "query contains NaN/Inf");
+    if (k == 0) return CSGPU_OK;
+    static const uint64_t empty_word = 0;
+    return search_one(ix, q, k, id_bitmap ? id_bitmap : &empty_word, n_bits, out_ids, out_dist, out_n);
+}
+
+int csgpu_search_batch(const csgpu_index *ix, const float *q, uint32_t q_len, uint32_t b, uint32_t k,
+                       uint32_t *out_ids, float *out_dist, uint32_t *out_n)
+{
+    for (uint32_t j = 0; j < b && out_n; ++j) out_n[j] = 0;
+    int rc = check_search_args(ix, q, q_len, k);
+    if (rc) return rc;
+    if (!all_finite(q, q_len * b)) return fail(CSGPU_ERR_ARG, "query contains NaN/Inf");
+    if (k == 0 || b == 0) return CSGPU_OK;
+    // v1: one fused scan per query (multi-query single-pass kernel: see DESIGN.md roadmap)
+    for (uint32_t j = 0; j < b; ++j) {
+        rc = search_one(ix, q + (size_t)j * q_len, k, nullptr, 0, out_ids + (size_t)j * k, out_dist + (size_t)j * k,
+                        out_n ? out_n + j : nullptr);
+        if (rc) return rc;
+    }
+    return CSGPU_OK;
+}
+
+int csgpu_search_keys_device(const csgpu_index *ix, const float *q_dev, uint32_t k, uint64_t *out_keys_dev, void *stream)
+{
+    if (!ix) return fail(CSGPU_ERR_ARG, "null index");
+    if (!ix->built) return fail(CSGPU_ERR_NOT_BUILT, "Index not built. Call build_index() after inserting chunks.");
+    if (ix->shards.size() != 1) return fail(CSGPU_ERR_ARG, "device entry points need a single-device index");
+    if (!q_dev || !out_keys_dev) return fail(CSGPU_ERR_ARG, "null device pointer");
+    if (k == 0 || k > CSGPU_MAX_K) return fail(CSGPU_ERR_ARG, "k must be in [1, 1024]");
+    Shard *sh = ix->shards[0];
+    SearchCtx *c = nullptr;
+    int rc = ctx_acquire(ix, sh, &c);
+    if (rc) return rc;
+    DeviceGuard dg(sh->device);
+    // NOTE: the scratch (cand/ticket) of this context is in flight until `stream` drains; the
+    // context is returned to the pool immediately, so callers must not run two device-entry
+    // searches of one index concurrently on different streams (documented in INTEGRATION.md).
+    rc = enqueue_scan(ix, sh, c, q_dev, k, nullptr, 0, true, out_keys_dev, (cudaStream_t)stream);
+    ctx_release(sh, c);
+    return rc;
+}
+
+int csgpu_merge_keys_device(const csgpu_index *ix, const uint64_t *keys_dev, uint32_t n_lists, uint32_t k,
+                            uint64_t *out_keys_dev, void *stream)
+{
+    if (!ix) return fail(CSGPU_ERR_ARG, "null index");
+    if (!keys_dev || !out_keys_dev) return fail(CSGPU_ERR_ARG, "null device pointer");
+    if (k == 0 || k > CSGPU_MAX_K || n_lists == 0) return fail(CSGPU_ERR_ARG, "bad k / n_lists");
+    DeviceGuard dg(ix->shards[0]->device);
+    return enqueue_merge(keys_dev, (uint64_t)n_lists * k, k, out_keys_dev, (cudaStream_t)stream);
+}
+
+void csgpu_decode_keys(const uint64_t *keys, uint32_t k, uint32_t *out_ids, float *out_dist, uint32_t *out_n)
+{
+    decode_keys(keys, k, out_ids, out_dist, out_n);
+}
+
+int csgpu_stats(const csgpu_index *ix, csgpu_stats_t *out)
+{
+    if (!ix || !out) return fail(CSGPU_ERR_ARG, "null argument");
+    memset(out, 0, sizeof *out);
+    out->dim = ix->dim;
+    out->dtype = ix->dtype;
+    out->n_devices = (uint32_t)ix->shards.size();
+    out->built = ix->built ? 1 : 0;
+    out->abi_version = CSGPU_ABI_VERSION;
+    out->zero_norm_rows = ix->zero_ids.size();
+    out->nonfinite_rows = ix->nonfinite_rows;
+    out->tombstones = ix->tombstones;
+    out->last_search_us = ix->last_search_us.load();
+    for (size_t g = 0; g < ix->shards.size(); ++g) {
+        const Shard *sh = ix->shards[g];
+        out->live_rows += sh->n_built;
+        out->pending_rows += sh->n_total - sh->n_built;
+        out->rows_per_device[g] = sh->n_built;
+        out->bytes_on_device += sh->cap * ((size_t)ix->dim_pad * sizeof(float) + sizeof(uint32_t) + 1);
+    }
+    out->live_rows += ix->zero_ids.size();
+    return CSGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,73 @@
+// index.h — host-side state of a csgpu_index (library-private; the public surface is include/csgpu.h).
+#pragma once
+#include <atomic>
+#include <cstdint>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/csgpu.h"
+
+namespace csgpu {
+
+// thread-local error text (csgpu_last_error)
+void set_error(const std::string &msg);
+int fail(int code, const std::string &msg);
+int fail_cuda(cudaError_t e, const char *what, const char *file, int line);
+extern std::atomic<uint64_t> g_kernel_launches;
+
+#define CS_CUDA(call)                                                                  \
+    do {                                                                               \
+        cudaError_t e__ = (call);                                                      \
+        if (e__ != cudaSuccess) return ::csgpu::fail_cuda(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+// Per-search scratch: one stream + buffers, so searches from different host threads overlap
+// (VectorStore::search is &self and is called from rayon/tokio threads concurrently,
+// /root/reference/src/search/mod.rs:508-511, src/server/mod.rs:545-548).
+struct SearchCtx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float *q_dev = nullptr;         // [max_b * dim_pad]
+    float *q_pin = nullptr;         // pinned staging for the query
+    uint64_t *cand = nullptr;       // [grid_max * CSGPU_MAX_K]
+    uint64_t *gather = nullptr;     // [8 * CSGPU_MAX_K] per-shard results gathered for the cross-GPU merge
+    unsigned *ticket = nullptr;
+    uint64_t *out_dev = nullptr;    // [max_b * CSGPU_MAX_K]
+    uint64_t *out_pin = nullptr;    // pinned, device-mapped; kernels write results straight here
+    uint64_t *bitmap_dev = nullptr; // filter bitmap staging
+    size_t bitmap_cap = 0;          // in u64 words
+    size_t cand_cap = 0;            // in keys
+};
+
+struct Shard {
+    int device = 0;
+    float *rows = nullptr;     // [cap, dim_pad] fp32; rows [0, n_built) are unit vectors
+    uint32_t *ids = nullptr;   // [cap]
+    uint8_t *status = nullptr; // [cap] ROW_* (all ROW_OK in [0, n_built) after build)
+    uint64_t n_built = 0;      // searchable rows
+    uint64_t n_total = 0;      // built + pending
+    uint64_t cap = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;  // build/append stream
+    std::mutex ctx_mu;
+    std::vector<SearchCtx *> free_ctx;
+    std::vector<SearchCtx *> all_ctx;
+};
+
+}  // namespace csgpu
+
+struct csgpu_index {
+    uint32_t dim = 0, dim_pad = 0, dim4 = 0;
+    uint32_t dtype = 0;
+    bool built = false;
+    std::vector<csgpu::Shard *> shards;
+    std::vector<uint32_t> zero_ids;       // ascending; rows with |v| = 0 (host truth)
+    uint32_t *zero_ids_dev = nullptr;     // on shards[0]->device
+    uint64_t nonfinite_rows = 0;
+    uint64_t tombstones = 0;
+    mutable std::atomic<float> last_search_us{0.f};
+};

@@ -1,0 +1,238 @@
+// scan.cuh — single-query exact cosine scan fused with top-k (the headline kernel).
+//
+// Replaces the arroy block at /root/reference/src/vectordb/store.rs:446-459 with the exact
+// ranking of /root/reference/examples/benchmark_models.rs:155-165,323-328 generalised to top-k.
+//
+// HBM layout: rows are row-major fp32 UNIT vectors, dim padded to a multiple of 4 floats, so a
+// row is `dim4` float4 (1536 B at D=384) and every warp-level load is a run of full 128 B lines.
+// ids[row] is the chunk id of that row (u32).
+//
+// Roofline: HBM-bound. Algorithmic bytes per query = n_rows * dim * 4. Per row a
+// warp issues V LDG.128, 4V FFMA, 5 SHFL+FADD and one compare against a warp-uniform threshold
+// (~30 instructions per 1536 B), far below issue limits; what matters is bytes in flight:
+// R rows x V x 512 B per warp x 8 warps x 2 CTAs/SM ~= 96 KB/SM.
+//
+// Determinism: each row's dot product uses one fixed FMA chain per lane and one fixed xor-shuffle
+// tree, independent of which warp/CTA/GPU scans the row. Duplicate rows therefore tie bit-exactly
+// and the id tie-break is well defined; a row-sharded multi-GPU search returns bit-identical
+// results to a single-GPU one.
+#pragma once
+#include "topk.cuh"
+
+namespace csgpu {
+
+constexpr int SCAN_WARPS = 8;
+constexpr int SCAN_THREADS = SCAN_WARPS * 32;
+
+struct ScanArgs {
+    const float4 *rows;      // [n_rows, dim4]
+    const uint32_t *ids;     // [n_rows]
+    uint64_t n_rows;
+    uint32_t dim4;
+    const float *q;          // [dim4*4] device, raw (normalised in the prologue)
+    uint32_t k, kpad;
+    const uint64_t *bitmap;  // id-indexed allow bitmap or nullptr
+    uint64_t n_bits;
+    const uint32_t *zero_ids;  // ascending ids of zero-norm rows (distance 0.0), or nullptr
+    uint32_t n_zero;
+    uint64_t *cand;          // [gridDim.x, k] per-CTA results
+    unsigned *ticket;        // last-CTA-done counter (self-resetting)
+    uint64_t *out_keys;      // [k] final keys, ascending, KEY_EMPTY padded
+};
+
+__device__ __forceinline__ float4 ldg_stream(const float4 *p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ bool id_allowed(const uint64_t *bitmap, uint64_t n_bits, uint32_t id)
+{
+    if (bitmap == nullptr) return true;
+    if ((uint64_t)id >= n_bits) return false;
+    return (bitmap[id >> 6] >> (id & 63)) & 1ull;
+}
+
+__device__ __forceinline__ float warp_sum_tree(float v)
+{
+    v += __shfl_xor_sync(FULL, v, 16);
+    v += __shfl_xor_sync(FULL, v, 8);
+    v += __shfl_xor_sync(FULL, v, 4);
+    v += __shfl_xor_sync(FULL, v, 2);
+    v += __shfl_xor_sync(FULL, v, 1);
+    return v;
+}
+
+// Offer each lane's key (KEY_EMPTY = nothing) to the warp's selector.
+template <class Sel>
+__device__ __forceinline__ void offer_lane_keys(Sel &sel, uint64_t key, int lane)
+{
+    unsigned m = __ballot_sync(FULL, key < sel.thr);
+    while (m) {
+        int src = __ffs(m) - 1;
+        m &= m - 1;
+        uint64_t kk = shfl64(key, src);
+        if (kk < sel.thr) sel.insert(kk, lane);
+    }
+}
+
+// Warp selectors -> the CTA's top-k, ascending, into dst[0..k) (global or shared).
+// smem: BIG: [2][SCAN_WARPS][kpad] (region A then B); !BIG: [SCAN_WARPS*32].
+template <bool BIG, class Sel>
+__device__ __forceinline__ void cta_reduce(Sel &sel, uint64_t *smem, uint32_t k, uint32_t kpad,
+                                           uint64_t *dst, int warp, int lane)
+{
+    sel.flush(lane);
+    uint32_t n;
+    if constexpr (BIG) {
+        uint64_t *mine = smem + (size_t)warp * kpad;
+        if (sel.cur != mine)
+            for (uint32_t j = lane; j < kpad; j += 32) mine[j] = sel.cur[j];
+        n = SCAN_WARPS * kpad;
+    } else {
+        smem[warp * 32 + lane] = sel.v;
+        n = SCAN_WARPS * 32;
+    }
+    cta_sort(smem, n);
+    for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) dst[j] = smem[j];
+    __syncthreads();
+}
+
+template <bool BIG>
+struct SelOf { using type = WarpSel32; };
+template <>
+struct SelOf<true> { using type = WarpSelBig; };
+
+// V = float4 per lane (ceil(dim4/32)); EXACT: dim4 == 32*V; R = rows in flight per warp.
+template <int V, bool EXACT, int R, bool BIG>
+__global__ void __launch_bounds__(SCAN_THREADS, BIG ? 1 : 2) scan_topk_kernel(const ScanArgs a)
+{
+    extern __shared__ __align__(16) uint64_t smem[];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    using Sel = typename SelOf<BIG>::type;
+    Sel sel;
+    if constexpr (BIG) {
+        sel.init(smem + (size_t)warp * a.kpad, smem + (size_t)(SCAN_WARPS + warp) * a.kpad, a.k, a.kpad, lane);
+    } else {
+        sel.init(a.k);
+    }
+
+    // ---- query -> registers, scaled to unit length -------------------------------------
+    float4 qv[V];
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const uint32_t c = lane + 32 * j;
+        if (EXACT || c < a.dim4) qv[j] = reinterpret_cast<const float4 *>(a.q)[c];
+        else qv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ss = fmaf(qv[j].x, qv[j].x, ss); ss = fmaf(qv[j].y, qv[j].y, ss);
+        ss = fmaf(qv[j].z, qv[j].z, ss); ss = fmaf(qv[j].w, qv[j].w, ss);
+    }
+    ss = warp_sum_tree(ss);
+    const bool qzero = !(ss > 0.f);  // zero-norm query: every distance is 0.0 (arroy pn*qn == 0)
+    const float qinv = qzero ? 0.f : 1.0f / sqrtf(ss);
+#pragma unroll
+    for (int j = 0; j < V; ++j) { qv[j].x *= qinv; qv[j].y *= qinv; qv[j].z *= qinv; qv[j].w *= qinv; }
+
+    // ---- stream the rows ---------------------------------------------------------------
+    const uint64_t n = a.n_rows;
+    const uint64_t gw = (uint64_t)blockIdx.x * SCAN_WARPS + warp;
+    const uint64_t stride = (uint64_t)gridDim.x * SCAN_WARPS * R;
+    for (uint64_t base = gw * R; base < n; base += stride) {
+        float4 x[R][V];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint64_t row = base + r;
+            const float4 *p = a.rows + row * a.dim4 + lane;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                if (row < n && (EXACT || lane + 32 * j < a.dim4)) x[r][j] = ldg_stream(p + 32 * j);
+                else x[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                acc = fmaf(x[r][j].x, qv[j].x, acc); acc = fmaf(x[r][j].y, qv[j].y, acc);
+                acc = fmaf(x[r][j].z, qv[j].z, acc); acc = fmaf(x[r][j].w, qv[j].w, acc);
+            }
+            acc = warp_sum_tree(acc);
+            const float dist = qzero ? 0.f : fmaf(-0.5f, acc, 0.5f);  // (1 - cos)/2
+            const uint64_t row = base + r;
+            if (row < n && okey(dist) <= (uint32_t)(sel.thr >> 32)) {  // warp-uniform, rare
+                const uint32_t id = a.ids[row];
+                const uint64_t key = make_key(dist, id);
+                if (key < sel.thr && id_allowed(a.bitmap, a.n_bits, id)) sel.insert(key, lane);
+            }
+        }
+    }
+
+    // ---- CTA top-k -> cand[blockIdx.x] ---------------------------------------------------
+    cta_reduce<BIG>(sel, smem, a.k, a.kpad, a.cand + (size_t)blockIdx.x * a.k, warp, lane);
+
+    // ---- last CTA merges all CTAs' results (threadfence-reduction pattern) ---------------
+    __threadfence();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(a.ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+
+    if constexpr (BIG) {
+        sel.init(smem + (size_t)warp * a.kpad, smem + (size_t)(SCAN_WARPS + warp) * a.kpad, a.k, a.kpad, lane);
+    } else {
+        sel.init(a.k);
+    }
+    const uint64_t total = (uint64_t)gridDim.x * a.k;
+    const volatile uint64_t *cand = a.cand;
+    for (uint64_t b = (uint64_t)warp * 32; b < total; b += SCAN_WARPS * 32) {
+        uint64_t key = (b + lane < total) ? cand[b + lane] : KEY_EMPTY;
+        offer_lane_keys(sel, key, lane);
+    }
+    if (warp == 0 && a.n_zero) {  // zero-norm rows: distance 0.0, ascending id; first k allowed suffice
+        uint32_t found = 0;
+        for (uint32_t b = 0; b < a.n_zero && found < a.k; b += 32) {
+            uint64_t key = KEY_EMPTY;
+            if (b + lane < a.n_zero) {
+                uint32_t id = a.zero_ids[b + lane];
+                if (id_allowed(a.bitmap, a.n_bits, id)) key = make_key(0.f, id);
+            }
+            found += __popc(__ballot_sync(FULL, key != KEY_EMPTY));
+            offer_lane_keys(sel, key, lane);
+        }
+    }
+    cta_reduce<BIG>(sel, smem, a.k, a.kpad, a.out_keys, warp, lane);
+    if (threadIdx.x == 0) *a.ticket = 0;
+}
+
+// Generic k-way merge: n_lists x k keys -> top-k. One CTA. Used for the cross-GPU merge.
+template <bool BIG>
+__global__ void __launch_bounds__(SCAN_THREADS, 1)
+merge_keys_kernel(const uint64_t *__restrict__ keys, uint64_t total, uint32_t k, uint32_t kpad,
+                  uint64_t *__restrict__ out)
+{
+    extern __shared__ __align__(16) uint64_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    using Sel = typename SelOf<BIG>::type;
+    Sel sel;
+    if constexpr (BIG) {
+        sel.init(smem + (size_t)warp * kpad, smem + (size_t)(SCAN_WARPS + warp) * kpad, k, kpad, lane);
+    } else {
+        sel.init(k);
+    }
+    for (uint64_t b = (uint64_t)warp * 32; b < total; b += SCAN_WARPS * 32) {
+        uint64_t key = (b + lane < total) ? keys[b + lane] : KEY_EMPTY;
+        offer_lane_keys(sel, key, lane);
+    }
+    cta_reduce<BIG>(sel, smem, k, kpad, out, warp, lane);
+}
+
+}  // namespace csgpu

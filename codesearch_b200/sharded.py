@@ -1,0 +1,76 @@
+"""Rank-per-GPU sharded search: one process per GPU under torch.distributed (NCCL over NVLink).
+
+Each rank owns a contiguous row shard in its own single-device csgpu index. A query is scanned by
+every rank (local fused scan + top-k, one kernel), the k sortable keys per rank are exchanged with
+ONE all-gather (k * 8 B per rank — latency-bound), and every rank runs the same k-way merge kernel,
+so all ranks end with the identical global top-k, ties broken by chunk id.
+
+torch is plumbing here (device buffers, the current stream, the process group); the scan and the
+merge are csgpu kernels reached through the C ABI's device entry points.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .store import VectorStore
+
+
+class ShardedSearcher:
+    def __init__(self, store: VectorStore, k_max: int = _lib.MAX_K, group=None):
+        self.store = store
+        self.lib = _lib.load()
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        d = store.dimensions
+        self.d_pad = (d + 3) // 4 * 4
+        self.q_pin = torch.zeros(self.d_pad, dtype=torch.float32).pin_memory()
+        self.q_dev = torch.zeros(self.d_pad, dtype=torch.float32, device=self.dev)
+        self.local = torch.empty(k_max, dtype=torch.int64, device=self.dev)
+        self.gathered = torch.empty(self.world * k_max, dtype=torch.int64, device=self.dev)
+        self.out = torch.empty(k_max, dtype=torch.int64, device=self.dev)
+        self.out_pin = torch.empty(k_max, dtype=torch.int64).pin_memory()
+
+    # -- device-resident: q_dev is a [d_pad] float32 CUDA tensor; returns a view of k keys (int64 bits)
+    def search_keys_device(self, q_dev: torch.Tensor, k: int) -> torch.Tensor:
+        stream = torch.cuda.current_stream().cuda_stream
+        local = self.local[:k]
+        _lib.check(self.lib.csgpu_search_keys_device(self.store.handle, q_dev.data_ptr(), k, local.data_ptr(), stream))
+        if self.world == 1:
+            return local
+        gathered = self.gathered[: self.world * k]
+        dist.all_gather_into_tensor(gathered, local, group=self.group)
+        out = self.out[:k]
+        _lib.check(self.lib.csgpu_merge_keys_device(self.store.handle, gathered.data_ptr(), self.world, k,
+                                                    out.data_ptr(), stream))
+        return out
+
+    # -- end to end: host query in, host (ids, distances) out
+    def search(self, query_embedding, k: int):
+        q = np.ascontiguousarray(query_embedding, dtype=np.float32).reshape(-1)
+        if q.size != self.store.dimensions:
+            raise _lib.CsgpuError(_lib.ERR_DIM, f"Query embedding dimension mismatch: expected "
+                                                f"{self.store.dimensions}, got {q.size}")
+        self.q_pin[: q.size].copy_(torch.from_numpy(q))
+        self.q_dev.copy_(self.q_pin, non_blocking=True)
+        keys = self.search_keys_device(self.q_dev, k)
+        self.out_pin[:k].copy_(keys, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return decode_keys(self.out_pin[:k].numpy())
+
+
+def decode_keys(keys_i64: np.ndarray):
+    lib = _lib.load()
+    keys = np.ascontiguousarray(keys_i64).view(np.uint64)
+    k = keys.size
+    ids = np.empty(k, np.uint32)
+    dd = np.empty(k, np.float32)
+    n = ctypes.c_uint32()
+    lib.csgpu_decode_keys(keys.ctypes.data_as(_lib._u64p), k, ids.ctypes.data_as(_lib._u32p),
+                          dd.ctypes.data_as(_lib._f32p), ctypes.byref(n))
+    return ids[: n.value], dd[: n.value]

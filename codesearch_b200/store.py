@@ -1,0 +1,288 @@
+"""Host-side mirror of the reference's `VectorStore` (src/vectordb/store.rs) over libcsgpu.so.
+
+Same method names, argument meaning and error text as the Rust struct so the parity tests read
+like the reference's own tests (store.rs:826-1029):
+
+    VectorStore.new(db_path, dimensions)            store.rs:110
+    insert_chunks / insert_chunks_with_ids           store.rs:334,618
+    delete_chunks(ids) -> count                      store.rs:548
+    build_index()                                    store.rs:386
+    search(query_embedding, limit) -> [SearchResult] store.rs:431   <- the CUDA path
+    search_filtered / search_batch                   new, additive
+    get_chunk / get_chunk_as_result / get_chunks_by_file / stats / clear / is_indexed
+
+Chunk metadata (the LMDB "chunks" table, store.rs:97) stays on the host, here as a dict keyed by
+chunk id; only the arroy block (store.rs:446-459) runs on the GPU. This file contains no scoring
+arithmetic and no fallback: every search is one call into the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import CsgpuError
+
+
+@dataclass
+class Chunk:
+    """chunker::Chunk (src/chunker/mod.rs:22-63), the fields the store persists."""
+    content: str
+    start_line: int
+    end_line: int
+    kind: str
+    path: str
+    signature: str | None = None
+    docstring: str | None = None
+    context: str | None = None
+    hash: str = ""
+    context_prev: str | None = None
+    context_next: str | None = None
+
+
+@dataclass
+class EmbeddedChunk:
+    """embed::EmbeddedChunk (src/embed/batch.rs:47-51)."""
+    chunk: Chunk
+    embedding: Sequence[float]
+
+
+@dataclass
+class SearchResult:
+    """store.rs:753-772."""
+    id: int
+    content: str
+    path: str
+    start_line: int
+    end_line: int
+    kind: str
+    signature: str | None
+    docstring: str | None
+    context: str | None
+    hash: str
+    distance: float
+    score: float
+    context_prev: str | None = None
+    context_next: str | None = None
+
+
+@dataclass
+class StoreStats:
+    """store.rs:784-792."""
+    total_chunks: int
+    total_files: int
+    indexed: bool
+    dimensions: int
+    max_chunk_id: int
+
+
+@dataclass
+class RowFilter:
+    """Allow-set over chunk ids for search_filtered (bit i set <=> chunk id i may be returned)."""
+    bitmap: np.ndarray  # uint64 words
+    n_bits: int
+
+    @staticmethod
+    def from_ids(ids: Iterable[int], n_bits: int) -> "RowFilter":
+        bm = np.zeros((n_bits + 63) // 64, dtype=np.uint64)
+        ids = np.asarray(list(ids) if not isinstance(ids, np.ndarray) else ids, dtype=np.uint64)
+        ids = ids[ids < n_bits]
+        np.bitwise_or.at(bm, (ids >> np.uint64(6)).astype(np.int64), np.uint64(1) << (ids & np.uint64(63)))
+        return RowFilter(bm, n_bits)
+
+    @staticmethod
+    def from_mask(mask: np.ndarray) -> "RowFilter":
+        mask = np.asarray(mask, dtype=bool)
+        n_bits = mask.size
+        padded = np.zeros(((n_bits + 63) // 64) * 64, dtype=np.uint8)
+        padded[:n_bits] = mask
+        bm = np.packbits(padded.reshape(-1, 8), axis=1, bitorder="little").reshape(-1).view(np.uint64)
+        return RowFilter(np.ascontiguousarray(bm), n_bits)
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class VectorStore:
+    def __init__(self, dimensions: int, devices: Sequence[int] | None = None, db_path=None):
+        self._lib = _lib.load()
+        self.dimensions = int(dimensions)
+        self.db_path = db_path
+        self.next_id = 0
+        self._chunks: dict[int, Chunk] = {}
+        self._h = ctypes.c_void_p()
+        devs = None
+        n = 1
+        if devices is not None:
+            n = len(devices)
+            devs = (ctypes.c_int32 * n)(*devices)
+        _lib.check(self._lib.csgpu_create(ctypes.byref(self._h), self.dimensions, _lib.DTYPE_F32, devs, n))
+
+    # -- lifecycle ---------------------------------------------------------------------------
+    @classmethod
+    def new(cls, db_path, dimensions: int, devices: Sequence[int] | None = None) -> "VectorStore":
+        return cls(dimensions, devices=devices, db_path=db_path)
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.csgpu_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def is_indexed(self) -> bool:
+        return bool(self._stats().built)
+
+    # -- write side --------------------------------------------------------------------------
+    def insert_chunks_with_ids(self, chunks: Sequence[EmbeddedChunk]) -> list[int]:
+        if not chunks:
+            return []
+        for c in chunks:
+            if len(c.embedding) != self.dimensions:
+                raise ValueError(
+                    f"Embedding dimension mismatch: expected {self.dimensions}, got {len(c.embedding)}")
+        start = self.next_id
+        ids = np.arange(start, start + len(chunks), dtype=np.uint32)
+        rows = _f32([c.embedding for c in chunks])
+        self.append_rows(rows, ids)
+        for i, c in zip(ids, chunks):
+            self._chunks[int(i)] = c.chunk
+        self.next_id = start + len(chunks)
+        return [int(i) for i in ids]
+
+    def insert_chunks(self, chunks: Sequence[EmbeddedChunk]) -> int:
+        return len(self.insert_chunks_with_ids(chunks))
+
+    def append_rows(self, rows: np.ndarray, ids: np.ndarray) -> None:
+        """Bulk path: raw [n, dim] embeddings with explicit chunk ids (no metadata)."""
+        rows = _f32(rows)
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        if rows.ndim != 2 or rows.shape[1] != self.dimensions:
+            raise ValueError(
+                f"Embedding dimension mismatch: expected {self.dimensions}, got {rows.shape[-1]}")
+        assert ids.shape == (rows.shape[0],)
+        _lib.check(self._lib.csgpu_append(self._h, rows.ctypes.data_as(_lib._f32p),
+                                          ids.ctypes.data_as(_lib._u32p), rows.shape[0]))
+        if ids.size:
+            self.next_id = max(self.next_id, int(ids.max()) + 1)
+
+    def append_synthetic(self, seed: int, first_row: int, n: int, id_base: int = 0) -> None:
+        _lib.check(self._lib.csgpu_append_synthetic(self._h, seed, first_row, n, id_base))
+
+    def reserve(self, total_rows: int) -> None:
+        _lib.check(self._lib.csgpu_reserve(self._h, total_rows))
+
+    def delete_chunks(self, chunk_ids: Sequence[int]) -> int:
+        if len(chunk_ids) == 0:
+            return 0
+        ids = np.ascontiguousarray(chunk_ids, dtype=np.uint32)
+        removed = ctypes.c_uint64(0)
+        _lib.check(self._lib.csgpu_remove(self._h, ids.ctypes.data_as(_lib._u32p), ids.size, ctypes.byref(removed)))
+        for i in ids:
+            self._chunks.pop(int(i), None)
+        return int(removed.value)
+
+    def build_index(self) -> None:
+        _lib.check(self._lib.csgpu_build(self._h))
+
+    def clear(self) -> None:
+        _lib.check(self._lib.csgpu_clear(self._h))
+        self._chunks.clear()
+        self.next_id = 0
+
+    # -- search ------------------------------------------------------------------------------
+    def search_ids(self, query_embedding, limit: int, filter: RowFilter | None = None):
+        """The raw hot path: (ids[u32], distance[f32]) ascending (distance, id)."""
+        q = _f32(query_embedding).reshape(-1)
+        k = int(limit)
+        oi = np.empty(max(k, 1), dtype=np.uint32)
+        od = np.empty(max(k, 1), dtype=np.float32)
+        on = ctypes.c_uint32(0)
+        if filter is None:
+            rc = self._lib.csgpu_search(self._h, q.ctypes.data_as(_lib._f32p), q.size, k,
+                                        oi.ctypes.data_as(_lib._u32p), od.ctypes.data_as(_lib._f32p), ctypes.byref(on))
+        else:
+            bm = np.ascontiguousarray(filter.bitmap, dtype=np.uint64)
+            rc = self._lib.csgpu_search_filtered(self._h, q.ctypes.data_as(_lib._f32p), q.size, k,
+                                                 bm.ctypes.data_as(_lib._u64p), filter.n_bits,
+                                                 oi.ctypes.data_as(_lib._u32p), od.ctypes.data_as(_lib._f32p),
+                                                 ctypes.byref(on))
+        _lib.check(rc)
+        return oi[: on.value].copy(), od[: on.value].copy()
+
+    def search_batch_ids(self, queries, limit: int):
+        q = _f32(queries)
+        b, d = q.shape
+        k = int(limit)
+        oi = np.zeros((b, max(k, 1)), dtype=np.uint32)
+        od = np.zeros((b, max(k, 1)), dtype=np.float32)
+        on = np.zeros(b, dtype=np.uint32)
+        _lib.check(self._lib.csgpu_search_batch(self._h, q.ctypes.data_as(_lib._f32p), d, b, k,
+                                                oi.ctypes.data_as(_lib._u32p), od.ctypes.data_as(_lib._f32p),
+                                                on.ctypes.data_as(_lib._u32p)))
+        return oi, od, on
+
+    def _join(self, ids, dist) -> list[SearchResult]:
+        out = []
+        for i, d in zip(ids, dist):
+            c = self._chunks.get(int(i))
+            if c is None:  # store.rs:465 silently drops ids without metadata
+                continue
+            d = np.float32(d)
+            out.append(SearchResult(int(i), c.content, c.path, c.start_line, c.end_line, c.kind, c.signature,
+                                    c.docstring, c.context, c.hash, float(d), float(np.float32(1.0) - d),
+                                    c.context_prev, c.context_next))
+        return out
+
+    def search(self, query_embedding, limit: int) -> list[SearchResult]:
+        return self._join(*self.search_ids(query_embedding, limit))
+
+    def search_filtered(self, query_embedding, limit: int, filter: RowFilter) -> list[SearchResult]:
+        return self._join(*self.search_ids(query_embedding, limit, filter))
+
+    def search_batch(self, queries, limit: int) -> list[list[SearchResult]]:
+        oi, od, on = self.search_batch_ids(queries, limit)
+        return [self._join(oi[j, : on[j]], od[j, : on[j]]) for j in range(len(on))]
+
+    # -- metadata / stats --------------------------------------------------------------------
+    def get_chunk(self, id: int) -> Chunk | None:
+        return self._chunks.get(int(id))
+
+    def get_chunk_as_result(self, id: int) -> SearchResult | None:
+        c = self._chunks.get(int(id))
+        if c is None:
+            return None
+        return SearchResult(int(id), c.content, c.path, c.start_line, c.end_line, c.kind, c.signature, c.docstring,
+                            c.context, c.hash, 0.0, 0.0, c.context_prev, c.context_next)
+
+    def get_chunks_by_file(self) -> dict[str, list[int]]:
+        out: dict[str, list[int]] = {}
+        for i in sorted(self._chunks):
+            out.setdefault(self._chunks[i].path, []).append(i)
+        return out
+
+    def _stats(self) -> _lib.Stats:
+        s = _lib.Stats()
+        _lib.check(self._lib.csgpu_stats(self._h, ctypes.byref(s)))
+        return s
+
+    def device_stats(self) -> _lib.Stats:
+        return self._stats()
+
+    def stats(self) -> StoreStats:
+        s = self._stats()
+        return StoreStats(total_chunks=len(self._chunks), total_files=len({c.path for c in self._chunks.values()}),
+                          indexed=bool(s.built), dimensions=self.dimensions,
+                          max_chunk_id=max(self._chunks) if self._chunks else 0)
+
+    @property
+    def handle(self) -> ctypes.c_void_p:
+        return self._h

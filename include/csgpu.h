@@ -1,0 +1,163 @@
+/*
+ * csgpu.h — C ABI of the B200-native vector-retrieval hot path for codesearch.
+ *
+ * This is the drop-in boundary. The reference has no FFI today:
+ * `VectorStore` (src/vectordb/store.rs:94-102) calls arroy directly and build.rs
+ * compiles nothing (build.rs:1-48). A maintainer replaces the arroy block
+ *     src/vectordb/store.rs:446-459   (read_txn / Reader::open / nns / search_k / by_vector)
+ * with one csgpu_search*() call, feeds csgpu_append/csgpu_remove/csgpu_build from
+ *     src/vectordb/store.rs:618-686   (insert_chunks_with_ids: writer.add_item(id, &embedding))
+ *     src/vectordb/store.rs:548-610   (delete_chunks: writer.del_item(id))
+ *     src/vectordb/store.rs:386-430   (build_index)
+ *     src/vectordb/store.rs:690-706   (clear)
+ * and keeps the metadata join (store.rs:464-483) and score = 1 - distance
+ * (store.rs:478) on the host. INTEGRATION.md shows the Rust binding.
+ *
+ * Semantics common to every search entry point
+ *   - out_dist[i] = (1 - cos(row, q)) / 2 in [0, 1]   (arroy 0.5.0 Cosine distance)
+ *   - results ascending (distance, chunk id); ties broken by the smaller id
+ *   - *out_n = min(k, live rows passing the filter)
+ *   - the query is normalised inside; a zero-norm query or row has distance 0.0
+ *   - rows/queries containing NaN/Inf: queries are rejected (CSGPU_ERR_ARG);
+ *     such rows are dropped at csgpu_build and counted in csgpu_stats_t.nonfinite_rows
+ *   - caller owns every out_* buffer; the library never hands out device memory
+ *     through the host-pointer entry points
+ *
+ * Threading
+ *   csgpu_search* on a built index are re-entrant from any number of host threads
+ *   (`&self` in the reference; rayon par_iter at src/search/mod.rs:508-511).
+ *   csgpu_append/remove/build/clear/destroy need exclusive access (`&mut self`).
+ *
+ * Errors: 0 = ok, otherwise a CSGPU_ERR_* code; text via csgpu_last_error()
+ * (thread-local). Never aborts. There is NO CPU fallback: no usable device =>
+ * csgpu_create fails with CSGPU_ERR_CUDA.
+ */
+#ifndef CSGPU_H
+#define CSGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSGPU_ABI_VERSION 1
+
+enum {
+    CSGPU_OK            = 0,
+    CSGPU_ERR_DIM       = 1, /* "Query embedding dimension mismatch: expected {}, got {}"  store.rs:432-438 */
+    CSGPU_ERR_NOT_BUILT = 2, /* "Index not built. Call build_index() after inserting chunks."  store.rs:440-444 */
+    CSGPU_ERR_CUDA      = 3,
+    CSGPU_ERR_NCCL      = 4,
+    CSGPU_ERR_OOM       = 5,
+    CSGPU_ERR_ARG       = 6
+};
+
+enum { CSGPU_DTYPE_F32 = 0, CSGPU_DTYPE_BF16 = 1 };
+
+#define CSGPU_MAX_K   1024u
+#define CSGPU_MAX_DIM 4096u
+
+typedef struct csgpu_index csgpu_index;
+
+typedef struct csgpu_stats_t {
+    uint64_t live_rows;        /* rows searchable after the last build (all devices)           */
+    uint64_t pending_rows;     /* appended since the last build                                */
+    uint64_t tombstones;       /* removed since the last build                                 */
+    uint64_t zero_norm_rows;   /* rows with |v| = 0: kept, distance 0.0 (arroy pn*qn == 0)     */
+    uint64_t nonfinite_rows;   /* rows with NaN/Inf: dropped at build                          */
+    uint64_t bytes_on_device;  /* total HBM held by the index (all devices)                    */
+    uint32_t dim;
+    uint32_t dtype;
+    uint32_t n_devices;
+    uint32_t built;            /* mirrors VectorStore::is_indexed()  store.rs:747              */
+    float    last_search_us;   /* device time of the most recent search (CUDA events)          */
+    uint32_t abi_version;
+    uint64_t rows_per_device[8];
+} csgpu_stats_t;
+
+/* ---- lifecycle (VectorStore::new / open_readonly  store.rs:110-176,183-250) ------------ */
+
+/* devices == NULL => device 0. n_devices in {1,2,4,8}: rows are sharded row-wise. */
+int  csgpu_create(csgpu_index **out, uint32_t dim, uint32_t dtype,
+                  const int32_t *devices, uint32_t n_devices);
+void csgpu_destroy(csgpu_index *ix);
+
+/* rows: [n, dim] row-major host floats; ids: [n] chunk ids. Copies; marks the index dirty
+ * (store.rs:674,682: add_item + indexed=false). Appending an id that is live replaces it
+ * at the next build (LMDB put semantics). */
+int  csgpu_append(csgpu_index *ix, const float *rows, const uint32_t *ids, uint64_t n);
+
+/* Tombstones ids; marks the index dirty (store.rs:595,605-607). n_removed may be NULL. */
+int  csgpu_remove(csgpu_index *ix, const uint32_t *ids, uint64_t n, uint64_t *n_removed);
+
+/* Pre-sizes device storage for total_rows rows (avoids grow-and-copy; needed when a shard is
+ * more than half of HBM). Optional. */
+int  csgpu_reserve(csgpu_index *ix, uint64_t total_rows);
+
+/* Normalises new rows to unit length, applies tombstones/replacements, rebalances shards;
+ * index becomes searchable (store.rs:422-430: indexed=true). */
+int  csgpu_build(csgpu_index *ix);
+
+/* Drops every row; index is empty and NOT built (store.rs:690-706). */
+int  csgpu_clear(csgpu_index *ix);
+
+/* ---- search (VectorStore::search  store.rs:431-486, arroy block :446-459) -------------- */
+
+int  csgpu_search(const csgpu_index *ix, const float *q, uint32_t q_len, uint32_t k,
+                  uint32_t *out_ids /*[k]*/, float *out_dist /*[k]*/, uint32_t *out_n);
+
+/* b queries [b, dim]; outputs [b, k] (row j holds out_n[j] valid entries). Serves the
+ * <= 9 query variants of src/search/mod.rs:508-511 in one pass over the corpus. */
+int  csgpu_search_batch(const csgpu_index *ix, const float *q, uint32_t q_len, uint32_t b, uint32_t k,
+                        uint32_t *out_ids, float *out_dist, uint32_t *out_n /*[b]*/);
+
+/* Exact top-k over rows whose chunk id has its bit set (bit i of id_bitmap[i/64]); ids >=
+ * n_bits are excluded. New capability: the reference only post-filters on the host
+ * (src/search/mod.rs:727-737, src/server/mod.rs:553-559). */
+int  csgpu_search_filtered(const csgpu_index *ix, const float *q, uint32_t q_len, uint32_t k,
+                           const uint64_t *id_bitmap, uint64_t n_bits,
+                           uint32_t *out_ids, float *out_dist, uint32_t *out_n);
+
+/* ---- device-resident entry points (single-device index; for hosts that already hold the
+ *      query on the GPU, and for rank-per-GPU sharding under torch.distributed) -----------
+ * All pointers are DEVICE pointers on the index's device; `stream` is a cudaStream_t (NULL
+ * = default stream). Calls only enqueue work; nothing is synchronised.
+ *
+ * A "key" is the sortable 64-bit form of one result:  (okey(distance) << 32) | chunk id,
+ * okey = order-preserving map of the f32 bits, so ascending u64 == ascending (distance, id).
+ * 0xFFFFFFFFFFFFFFFF is the empty slot. csgpu_decode_keys() converts on the host. */
+
+/* One query -> this index's local top-k keys, sorted ascending, padded with empty slots. */
+int  csgpu_search_keys_device(const csgpu_index *ix, const float *q_dev, uint32_t k,
+                              uint64_t *out_keys_dev /*[k]*/, void *stream);
+
+/* k-way merge of n_lists lists of k keys (e.g. the all-gathered per-rank results) into the
+ * global top-k, ties by chunk id. keys_dev: [n_lists, k]. */
+int  csgpu_merge_keys_device(const csgpu_index *ix, const uint64_t *keys_dev, uint32_t n_lists,
+                             uint32_t k, uint64_t *out_keys_dev /*[k]*/, void *stream);
+
+/* Host-side: keys -> (ids, distances); returns the number of non-empty slots in *out_n. */
+void csgpu_decode_keys(const uint64_t *keys, uint32_t k, uint32_t *out_ids, float *out_dist,
+                       uint32_t *out_n);
+
+/* ---- synthetic corpus (bench/tests): rows generated ON the device, never on the host --- */
+/* Appends rows [first_row, first_row+n) of the counter-based generator (Philox4x32-10,
+ * spec in codesearch_b200/csrc/synth.cuh), chunk id = (uint32_t)global row index + id_base. */
+int  csgpu_append_synthetic(csgpu_index *ix, uint64_t seed, uint64_t first_row, uint64_t n,
+                            uint32_t id_base);
+/* The same generator into a host buffer via the device (for cross-checking the generators). */
+int  csgpu_synth_rows_host(const csgpu_index *ix, uint64_t seed, uint64_t first_row, uint64_t n,
+                           float *out_rows /*[n, dim] host*/);
+
+/* ---- introspection --------------------------------------------------------------------- */
+int  csgpu_stats(const csgpu_index *ix, csgpu_stats_t *out);
+/* Number of kernels this library has launched in this process (all indexes, all threads). */
+uint64_t csgpu_kernel_launches(void);
+const char *csgpu_last_error(void);   /* thread-local; valid until the next call on this thread */
+uint32_t csgpu_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSGPU_H */
