@@ -268,6 +268,12 @@ def main():
         peak, peak_src = peaks()
         kern_ms = statistics.mean(scan_ms)
         achieved = n * d * 4 / (kern_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                traffic = json.load(f).get(f"scan_topk_kernel<3,true,4,false>|rows={n}|dim={d}|k={k}", {}).get("traffic_bytes")
+        except Exception:  # noqa: BLE001
+            pass
         line = {
             "metric": "scanned_GBps_single_query_top10_fp32", "value": round(value, 2), "unit": "GB/s",
             "qps": round(1e3 / ms_per_step, 3),
@@ -279,7 +285,7 @@ def main():
                        "l2": "no flush needed: 15.36 GB scanned per GPU per step >> 126 MB L2",
                        "parallelism": f"row-shard x{world}" + ("" if world == 1 else " + NCCL all-gather of k keys + merge kernel")},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": None,
+                         "frac": round(achieved / peak, 4), "traffic": traffic,
                          "kernel": "scan_topk_kernel<3,true,4,false>", "kernel_ms": round(kern_ms, 4),
                          "algorithmic_bytes_per_launch": n * d * 4, "peak_source": peak_src,
                          "frac_of_nominal_8TBps": round(achieved / 8000.0, 4)},

@@ -40,12 +40,20 @@ struct ScanArgs {
     uint64_t *out_keys;      // [k] final keys, ascending, KEY_EMPTY padded
 };
 
+// LD selects the load flavour (tuned on B200, see profiles/): 0 = ld.global.nc.L1::no_allocate,
+// 1 = plain ld.global.nc (__ldg), 2 = ld.global.cs (streaming / evict-first).
+template <int LD>
 __device__ __forceinline__ float4 ldg_stream(const float4 *p)
 {
     float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                 : "l"(p));
+    if constexpr (LD == 0) {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    } else if constexpr (LD == 1) {
+        v = __ldg(p);
+    } else {
+        v = __ldcs(p);
+    }
     return v;
 }
 
@@ -107,8 +115,8 @@ template <>
 struct SelOf<true> { using type = WarpSelBig; };
 
 // V = float4 per lane (ceil(dim4/32)); EXACT: dim4 == 32*V; R = rows in flight per warp.
-template <int V, bool EXACT, int R, bool BIG>
-__global__ void __launch_bounds__(SCAN_THREADS, BIG ? 1 : 2) scan_topk_kernel(const ScanArgs a)
+template <int V, bool EXACT, int R, bool BIG, int OCC = (BIG ? 1 : 2), int LD = 0>
+__global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const ScanArgs a)
 {
     extern __shared__ __align__(16) uint64_t smem[];
     __shared__ bool is_last;
@@ -150,7 +158,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, BIG ? 1 : 2) scan_topk_kernel(co
             const float4 *p = a.rows + row * a.dim4 + lane;
 #pragma unroll
             for (int j = 0; j < V; ++j) {
-                if (row < n && (EXACT || lane + 32 * j < a.dim4)) x[r][j] = ldg_stream(p + 32 * j);
+                if (row < n && (EXACT || lane + 32 * j < a.dim4)) x[r][j] = ldg_stream<LD>(p + 32 * j);
                 else x[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }

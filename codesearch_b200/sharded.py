@@ -20,6 +20,23 @@ from . import _lib
 from .store import VectorStore
 
 
+def shard_range(n_total: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous row range [first, first+count) owned by `rank` (GPU g owns rows
+    [g*N/G, (g+1)*N/G))."""
+    first = n_total * rank // world
+    return first, n_total * (rank + 1) // world - first
+
+
+def allgather_keys(local: torch.Tensor, world: int, group=None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """The path's one exchange step: every rank contributes its k sorted keys (int64 bit pattern of
+    the u64 key), every rank receives [world, k]. Backend-agnostic (NCCL on GPUs, gloo in CPU tests)."""
+    k = local.numel()
+    if out is None:
+        out = torch.empty(world * k, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local, group=group)
+    return out
+
+
 class ShardedSearcher:
     def __init__(self, store: VectorStore, k_max: int = _lib.MAX_K, group=None):
         self.store = store
@@ -43,8 +60,7 @@ class ShardedSearcher:
         _lib.check(self.lib.csgpu_search_keys_device(self.store.handle, q_dev.data_ptr(), k, local.data_ptr(), stream))
         if self.world == 1:
             return local
-        gathered = self.gathered[: self.world * k]
-        dist.all_gather_into_tensor(gathered, local, group=self.group)
+        gathered = allgather_keys(local, self.world, self.group, self.gathered[: self.world * k])
         out = self.out[:k]
         _lib.check(self.lib.csgpu_merge_keys_device(self.store.handle, gathered.data_ptr(), self.world, k,
                                                     out.data_ptr(), stream))

