@@ -108,6 +108,8 @@ def cpu_baseline(args, kind_note=""):
     restated in C (oracle/oracle.c cs_cpu_baseline_search), all host threads, on a bounded sample."""
     from oracle import oracle as O
     O.build()
+    # torchrun exports OMP_NUM_THREADS=1; the baseline is defined as ALL host threads this process may use
+    O.set_threads(len(os.sched_getaffinity(0)))
     n = args.cpu_rows
     rows = O.synth_rows(SEED_CORPUS, 0, n, args.dim)
     qs = O.synth_rows(SEED_QUERY, 0, N_QUERIES, args.dim)

@@ -12,6 +12,7 @@
 
 #include "index.h"
 #include "scan.cuh"
+#include "scan_multi.cuh"
 #include "synth.cuh"
 
 namespace csgpu {
@@ -56,7 +57,7 @@ static int ctx_create(const csgpu_index *ix, Shard *sh, SearchCtx **out)
     CS_CUDA(cudaHostAlloc(&c->q_pin, (size_t)MAX_BATCH * ix->dim_pad * sizeof(float), cudaHostAllocDefault));
     c->cand_cap = (size_t)MAX_GRID * CSGPU_MAX_K;
     CS_CUDA(cudaMalloc(&c->cand, c->cand_cap * sizeof(uint64_t)));
-    CS_CUDA(cudaMalloc(&c->gather, (size_t)8 * CSGPU_MAX_K * sizeof(uint64_t)));
+    CS_CUDA(cudaMalloc(&c->gather, (size_t)8 * 2 * CSGPU_MAX_K * sizeof(uint64_t)));
     CS_CUDA(cudaMalloc(&c->ticket, 64 * sizeof(unsigned)));
     CS_CUDA(cudaMemset(c->ticket, 0, 64 * sizeof(unsigned)));
     CS_CUDA(cudaMalloc(&c->out_dev, (size_t)MAX_BATCH * CSGPU_MAX_K * sizeof(uint64_t)));
@@ -168,7 +169,7 @@ static int enqueue_scan(const csgpu_index *ix, const Shard *sh, SearchCtx *c, co
     return CSGPU_OK;
 }
 
-static int enqueue_merge(const uint64_t *keys_dev, uint64_t total, uint32_t k, uint64_t *out, cudaStream_t st)
+static int enqueue_merge(const uint64_t *keys_dev, uint32_t n_lists, uint32_t nq, uint32_t k, uint64_t *out, cudaStream_t st)
 {
     const bool big = k > 32;
     const uint32_t kpad = big ? pow2_at_least(k, 64) : 32;
@@ -179,13 +180,41 @@ static int enqueue_merge(const uint64_t *keys_dev, uint64_t total, uint32_t k, u
             e = cudaFuncSetAttribute(merge_keys_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return fail_cuda(e, "merge attr", __FILE__, __LINE__);
         }
-        merge_keys_kernel<true><<<1, SCAN_THREADS, smem, st>>>(keys_dev, total, k, kpad, out);
+        merge_keys_kernel<true><<<nq, SCAN_THREADS, smem, st>>>(keys_dev, n_lists, k, kpad, out);
     } else {
-        merge_keys_kernel<false><<<1, SCAN_THREADS, smem, st>>>(keys_dev, total, k, kpad, out);
+        merge_keys_kernel<false><<<nq, SCAN_THREADS, smem, st>>>(keys_dev, n_lists, k, kpad, out);
     }
     count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(e, "merge_keys_kernel launch", __FILE__, __LINE__);
+    return CSGPU_OK;
+}
+
+// Enqueue one multi-query (nq <= 8) scan of `sh`. q_dev: [nq, dim_pad]; out_keys: [nq, k].
+static int enqueue_scan_multi(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const float *q_dev, uint32_t nq,
+                              uint32_t k, bool with_zero_ids, uint64_t *out_keys, cudaStream_t st)
+{
+    MultiArgs a;
+    a.rows = reinterpret_cast<const float4 *>(sh->rows);
+    a.ids = sh->ids;
+    a.n_rows = sh->n_built;
+    a.dim4 = ix->dim4;
+    a.q = q_dev;
+    a.nq = nq;
+    a.k = k;
+    a.kpad = pow2_at_least(k, 32);
+    a.bitmap = nullptr;
+    a.n_bits = 0;
+    a.zero_ids = with_zero_ids ? ix->zero_ids_dev : nullptr;
+    a.n_zero = with_zero_ids ? (uint32_t)ix->zero_ids.size() : 0;
+    a.cand = c->cand;
+    a.ticket = c->ticket;
+    a.out_keys = out_keys;
+    const uint32_t R = (ix->dim4 / 32 <= 4) ? 4 : 2;
+    const uint64_t want = (sh->n_built + SCAN_WARPS * R - 1) / (SCAN_WARPS * R);
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sh->sm_count * multi_scan_ctas_per_sm(a.kpad), std::max<uint64_t>(want, 1));
+    cudaError_t e = launch_scan_multi(a, grid, st);
+    if (e != cudaSuccess) return fail_cuda(e, "scan_multi_topk_kernel launch", __FILE__, __LINE__);
     return CSGPU_OK;
 }
 
@@ -444,7 +473,7 @@ static int search_one(const csgpu_index *ix, const float *q, uint32_t k, const u
             }
             for (size_t g = 1; g < G; ++g) CS_CUDA(cudaStreamWaitEvent(c0->stream, ctx[g]->ev1, 0));
             CS_CUDA(cudaMemcpyAsync(gather, c0->out_dev, (size_t)k * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c0->stream));
-            int r = enqueue_merge(gather, (uint64_t)G * k, k, c0->out_pin, c0->stream);
+            int r = enqueue_merge(gather, (uint32_t)G, 1, k, c0->out_pin, c0->stream);
             if (r) return r;
         }
         {
@@ -455,6 +484,62 @@ static int search_one(const csgpu_index *ix, const float *q, uint32_t k, const u
             if (cudaEventElapsedTime(&ms, c0->ev0, c0->ev1) == cudaSuccess) ix->last_search_us.store(ms * 1000.f);
         }
         decode_keys(c0->out_pin, k, out_ids, out_dist, out_n);
+        return CSGPU_OK;
+    };
+    rc = body();
+    if (rc) for (size_t g = 0; g < G; ++g) { DeviceGuard dg(ix->shards[g]->device); cudaStreamSynchronize(ctx[g]->stream); }
+    release_all();
+    return rc;
+}
+
+// nq (2..8) queries in ONE pass over every shard; results [nq][k] land in ctx0->out_pin.
+static int search_multi(const csgpu_index *ix, const float *q, uint32_t nq, uint32_t k,
+                        uint32_t *out_ids, float *out_dist, uint32_t *out_n)
+{
+    const size_t G = ix->shards.size();
+    std::vector<SearchCtx *> ctx(G, nullptr);
+    int rc = CSGPU_OK;
+    auto release_all = [&]() { for (size_t g = 0; g < G; ++g) if (ctx[g]) ctx_release(ix->shards[g], ctx[g]); };
+    for (size_t g = 0; g < G && !rc; ++g) rc = ctx_acquire(ix, ix->shards[g], &ctx[g]);
+    if (rc) { release_all(); return rc; }
+    const size_t qbytes = (size_t)nq * ix->dim_pad * sizeof(float);
+    auto body = [&]() -> int {
+        for (size_t g = 0; g < G; ++g) {
+            Shard *sh = ix->shards[g];
+            SearchCtx *c = ctx[g];
+            DeviceGuard dg(sh->device);
+            memset(c->q_pin, 0, qbytes);
+            for (uint32_t j = 0; j < nq; ++j) memcpy(c->q_pin + (size_t)j * ix->dim_pad, q + (size_t)j * ix->dim, (size_t)ix->dim * sizeof(float));
+            CS_CUDA(cudaMemcpyAsync(c->q_dev, c->q_pin, qbytes, cudaMemcpyHostToDevice, c->stream));
+            if (g == 0) CS_CUDA(cudaEventRecord(c->ev0, c->stream));
+            uint64_t *dst = (G == 1) ? c->out_pin : c->out_dev;
+            int r = enqueue_scan_multi(ix, sh, c, c->q_dev, nq, k, g == 0, dst, c->stream);
+            if (r) return r;
+        }
+        SearchCtx *c0 = ctx[0];
+        if (G > 1) {
+            DeviceGuard dg(ix->shards[0]->device);
+            const size_t per = (size_t)nq * k;
+            for (size_t g = 1; g < G; ++g) {
+                DeviceGuard dg2(ix->shards[g]->device);
+                CS_CUDA(cudaMemcpyPeerAsync(c0->gather + g * per, ix->shards[0]->device, ctx[g]->out_dev, ix->shards[g]->device,
+                                            per * sizeof(uint64_t), ctx[g]->stream));
+                CS_CUDA(cudaEventRecord(ctx[g]->ev1, ctx[g]->stream));
+            }
+            for (size_t g = 1; g < G; ++g) CS_CUDA(cudaStreamWaitEvent(c0->stream, ctx[g]->ev1, 0));
+            CS_CUDA(cudaMemcpyAsync(c0->gather, c0->out_dev, per * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c0->stream));
+            int r = enqueue_merge(c0->gather, (uint32_t)G, nq, k, c0->out_pin, c0->stream);
+            if (r) return r;
+        }
+        {
+            DeviceGuard dg(ix->shards[0]->device);
+            CS_CUDA(cudaEventRecord(c0->ev1, c0->stream));
+            CS_CUDA(cudaStreamSynchronize(c0->stream));
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, c0->ev0, c0->ev1) == cudaSuccess) ix->last_search_us.store(ms * 1000.f);
+        }
+        for (uint32_t j = 0; j < nq; ++j)
+            decode_keys(c0->out_pin + (size_t)j * k, k, out_ids + (size_t)j * k, out_dist + (size_t)j * k, out_n ? out_n + j : nullptr);
         return CSGPU_OK;
     };
     rc = body();
@@ -739,11 +824,23 @@ int csgpu_search_batch(const csgpu_index *ix, const float *q, uint32_t q_len, ui
     if (rc) return rc;
     if (!all_finite(q, q_len * b)) return fail(CSGPU_ERR_ARG, "query contains NaN/Inf");
     if (k == 0 || b == 0) return CSGPU_OK;
-    // v1: one fused scan per query (multi-query single-pass kernel: see DESIGN.md roadmap)
-    for (uint32_t j = 0; j < b; ++j) {
-        rc = search_one(ix, q + (size_t)j * q_len, k, nullptr, 0, out_ids + (size_t)j * k, out_dist + (size_t)j * k,
-                        out_n ? out_n + j : nullptr);
-        if (rc) return rc;
+    // chunks of up to 8 queries share ONE pass over the corpus (scan_multi.cuh); leftovers of one query,
+    // k > 256 or dims that are not a multiple of 128 take the single-query kernel.
+    const uint32_t MQ = multi_scan_max_queries();
+    const bool multi_ok = multi_scan_supported(ix->dim4, k);
+    for (uint32_t j = 0; j < b;) {
+        const uint32_t nq = std::min(MQ, b - j);
+        if (multi_ok && nq >= 2) {
+            rc = search_multi(ix, q + (size_t)j * q_len, nq, k, out_ids + (size_t)j * k, out_dist + (size_t)j * k,
+                              out_n ? out_n + j : nullptr);
+            if (rc) return rc;
+            j += nq;
+        } else {
+            rc = search_one(ix, q + (size_t)j * q_len, k, nullptr, 0, out_ids + (size_t)j * k, out_dist + (size_t)j * k,
+                            out_n ? out_n + j : nullptr);
+            if (rc) return rc;
+            j += 1;
+        }
     }
     return CSGPU_OK;
 }
@@ -775,7 +872,7 @@ int csgpu_merge_keys_device(const csgpu_index *ix, const uint64_t *keys_dev, uin
     if (!keys_dev || !out_keys_dev) return fail(CSGPU_ERR_ARG, "null device pointer");
     if (k == 0 || k > CSGPU_MAX_K || n_lists == 0) return fail(CSGPU_ERR_ARG, "bad k / n_lists");
     DeviceGuard dg(ix->shards[0]->device);
-    return enqueue_merge(keys_dev, (uint64_t)n_lists * k, k, out_keys_dev, (cudaStream_t)stream);
+    return enqueue_merge(keys_dev, n_lists, 1, k, out_keys_dev, (cudaStream_t)stream);
 }
 
 void csgpu_decode_keys(const uint64_t *keys, uint32_t k, uint32_t *out_ids, float *out_dist, uint32_t *out_n)

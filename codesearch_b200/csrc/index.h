@@ -34,7 +34,7 @@ struct SearchCtx {
     float *q_dev = nullptr;         // [max_b * dim_pad]
     float *q_pin = nullptr;         // pinned staging for the query
     uint64_t *cand = nullptr;       // [grid_max * CSGPU_MAX_K]
-    uint64_t *gather = nullptr;     // [8 * CSGPU_MAX_K] per-shard results gathered for the cross-GPU merge
+    uint64_t *gather = nullptr;     // [8 * 2 * CSGPU_MAX_K] per-shard results gathered for the cross-GPU merge
     unsigned *ticket = nullptr;
     uint64_t *out_dev = nullptr;    // [max_b * CSGPU_MAX_K]
     uint64_t *out_pin = nullptr;    // pinned, device-mapped; kernels write results straight here
@@ -57,6 +57,13 @@ struct Shard {
     std::vector<SearchCtx *> free_ctx;
     std::vector<SearchCtx *> all_ctx;
 };
+
+// scan_multi.cu
+struct MultiArgs;
+bool multi_scan_supported(uint32_t dim4, uint32_t k);
+uint32_t multi_scan_max_queries();
+uint32_t multi_scan_ctas_per_sm(uint32_t kpad);
+cudaError_t launch_scan_multi(const MultiArgs &a, uint32_t grid, cudaStream_t st);
 
 }  // namespace csgpu
 

@@ -221,10 +221,11 @@ __global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const Scan
     if (threadIdx.x == 0) *a.ticket = 0;
 }
 
-// Generic k-way merge: n_lists x k keys -> top-k. One CTA. Used for the cross-GPU merge.
+// Generic k-way merge: for query b = blockIdx.x, n_lists lists of k keys -> top-k. One CTA per query.
+// keys layout [n_lists][nq = gridDim.x][k]; out [nq][k]. Used for the cross-GPU merge.
 template <bool BIG>
 __global__ void __launch_bounds__(SCAN_THREADS, 1)
-merge_keys_kernel(const uint64_t *__restrict__ keys, uint64_t total, uint32_t k, uint32_t kpad,
+merge_keys_kernel(const uint64_t *__restrict__ keys, uint32_t n_lists, uint32_t k, uint32_t kpad,
                   uint64_t *__restrict__ out)
 {
     extern __shared__ __align__(16) uint64_t smem[];
@@ -236,11 +237,18 @@ merge_keys_kernel(const uint64_t *__restrict__ keys, uint64_t total, uint32_t k,
     } else {
         sel.init(k);
     }
+    const uint64_t total = (uint64_t)n_lists * k;
+    const size_t list_stride = (size_t)gridDim.x * k, q_off = (size_t)blockIdx.x * k;
     for (uint64_t b = (uint64_t)warp * 32; b < total; b += SCAN_WARPS * 32) {
-        uint64_t key = (b + lane < total) ? keys[b + lane] : KEY_EMPTY;
+        uint64_t key = KEY_EMPTY;
+        if (b + lane < total) {
+            const uint64_t t = b + lane;
+            const uint64_t l = t / k, i = t - l * k;
+            key = keys[l * list_stride + q_off + i];
+        }
         offer_lane_keys(sel, key, lane);
     }
-    cta_reduce<BIG>(sel, smem, k, kpad, out, warp, lane);
+    cta_reduce<BIG>(sel, smem, k, kpad, out + q_off, warp, lane);
 }
 
 }  // namespace csgpu

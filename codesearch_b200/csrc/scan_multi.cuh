@@ -1,0 +1,296 @@
+// scan_multi.cuh — one pass over the corpus for MQ (4 or 8) queries at once.
+//
+// Serves the caller pattern at /root/reference/src/search/mod.rs:508-511 (<= 9 query-variant
+// embeddings searched with the same limit) and csgpu_search_batch in general: the corpus is read
+// from HBM ONCE per MQ queries, so queries/s scales ~MQ x while the scan stays HBM-bound
+// (fp32 machine balance ~11 flop/B vs MQ/2 flop/B here).
+//
+// Arithmetic is bit-identical to scan.cuh: every (row, query) dot product uses the same per-lane
+// FMA chain (j outer, xyzw inner) and the same pairing tree (offsets 16,8,4,2,1); the tree is just
+// evaluated "transposed" — at each level a lane keeps half of its values and ships the other half
+// to its partner — so R*MQ sums cost R*MQ-1 shuffles instead of 5*R*MQ, and every lane ends up
+// owning exactly one (row, query) result: lane l -> row l/MQ, query l%MQ (MQ=8, R=4).
+//
+// Selection: per warp, per query, a sorted list of kpad keys in shared memory + a 32-entry pending
+// buffer (also smem); merged in registers (E = kpad/32 keys per lane, in place). k <= 256.
+#pragma once
+#include "scan.cuh"
+
+namespace csgpu {
+
+struct MultiArgs {
+    const float4 *rows;
+    const uint32_t *ids;
+    uint64_t n_rows;
+    uint32_t dim4;
+    const float *q;        // [nq, dim4*4] device, raw
+    uint32_t nq;           // active queries (<= MQ)
+    uint32_t k, kpad;
+    const uint64_t *bitmap;
+    uint64_t n_bits;
+    const uint32_t *zero_ids;
+    uint32_t n_zero;
+    uint64_t *cand;        // [MQ][gridDim.x][k]
+    unsigned *ticket;
+    uint64_t *out_keys;    // [nq][k]
+};
+
+template <int NV, int O>
+__device__ __forceinline__ void butterfly_level(float (&v)[32], int lane)
+{
+    if constexpr (NV > 1) {
+        constexpr int H = NV / 2;
+        const bool up = (lane & O) != 0;
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            const float send = up ? v[i] : v[i + H];
+            const float keep = up ? v[i + H] : v[i];
+            v[i] = keep + __shfl_xor_sync(FULL, send, O);
+        }
+    } else {
+        v[0] += __shfl_xor_sync(FULL, v[0], O);
+    }
+}
+
+// Per-warp, per-query selection state in shared memory.
+template <int E>
+struct MultiSel {
+    static constexpr uint32_t KPAD = 32u * E;
+    uint64_t *list;    // [MQ][KPAD]
+    uint64_t *pend;    // [MQ][32]
+    uint32_t *npend;   // [MQ]
+    uint32_t km1;
+
+    __device__ __forceinline__ uint64_t thr_of(int b) const { return list[(size_t)b * KPAD + km1]; }
+
+    __device__ __forceinline__ void init(uint64_t *l, uint64_t *p, uint32_t *np, uint32_t k, int mq, int lane)
+    {
+        list = l; pend = p; npend = np; km1 = k - 1;
+        for (int j = lane; j < mq * (int)KPAD; j += 32) list[j] = KEY_EMPTY;
+        if (lane < mq) npend[lane] = 0;
+        __syncwarp();
+    }
+    // warp-uniform (b, key)
+    __device__ __forceinline__ void append(int b, uint64_t key, int lane)
+    {
+        const uint32_t np = npend[b];
+        __syncwarp();
+        if (lane == 0) { pend[b * 32 + np] = key; npend[b] = np + 1; }
+        __syncwarp();
+        if (np + 1 == 32) flush(b, lane);
+    }
+    __device__ __noinline__ void flush(int b, int lane)
+    {
+        const uint32_t np = npend[b];
+        if (np == 0) return;
+        uint64_t *L = list + (size_t)b * KPAD;
+        uint64_t p = ((uint32_t)lane < np) ? pend[b * 32 + lane] : KEY_EMPTY;
+        p = warp_sort32(p, lane);
+        uint64_t l[E];
+        uint32_t pos[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const uint32_t j = lane + 32 * e;
+            l[e] = L[j];
+            int c = 0;
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) {
+                const uint64_t pv = shfl64(p, c + s - 1);
+                if (pv < l[e]) c += s;
+            }
+            const uint64_t pv = shfl64(p, c);
+            if (pv < l[e]) c += 1;
+            pos[e] = j + (uint32_t)c;
+        }
+        uint32_t c = 0;
+#pragma unroll
+        for (uint32_t s = KPAD >> 1; s > 0; s >>= 1)
+            if (L[c + s - 1] <= p) c += s;
+        if (L[c] <= p) c += 1;
+        const uint32_t ppos = (uint32_t)lane + c;
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            if (pos[e] < KPAD) L[pos[e]] = l[e];
+        if (ppos < KPAD) L[ppos] = p;
+        if (lane == 0) npend[b] = 0;
+        __syncwarp();
+    }
+};
+
+// smem per CTA: queries MQ*dim4 float4 | per warp: MQ*KPAD + MQ*32 keys + MQ u32 | sort buffer WARPS*KPAD keys
+template <int E>
+__host__ __device__ constexpr size_t multi_warp_keys(int mq) { return (size_t)mq * (32 * E) + (size_t)mq * 32; }
+
+template <int V, int R, int MQ, int E>
+__global__ void __launch_bounds__(SCAN_THREADS, (E <= 4) ? 2 : 1) scan_multi_topk_kernel(const MultiArgs a)
+{
+    constexpr bool EXACT = true;   // dim % 128 == 0 only (other dims: per-query loop of scan.cuh)
+    constexpr int NV = R * MQ;     // 8, 16 or 32 results per warp iteration
+    constexpr int SH = (NV == 32) ? 0 : (NV == 16 ? 1 : 2);
+    static_assert(NV == 32 || NV == 16 || NV == 8, "R*MQ must be 8, 16 or 32");
+    constexpr uint32_t KPAD = 32u * E;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t dim4 = a.dim4;
+
+    float4 *qs = reinterpret_cast<float4 *>(smem_raw);                                   // [MQ][dim4]
+    uint64_t *keys0 = reinterpret_cast<uint64_t *>(smem_raw + (size_t)MQ * dim4 * sizeof(float4));
+    const size_t wkeys = multi_warp_keys<E>(MQ);
+    uint64_t *wbase = keys0 + (size_t)warp * wkeys;
+    uint64_t *sortbuf = keys0 + (size_t)SCAN_WARPS * wkeys;                              // [WARPS*KPAD]
+    uint32_t *np_all = reinterpret_cast<uint32_t *>(sortbuf + (size_t)SCAN_WARPS * KPAD); // [WARPS][MQ]
+    __shared__ float qflag[MQ];  // 1.0f if the query has zero norm (distance 0.0 everywhere)
+
+    // ---- queries -> smem, unit-normalised exactly as scan.cuh does it (warp w handles query w) ----
+    for (int b = warp; b < MQ; b += SCAN_WARPS) {
+        float4 t[V];
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const uint32_t c = lane + 32 * j;
+            if ((uint32_t)b < a.nq && (EXACT || c < dim4)) t[j] = reinterpret_cast<const float4 *>(a.q)[(size_t)b * dim4 + c];
+            else t[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            ss = fmaf(t[j].x, t[j].x, ss); ss = fmaf(t[j].y, t[j].y, ss);
+            ss = fmaf(t[j].z, t[j].z, ss); ss = fmaf(t[j].w, t[j].w, ss);
+        }
+        ss = warp_sum_tree(ss);
+        const bool qzero = !(ss > 0.f);
+        const float qinv = qzero ? 0.f : 1.0f / sqrtf(ss);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const uint32_t c = lane + 32 * j;
+            if (EXACT || c < dim4) qs[(size_t)b * dim4 + c] = make_float4(t[j].x * qinv, t[j].y * qinv, t[j].z * qinv, t[j].w * qinv);
+        }
+        if (lane == 0) qflag[b] = qzero ? 1.f : 0.f;
+    }
+    MultiSel<E> sel;
+    sel.init(wbase, wbase + (size_t)MQ * KPAD, np_all + warp * MQ, a.k, MQ, lane);
+    __syncthreads();
+
+    // lane -> (row slot, query) ownership after the butterfly
+    const int own = lane >> SH;
+    const bool owner = (lane & ((1 << SH) - 1)) == 0;
+    const int my_b = own % MQ, my_r = own / MQ;
+    const bool my_active = owner && (uint32_t)my_b < a.nq;
+    const bool my_qzero = qflag[my_b] != 0.f;
+    uint64_t thr = my_active ? KEY_EMPTY : 0ull;  // inactive lanes never pass
+
+    const uint64_t n = a.n_rows;
+    const uint64_t gw = (uint64_t)blockIdx.x * SCAN_WARPS + warp;
+    const uint64_t stride = (uint64_t)gridDim.x * SCAN_WARPS * R;
+    for (uint64_t base = gw * R; base < n; base += stride) {
+        float4 x[R][V];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint64_t row = base + r;
+            const float4 *p = a.rows + row * dim4 + lane;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                if (row < n && (EXACT || lane + 32 * j < dim4)) x[r][j] = ldg_stream<0>(p + 32 * j);
+                else x[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+#pragma unroll
+            for (int b = 0; b < MQ; ++b) {
+                float4 qq = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (EXACT || lane + 32 * j < dim4) qq = qs[(size_t)b * dim4 + lane + 32 * j];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    float acc = v[r * MQ + b];
+                    acc = fmaf(x[r][j].x, qq.x, acc); acc = fmaf(x[r][j].y, qq.y, acc);
+                    acc = fmaf(x[r][j].z, qq.z, acc); acc = fmaf(x[r][j].w, qq.w, acc);
+                    v[r * MQ + b] = acc;
+                }
+            }
+        }
+        butterfly_level<NV, 16>(v, lane);
+        butterfly_level<(NV / 2 > 0 ? NV / 2 : 1), 8>(v, lane);
+        butterfly_level<(NV / 4 > 0 ? NV / 4 : 1), 4>(v, lane);
+        butterfly_level<(NV / 8 > 0 ? NV / 8 : 1), 2>(v, lane);
+        butterfly_level<(NV / 16 > 0 ? NV / 16 : 1), 1>(v, lane);
+        const float dist = my_qzero ? 0.f : fmaf(-0.5f, v[0], 0.5f);
+        const uint64_t row = base + my_r;
+        uint64_t key = KEY_EMPTY;
+        if (my_active && row < n && okey(dist) <= (uint32_t)(thr >> 32)) {
+            const uint32_t id = a.ids[row];
+            const uint64_t kk = make_key(dist, id);
+            if (kk < thr && id_allowed(a.bitmap, a.n_bits, id)) key = kk;
+        }
+        unsigned m = __ballot_sync(FULL, key != KEY_EMPTY);
+        if (m) {
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const uint64_t kk = shfl64(key, src);
+                const int b = (src >> SH) % MQ;
+                if (kk < sel.thr_of(b)) sel.append(b, kk, lane);
+            }
+            if (my_active) thr = sel.thr_of(my_b);
+        }
+    }
+
+    // ---- per query: CTA top-k -> cand[b][cta][k]; last CTA merges across CTAs ----------------
+    auto reduce_query = [&](int b, uint64_t *dst) {
+        sel.flush(b, lane);
+        const uint64_t *L = sel.list + (size_t)b * KPAD;
+        for (uint32_t j = lane; j < KPAD; j += 32) sortbuf[(size_t)warp * KPAD + j] = L[j];
+        cta_sort(sortbuf, SCAN_WARPS * KPAD);
+        for (uint32_t j = threadIdx.x; j < a.k; j += blockDim.x) dst[j] = sortbuf[j];
+        __syncthreads();
+    };
+    for (int b = 0; b < (int)a.nq; ++b) reduce_query(b, a.cand + ((size_t)b * gridDim.x + blockIdx.x) * a.k);
+
+    __threadfence();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(a.ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+
+    sel.init(wbase, wbase + (size_t)MQ * KPAD, np_all + warp * MQ, a.k, MQ, lane);
+    const uint64_t total = (uint64_t)gridDim.x * a.k;
+    for (int b = 0; b < (int)a.nq; ++b) {
+        const volatile uint64_t *cand = a.cand + (size_t)b * total;
+        for (uint64_t o = (uint64_t)warp * 32; o < total; o += SCAN_WARPS * 32) {
+            const uint64_t key = (o + lane < total) ? cand[o + lane] : KEY_EMPTY;
+            unsigned m = __ballot_sync(FULL, key < sel.thr_of(b));
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const uint64_t kk = shfl64(key, src);
+                if (kk < sel.thr_of(b)) sel.append(b, kk, lane);
+            }
+        }
+        if (warp == 0 && a.n_zero) {
+            uint32_t found = 0;
+            for (uint32_t o = 0; o < a.n_zero && found < a.k; o += 32) {
+                uint64_t key = KEY_EMPTY;
+                if (o + lane < a.n_zero) {
+                    const uint32_t id = a.zero_ids[o + lane];
+                    if (id_allowed(a.bitmap, a.n_bits, id)) key = make_key(0.f, id);
+                }
+                unsigned m = __ballot_sync(FULL, key != KEY_EMPTY);
+                found += __popc(m);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint64_t kk = shfl64(key, src);
+                    if (kk < sel.thr_of(b)) sel.append(b, kk, lane);
+                }
+            }
+        }
+        reduce_query(b, a.out_keys + (size_t)b * a.k);
+    }
+    if (threadIdx.x == 0) *a.ticket = 0;
+}
+
+}  // namespace csgpu

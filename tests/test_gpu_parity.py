@@ -313,9 +313,39 @@ def test_batch_matches_single(cs, oracle):
     oi, od, on = st.search_batch_ids(qs, 100)
     for j in range(9):
         gi, gd = st.search_ids(qs[j], 100)
+        # the multi-query kernel is bit-identical to the single-query kernel (same FMA chain, same tree)
         assert on[j] == 100 and np.array_equal(oi[j], gi) and np.array_equal(od[j], gd)
         ri, rd, r64 = oracle.np_search(rows, qs[j], 100 + MARGIN)
         check_topk(oi[j], od[j], ri, rd, r64, 100)
+
+
+@pytest.mark.parametrize("n,d,b,k", [
+    (20000, 384, 2, 10), (20000, 384, 3, 32), (20000, 384, 8, 10), (20000, 384, 9, 33), (20000, 384, 17, 100),
+    (20000, 384, 5, 256), (5000, 384, 4, 300), (5000, 768, 8, 200), (5000, 1024, 7, 25), (5000, 128, 16, 64),
+    (5000, 256, 3, 10), (5000, 512, 8, 128), (3000, 100, 5, 10), (3, 384, 8, 10), (1, 384, 2, 1),
+])
+def test_batch_parity(cs, oracle, n, d, b, k):
+    from codesearch_b200 import _lib
+    rng = np.random.default_rng(n + d * 7 + b * 13 + k)
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    rows[n // 2] = 0.0                                           # a zero-norm row rides along
+    ids = rng.permutation(n * 2)[:n].astype(np.uint32)
+    st = make_store(cs, rows, ids)
+    qs = rng.standard_normal((b, d)).astype(np.float32)
+    if b > 2:
+        qs[1] = 0.0                                              # and a zero-norm query
+    launches0 = _lib.load().csgpu_kernel_launches()
+    oi, od, on = st.search_batch_ids(qs, k)
+    launches = _lib.load().csgpu_kernel_launches() - launches0
+    if d % 128 == 0 and k <= 256:                                # one pass per <= 8 queries
+        assert launches == (b // 8) + (1 if b % 8 else 0)
+    k_eff = min(k, n)
+    for j in range(b):
+        ri, rd, r64 = oracle.np_search(rows, qs[j], k + MARGIN, ids=ids)
+        assert on[j] == k_eff
+        check_topk(oi[j, :k_eff], od[j, :k_eff], ri, rd, r64, k_eff)
+        gi, gd = st.search_ids(qs[j], k)
+        assert np.array_equal(oi[j, :k_eff], gi) and np.array_equal(od[j, :k_eff], gd)
 
 
 # ---- device entry points + cross-shard merge ---------------------------------------------------
