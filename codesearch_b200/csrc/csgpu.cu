@@ -31,13 +31,7 @@ int fail_cuda(cudaError_t e, const char *what, const char *file, int line)
     return (e == cudaErrorMemoryAllocation) ? CSGPU_ERR_OOM : CSGPU_ERR_CUDA;
 }
 
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int d) { cudaGetDevice(&prev); if (prev != d) cudaSetDevice(d); else prev = -1; }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
-
-static inline void count_launch(uint64_t n = 1) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
+void count_launch(uint64_t n) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ---------------------------------------------------------------------------------------
 // contexts
@@ -223,6 +217,7 @@ static int enqueue_scan_multi(const csgpu_index *ix, const Shard *sh, SearchCtx 
 // ---------------------------------------------------------------------------------------
 static int shard_reserve(const csgpu_index *ix, Shard *sh, uint64_t rows)
 {
+    if (ix->dtype == CSGPU_DTYPE_BF16) return bf16_reserve_rows(ix, sh, rows);
     if (rows <= sh->cap) return CSGPU_OK;
     DeviceGuard g(sh->device);
     uint64_t ncap = std::max<uint64_t>(rows, sh->cap + sh->cap / 2);
@@ -334,7 +329,14 @@ static int shard_build(csgpu_index *ix, Shard *sh, std::vector<uint32_t> &new_ze
     const uint64_t n = sh->n_total;
     if (n == 0) { sh->n_built = 0; return CSGPU_OK; }
     const uint64_t pending = n - sh->n_built;
-    if (pending) {
+    const bool bf16 = ix->dtype == CSGPU_DTYPE_BF16;
+    char *rowbase = bf16 ? reinterpret_cast<char *>(sh->rows_bf16) : reinterpret_cast<char *>(sh->rows);
+    const size_t row_bytes = bf16 ? (size_t)ix->dim * 2 : (size_t)ix->dim_pad * sizeof(float);
+    const uint32_t row_u4 = (uint32_t)(row_bytes / 16);
+    if (bf16) {
+        int rc = bf16_convert_pending(ix, sh);
+        if (rc) return rc;
+    } else if (pending) {
         const uint32_t grid = (uint32_t)std::min<uint64_t>((pending + 7) / 8, (uint64_t)sh->sm_count * 8);
         normalise_rows_kernel<<<grid, 256, 0, sh->stream>>>(reinterpret_cast<float4 *>(sh->rows), sh->status, sh->n_built, pending, ix->dim4);
         count_launch();
@@ -366,17 +368,17 @@ static int shard_build(csgpu_index *ix, Shard *sh, std::vector<uint32_t> &new_ze
         const uint64_t CH = 65536;  // rows per bounce chunk
         uint32_t *keep_dev = nullptr; float *bounce = nullptr; uint32_t *bounce_ids = nullptr;
         CS_CUDA(cudaMalloc(&keep_dev, moved * sizeof(uint32_t)));
-        CS_CUDA(cudaMalloc(&bounce, std::min(CH, moved) * (size_t)ix->dim_pad * sizeof(float)));
+        CS_CUDA(cudaMalloc(&bounce, std::min(CH, moved) * row_bytes));
         CS_CUDA(cudaMalloc(&bounce_ids, std::min(CH, moved) * sizeof(uint32_t)));
         CS_CUDA(cudaMemcpyAsync(keep_dev, keep_src.data(), moved * sizeof(uint32_t), cudaMemcpyHostToDevice, sh->stream));
         for (uint64_t c0 = 0; c0 < moved; c0 += CH) {
             const uint64_t cn = std::min(CH, moved - c0);
             const uint32_t grid = (uint32_t)std::min<uint64_t>((cn + 7) / 8, (uint64_t)sh->sm_count * 8);
-            gather_rows_bounce_kernel<<<grid, 256, 0, sh->stream>>>(reinterpret_cast<const float4 *>(sh->rows),
-                                                                     reinterpret_cast<float4 *>(bounce), keep_dev + c0, cn, ix->dim4);
+            gather_rows_bounce_kernel<<<grid, 256, 0, sh->stream>>>(reinterpret_cast<const float4 *>(rowbase),
+                                                                     reinterpret_cast<float4 *>(bounce), keep_dev + c0, cn, row_u4);
             gather_u32_kernel<<<(uint32_t)((cn + 255) / 256), 256, 0, sh->stream>>>(sh->ids, bounce_ids, keep_dev + c0, cn);
             count_launch(2);
-            CS_CUDA(cudaMemcpyAsync(sh->rows + (first_bad + c0) * ix->dim_pad, bounce, cn * (size_t)ix->dim_pad * sizeof(float), cudaMemcpyDeviceToDevice, sh->stream));
+            CS_CUDA(cudaMemcpyAsync(rowbase + (first_bad + c0) * row_bytes, bounce, cn * row_bytes, cudaMemcpyDeviceToDevice, sh->stream));
             CS_CUDA(cudaMemcpyAsync(sh->ids + first_bad + c0, bounce_ids, cn * sizeof(uint32_t), cudaMemcpyDeviceToDevice, sh->stream));
         }
         CS_CUDA(cudaStreamSynchronize(sh->stream));
@@ -408,7 +410,7 @@ static int check_search_args(const csgpu_index *ix, const float *q, uint32_t q_l
     return CSGPU_OK;
 }
 
-static void decode_keys(const uint64_t *keys, uint32_t k, uint32_t *out_ids, float *out_dist, uint32_t *out_n)
+void decode_keys(const uint64_t *keys, uint32_t k, uint32_t *out_ids, float *out_dist, uint32_t *out_n)
 {
     uint32_t m = 0;
     for (uint32_t i = 0; i < k; ++i) {
@@ -567,7 +569,9 @@ int csgpu_create(csgpu_index **out, uint32_t dim, uint32_t dtype, const int32_t 
     *out = nullptr;
     if (dim == 0 || dim > CSGPU_MAX_DIM) return fail(CSGPU_ERR_ARG, "dim must be in [1, 4096]");
     if (((dim + 3) / 4 + 31) / 32 > 8) return fail(CSGPU_ERR_ARG, "dim > 1024 is not supported by the scan kernels yet");
-    if (dtype != CSGPU_DTYPE_F32) return fail(CSGPU_ERR_ARG, "only CSGPU_DTYPE_F32 is implemented (bf16 index: planned)");
+    if (dtype != CSGPU_DTYPE_F32 && dtype != CSGPU_DTYPE_BF16) return fail(CSGPU_ERR_ARG, "dtype must be CSGPU_DTYPE_F32 or CSGPU_DTYPE_BF16");
+    if (dtype == CSGPU_DTYPE_BF16 && !bf16_dim_supported(dim)) return fail(CSGPU_ERR_ARG, "bf16 index needs dim % 64 == 0 and 64 <= dim <= 512");
+    if (dtype == CSGPU_DTYPE_BF16 && n_devices > 1) return fail(CSGPU_ERR_ARG, "bf16 index: multi-device sharding is not implemented yet");
     if (n_devices == 0) n_devices = 1;
     if (n_devices > 8) return fail(CSGPU_ERR_ARG, "n_devices must be <= 8");
     int count = 0;
@@ -615,6 +619,8 @@ void csgpu_destroy(csgpu_index *ix)
     for (Shard *sh : ix->shards) {
         DeviceGuard dg(sh->device);
         for (SearchCtx *c : sh->all_ctx) ctx_destroy(c);
+        bf16_free_batch_ctx(sh);
+        cudaFree(sh->rows_bf16); cudaFree(sh->stage);
         cudaFree(sh->rows); cudaFree(sh->ids); cudaFree(sh->status);
         if (sh->stream) cudaStreamDestroy(sh->stream);
         delete sh;
@@ -673,8 +679,10 @@ int csgpu_append(csgpu_index *ix, const float *rows, const uint32_t *ids, uint64
         if (!m) continue;
         int rc = shard_reserve(ix, sh, sh->n_total + m);
         if (rc) return rc;
+        const bool bf16 = ix->dtype == CSGPU_DTYPE_BF16;
+        if (bf16 && (rc = bf16_reserve_stage(ix, sh, sh->n_total - sh->n_built + m))) return rc;
         DeviceGuard dg(sh->device);
-        float *dst = sh->rows + sh->n_total * ix->dim_pad;
+        float *dst = bf16 ? sh->stage + (sh->n_total - sh->n_built) * ix->dim_pad : sh->rows + sh->n_total * ix->dim_pad;
         if (ix->dim_pad == ix->dim) {
             CS_CUDA(cudaMemcpyAsync(dst, rows + a * ix->dim, m * (size_t)ix->dim * sizeof(float), cudaMemcpyHostToDevice, sh->stream));
         } else {
@@ -704,10 +712,14 @@ int csgpu_append_synthetic(csgpu_index *ix, uint64_t seed, uint64_t first_row, u
         if (!m) continue;
         int rc = shard_reserve(ix, sh, sh->n_total + m);
         if (rc) return rc;
+        const bool bf16 = ix->dtype == CSGPU_DTYPE_BF16;
+        if (bf16 && (rc = bf16_reserve_stage(ix, sh, sh->n_total - sh->n_built + m))) return rc;
         DeviceGuard dg(sh->device);
         const uint64_t total = m * ix->dim4;
         const uint32_t grid = (uint32_t)std::min<uint64_t>((total + 255) / 256, (uint64_t)sh->sm_count * 16);
-        synth_rows_kernel<<<grid, 256, 0, sh->stream>>>(reinterpret_cast<float4 *>(sh->rows) + sh->n_total * ix->dim4,
+        float4 *synth_dst = bf16 ? reinterpret_cast<float4 *>(sh->stage) + (sh->n_total - sh->n_built) * ix->dim4
+                                 : reinterpret_cast<float4 *>(sh->rows) + sh->n_total * ix->dim4;
+        synth_rows_kernel<<<grid, 256, 0, sh->stream>>>(synth_dst,
                                                         sh->ids + sh->n_total, seed, first_row + a, m, ix->dim4, id_base);
         count_launch();
         CS_CUDA(cudaGetLastError());
@@ -769,6 +781,8 @@ int csgpu_build(csgpu_index *ix)
     }
     int rc = upload_zero_ids(ix);
     if (rc) return rc;
+    if (ix->dtype == CSGPU_DTYPE_BF16)
+        for (Shard *sh : ix->shards) if ((rc = bf16_after_build(ix, sh))) return rc;
     ix->tombstones = 0;
     ix->built = true;
     return CSGPU_OK;
@@ -780,6 +794,8 @@ int csgpu_clear(csgpu_index *ix)
     for (Shard *sh : ix->shards) {
         DeviceGuard dg(sh->device);
         cudaFree(sh->rows); cudaFree(sh->ids); cudaFree(sh->status);
+        cudaFree(sh->rows_bf16); cudaFree(sh->stage);
+        sh->rows_bf16 = nullptr; sh->stage = nullptr; sh->stage_cap = 0;
         sh->rows = nullptr; sh->ids = nullptr; sh->status = nullptr;
         sh->n_built = sh->n_total = sh->cap = 0;
     }
@@ -799,6 +815,7 @@ int csgpu_search(const csgpu_index *ix, const float *q, uint32_t q_len, uint32_t
     if (rc) return rc;
     if (!all_finite(q, q_len)) return fail(CSGPU_ERR_ARG, "query contains NaN/Inf");
     if (k == 0) return CSGPU_OK;
+    if (ix->dtype == CSGPU_DTYPE_BF16) return bf16_search_batch(ix, q, 1, k, out_ids, out_dist, out_n);
     return search_one(ix, q, k, nullptr, 0, out_ids, out_dist, out_n);
 }
 
@@ -810,6 +827,7 @@ int csgpu_search_filtered(const csgpu_index *ix, const float *q, uint32_t q_len,
     int rc = check_search_args(ix, q, q_len, k);
     if (rc) return rc;
     if (!id_bitmap && n_bits) return fail(CSGPU_ERR_ARG, "id_bitmap is null");
+    if (ix->dtype == CSGPU_DTYPE_BF16) return fail(CSGPU_ERR_ARG, "filtered search is not implemented for the bf16 index yet");
     if (!all_finite(q, q_len)) return fail(CSGPU_ERR_ARG, "query contains NaN/Inf");
     if (k == 0) return CSGPU_OK;
     static const uint64_t empty_word = 0;
@@ -824,6 +842,7 @@ int csgpu_search_batch(const csgpu_index *ix, const float *q, uint32_t q_len, ui
     if (rc) return rc;
     if (!all_finite(q, q_len * b)) return fail(CSGPU_ERR_ARG, "query contains NaN/Inf");
     if (k == 0 || b == 0) return CSGPU_OK;
+    if (ix->dtype == CSGPU_DTYPE_BF16) return bf16_search_batch(ix, q, b, k, out_ids, out_dist, out_n);
     // chunks of up to 8 queries share ONE pass over the corpus (scan_multi.cuh); leftovers of one query,
     // k > 256 or dims that are not a multiple of 128 take the single-query kernel.
     const uint32_t MQ = multi_scan_max_queries();
@@ -850,6 +869,7 @@ int csgpu_search_keys_device(const csgpu_index *ix, const float *q_dev, uint32_t
     if (!ix) return fail(CSGPU_ERR_ARG, "null index");
     if (!ix->built) return fail(CSGPU_ERR_NOT_BUILT, "Index not built. Call build_index() after inserting chunks.");
     if (ix->shards.size() != 1) return fail(CSGPU_ERR_ARG, "device entry points need a single-device index");
+    if (ix->dtype != CSGPU_DTYPE_F32) return fail(CSGPU_ERR_ARG, "device entry points need an fp32 index");
     if (!q_dev || !out_keys_dev) return fail(CSGPU_ERR_ARG, "null device pointer");
     if (k == 0 || k > CSGPU_MAX_K) return fail(CSGPU_ERR_ARG, "k must be in [1, 1024]");
     Shard *sh = ix->shards[0];
@@ -898,7 +918,8 @@ int csgpu_stats(const csgpu_index *ix, csgpu_stats_t *out)
         out->live_rows += sh->n_built;
         out->pending_rows += sh->n_total - sh->n_built;
         out->rows_per_device[g] = sh->n_built;
-        out->bytes_on_device += sh->cap * ((size_t)ix->dim_pad * sizeof(float) + sizeof(uint32_t) + 1);
+        const size_t row_bytes = ix->dtype == CSGPU_DTYPE_BF16 ? (size_t)ix->dim * 2 : (size_t)ix->dim_pad * sizeof(float);
+        out->bytes_on_device += sh->cap * (row_bytes + sizeof(uint32_t) + 1) + sh->stage_cap * (size_t)ix->dim_pad * sizeof(float);
     }
     out->live_rows += ix->zero_ids.size();
     return CSGPU_OK;

@@ -1,0 +1,398 @@
+// gemm_topk.cu — bf16 index: storage hooks, TMA tensor maps, the phase loop around
+// gemm_topk_kernel (tcgen05) and the per-query exact select kernel. See gemm_topk.cuh for the design.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "index.h"
+#include "gemm_topk.cuh"
+#include "scan.cuh"
+#include "synth.cuh"
+
+namespace csgpu {
+
+constexpr uint32_t BF_CAP = 8192;          // candidate slots per query
+constexpr uint32_t BF_MAX_QBLOCKS = 8;     // 1024 queries per pass
+constexpr uint32_t BF_PHASE_GROWTH = 8;
+
+// ---------------------------------------------------------------------------------------------
+// kernels local to this file
+// ---------------------------------------------------------------------------------------------
+template <bool BIG>
+__global__ void __launch_bounds__(SCAN_THREADS, 1)
+select_candidates_kernel(uint64_t *__restrict__ cand, unsigned *__restrict__ count, float *__restrict__ thr,
+                         uint32_t cap, uint32_t k, uint32_t kpad, uint32_t n_active,
+                         const uint32_t *__restrict__ zero_ids, uint32_t n_zero, uint64_t *__restrict__ final_out)
+{
+    extern __shared__ __align__(16) uint64_t smem[];
+    const uint32_t q = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (q >= n_active) {
+        if (threadIdx.x == 0) { count[q] = 0; thr[q] = -1.f; }
+        return;
+    }
+    using Sel = typename SelOf<BIG>::type;
+    Sel sel;
+    if constexpr (BIG) sel.init(smem + (size_t)warp * kpad, smem + (size_t)(SCAN_WARPS + warp) * kpad, k, kpad, lane);
+    else sel.init(k);
+    uint64_t *mine = cand + (size_t)q * cap;
+    const uint32_t n = min(count[q], cap);
+    for (uint32_t b = warp * 32; b < n; b += SCAN_WARPS * 32) {
+        const uint64_t key = (b + lane < n) ? mine[b + lane] : KEY_EMPTY;
+        offer_lane_keys(sel, key, lane);
+    }
+    if (final_out != nullptr && warp == 0 && n_zero) {   // zero-norm rows: distance 0.0 (arroy pn*qn == 0)
+        uint32_t found = 0;
+        for (uint32_t b = 0; b < n_zero && found < k; b += 32) {
+            const uint64_t key = (b + lane < n_zero) ? make_key(0.f, zero_ids[b + lane]) : KEY_EMPTY;
+            found += __popc(__ballot_sync(FULL, key != KEY_EMPTY));
+            offer_lane_keys(sel, key, lane);
+        }
+    }
+    __syncthreads();   // every warp has finished reading cand[q] before it is overwritten
+    cta_reduce<BIG>(sel, smem, k, kpad, mine, warp, lane);
+    if (final_out != nullptr)
+        for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) final_out[(size_t)q * k + j] = mine[j];
+    if (threadIdx.x == 0) {
+        uint32_t m = 0;
+        while (m < k && mine[m] != KEY_EMPTY) ++m;
+        count[q] = m;
+        float t = __int_as_float(0x7f800000);  // +inf: everything passes until k candidates exist
+        if (m >= k) t = __uint_as_float(bits_from_okey((uint32_t)(mine[k - 1] >> 32)));
+        thr[q] = t;
+    }
+}
+
+__global__ void init_thresholds_kernel(float *thr, unsigned *count, uint32_t n_active, uint32_t n_total)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_total) { thr[i] = (i < n_active) ? __int_as_float(0x7f800000) : -1.f; count[i] = 0; }
+}
+
+__global__ void max_count_kernel(const unsigned *count, uint32_t n, unsigned *out)
+{
+    unsigned m = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) m = max(m, count[i]);
+    atomicMax(out, m);
+}
+
+// pending fp32 rows (stage) -> unit length (f64 norm) -> bf16 rows at [dst_first + i]; flags zero / non-finite
+__global__ void normalise_to_bf16_kernel(const float *__restrict__ stage, __nv_bfloat16 *__restrict__ rows,
+                                         uint8_t *__restrict__ status, uint64_t dst_first, uint64_t n, uint32_t dim)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t w0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t i = w0; i < n; i += nw) {
+        const uint64_t row = dst_first + i;
+        const float *p = stage + i * dim;
+        __nv_bfloat16 *o = rows + row * dim;
+        double ss = 0.0;
+        bool finite = true;
+        for (uint32_t c = lane; c < dim; c += 32) { const float x = p[c]; ss += (double)x * x; finite = finite && isfinite(x); }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, m);
+        finite = __all_sync(0xFFFFFFFFu, finite);
+        const bool dead = status[row] == ROW_DEAD;
+        const bool zero = !(ss > 0.0);
+        const double inv = (finite && !zero) ? 1.0 / sqrt(ss) : 0.0;
+        for (uint32_t c = lane; c < dim; c += 32) o[c] = __float2bfloat16((float)(p[c] * inv));
+        if (lane == 0 && !dead) {
+            if (!finite) status[row] = ROW_NONFINITE;
+            else if (zero) status[row] = ROW_ZERO;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tensor maps
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// [rows][dim] bf16 row-major, box = [box_rows][64], 128-byte swizzle
+static int make_map(CUtensorMap *map, const void *base, uint64_t rows, uint32_t dim, uint32_t box_rows)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(CSGPU_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable in this driver");
+    const cuuint64_t gdim[2] = {dim, std::max<uint64_t>(rows, 1)};
+    const cuuint64_t gstride[1] = {(cuuint64_t)dim * 2};
+    const cuuint32_t box[2] = {GT_BLOCK_K, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(CSGPU_ERR_CUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+    return CSGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// storage hooks (called from csgpu.cu when ix->dtype == BF16)
+// ---------------------------------------------------------------------------------------------
+bool bf16_dim_supported(uint32_t dim) { return dim % 64 == 0 && dim >= 64 && dim <= 512; }
+
+int bf16_reserve_rows(const csgpu_index *ix, Shard *sh, uint64_t rows)
+{
+    if (rows <= sh->cap) return CSGPU_OK;
+    DeviceGuard g(sh->device);
+    uint64_t ncap = std::max<uint64_t>(std::max<uint64_t>(rows, sh->cap + sh->cap / 2), 1024);
+    void *nrows = nullptr; uint32_t *nids = nullptr; uint8_t *nst = nullptr;
+    const size_t row_bytes = (size_t)ix->dim * 2;
+    cudaError_t e = cudaMalloc(&nrows, ncap * row_bytes);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(bf16 rows)", __FILE__, __LINE__);
+    if ((e = cudaMalloc(&nids, ncap * sizeof(uint32_t))) != cudaSuccess) { cudaFree(nrows); return fail_cuda(e, "cudaMalloc(ids)", __FILE__, __LINE__); }
+    if ((e = cudaMalloc(&nst, ncap)) != cudaSuccess) { cudaFree(nrows); cudaFree(nids); return fail_cuda(e, "cudaMalloc(status)", __FILE__, __LINE__); }
+    CS_CUDA(cudaMemsetAsync(nst, 0, ncap, sh->stream));
+    if (sh->n_built) CS_CUDA(cudaMemcpyAsync(nrows, sh->rows_bf16, sh->n_built * row_bytes, cudaMemcpyDeviceToDevice, sh->stream));
+    if (sh->n_total) {
+        CS_CUDA(cudaMemcpyAsync(nids, sh->ids, sh->n_total * sizeof(uint32_t), cudaMemcpyDeviceToDevice, sh->stream));
+        CS_CUDA(cudaMemcpyAsync(nst, sh->status, sh->n_total, cudaMemcpyDeviceToDevice, sh->stream));
+    }
+    CS_CUDA(cudaStreamSynchronize(sh->stream));
+    cudaFree(sh->rows_bf16); cudaFree(sh->ids); cudaFree(sh->status);
+    sh->rows_bf16 = nrows; sh->ids = nids; sh->status = nst; sh->cap = ncap;
+    return CSGPU_OK;
+}
+
+// room for `pending` fp32 rows in the staging area
+int bf16_reserve_stage(const csgpu_index *ix, Shard *sh, uint64_t pending)
+{
+    if (pending <= sh->stage_cap) return CSGPU_OK;
+    DeviceGuard g(sh->device);
+    const uint64_t have = sh->n_total - sh->n_built;
+    uint64_t ncap = std::max<uint64_t>(std::max<uint64_t>(pending, sh->stage_cap * 2), 1024);
+    float *ns = nullptr;
+    cudaError_t e = cudaMalloc(&ns, ncap * (size_t)ix->dim * sizeof(float));
+    if (e != cudaSuccess && ncap > pending) { cudaGetLastError(); ncap = pending; e = cudaMalloc(&ns, ncap * (size_t)ix->dim * sizeof(float)); }
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(stage)", __FILE__, __LINE__);
+    if (have) CS_CUDA(cudaMemcpyAsync(ns, sh->stage, have * (size_t)ix->dim * sizeof(float), cudaMemcpyDeviceToDevice, sh->stream));
+    CS_CUDA(cudaStreamSynchronize(sh->stream));
+    cudaFree(sh->stage);
+    sh->stage = ns; sh->stage_cap = ncap;
+    return CSGPU_OK;
+}
+
+// normalise + convert pending rows; leaves status flags for the generic compaction in csgpu.cu
+int bf16_convert_pending(const csgpu_index *ix, Shard *sh)
+{
+    const uint64_t pending = sh->n_total - sh->n_built;
+    if (!pending) return CSGPU_OK;
+    DeviceGuard g(sh->device);
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((pending + 7) / 8, (uint64_t)sh->sm_count * 8);
+    normalise_to_bf16_kernel<<<grid, 256, 0, sh->stream>>>(sh->stage, reinterpret_cast<__nv_bfloat16 *>(sh->rows_bf16), sh->status,
+                                                           sh->n_built, pending, ix->dim);
+    count_launch();
+    CS_CUDA(cudaGetLastError());
+    CS_CUDA(cudaStreamSynchronize(sh->stream));
+    cudaFree(sh->stage);   // staging is only needed between append and build
+    sh->stage = nullptr; sh->stage_cap = 0;
+    return CSGPU_OK;
+}
+
+int bf16_after_build(const csgpu_index *ix, Shard *sh)
+{
+    return make_map(&sh->map_c, sh->rows_bf16 ? sh->rows_bf16 : (void *)sh->ids, sh->n_built, ix->dim, GT_BLOCK_N);
+}
+
+void bf16_free_batch_ctx(Shard *sh)
+{
+    if (!sh->bf) return;
+    DeviceGuard g(sh->device);
+    Bf16BatchCtx *c = sh->bf;
+    if (c->stream) cudaStreamDestroy(c->stream);
+    cudaFree(c->q_f32); cudaFree(c->q_bf16); cudaFree(c->flags); cudaFree(c->thr); cudaFree(c->count); cudaFree(c->count_saved);
+    cudaFree(c->cand); cudaFree(c->out); cudaFree(c->scalar);
+    cudaFreeHost(c->q_pin); cudaFreeHost(c->out_pin);
+    delete c;
+    sh->bf = nullptr;
+}
+
+static int bf16_batch_ctx(const csgpu_index *ix, Shard *sh, Bf16BatchCtx **out)
+{
+    if (sh->bf) { *out = sh->bf; return CSGPU_OK; }
+    DeviceGuard g(sh->device);
+    Bf16BatchCtx *c = new Bf16BatchCtx();
+    sh->bf = c;
+    const size_t nq = (size_t)BF_MAX_QBLOCKS * GT_BLOCK_M;
+    CS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CS_CUDA(cudaMalloc(&c->q_f32, nq * ix->dim * sizeof(float)));
+    CS_CUDA(cudaMalloc(&c->q_bf16, nq * ix->dim * 2));
+    CS_CUDA(cudaMalloc(&c->flags, nq));
+    CS_CUDA(cudaMalloc(&c->thr, nq * sizeof(float)));
+    CS_CUDA(cudaMalloc(&c->count, nq * sizeof(unsigned)));
+    CS_CUDA(cudaMalloc(&c->count_saved, nq * sizeof(unsigned)));
+    CS_CUDA(cudaMalloc(&c->cand, nq * BF_CAP * sizeof(uint64_t)));
+    CS_CUDA(cudaMalloc(&c->out, nq * CSGPU_MAX_K * sizeof(uint64_t)));
+    CS_CUDA(cudaMalloc(&c->scalar, 64));
+    CS_CUDA(cudaHostAlloc(&c->q_pin, nq * ix->dim * sizeof(float), cudaHostAllocDefault));
+    CS_CUDA(cudaHostAlloc(&c->out_pin, nq * CSGPU_MAX_K * sizeof(uint64_t) + nq, cudaHostAllocDefault));
+    *out = c;
+    return CSGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// search
+// ---------------------------------------------------------------------------------------------
+static int launch_gemm(const csgpu_index *ix, Shard *sh, Bf16BatchCtx *c, const CUtensorMap &map_q, uint32_t n_qblocks,
+                       uint64_t t0, uint64_t t1)
+{
+    GemmTopkArgs a;
+    a.ids = sh->ids;
+    a.n_rows = sh->n_built;
+    a.tile_begin = t0;
+    a.tile_end = t1;
+    a.n_kchunks = ix->dim / GT_BLOCK_K;
+    a.n_qblocks = n_qblocks;
+    a.thr = c->thr;
+    a.cand = c->cand;
+    a.count = c->count;
+    a.cap = BF_CAP;
+    const size_t q_bytes = (size_t)a.n_kchunks * GT_QCHUNK_BYTES;
+    const size_t avail = 227 * 1024 - 1024 /*alignment slack*/ - 256 /*static*/ - q_bytes;
+    const int stages = (int)std::min<size_t>(4, avail / GT_STAGE_BYTES);
+    if (stages < 2) return fail(CSGPU_ERR_ARG, "dim too large for the bf16 kernel's shared-memory plan");
+    const size_t smem = q_bytes + (size_t)stages * GT_STAGE_BYTES + 1024;
+    const uint64_t n_tiles = t1 - t0;
+    const uint32_t groups = (uint32_t)std::min<uint64_t>(std::max<uint32_t>(sh->sm_count / n_qblocks, 1), n_tiles);
+    const uint32_t grid = groups * n_qblocks;
+    cudaError_t e = cudaSuccess;
+#define CS_GT(S)                                                                                                   \
+    case S:                                                                                                        \
+        e = cudaFuncSetAttribute(gemm_topk_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+        if (e == cudaSuccess) gemm_topk_kernel<S><<<grid, GT_THREADS, smem, c->stream>>>(map_q, sh->map_c, a);     \
+        break;
+    switch (stages) { CS_GT(2) CS_GT(3) CS_GT(4) }
+#undef CS_GT
+    count_launch();
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(e, "gemm_topk_kernel launch", __FILE__, __LINE__);
+    return CSGPU_OK;
+}
+
+static int launch_select(const csgpu_index *ix, Shard *sh, Bf16BatchCtx *c, uint32_t nq_pad, uint32_t nq, uint32_t k, bool final)
+{
+    const bool big = k > 32;
+    const uint32_t kpad = big ? pow2_at_least(k, 64) : 32;
+    const size_t smem = big ? (size_t)2 * SCAN_WARPS * kpad * sizeof(uint64_t) : (size_t)SCAN_WARPS * 32 * sizeof(uint64_t);
+    const uint32_t *zi = final ? ix->zero_ids_dev : nullptr;
+    const uint32_t nz = final ? (uint32_t)ix->zero_ids.size() : 0;
+    cudaError_t e;
+    if (big) {
+        e = cudaFuncSetAttribute(select_candidates_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail_cuda(e, "select attr", __FILE__, __LINE__);
+        select_candidates_kernel<true><<<nq_pad, SCAN_THREADS, smem, c->stream>>>(c->cand, c->count, c->thr, BF_CAP, k, kpad, nq, zi, nz, final ? c->out : nullptr);
+    } else {
+        select_candidates_kernel<false><<<nq_pad, SCAN_THREADS, smem, c->stream>>>(c->cand, c->count, c->thr, BF_CAP, k, kpad, nq, zi, nz, final ? c->out : nullptr);
+    }
+    count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(e, "select_candidates_kernel launch", __FILE__, __LINE__);
+    return CSGPU_OK;
+}
+
+// scan tiles [t0, t1) with the current thresholds; on candidate-buffer overflow roll back and split
+static int run_range(const csgpu_index *ix, Shard *sh, Bf16BatchCtx *c, const CUtensorMap &map_q, uint32_t n_qblocks,
+                     uint32_t nq, uint32_t k, uint64_t t0, uint64_t t1, int depth)
+{
+    const uint32_t nq_pad = n_qblocks * GT_BLOCK_M;
+    CS_CUDA(cudaMemcpyAsync(c->count_saved, c->count, nq_pad * sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
+    CS_CUDA(cudaMemsetAsync(c->scalar, 0, sizeof(unsigned), c->stream));
+    int rc = launch_gemm(ix, sh, c, map_q, n_qblocks, t0, t1);
+    if (rc) return rc;
+    max_count_kernel<<<1, 256, 0, c->stream>>>(c->count, nq_pad, c->scalar);
+    count_launch();
+    unsigned maxc = 0;
+    CS_CUDA(cudaMemcpyAsync(&maxc, c->scalar, sizeof maxc, cudaMemcpyDeviceToHost, c->stream));
+    CS_CUDA(cudaStreamSynchronize(c->stream));
+    if (maxc > BF_CAP) {
+        if (t1 - t0 <= 1 || depth > 40) return fail(CSGPU_ERR_CUDA, "bf16 candidate buffer overflow on a single tile (internal error)");
+        CS_CUDA(cudaMemcpyAsync(c->count, c->count_saved, nq_pad * sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
+        const uint64_t mid = t0 + (t1 - t0) / 2;
+        rc = run_range(ix, sh, c, map_q, n_qblocks, nq, k, t0, mid, depth + 1);
+        if (rc) return rc;
+        return run_range(ix, sh, c, map_q, n_qblocks, nq, k, mid, t1, depth + 1);
+    }
+    return launch_select(ix, sh, c, nq_pad, nq, k, false);
+}
+
+// Up to 1024 queries against one shard; final keys land in c->out [nq][k] (device) .
+static int bf16_search_shard(const csgpu_index *ix, Shard *sh, Bf16BatchCtx *c, const float *q_host, uint32_t nq, uint32_t k)
+{
+    DeviceGuard g(sh->device);
+    const uint32_t n_qblocks = (nq + GT_BLOCK_M - 1) / GT_BLOCK_M;
+    const uint32_t nq_pad = n_qblocks * GT_BLOCK_M;
+    memcpy(c->q_pin, q_host, (size_t)nq * ix->dim * sizeof(float));
+    CS_CUDA(cudaMemcpyAsync(c->q_f32, c->q_pin, (size_t)nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    prep_queries_bf16_kernel<<<(nq_pad * 32 + 255) / 256, 256, 0, c->stream>>>(c->q_f32, nq, ix->dim, reinterpret_cast<__nv_bfloat16 *>(c->q_bf16), nq_pad, c->flags);
+    init_thresholds_kernel<<<(nq_pad + 255) / 256, 256, 0, c->stream>>>(c->thr, c->count, nq, nq_pad);
+    count_launch(2);
+    uint8_t *flags_host = reinterpret_cast<uint8_t *>(c->out_pin) + (size_t)BF_MAX_QBLOCKS * GT_BLOCK_M * CSGPU_MAX_K * sizeof(uint64_t);
+    CS_CUDA(cudaMemcpyAsync(flags_host, c->flags, nq, cudaMemcpyDeviceToHost, c->stream));
+    CS_CUDA(cudaStreamSynchronize(c->stream));
+    for (uint32_t j = 0; j < nq; ++j)
+        if (flags_host[j]) return fail(CSGPU_ERR_ARG, "zero-norm query is not supported on a bf16 index");
+    CUtensorMap map_q;
+    int rc = make_map(&map_q, c->q_bf16, nq_pad, ix->dim, GT_BLOCK_M);
+    if (rc) return rc;
+
+    const uint64_t n_tiles = (sh->n_built + GT_BLOCK_N - 1) / GT_BLOCK_N;
+    // phase 0 lets everything through, so it must fit the buffer on its own: <= CAP/2 rows
+    uint64_t done = 0;
+    uint64_t next = std::max<uint64_t>(1, (BF_CAP / 2) / GT_BLOCK_N);
+    while (done < n_tiles) {
+        const uint64_t t1 = std::min(n_tiles, done + next);
+        rc = run_range(ix, sh, c, map_q, n_qblocks, nq, k, done, t1, 0);
+        if (rc) return rc;
+        done = t1;
+        next = done * (BF_PHASE_GROWTH - 1);   // each phase scans (growth-1) x everything seen so far
+    }
+    return launch_select(ix, sh, c, nq_pad, nq, k, true);
+}
+
+int bf16_search_batch(const csgpu_index *ix, const float *q, uint32_t b, uint32_t k,
+                      uint32_t *out_ids, float *out_dist, uint32_t *out_n)
+{
+    if (ix->shards.size() != 1) return fail(CSGPU_ERR_ARG, "bf16 index: multi-device sharding is not implemented yet");
+    Shard *sh = ix->shards[0];
+    std::lock_guard<std::mutex> lk(sh->bf_mu);   // one bf16 batch at a time per index
+    Bf16BatchCtx *c = nullptr;
+    int rc = bf16_batch_ctx(ix, sh, &c);
+    if (rc) return rc;
+    DeviceGuard g(sh->device);
+    const uint32_t chunk = BF_MAX_QBLOCKS * GT_BLOCK_M;
+    cudaEvent_t e0, e1;
+    CS_CUDA(cudaEventCreate(&e0)); CS_CUDA(cudaEventCreate(&e1));
+    CS_CUDA(cudaEventRecord(e0, c->stream));
+    for (uint32_t j = 0; j < b; j += chunk) {
+        const uint32_t nq = std::min(chunk, b - j);
+        rc = bf16_search_shard(ix, sh, c, q + (size_t)j * ix->dim, nq, k);
+        if (rc) break;
+        CS_CUDA(cudaMemcpyAsync(c->out_pin, c->out, (size_t)nq * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+        CS_CUDA(cudaStreamSynchronize(c->stream));
+        for (uint32_t i = 0; i < nq; ++i)
+            decode_keys(c->out_pin + (size_t)i * k, k, out_ids + (size_t)(j + i) * k, out_dist + (size_t)(j + i) * k, out_n ? out_n + j + i : nullptr);
+    }
+    cudaEventRecord(e1, c->stream);
+    cudaStreamSynchronize(c->stream);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) ix->last_search_us.store(ms * 1000.f);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return rc;
+}
+
+}  // namespace csgpu

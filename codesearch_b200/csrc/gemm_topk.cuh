@@ -1,0 +1,285 @@
+// gemm_topk.cuh — batched search on the opt-in bf16 index: dense Q x C^T on the 5th-gen tensor
+// cores (tcgen05.mma, accumulators in TMEM) with the top-k filter fused into the epilogue.
+// SURVEY.md §8a row A9 / BASELINE config C3 (10M x 384, B = 1024, k = 100). No reference
+// counterpart (the reference has one f32 ANN path, /root/reference/src/vectordb/store.rs:446-459);
+// semantics are the same ranking on bf16-rounded unit vectors, fp32 accumulate.
+//
+// Shapes. One CTA = 128 queries (MMA M = 128, one TMEM lane per query) x a stream of 256-row
+// corpus tiles (MMA N = 256) x K = dim in 64-element chunks (UMMA_K = 16 -> 4 MMAs per chunk).
+//   smem: the CTA's 128 queries, all of K, resident   [dim/64][128 x 64] bf16  (96 KB at D = 384)
+//         ring of STAGES corpus chunks                 [256 x 64] bf16 = 32 KB each
+//         both in the canonical K-major SWIZZLE_128B layout that TMA writes and UMMA reads.
+//   TMEM: 2 accumulator buffers x 256 fp32 columns = all 512 columns (epilogue of tile i overlaps
+//         the MMAs of tile i+1).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer (one elected
+// lane), warps 2-5 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31, i.e. 32 queries).
+//
+// Epilogue = progressive-threshold filter. Each epilogue thread owns ONE query: it holds that
+// query's current threshold distance in a register, reads its lane's 256 scores with tcgen05.ld,
+// and appends (distance, id) keys that pass to the query's candidate buffer in HBM (atomic
+// counter). Between row phases (sizes growing geometrically) a select kernel reduces each buffer
+// to its exact top-k and publishes the new threshold, so after the first phases only
+// ~k * phase_growth rows per query pass. Exactness: the threshold is always the k-th best of a
+// SUBSET of the rows, hence never tighter than the final k-th best; ties pass (<=) and are
+// ordered by the full (distance, id) key in the select kernel. If a buffer overflows (adversarially
+// ordered data) the host halves the phase and retries, which terminates because a phase of
+// <= CAP - k rows cannot overflow.
+//
+// CTA -> work: query block qb = cta % QB, group = cta / QB; the QB CTAs of a group walk the same
+// tiles at the same time, so a corpus tile is read from HBM once and served to the other QB-1
+// CTAs from L2.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "scan_tma.cuh"  // mbarrier helpers
+#include "topk.cuh"
+
+namespace csgpu {
+
+constexpr int GT_BLOCK_M = 128;   // queries per CTA
+constexpr int GT_BLOCK_N = 256;   // corpus rows per tile
+constexpr int GT_BLOCK_K = 64;    // bf16 elements per K chunk (= 128 B = one swizzle row)
+constexpr int GT_UMMA_K = 16;
+constexpr int GT_THREADS = 192;
+constexpr uint32_t GT_STAGE_BYTES = GT_BLOCK_N * GT_BLOCK_K * 2;   // 32 KB
+constexpr uint32_t GT_QCHUNK_BYTES = GT_BLOCK_M * GT_BLOCK_K * 2;  // 16 KB
+
+struct GemmTopkArgs {
+    const uint32_t *ids;       // [n_rows]
+    uint64_t n_rows;           // rows in the matrix (tensor map extent)
+    uint64_t tile_begin, tile_end;  // this phase scans tiles [tile_begin, tile_end)
+    uint32_t n_kchunks;        // dim / 64
+    uint32_t n_qblocks;        // QB
+    const float *thr;          // [QB*128] threshold distance per query (< 0: inactive, +inf: pass all)
+    uint64_t *cand;            // [QB*128][cap] candidate keys
+    unsigned *count;           // [QB*128] entries in cand (may exceed cap => overflow)
+    uint32_t cap;
+};
+
+// ---- tcgen05 wrappers ---------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 x bf16 -> f32, cta_group::1
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
+{
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 2-D TMA tile load (inner coordinate = element column, outer = row), completes on an mbarrier
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int32_t c_inner, int32_t c_outer)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
+        : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major) | SBO>>4 [32,46) = 1024 B (8 rows x 128 B)
+// | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// cute::UMMA::InstrDescriptor: c_format=F32(1) [4,6) | a_format=BF16(1) [7,10) | b_format=BF16(1) [10,13)
+// | a_major=K(0) [15] | b_major=K(0) [16] | N>>3 [17,23) | M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc_bf16_f32(uint32_t M, uint32_t N)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// dynamic smem: [n_kchunks][16 KB] queries | [STAGES][32 KB] corpus ring   (1024-B aligned)
+template <int STAGES>
+__global__ void __launch_bounds__(GT_THREADS, 1)
+gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c, const GemmTopkArgs a)
+{
+    extern __shared__ __align__(1024) unsigned char gt_smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], q_bar, tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // 1024-B alignment of the dynamic region (swizzle atoms are 1024 B)
+    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(gt_smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *q_smem = base;
+    unsigned char *ring = base + (size_t)a.n_kchunks * GT_QCHUNK_BYTES;
+
+    const uint32_t qb = blockIdx.x % a.n_qblocks;
+    const uint32_t group = blockIdx.x / a.n_qblocks;
+    const uint32_t n_groups = gridDim.x / a.n_qblocks;
+    const bool cta_active = group < n_groups;   // leftover CTAs (gridDim % QB) idle
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&q_bar, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (cta_active) {
+        if (warp == 0) {
+            // ================= TMA producer =================
+            if (lane == 0) {
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
+                mbar_expect_tx(&q_bar, a.n_kchunks * GT_QCHUNK_BYTES);
+                for (uint32_t kc = 0; kc < a.n_kchunks; ++kc)
+                    tma_load_2d(q_smem + (size_t)kc * GT_QCHUNK_BYTES, &map_q, &q_bar, (int32_t)(kc * GT_BLOCK_K), (int32_t)(qb * GT_BLOCK_M));
+                uint32_t it = 0;
+                for (uint64_t t = a.tile_begin + group; t < a.tile_end; t += n_groups) {
+                    for (uint32_t kc = 0; kc < a.n_kchunks; ++kc, ++it) {
+                        const int s = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        mbar_expect_tx(&full_bar[s], GT_STAGE_BYTES);
+                        tma_load_2d(ring + (size_t)s * GT_STAGE_BYTES, &map_c, &full_bar[s], (int32_t)(kc * GT_BLOCK_K), (int32_t)(t * GT_BLOCK_N));
+                    }
+                }
+            }
+            __syncwarp();
+        } else if (warp == 1) {
+            // ================= MMA issuer =================
+            if (lane == 0) {
+                constexpr uint32_t idesc = make_idesc_bf16_f32(GT_BLOCK_M, GT_BLOCK_N);
+                mbar_wait(&q_bar, 0);
+                tc_fence_after();
+                uint32_t it = 0, tile_it = 0;
+                for (uint64_t t = a.tile_begin + group; t < a.tile_end; t += n_groups, ++tile_it) {
+                    const uint32_t acc = tile_it & 1;
+                    mbar_wait(&tempty_bar[acc], ((tile_it >> 1) & 1) ^ 1);   // epilogue drained this buffer
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * GT_BLOCK_N;
+                    for (uint32_t kc = 0; kc < a.n_kchunks; ++kc, ++it) {
+                        const int s = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        mbar_wait(&full_bar[s], ph);
+                        tc_fence_after();
+                        const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(q_smem + (size_t)kc * GT_QCHUNK_BYTES));
+                        const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(ring + (size_t)s * GT_STAGE_BYTES));
+#pragma unroll
+                        for (uint32_t k = 0; k < GT_BLOCK_K / GT_UMMA_K; ++k) {
+                            // advance 16 elements = 32 B along K inside the swizzle atom: +2 in (addr >> 4) units
+                            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) ? 1u : 0u);
+                        }
+                        umma_commit(&empty_bar[s]);          // smem slot reusable once these MMAs retire
+                    }
+                    umma_commit(&tfull_bar[acc]);            // accumulator ready for the epilogue
+                }
+            }
+            __syncwarp();
+        } else {
+            // ================= epilogue: one thread = one query =================
+            const uint32_t quarter = warp & 3;                       // TMEM lane quarter this warp may access
+            const uint32_t q_local = quarter * 32 + lane;
+            const uint32_t q_glob = qb * GT_BLOCK_M + q_local;
+            const float thr = a.thr[q_glob];
+            uint64_t *my_cand = a.cand + (size_t)q_glob * a.cap;
+            unsigned *my_count = a.count + q_glob;
+            uint32_t tile_it = 0;
+            for (uint64_t t = a.tile_begin + group; t < a.tile_end; t += n_groups, ++tile_it) {
+                const uint32_t acc = tile_it & 1;
+                mbar_wait(&tfull_bar[acc], (tile_it >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * GT_BLOCK_N;
+                const uint64_t row0 = t * GT_BLOCK_N;
+#pragma unroll 1
+                for (uint32_t c = 0; c < GT_BLOCK_N / 32; ++c) {
+                    float v[32];
+                    tmem_ld32(taddr + c * 32, v);
+                    float best = v[0];
+#pragma unroll
+                    for (int j = 1; j < 32; ++j) best = fmaxf(best, v[j]);
+                    if (fmaf(-0.5f, best, 0.5f) <= thr) {             // rare after the first phases
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float dist = fmaf(-0.5f, v[j], 0.5f);
+                            const uint64_t row = row0 + c * 32 + j;
+                            if (dist <= thr && row < a.n_rows) {
+                                const unsigned pos = atomicAdd(my_count, 1u);
+                                if (pos < a.cap) my_cand[pos] = make_key(dist, a.ids[row]);
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- query prep: fp32 [b][dim] -> unit length -> bf16 [QB*128][dim] (rows >= b zero) -------------
+// flags[q] = 1 if the query has zero norm.
+static __global__ void prep_queries_bf16_kernel(const float *__restrict__ q, uint32_t b, uint32_t dim,
+                                         __nv_bfloat16 *__restrict__ out, uint32_t b_pad, uint8_t *__restrict__ flags)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= b_pad) return;
+    if (w >= b) {
+        for (uint32_t c = lane; c < dim; c += 32) out[(size_t)w * dim + c] = __float2bfloat16(0.f);
+        return;
+    }
+    double ss = 0.0;
+    for (uint32_t c = lane; c < dim; c += 32) { const float x = q[(size_t)w * dim + c]; ss += (double)x * x; }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) ss += __shfl_xor_sync(FULL, ss, m);
+    const bool zero = !(ss > 0.0);
+    const double inv = zero ? 0.0 : 1.0 / sqrt(ss);
+    for (uint32_t c = lane; c < dim; c += 32) out[(size_t)w * dim + c] = __float2bfloat16((float)(q[(size_t)w * dim + c] * inv));
+    if (lane == 0) flags[w] = zero ? 1 : 0;
+}
+
+}  // namespace csgpu

@@ -6,9 +6,12 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "../../include/csgpu.h"
+
+struct csgpu_index;
 
 namespace csgpu {
 
@@ -17,6 +20,15 @@ void set_error(const std::string &msg);
 int fail(int code, const std::string &msg);
 int fail_cuda(cudaError_t e, const char *what, const char *file, int line);
 extern std::atomic<uint64_t> g_kernel_launches;
+
+void count_launch(uint64_t n = 1);
+void decode_keys(const uint64_t *keys, uint32_t k, uint32_t *out_ids, float *out_dist, uint32_t *out_n);
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int d) { cudaGetDevice(&prev); if (prev != d) cudaSetDevice(d); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 #define CS_CUDA(call)                                                                  \
     do {                                                                               \
@@ -43,8 +55,30 @@ struct SearchCtx {
     size_t cand_cap = 0;            // in keys
 };
 
+// Scratch of the bf16 batched path (gemm_topk.cu): one per shard, serialised by Shard::bf_mu.
+struct Bf16BatchCtx {
+    cudaStream_t stream = nullptr;
+    float *q_f32 = nullptr;        // [1024][dim]
+    void *q_bf16 = nullptr;        // [1024][dim] unit-normalised bf16
+    uint8_t *flags = nullptr;      // [1024] zero-norm query flags
+    float *thr = nullptr;          // [1024] threshold distance per query
+    unsigned *count = nullptr, *count_saved = nullptr;
+    uint64_t *cand = nullptr;      // [1024][BF_CAP]
+    uint64_t *out = nullptr;       // [1024][CSGPU_MAX_K]
+    unsigned *scalar = nullptr;
+    float *q_pin = nullptr;
+    uint64_t *out_pin = nullptr;
+};
+
 struct Shard {
     int device = 0;
+    // bf16 index (dtype == CSGPU_DTYPE_BF16): built rows live here, pending rows in `stage` as fp32
+    void *rows_bf16 = nullptr;     // [cap, dim] bf16 unit vectors
+    float *stage = nullptr;        // [stage_cap, dim] fp32, rows appended since the last build
+    uint64_t stage_cap = 0;
+    CUtensorMap map_c;             // TMA map over rows_bf16[0, n_built)
+    Bf16BatchCtx *bf = nullptr;
+    std::mutex bf_mu;
     float *rows = nullptr;     // [cap, dim_pad] fp32; rows [0, n_built) are unit vectors
     uint32_t *ids = nullptr;   // [cap]
     uint8_t *status = nullptr; // [cap] ROW_* (all ROW_OK in [0, n_built) after build)
@@ -57,6 +91,16 @@ struct Shard {
     std::vector<SearchCtx *> free_ctx;
     std::vector<SearchCtx *> all_ctx;
 };
+
+// gemm_topk.cu (bf16 index)
+bool bf16_dim_supported(uint32_t dim);
+int bf16_reserve_rows(const csgpu_index *ix, Shard *sh, uint64_t rows);
+int bf16_reserve_stage(const csgpu_index *ix, Shard *sh, uint64_t pending);
+int bf16_convert_pending(const csgpu_index *ix, Shard *sh);
+int bf16_after_build(const csgpu_index *ix, Shard *sh);
+void bf16_free_batch_ctx(Shard *sh);
+int bf16_search_batch(const csgpu_index *ix, const float *q, uint32_t b, uint32_t k,
+                      uint32_t *out_ids, float *out_dist, uint32_t *out_n);
 
 // scan_multi.cu
 struct MultiArgs;

@@ -32,7 +32,7 @@ __device__ __forceinline__ float synth_val(uint32_t x)
 }
 
 // One thread per float4. rows: [n, dim4] float4, row-major.
-__global__ void synth_rows_kernel(float4 *__restrict__ rows, uint32_t *__restrict__ ids, uint64_t seed,
+static __global__ void synth_rows_kernel(float4 *__restrict__ rows, uint32_t *__restrict__ ids, uint64_t seed,
                                   uint64_t first_row, uint64_t n, uint32_t dim4, uint32_t id_base)
 {
     const uint64_t total = n * dim4;
@@ -54,7 +54,7 @@ enum : uint8_t { ROW_OK = 0, ROW_DEAD = 1, ROW_ZERO = 2, ROW_NONFINITE = 3 };
 // One warp per row: unit-normalise rows [first, first+n) in place. The norm is accumulated in
 // f64 (build is a one-off pass; B200 has the f64 rate to spare) so stored unit rows are the
 // correctly-rounded v/|v| to within 1 ulp. Zero-norm and non-finite rows are flagged, not scaled.
-__global__ void normalise_rows_kernel(float4 *__restrict__ rows, uint8_t *__restrict__ status,
+static __global__ void normalise_rows_kernel(float4 *__restrict__ rows, uint8_t *__restrict__ status,
                                       uint64_t first, uint64_t n, uint32_t dim4)
 {
     const int lane = threadIdx.x & 31;
@@ -88,7 +88,7 @@ __global__ void normalise_rows_kernel(float4 *__restrict__ rows, uint8_t *__rest
 
 // Marks rows [0, n) whose id is in the sorted list `kill` (ascending, n_kill entries) as ROW_DEAD.
 // counts[0] += rows newly killed.
-__global__ void mark_dead_kernel(const uint32_t *__restrict__ ids, uint8_t *__restrict__ status, uint64_t n,
+static __global__ void mark_dead_kernel(const uint32_t *__restrict__ ids, uint8_t *__restrict__ status, uint64_t n,
                                  const uint32_t *__restrict__ kill, uint32_t n_kill,
                                  unsigned long long *__restrict__ counts)
 {
@@ -110,7 +110,7 @@ __global__ void mark_dead_kernel(const uint32_t *__restrict__ ids, uint8_t *__re
 // Stable compaction, one chunk at a time through a bounce buffer (dst <= src always, so moving
 // chunk c never overwrites rows of chunks > c). dst_index[i] = destination row of row (first+i)
 // or ~0ull if dropped; one warp per row.
-__global__ void gather_rows_kernel(const float4 *__restrict__ src, float4 *__restrict__ dst,
+static __global__ void gather_rows_kernel(const float4 *__restrict__ src, float4 *__restrict__ dst,
                                    const uint64_t *__restrict__ dst_index, uint64_t n, uint32_t dim4,
                                    uint64_t src_first, uint64_t dst_base_sub)
 {

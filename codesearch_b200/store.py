@@ -108,7 +108,7 @@ def _f32(a) -> np.ndarray:
 
 
 class VectorStore:
-    def __init__(self, dimensions: int, devices: Sequence[int] | None = None, db_path=None):
+    def __init__(self, dimensions: int, devices: Sequence[int] | None = None, db_path=None, dtype: str = "fp32"):
         self._lib = _lib.load()
         self.dimensions = int(dimensions)
         self.db_path = db_path
@@ -120,12 +120,15 @@ class VectorStore:
         if devices is not None:
             n = len(devices)
             devs = (ctypes.c_int32 * n)(*devices)
-        _lib.check(self._lib.csgpu_create(ctypes.byref(self._h), self.dimensions, _lib.DTYPE_F32, devs, n))
+        # CODESEARCH_GPU_INDEX_DTYPE=fp32|bf16 in the reference's env-knob style; bf16 is opt-in
+        self.dtype = dtype
+        code = {"fp32": _lib.DTYPE_F32, "bf16": _lib.DTYPE_BF16}[dtype]
+        _lib.check(self._lib.csgpu_create(ctypes.byref(self._h), self.dimensions, code, devs, n))
 
     # -- lifecycle ---------------------------------------------------------------------------
     @classmethod
-    def new(cls, db_path, dimensions: int, devices: Sequence[int] | None = None) -> "VectorStore":
-        return cls(dimensions, devices=devices, db_path=db_path)
+    def new(cls, db_path, dimensions: int, devices: Sequence[int] | None = None, dtype: str = "fp32") -> "VectorStore":
+        return cls(dimensions, devices=devices, db_path=db_path, dtype=dtype)
 
     def close(self) -> None:
         if self._h:

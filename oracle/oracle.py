@@ -262,6 +262,34 @@ def np_search(rows, q, k, ids=None, allowed=None):
     return ids[order], d32[order], d64[order]
 
 
+def bf16_round(x: np.ndarray) -> np.ndarray:
+    """float32 -> nearest bfloat16 (round to nearest even), returned as float32."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + ((u >> np.uint64(16)) & np.uint64(1)) + np.uint64(0x7FFF)) & np.uint64(0xFFFF0000)
+    return u.astype(np.uint32).view(np.float32).reshape(np.shape(x))
+
+
+def np_search_bf16(rows, q, k, ids=None):
+    """Restatement of the opt-in bf16 index (no reference counterpart): rows and
+    query are unit-normalised (f64 norm) and rounded f32 -> bf16; distance = (1 - dot)/2 with the dot
+    product of the ROUNDED vectors taken exactly (f64), NOT re-normalised. Ascending (f32 distance, id).
+    Returns (ids, dist32, dist64)."""
+    rows = np.asarray(rows, dtype=np.float32)
+    q = np.asarray(q, dtype=np.float32)
+    n = rows.shape[0]
+    ids = np.arange(n, dtype=np.uint32) if ids is None else np.asarray(ids, dtype=np.uint32)
+    r64 = rows.astype(np.float64)
+    rn = np.sqrt(np.einsum("ij,ij->i", r64, r64))
+    keep = rn > 0
+    ru = bf16_round((r64 / np.where(keep, rn, 1.0)[:, None]).astype(np.float32)).astype(np.float64)
+    q64 = q.astype(np.float64)
+    qu = bf16_round((q64 / np.sqrt(q64 @ q64)).astype(np.float32)).astype(np.float64)
+    d64 = np.where(keep, (1.0 - ru @ qu) / 2.0, 0.0)
+    d32 = d64.astype(np.float32)
+    order = np.lexsort((ids, d32))[:k]
+    return ids[order], d32[order], d64[order]
+
+
 def score_from_distance(distance):
     """store.rs:478."""
     return np.float32(1.0) - np.asarray(distance, dtype=np.float32)

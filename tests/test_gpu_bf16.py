@@ -1,0 +1,139 @@
+"""Opt-in bf16 index + tcgen05/TMEM batched kernel (BASELINE config C3). GPU only.
+
+There is no reference counterpart for this variant, so the bar is the one the north star states:
+  * against the bf16 restatement (oracle.np_search_bf16: same rounded unit vectors, exact dot):
+    ids equal except inside near-ties of < 3e-6 (tensor-core fp32 accumulation order), |d| <= 1e-5;
+  * against the fp32 exact oracle: ids NOT required exact; |distance - fp32 distance| <= 2e-3
+    (worst case 2*2^-9 + 2^-18 on cos, halved; typical ~4e-5) and recall@k is reported/asserted.
+"""
+import numpy as np
+import pytest
+
+from parity import SCORE_TOL
+
+pytestmark = pytest.mark.gpu
+
+TIE_EPS_BF16 = 3e-6
+BF16_VS_FP32_TOL = 2e-3
+
+
+@pytest.fixture(scope="module")
+def cs():
+    import codesearch_b200 as m
+    m.load_library()
+    return m
+
+
+def make_bf16_store(cs, rows, ids=None):
+    st = cs.VectorStore.new(None, rows.shape[1], dtype="bf16")
+    st.append_rows(rows, np.arange(rows.shape[0], dtype=np.uint32) if ids is None else ids)
+    st.build_index()
+    return st
+
+
+def check_bf16(gi, gd, oi, od, o64, k_eff):
+    assert len(gi) == k_eff and len(set(gi.tolist())) == k_eff
+    for i in range(1, k_eff):
+        assert (gd[i - 1], gi[i - 1]) < (gd[i], gi[i])
+    d64 = {int(i): float(d) for i, d in zip(oi, o64)}
+    swaps = 0
+    for i in range(k_eff):
+        g = int(gi[i])
+        assert g in d64, f"rank {i}: id {g} not in the bf16 oracle's top-{len(oi)}"
+        assert abs(float(gd[i]) - d64[g]) <= SCORE_TOL
+        if g != int(oi[i]):
+            assert abs(d64[g] - float(o64[i])) < TIE_EPS_BF16
+            swaps += 1
+    return swaps
+
+
+@pytest.mark.parametrize("n,d,b,k", [
+    (256, 64, 1, 10), (1000, 384, 3, 10), (5000, 384, 128, 100), (20000, 384, 130, 100),
+    (20000, 384, 1, 10), (30000, 128, 64, 32), (30000, 256, 200, 50), (9000, 512, 129, 200),
+    (70000, 384, 257, 100), (300, 384, 5, 1000),
+])
+def test_bf16_batch_parity(cs, oracle, n, d, b, k):
+    rng = np.random.default_rng(n + 3 * d + 5 * b + 7 * k)
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    ids = rng.permutation(n * 2)[:n].astype(np.uint32)
+    st = make_bf16_store(cs, rows, ids)
+    qs = rng.standard_normal((b, d)).astype(np.float32)
+    oi, od, on = st.search_batch_ids(qs, k)
+    k_eff = min(k, n)
+    for j in list(range(min(b, 6))) + [b - 1]:
+        assert on[j] == k_eff
+        ri, rd, r64 = oracle.np_search_bf16(rows, qs[j], k + 16, ids=ids)
+        check_bf16(oi[j, :k_eff], od[j, :k_eff], ri, rd, r64, k_eff)
+        # against the fp32 exact ranking: bounded distance error, high recall
+        fi, fd, _ = oracle.np_search(rows, qs[j], k, ids=ids)
+        f = dict(zip(fi.tolist(), fd.tolist()))
+        common = [i for i in oi[j, :k_eff].tolist() if i in f]
+        assert len(common) / k_eff >= 0.8
+        for i, dd in zip(oi[j, :k_eff].tolist(), od[j, :k_eff].tolist()):
+            if i in f:
+                assert abs(dd - f[i]) <= BF16_VS_FP32_TOL
+    # single-query entry point routes to the same kernel
+    gi, gd = st.search_ids(qs[0], k)
+    assert np.array_equal(gi, oi[0, :k_eff]) and np.array_equal(gd, od[0, :k_eff])
+
+
+def test_bf16_sorted_corpus_overflow_path(cs, oracle):
+    """Adversarial order: rows sorted so that every later row beats the threshold -> candidate buffers
+    overflow, the host halves the phase and retries; the result must still be exact."""
+    rng = np.random.default_rng(3)
+    n, d, k = 60000, 128, 10
+    q = rng.standard_normal(d).astype(np.float32)
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    cos = (rows @ q) / np.linalg.norm(rows, axis=1)
+    rows = rows[np.argsort(cos)]                      # ascending similarity: best rows last
+    st = make_bf16_store(cs, rows)
+    oi, od, on = st.search_batch_ids(q[None], k)
+    ri, rd, r64 = oracle.np_search_bf16(rows, q, k + 16)
+    check_bf16(oi[0], od[0], ri, rd, r64, k)
+
+
+def test_bf16_lifecycle_and_errors(cs, oracle):
+    rng = np.random.default_rng(4)
+    rows = rng.standard_normal((3000, 384)).astype(np.float32)
+    rows[17] = 0.0
+    st = cs.VectorStore.new(None, 384, dtype="bf16")
+    with pytest.raises(cs.CsgpuError) as e:
+        st.search_ids(rows[0], 5)
+    assert e.value.code == 2
+    st.append_rows(rows[:2000], np.arange(2000, dtype=np.uint32))
+    st.build_index()
+    assert st.delete_chunks([5, 6, 7]) == 3
+    st.append_rows(rows[2000:], np.arange(2000, 3000, dtype=np.uint32))
+    assert not st.is_indexed()
+    st.build_index()
+    s = st.device_stats()
+    assert s.live_rows == 2997 and s.zero_norm_rows == 1 and s.dtype == 1
+    keep = np.ones(3000, bool); keep[[5, 6, 7]] = False
+    q = rng.standard_normal(384).astype(np.float32)
+    gi, gd = st.search_ids(q, 20)
+    ri, rd, r64 = oracle.np_search_bf16(rows[keep], q, 36, ids=np.arange(3000, dtype=np.uint32)[keep])
+    assert gi[0] == 17 and gd[0] == 0.0                       # zero-norm row: distance 0.0
+    check_bf16(gi, gd, ri, rd, r64, 20)
+    with pytest.raises(cs.CsgpuError):
+        cs.VectorStore.new(None, 100, dtype="bf16")           # dim % 64 != 0
+    with pytest.raises(cs.CsgpuError):
+        st.search_ids(np.zeros(384, np.float32), 5)           # zero-norm query unsupported on bf16
+
+
+def test_bf16_recall_reported(cs, oracle, capsys):
+    n, d, b, k = 200_000, 384, 64, 100
+    st = cs.VectorStore.new(None, d, dtype="bf16")
+    st.append_synthetic(1234, 0, n)
+    st.build_index()
+    rows = oracle.synth_rows(1234, 0, n, d)
+    qs = oracle.synth_rows(4321, 0, b, d)
+    oi, od, on = st.search_batch_ids(qs, k)
+    rec, err = [], []
+    for j in range(b):
+        fi, fd, _ = oracle.search(rows, qs[j], k)
+        f = dict(zip(fi.tolist(), fd.tolist()))
+        rec.append(len(set(fi.tolist()) & set(oi[j].tolist())) / k)
+        err += [abs(dd - f[i]) for i, dd in zip(oi[j].tolist(), od[j].tolist()) if i in f]
+    print(f"bf16 recall@{k} vs fp32 exact: mean {np.mean(rec):.4f} min {np.min(rec):.2f}; "
+          f"|d_bf16 - d_fp32| mean {np.mean(err):.2e} max {np.max(err):.2e}")
+    assert np.mean(rec) >= 0.9 and np.max(err) <= BF16_VS_FP32_TOL
