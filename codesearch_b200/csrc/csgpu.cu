@@ -38,6 +38,7 @@ void count_launch(uint64_t n) { g_kernel_launches.fetch_add(n, std::memory_order
 // ---------------------------------------------------------------------------------------
 constexpr uint32_t MAX_GRID = 148 * 4;   // upper bound on persistent grid size we ever launch
 constexpr uint32_t MAX_BATCH = 16;       // queries per multi-query scan
+constexpr uint32_t GEMM_MIN_BATCH = 40;  // csgpu_search_batch switches to the SIMT GEMM path from here
 
 static int ctx_create(const csgpu_index *ix, Shard *sh, SearchCtx **out)
 {
@@ -619,7 +620,7 @@ void csgpu_destroy(csgpu_index *ix)
     for (Shard *sh : ix->shards) {
         DeviceGuard dg(sh->device);
         for (SearchCtx *c : sh->all_ctx) ctx_destroy(c);
-        bf16_free_batch_ctx(sh);
+        batch_free_ctx(sh);
         cudaFree(sh->rows_bf16); cudaFree(sh->stage);
         cudaFree(sh->rows); cudaFree(sh->ids); cudaFree(sh->status);
         if (sh->stream) cudaStreamDestroy(sh->stream);
@@ -781,8 +782,7 @@ int csgpu_build(csgpu_index *ix)
     }
     int rc = upload_zero_ids(ix);
     if (rc) return rc;
-    if (ix->dtype == CSGPU_DTYPE_BF16)
-        for (Shard *sh : ix->shards) if ((rc = bf16_after_build(ix, sh))) return rc;
+    for (Shard *sh : ix->shards) if ((rc = batch_after_build(ix, sh))) return rc;
     ix->tombstones = 0;
     ix->built = true;
     return CSGPU_OK;
@@ -795,7 +795,7 @@ int csgpu_clear(csgpu_index *ix)
         DeviceGuard dg(sh->device);
         cudaFree(sh->rows); cudaFree(sh->ids); cudaFree(sh->status);
         cudaFree(sh->rows_bf16); cudaFree(sh->stage);
-        sh->rows_bf16 = nullptr; sh->stage = nullptr; sh->stage_cap = 0;
+        sh->rows_bf16 = nullptr; sh->stage = nullptr; sh->stage_cap = 0; sh->map_valid = false;
         sh->rows = nullptr; sh->ids = nullptr; sh->status = nullptr;
         sh->n_built = sh->n_total = sh->cap = 0;
     }
@@ -815,7 +815,7 @@ int csgpu_search(const csgpu_index *ix, const float *q, uint32_t q_len, uint32_t
     if (rc) return rc;
     if (!all_finite(q, q_len)) return fail(CSGPU_ERR_ARG, "query contains NaN/Inf");
     if (k == 0) return CSGPU_OK;
-    if (ix->dtype == CSGPU_DTYPE_BF16) return bf16_search_batch(ix, q, 1, k, out_ids, out_dist, out_n);
+    if (ix->dtype == CSGPU_DTYPE_BF16) return batch_search(ix, q, 1, k, out_ids, out_dist, out_n, nullptr);
     return search_one(ix, q, k, nullptr, 0, out_ids, out_dist, out_n);
 }
 
@@ -842,7 +842,19 @@ int csgpu_search_batch(const csgpu_index *ix, const float *q, uint32_t q_len, ui
     if (rc) return rc;
     if (!all_finite(q, q_len * b)) return fail(CSGPU_ERR_ARG, "query contains NaN/Inf");
     if (k == 0 || b == 0) return CSGPU_OK;
-    if (ix->dtype == CSGPU_DTYPE_BF16) return bf16_search_batch(ix, q, b, k, out_ids, out_dist, out_n);
+    if (ix->dtype == CSGPU_DTYPE_BF16) return batch_search(ix, q, b, k, out_ids, out_dist, out_n, nullptr);
+    // large batches: register-tiled fp32 SIMT GEMM + fused threshold filter (gemm_simt.cuh). It pads to 128-query
+    // blocks, so below ~40 queries the HBM-bound multi-query scan (8 queries per pass) is faster.
+    if (b >= GEMM_MIN_BATCH && batch_gemm_available(ix)) {
+        std::vector<uint32_t> zero_q;
+        rc = batch_search(ix, q, b, k, out_ids, out_dist, out_n, &zero_q);
+        for (size_t z = 0; z < zero_q.size() && !rc; ++z) {   // zero-norm queries: distance 0.0 everywhere (scan kernel)
+            const uint32_t j = zero_q[z];
+            rc = search_one(ix, q + (size_t)j * q_len, k, nullptr, 0, out_ids + (size_t)j * k, out_dist + (size_t)j * k,
+                            out_n ? out_n + j : nullptr);
+        }
+        return rc;
+    }
     // chunks of up to 8 queries share ONE pass over the corpus (scan_multi.cuh); leftovers of one query,
     // k > 256 or dims that are not a multiple of 128 take the single-query kernel.
     const uint32_t MQ = multi_scan_max_queries();

@@ -1,11 +1,15 @@
-// gemm_topk.cu — bf16 index: storage hooks, TMA tensor maps, the phase loop around
-// gemm_topk_kernel (tcgen05) and the per-query exact select kernel. See gemm_topk.cuh for the design.
+// gemm_topk.cu — the batched search path (BASELINE config C3): TMA tensor maps, the phase loop around the
+// GEMM-shaped kernels and the per-query exact select kernel. Two contraction kernels share it:
+//   fp32 index (default): gemm_simt_topk_kernel  (gemm_simt.cuh, register-tiled FP32 SIMT)
+//   bf16 index (opt-in) : gemm_topk_kernel       (gemm_topk.cuh, tcgen05 / TMEM)
+// plus the bf16 index's storage hooks. See gemm_topk.cuh for the progressive-threshold design.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <limits>
 
 #include "index.h"
+#include "gemm_simt.cuh"
 #include "gemm_topk.cuh"
 #include "scan.cuh"
 #include "synth.cuh"
@@ -19,9 +23,14 @@ constexpr uint32_t BF_PHASE_GROWTH = 8;
 // ---------------------------------------------------------------------------------------------
 // kernels local to this file
 // ---------------------------------------------------------------------------------------------
+// One CTA per query: candidate buffer -> exact top-k (ascending (distance, id)) written back to the
+// front of the buffer, new threshold published. Entries [0, n_done[q]) are survivors of earlier
+// selects and already carry chunk ids; entries beyond carry ROW indices (the GEMM epilogues do no
+// dependent loads) and get ids[row] swapped in here, lanes in parallel.
 template <bool BIG>
 __global__ void __launch_bounds__(SCAN_THREADS, 1)
-select_candidates_kernel(uint64_t *__restrict__ cand, unsigned *__restrict__ count, float *__restrict__ thr,
+select_candidates_kernel(uint64_t *__restrict__ cand, unsigned *__restrict__ count, const unsigned *__restrict__ n_done,
+                         float *__restrict__ thr, const uint32_t *__restrict__ ids,
                          uint32_t cap, uint32_t k, uint32_t kpad, uint32_t n_active,
                          const uint32_t *__restrict__ zero_ids, uint32_t n_zero, uint64_t *__restrict__ final_out)
 {
@@ -38,8 +47,13 @@ select_candidates_kernel(uint64_t *__restrict__ cand, unsigned *__restrict__ cou
     else sel.init(k);
     uint64_t *mine = cand + (size_t)q * cap;
     const uint32_t n = min(count[q], cap);
+    const uint32_t done = min(n_done[q], n);
     for (uint32_t b = warp * 32; b < n; b += SCAN_WARPS * 32) {
-        const uint64_t key = (b + lane < n) ? mine[b + lane] : KEY_EMPTY;
+        uint64_t key = KEY_EMPTY;
+        if (b + lane < n) {
+            key = mine[b + lane];
+            if (b + lane >= done) key = (key & 0xFFFFFFFF00000000ull) | ids[(uint32_t)key];
+        }
         offer_lane_keys(sel, key, lane);
     }
     if (final_out != nullptr && warp == 0 && n_zero) {   // zero-norm rows: distance 0.0 (arroy pn*qn == 0)
@@ -125,24 +139,26 @@ static EncodeTiledFn encode_fn()
     return fn;
 }
 
-// [rows][dim] bf16 row-major, box = [box_rows][64], 128-byte swizzle
-static int make_map(CUtensorMap *map, const void *base, uint64_t rows, uint32_t dim, uint32_t box_rows)
+// [rows][cols] row-major matrix of 2-byte (bf16) or 4-byte (fp32) elements with a row pitch of `cols` elements;
+// box = [box_rows][128 bytes], 128-byte swizzle; out-of-bounds elements read as zero.
+static int make_map(CUtensorMap *map, const void *base, uint64_t rows, uint32_t cols, uint32_t box_rows, bool f32)
 {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(CSGPU_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable in this driver");
-    const cuuint64_t gdim[2] = {dim, std::max<uint64_t>(rows, 1)};
-    const cuuint64_t gstride[1] = {(cuuint64_t)dim * 2};
-    const cuuint32_t box[2] = {GT_BLOCK_K, box_rows};
+    const uint32_t esz = f32 ? 4 : 2;
+    const cuuint64_t gdim[2] = {cols, std::max<uint64_t>(rows, 1)};
+    const cuuint64_t gstride[1] = {(cuuint64_t)cols * esz};
+    const cuuint32_t box[2] = {128 / esz, box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base),
+                    gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(CSGPU_ERR_CUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
     return CSGPU_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
-// storage hooks (called from csgpu.cu when ix->dtype == BF16)
+// storage hooks (called from csgpu.cu)
 // ---------------------------------------------------------------------------------------------
 bool bf16_dim_supported(uint32_t dim) { return dim % 64 == 0 && dim >= 64 && dim <= 512; }
 
@@ -204,34 +220,47 @@ int bf16_convert_pending(const csgpu_index *ix, Shard *sh)
     return CSGPU_OK;
 }
 
-int bf16_after_build(const csgpu_index *ix, Shard *sh)
+// (re)encode the TMA map over the shard's built rows; the base pointer can move at every reserve
+int batch_after_build(const csgpu_index *ix, Shard *sh)
 {
-    return make_map(&sh->map_c, sh->rows_bf16 ? sh->rows_bf16 : (void *)sh->ids, sh->n_built, ix->dim, GT_BLOCK_N);
+    sh->map_valid = false;
+    if (ix->dtype == CSGPU_DTYPE_BF16) {
+        int rc = make_map(&sh->map_c, sh->rows_bf16 ? sh->rows_bf16 : (void *)sh->ids, sh->n_built, ix->dim, GT_BLOCK_N, false);
+        if (rc) return rc;
+    } else {
+        if (!batch_f32_dim_supported(ix->dim_pad) || sh->rows == nullptr) return CSGPU_OK;
+        int rc = make_map(&sh->map_c, sh->rows, sh->n_built, ix->dim_pad, GS_BN, true);
+        if (rc) return rc;
+    }
+    sh->map_valid = true;
+    return CSGPU_OK;
 }
 
-void bf16_free_batch_ctx(Shard *sh)
+bool batch_f32_dim_supported(uint32_t dim_pad) { return dim_pad >= GS_BK; }
+
+void batch_free_ctx(Shard *sh)
 {
-    if (!sh->bf) return;
+    if (!sh->batch) return;
     DeviceGuard g(sh->device);
-    Bf16BatchCtx *c = sh->bf;
+    BatchCtx *c = sh->batch;
     if (c->stream) cudaStreamDestroy(c->stream);
-    cudaFree(c->q_f32); cudaFree(c->q_bf16); cudaFree(c->flags); cudaFree(c->thr); cudaFree(c->count); cudaFree(c->count_saved);
+    cudaFree(c->q_f32); cudaFree(c->q_prep); cudaFree(c->flags); cudaFree(c->thr); cudaFree(c->count); cudaFree(c->count_saved);
     cudaFree(c->cand); cudaFree(c->out); cudaFree(c->scalar);
     cudaFreeHost(c->q_pin); cudaFreeHost(c->out_pin);
     delete c;
-    sh->bf = nullptr;
+    sh->batch = nullptr;
 }
 
-static int bf16_batch_ctx(const csgpu_index *ix, Shard *sh, Bf16BatchCtx **out)
+static int batch_ctx(const csgpu_index *ix, Shard *sh, BatchCtx **out)
 {
-    if (sh->bf) { *out = sh->bf; return CSGPU_OK; }
+    if (sh->batch) { *out = sh->batch; return CSGPU_OK; }
     DeviceGuard g(sh->device);
-    Bf16BatchCtx *c = new Bf16BatchCtx();
-    sh->bf = c;
+    BatchCtx *c = new BatchCtx();
+    sh->batch = c;
     const size_t nq = (size_t)BF_MAX_QBLOCKS * GT_BLOCK_M;
     CS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CS_CUDA(cudaMalloc(&c->q_f32, nq * ix->dim * sizeof(float)));
-    CS_CUDA(cudaMalloc(&c->q_bf16, nq * ix->dim * 2));
+    CS_CUDA(cudaMalloc(&c->q_prep, nq * ix->dim_pad * sizeof(float)));   // bf16 uses half of it
     CS_CUDA(cudaMalloc(&c->flags, nq));
     CS_CUDA(cudaMalloc(&c->thr, nq * sizeof(float)));
     CS_CUDA(cudaMalloc(&c->count, nq * sizeof(unsigned)));
@@ -248,43 +277,53 @@ static int bf16_batch_ctx(const csgpu_index *ix, Shard *sh, Bf16BatchCtx **out)
 // ---------------------------------------------------------------------------------------------
 // search
 // ---------------------------------------------------------------------------------------------
-static int launch_gemm(const csgpu_index *ix, Shard *sh, Bf16BatchCtx *c, const CUtensorMap &map_q, uint32_t n_qblocks,
+static uint32_t tile_rows_of(const csgpu_index *ix) { return ix->dtype == CSGPU_DTYPE_BF16 ? GT_BLOCK_N : GS_BN; }
+
+static int launch_gemm(const csgpu_index *ix, Shard *sh, BatchCtx *c, const CUtensorMap &map_q, uint32_t n_qblocks,
                        uint64_t t0, uint64_t t1)
 {
     GemmTopkArgs a;
-    a.ids = sh->ids;
     a.n_rows = sh->n_built;
     a.tile_begin = t0;
     a.tile_end = t1;
-    a.n_kchunks = ix->dim / GT_BLOCK_K;
     a.n_qblocks = n_qblocks;
     a.thr = c->thr;
     a.cand = c->cand;
     a.count = c->count;
     a.cap = BF_CAP;
-    const size_t q_bytes = (size_t)a.n_kchunks * GT_QCHUNK_BYTES;
-    const size_t avail = 227 * 1024 - 1024 /*alignment slack*/ - 256 /*static*/ - q_bytes;
-    const int stages = (int)std::min<size_t>(4, avail / GT_STAGE_BYTES);
-    if (stages < 2) return fail(CSGPU_ERR_ARG, "dim too large for the bf16 kernel's shared-memory plan");
-    const size_t smem = q_bytes + (size_t)stages * GT_STAGE_BYTES + 1024;
     const uint64_t n_tiles = t1 - t0;
-    const uint32_t groups = (uint32_t)std::min<uint64_t>(std::max<uint32_t>(sh->sm_count / n_qblocks, 1), n_tiles);
-    const uint32_t grid = groups * n_qblocks;
     cudaError_t e = cudaSuccess;
+    if (ix->dtype == CSGPU_DTYPE_BF16) {
+        a.n_kchunks = ix->dim / GT_BLOCK_K;
+        const size_t q_bytes = (size_t)a.n_kchunks * GT_QCHUNK_BYTES;
+        const size_t avail = 227 * 1024 - 1024 /*alignment slack*/ - 256 /*static*/ - q_bytes;
+        const int stages = (int)std::min<size_t>(4, avail / GT_STAGE_BYTES);
+        if (stages < 2) return fail(CSGPU_ERR_ARG, "dim too large for the bf16 kernel's shared-memory plan");
+        const size_t smem = q_bytes + (size_t)stages * GT_STAGE_BYTES + 1024;
+        const uint32_t groups = (uint32_t)std::min<uint64_t>(std::max<uint32_t>(sh->sm_count / n_qblocks, 1), n_tiles);
+        const uint32_t grid = groups * n_qblocks;
 #define CS_GT(S)                                                                                                   \
     case S:                                                                                                        \
         e = cudaFuncSetAttribute(gemm_topk_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
         if (e == cudaSuccess) gemm_topk_kernel<S><<<grid, GT_THREADS, smem, c->stream>>>(map_q, sh->map_c, a);     \
         break;
-    switch (stages) { CS_GT(2) CS_GT(3) CS_GT(4) }
+        switch (stages) { CS_GT(2) CS_GT(3) CS_GT(4) }
 #undef CS_GT
+    } else {
+        a.n_kchunks = (ix->dim_pad + GS_BK - 1) / GS_BK;
+        constexpr int STAGES = 6;
+        const size_t smem = (size_t)STAGES * GS_STAGE_BYTES + 1024;
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sh->sm_count, n_tiles * n_qblocks);
+        e = cudaFuncSetAttribute(gemm_simt_topk_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) gemm_simt_topk_kernel<STAGES><<<grid, GS_THREADS, smem, c->stream>>>(map_q, sh->map_c, a);
+    }
     count_launch();
     if (e == cudaSuccess) e = cudaGetLastError();
-    if (e != cudaSuccess) return fail_cuda(e, "gemm_topk_kernel launch", __FILE__, __LINE__);
+    if (e != cudaSuccess) return fail_cuda(e, "gemm top-k kernel launch", __FILE__, __LINE__);
     return CSGPU_OK;
 }
 
-static int launch_select(const csgpu_index *ix, Shard *sh, Bf16BatchCtx *c, uint32_t nq_pad, uint32_t nq, uint32_t k, bool final)
+static int launch_select(const csgpu_index *ix, Shard *sh, BatchCtx *c, uint32_t nq_pad, uint32_t nq, uint32_t k, bool final)
 {
     const bool big = k > 32;
     const uint32_t kpad = big ? pow2_at_least(k, 64) : 32;
@@ -295,9 +334,9 @@ static int launch_select(const csgpu_index *ix, Shard *sh, Bf16BatchCtx *c, uint
     if (big) {
         e = cudaFuncSetAttribute(select_candidates_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail_cuda(e, "select attr", __FILE__, __LINE__);
-        select_candidates_kernel<true><<<nq_pad, SCAN_THREADS, smem, c->stream>>>(c->cand, c->count, c->thr, BF_CAP, k, kpad, nq, zi, nz, final ? c->out : nullptr);
+        select_candidates_kernel<true><<<nq_pad, SCAN_THREADS, smem, c->stream>>>(c->cand, c->count, c->count_saved, c->thr, sh->ids, BF_CAP, k, kpad, nq, zi, nz, final ? c->out : nullptr);
     } else {
-        select_candidates_kernel<false><<<nq_pad, SCAN_THREADS, smem, c->stream>>>(c->cand, c->count, c->thr, BF_CAP, k, kpad, nq, zi, nz, final ? c->out : nullptr);
+        select_candidates_kernel<false><<<nq_pad, SCAN_THREADS, smem, c->stream>>>(c->cand, c->count, c->count_saved, c->thr, sh->ids, BF_CAP, k, kpad, nq, zi, nz, final ? c->out : nullptr);
     }
     count_launch();
     e = cudaGetLastError();
@@ -305,8 +344,9 @@ static int launch_select(const csgpu_index *ix, Shard *sh, Bf16BatchCtx *c, uint
     return CSGPU_OK;
 }
 
-// scan tiles [t0, t1) with the current thresholds; on candidate-buffer overflow roll back and split
-static int run_range(const csgpu_index *ix, Shard *sh, Bf16BatchCtx *c, const CUtensorMap &map_q, uint32_t n_qblocks,
+// scan tiles [t0, t1) with the current thresholds; on candidate-buffer overflow roll back and split.
+// count_saved = entries per query before this range = the survivors of the previous select (they carry ids).
+static int run_range(const csgpu_index *ix, Shard *sh, BatchCtx *c, const CUtensorMap &map_q, uint32_t n_qblocks,
                      uint32_t nq, uint32_t k, uint64_t t0, uint64_t t1, int depth)
 {
     const uint32_t nq_pad = n_qblocks * GT_BLOCK_M;
@@ -320,7 +360,7 @@ static int run_range(const csgpu_index *ix, Shard *sh, Bf16BatchCtx *c, const CU
     CS_CUDA(cudaMemcpyAsync(&maxc, c->scalar, sizeof maxc, cudaMemcpyDeviceToHost, c->stream));
     CS_CUDA(cudaStreamSynchronize(c->stream));
     if (maxc > BF_CAP) {
-        if (t1 - t0 <= 1 || depth > 40) return fail(CSGPU_ERR_CUDA, "bf16 candidate buffer overflow on a single tile (internal error)");
+        if (t1 - t0 <= 1 || depth > 40) return fail(CSGPU_ERR_CUDA, "candidate buffer overflow on a single tile (internal error)");
         CS_CUDA(cudaMemcpyAsync(c->count, c->count_saved, nq_pad * sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
         const uint64_t mid = t0 + (t1 - t0) / 2;
         rc = run_range(ix, sh, c, map_q, n_qblocks, nq, k, t0, mid, depth + 1);
@@ -330,30 +370,39 @@ static int run_range(const csgpu_index *ix, Shard *sh, Bf16BatchCtx *c, const CU
     return launch_select(ix, sh, c, nq_pad, nq, k, false);
 }
 
-// Up to 1024 queries against one shard; final keys land in c->out [nq][k] (device) .
-static int bf16_search_shard(const csgpu_index *ix, Shard *sh, Bf16BatchCtx *c, const float *q_host, uint32_t nq, uint32_t k)
+// Up to 1024 queries against one shard; final keys land in c->out [nq][k] (device); zero-norm query flags
+// in flags_host[0..nq).
+static int batch_search_shard(const csgpu_index *ix, Shard *sh, BatchCtx *c, const float *q_host, uint32_t nq, uint32_t k,
+                              const uint8_t **flags_out)
 {
     DeviceGuard g(sh->device);
+    const bool bf16 = ix->dtype == CSGPU_DTYPE_BF16;
     const uint32_t n_qblocks = (nq + GT_BLOCK_M - 1) / GT_BLOCK_M;
     const uint32_t nq_pad = n_qblocks * GT_BLOCK_M;
     memcpy(c->q_pin, q_host, (size_t)nq * ix->dim * sizeof(float));
     CS_CUDA(cudaMemcpyAsync(c->q_f32, c->q_pin, (size_t)nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    prep_queries_bf16_kernel<<<(nq_pad * 32 + 255) / 256, 256, 0, c->stream>>>(c->q_f32, nq, ix->dim, reinterpret_cast<__nv_bfloat16 *>(c->q_bf16), nq_pad, c->flags);
+    if (bf16)
+        prep_queries_bf16_kernel<<<(nq_pad * 32 + 255) / 256, 256, 0, c->stream>>>(c->q_f32, nq, ix->dim, reinterpret_cast<__nv_bfloat16 *>(c->q_prep), nq_pad, c->flags);
+    else
+        prep_queries_f32_kernel<<<(nq_pad * 32 + 255) / 256, 256, 0, c->stream>>>(c->q_f32, nq, ix->dim, ix->dim_pad, reinterpret_cast<float *>(c->q_prep), nq_pad, c->flags);
     init_thresholds_kernel<<<(nq_pad + 255) / 256, 256, 0, c->stream>>>(c->thr, c->count, nq, nq_pad);
     count_launch(2);
     uint8_t *flags_host = reinterpret_cast<uint8_t *>(c->out_pin) + (size_t)BF_MAX_QBLOCKS * GT_BLOCK_M * CSGPU_MAX_K * sizeof(uint64_t);
     CS_CUDA(cudaMemcpyAsync(flags_host, c->flags, nq, cudaMemcpyDeviceToHost, c->stream));
     CS_CUDA(cudaStreamSynchronize(c->stream));
-    for (uint32_t j = 0; j < nq; ++j)
-        if (flags_host[j]) return fail(CSGPU_ERR_ARG, "zero-norm query is not supported on a bf16 index");
+    *flags_out = flags_host;
+    if (bf16)
+        for (uint32_t j = 0; j < nq; ++j)
+            if (flags_host[j]) return fail(CSGPU_ERR_ARG, "zero-norm query is not supported on a bf16 index");
     CUtensorMap map_q;
-    int rc = make_map(&map_q, c->q_bf16, nq_pad, ix->dim, GT_BLOCK_M);
+    int rc = make_map(&map_q, c->q_prep, nq_pad, bf16 ? ix->dim : ix->dim_pad, GT_BLOCK_M, !bf16);
     if (rc) return rc;
 
-    const uint64_t n_tiles = (sh->n_built + GT_BLOCK_N - 1) / GT_BLOCK_N;
+    const uint32_t tile_rows = tile_rows_of(ix);
+    const uint64_t n_tiles = (sh->n_built + tile_rows - 1) / tile_rows;
     // phase 0 lets everything through, so it must fit the buffer on its own: <= CAP/2 rows
     uint64_t done = 0;
-    uint64_t next = std::max<uint64_t>(1, (BF_CAP / 2) / GT_BLOCK_N);
+    uint64_t next = std::max<uint64_t>(1, (BF_CAP / 2) / tile_rows);
     while (done < n_tiles) {
         const uint64_t t1 = std::min(n_tiles, done + next);
         rc = run_range(ix, sh, c, map_q, n_qblocks, nq, k, done, t1, 0);
@@ -361,17 +410,26 @@ static int bf16_search_shard(const csgpu_index *ix, Shard *sh, Bf16BatchCtx *c, 
         done = t1;
         next = done * (BF_PHASE_GROWTH - 1);   // each phase scans (growth-1) x everything seen so far
     }
+    CS_CUDA(cudaMemcpyAsync(c->count_saved, c->count, nq_pad * sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
     return launch_select(ix, sh, c, nq_pad, nq, k, true);
 }
 
-int bf16_search_batch(const csgpu_index *ix, const float *q, uint32_t b, uint32_t k,
-                      uint32_t *out_ids, float *out_dist, uint32_t *out_n)
+bool batch_gemm_available(const csgpu_index *ix)
 {
-    if (ix->shards.size() != 1) return fail(CSGPU_ERR_ARG, "bf16 index: multi-device sharding is not implemented yet");
+    return ix->shards.size() == 1 && ix->shards[0]->map_valid;
+}
+
+// b queries through the GEMM-shaped path of a single-shard index. zero_queries (fp32 index only) receives the
+// batch positions of zero-norm queries, whose outputs are left untouched for the caller to fill in.
+int batch_search(const csgpu_index *ix, const float *q, uint32_t b, uint32_t k,
+                 uint32_t *out_ids, float *out_dist, uint32_t *out_n, std::vector<uint32_t> *zero_queries)
+{
+    if (ix->shards.size() != 1) return fail(CSGPU_ERR_ARG, "batched GEMM path: multi-device sharding is not implemented yet");
     Shard *sh = ix->shards[0];
-    std::lock_guard<std::mutex> lk(sh->bf_mu);   // one bf16 batch at a time per index
-    Bf16BatchCtx *c = nullptr;
-    int rc = bf16_batch_ctx(ix, sh, &c);
+    if (!sh->map_valid) return fail(CSGPU_ERR_ARG, "batched GEMM path is unavailable for this index");
+    std::lock_guard<std::mutex> lk(sh->batch_mu);   // one GEMM batch at a time per index
+    BatchCtx *c = nullptr;
+    int rc = batch_ctx(ix, sh, &c);
     if (rc) return rc;
     DeviceGuard g(sh->device);
     const uint32_t chunk = BF_MAX_QBLOCKS * GT_BLOCK_M;
@@ -380,12 +438,16 @@ int bf16_search_batch(const csgpu_index *ix, const float *q, uint32_t b, uint32_
     CS_CUDA(cudaEventRecord(e0, c->stream));
     for (uint32_t j = 0; j < b; j += chunk) {
         const uint32_t nq = std::min(chunk, b - j);
-        rc = bf16_search_shard(ix, sh, c, q + (size_t)j * ix->dim, nq, k);
+        const uint8_t *flags = nullptr;
+        rc = batch_search_shard(ix, sh, c, q + (size_t)j * ix->dim, nq, k, &flags);
         if (rc) break;
+        std::vector<uint8_t> zf(flags, flags + nq);   // out_pin is reused for the results below
         CS_CUDA(cudaMemcpyAsync(c->out_pin, c->out, (size_t)nq * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
         CS_CUDA(cudaStreamSynchronize(c->stream));
-        for (uint32_t i = 0; i < nq; ++i)
+        for (uint32_t i = 0; i < nq; ++i) {
+            if (zf[i]) { if (zero_queries) zero_queries->push_back(j + i); continue; }
             decode_keys(c->out_pin + (size_t)i * k, k, out_ids + (size_t)(j + i) * k, out_dist + (size_t)(j + i) * k, out_n ? out_n + j + i : nullptr);
+        }
     }
     cudaEventRecord(e1, c->stream);
     cudaStreamSynchronize(c->stream);

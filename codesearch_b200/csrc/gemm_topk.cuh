@@ -46,13 +46,12 @@ constexpr uint32_t GT_STAGE_BYTES = GT_BLOCK_N * GT_BLOCK_K * 2;   // 32 KB
 constexpr uint32_t GT_QCHUNK_BYTES = GT_BLOCK_M * GT_BLOCK_K * 2;  // 16 KB
 
 struct GemmTopkArgs {
-    const uint32_t *ids;       // [n_rows]
     uint64_t n_rows;           // rows in the matrix (tensor map extent)
     uint64_t tile_begin, tile_end;  // this phase scans tiles [tile_begin, tile_end)
     uint32_t n_kchunks;        // dim / 64
     uint32_t n_qblocks;        // QB
     const float *thr;          // [QB*128] threshold distance per query (< 0: inactive, +inf: pass all)
-    uint64_t *cand;            // [QB*128][cap] candidate keys
+    uint64_t *cand;            // [QB*128][cap] candidate keys (okey(distance) << 32 | ROW index)
     unsigned *count;           // [QB*128] entries in cand (may exceed cap => overflow)
     uint32_t cap;
 };
@@ -230,6 +229,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * GT_BLOCK_N;
                 const uint64_t row0 = t * GT_BLOCK_N;
+                // pass 1: per 32-column chunk, max -> one compare; chunks where some lane passes are
+                // counted exactly. Common case (late phases): 8 x (LDTM + 31 FMNMX + vote).
+                uint32_t chunkmask = 0, cnt = 0;   // chunkmask is warp-uniform
 #pragma unroll 1
                 for (uint32_t c = 0; c < GT_BLOCK_N / 32; ++c) {
                     float v[32];
@@ -237,14 +239,37 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     float best = v[0];
 #pragma unroll
                     for (int j = 1; j < 32; ++j) best = fmaxf(best, v[j]);
-                    if (fmaf(-0.5f, best, 0.5f) <= thr) {             // rare after the first phases
+                    const bool hit = fmaf(-0.5f, best, 0.5f) <= thr;
+                    if (__any_sync(FULL, hit)) {
+                        chunkmask |= 1u << c;
+                        if (hit) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float dist = fmaf(-0.5f, v[j], 0.5f);
-                            const uint64_t row = row0 + c * 32 + j;
-                            if (dist <= thr && row < a.n_rows) {
-                                const unsigned pos = atomicAdd(my_count, 1u);
-                                if (pos < a.cap) my_cand[pos] = make_key(dist, a.ids[row]);
+                            for (int j = 0; j < 32; ++j)
+                                cnt += (fmaf(-0.5f, v[j], 0.5f) <= thr && row0 + c * 32 + j < a.n_rows) ? 1u : 0u;
+                        }
+                    }
+                }
+                // pass 2 (only if some query of this warp has candidates in the tile): ONE atomic per
+                // query per tile reserves the slots, then the hit chunks are re-read from TMEM and the
+                // keys written. The atomic's latency is exposed once per tile, not once per candidate.
+                if (chunkmask) {
+                    unsigned pos = cnt ? atomicAdd(my_count, cnt) : 0u;
+#pragma unroll 1
+                    for (uint32_t c = 0; c < GT_BLOCK_N / 32; ++c) {
+                        if (!((chunkmask >> c) & 1u)) continue;
+                        float v[32];
+                        tmem_ld32(taddr + c * 32, v);
+                        if (cnt) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float dist = fmaf(-0.5f, v[j], 0.5f);
+                                const uint64_t row = row0 + c * 32 + j;
+                                if (dist <= thr && row < a.n_rows) {
+                                    // the key carries the ROW index; select_candidates_kernel swaps in the
+                                    // chunk id (no dependent global load inside this divergent loop)
+                                    if (pos < a.cap) my_cand[pos] = make_key(dist, (uint32_t)row);
+                                    ++pos;
+                                }
                             }
                         }
                     }

@@ -55,11 +55,11 @@ struct SearchCtx {
     size_t cand_cap = 0;            // in keys
 };
 
-// Scratch of the bf16 batched path (gemm_topk.cu): one per shard, serialised by Shard::bf_mu.
-struct Bf16BatchCtx {
+// Scratch of the batched GEMM-shaped path (gemm_topk.cu): one per shard, serialised by Shard::batch_mu.
+struct BatchCtx {
     cudaStream_t stream = nullptr;
-    float *q_f32 = nullptr;        // [1024][dim]
-    void *q_bf16 = nullptr;        // [1024][dim] unit-normalised bf16
+    float *q_f32 = nullptr;        // [1024][dim] raw queries
+    void *q_prep = nullptr;        // [1024][dim_pad] unit-normalised queries: fp32, or bf16 on a bf16 index
     uint8_t *flags = nullptr;      // [1024] zero-norm query flags
     float *thr = nullptr;          // [1024] threshold distance per query
     unsigned *count = nullptr, *count_saved = nullptr;
@@ -76,9 +76,10 @@ struct Shard {
     void *rows_bf16 = nullptr;     // [cap, dim] bf16 unit vectors
     float *stage = nullptr;        // [stage_cap, dim] fp32, rows appended since the last build
     uint64_t stage_cap = 0;
-    CUtensorMap map_c;             // TMA map over rows_bf16[0, n_built)
-    Bf16BatchCtx *bf = nullptr;
-    std::mutex bf_mu;
+    CUtensorMap map_c;             // TMA map over the built rows (bf16 or fp32), re-encoded at every build
+    bool map_valid = false;
+    BatchCtx *batch = nullptr;
+    std::mutex batch_mu;
     float *rows = nullptr;     // [cap, dim_pad] fp32; rows [0, n_built) are unit vectors
     uint32_t *ids = nullptr;   // [cap]
     uint8_t *status = nullptr; // [cap] ROW_* (all ROW_OK in [0, n_built) after build)
@@ -92,15 +93,17 @@ struct Shard {
     std::vector<SearchCtx *> all_ctx;
 };
 
-// gemm_topk.cu (bf16 index)
+// gemm_topk.cu (batched GEMM-shaped path for both index dtypes + bf16 storage hooks)
 bool bf16_dim_supported(uint32_t dim);
 int bf16_reserve_rows(const csgpu_index *ix, Shard *sh, uint64_t rows);
 int bf16_reserve_stage(const csgpu_index *ix, Shard *sh, uint64_t pending);
 int bf16_convert_pending(const csgpu_index *ix, Shard *sh);
-int bf16_after_build(const csgpu_index *ix, Shard *sh);
-void bf16_free_batch_ctx(Shard *sh);
-int bf16_search_batch(const csgpu_index *ix, const float *q, uint32_t b, uint32_t k,
-                      uint32_t *out_ids, float *out_dist, uint32_t *out_n);
+bool batch_f32_dim_supported(uint32_t dim_pad);
+int batch_after_build(const csgpu_index *ix, Shard *sh);
+void batch_free_ctx(Shard *sh);
+bool batch_gemm_available(const csgpu_index *ix);
+int batch_search(const csgpu_index *ix, const float *q, uint32_t b, uint32_t k,
+                 uint32_t *out_ids, float *out_dist, uint32_t *out_n, std::vector<uint32_t> *zero_queries);
 
 // scan_multi.cu
 struct MultiArgs;
