@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libcsgpu.so")
 OK, ERR_DIM, ERR_NOT_BUILT, ERR_CUDA, ERR_NCCL, ERR_OOM, ERR_ARG = range(7)
 DTYPE_F32, DTYPE_BF16 = 0, 1
 MAX_K = 1024
+EXCHANGE_HANDLE_BYTES = 64
 KEY_EMPTY = 0xFFFFFFFFFFFFFFFF
 
 
@@ -57,11 +58,19 @@ SIGNATURES = {
     "csgpu_reserve": (ctypes.c_int, [_vp, ctypes.c_uint64]),
     "csgpu_build": (ctypes.c_int, [_vp]),
     "csgpu_clear": (ctypes.c_int, [_vp]),
+    "csgpu_save": (ctypes.c_int, [_vp, ctypes.c_char_p]),
+    "csgpu_load": (ctypes.c_int, [_vp, ctypes.c_char_p]),
     "csgpu_search": (ctypes.c_int, [_vp, _f32p, ctypes.c_uint32, ctypes.c_uint32, _u32p, _f32p, _u32p]),
     "csgpu_search_batch": (ctypes.c_int, [_vp, _f32p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _u32p, _f32p, _u32p]),
     "csgpu_search_filtered": (ctypes.c_int, [_vp, _f32p, ctypes.c_uint32, ctypes.c_uint32, _u64p, ctypes.c_uint64, _u32p, _f32p, _u32p]),
     "csgpu_search_keys_device": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, _vp, _vp]),
     "csgpu_merge_keys_device": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp]),
+    "csgpu_exchange_create": (ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32, _vp]),
+    "csgpu_exchange_connect": (ctypes.c_int, [_vp, _vp]),
+    "csgpu_exchange_connect_local": (ctypes.c_int, [_vp, ctypes.POINTER(_vp)]),
+    "csgpu_search_keys_exchange_device": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, _vp, _vp]),
+    "csgpu_exchange_status": (ctypes.c_int, [_vp, _u32p]),
+    "csgpu_exchange_destroy": (None, [_vp]),
     "csgpu_decode_keys": (None, [_u64p, ctypes.c_uint32, _u32p, _f32p, _u32p]),
     "csgpu_append_synthetic": (ctypes.c_int, [_vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32]),
     "csgpu_synth_rows_host": (ctypes.c_int, [_vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, _f32p]),

@@ -98,11 +98,14 @@ static void ctx_release(Shard *sh, SearchCtx *c)
 // ---------------------------------------------------------------------------------------
 // scan dispatch
 // ---------------------------------------------------------------------------------------
-template <int V, bool EXACT, bool BIG>
+// OCC = resident CTAs per SM. The scan needs ~96 KB of loads in flight per SM (profiles/r01_tune_scan.txt:
+// occupancy 1 loses 30 %), so the big-k selector also runs 2 CTAs/SM while its lists fit (kpad <= 512:
+// 2 x 8 warps x 512 keys x 8 B = 64 KB per CTA).
+template <int V, bool EXACT, bool BIG, int OCC>
 static cudaError_t launch_scan_v(const ScanArgs &a, uint32_t grid, size_t smem, cudaStream_t st)
 {
     constexpr int R = (V <= 2) ? 8 : (V <= 4 ? 4 : 2);
-    auto kern = scan_topk_kernel<V, EXACT, R, BIG>;
+    auto kern = scan_topk_kernel<V, EXACT, R, BIG, OCC>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -112,14 +115,14 @@ static cudaError_t launch_scan_v(const ScanArgs &a, uint32_t grid, size_t smem, 
     return cudaGetLastError();
 }
 
-template <bool BIG>
+template <bool BIG, int OCC>
 static cudaError_t launch_scan_b(const ScanArgs &a, uint32_t grid, size_t smem, cudaStream_t st)
 {
     const uint32_t V = (a.dim4 + 31) / 32;
     const bool exact = (a.dim4 % 32) == 0;
 #define CS_CASE(v)                                                                    \
-    case v: return exact ? launch_scan_v<v, true, BIG>(a, grid, smem, st)              \
-                         : launch_scan_v<v, false, BIG>(a, grid, smem, st);
+    case v: return exact ? launch_scan_v<v, true, BIG, OCC>(a, grid, smem, st)         \
+                         : launch_scan_v<v, false, BIG, OCC>(a, grid, smem, st);
     switch (V) {
         CS_CASE(1) CS_CASE(2) CS_CASE(3) CS_CASE(4) CS_CASE(5) CS_CASE(6) CS_CASE(7) CS_CASE(8)
         default: return cudaErrorInvalidValue;
@@ -136,7 +139,7 @@ static uint32_t rows_in_flight(uint32_t dim4)
 // Enqueue one single-query scan of `sh` on `st`. q_dev: [dim_pad] on the shard's device.
 static int enqueue_scan(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const float *q_dev, uint32_t k,
                         const uint64_t *bitmap_dev, uint64_t n_bits, bool with_zero_ids, uint64_t *out_keys,
-                        cudaStream_t st)
+                        cudaStream_t st, const ExchangeDev *xchg = nullptr, uint32_t seq = 0)
 {
     ScanArgs a;
     a.rows = reinterpret_cast<const float4 *>(sh->rows);
@@ -154,12 +157,25 @@ static int enqueue_scan(const csgpu_index *ix, const Shard *sh, SearchCtx *c, co
     a.cand = c->cand;
     a.ticket = c->ticket;
     a.out_keys = out_keys;
+    a.xchg = xchg;
+    a.seq = seq;
     const uint32_t per_cta_rows = SCAN_WARPS * rows_in_flight(ix->dim4);
     uint64_t want = (sh->n_built + per_cta_rows - 1) / per_cta_rows;
-    uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sh->sm_count * (big ? 1 : 2), std::max<uint64_t>(want, 1));
+    if (bitmap_dev != nullptr) {   // filtered: pre-filter variant (scan_filtered.cu)
+        const uint64_t want32 = (sh->n_built + 32 * SCAN_WARPS - 1) / (32 * SCAN_WARPS);
+        const uint32_t occf = (big && a.kpad > 512) ? 1 : 2;
+        const uint32_t gridf = (uint32_t)std::min<uint64_t>((uint64_t)sh->sm_count * occf, std::max<uint64_t>(want32, 1));
+        const size_t smemf = big ? (size_t)2 * SCAN_WARPS * a.kpad * sizeof(uint64_t) : (size_t)SCAN_WARPS * 32 * sizeof(uint64_t);
+        cudaError_t ef = launch_scan_filtered(a, gridf, smemf, st);
+        if (ef != cudaSuccess) return fail_cuda(ef, "scan_topk_kernel (filtered) launch", __FILE__, __LINE__);
+        return CSGPU_OK;
+    }
+    const uint32_t occ = (big && a.kpad > 512) ? 1 : 2;
+    uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sh->sm_count * occ, std::max<uint64_t>(want, 1));
     if (grid > MAX_GRID) grid = MAX_GRID;
     const size_t smem = big ? (size_t)2 * SCAN_WARPS * a.kpad * sizeof(uint64_t) : (size_t)SCAN_WARPS * 32 * sizeof(uint64_t);
-    cudaError_t e = big ? launch_scan_b<true>(a, grid, smem, st) : launch_scan_b<false>(a, grid, smem, st);
+    cudaError_t e = !big ? launch_scan_b<false, 2>(a, grid, smem, st)
+                         : (occ == 2 ? launch_scan_b<true, 2>(a, grid, smem, st) : launch_scan_b<true, 1>(a, grid, smem, st));
     if (e != cudaSuccess) return fail_cuda(e, "scan_topk_kernel launch", __FILE__, __LINE__);
     return CSGPU_OK;
 }
@@ -614,9 +630,12 @@ int csgpu_create(csgpu_index **out, uint32_t dim, uint32_t dtype, const int32_t 
     return CSGPU_OK;
 }
 
+static void exchange_free(csgpu_index *ix);
+
 void csgpu_destroy(csgpu_index *ix)
 {
     if (!ix) return;
+    exchange_free(ix);
     for (Shard *sh : ix->shards) {
         DeviceGuard dg(sh->device);
         for (SearchCtx *c : sh->all_ctx) ctx_destroy(c);
@@ -910,6 +929,146 @@ int csgpu_merge_keys_device(const csgpu_index *ix, const uint64_t *keys_dev, uin
 void csgpu_decode_keys(const uint64_t *keys, uint32_t k, uint32_t *out_ids, float *out_dist, uint32_t *out_n)
 {
     decode_keys(keys, k, out_ids, out_dist, out_n);
+}
+
+// ---- snapshot / hydrate (snapshot.cu) -----------------------------------------------------------------
+static int load_finish(csgpu_index *ix)
+{
+    int rc = upload_zero_ids(ix);
+    if (rc) return rc;
+    for (Shard *sh : ix->shards) if ((rc = batch_after_build(ix, sh))) return rc;
+    ix->tombstones = 0;
+    ix->built = true;
+    return CSGPU_OK;
+}
+
+int csgpu_save(const csgpu_index *ix, const char *dir) { return snapshot_save(ix, dir); }
+
+int csgpu_load(csgpu_index *ix, const char *dir) { return snapshot_load(ix, dir, csgpu_reserve, load_finish); }
+
+// ---- fused cross-GPU exchange (rank-per-GPU) ---------------------------------------------------------
+static void exchange_free(csgpu_index *ix)
+{
+    Exchange *x = ix->xchg;
+    if (!x) return;
+    DeviceGuard dg(ix->shards[0]->device);
+    for (uint32_t p = 0; p < x->world; ++p)
+        if (x->peer_ipc[p] && x->peer_base[p]) cudaIpcCloseMemHandle(x->peer_base[p]);
+    cudaFree(x->dev);
+    cudaFree(x->base);
+    delete x;
+    ix->xchg = nullptr;
+}
+
+int csgpu_exchange_create(csgpu_index *ix, uint32_t world, uint32_t rank, void *out_handle)
+{
+    if (!ix || !out_handle) return fail(CSGPU_ERR_ARG, "null argument");
+    if (ix->shards.size() != 1) return fail(CSGPU_ERR_ARG, "the fused exchange needs a single-device index (one rank per GPU)");
+    if (world == 0 || world > (uint32_t)XCHG_MAX_WORLD || rank >= world) return fail(CSGPU_ERR_ARG, "world must be in [1, 8] and rank < world");
+    exchange_free(ix);
+    DeviceGuard dg(ix->shards[0]->device);
+    Exchange *x = new Exchange();
+    x->world = world; x->rank = rank;
+    ix->xchg = x;
+    CS_CUDA(cudaMalloc(&x->base, x->block_bytes()));
+    CS_CUDA(cudaMemset(x->base, 0, x->block_bytes()));
+    CS_CUDA(cudaMalloc(&x->dev, sizeof(ExchangeDev)));
+    static_assert(sizeof(cudaIpcMemHandle_t) == CSGPU_EXCHANGE_HANDLE_BYTES, "handle size");
+    cudaIpcMemHandle_t h;
+    CS_CUDA(cudaIpcGetMemHandle(&h, x->base));
+    memcpy(out_handle, &h, sizeof h);
+    return CSGPU_OK;
+}
+
+static int exchange_finish_connect(csgpu_index *ix)
+{
+    Exchange *x = ix->xchg;
+    ExchangeDev d;
+    memset(&d, 0, sizeof d);
+    for (uint32_t p = 0; p < x->world; ++p) {
+        d.slots[p] = reinterpret_cast<uint64_t *>(x->peer_base[p]);
+        d.flags[p] = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(x->peer_base[p]) + x->slots_bytes());
+    }
+    d.status = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(x->base) + x->slots_bytes() + (size_t)2 * x->world * sizeof(unsigned));
+    d.world = x->world; d.rank = x->rank; d.kmax = x->kmax;
+    DeviceGuard dg(ix->shards[0]->device);
+    CS_CUDA(cudaMemcpy(x->dev, &d, sizeof d, cudaMemcpyHostToDevice));
+    x->connected = true;
+    return CSGPU_OK;
+}
+
+int csgpu_exchange_connect(csgpu_index *ix, const void *handles)
+{
+    if (!ix || !ix->xchg || !handles) return fail(CSGPU_ERR_ARG, "csgpu_exchange_create first");
+    Exchange *x = ix->xchg;
+    DeviceGuard dg(ix->shards[0]->device);
+    for (uint32_t p = 0; p < x->world; ++p) {
+        if (p == x->rank) { x->peer_base[p] = x->base; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, reinterpret_cast<const char *>(handles) + (size_t)p * CSGPU_EXCHANGE_HANDLE_BYTES, sizeof h);
+        CS_CUDA(cudaIpcOpenMemHandle(&x->peer_base[p], h, cudaIpcMemLazyEnablePeerAccess));
+        x->peer_ipc[p] = true;
+    }
+    return exchange_finish_connect(ix);
+}
+
+int csgpu_exchange_connect_local(csgpu_index *ix, csgpu_index *const *peers)
+{
+    if (!ix || !ix->xchg || !peers) return fail(CSGPU_ERR_ARG, "csgpu_exchange_create first");
+    Exchange *x = ix->xchg;
+    for (uint32_t p = 0; p < x->world; ++p) {
+        if (p == x->rank) { x->peer_base[p] = x->base; continue; }
+        const csgpu_index *o = peers[p];
+        if (!o || !o->xchg || o->xchg->world != x->world || o->xchg->rank != p)
+            return fail(CSGPU_ERR_ARG, "peer index has no matching exchange (world/rank)");
+        const int da = ix->shards[0]->device, db = o->shards[0]->device;
+        if (da != db) {   // same process, different GPUs: plain peer access
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, da, db);
+            if (!can) return fail(CSGPU_ERR_CUDA, "no peer access between the devices of the exchange");
+            DeviceGuard dg(da);
+            cudaError_t pe = cudaDeviceEnablePeerAccess(db, 0);
+            if (pe != cudaSuccess) cudaGetLastError();   // already enabled
+        }
+        x->peer_base[p] = o->xchg->base;
+    }
+    return exchange_finish_connect(ix);
+}
+
+int csgpu_search_keys_exchange_device(const csgpu_index *ix, const float *q_dev, uint32_t k, uint64_t *out_keys_dev, void *stream)
+{
+    if (!ix) return fail(CSGPU_ERR_ARG, "null index");
+    if (!ix->built) return fail(CSGPU_ERR_NOT_BUILT, "Index not built. Call build_index() after inserting chunks.");
+    if (!ix->xchg || !ix->xchg->connected) return fail(CSGPU_ERR_ARG, "exchange is not connected (csgpu_exchange_create/connect)");
+    if (ix->dtype != CSGPU_DTYPE_F32) return fail(CSGPU_ERR_ARG, "device entry points need an fp32 index");
+    if (!q_dev || !out_keys_dev) return fail(CSGPU_ERR_ARG, "null device pointer");
+    if (k == 0 || k > CSGPU_MAX_K) return fail(CSGPU_ERR_ARG, "k must be in [1, 1024]");
+    Shard *sh = ix->shards[0];
+    SearchCtx *c = nullptr;
+    int rc = ctx_acquire(ix, sh, &c);
+    if (rc) return rc;
+    DeviceGuard dg(sh->device);
+    const uint32_t seq = ix->xchg->seq.fetch_add(1) + 1;   // every rank issues the same sequence of searches
+    rc = enqueue_scan(ix, sh, c, q_dev, k, nullptr, 0, true, out_keys_dev, (cudaStream_t)stream, ix->xchg->dev, seq);
+    ctx_release(sh, c);
+    return rc;
+}
+
+int csgpu_exchange_status(const csgpu_index *ix, uint32_t *timed_out)
+{
+    if (!ix || !ix->xchg || !timed_out) return fail(CSGPU_ERR_ARG, "no exchange");
+    const Exchange *x = ix->xchg;
+    DeviceGuard dg(ix->shards[0]->device);
+    unsigned v = 0;
+    CS_CUDA(cudaMemcpy(&v, reinterpret_cast<const char *>(x->base) + x->slots_bytes() + (size_t)2 * x->world * sizeof(unsigned),
+                       sizeof v, cudaMemcpyDeviceToHost));
+    *timed_out = v;
+    return CSGPU_OK;
+}
+
+void csgpu_exchange_destroy(csgpu_index *ix)
+{
+    if (ix) exchange_free(ix);
 }
 
 int csgpu_stats(const csgpu_index *ix, csgpu_stats_t *out)

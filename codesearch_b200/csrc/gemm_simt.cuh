@@ -74,7 +74,7 @@ gemm_simt_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
                 for (uint32_t kc = 0; kc < a.n_kchunks; ++kc, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_wait_backoff(&empty_bar[s], ph ^ 1, 256);   // a stage lasts ~3 us: do not spin
                     mbar_expect_tx(&full_bar[s], GS_STAGE_BYTES);
                     unsigned char *dst = ring + (size_t)s * GS_STAGE_BYTES;
                     tma_load_2d(dst, &map_q, &full_bar[s], (int32_t)(kc * GS_BK), (int32_t)(qb * GS_BM));

@@ -5,6 +5,7 @@
 // plus the bf16 index's storage hooks. See gemm_topk.cuh for the progressive-threshold design.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -291,6 +292,10 @@ static int launch_gemm(const csgpu_index *ix, Shard *sh, BatchCtx *c, const CUte
     a.cand = c->cand;
     a.count = c->count;
     a.cap = BF_CAP;
+    // L2 prefetch of upcoming tiles: measured slower than no prefetch at every distance (profiles/r01_bf16_prefetch.txt:
+    // 8.5 ms off vs 8.9-9.2 ms at distance 1-4), so it is off; CSGPU_BF16_PREFETCH=<tiles> re-enables it for experiments
+    static const int env_pf = getenv("CSGPU_BF16_PREFETCH") ? atoi(getenv("CSGPU_BF16_PREFETCH")) : 0;
+    a.prefetch_tiles = env_pf > 0 ? (uint32_t)env_pf : 0u;
     const uint64_t n_tiles = t1 - t0;
     cudaError_t e = cudaSuccess;
     if (ix->dtype == CSGPU_DTYPE_BF16) {

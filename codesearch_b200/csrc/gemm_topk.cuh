@@ -54,6 +54,7 @@ struct GemmTopkArgs {
     uint64_t *cand;            // [QB*128][cap] candidate keys (okey(distance) << 32 | ROW index)
     unsigned *count;           // [QB*128] entries in cand (may exceed cap => overflow)
     uint32_t cap;
+    uint32_t prefetch_tiles;   // bf16 kernel: L2 prefetch distance in tiles of a CTA's walk (0 = off)
 };
 
 // ---- tcgen05 wrappers ---------------------------------------------------------------------
@@ -109,6 +110,18 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
         : "memory");
+}
+
+// predicated 8-byte global store without a branch
+__device__ __forceinline__ void st_global_pred(uint64_t *p, uint64_t v, bool pred)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.u64 [%0], %1;\n\t}" ::"l"(p), "l"(v), "r"((uint32_t)pred) : "memory");
+}
+
+// L2 prefetch of a 2-D TMA tile (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int32_t c_inner, int32_t c_outer)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c_inner), "r"(c_outer) : "memory");
 }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
@@ -174,10 +187,19 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     tma_load_2d(q_smem + (size_t)kc * GT_QCHUNK_BYTES, &map_q, &q_bar, (int32_t)(kc * GT_BLOCK_K), (int32_t)(qb * GT_BLOCK_M));
                 uint32_t it = 0;
                 for (uint64_t t = a.tile_begin + group; t < a.tile_end; t += n_groups) {
+                    // The QB CTAs of a group read the same tile at about the same time; the first one pulls the
+                    // tile it will need prefetch_tiles iterations from now into L2, so the demand loads of all
+                    // QB CTAs hit L2 (DRAM latency off the MMA's critical path, one DRAM read per tile).
+                    if (qb == 0 && a.prefetch_tiles) {
+                        const uint64_t tp = t + (uint64_t)a.prefetch_tiles * n_groups;
+                        if (tp < a.tile_end)
+                            for (uint32_t kc = 0; kc < a.n_kchunks; ++kc)
+                                tma_prefetch_2d(&map_c, (int32_t)(kc * GT_BLOCK_K), (int32_t)(tp * GT_BLOCK_N));
+                    }
                     for (uint32_t kc = 0; kc < a.n_kchunks; ++kc, ++it) {
                         const int s = it % STAGES;
                         const uint32_t ph = (it / STAGES) & 1;
-                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        mbar_wait_backoff(&empty_bar[s], ph ^ 1, 64);
                         mbar_expect_tx(&full_bar[s], GT_STAGE_BYTES);
                         tma_load_2d(ring + (size_t)s * GT_STAGE_BYTES, &map_c, &full_bar[s], (int32_t)(kc * GT_BLOCK_K), (int32_t)(t * GT_BLOCK_N));
                     }
@@ -260,16 +282,16 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         float v[32];
                         tmem_ld32(taddr + c * 32, v);
                         if (cnt) {
+                            // branch-free: one predicated 8-byte store per column. The key carries the ROW index;
+                            // select_candidates_kernel swaps in the chunk id (no dependent load in here).
+                            const uint32_t rbase = (uint32_t)(row0 + c * 32);
+                            const uint32_t lim = (uint32_t)min((uint64_t)32, a.n_rows - min(a.n_rows, row0 + c * 32));
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
                                 const float dist = fmaf(-0.5f, v[j], 0.5f);
-                                const uint64_t row = row0 + c * 32 + j;
-                                if (dist <= thr && row < a.n_rows) {
-                                    // the key carries the ROW index; select_candidates_kernel swaps in the
-                                    // chunk id (no dependent global load inside this divergent loop)
-                                    if (pos < a.cap) my_cand[pos] = make_key(dist, (uint32_t)row);
-                                    ++pos;
-                                }
+                                const bool pass = (dist <= thr) & ((uint32_t)j < lim);
+                                st_global_pred(my_cand + min(pos, a.cap - 1), make_key(dist, rbase + j), pass & (pos < a.cap));
+                                pos += pass ? 1u : 0u;
                             }
                         }
                     }

@@ -70,6 +70,21 @@ struct BatchCtx {
     uint64_t *out_pin = nullptr;
 };
 
+// Fused cross-GPU exchange state of a single-device index (scan.cuh: ExchangeDev). One cudaMalloc block:
+// [2][world][kmax] keys, then [2][world] flags, then one status word — shared with peers through cudaIpc.
+struct ExchangeDev;
+struct Exchange {
+    uint32_t world = 0, rank = 0, kmax = CSGPU_MAX_K;
+    void *base = nullptr;                 // local block
+    void *peer_base[8] = {};              // peers' blocks as mapped here (own entry = base)
+    bool peer_ipc[8] = {};                // opened with cudaIpcOpenMemHandle (needs cudaIpcCloseMemHandle)
+    ExchangeDev *dev = nullptr;           // device copy of the pointer table
+    bool connected = false;
+    std::atomic<uint32_t> seq{0};
+    size_t slots_bytes() const { return (size_t)2 * world * kmax * sizeof(uint64_t); }
+    size_t block_bytes() const { return slots_bytes() + (size_t)2 * world * sizeof(unsigned) + 64; }
+};
+
 struct Shard {
     int device = 0;
     // bf16 index (dtype == CSGPU_DTYPE_BF16): built rows live here, pending rows in `stage` as fp32
@@ -105,6 +120,14 @@ bool batch_gemm_available(const csgpu_index *ix);
 int batch_search(const csgpu_index *ix, const float *q, uint32_t b, uint32_t k,
                  uint32_t *out_ids, float *out_dist, uint32_t *out_n, std::vector<uint32_t> *zero_queries);
 
+// snapshot.cu
+int snapshot_save(const csgpu_index *ix, const char *dir);
+int snapshot_load(csgpu_index *ix, const char *dir, int (*reserve)(csgpu_index *, uint64_t), int (*finish)(csgpu_index *));
+
+// scan_filtered.cu
+struct ScanArgs;
+cudaError_t launch_scan_filtered(const ScanArgs &a, uint32_t grid, size_t smem, cudaStream_t st);
+
 // scan_multi.cu
 struct MultiArgs;
 bool multi_scan_supported(uint32_t dim4, uint32_t k);
@@ -124,4 +147,5 @@ struct csgpu_index {
     uint64_t nonfinite_rows = 0;
     uint64_t tombstones = 0;
     mutable std::atomic<float> last_search_us{0.f};
+    csgpu::Exchange *xchg = nullptr;      // rank-per-GPU fused exchange (csgpu_exchange_*)
 };

@@ -24,6 +24,20 @@ namespace csgpu {
 constexpr int SCAN_WARPS = 8;
 constexpr int SCAN_THREADS = SCAN_WARPS * 32;
 
+// Cross-GPU exchange fused into the scan kernel (rank-per-GPU sharding). Every rank owns a
+// slot array + flags in its HBM that all peers can write over NVLink (cudaIpc-mapped, or plain pointers in
+// one process). The last CTA of a rank's scan stores its k local keys straight into every peer's slot,
+// publishes a sequence flag, waits for the peers' flags in its own memory and merges — no NCCL call, no
+// separate merge launch. Slots/flags are double-buffered by sequence parity: a rank can be at most one
+// query ahead of a peer, because finishing query s needs the peer's keys of query s.
+constexpr int XCHG_MAX_WORLD = 8;
+struct ExchangeDev {
+    uint64_t *slots[XCHG_MAX_WORLD];   // slots[p]: rank p's array [2][world][kmax], as mapped on THIS device
+    unsigned *flags[XCHG_MAX_WORLD];   // flags[p]: rank p's flags [2][world]
+    unsigned *status;                  // local: set to 1 if a wait timed out
+    uint32_t world, rank, kmax;
+};
+
 struct ScanArgs {
     const float4 *rows;      // [n_rows, dim4]
     const uint32_t *ids;     // [n_rows]
@@ -38,6 +52,8 @@ struct ScanArgs {
     uint64_t *cand;          // [gridDim.x, k] per-CTA results
     unsigned *ticket;        // last-CTA-done counter (self-resetting)
     uint64_t *out_keys;      // [k] final keys, ascending, KEY_EMPTY padded
+    const ExchangeDev *xchg = nullptr;  // non-null: out_keys receives the GLOBAL top-k over all ranks
+    uint32_t seq = 0;                   // exchange sequence number of this query (same on every rank, >= 1)
 };
 
 // LD selects the load flavour (tuned on B200, see profiles/): 0 = ld.global.nc.L1::no_allocate,
@@ -109,13 +125,132 @@ __device__ __forceinline__ void cta_reduce(Sel &sel, uint64_t *smem, uint32_t k,
     __syncthreads();
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 template <bool BIG>
 struct SelOf { using type = WarpSel32; };
 template <>
 struct SelOf<true> { using type = WarpSelBig; };
 
+// Tail of the last CTA when a.xchg is set. Precondition: smem[0..k) holds this rank's sorted local top-k
+// (left there by cta_reduce) and all threads are past a barrier.
+template <bool BIG, class Sel>
+__device__ __forceinline__ void exchange_and_merge(const ScanArgs &a, Sel &sel, uint64_t *smem, int warp, int lane)
+{
+    const ExchangeDev &x = *a.xchg;   // pointer table stays in global memory (no local copy)
+    const uint32_t par = a.seq & 1u, W = x.world, R = x.rank, KM = x.kmax, k = a.k;
+    // my k keys -> slot [par][R] of every rank (own copy included): peer stores over NVLink
+    for (uint32_t t = threadIdx.x; t < W * k; t += blockDim.x) {
+        const uint32_t p = t / k, j = t - p * k;
+        x.slots[p][((size_t)par * W + R) * KM + j] = smem[j];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < W) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned *>(x.flags[threadIdx.x] + par * W + R) = a.seq;   // publish to rank threadIdx.x
+        // wait until rank threadIdx.x's keys of this query have landed in MY memory
+        const volatile unsigned *f = x.flags[R] + par * W + threadIdx.x;
+        const unsigned long long t0 = global_timer_ns();
+        while (*f != a.seq) {
+            if (global_timer_ns() - t0 > 4000000000ull) { atomicExch(x.status, 1u); break; }   // 4 s: a peer died
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if constexpr (BIG) {
+        sel.init(smem + (size_t)warp * a.kpad, smem + (size_t)(SCAN_WARPS + warp) * a.kpad, a.k, a.kpad, lane);
+    } else {
+        sel.init(a.k);
+    }
+    const volatile uint64_t *mine = x.slots[R] + (size_t)par * W * KM;   // volatile: peers wrote it, L1 may be stale
+    const uint32_t total = W * k;
+    for (uint32_t b = (uint32_t)warp * 32; b < total; b += SCAN_WARPS * 32) {
+        uint64_t key = KEY_EMPTY;
+        if (b + lane < total) {
+            const uint32_t t = b + lane, r = t / k, j = t - r * k;
+            key = mine[(size_t)r * KM + j];
+        }
+        offer_lane_keys(sel, key, lane);
+    }
+    cta_reduce<BIG>(sel, smem, a.k, a.kpad, a.out_keys, warp, lane);
+}
+
 // V = float4 per lane (ceil(dim4/32)); EXACT: dim4 == 32*V; R = rows in flight per warp.
-template <int V, bool EXACT, int R, bool BIG, int OCC = (BIG ? 1 : 2), int LD = 0>
+// Filtered scan body (csgpu_search_filtered): the allow bitmap is tested BEFORE a row is read, so masked rows cost
+// no HBM traffic at all — bytes scanned = passing rows x dim x 4 (+ 4 B of id per row). A warp walks blocks of 32
+// consecutive rows: lane l owns row 32b + l, loads its chunk id (one coalesced 128 B line per block) and its bitmap
+// word (id-indexed, L2-resident: 1.25 MB per 10M ids); the ballot of allowed lanes is then consumed R rows at a time
+// with the same per-row FMA chain + shuffle tree as the unfiltered body (bit-identical scores). The id and bitmap
+// loads run two / one blocks ahead so their latency stays off the critical path.
+template <int V, bool EXACT, int R, int LD, class Sel>
+__device__ __forceinline__ void scan_rows_filtered(const ScanArgs &a, const float4 (&qv)[V], bool qzero, Sel &sel, int lane,
+                                                   uint64_t gw, uint64_t n_warps)
+{
+    const uint64_t n = a.n_rows;
+    const uint64_t n_blocks = (n + 31) / 32;
+    auto load_id = [&](uint64_t b, bool &valid) -> uint32_t {
+        const uint64_t row = b * 32 + lane;
+        valid = b < n_blocks && row < n;
+        return valid ? __ldg(a.ids + row) : 0u;
+    };
+    auto load_word = [&](uint32_t id, bool valid) -> uint64_t {
+        return (valid && (uint64_t)id < a.n_bits) ? __ldg(reinterpret_cast<const unsigned long long *>(a.bitmap) + (id >> 6)) : 0ull;
+    };
+    bool v_cur, v_nxt, v_nx2;
+    uint32_t id_cur = load_id(gw, v_cur);
+    uint64_t w_cur = load_word(id_cur, v_cur);
+    uint32_t id_nxt = load_id(gw + n_warps, v_nxt);
+    for (uint64_t b = gw; b < n_blocks; b += n_warps) {
+        const uint64_t w_nxt = load_word(id_nxt, v_nxt);
+        const uint32_t id_nx2 = load_id(b + 2 * n_warps, v_nx2);
+        unsigned m = __ballot_sync(FULL, (w_cur >> (id_cur & 63)) & 1ull);
+        const float4 *blk = a.rows + b * 32 * a.dim4 + lane;
+        while (m) {
+            int rl[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                rl[r] = m ? (__ffs(m) - 1) : -1;
+                m &= m - 1;   // 0 stays 0
+            }
+            float4 x[R][V];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float4 *p = blk + (size_t)(rl[r] < 0 ? 0 : rl[r]) * a.dim4;
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    if (rl[r] >= 0 && (EXACT || lane + 32 * j < a.dim4)) x[r][j] = ldg_stream<LD>(p + 32 * j);
+                    else x[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                float acc = 0.f;
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    acc = fmaf(x[r][j].x, qv[j].x, acc); acc = fmaf(x[r][j].y, qv[j].y, acc);
+                    acc = fmaf(x[r][j].z, qv[j].z, acc); acc = fmaf(x[r][j].w, qv[j].w, acc);
+                }
+                acc = warp_sum_tree(acc);
+                const float dist = qzero ? 0.f : fmaf(-0.5f, acc, 0.5f);
+                if (rl[r] >= 0 && okey(dist) <= (uint32_t)(sel.thr >> 32)) {   // warp-uniform
+                    const uint32_t id = __shfl_sync(FULL, id_cur, rl[r]);
+                    const uint64_t key = make_key(dist, id);
+                    if (key < sel.thr) sel.insert(key, lane);
+                }
+            }
+        }
+        id_cur = id_nxt; v_cur = v_nxt; w_cur = w_nxt;
+        id_nxt = id_nx2; v_nxt = v_nx2;
+    }
+}
+
+template <int V, bool EXACT, int R, bool BIG, int OCC = (BIG ? 1 : 2), int LD = 0, bool FILT = false>
 __global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const ScanArgs a)
 {
     extern __shared__ __align__(16) uint64_t smem[];
@@ -150,6 +285,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const Scan
     const uint64_t n = a.n_rows;
     const uint64_t gw = (uint64_t)blockIdx.x * SCAN_WARPS + warp;
     const uint64_t stride = (uint64_t)gridDim.x * SCAN_WARPS * R;
+    if constexpr (FILT) scan_rows_filtered<V, EXACT, R, LD>(a, qv, qzero, sel, lane, gw, (uint64_t)gridDim.x * SCAN_WARPS);
+    else
     for (uint64_t base = gw * R; base < n; base += stride) {
         float4 x[R][V];
 #pragma unroll
@@ -176,7 +313,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const Scan
             if (row < n && okey(dist) <= (uint32_t)(sel.thr >> 32)) {  // warp-uniform, rare
                 const uint32_t id = a.ids[row];
                 const uint64_t key = make_key(dist, id);
-                if (key < sel.thr && id_allowed(a.bitmap, a.n_bits, id)) sel.insert(key, lane);
+                if (key < sel.thr) sel.insert(key, lane);
             }
         }
     }
@@ -217,7 +354,13 @@ __global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const Scan
             offer_lane_keys(sel, key, lane);
         }
     }
-    cta_reduce<BIG>(sel, smem, a.k, a.kpad, a.out_keys, warp, lane);
+    if (a.xchg == nullptr) {
+        cta_reduce<BIG>(sel, smem, a.k, a.kpad, a.out_keys, warp, lane);
+    } else {
+        // local top-k stays in smem[0..k) (cand[0] is a scratch destination), then exchange + global merge
+        cta_reduce<BIG>(sel, smem, a.k, a.kpad, a.cand, warp, lane);
+        exchange_and_merge<BIG>(a, sel, smem, warp, lane);
+    }
     if (threadIdx.x == 0) *a.ticket = 0;
 }
 

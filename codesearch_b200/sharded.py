@@ -37,12 +37,34 @@ def allgather_keys(local: torch.Tensor, world: int, group=None, out: torch.Tenso
     return out
 
 
+def connect_fused_exchange(store: VectorStore, rank: int, world: int, group=None) -> None:
+    """One-time setup of the fused exchange (include/csgpu.h): every rank creates its slot block, the 64-byte
+    cudaIpc handles are all-gathered on the host (the only use of the process group on this path), and each
+    rank maps its peers' blocks. After this, a search is ONE kernel per rank with peer stores over NVLink."""
+    lib = _lib.load()
+    mine = (ctypes.c_ubyte * _lib.EXCHANGE_HANDLE_BYTES)()
+    _lib.check(lib.csgpu_exchange_create(store.handle, world, rank, mine))
+    handles = [None] * world
+    dist.all_gather_object(handles, bytes(mine), group=group)
+    blob = (ctypes.c_ubyte * (_lib.EXCHANGE_HANDLE_BYTES * world)).from_buffer_copy(b"".join(handles))
+    _lib.check(lib.csgpu_exchange_connect(store.handle, blob))
+    dist.barrier(group=group)   # nobody searches before every rank has mapped every block
+
+
 class ShardedSearcher:
-    def __init__(self, store: VectorStore, k_max: int = _lib.MAX_K, group=None):
+    """exchange="nccl": local scan kernel -> NCCL all-gather of k keys -> merge kernel (3 launches per query).
+    exchange="fused": the scan kernel writes its keys into every peer's HBM and merges in its own tail
+    (1 launch per query, no collective library on the data path)."""
+
+    def __init__(self, store: VectorStore, k_max: int = _lib.MAX_K, group=None, exchange: str = "nccl"):
         self.store = store
         self.lib = _lib.load()
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.exchange = exchange if self.world > 1 else "none"
+        assert exchange in ("nccl", "fused")
+        if self.exchange == "fused":
+            connect_fused_exchange(store, dist.get_rank(group), self.world, group)
         self.dev = torch.device("cuda", torch.cuda.current_device())
         d = store.dimensions
         self.d_pad = (d + 3) // 4 * 4
@@ -56,6 +78,11 @@ class ShardedSearcher:
     # -- device-resident: q_dev is a [d_pad] float32 CUDA tensor; returns a view of k keys (int64 bits)
     def search_keys_device(self, q_dev: torch.Tensor, k: int) -> torch.Tensor:
         stream = torch.cuda.current_stream().cuda_stream
+        if self.exchange == "fused":
+            out = self.out[:k]
+            _lib.check(self.lib.csgpu_search_keys_exchange_device(self.store.handle, q_dev.data_ptr(), k,
+                                                                  out.data_ptr(), stream))
+            return out
         local = self.local[:k]
         _lib.check(self.lib.csgpu_search_keys_device(self.store.handle, q_dev.data_ptr(), k, local.data_ptr(), stream))
         if self.world == 1:

@@ -18,7 +18,9 @@ arithmetic and no fallback: every search is one call into the C ABI.
 from __future__ import annotations
 
 import ctypes
-from dataclasses import dataclass, field
+import json
+import os
+from dataclasses import asdict, dataclass, field
 from typing import Iterable, Sequence
 
 import numpy as np
@@ -124,11 +126,39 @@ class VectorStore:
         self.dtype = dtype
         code = {"fp32": _lib.DTYPE_F32, "bf16": _lib.DTYPE_BF16}[dtype]
         _lib.check(self._lib.csgpu_create(ctypes.byref(self._h), self.dimensions, code, devs, n))
+        self.read_only = False
+        if db_path is not None:
+            # store.rs:116 create_dir_all; :141-163 next_id = last key + 1, indexed = "Reader::open succeeds".
+            # Here: the device snapshot <db>/gpu (csgpu_save at build_index) plays arroy's part and
+            # <db>/chunks.jsonl the LMDB "chunks" table's (store.rs:135-136).
+            os.makedirs(db_path, exist_ok=True)
+            if os.path.exists(os.path.join(self._gpu_dir(), "meta.json")):
+                _lib.check(self._lib.csgpu_load(self._h, self._gpu_dir().encode()))
+                with open(os.path.join(db_path, "chunks.jsonl")) as f:
+                    for line in f:
+                        rec = json.loads(line)
+                        self._chunks[int(rec.pop("id"))] = Chunk(**rec)
+                if self._chunks:
+                    self.next_id = max(self._chunks) + 1
 
     # -- lifecycle ---------------------------------------------------------------------------
     @classmethod
     def new(cls, db_path, dimensions: int, devices: Sequence[int] | None = None, dtype: str = "fp32") -> "VectorStore":
         return cls(dimensions, devices=devices, db_path=db_path, dtype=dtype)
+
+    @classmethod
+    def open_readonly(cls, db_path, dimensions: int, devices: Sequence[int] | None = None, dtype: str = "fp32") -> "VectorStore":
+        """store.rs:183-250: searches while another process writes; mutations are refused."""
+        st = cls(dimensions, devices=devices, db_path=db_path, dtype=dtype)
+        st.read_only = True
+        return st
+
+    def _gpu_dir(self) -> str:
+        return os.path.join(self.db_path, "gpu")
+
+    def _check_writable(self) -> None:
+        if self.read_only:
+            raise CsgpuError(_lib.ERR_ARG, "VectorStore is open read-only")
 
     def close(self) -> None:
         if self._h:
@@ -146,6 +176,7 @@ class VectorStore:
 
     # -- write side --------------------------------------------------------------------------
     def insert_chunks_with_ids(self, chunks: Sequence[EmbeddedChunk]) -> list[int]:
+        self._check_writable()
         if not chunks:
             return []
         for c in chunks:
@@ -184,6 +215,7 @@ class VectorStore:
         _lib.check(self._lib.csgpu_reserve(self._h, total_rows))
 
     def delete_chunks(self, chunk_ids: Sequence[int]) -> int:
+        self._check_writable()
         if len(chunk_ids) == 0:
             return 0
         ids = np.ascontiguousarray(chunk_ids, dtype=np.uint32)
@@ -194,12 +226,31 @@ class VectorStore:
         return int(removed.value)
 
     def build_index(self) -> None:
+        self._check_writable()
         _lib.check(self._lib.csgpu_build(self._h))
+        if self.db_path is not None:
+            self.save_snapshot()
+
+    def save_snapshot(self) -> None:
+        """Sidecar snapshot: device rows/ids via csgpu_save + the chunk table."""
+        tmp = os.path.join(self.db_path, "chunks.jsonl.tmp")
+        with open(tmp, "w") as f:
+            for i in sorted(self._chunks):
+                f.write(json.dumps({"id": i, **asdict(self._chunks[i])}) + "\n")
+        os.replace(tmp, os.path.join(self.db_path, "chunks.jsonl"))
+        _lib.check(self._lib.csgpu_save(self._h, self._gpu_dir().encode()))
 
     def clear(self) -> None:
+        self._check_writable()
         _lib.check(self._lib.csgpu_clear(self._h))
         self._chunks.clear()
         self.next_id = 0
+        if self.db_path is not None:   # store.rs:690-706 clears both LMDB tables
+            for name in ("gpu/meta.json", "gpu/ids.u32", "gpu/rows.f32", "gpu/rows.bf16", "gpu/zero.u32", "chunks.jsonl"):
+                try:
+                    os.remove(os.path.join(self.db_path, name))
+                except FileNotFoundError:
+                    pass
 
     # -- search ------------------------------------------------------------------------------
     def search_ids(self, query_embedding, limit: int, filter: RowFilter | None = None):

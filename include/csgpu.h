@@ -102,6 +102,15 @@ int  csgpu_build(csgpu_index *ix);
 /* Drops every row; index is empty and NOT built (store.rs:690-706). */
 int  csgpu_clear(csgpu_index *ix);
 
+/* ---- snapshot / hydrate: HBM is volatile, LMDB is the reference's truth (store.rs:110-176: `new` reopens the
+ *      environment and probes Reader::open to learn `indexed`). csgpu_save writes a flat sidecar of a BUILT index,
+ *      <dir>/{meta.json, ids.u32, rows.f32 | rows.bf16, zero.u32} (rows exactly as they sit in HBM, checksummed,
+ *      published by rename with meta.json last); csgpu_load fills an EMPTY index of the same dim/dtype from it and
+ *      leaves it built: searches return bit-identical results to the index that was saved. A maintainer calls
+ *      csgpu_save at the end of build_index (store.rs:422-430) and csgpu_load in new/open_readonly. */
+int  csgpu_save(const csgpu_index *ix, const char *dir);
+int  csgpu_load(csgpu_index *ix, const char *dir);
+
 /* ---- search (VectorStore::search  store.rs:431-486, arroy block :446-459) -------------- */
 
 int  csgpu_search(const csgpu_index *ix, const float *q, uint32_t q_len, uint32_t k,
@@ -136,6 +145,27 @@ int  csgpu_search_keys_device(const csgpu_index *ix, const float *q_dev, uint32_
  * global top-k, ties by chunk id. keys_dev: [n_lists, k]. */
 int  csgpu_merge_keys_device(const csgpu_index *ix, const uint64_t *keys_dev, uint32_t n_lists,
                              uint32_t k, uint64_t *out_keys_dev /*[k]*/, void *stream);
+
+/* ---- fused cross-GPU exchange: rank-per-GPU sharding without a collective library on the data path.
+ * Each rank (one process per GPU) owns a slot block in its HBM that its peers write over NVLink. The scan
+ * kernel's last CTA stores the rank's k local keys straight into every peer's block, raises a sequence
+ * flag, waits for the peers' flags and merges: ONE kernel per query returns the GLOBAL top-k on every
+ * rank (replaces: scan kernel + NCCL all-gather + merge kernel). Every rank must issue the same sequence
+ * of csgpu_search_keys_exchange_device calls (same k), like any collective.
+ *   1. csgpu_exchange_create on every rank -> 64-byte handle
+ *   2. all-gather the handles (torch.distributed / MPI / a file: host side, once)
+ *   3. csgpu_exchange_connect with all world handles (cudaIpcOpenMemHandle on the peers' blocks)
+ * csgpu_exchange_connect_local wires indexes that live in ONE process (several GPUs, or tests).
+ * A peer that never arrives makes the wait time out after 4 s: results are then undefined and
+ * csgpu_exchange_status reports it. */
+#define CSGPU_EXCHANGE_HANDLE_BYTES 64
+int  csgpu_exchange_create(csgpu_index *ix, uint32_t world, uint32_t rank, void *out_handle /*[64]*/);
+int  csgpu_exchange_connect(csgpu_index *ix, const void *handles /*[world][64]; own entry ignored*/);
+int  csgpu_exchange_connect_local(csgpu_index *ix, csgpu_index *const *peers /*[world]*/);
+int  csgpu_search_keys_exchange_device(const csgpu_index *ix, const float *q_dev, uint32_t k,
+                                       uint64_t *out_keys_dev /*[k] global top-k*/, void *stream);
+int  csgpu_exchange_status(const csgpu_index *ix, uint32_t *timed_out);
+void csgpu_exchange_destroy(csgpu_index *ix);
 
 /* Host-side: keys -> (ids, distances); returns the number of non-empty slots in *out_n. */
 void csgpu_decode_keys(const uint64_t *keys, uint32_t k, uint32_t *out_ids, float *out_dist,
