@@ -44,6 +44,9 @@ def parse():
     p.add_argument("--cpu-seconds", type=float, default=12.0)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                   help="N>1: fused = scan kernel writes its keys into the peers' HBM and merges in its tail (1 launch); "
+                        "nccl = scan kernel + NCCL all-gather + merge kernel")
     return p.parse_args()
 
 
@@ -183,7 +186,7 @@ def main():
     store.reserve(n)
     store.append_synthetic(SEED_CORPUS, rank * n, n, 0)   # chunk id = global row index
     store.build_index()
-    searcher = ShardedSearcher(store, k_max=max(k, 16))
+    searcher = ShardedSearcher(store, k_max=max(k, 16), exchange=args.exchange)
 
     # queries: same generator, different seed; produced by the device generator, kept on host AND device
     q_host = np.empty((N_QUERIES, d), dtype=np.float32)
@@ -214,6 +217,11 @@ def main():
         if world == 1:
             scan_ev[i][0].record()
             searcher.search_keys_device(q, k)
+            scan_ev[i][1].record()
+        elif args.exchange == "fused":
+            scan_ev[i][0].record()     # one kernel: scan + peer stores over NVLink + flag wait + global merge
+            _lib.check(lib.csgpu_search_keys_exchange_device(store.handle, q.data_ptr(), k,
+                                                             searcher.out[:k].data_ptr(), stream))
             scan_ev[i][1].record()
         else:
             scan_ev[i][0].record()
@@ -261,7 +269,9 @@ def main():
                "qps": round(1e3 / e2e_ms, 3), "ms_per_step": round(e2e_ms, 4),
                "h2d_bytes_per_step": d * 4, "d2h_bytes_per_step": k * 8,
                "api": "VectorStore.search_ids -> csgpu_search (host pointers)" if world == 1 else
-                      "ShardedSearcher.search (pinned H2D, csgpu_search_keys_device, NCCL all-gather, csgpu_merge_keys_device, D2H)"}
+                      ("ShardedSearcher.search (pinned H2D, csgpu_search_keys_exchange_device: fused scan + peer-memory exchange + merge, D2H)"
+                       if args.exchange == "fused" else
+                       "ShardedSearcher.search (pinned H2D, csgpu_search_keys_device, NCCL all-gather, csgpu_merge_keys_device, D2H)")}
 
     if rank == 0:
         ms_per_step = elapsed_ms / args.steps
@@ -285,7 +295,9 @@ def main():
                                    f"single-query exact cosine top-{k} (BASELINE configs[1] per GPU)",
                        "rows_per_gpu": n, "dim": d, "k": k, "queries": N_QUERIES,
                        "l2": "no flush needed: 15.36 GB scanned per GPU per step >> 126 MB L2",
-                       "parallelism": f"row-shard x{world}" + ("" if world == 1 else " + NCCL all-gather of k keys + merge kernel")},
+                       "parallelism": f"row-shard x{world}" + ("" if world == 1 else (
+                           " + exchange fused into the scan kernel (peer stores over NVLink, flags, in-kernel merge)"
+                           if args.exchange == "fused" else " + NCCL all-gather of k keys + merge kernel"))},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic,
                          "kernel": "scan_topk_kernel<3,true,4,false>", "kernel_ms": round(kern_ms, 4),

@@ -40,6 +40,8 @@ class Stats(ctypes.Structure):
         ("last_search_us", ctypes.c_float),
         ("abi_version", ctypes.c_uint32),
         ("rows_per_device", ctypes.c_uint64 * 8),
+        ("coalesced_passes", ctypes.c_uint64),
+        ("coalesced_queries", ctypes.c_uint64),
     ]
 
 
@@ -61,7 +63,9 @@ SIGNATURES = {
     "csgpu_save": (ctypes.c_int, [_vp, ctypes.c_char_p]),
     "csgpu_load": (ctypes.c_int, [_vp, ctypes.c_char_p]),
     "csgpu_search": (ctypes.c_int, [_vp, _f32p, ctypes.c_uint32, ctypes.c_uint32, _u32p, _f32p, _u32p]),
+    "csgpu_set_coalescing": (ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32]),
     "csgpu_search_batch": (ctypes.c_int, [_vp, _f32p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _u32p, _f32p, _u32p]),
+    "csgpu_search_variants": (ctypes.c_int, [_vp, _f32p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _u32p, _f32p, _u32p]),
     "csgpu_search_filtered": (ctypes.c_int, [_vp, _f32p, ctypes.c_uint32, ctypes.c_uint32, _u64p, ctypes.c_uint64, _u32p, _f32p, _u32p]),
     "csgpu_search_keys_device": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, _vp, _vp]),
     "csgpu_merge_keys_device": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp]),

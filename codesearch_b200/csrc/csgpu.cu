@@ -5,10 +5,12 @@
 //   flips it back; search on a dirty index is an error (:440-444); clear (:690-706) empties.
 // There is no CPU fallback anywhere in this file: every search is a CUDA kernel launch.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <numeric>
+#include <thread>
 
 #include "index.h"
 #include "scan.cuh"
@@ -567,6 +569,108 @@ static int search_multi(const csgpu_index *ix, const float *q, uint32_t nq, uint
     return rc;
 }
 
+// b (<= MAX_BATCH) variants of one user query: searched in ceil(b/8) passes, lists kept on the device, deduplicated
+// by chunk id (best distance wins) and cut to the best k by dedup_variants_kernel. Single-device index.
+static int search_variants(const csgpu_index *ix, const float *q, uint32_t b, uint32_t k,
+                           uint32_t *out_ids, float *out_dist, uint32_t *out_n)
+{
+    Shard *sh = ix->shards[0];
+    SearchCtx *c = nullptr;
+    int rc = ctx_acquire(ix, sh, &c);
+    if (rc) return rc;
+    auto body = [&]() -> int {
+        DeviceGuard dg(sh->device);
+        const size_t qbytes = (size_t)b * ix->dim_pad * sizeof(float);
+        memset(c->q_pin, 0, qbytes);
+        for (uint32_t j = 0; j < b; ++j) memcpy(c->q_pin + (size_t)j * ix->dim_pad, q + (size_t)j * ix->dim, (size_t)ix->dim * sizeof(float));
+        CS_CUDA(cudaMemcpyAsync(c->q_dev, c->q_pin, qbytes, cudaMemcpyHostToDevice, c->stream));
+        CS_CUDA(cudaEventRecord(c->ev0, c->stream));
+        const uint32_t MQ = multi_scan_max_queries();
+        const bool multi_ok = multi_scan_supported(ix->dim4, k);
+        for (uint32_t j = 0; j < b;) {
+            const uint32_t nq = std::min(MQ, b - j);
+            int r;
+            if (multi_ok && nq >= 2) {
+                r = enqueue_scan_multi(ix, sh, c, c->q_dev + (size_t)j * ix->dim_pad, nq, k, true, c->out_dev + (size_t)j * k, c->stream);
+                j += nq;
+            } else {
+                r = enqueue_scan(ix, sh, c, c->q_dev + (size_t)j * ix->dim_pad, k, nullptr, 0, true, c->out_dev + (size_t)j * k, c->stream);
+                j += 1;
+            }
+            if (r) return r;
+        }
+        const uint32_t total = b * k, npad = pow2_at_least(total, 64);
+        const size_t smem = (size_t)npad * sizeof(uint64_t);
+        if (smem > 48 * 1024) CS_CUDA(cudaFuncSetAttribute(dedup_variants_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dedup_variants_kernel<<<1, SCAN_THREADS, smem, c->stream>>>(c->out_dev, total, npad, k, c->out_pin);
+        count_launch();
+        CS_CUDA(cudaGetLastError());
+        CS_CUDA(cudaEventRecord(c->ev1, c->stream));
+        CS_CUDA(cudaStreamSynchronize(c->stream));
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) ix->last_search_us.store(ms * 1000.f);
+        decode_keys(c->out_pin, k, out_ids, out_dist, out_n);
+        return CSGPU_OK;
+    };
+    rc = body();
+    if (rc) { DeviceGuard dg(sh->device); cudaStreamSynchronize(c->stream); }
+    ctx_release(sh, c);
+    return rc;
+}
+
+// One query through the micro-batcher (see Coalescer in index.h).
+static int search_coalesced(const csgpu_index *ix, const float *q, uint32_t k, uint32_t *out_ids, float *out_dist, uint32_t *out_n)
+{
+    Coalescer &co = ix->coalescer;
+    PendingSearch me{q, k, out_ids, out_dist, out_n};
+    std::unique_lock<std::mutex> lk(co.mu);
+    co.queue.push_back(&me);
+    const uint32_t MQ = multi_scan_max_queries();
+    while (!me.done) {
+        if (co.leader_active) { co.cv.wait(lk); continue; }
+        co.leader_active = true;
+        if (co.window_us && co.queue.size() < MQ) {
+            lk.unlock();
+            std::this_thread::sleep_for(std::chrono::microseconds(co.window_us));
+            lk.lock();
+        }
+        // one pass: up to MQ queued requests that share the k of the oldest one
+        std::vector<PendingSearch *> batch;
+        const uint32_t bk = co.queue.front()->k;
+        for (size_t i = 0; i < co.queue.size() && batch.size() < MQ;) {
+            if (co.queue[i]->k == bk) { batch.push_back(co.queue[i]); co.queue.erase(co.queue.begin() + i); }
+            else ++i;
+        }
+        lk.unlock();
+        int rc;
+        const uint32_t nb = (uint32_t)batch.size();
+        if (nb == 1) {
+            PendingSearch *r = batch[0];
+            rc = search_one(ix, r->q, bk, nullptr, 0, r->out_ids, r->out_dist, r->out_n);
+        } else {
+            std::vector<float> qs((size_t)nb * ix->dim);
+            std::vector<uint32_t> ids((size_t)nb * bk), ns(nb);
+            std::vector<float> dd((size_t)nb * bk);
+            for (uint32_t j = 0; j < nb; ++j) memcpy(qs.data() + (size_t)j * ix->dim, batch[j]->q, (size_t)ix->dim * sizeof(float));
+            rc = search_multi(ix, qs.data(), nb, bk, ids.data(), dd.data(), ns.data());
+            for (uint32_t j = 0; j < nb && !rc; ++j) {
+                memcpy(batch[j]->out_ids, ids.data() + (size_t)j * bk, (size_t)ns[j] * sizeof(uint32_t));
+                memcpy(batch[j]->out_dist, dd.data() + (size_t)j * bk, (size_t)ns[j] * sizeof(float));
+                if (batch[j]->out_n) *batch[j]->out_n = ns[j];
+            }
+        }
+        co.passes.fetch_add(1, std::memory_order_relaxed);
+        co.queries.fetch_add(nb, std::memory_order_relaxed);
+        const std::string err = rc ? t_error : std::string();
+        lk.lock();
+        for (PendingSearch *r : batch) { r->rc = rc; r->err = err; r->done = true; }
+        co.leader_active = false;
+        co.cv.notify_all();
+    }
+    if (me.rc) t_error = me.err;   // the error text is thread-local: hand the leader's message to this caller
+    return me.rc;
+}
+
 }  // namespace csgpu
 
 using namespace csgpu;
@@ -835,7 +939,18 @@ int csgpu_search(const csgpu_index *ix, const float *q, uint32_t q_len, uint32_t
     if (!all_finite(q, q_len)) return fail(CSGPU_ERR_ARG, "query contains NaN/Inf");
     if (k == 0) return CSGPU_OK;
     if (ix->dtype == CSGPU_DTYPE_BF16) return batch_search(ix, q, 1, k, out_ids, out_dist, out_n, nullptr);
+    if (ix->coalescer.enabled.load(std::memory_order_relaxed) && multi_scan_supported(ix->dim4, k))
+        return search_coalesced(ix, q, k, out_ids, out_dist, out_n);
     return search_one(ix, q, k, nullptr, 0, out_ids, out_dist, out_n);
+}
+
+int csgpu_set_coalescing(csgpu_index *ix, uint32_t enabled, uint32_t window_us)
+{
+    if (!ix) return fail(CSGPU_ERR_ARG, "null index");
+    std::lock_guard<std::mutex> lk(ix->coalescer.mu);
+    ix->coalescer.window_us = window_us;
+    ix->coalescer.enabled.store(enabled ? 1 : 0);
+    return CSGPU_OK;
 }
 
 int csgpu_search_filtered(const csgpu_index *ix, const float *q, uint32_t q_len, uint32_t k,
@@ -893,6 +1008,20 @@ int csgpu_search_batch(const csgpu_index *ix, const float *q, uint32_t q_len, ui
         }
     }
     return CSGPU_OK;
+}
+
+int csgpu_search_variants(const csgpu_index *ix, const float *q, uint32_t q_len, uint32_t b, uint32_t k,
+                          uint32_t *out_ids, float *out_dist, uint32_t *out_n)
+{
+    if (out_n) *out_n = 0;
+    int rc = check_search_args(ix, q, q_len, k);
+    if (rc) return rc;
+    if (b == 0 || b > MAX_BATCH) return fail(CSGPU_ERR_ARG, "b must be in [1, 16] query variants");
+    if (ix->dtype != CSGPU_DTYPE_F32) return fail(CSGPU_ERR_ARG, "csgpu_search_variants needs an fp32 index");
+    if (ix->shards.size() != 1) return fail(CSGPU_ERR_ARG, "csgpu_search_variants: multi-device index is not implemented yet");
+    if (!all_finite(q, q_len * b)) return fail(CSGPU_ERR_ARG, "query contains NaN/Inf");
+    if (k == 0) return CSGPU_OK;
+    return search_variants(ix, q, b, k, out_ids, out_dist, out_n);
 }
 
 int csgpu_search_keys_device(const csgpu_index *ix, const float *q_dev, uint32_t k, uint64_t *out_keys_dev, void *stream)
@@ -1093,6 +1222,8 @@ int csgpu_stats(const csgpu_index *ix, csgpu_stats_t *out)
         out->bytes_on_device += sh->cap * (row_bytes + sizeof(uint32_t) + 1) + sh->stage_cap * (size_t)ix->dim_pad * sizeof(float);
     }
     out->live_rows += ix->zero_ids.size();
+    out->coalesced_passes = ix->coalescer.passes.load();
+    out->coalesced_queries = ix->coalescer.queries.load();
     return CSGPU_OK;
 }
 

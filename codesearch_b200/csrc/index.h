@@ -1,6 +1,7 @@
 // index.h — host-side state of a csgpu_index (library-private; the public surface is include/csgpu.h).
 #pragma once
 #include <atomic>
+#include <condition_variable>
 #include <cstdint>
 #include <mutex>
 #include <string>
@@ -85,6 +86,27 @@ struct Exchange {
     size_t block_bytes() const { return slots_bytes() + (size_t)2 * world * sizeof(unsigned) + 64; }
 };
 
+// Host micro-batcher in front of csgpu_search. Concurrent single-query searches with the same k
+// (the <= 9 query variants of /root/reference/src/search/mod.rs:508-511 arrive from rayon threads; MCP/HTTP readers
+// from tokio tasks, src/mcp/mod.rs:251-252, src/server/mod.rs:545-548) are coalesced into ONE multi-query pass over
+// the corpus (scan_multi.cuh, up to 8 queries per pass). Group-commit style: the first caller to find no pass in
+// flight becomes the leader, takes whatever is queued and launches; callers arriving during a pass queue up and
+// ride the next one. An idle index therefore adds no latency to a lone query.
+struct PendingSearch {
+    const float *q; uint32_t k;
+    uint32_t *out_ids; float *out_dist; uint32_t *out_n;
+    int rc = 0; bool done = false; std::string err;
+};
+struct Coalescer {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<PendingSearch *> queue;
+    bool leader_active = false;
+    std::atomic<uint32_t> enabled{0};
+    uint32_t window_us = 0;               // optional: the leader lingers this long for company before launching
+    std::atomic<uint64_t> passes{0}, queries{0};
+};
+
 struct Shard {
     int device = 0;
     // bf16 index (dtype == CSGPU_DTYPE_BF16): built rows live here, pending rows in `stage` as fp32
@@ -148,4 +170,5 @@ struct csgpu_index {
     uint64_t tombstones = 0;
     mutable std::atomic<float> last_search_us{0.f};
     csgpu::Exchange *xchg = nullptr;      // rank-per-GPU fused exchange (csgpu_exchange_*)
+    mutable csgpu::Coalescer coalescer;   // csgpu_set_coalescing
 };

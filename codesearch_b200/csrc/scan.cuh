@@ -394,4 +394,36 @@ merge_keys_kernel(const uint64_t *__restrict__ keys, uint32_t n_lists, uint32_t 
     cta_reduce<BIG>(sel, smem, k, kpad, out + q_off, warp, lane);
 }
 
+// Device-side dedup of the per-variant lists of one user query (the HashMap + BinaryHeap pass at
+// /root/reference/src/search/mod.rs:513-590): keys [total] (any order, KEY_EMPTY = hole) -> per chunk id the entry
+// with the smallest distance -> the best k_out of the union, ascending (distance, id). One CTA; two bitonic sorts
+// in shared memory (by (id, distance), then by (distance, id)). npad = pow2 >= total.
+static __global__ void __launch_bounds__(SCAN_THREADS, 1)
+dedup_variants_kernel(const uint64_t *__restrict__ keys, uint32_t total, uint32_t npad, uint32_t k_out, uint64_t *__restrict__ out)
+{
+    extern __shared__ __align__(16) uint64_t smem[];
+    for (uint32_t t = threadIdx.x; t < npad; t += blockDim.x) {
+        const uint64_t key = t < total ? keys[t] : KEY_EMPTY;
+        smem[t] = key == KEY_EMPTY ? KEY_EMPTY : ((key << 32) | (key >> 32));   // (id, okey(distance))
+    }
+    cta_sort(smem, npad);
+    // keep the first (= closest) entry of every id run. Batches run from the top down: batch i reads element
+    // i*B - 1, which only a LOWER batch may overwrite later.
+    const uint32_t B = blockDim.x;
+    for (int64_t base = (int64_t)((npad - 1) / B) * B; base >= 0; base -= B) {
+        const uint32_t t = (uint32_t)base + threadIdx.x;
+        uint64_t v = KEY_EMPTY;
+        if (t < npad) {
+            const uint64_t cur = smem[t];
+            const bool dup = cur == KEY_EMPTY || (t > 0 && (smem[t - 1] >> 32) == (cur >> 32));
+            v = dup ? KEY_EMPTY : ((cur << 32) | (cur >> 32));                   // back to (okey(distance), id)
+        }
+        __syncthreads();
+        if (t < npad) smem[t] = v;
+        __syncthreads();
+    }
+    cta_sort(smem, npad);
+    for (uint32_t j = threadIdx.x; j < k_out; j += blockDim.x) out[j] = j < npad ? smem[j] : KEY_EMPTY;
+}
+
 }  // namespace csgpu

@@ -137,7 +137,8 @@ class VectorStore:
                 with open(os.path.join(db_path, "chunks.jsonl")) as f:
                     for line in f:
                         rec = json.loads(line)
-                        self._chunks[int(rec.pop("id"))] = Chunk(**rec)
+                        cid = int(rec.pop("id"))
+                        self._chunks[cid] = Chunk(**rec)
                 if self._chunks:
                     self.next_id = max(self._chunks) + 1
 
@@ -283,6 +284,26 @@ class VectorStore:
                                                 oi.ctypes.data_as(_lib._u32p), od.ctypes.data_as(_lib._f32p),
                                                 on.ctypes.data_as(_lib._u32p)))
         return oi, od, on
+
+    def search_variants_ids(self, queries, limit: int):
+        """<= 16 query variants of one user query -> one deduplicated list (src/search/mod.rs:508-590 on the device)."""
+        q = _f32(queries)
+        b, d = q.shape
+        k = int(limit)
+        oi = np.empty(max(k, 1), dtype=np.uint32)
+        od = np.empty(max(k, 1), dtype=np.float32)
+        on = ctypes.c_uint32(0)
+        _lib.check(self._lib.csgpu_search_variants(self._h, q.ctypes.data_as(_lib._f32p), d, b, k,
+                                                   oi.ctypes.data_as(_lib._u32p), od.ctypes.data_as(_lib._f32p),
+                                                   ctypes.byref(on)))
+        return oi[: on.value].copy(), od[: on.value].copy()
+
+    def search_variants(self, queries, limit: int) -> list[SearchResult]:
+        return self._join(*self.search_variants_ids(queries, limit))
+
+    def set_coalescing(self, enabled: bool, window_us: int = 0) -> None:
+        """Host micro-batcher: concurrent search() calls with the same limit share one pass over the corpus."""
+        _lib.check(self._lib.csgpu_set_coalescing(self._h, 1 if enabled else 0, int(window_us)))
 
     def _join(self, ids, dist) -> list[SearchResult]:
         out = []

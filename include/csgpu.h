@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define CSGPU_ABI_VERSION 1
+#define CSGPU_ABI_VERSION 2
 
 enum {
     CSGPU_OK            = 0,
@@ -74,6 +74,8 @@ typedef struct csgpu_stats_t {
     float    last_search_us;   /* device time of the most recent search (CUDA events)          */
     uint32_t abi_version;
     uint64_t rows_per_device[8];
+    uint64_t coalesced_passes;   /* micro-batcher: corpus passes launched ...                       */
+    uint64_t coalesced_queries;  /* ... for this many csgpu_search calls (csgpu_set_coalescing)     */
 } csgpu_stats_t;
 
 /* ---- lifecycle (VectorStore::new / open_readonly  store.rs:110-176,183-250) ------------ */
@@ -116,10 +118,24 @@ int  csgpu_load(csgpu_index *ix, const char *dir);
 int  csgpu_search(const csgpu_index *ix, const float *q, uint32_t q_len, uint32_t k,
                   uint32_t *out_ids /*[k]*/, float *out_dist /*[k]*/, uint32_t *out_n);
 
+/* Host micro-batcher (off by default). When enabled, concurrent csgpu_search calls with the same k are coalesced
+ * into one multi-query pass over the corpus (up to 8 per pass) — the caller pattern of src/search/mod.rs:508-511
+ * (rayon par_iter over <= 9 query variants) and of concurrent MCP/HTTP readers. Results are bit-identical to the
+ * uncoalesced call. window_us > 0 lets a pass linger that long for company before launching (0 = never wait:
+ * only requests that arrive while a pass is in flight get batched). */
+int  csgpu_set_coalescing(csgpu_index *ix, uint32_t enabled, uint32_t window_us);
+
 /* b queries [b, dim]; outputs [b, k] (row j holds out_n[j] valid entries). Serves the
  * <= 9 query variants of src/search/mod.rs:508-511 in one pass over the corpus. */
 int  csgpu_search_batch(const csgpu_index *ix, const float *q, uint32_t q_len, uint32_t b, uint32_t k,
                         uint32_t *out_ids, float *out_dist, uint32_t *out_n /*[b]*/);
+
+/* b (<= 16) query VARIANTS of one user query (query expansion, src/search/mod.rs:479-483), searched with the same
+ * limit and merged on the device: per chunk id the best (smallest) distance over the variants, then the best k of
+ * the union, ascending (distance, id). Replaces the par_iter of searches plus the HashMap/BinaryHeap dedup at
+ * src/search/mod.rs:508-590 with ceil(b/8) corpus passes and one merge kernel; outputs [k]. */
+int  csgpu_search_variants(const csgpu_index *ix, const float *q /*[b, dim]*/, uint32_t q_len, uint32_t b, uint32_t k,
+                           uint32_t *out_ids, float *out_dist, uint32_t *out_n);
 
 /* Exact top-k over rows whose chunk id has its bit set (bit i of id_bitmap[i/64]); ids >=
  * n_bits are excluded. New capability: the reference only post-filters on the host

@@ -290,6 +290,20 @@ def np_search_bf16(rows, q, k, ids=None):
     return ids[order], d32[order], d64[order]
 
 
+def dedup_variants(lists, k):
+    """src/search/mod.rs:513-590 restated: the per-variant result lists of ONE user query are merged keeping, per
+    chunk id, the entry with the best score (= smallest distance), then the top `k` of the union are returned best
+    first. The reference pops a BinaryHeap fed from a HashMap, so ties come out in arbitrary order; here ties break
+    by ascending id (the store's own order). lists: iterable of (ids, dist32). Returns (ids u32, dist f32)."""
+    best = {}
+    for ids, dist in lists:
+        for i, d in zip(np.asarray(ids).tolist(), np.asarray(dist, dtype=np.float32).tolist()):
+            if i not in best or d < best[i]:
+                best[i] = d
+    order = sorted(best.items(), key=lambda t: (np.float32(t[1]), t[0]))[:k]
+    return (np.array([i for i, _ in order], dtype=np.uint32), np.array([d for _, d in order], dtype=np.float32))
+
+
 def score_from_distance(distance):
     """store.rs:478."""
     return np.float32(1.0) - np.asarray(distance, dtype=np.float32)
