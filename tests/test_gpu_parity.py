@@ -142,6 +142,14 @@ def test_parity_synthetic_100k_config0(cs, oracle):
         swaps += assert_parity(oracle, st, rows, q, 10)
         swaps += assert_parity(oracle, st, rows, q, 100)
     assert swaps == 0   # these seeds have no near-ties: ids are bit-exact
+    # the committed golden fixture (tests/golden/c1_100k_top10.json): ids identical, distances within 1e-5
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c1_100k_top10.json")))
+    for q, want in zip(qs, g["queries"]):
+        gi, gd = st.search_ids(q, 10)
+        assert gi.tolist() == want["ids"]
+        assert np.abs(gd.astype(np.float64) - np.array(want["distance_f64"])).max() <= 1e-5
     # device generator == CPU generator, bit for bit
     host = np.empty((257, d), dtype=np.float32)
     from codesearch_b200 import _lib

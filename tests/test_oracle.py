@@ -136,3 +136,58 @@ def test_rrf_consumer_contract(oracle):
     # src/rerank/mod.rs:57-59: rank = position, score = 1/(k + rank + 1)
     s = oracle.rrf_scores([7, 3, 9], 60.0)
     assert s[7] == pytest.approx(1 / 61) and s[3] == pytest.approx(1 / 62) and s[9] == pytest.approx(1 / 63)
+
+
+# ---- committed golden fixtures (tests/golden/, regenerated by tests/golden/make_golden.py) ---------------
+def _golden(name):
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)))
+
+
+def test_golden_reference_kats(oracle):
+    g = _golden("reference_kats.json")
+    c = g["insert_and_search"]
+    rows, q = np.array(c["rows"], np.float32), np.array(c["query"], np.float32)
+    ids, dist, _ = oracle.search(rows, q, c["limit"])
+    assert ids.tolist() == c["expect_ids"] and len(ids) == c["expect_len"]
+    assert np.allclose(dist, c["implied_distance"], atol=2e-7)
+    assert np.allclose(oracle.score_from_distance(dist), c["implied_score"], atol=2e-7)
+    for case in g["cosine_similarity"]["cases"]:
+        s = float(oracle.py_cosine_similarity(case["a"], case["b"]))
+        if "approx" in case:
+            assert abs(s - case["approx"]) < case["tol"]
+        else:
+            assert case["between"][0] < s < case["between"][1]
+    z = g["cosine_similarity"]["zero_norm"]
+    assert oracle.c_cosine(z["a"], z["b"], guarded=True) == z["guarded_helper_returns"]
+    r = g["rrf"]
+    s = oracle.rrf_scores(r["ranked_ids"], r["k"])
+    assert [s[i] for i in r["ranked_ids"]] == pytest.approx(r["scores"])
+    for case in g["distance_scale"]["cases"]:
+        a = np.array([1, 0], np.float32)
+        b = np.array([case["cos"], np.sqrt(max(0.0, 1 - case["cos"] ** 2))], np.float32)
+        assert oracle.c_distance_f32(a, b) == pytest.approx(case["distance"], abs=1e-7)
+
+
+def test_golden_c1_config0(oracle):
+    g = _golden("c1_100k_top10.json")
+    rows = oracle.synth_rows(1234, 0, 100_000, 384)
+    qs = oracle.synth_rows(4321, 0, len(g["queries"]), 384)
+    for q, want in zip(qs, g["queries"]):
+        for fn in (oracle.search, oracle.np_search):                 # C and numpy restatements both hit the fixture
+            ids, d32, d64 = fn(rows, q, 10)
+            assert ids.tolist() == want["ids"]
+            assert [float(x).hex() for x in d32] == want["distance_f32_hex"]
+            assert np.allclose(d64, want["distance_f64"], atol=1e-12)
+
+
+def test_dedup_variants_restatement(oracle):
+    # src/search/mod.rs:513-590: per id the best score over the variant lists, top-N of the union, best first
+    lists = [(np.array([5, 2, 9], np.uint32), np.array([0.10, 0.20, 0.30], np.float32)),
+             (np.array([2, 7, 5], np.uint32), np.array([0.05, 0.20, 0.25], np.float32)),
+             (np.array([], np.uint32), np.array([], np.float32))]
+    ids, dist = oracle.dedup_variants(lists, 3)
+    assert ids.tolist() == [2, 5, 7] and dist.tolist() == [np.float32(0.05), np.float32(0.10), np.float32(0.20)]
+    ids, dist = oracle.dedup_variants(lists, 10)
+    assert ids.tolist() == [2, 5, 7, 9]
