@@ -227,6 +227,7 @@ int batch_after_build(const csgpu_index *ix, Shard *sh)
     sh->map_valid = false;
     if (ix->dtype == CSGPU_DTYPE_BF16) {
         int rc = make_map(&sh->map_c, sh->rows_bf16 ? sh->rows_bf16 : (void *)sh->ids, sh->n_built, ix->dim, GT_BLOCK_N, false);
+        if (!rc) rc = make_map(&sh->map_c2, sh->rows_bf16 ? sh->rows_bf16 : (void *)sh->ids, sh->n_built, ix->dim, GT_BLOCK_N / 2, false);
         if (rc) return rc;
     } else {
         if (!batch_f32_dim_supported(ix->dim_pad) || sh->rows == nullptr) return CSGPU_OK;
@@ -304,6 +305,32 @@ static int launch_gemm(const csgpu_index *ix, Shard *sh, BatchCtx *c, const CUte
         const size_t avail = 227 * 1024 - 1024 /*alignment slack*/ - 256 /*static*/ - q_bytes;
         const int stages = (int)std::min<size_t>(4, avail / GT_STAGE_BYTES);
         if (stages < 2) return fail(CSGPU_ERR_ARG, "dim too large for the bf16 kernel's shared-memory plan");
+        // CTA-pair kernel (cta_group::2, M = 256): correct (same tests) but measured 4-7 % SLOWER than the one-CTA kernel
+        // (profiles/r01_bf16_2cta.txt: 9.06 vs 8.44 ms at B=1024,k=100) — under the 1 kW cap the MMA rate, not the
+        // operand stream, is what binds — so it is opt-in: CSGPU_BF16_2CTA=1
+        static const int env_2cta = getenv("CSGPU_BF16_2CTA") ? atoi(getenv("CSGPU_BF16_2CTA")) : 0;
+        if (env_2cta && n_qblocks >= 2 && n_qblocks % 2 == 0) {
+            const size_t avail2 = 227 * 1024 - 1024 - 512 - q_bytes;
+            const int st2 = (int)std::min<size_t>(8, avail2 / GT2_STAGE_BYTES);
+            if (st2 >= 4) {
+                const size_t smem2 = q_bytes + (size_t)st2 * GT2_STAGE_BYTES + 1024;
+                const uint32_t n_qpairs = n_qblocks / 2;
+                const uint32_t pairs = std::max<uint32_t>((uint32_t)sh->sm_count / 2, 1);
+                const uint32_t groups2 = (uint32_t)std::min<uint64_t>(std::max<uint32_t>(pairs / n_qpairs, 1), n_tiles);
+                const uint32_t grid2 = groups2 * n_qpairs * 2;
+#define CS_GT2(S)                                                                                                    \
+    case S:                                                                                                          \
+        e = cudaFuncSetAttribute(gemm_topk2_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);     \
+        if (e == cudaSuccess) gemm_topk2_kernel<S><<<grid2, GT_THREADS, smem2, c->stream>>>(map_q, sh->map_c2, a);   \
+        break;
+                switch (st2) { CS_GT2(4) CS_GT2(5) CS_GT2(6) CS_GT2(7) CS_GT2(8) }
+#undef CS_GT2
+                count_launch();
+                if (e == cudaSuccess) e = cudaGetLastError();
+                if (e != cudaSuccess) return fail_cuda(e, "gemm_topk2_kernel launch", __FILE__, __LINE__);
+                return CSGPU_OK;
+            }
+        }
         const size_t smem = q_bytes + (size_t)stages * GT_STAGE_BYTES + 1024;
         const uint32_t groups = (uint32_t)std::min<uint64_t>(std::max<uint32_t>(sh->sm_count / n_qblocks, 1), n_tiles);
         const uint32_t grid = groups * n_qblocks;
@@ -382,7 +409,9 @@ static int batch_search_shard(const csgpu_index *ix, Shard *sh, BatchCtx *c, con
 {
     DeviceGuard g(sh->device);
     const bool bf16 = ix->dtype == CSGPU_DTYPE_BF16;
-    const uint32_t n_qblocks = (nq + GT_BLOCK_M - 1) / GT_BLOCK_M;
+    uint32_t n_qblocks = (nq + GT_BLOCK_M - 1) / GT_BLOCK_M;
+    static const bool pad_even = getenv("CSGPU_BF16_2CTA") && atoi(getenv("CSGPU_BF16_2CTA")) != 0;
+    if (pad_even && bf16 && n_qblocks >= 2 && (n_qblocks & 1)) ++n_qblocks;   // CTA pairs take two query blocks each
     const uint32_t nq_pad = n_qblocks * GT_BLOCK_M;
     memcpy(c->q_pin, q_host, (size_t)nq * ix->dim * sizeof(float));
     CS_CUDA(cudaMemcpyAsync(c->q_f32, c->q_pin, (size_t)nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
@@ -413,7 +442,8 @@ static int batch_search_shard(const csgpu_index *ix, Shard *sh, BatchCtx *c, con
         rc = run_range(ix, sh, c, map_q, n_qblocks, nq, k, done, t1, 0);
         if (rc) return rc;
         done = t1;
-        next = done * (BF_PHASE_GROWTH - 1);   // each phase scans (growth-1) x everything seen so far
+        static const uint64_t growth = getenv("CSGPU_BATCH_GROWTH") ? std::max(2, atoi(getenv("CSGPU_BATCH_GROWTH"))) : BF_PHASE_GROWTH;
+        next = done * (growth - 1);   // each phase scans (growth-1) x everything seen so far
     }
     CS_CUDA(cudaMemcpyAsync(c->count_saved, c->count, nq_pad * sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
     return launch_select(ix, sh, c, nq_pad, nq, k, true);

@@ -114,6 +114,7 @@ struct Shard {
     float *stage = nullptr;        // [stage_cap, dim] fp32, rows appended since the last build
     uint64_t stage_cap = 0;
     CUtensorMap map_c;             // TMA map over the built rows (bf16 or fp32), re-encoded at every build
+    CUtensorMap map_c2;            // bf16 only: same matrix, box = 128 rows (one CTA's half tile in the CTA-pair kernel)
     bool map_valid = false;
     BatchCtx *batch = nullptr;
     std::mutex batch_mu;

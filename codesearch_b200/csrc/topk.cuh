@@ -169,6 +169,45 @@ __device__ __forceinline__ void cta_sort(uint64_t *s, uint32_t n)
     __syncthreads();
 }
 
+// ----------------------------------------------------------------------------------------
+// 32 < k <= 1024, CTA-shared: ONE candidate buffer of `cap` (pow2) keys per query for the whole CTA instead of
+// a sorted list per warp (8 warps x 2 x kpad keys = 128 KB at k = 1000, i.e. one CTA per SM and 30 % of the
+// bandwidth gone). A row that beats the CTA's threshold is appended with one shared-memory atomic; when the
+// buffer comes within `slack` of full the whole CTA sorts it (bitonic, in place), keeps the best k and
+// publishes the k-th key as the new threshold. The threshold is always the k-th best of a subset of the rows,
+// so nothing that belongs to the final top-k is ever rejected; it is merely up to one refill stale.
+// Expected refills per CTA ~ k ln(rows_per_cta / k) / (cap - k - slack): a handful.
+// ----------------------------------------------------------------------------------------
+struct CtaBuf {
+    uint64_t *buf;            // [cap] shared
+    unsigned *cnt;            // shared: entries appended (never exceeds cap when the caller honours `slack`)
+    volatile uint64_t *thr;   // shared: current threshold key (KEY_EMPTY until k entries have been seen)
+
+    // warp-uniform call, key already tested against *thr by the caller
+    __device__ __forceinline__ void append(uint64_t key, int lane)
+    {
+        if (lane == 0) {
+            const unsigned pos = atomicAdd(cnt, 1u);
+            buf[pos] = key;
+        }
+    }
+};
+
+// CTA-wide: sort buf[0..cap) (entries >= *cnt are holes), keep the best k, publish the threshold.
+// Every thread of the CTA must call it (it synchronises).
+__device__ __forceinline__ void cta_buf_compact(uint64_t *buf, unsigned *cnt, volatile uint64_t *thr, uint32_t cap, uint32_t k)
+{
+    __syncthreads();
+    const unsigned n = min(*cnt, cap);
+    for (uint32_t t = n + threadIdx.x; t < cap; t += blockDim.x) buf[t] = KEY_EMPTY;
+    cta_sort(buf, cap);   // leading + trailing __syncthreads inside
+    if (threadIdx.x == 0) {
+        *cnt = min(n, k);
+        if (n >= k) *thr = buf[k - 1];
+    }
+    __syncthreads();
+}
+
 __host__ __device__ __forceinline__ uint32_t pow2_at_least(uint32_t x, uint32_t lo)
 {
     uint32_t p = lo;
