@@ -101,8 +101,8 @@ static void ctx_release(Shard *sh, SearchCtx *c)
 // scan dispatch
 // ---------------------------------------------------------------------------------------
 // OCC = resident CTAs per SM. The scan needs ~96 KB of loads in flight per SM (profiles/r01_tune_scan.txt:
-// occupancy 1 loses 30 %), so the big-k selector also runs 2 CTAs/SM while its lists fit (kpad <= 512:
-// 2 x 8 warps x 512 keys x 8 B = 64 KB per CTA).
+// occupancy 1 loses 30 %); the big-k selector is one CTA-shared buffer of <= 4096 keys (32 KB), so every k runs
+// 2 CTAs/SM.
 template <int V, bool EXACT, bool BIG, int OCC>
 static cudaError_t launch_scan_v(const ScanArgs &a, uint32_t grid, size_t smem, cudaStream_t st)
 {
@@ -151,7 +151,7 @@ static int enqueue_scan(const csgpu_index *ix, const Shard *sh, SearchCtx *c, co
     a.q = q_dev;
     a.k = k;
     const bool big = k > 32;
-    a.kpad = big ? pow2_at_least(k, 64) : 32;
+    a.kpad = big ? ctabuf_cap(k) : 32;   // big k: capacity of the CTA-shared candidate buffer (topk.cuh CtaBuf)
     a.bitmap = bitmap_dev;
     a.n_bits = n_bits;
     a.zero_ids = with_zero_ids ? ix->zero_ids_dev : nullptr;
@@ -165,19 +165,16 @@ static int enqueue_scan(const csgpu_index *ix, const Shard *sh, SearchCtx *c, co
     uint64_t want = (sh->n_built + per_cta_rows - 1) / per_cta_rows;
     if (bitmap_dev != nullptr) {   // filtered: pre-filter variant (scan_filtered.cu)
         const uint64_t want32 = (sh->n_built + 32 * SCAN_WARPS - 1) / (32 * SCAN_WARPS);
-        const uint32_t occf = (big && a.kpad > 512) ? 1 : 2;
-        const uint32_t gridf = (uint32_t)std::min<uint64_t>((uint64_t)sh->sm_count * occf, std::max<uint64_t>(want32, 1));
-        const size_t smemf = big ? (size_t)2 * SCAN_WARPS * a.kpad * sizeof(uint64_t) : (size_t)SCAN_WARPS * 32 * sizeof(uint64_t);
+        const uint32_t gridf = (uint32_t)std::min<uint64_t>((uint64_t)sh->sm_count * 2, std::max<uint64_t>(want32, 1));
+        const size_t smemf = big ? (size_t)a.kpad * sizeof(uint64_t) : (size_t)SCAN_WARPS * 32 * sizeof(uint64_t);
         cudaError_t ef = launch_scan_filtered(a, gridf, smemf, st);
         if (ef != cudaSuccess) return fail_cuda(ef, "scan_topk_kernel (filtered) launch", __FILE__, __LINE__);
         return CSGPU_OK;
     }
-    const uint32_t occ = (big && a.kpad > 512) ? 1 : 2;
-    uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sh->sm_count * occ, std::max<uint64_t>(want, 1));
+    uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sh->sm_count * 2, std::max<uint64_t>(want, 1));
     if (grid > MAX_GRID) grid = MAX_GRID;
-    const size_t smem = big ? (size_t)2 * SCAN_WARPS * a.kpad * sizeof(uint64_t) : (size_t)SCAN_WARPS * 32 * sizeof(uint64_t);
-    cudaError_t e = !big ? launch_scan_b<false, 2>(a, grid, smem, st)
-                         : (occ == 2 ? launch_scan_b<true, 2>(a, grid, smem, st) : launch_scan_b<true, 1>(a, grid, smem, st));
+    const size_t smem = big ? (size_t)a.kpad * sizeof(uint64_t) : (size_t)SCAN_WARPS * 32 * sizeof(uint64_t);
+    cudaError_t e = !big ? launch_scan_b<false, 2>(a, grid, smem, st) : launch_scan_b<true, 2>(a, grid, smem, st);
     if (e != cudaSuccess) return fail_cuda(e, "scan_topk_kernel launch", __FILE__, __LINE__);
     return CSGPU_OK;
 }

@@ -136,6 +136,11 @@ template <bool BIG>
 struct SelOf { using type = WarpSel32; };
 template <>
 struct SelOf<true> { using type = WarpSelBig; };
+// selectors of the scan kernels proper: per-warp registers for k <= 32, one CTA-shared buffer above
+template <bool BIG>
+struct ScanSelOf { using type = WarpSel32; };
+template <>
+struct ScanSelOf<true> { using type = CtaSel; };
 
 // Tail of the last CTA when a.xchg is set. Precondition: smem[0..k) holds this rank's sorted local top-k
 // (left there by cta_reduce) and all threads are past a barrier.
@@ -163,22 +168,26 @@ __device__ __forceinline__ void exchange_and_merge(const ScanArgs &a, Sel &sel, 
         __threadfence_system();
     }
     __syncthreads();
-    if constexpr (BIG) {
-        sel.init(smem + (size_t)warp * a.kpad, smem + (size_t)(SCAN_WARPS + warp) * a.kpad, a.k, a.kpad, lane);
-    } else {
-        sel.init(a.k);
-    }
     const volatile uint64_t *mine = x.slots[R] + (size_t)par * W * KM;   // volatile: peers wrote it, L1 may be stale
     const uint32_t total = W * k;
-    for (uint32_t b = (uint32_t)warp * 32; b < total; b += SCAN_WARPS * 32) {
-        uint64_t key = KEY_EMPTY;
-        if (b + lane < total) {
-            const uint32_t t = b + lane, r = t / k, j = t - r * k;
-            key = mine[(size_t)r * KM + j];
+    if constexpr (BIG) {
+        sel.reset();
+        cta_buf_stream(sel.cb, sel.cap, k, total, [&](uint64_t t) { const uint32_t r = (uint32_t)t / k, j = (uint32_t)t - r * k; return mine[(size_t)r * KM + j]; });
+        sel.finish();
+        for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) a.out_keys[j] = smem[j];
+        __syncthreads();
+    } else {
+        sel.init(a.k);
+        for (uint32_t b = (uint32_t)warp * 32; b < total; b += SCAN_WARPS * 32) {
+            uint64_t key = KEY_EMPTY;
+            if (b + lane < total) {
+                const uint32_t t = b + lane, r = t / k, j = t - r * k;
+                key = mine[(size_t)r * KM + j];
+            }
+            offer_lane_keys(sel, key, lane);
         }
-        offer_lane_keys(sel, key, lane);
+        cta_reduce<false>(sel, smem, a.k, a.kpad, a.out_keys, warp, lane);
     }
-    cta_reduce<BIG>(sel, smem, a.k, a.kpad, a.out_keys, warp, lane);
 }
 
 // V = float4 per lane (ceil(dim4/32)); EXACT: dim4 == 32*V; R = rows in flight per warp.
@@ -206,7 +215,12 @@ __device__ __forceinline__ void scan_rows_filtered(const ScanArgs &a, const floa
     uint32_t id_cur = load_id(gw, v_cur);
     uint64_t w_cur = load_word(id_cur, v_cur);
     uint32_t id_nxt = load_id(gw + n_warps, v_nxt);
-    for (uint64_t b = gw; b < n_blocks; b += n_warps) {
+    // the trip count is the same for every warp of the CTA (the CTA-shared selector synchronises inside the loop);
+    // blocks past the end are fully predicated off by load_id
+    const uint64_t b_first = gw - (gw % SCAN_WARPS);
+    const uint64_t n_iters = b_first < n_blocks ? (n_blocks - b_first + n_warps - 1) / n_warps : 0;
+    uint64_t b = gw;
+    for (uint64_t it = 0; it < n_iters; ++it, b += n_warps) {
         const uint64_t w_nxt = load_word(id_nxt, v_nxt);
         const uint32_t id_nx2 = load_id(b + 2 * n_warps, v_nx2);
         unsigned m = __ballot_sync(FULL, (w_cur >> (id_cur & 63)) & 1ull);
@@ -247,6 +261,7 @@ __device__ __forceinline__ void scan_rows_filtered(const ScanArgs &a, const floa
         }
         id_cur = id_nxt; v_cur = v_nxt; w_cur = w_nxt;
         id_nxt = id_nx2; v_nxt = v_nx2;
+        if constexpr (Sel::CTA_SHARED) { if (it & 1) sel.sync_point(2 * 32 * SCAN_WARPS); }
     }
 }
 
@@ -256,10 +271,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const Scan
     extern __shared__ __align__(16) uint64_t smem[];
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    using Sel = typename SelOf<BIG>::type;
+    // k <= 32: per-warp register selector. k > 32: ONE candidate buffer per CTA (a.kpad = its capacity) + threshold
+    using Sel = typename ScanSelOf<BIG>::type;
+    __shared__ unsigned cb_cnt;
+    __shared__ uint64_t cb_thr;
     Sel sel;
     if constexpr (BIG) {
-        sel.init(smem + (size_t)warp * a.kpad, smem + (size_t)(SCAN_WARPS + warp) * a.kpad, a.k, a.kpad, lane);
+        sel.cb.buf = smem; sel.cb.cnt = &cb_cnt; sel.cb.thr = &cb_thr; sel.cap = a.kpad; sel.k = a.k;
+        sel.reset();
     } else {
         sel.init(a.k);
     }
@@ -284,10 +303,15 @@ __global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const Scan
     // ---- stream the rows ---------------------------------------------------------------
     const uint64_t n = a.n_rows;
     const uint64_t gw = (uint64_t)blockIdx.x * SCAN_WARPS + warp;
-    const uint64_t stride = (uint64_t)gridDim.x * SCAN_WARPS * R;
-    if constexpr (FILT) scan_rows_filtered<V, EXACT, R, LD>(a, qv, qzero, sel, lane, gw, (uint64_t)gridDim.x * SCAN_WARPS);
+    const uint64_t n_warps = (uint64_t)gridDim.x * SCAN_WARPS;
+    // same trip count for every warp of the CTA (rows past the end are predicated off): the CTA-shared selector
+    // synchronises every 8 iterations
+    const uint64_t n_groups = (n + R - 1) / R, g_first = (uint64_t)blockIdx.x * SCAN_WARPS;
+    const uint64_t n_iters = g_first < n_groups ? (n_groups - g_first + n_warps - 1) / n_warps : 0;
+    if constexpr (FILT) scan_rows_filtered<V, EXACT, R, LD>(a, qv, qzero, sel, lane, gw, n_warps);
     else
-    for (uint64_t base = gw * R; base < n; base += stride) {
+    for (uint64_t it = 0; it < n_iters; ++it) {
+        const uint64_t base = (gw + it * n_warps) * R;
         float4 x[R][V];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -316,10 +340,18 @@ __global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const Scan
                 if (key < sel.thr) sel.insert(key, lane);
             }
         }
+        if constexpr (BIG) { if ((it & 7) == 7) sel.sync_point(8 * R * SCAN_WARPS); }
     }
 
     // ---- CTA top-k -> cand[blockIdx.x] ---------------------------------------------------
-    cta_reduce<BIG>(sel, smem, a.k, a.kpad, a.cand + (size_t)blockIdx.x * a.k, warp, lane);
+    if constexpr (BIG) {
+        sel.finish();
+        uint64_t *dst = a.cand + (size_t)blockIdx.x * a.k;
+        for (uint32_t j = threadIdx.x; j < a.k; j += blockDim.x) dst[j] = smem[j];
+        __syncthreads();
+    } else {
+        cta_reduce<false>(sel, smem, a.k, a.kpad, a.cand + (size_t)blockIdx.x * a.k, warp, lane);
+    }
 
     // ---- last CTA merges all CTAs' results (threadfence-reduction pattern) ---------------
     __threadfence();
@@ -331,35 +363,53 @@ __global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const Scan
     if (!is_last) return;
     __threadfence();
 
-    if constexpr (BIG) {
-        sel.init(smem + (size_t)warp * a.kpad, smem + (size_t)(SCAN_WARPS + warp) * a.kpad, a.k, a.kpad, lane);
-    } else {
-        sel.init(a.k);
-    }
     const uint64_t total = (uint64_t)gridDim.x * a.k;
     const volatile uint64_t *cand = a.cand;
-    for (uint64_t b = (uint64_t)warp * 32; b < total; b += SCAN_WARPS * 32) {
-        uint64_t key = (b + lane < total) ? cand[b + lane] : KEY_EMPTY;
-        offer_lane_keys(sel, key, lane);
-    }
-    if (warp == 0 && a.n_zero) {  // zero-norm rows: distance 0.0, ascending id; first k allowed suffice
+    if constexpr (BIG) {
+        sel.reset();
+        cta_buf_stream(sel.cb, sel.cap, a.k, total, [&](uint64_t t) { return cand[t]; });
+        // zero-norm rows: distance 0.0, ascending id; the first k allowed ones suffice
         uint32_t found = 0;
-        for (uint32_t b = 0; b < a.n_zero && found < a.k; b += 32) {
+        for (uint32_t b = 0; b < a.n_zero && found < a.k; b += blockDim.x) {
             uint64_t key = KEY_EMPTY;
-            if (b + lane < a.n_zero) {
-                uint32_t id = a.zero_ids[b + lane];
+            if (b + threadIdx.x < a.n_zero) {
+                const uint32_t id = a.zero_ids[b + threadIdx.x];
                 if (id_allowed(a.bitmap, a.n_bits, id)) key = make_key(0.f, id);
             }
-            found += __popc(__ballot_sync(FULL, key != KEY_EMPTY));
+            found += __syncthreads_count(key != KEY_EMPTY);
+            cta_buf_stream(sel.cb, sel.cap, a.k, blockDim.x, [&](uint64_t) { return key; });
+        }
+        sel.finish();   // smem[0..k) = this rank's top-k
+        if (a.xchg == nullptr) {
+            for (uint32_t j = threadIdx.x; j < a.k; j += blockDim.x) a.out_keys[j] = smem[j];
+        } else {
+            exchange_and_merge<true>(a, sel, smem, warp, lane);
+        }
+    } else {
+        sel.init(a.k);
+        for (uint64_t b = (uint64_t)warp * 32; b < total; b += SCAN_WARPS * 32) {
+            uint64_t key = (b + lane < total) ? cand[b + lane] : KEY_EMPTY;
             offer_lane_keys(sel, key, lane);
         }
-    }
-    if (a.xchg == nullptr) {
-        cta_reduce<BIG>(sel, smem, a.k, a.kpad, a.out_keys, warp, lane);
-    } else {
-        // local top-k stays in smem[0..k) (cand[0] is a scratch destination), then exchange + global merge
-        cta_reduce<BIG>(sel, smem, a.k, a.kpad, a.cand, warp, lane);
-        exchange_and_merge<BIG>(a, sel, smem, warp, lane);
+        if (warp == 0 && a.n_zero) {  // zero-norm rows: distance 0.0, ascending id; first k allowed suffice
+            uint32_t found = 0;
+            for (uint32_t b = 0; b < a.n_zero && found < a.k; b += 32) {
+                uint64_t key = KEY_EMPTY;
+                if (b + lane < a.n_zero) {
+                    uint32_t id = a.zero_ids[b + lane];
+                    if (id_allowed(a.bitmap, a.n_bits, id)) key = make_key(0.f, id);
+                }
+                found += __popc(__ballot_sync(FULL, key != KEY_EMPTY));
+                offer_lane_keys(sel, key, lane);
+            }
+        }
+        if (a.xchg == nullptr) {
+            cta_reduce<false>(sel, smem, a.k, a.kpad, a.out_keys, warp, lane);
+        } else {
+            // local top-k stays in smem[0..k) (cand[0] is a scratch destination), then exchange + global merge
+            cta_reduce<false>(sel, smem, a.k, a.kpad, a.cand, warp, lane);
+            exchange_and_merge<false>(a, sel, smem, warp, lane);
+        }
     }
     if (threadIdx.x == 0) *a.ticket = 0;
 }

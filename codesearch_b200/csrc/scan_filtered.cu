@@ -37,9 +37,7 @@ static cudaError_t launch_f_b(const ScanArgs &a, uint32_t grid, size_t smem, cud
 
 cudaError_t launch_scan_filtered(const ScanArgs &a, uint32_t grid, size_t smem, cudaStream_t st)
 {
-    const bool big = a.k > 32;
-    if (!big) return launch_f_b<false, 2>(a, grid, smem, st);
-    return a.kpad > 512 ? launch_f_b<true, 1>(a, grid, smem, st) : launch_f_b<true, 2>(a, grid, smem, st);
+    return a.k > 32 ? launch_f_b<true, 2>(a, grid, smem, st) : launch_f_b<false, 2>(a, grid, smem, st);
 }
 
 }  // namespace csgpu

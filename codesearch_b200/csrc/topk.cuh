@@ -71,6 +71,7 @@ __device__ __forceinline__ uint64_t warp_sort32(uint64_t v, int lane)
 // current k-th best, i.e. ~k*ln(rows_per_warp/k) times per warp.
 // ----------------------------------------------------------------------------------------
 struct WarpSel32 {
+    static constexpr bool CTA_SHARED = false;
     uint64_t v;    // lane's slot
     uint64_t thr;  // warp-uniform: key of the k-th best so far (KEY_EMPTY until k rows seen)
     int km1;
@@ -97,6 +98,7 @@ struct WarpSel32 {
 // stale - that only lets a few extra rows through, never loses one.
 // ----------------------------------------------------------------------------------------
 struct WarpSelBig {
+    static constexpr bool CTA_SHARED = false;
     uint64_t *cur, *nxt;  // [kpad] each, this warp's
     uint64_t pend;
     uint64_t thr;
@@ -207,6 +209,48 @@ __device__ __forceinline__ void cta_buf_compact(uint64_t *buf, unsigned *cnt, vo
     }
     __syncthreads();
 }
+
+// CTA-uniform: offer `total` keys (key = load(t)) to the buffer, all threads in lockstep, compacting whenever
+// fewer than blockDim.x free slots remain. Precondition: *cnt + blockDim.x <= cap.
+template <class F>
+__device__ __forceinline__ void cta_buf_stream(CtaBuf &cb, uint32_t cap, uint32_t k, uint64_t total, F load)
+{
+    for (uint64_t b0 = 0; b0 < total; b0 += blockDim.x) {
+        const uint64_t t = b0 + threadIdx.x;
+        const uint64_t key = t < total ? load(t) : KEY_EMPTY;
+        if (key < *cb.thr) cb.buf[atomicAdd(cb.cnt, 1u)] = key;
+        if (__syncthreads_or(*reinterpret_cast<volatile unsigned *>(cb.cnt) + blockDim.x > cap))
+            cta_buf_compact(cb.buf, cb.cnt, cb.thr, cap, k);
+    }
+}
+
+// Selector facade over CtaBuf with the interface the scan loops use (thr / insert / sync_point).
+struct CtaSel {
+    static constexpr bool CTA_SHARED = true;
+    uint64_t thr;   // register copy of the CTA threshold, refreshed at sync points
+    CtaBuf cb;
+    uint32_t cap, k;
+
+    __device__ __forceinline__ void reset()   // CTA-uniform
+    {
+        __syncthreads();
+        if (threadIdx.x == 0) { *cb.cnt = 0; *cb.thr = KEY_EMPTY; }
+        __syncthreads();
+        thr = KEY_EMPTY;
+    }
+    __device__ __forceinline__ void insert(uint64_t key, int lane) { cb.append(key, lane); }
+    // CTA-uniform; `slack` = the most keys the CTA can append before the next sync point
+    __device__ __forceinline__ void sync_point(uint32_t slack)
+    {
+        if (__syncthreads_or(*reinterpret_cast<volatile unsigned *>(cb.cnt) + slack > cap))
+            cta_buf_compact(cb.buf, cb.cnt, cb.thr, cap, k);
+        thr = *cb.thr;
+    }
+    // CTA-uniform: buf[0..k) = best k ascending (KEY_EMPTY padded)
+    __device__ __forceinline__ void finish() { cta_buf_compact(cb.buf, cb.cnt, cb.thr, cap, k); }
+};
+
+__host__ __device__ __forceinline__ uint32_t ctabuf_cap(uint32_t k) { uint32_t p = 1024; while (p < 2 * k + 512) p <<= 1; return p; }
 
 __host__ __device__ __forceinline__ uint32_t pow2_at_least(uint32_t x, uint32_t lo)
 {
