@@ -45,6 +45,18 @@ class Stats(ctypes.Structure):
     ]
 
 
+class Predicate(ctypes.Structure):
+    """csgpu_predicate_t (include/csgpu.h)."""
+    _fields_ = [
+        ("lang_mask", ctypes.c_uint32),
+        ("file_lo", ctypes.c_uint32),
+        ("file_hi", ctypes.c_uint32),
+        ("reserved", ctypes.c_uint32),
+        ("file_bitmap", ctypes.c_void_p),
+        ("n_file_bits", ctypes.c_uint64),
+    ]
+
+
 _u32p = ctypes.POINTER(ctypes.c_uint32)
 _u64p = ctypes.POINTER(ctypes.c_uint64)
 _f32p = ctypes.POINTER(ctypes.c_float)
@@ -67,6 +79,11 @@ SIGNATURES = {
     "csgpu_search_batch": (ctypes.c_int, [_vp, _f32p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _u32p, _f32p, _u32p]),
     "csgpu_search_variants": (ctypes.c_int, [_vp, _f32p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _u32p, _f32p, _u32p]),
     "csgpu_search_filtered": (ctypes.c_int, [_vp, _f32p, ctypes.c_uint32, ctypes.c_uint32, _u64p, ctypes.c_uint64, _u32p, _f32p, _u32p]),
+    "csgpu_append_tagged": (ctypes.c_int, [_vp, _f32p, _u32p, _u32p, ctypes.c_uint64]),
+    "csgpu_search_tagged": (ctypes.c_int, [_vp, _f32p, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(Predicate), _u32p, _f32p, _u32p]),
+    "csgpu_get_tags": (ctypes.c_int, [_vp, _u32p, ctypes.c_uint64, _u32p]),
+    "csgpu_search_tagged_keys_device": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.POINTER(Predicate), ctypes.c_uint32, _vp, _vp]),
+    "csgpu_append_synthetic_tagged": (ctypes.c_int, [_vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32]),
     "csgpu_search_keys_device": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, _vp, _vp]),
     "csgpu_merge_keys_device": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp]),
     "csgpu_exchange_create": (ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32, _vp]),

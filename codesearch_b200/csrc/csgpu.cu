@@ -141,7 +141,8 @@ static uint32_t rows_in_flight(uint32_t dim4)
 // Enqueue one single-query scan of `sh` on `st`. q_dev: [dim_pad] on the shard's device.
 static int enqueue_scan(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const float *q_dev, uint32_t k,
                         const uint64_t *bitmap_dev, uint64_t n_bits, bool with_zero_ids, uint64_t *out_keys,
-                        cudaStream_t st, const ExchangeDev *xchg = nullptr, uint32_t seq = 0)
+                        cudaStream_t st, const ExchangeDev *xchg = nullptr, uint32_t seq = 0,
+                        const csgpu_predicate_t *pred = nullptr /* row-tag predicate; bitmap_dev is then its FILE bitmap */)
 {
     ScanArgs a;
     a.rows = reinterpret_cast<const float4 *>(sh->rows);
@@ -161,9 +162,10 @@ static int enqueue_scan(const csgpu_index *ix, const Shard *sh, SearchCtx *c, co
     a.out_keys = out_keys;
     a.xchg = xchg;
     a.seq = seq;
+    if (pred) { a.tags = sh->tags; a.lang_mask = pred->lang_mask; a.file_lo = pred->file_lo; a.file_hi = pred->file_hi; }
     const uint32_t per_cta_rows = SCAN_WARPS * rows_in_flight(ix->dim4);
     uint64_t want = (sh->n_built + per_cta_rows - 1) / per_cta_rows;
-    if (bitmap_dev != nullptr) {   // filtered: pre-filter variant (scan_filtered.cu)
+    if (bitmap_dev != nullptr || pred != nullptr) {   // filtered: pre-filter variant (scan_filtered.cu)
         const uint64_t want32 = (sh->n_built + 32 * SCAN_WARPS - 1) / (32 * SCAN_WARPS);
         const uint32_t gridf = (uint32_t)std::min<uint64_t>((uint64_t)sh->sm_count * 2, std::max<uint64_t>(want32, 1));
         const size_t smemf = big ? (size_t)a.kpad * sizeof(uint64_t) : (size_t)SCAN_WARPS * 32 * sizeof(uint64_t);
@@ -238,7 +240,7 @@ static int shard_reserve(const csgpu_index *ix, Shard *sh, uint64_t rows)
     DeviceGuard g(sh->device);
     uint64_t ncap = std::max<uint64_t>(rows, sh->cap + sh->cap / 2);
     ncap = std::max<uint64_t>(ncap, 1024);
-    float *nrows = nullptr; uint32_t *nids = nullptr; uint8_t *nst = nullptr;
+    float *nrows = nullptr; uint32_t *nids = nullptr, *ntags = nullptr; uint8_t *nst = nullptr;
     const size_t row_bytes = (size_t)ix->dim_pad * sizeof(float);
     cudaError_t e = cudaMalloc(&nrows, ncap * row_bytes);
     if (e != cudaSuccess && ncap > rows) {  // retry with the exact size before giving up
@@ -249,15 +251,18 @@ static int shard_reserve(const csgpu_index *ix, Shard *sh, uint64_t rows)
     if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(rows)", __FILE__, __LINE__);
     if ((e = cudaMalloc(&nids, ncap * sizeof(uint32_t))) != cudaSuccess) { cudaFree(nrows); return fail_cuda(e, "cudaMalloc(ids)", __FILE__, __LINE__); }
     if ((e = cudaMalloc(&nst, ncap)) != cudaSuccess) { cudaFree(nrows); cudaFree(nids); return fail_cuda(e, "cudaMalloc(status)", __FILE__, __LINE__); }
+    if ((e = cudaMalloc(&ntags, ncap * sizeof(uint32_t))) != cudaSuccess) { cudaFree(nrows); cudaFree(nids); cudaFree(nst); return fail_cuda(e, "cudaMalloc(tags)", __FILE__, __LINE__); }
     CS_CUDA(cudaMemsetAsync(nst, 0, ncap, sh->stream));
+    CS_CUDA(cudaMemsetAsync(ntags, 0xFF, ncap * sizeof(uint32_t), sh->stream));   // CSGPU_TAG_NONE
     if (sh->n_total) {
         CS_CUDA(cudaMemcpyAsync(nrows, sh->rows, sh->n_total * row_bytes, cudaMemcpyDeviceToDevice, sh->stream));
         CS_CUDA(cudaMemcpyAsync(nids, sh->ids, sh->n_total * sizeof(uint32_t), cudaMemcpyDeviceToDevice, sh->stream));
+        CS_CUDA(cudaMemcpyAsync(ntags, sh->tags, sh->n_total * sizeof(uint32_t), cudaMemcpyDeviceToDevice, sh->stream));
         CS_CUDA(cudaMemcpyAsync(nst, sh->status, sh->n_total, cudaMemcpyDeviceToDevice, sh->stream));
     }
     CS_CUDA(cudaStreamSynchronize(sh->stream));
-    cudaFree(sh->rows); cudaFree(sh->ids); cudaFree(sh->status);
-    sh->rows = nrows; sh->ids = nids; sh->status = nst; sh->cap = ncap;
+    cudaFree(sh->rows); cudaFree(sh->ids); cudaFree(sh->status); cudaFree(sh->tags);
+    sh->rows = nrows; sh->ids = nids; sh->status = nst; sh->tags = ntags; sh->cap = ncap;
     return CSGPU_OK;
 }
 
@@ -271,12 +276,15 @@ static int kill_ids(csgpu_index *ix, const uint32_t *ids, uint64_t n, uint64_t *
     sorted.erase(std::unique(sorted.begin(), sorted.end()), sorted.end());
     // zero-norm rows live on the host list only
     if (!ix->zero_ids.empty()) {
-        std::vector<uint32_t> keep;
+        std::vector<uint32_t> keep, keep_tags;
         keep.reserve(ix->zero_ids.size());
-        for (uint32_t z : ix->zero_ids) {
-            if (std::binary_search(sorted.begin(), sorted.end(), z)) ++*killed; else keep.push_back(z);
+        for (size_t i = 0; i < ix->zero_ids.size(); ++i) {
+            const uint32_t z = ix->zero_ids[i];
+            if (std::binary_search(sorted.begin(), sorted.end(), z)) ++*killed;
+            else { keep.push_back(z); keep_tags.push_back(ix->zero_tags[i]); }
         }
         ix->zero_ids.swap(keep);
+        ix->zero_tags.swap(keep_tags);
     }
     for (Shard *sh : ix->shards) {
         if (sh->n_total == 0) continue;
@@ -312,9 +320,12 @@ static int upload_zero_ids(csgpu_index *ix)
     DeviceGuard g(s0->device);
     cudaFree(ix->zero_ids_dev);
     ix->zero_ids_dev = nullptr;
-    if (!ix->zero_ids.empty()) {
-        CS_CUDA(cudaMalloc(&ix->zero_ids_dev, ix->zero_ids.size() * sizeof(uint32_t)));
-        CS_CUDA(cudaMemcpy(ix->zero_ids_dev, ix->zero_ids.data(), ix->zero_ids.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (!ix->zero_ids.empty()) {   // [n_zero] ids, then [n_zero] tags
+        const size_t nz = ix->zero_ids.size();
+        ix->zero_tags.resize(nz, CSGPU_TAG_NONE);
+        CS_CUDA(cudaMalloc(&ix->zero_ids_dev, 2 * nz * sizeof(uint32_t)));
+        CS_CUDA(cudaMemcpy(ix->zero_ids_dev, ix->zero_ids.data(), nz * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CS_CUDA(cudaMemcpy(ix->zero_ids_dev + nz, ix->zero_tags.data(), nz * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
     return CSGPU_OK;
 }
@@ -339,7 +350,7 @@ __global__ void gather_u32_kernel(const uint32_t *__restrict__ in, uint32_t *__r
 }
 
 // Normalise pending rows, drop dead/zero/non-finite rows (stable), leave [0, n_built) all live.
-static int shard_build(csgpu_index *ix, Shard *sh, std::vector<uint32_t> &new_zero_ids)
+static int shard_build(csgpu_index *ix, Shard *sh, std::vector<std::pair<uint32_t, uint32_t>> &new_zero_ids /* (id, tag) */)
 {
     DeviceGuard g(sh->device);
     const uint64_t n = sh->n_total;
@@ -375,17 +386,19 @@ static int shard_build(csgpu_index *ix, Shard *sh, std::vector<uint32_t> &new_ze
         else if (st[i] == ROW_NONFINITE) ix->nonfinite_rows++;
     }
     for (uint64_t r : zero_rows) {
-        uint32_t id;
+        uint32_t id, tag;
         CS_CUDA(cudaMemcpy(&id, sh->ids + r, sizeof id, cudaMemcpyDeviceToHost));
-        new_zero_ids.push_back(id);
+        CS_CUDA(cudaMemcpy(&tag, sh->tags + r, sizeof tag, cudaMemcpyDeviceToHost));
+        new_zero_ids.push_back({id, tag});
     }
     const uint64_t moved = keep_src.size();
     if (moved) {
         const uint64_t CH = 65536;  // rows per bounce chunk
-        uint32_t *keep_dev = nullptr; float *bounce = nullptr; uint32_t *bounce_ids = nullptr;
+        uint32_t *keep_dev = nullptr; float *bounce = nullptr; uint32_t *bounce_ids = nullptr, *bounce_tags = nullptr;
         CS_CUDA(cudaMalloc(&keep_dev, moved * sizeof(uint32_t)));
         CS_CUDA(cudaMalloc(&bounce, std::min(CH, moved) * row_bytes));
         CS_CUDA(cudaMalloc(&bounce_ids, std::min(CH, moved) * sizeof(uint32_t)));
+        CS_CUDA(cudaMalloc(&bounce_tags, std::min(CH, moved) * sizeof(uint32_t)));
         CS_CUDA(cudaMemcpyAsync(keep_dev, keep_src.data(), moved * sizeof(uint32_t), cudaMemcpyHostToDevice, sh->stream));
         for (uint64_t c0 = 0; c0 < moved; c0 += CH) {
             const uint64_t cn = std::min(CH, moved - c0);
@@ -393,12 +406,14 @@ static int shard_build(csgpu_index *ix, Shard *sh, std::vector<uint32_t> &new_ze
             gather_rows_bounce_kernel<<<grid, 256, 0, sh->stream>>>(reinterpret_cast<const float4 *>(rowbase),
                                                                      reinterpret_cast<float4 *>(bounce), keep_dev + c0, cn, row_u4);
             gather_u32_kernel<<<(uint32_t)((cn + 255) / 256), 256, 0, sh->stream>>>(sh->ids, bounce_ids, keep_dev + c0, cn);
-            count_launch(2);
+            gather_u32_kernel<<<(uint32_t)((cn + 255) / 256), 256, 0, sh->stream>>>(sh->tags, bounce_tags, keep_dev + c0, cn);
+            count_launch(3);
             CS_CUDA(cudaMemcpyAsync(rowbase + (first_bad + c0) * row_bytes, bounce, cn * row_bytes, cudaMemcpyDeviceToDevice, sh->stream));
             CS_CUDA(cudaMemcpyAsync(sh->ids + first_bad + c0, bounce_ids, cn * sizeof(uint32_t), cudaMemcpyDeviceToDevice, sh->stream));
+            CS_CUDA(cudaMemcpyAsync(sh->tags + first_bad + c0, bounce_tags, cn * sizeof(uint32_t), cudaMemcpyDeviceToDevice, sh->stream));
         }
         CS_CUDA(cudaStreamSynchronize(sh->stream));
-        cudaFree(keep_dev); cudaFree(bounce); cudaFree(bounce_ids);
+        cudaFree(keep_dev); cudaFree(bounce); cudaFree(bounce_ids); cudaFree(bounce_tags);
     }
     sh->n_built = sh->n_total = first_bad + moved;
     CS_CUDA(cudaMemsetAsync(sh->status, 0, sh->cap, sh->stream));
@@ -443,8 +458,9 @@ void decode_keys(const uint64_t *keys, uint32_t k, uint32_t *out_ids, float *out
 
 // One query (optionally filtered) through every shard; result keys land in ctx0->out_pin[0..k).
 static int search_one(const csgpu_index *ix, const float *q, uint32_t k, const uint64_t *bitmap, uint64_t n_bits,
-                      uint32_t *out_ids, float *out_dist, uint32_t *out_n)
+                      uint32_t *out_ids, float *out_dist, uint32_t *out_n, const csgpu_predicate_t *pred = nullptr)
 {
+    if (pred) { bitmap = pred->file_bitmap; n_bits = pred->file_bitmap ? pred->n_file_bits : 0; }
     const size_t G = ix->shards.size();
     std::vector<SearchCtx *> ctx(G, nullptr);
     int rc = CSGPU_OK;
@@ -475,7 +491,7 @@ static int search_one(const csgpu_index *ix, const float *q, uint32_t k, const u
             }
             if (g == 0) CS_CUDA(cudaEventRecord(c->ev0, c->stream));
             uint64_t *dst = (G == 1) ? c->out_pin : c->out_dev;
-            int r = enqueue_scan(ix, sh, c, c->q_dev, k, bm_dev, n_bits, /*with_zero_ids=*/g == 0, dst, c->stream);
+            int r = enqueue_scan(ix, sh, c, c->q_dev, k, bm_dev, n_bits, /*with_zero_ids=*/g == 0, dst, c->stream, nullptr, 0, pred);
             if (r) return r;
         }
         SearchCtx *c0 = ctx[0];
@@ -742,7 +758,7 @@ void csgpu_destroy(csgpu_index *ix)
         for (SearchCtx *c : sh->all_ctx) ctx_destroy(c);
         batch_free_ctx(sh);
         cudaFree(sh->rows_bf16); cudaFree(sh->stage);
-        cudaFree(sh->rows); cudaFree(sh->ids); cudaFree(sh->status);
+        cudaFree(sh->rows); cudaFree(sh->ids); cudaFree(sh->status); cudaFree(sh->tags);
         if (sh->stream) cudaStreamDestroy(sh->stream);
         delete sh;
     }
@@ -761,7 +777,7 @@ int csgpu_reserve(csgpu_index *ix, uint64_t total_rows)
     return CSGPU_OK;
 }
 
-int csgpu_append(csgpu_index *ix, const float *rows, const uint32_t *ids, uint64_t n)
+static int append_rows(csgpu_index *ix, const float *rows, const uint32_t *ids, const uint32_t *tags, uint64_t n)
 {
     if (!ix) return fail(CSGPU_ERR_ARG, "null index");
     if (n == 0) return CSGPU_OK;
@@ -812,6 +828,8 @@ int csgpu_append(csgpu_index *ix, const float *rows, const uint32_t *ids, uint64
                                       (size_t)ix->dim * sizeof(float), m, cudaMemcpyHostToDevice, sh->stream));
         }
         CS_CUDA(cudaMemcpyAsync(sh->ids + sh->n_total, ids + a, m * sizeof(uint32_t), cudaMemcpyHostToDevice, sh->stream));
+        if (tags) CS_CUDA(cudaMemcpyAsync(sh->tags + sh->n_total, tags + a, m * sizeof(uint32_t), cudaMemcpyHostToDevice, sh->stream));
+        else CS_CUDA(cudaMemsetAsync(sh->tags + sh->n_total, 0xFF, m * sizeof(uint32_t), sh->stream));
         if (!dup.empty()) CS_CUDA(cudaMemcpyAsync(sh->status + sh->n_total, dup.data() + a, m, cudaMemcpyHostToDevice, sh->stream));
         else CS_CUDA(cudaMemsetAsync(sh->status + sh->n_total, 0, m, sh->stream));
         CS_CUDA(cudaStreamSynchronize(sh->stream));
@@ -821,7 +839,18 @@ int csgpu_append(csgpu_index *ix, const float *rows, const uint32_t *ids, uint64
     return CSGPU_OK;
 }
 
-int csgpu_append_synthetic(csgpu_index *ix, uint64_t seed, uint64_t first_row, uint64_t n, uint32_t id_base)
+int csgpu_append(csgpu_index *ix, const float *rows, const uint32_t *ids, uint64_t n)
+{
+    return append_rows(ix, rows, ids, nullptr, n);
+}
+
+int csgpu_append_tagged(csgpu_index *ix, const float *rows, const uint32_t *ids, const uint32_t *tags, uint64_t n)
+{
+    if (n && !tags) return fail(CSGPU_ERR_ARG, "tags is null");
+    return append_rows(ix, rows, ids, tags, n);
+}
+
+static int append_synthetic(csgpu_index *ix, uint64_t seed, uint64_t first_row, uint64_t n, uint32_t id_base, bool tagged)
 {
     if (!ix) return fail(CSGPU_ERR_ARG, "null index");
     if (n == 0) return CSGPU_OK;
@@ -844,12 +873,29 @@ int csgpu_append_synthetic(csgpu_index *ix, uint64_t seed, uint64_t first_row, u
                                                         sh->ids + sh->n_total, seed, first_row + a, m, ix->dim4, id_base);
         count_launch();
         CS_CUDA(cudaGetLastError());
+        if (tagged) {
+            synth_tags_kernel<<<(uint32_t)std::min<uint64_t>((m + 255) / 256, (uint64_t)sh->sm_count * 16), 256, 0, sh->stream>>>(sh->tags + sh->n_total, first_row + a, m);
+            count_launch();
+            CS_CUDA(cudaGetLastError());
+        } else {
+            CS_CUDA(cudaMemsetAsync(sh->tags + sh->n_total, 0xFF, m * sizeof(uint32_t), sh->stream));
+        }
         CS_CUDA(cudaMemsetAsync(sh->status + sh->n_total, 0, m, sh->stream));
         CS_CUDA(cudaStreamSynchronize(sh->stream));
         sh->n_total += m;
     }
     ix->built = false;
     return CSGPU_OK;
+}
+
+int csgpu_append_synthetic(csgpu_index *ix, uint64_t seed, uint64_t first_row, uint64_t n, uint32_t id_base)
+{
+    return append_synthetic(ix, seed, first_row, n, id_base, false);
+}
+
+int csgpu_append_synthetic_tagged(csgpu_index *ix, uint64_t seed, uint64_t first_row, uint64_t n, uint32_t id_base)
+{
+    return append_synthetic(ix, seed, first_row, n, id_base, true);
 }
 
 int csgpu_synth_rows_host(const csgpu_index *ix, uint64_t seed, uint64_t first_row, uint64_t n, float *out_rows)
@@ -890,15 +936,18 @@ int csgpu_remove(csgpu_index *ix, const uint32_t *ids, uint64_t n, uint64_t *n_r
 int csgpu_build(csgpu_index *ix)
 {
     if (!ix) return fail(CSGPU_ERR_ARG, "null index");
-    std::vector<uint32_t> new_zero;
+    std::vector<std::pair<uint32_t, uint32_t>> new_zero;
     for (Shard *sh : ix->shards) {
         int rc = shard_build(ix, sh, new_zero);
         if (rc) return rc;
     }
     if (!new_zero.empty()) {
-        ix->zero_ids.insert(ix->zero_ids.end(), new_zero.begin(), new_zero.end());
-        std::sort(ix->zero_ids.begin(), ix->zero_ids.end());
-        ix->zero_ids.erase(std::unique(ix->zero_ids.begin(), ix->zero_ids.end()), ix->zero_ids.end());
+        ix->zero_tags.resize(ix->zero_ids.size(), CSGPU_TAG_NONE);
+        for (size_t i = 0; i < ix->zero_ids.size(); ++i) new_zero.push_back({ix->zero_ids[i], ix->zero_tags[i]});
+        std::sort(new_zero.begin(), new_zero.end());
+        new_zero.erase(std::unique(new_zero.begin(), new_zero.end(), [](const auto &x, const auto &y) { return x.first == y.first; }), new_zero.end());
+        ix->zero_ids.clear(); ix->zero_tags.clear();
+        for (const auto &z : new_zero) { ix->zero_ids.push_back(z.first); ix->zero_tags.push_back(z.second); }
     }
     int rc = upload_zero_ids(ix);
     if (rc) return rc;
@@ -913,13 +962,14 @@ int csgpu_clear(csgpu_index *ix)
     if (!ix) return fail(CSGPU_ERR_ARG, "null index");
     for (Shard *sh : ix->shards) {
         DeviceGuard dg(sh->device);
-        cudaFree(sh->rows); cudaFree(sh->ids); cudaFree(sh->status);
+        cudaFree(sh->rows); cudaFree(sh->ids); cudaFree(sh->status); cudaFree(sh->tags);
         cudaFree(sh->rows_bf16); cudaFree(sh->stage);
         sh->rows_bf16 = nullptr; sh->stage = nullptr; sh->stage_cap = 0; sh->map_valid = false;
-        sh->rows = nullptr; sh->ids = nullptr; sh->status = nullptr;
+        sh->rows = nullptr; sh->ids = nullptr; sh->status = nullptr; sh->tags = nullptr;
         sh->n_built = sh->n_total = sh->cap = 0;
     }
     ix->zero_ids.clear();
+    ix->zero_tags.clear();
     upload_zero_ids(ix);
     ix->nonfinite_rows = 0;
     ix->tombstones = 0;
@@ -963,6 +1013,75 @@ int csgpu_search_filtered(const csgpu_index *ix, const float *q, uint32_t q_len,
     if (k == 0) return CSGPU_OK;
     static const uint64_t empty_word = 0;
     return search_one(ix, q, k, id_bitmap ? id_bitmap : &empty_word, n_bits, out_ids, out_dist, out_n);
+}
+
+int csgpu_search_tagged(const csgpu_index *ix, const float *q, uint32_t q_len, uint32_t k, const csgpu_predicate_t *pred,
+                        uint32_t *out_ids, float *out_dist, uint32_t *out_n)
+{
+    if (out_n) *out_n = 0;
+    int rc = check_search_args(ix, q, q_len, k);
+    if (rc) return rc;
+    if (!pred) return fail(CSGPU_ERR_ARG, "pred is null");
+    if (!pred->file_bitmap && pred->n_file_bits) return fail(CSGPU_ERR_ARG, "file_bitmap is null");
+    if (ix->dtype == CSGPU_DTYPE_BF16) return fail(CSGPU_ERR_ARG, "filtered search is not implemented for the bf16 index yet");
+    if (!all_finite(q, q_len)) return fail(CSGPU_ERR_ARG, "query contains NaN/Inf");
+    if (k == 0) return CSGPU_OK;
+    csgpu_predicate_t p = *pred;
+    static const uint64_t empty_word = 0;
+    if (p.file_bitmap && p.n_file_bits == 0) p.file_bitmap = &empty_word;   // an empty bitmap allows nothing
+    return search_one(ix, q, k, nullptr, 0, out_ids, out_dist, out_n, &p);
+}
+
+// tags[i] of every live row whose id is in `ids` (sorted copy on the device; one thread per row)
+__global__ void lookup_tags_kernel(const uint32_t *__restrict__ ids, const uint32_t *__restrict__ tags, uint64_t n_rows,
+                                   const uint32_t *__restrict__ want_sorted, const uint32_t *__restrict__ want_pos, uint32_t n_want,
+                                   uint32_t *__restrict__ out)
+{
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t id = ids[r];
+        uint32_t lo = 0, hi = n_want;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (want_sorted[mid] < id) lo = mid + 1; else hi = mid; }
+        for (; lo < n_want && want_sorted[lo] == id; ++lo) out[want_pos[lo]] = tags[r];
+    }
+}
+
+int csgpu_get_tags(const csgpu_index *ix, const uint32_t *ids, uint64_t n, uint32_t *out_tags)
+{
+    if (!ix) return fail(CSGPU_ERR_ARG, "null index");
+    if (n == 0) return CSGPU_OK;
+    if (!ids || !out_tags) return fail(CSGPU_ERR_ARG, "null argument");
+    if (!ix->built) return fail(CSGPU_ERR_NOT_BUILT, "Index not built. Call build_index() after inserting chunks.");
+    if (n > 0xFFFFFFFFull) return fail(CSGPU_ERR_ARG, "too many ids");
+    std::vector<uint32_t> order(n), sorted(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ids[a] < ids[b]; });
+    for (uint64_t i = 0; i < n; ++i) sorted[i] = ids[order[i]];
+    std::vector<uint32_t> result(n, CSGPU_TAG_NONE);
+    for (Shard *sh : ix->shards) {
+        if (!sh->n_built) continue;
+        DeviceGuard dg(sh->device);
+        uint32_t *d = nullptr;
+        CS_CUDA(cudaMalloc(&d, 3 * n * sizeof(uint32_t)));
+        CS_CUDA(cudaMemcpyAsync(d, sorted.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, sh->stream));
+        CS_CUDA(cudaMemcpyAsync(d + n, order.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, sh->stream));
+        CS_CUDA(cudaMemcpyAsync(d + 2 * n, result.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, sh->stream));
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((sh->n_built + 255) / 256, (uint64_t)sh->sm_count * 8);
+        lookup_tags_kernel<<<grid, 256, 0, sh->stream>>>(sh->ids, sh->tags, sh->n_built, d, d + n, (uint32_t)n, d + 2 * n);
+        count_launch();
+        cudaError_t e = cudaMemcpyAsync(result.data(), d + 2 * n, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, sh->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(sh->stream);
+        cudaFree(d);
+        if (e != cudaSuccess) return fail_cuda(e, "csgpu_get_tags", __FILE__, __LINE__);
+    }
+    for (uint64_t i = 0; i < n; ++i) {   // zero-norm rows live on the host list
+        auto it = std::lower_bound(ix->zero_ids.begin(), ix->zero_ids.end(), ids[i]);
+        if (it != ix->zero_ids.end() && *it == ids[i]) {
+            const size_t z = it - ix->zero_ids.begin();
+            result[i] = z < ix->zero_tags.size() ? ix->zero_tags[z] : CSGPU_TAG_NONE;
+        }
+    }
+    memcpy(out_tags, result.data(), n * sizeof(uint32_t));
+    return CSGPU_OK;
 }
 
 int csgpu_search_batch(const csgpu_index *ix, const float *q, uint32_t q_len, uint32_t b, uint32_t k,
@@ -1180,6 +1299,29 @@ int csgpu_search_keys_exchange_device(const csgpu_index *ix, const float *q_dev,
     return rc;
 }
 
+int csgpu_search_tagged_keys_device(const csgpu_index *ix, const float *q_dev, uint32_t k, const csgpu_predicate_t *pred,
+                                    uint32_t exchange, uint64_t *out_keys_dev, void *stream)
+{
+    if (!ix) return fail(CSGPU_ERR_ARG, "null index");
+    if (!ix->built) return fail(CSGPU_ERR_NOT_BUILT, "Index not built. Call build_index() after inserting chunks.");
+    if (ix->shards.size() != 1) return fail(CSGPU_ERR_ARG, "device entry points need a single-device index");
+    if (ix->dtype != CSGPU_DTYPE_F32) return fail(CSGPU_ERR_ARG, "device entry points need an fp32 index");
+    if (exchange && (!ix->xchg || !ix->xchg->connected)) return fail(CSGPU_ERR_ARG, "exchange is not connected (csgpu_exchange_create/connect)");
+    if (!q_dev || !out_keys_dev || !pred) return fail(CSGPU_ERR_ARG, "null pointer");
+    if (k == 0 || k > CSGPU_MAX_K) return fail(CSGPU_ERR_ARG, "k must be in [1, 1024]");
+    if (pred->file_bitmap && pred->n_file_bits == 0) return fail(CSGPU_ERR_ARG, "file_bitmap with n_file_bits == 0");
+    Shard *sh = ix->shards[0];
+    SearchCtx *c = nullptr;
+    int rc = ctx_acquire(ix, sh, &c);
+    if (rc) return rc;
+    DeviceGuard dg(sh->device);
+    const uint32_t seq = exchange ? ix->xchg->seq.fetch_add(1) + 1 : 0;
+    rc = enqueue_scan(ix, sh, c, q_dev, k, pred->file_bitmap, pred->file_bitmap ? pred->n_file_bits : 0, true, out_keys_dev,
+                      (cudaStream_t)stream, exchange ? ix->xchg->dev : nullptr, seq, pred);
+    ctx_release(sh, c);
+    return rc;
+}
+
 int csgpu_exchange_status(const csgpu_index *ix, uint32_t *timed_out)
 {
     if (!ix || !ix->xchg || !timed_out) return fail(CSGPU_ERR_ARG, "no exchange");
@@ -1216,7 +1358,7 @@ int csgpu_stats(const csgpu_index *ix, csgpu_stats_t *out)
         out->pending_rows += sh->n_total - sh->n_built;
         out->rows_per_device[g] = sh->n_built;
         const size_t row_bytes = ix->dtype == CSGPU_DTYPE_BF16 ? (size_t)ix->dim * 2 : (size_t)ix->dim_pad * sizeof(float);
-        out->bytes_on_device += sh->cap * (row_bytes + sizeof(uint32_t) + 1) + sh->stage_cap * (size_t)ix->dim_pad * sizeof(float);
+        out->bytes_on_device += sh->cap * (row_bytes + 2 * sizeof(uint32_t) + 1) + sh->stage_cap * (size_t)ix->dim_pad * sizeof(float);
     }
     out->live_rows += ix->zero_ids.size();
     out->coalesced_passes = ix->coalescer.passes.load();

@@ -168,21 +168,24 @@ int bf16_reserve_rows(const csgpu_index *ix, Shard *sh, uint64_t rows)
     if (rows <= sh->cap) return CSGPU_OK;
     DeviceGuard g(sh->device);
     uint64_t ncap = std::max<uint64_t>(std::max<uint64_t>(rows, sh->cap + sh->cap / 2), 1024);
-    void *nrows = nullptr; uint32_t *nids = nullptr; uint8_t *nst = nullptr;
+    void *nrows = nullptr; uint32_t *nids = nullptr, *ntags = nullptr; uint8_t *nst = nullptr;
     const size_t row_bytes = (size_t)ix->dim * 2;
     cudaError_t e = cudaMalloc(&nrows, ncap * row_bytes);
     if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(bf16 rows)", __FILE__, __LINE__);
     if ((e = cudaMalloc(&nids, ncap * sizeof(uint32_t))) != cudaSuccess) { cudaFree(nrows); return fail_cuda(e, "cudaMalloc(ids)", __FILE__, __LINE__); }
     if ((e = cudaMalloc(&nst, ncap)) != cudaSuccess) { cudaFree(nrows); cudaFree(nids); return fail_cuda(e, "cudaMalloc(status)", __FILE__, __LINE__); }
+    if ((e = cudaMalloc(&ntags, ncap * sizeof(uint32_t))) != cudaSuccess) { cudaFree(nrows); cudaFree(nids); cudaFree(nst); return fail_cuda(e, "cudaMalloc(tags)", __FILE__, __LINE__); }
     CS_CUDA(cudaMemsetAsync(nst, 0, ncap, sh->stream));
+    CS_CUDA(cudaMemsetAsync(ntags, 0xFF, ncap * sizeof(uint32_t), sh->stream));
     if (sh->n_built) CS_CUDA(cudaMemcpyAsync(nrows, sh->rows_bf16, sh->n_built * row_bytes, cudaMemcpyDeviceToDevice, sh->stream));
     if (sh->n_total) {
         CS_CUDA(cudaMemcpyAsync(nids, sh->ids, sh->n_total * sizeof(uint32_t), cudaMemcpyDeviceToDevice, sh->stream));
         CS_CUDA(cudaMemcpyAsync(nst, sh->status, sh->n_total, cudaMemcpyDeviceToDevice, sh->stream));
+        CS_CUDA(cudaMemcpyAsync(ntags, sh->tags, sh->n_total * sizeof(uint32_t), cudaMemcpyDeviceToDevice, sh->stream));
     }
     CS_CUDA(cudaStreamSynchronize(sh->stream));
-    cudaFree(sh->rows_bf16); cudaFree(sh->ids); cudaFree(sh->status);
-    sh->rows_bf16 = nrows; sh->ids = nids; sh->status = nst; sh->cap = ncap;
+    cudaFree(sh->rows_bf16); cudaFree(sh->ids); cudaFree(sh->status); cudaFree(sh->tags);
+    sh->rows_bf16 = nrows; sh->ids = nids; sh->status = nst; sh->tags = ntags; sh->cap = ncap;
     return CSGPU_OK;
 }
 

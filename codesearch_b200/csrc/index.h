@@ -120,6 +120,7 @@ struct Shard {
     std::mutex batch_mu;
     float *rows = nullptr;     // [cap, dim_pad] fp32; rows [0, n_built) are unit vectors
     uint32_t *ids = nullptr;   // [cap]
+    uint32_t *tags = nullptr;  // [cap] packed (lang_id << 27 | file_id) row tags, CSGPU_TAG_NONE when untagged (§8f N4)
     uint8_t *status = nullptr; // [cap] ROW_* (all ROW_OK in [0, n_built) after build)
     uint64_t n_built = 0;      // searchable rows
     uint64_t n_total = 0;      // built + pending
@@ -166,7 +167,8 @@ struct csgpu_index {
     bool built = false;
     std::vector<csgpu::Shard *> shards;
     std::vector<uint32_t> zero_ids;       // ascending; rows with |v| = 0 (host truth)
-    uint32_t *zero_ids_dev = nullptr;     // on shards[0]->device
+    std::vector<uint32_t> zero_tags;      // parallel to zero_ids
+    uint32_t *zero_ids_dev = nullptr;     // on shards[0]->device: [n_zero] ids then [n_zero] tags
     uint64_t nonfinite_rows = 0;
     uint64_t tombstones = 0;
     mutable std::atomic<float> last_search_us{0.f};

@@ -45,9 +45,11 @@ struct ScanArgs {
     uint32_t dim4;
     const float *q;          // [dim4*4] device, raw (normalised in the prologue)
     uint32_t k, kpad;
-    const uint64_t *bitmap;  // id-indexed allow bitmap or nullptr
+    const uint64_t *bitmap;  // id-indexed allow bitmap or nullptr; with `tags` set: FILE-id-indexed bitmap or nullptr
     uint64_t n_bits;
-    const uint32_t *zero_ids;  // ascending ids of zero-norm rows (distance 0.0), or nullptr
+    const uint32_t *tags = nullptr;   // [n_rows] packed row tags: non-null selects the predicate filter (csgpu_search_tagged)
+    uint32_t lang_mask = 0xFFFFFFFFu, file_lo = 0, file_hi = 0xFFFFFFFFu;
+    const uint32_t *zero_ids;  // ascending ids of zero-norm rows (distance 0.0), or nullptr; tags follow at [n_zero..2 n_zero)
     uint32_t n_zero;
     uint64_t *cand;          // [gridDim.x, k] per-CTA results
     unsigned *ticket;        // last-CTA-done counter (self-resetting)
@@ -78,6 +80,24 @@ __device__ __forceinline__ bool id_allowed(const uint64_t *bitmap, uint64_t n_bi
     if (bitmap == nullptr) return true;
     if ((uint64_t)id >= n_bits) return false;
     return (bitmap[id >> 6] >> (id & 63)) & 1ull;
+}
+
+// Row-tag predicate (csgpu_predicate_t): language bit and file range from the tag alone; the optional per-file
+// bitmap word is fetched separately (tag_word_needed) so its load can be pipelined like the id bitmap's.
+__device__ __forceinline__ bool tag_pass_static(uint32_t tag, uint32_t lang_mask, uint32_t file_lo, uint32_t file_hi)
+{
+    const uint32_t lang = tag >> 27, file = tag & 0x07FFFFFFu;
+    return ((lang_mask >> lang) & 1u) && file >= file_lo && file <= file_hi;
+}
+// zero-norm row i of the side list: allowed under whichever filter the launch carries
+__device__ __forceinline__ bool zero_row_allowed(const uint64_t *bitmap, uint64_t n_bits, const uint32_t *tags_on,
+                                                 uint32_t lang_mask, uint32_t file_lo, uint32_t file_hi,
+                                                 const uint32_t *zero_ids, uint32_t n_zero, uint32_t i)
+{
+    if (tags_on == nullptr) return id_allowed(bitmap, n_bits, zero_ids[i]);
+    const uint32_t tag = zero_ids[n_zero + i];
+    if (!tag_pass_static(tag, lang_mask, file_lo, file_hi)) return false;
+    return id_allowed(bitmap, n_bits, tag & 0x07FFFFFFu);
 }
 
 __device__ __forceinline__ float warp_sum_tree(float v)
@@ -203,12 +223,23 @@ __device__ __forceinline__ void scan_rows_filtered(const ScanArgs &a, const floa
 {
     const uint64_t n = a.n_rows;
     const uint64_t n_blocks = (n + 31) / 32;
+    // Two filter flavours share the pipeline (warp-uniform branch): the id bitmap (lane loads ids[row], then the
+    // bitmap word of that id) and the row-tag predicate (lane loads tags[row]; language bit + file range are tested
+    // on the tag, the optional per-file bitmap word is the second-stage load). In tag mode `id_*` holds the FILE id
+    // with bit 31 set when the static part of the predicate already failed; chunk ids are fetched at insert time.
+    const bool tagmode = a.tags != nullptr;
+    const bool have_bm = a.bitmap != nullptr;
     auto load_id = [&](uint64_t b, bool &valid) -> uint32_t {
         const uint64_t row = b * 32 + lane;
         valid = b < n_blocks && row < n;
-        return valid ? __ldg(a.ids + row) : 0u;
+        if (!valid) return 0u;
+        if (!tagmode) return __ldg(a.ids + row);
+        const uint32_t tag = __ldg(a.tags + row);
+        valid = tag_pass_static(tag, a.lang_mask, a.file_lo, a.file_hi);
+        return tag & 0x07FFFFFFu;
     };
     auto load_word = [&](uint32_t id, bool valid) -> uint64_t {
+        if (tagmode && !have_bm) return valid ? ~0ull : 0ull;
         return (valid && (uint64_t)id < a.n_bits) ? __ldg(reinterpret_cast<const unsigned long long *>(a.bitmap) + (id >> 6)) : 0ull;
     };
     bool v_cur, v_nxt, v_nx2;
@@ -253,7 +284,7 @@ __device__ __forceinline__ void scan_rows_filtered(const ScanArgs &a, const floa
                 acc = warp_sum_tree(acc);
                 const float dist = qzero ? 0.f : fmaf(-0.5f, acc, 0.5f);
                 if (rl[r] >= 0 && okey(dist) <= (uint32_t)(sel.thr >> 32)) {   // warp-uniform
-                    const uint32_t id = __shfl_sync(FULL, id_cur, rl[r]);
+                    const uint32_t id = tagmode ? __ldg(a.ids + b * 32 + rl[r]) : __shfl_sync(FULL, id_cur, rl[r]);
                     const uint64_t key = make_key(dist, id);
                     if (key < sel.thr) sel.insert(key, lane);
                 }
@@ -374,7 +405,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const Scan
             uint64_t key = KEY_EMPTY;
             if (b + threadIdx.x < a.n_zero) {
                 const uint32_t id = a.zero_ids[b + threadIdx.x];
-                if (id_allowed(a.bitmap, a.n_bits, id)) key = make_key(0.f, id);
+                if (zero_row_allowed(a.bitmap, a.n_bits, a.tags, a.lang_mask, a.file_lo, a.file_hi, a.zero_ids, a.n_zero, b + threadIdx.x))
+                    key = make_key(0.f, id);
             }
             found += __syncthreads_count(key != KEY_EMPTY);
             cta_buf_stream(sel.cb, sel.cap, a.k, blockDim.x, [&](uint64_t) { return key; });
@@ -397,7 +429,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const Scan
                 uint64_t key = KEY_EMPTY;
                 if (b + lane < a.n_zero) {
                     uint32_t id = a.zero_ids[b + lane];
-                    if (id_allowed(a.bitmap, a.n_bits, id)) key = make_key(0.f, id);
+                    if (zero_row_allowed(a.bitmap, a.n_bits, a.tags, a.lang_mask, a.file_lo, a.file_hi, a.zero_ids, a.n_zero, b + lane))
+                        key = make_key(0.f, id);
                 }
                 found += __popc(__ballot_sync(FULL, key != KEY_EMPTY));
                 offer_lane_keys(sel, key, lane);

@@ -6,7 +6,8 @@
 //     <db>/gpu/meta.json   {format, version, dim, dim_pad, dtype, rows, zero_ids, words, checksum}
 //     <db>/gpu/ids.u32     [rows]            chunk ids in row order
 //     <db>/gpu/rows.f32    [rows, dim_pad]   unit-normalised rows exactly as they sit in HBM   (rows.bf16: [rows, dim])
-//     <db>/gpu/zero.u32    [zero_ids]        ids of zero-norm rows (distance 0.0, kept off the matrix)
+//     <db>/gpu/tags.u32    [rows]            packed row tags (lang_id << 27 | file_id)
+//     <db>/gpu/zero.u32    [zero_ids] ids of zero-norm rows (distance 0.0, kept off the matrix), then [zero_ids] tags
 // and `VectorStore::new / open_readonly` (store.rs:110-176,183-250) load it with large sequential reads +
 // cudaMemcpyAsync from pinned staging. A loaded index is already built and returns bit-identical results
 // (the rows are not re-normalised). db_discovery's validity rule (src/db_discovery/mod.rs:8-15) extends naturally:
@@ -16,6 +17,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 #include <sys/stat.h>
 
 #include "index.h"
@@ -129,11 +131,13 @@ int snapshot_save(const csgpu_index *ix, const char *dir_c)
     uint64_t rows = 0, sum = 0xCBF29CE484222325ull;
     {
         FileCloser fi{open_in(dir, "ids.u32.tmp", "wb")}, fr{open_in(dir, bf16 ? "rows.bf16.tmp" : "rows.f32.tmp", "wb")};
-        if (!fi.f || !fr.f) return fail(CSGPU_ERR_ARG, "cannot open snapshot files in " + dir + ": " + strerror(errno));
+        FileCloser ft{open_in(dir, "tags.u32.tmp", "wb")};
+        if (!fi.f || !fr.f || !ft.f) return fail(CSGPU_ERR_ARG, "cannot open snapshot files in " + dir + ": " + strerror(errno));
         for (const Shard *sh : ix->shards) {   // shards are concatenated in order: row order is (shard, local row)
             DeviceGuard dg(sh->device);
             int rc = dump_device(fi.f, sh->ids, sh->n_built * sizeof(uint32_t), sh->stream, sg, &sum);
             if (!rc) rc = dump_device(fr.f, bf16 ? sh->rows_bf16 : (const void *)sh->rows, sh->n_built * row_bytes, sh->stream, sg, &sum);
+            if (!rc) rc = dump_device(ft.f, sh->tags, sh->n_built * sizeof(uint32_t), sh->stream, sg, &sum);
             if (rc) return rc;
             rows += sh->n_built;
         }
@@ -145,6 +149,10 @@ int snapshot_save(const csgpu_index *ix, const char *dir_c)
             sum = mix_words(sum, ix->zero_ids.data(), ix->zero_ids.size() * sizeof(uint32_t));
             if (fwrite(ix->zero_ids.data(), sizeof(uint32_t), ix->zero_ids.size(), fz.f) != ix->zero_ids.size())
                 return fail(CSGPU_ERR_ARG, "snapshot write failed");
+            std::vector<uint32_t> zt(ix->zero_tags);
+            zt.resize(ix->zero_ids.size(), CSGPU_TAG_NONE);
+            sum = mix_words(sum, zt.data(), zt.size() * sizeof(uint32_t));
+            if (fwrite(zt.data(), sizeof(uint32_t), zt.size(), fz.f) != zt.size()) return fail(CSGPU_ERR_ARG, "snapshot write failed");
         }
     }
     {
@@ -152,11 +160,11 @@ int snapshot_save(const csgpu_index *ix, const char *dir_c)
         if (!fm.f) return fail(CSGPU_ERR_ARG, "cannot open meta.json in " + dir);
         fprintf(fm.f,
                 "{\"format\": \"csgpu-snapshot\", \"version\": 1, \"dim\": %u, \"dim_pad\": %u, \"dtype\": \"%s\", "
-                "\"rows\": %" PRIu64 ", \"zero_ids\": %zu, \"checksum\": \"%016" PRIx64 "\"}\n",
+                "\"rows\": %" PRIu64 ", \"zero_ids\": %zu, \"tags\": 1, \"checksum\": \"%016" PRIx64 "\"}\n",
                 ix->dim, ix->dim_pad, bf16 ? "bf16" : "f32", rows, ix->zero_ids.size(), sum);
     }
     // publish: data files first, meta.json last (a reader that finds meta.json finds complete data)
-    const char *names[4] = {"ids.u32", bf16 ? "rows.bf16" : "rows.f32", "zero.u32", "meta.json"};
+    const char *names[5] = {"ids.u32", bf16 ? "rows.bf16" : "rows.f32", "tags.u32", "zero.u32", "meta.json"};
     for (const char *nm : names)
         if (rename((dir + "/" + nm + ".tmp").c_str(), (dir + "/" + nm).c_str()) != 0)
             return fail(CSGPU_ERR_ARG, std::string("rename failed for ") + nm + ": " + strerror(errno));
@@ -202,12 +210,13 @@ int snapshot_load(csgpu_index *ix, const char *dir_c, int (*reserve)(csgpu_index
         size_t n;
         while ((n = fread(buf, 1, sizeof buf, fm.f)) > 0) js.append(buf, n);
     }
-    uint64_t version = 0, dim = 0, dim_pad = 0, rows = 0, nzero = 0;
+    uint64_t version = 0, dim = 0, dim_pad = 0, rows = 0, nzero = 0, has_tags = 0;
     std::string fmt, dtype, checksum;
     if (!json_str(js, "format", &fmt) || fmt != "csgpu-snapshot" || !json_u64(js, "version", &version) || version != 1 ||
         !json_u64(js, "dim", &dim) || !json_u64(js, "dim_pad", &dim_pad) || !json_u64(js, "rows", &rows) ||
         !json_u64(js, "zero_ids", &nzero) || !json_str(js, "dtype", &dtype) || !json_str(js, "checksum", &checksum))
         return fail(CSGPU_ERR_ARG, "snapshot meta.json is malformed");
+    json_u64(js, "tags", &has_tags);   // absent in snapshots written before the tag column existed: rows load untagged
     const bool bf16 = ix->dtype == CSGPU_DTYPE_BF16;
     if (dim != ix->dim || dim_pad != ix->dim_pad) {
         char b[160];
@@ -226,7 +235,8 @@ int snapshot_load(csgpu_index *ix, const char *dir_c, int (*reserve)(csgpu_index
     uint64_t sum = 0xCBF29CE484222325ull;
     {
         FileCloser fi{open_in(dir, "ids.u32", "rb")}, fr{open_in(dir, bf16 ? "rows.bf16" : "rows.f32", "rb")};
-        if (!fi.f || !fr.f) return fail(CSGPU_ERR_ARG, "snapshot data files are missing in " + dir);
+        FileCloser ft{has_tags ? open_in(dir, "tags.u32", "rb") : nullptr};
+        if (!fi.f || !fr.f || (has_tags && !ft.f)) return fail(CSGPU_ERR_ARG, "snapshot data files are missing in " + dir);
         const uint64_t G = ix->shards.size();
         for (uint64_t g = 0; g < G; ++g) {
             Shard *sh = ix->shards[g];
@@ -234,7 +244,9 @@ int snapshot_load(csgpu_index *ix, const char *dir_c, int (*reserve)(csgpu_index
             DeviceGuard dg(sh->device);
             rc = fill_device(fi.f, sh->ids, m * sizeof(uint32_t), sh->stream, sg, &sum);
             if (!rc) rc = fill_device(fr.f, bf16 ? sh->rows_bf16 : (void *)sh->rows, m * row_bytes, sh->stream, sg, &sum);
+            if (!rc && has_tags) rc = fill_device(ft.f, sh->tags, m * sizeof(uint32_t), sh->stream, sg, &sum);
             if (rc) return rc;
+            if (!has_tags && sh->cap) CS_CUDA(cudaMemsetAsync(sh->tags, 0xFF, sh->cap * sizeof(uint32_t), sh->stream));
             CS_CUDA(cudaMemsetAsync(sh->status, 0, sh->cap, sh->stream));
             CS_CUDA(cudaStreamSynchronize(sh->stream));
             sh->n_total = sh->n_built = m;
@@ -248,12 +260,20 @@ int snapshot_load(csgpu_index *ix, const char *dir_c, int (*reserve)(csgpu_index
             return fail(CSGPU_ERR_ARG, "snapshot zero.u32 is missing or truncated");
         }
         sum = mix_words(sum, ix->zero_ids.data(), nzero * sizeof(uint32_t));
+        ix->zero_tags.assign(nzero, CSGPU_TAG_NONE);
+        if (has_tags) {
+            if (fread(ix->zero_tags.data(), sizeof(uint32_t), nzero, fz.f) != nzero) {
+                ix->zero_ids.clear(); ix->zero_tags.clear();
+                return fail(CSGPU_ERR_ARG, "snapshot zero.u32 is missing or truncated");
+            }
+            sum = mix_words(sum, ix->zero_tags.data(), nzero * sizeof(uint32_t));
+        }
     }
     char hex[32];
     snprintf(hex, sizeof hex, "%016" PRIx64, sum);
     if (checksum != hex) {
         for (Shard *sh : ix->shards) sh->n_total = sh->n_built = 0;
-        ix->zero_ids.clear();
+        ix->zero_ids.clear(); ix->zero_tags.clear();
         return fail(CSGPU_ERR_ARG, "snapshot checksum mismatch (corrupt or partially written snapshot)");
     }
     return finish(ix);

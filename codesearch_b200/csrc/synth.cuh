@@ -48,6 +48,21 @@ static __global__ void synth_rows_kernel(float4 *__restrict__ rows, uint32_t *__
     }
 }
 
+// Synthetic row tags (bit-identical to oracle/oracle.py synth_tags): file_id = row / 37,
+// lang_id = fmix32(file_id) % 23, tag = (lang_id << 27) | file_id.
+__host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h)
+{
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+static __global__ void synth_tags_kernel(uint32_t *__restrict__ tags, uint64_t first_row, uint64_t n)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t file = (uint32_t)((first_row + i) / 37) & 0x07FFFFFFu;
+        tags[i] = ((fmix32(file) % 23u) << 27) | file;
+    }
+}
+
 // Row status written by normalise_rows_kernel.
 enum : uint8_t { ROW_OK = 0, ROW_DEAD = 1, ROW_ZERO = 2, ROW_NONFINITE = 3 };
 

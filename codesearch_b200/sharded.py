@@ -76,8 +76,21 @@ class ShardedSearcher:
         self.out_pin = torch.empty(k_max, dtype=torch.int64).pin_memory()
 
     # -- device-resident: q_dev is a [d_pad] float32 CUDA tensor; returns a view of k keys (int64 bits)
-    def search_keys_device(self, q_dev: torch.Tensor, k: int) -> torch.Tensor:
+    def search_keys_device(self, q_dev: torch.Tensor, k: int, pred: "_lib.Predicate | None" = None) -> torch.Tensor:
+        """pred: row-tag predicate (its file_bitmap, if any, is a DEVICE pointer) -> csgpu_search_tagged_keys_device."""
         stream = torch.cuda.current_stream().cuda_stream
+        if pred is not None:
+            fused = self.exchange == "fused"
+            dst = self.out[:k] if (fused or self.world == 1) else self.local[:k]
+            _lib.check(self.lib.csgpu_search_tagged_keys_device(self.store.handle, q_dev.data_ptr(), k, ctypes.byref(pred),
+                                                                1 if fused else 0, dst.data_ptr(), stream))
+            if fused or self.world == 1:
+                return dst
+            gathered = allgather_keys(dst, self.world, self.group, self.gathered[: self.world * k])
+            out = self.out[:k]
+            _lib.check(self.lib.csgpu_merge_keys_device(self.store.handle, gathered.data_ptr(), self.world, k,
+                                                        out.data_ptr(), stream))
+            return out
         if self.exchange == "fused":
             out = self.out[:k]
             _lib.check(self.lib.csgpu_search_keys_exchange_device(self.store.handle, q_dev.data_ptr(), k,
@@ -94,14 +107,14 @@ class ShardedSearcher:
         return out
 
     # -- end to end: host query in, host (ids, distances) out
-    def search(self, query_embedding, k: int):
+    def search(self, query_embedding, k: int, pred: "_lib.Predicate | None" = None):
         q = np.ascontiguousarray(query_embedding, dtype=np.float32).reshape(-1)
         if q.size != self.store.dimensions:
             raise _lib.CsgpuError(_lib.ERR_DIM, f"Query embedding dimension mismatch: expected "
                                                 f"{self.store.dimensions}, got {q.size}")
         self.q_pin[: q.size].copy_(torch.from_numpy(q))
         self.q_dev.copy_(self.q_pin, non_blocking=True)
-        keys = self.search_keys_device(self.q_dev, k)
+        keys = self.search_keys_device(self.q_dev, k, pred)
         self.out_pin[:k].copy_(keys, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return decode_keys(self.out_pin[:k].numpy())

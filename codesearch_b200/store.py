@@ -27,6 +27,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import CsgpuError
+from .tags import FileTable, TagPredicate
 
 
 @dataclass
@@ -116,6 +117,7 @@ class VectorStore:
         self.db_path = db_path
         self.next_id = 0
         self._chunks: dict[int, Chunk] = {}
+        self.files = FileTable()   # path -> file_id / language for the row tags
         self._h = ctypes.c_void_p()
         devs = None
         n = 1
@@ -139,6 +141,8 @@ class VectorStore:
                         rec = json.loads(line)
                         cid = int(rec.pop("id"))
                         self._chunks[cid] = Chunk(**rec)
+                for cid in sorted(self._chunks):   # same first-seen order as the inserts that wrote the tags
+                    self.files.file_id(self._chunks[cid].path)
                 if self._chunks:
                     self.next_id = max(self._chunks) + 1
 
@@ -187,7 +191,8 @@ class VectorStore:
         start = self.next_id
         ids = np.arange(start, start + len(chunks), dtype=np.uint32)
         rows = _f32([c.embedding for c in chunks])
-        self.append_rows(rows, ids)
+        tags = np.array([self.files.tag(c.chunk.path) for c in chunks], dtype=np.uint32)
+        self.append_rows(rows, ids, tags)
         for i, c in zip(ids, chunks):
             self._chunks[int(i)] = c.chunk
         self.next_id = start + len(chunks)
@@ -196,21 +201,34 @@ class VectorStore:
     def insert_chunks(self, chunks: Sequence[EmbeddedChunk]) -> int:
         return len(self.insert_chunks_with_ids(chunks))
 
-    def append_rows(self, rows: np.ndarray, ids: np.ndarray) -> None:
-        """Bulk path: raw [n, dim] embeddings with explicit chunk ids (no metadata)."""
+    def append_rows(self, rows: np.ndarray, ids: np.ndarray, tags: np.ndarray | None = None) -> None:
+        """Bulk path: raw [n, dim] embeddings with explicit chunk ids (no metadata); optional packed row tags."""
         rows = _f32(rows)
         ids = np.ascontiguousarray(ids, dtype=np.uint32)
         if rows.ndim != 2 or rows.shape[1] != self.dimensions:
             raise ValueError(
                 f"Embedding dimension mismatch: expected {self.dimensions}, got {rows.shape[-1]}")
         assert ids.shape == (rows.shape[0],)
-        _lib.check(self._lib.csgpu_append(self._h, rows.ctypes.data_as(_lib._f32p),
-                                          ids.ctypes.data_as(_lib._u32p), rows.shape[0]))
+        if tags is None:
+            _lib.check(self._lib.csgpu_append(self._h, rows.ctypes.data_as(_lib._f32p),
+                                              ids.ctypes.data_as(_lib._u32p), rows.shape[0]))
+        else:
+            tags = np.ascontiguousarray(tags, dtype=np.uint32)
+            assert tags.shape == ids.shape
+            _lib.check(self._lib.csgpu_append_tagged(self._h, rows.ctypes.data_as(_lib._f32p), ids.ctypes.data_as(_lib._u32p),
+                                                     tags.ctypes.data_as(_lib._u32p), rows.shape[0]))
         if ids.size:
             self.next_id = max(self.next_id, int(ids.max()) + 1)
 
-    def append_synthetic(self, seed: int, first_row: int, n: int, id_base: int = 0) -> None:
-        _lib.check(self._lib.csgpu_append_synthetic(self._h, seed, first_row, n, id_base))
+    def append_synthetic(self, seed: int, first_row: int, n: int, id_base: int = 0, tagged: bool = False) -> None:
+        fn = self._lib.csgpu_append_synthetic_tagged if tagged else self._lib.csgpu_append_synthetic
+        _lib.check(fn(self._h, seed, first_row, n, id_base))
+
+    def get_tags(self, ids) -> np.ndarray:
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        out = np.empty(ids.size, dtype=np.uint32)
+        _lib.check(self._lib.csgpu_get_tags(self._h, ids.ctypes.data_as(_lib._u32p), ids.size, out.ctypes.data_as(_lib._u32p)))
+        return out
 
     def reserve(self, total_rows: int) -> None:
         _lib.check(self._lib.csgpu_reserve(self._h, total_rows))
@@ -245,9 +263,10 @@ class VectorStore:
         self._check_writable()
         _lib.check(self._lib.csgpu_clear(self._h))
         self._chunks.clear()
+        self.files = FileTable()
         self.next_id = 0
         if self.db_path is not None:   # store.rs:690-706 clears both LMDB tables
-            for name in ("gpu/meta.json", "gpu/ids.u32", "gpu/rows.f32", "gpu/rows.bf16", "gpu/zero.u32", "chunks.jsonl"):
+            for name in ("gpu/meta.json", "gpu/ids.u32", "gpu/rows.f32", "gpu/rows.bf16", "gpu/tags.u32", "gpu/zero.u32", "chunks.jsonl"):
                 try:
                     os.remove(os.path.join(self.db_path, name))
                 except FileNotFoundError:
@@ -272,6 +291,32 @@ class VectorStore:
                                                  ctypes.byref(on))
         _lib.check(rc)
         return oi[: on.value].copy(), od[: on.value].copy()
+
+    def search_tagged_ids(self, query_embedding, limit: int, pred: TagPredicate):
+        """Predicate-filtered hot path (csgpu_search_tagged): language mask / file range / per-file bitmap evaluated on
+        the device from the row tags; rows that fail are never read."""
+        q = _f32(query_embedding).reshape(-1)
+        k = int(limit)
+        oi = np.empty(max(k, 1), dtype=np.uint32)
+        od = np.empty(max(k, 1), dtype=np.float32)
+        on = ctypes.c_uint32(0)
+        cp = _lib.Predicate(pred.lang_mask & 0xFFFFFFFF, pred.file_lo, pred.file_hi & 0xFFFFFFFF, 0, None, 0)
+        bm = None
+        if pred.file_bitmap is not None:
+            bm = np.ascontiguousarray(pred.file_bitmap, dtype=np.uint64)
+            cp.file_bitmap = bm.ctypes.data
+            cp.n_file_bits = int(pred.n_file_bits)
+        _lib.check(self._lib.csgpu_search_tagged(self._h, q.ctypes.data_as(_lib._f32p), q.size, k, ctypes.byref(cp),
+                                                 oi.ctypes.data_as(_lib._u32p), od.ctypes.data_as(_lib._f32p), ctypes.byref(on)))
+        return oi[: on.value].copy(), od[: on.value].copy()
+
+    def search_tagged(self, query_embedding, limit: int, languages=None, path_prefix: str | None = None,
+                      path_contains: str | None = None, project_root: str = "") -> list[SearchResult]:
+        """search() restricted to files of the given languages and/or under a path prefix / containing a substring —
+        the filters the reference applies AFTER search on the host (src/search/mod.rs:727-737, src/server/mod.rs:553-559),
+        applied here BEFORE scoring so that `limit` results always survive."""
+        pred = self.files.predicate(languages, path_prefix, path_contains, project_root)
+        return self._join(*self.search_tagged_ids(query_embedding, limit, pred))
 
     def search_batch_ids(self, queries, limit: int):
         q = _f32(queries)

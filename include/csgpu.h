@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define CSGPU_ABI_VERSION 2
+#define CSGPU_ABI_VERSION 3
 
 enum {
     CSGPU_OK            = 0,
@@ -144,6 +144,46 @@ int  csgpu_search_filtered(const csgpu_index *ix, const float *q, uint32_t q_len
                            const uint64_t *id_bitmap, uint64_t n_bits,
                            uint32_t *out_ids, float *out_dist, uint32_t *out_n);
 
+/* ---- row-tag filter columns: every row carries ONE packed u32 tag = (lang_id << 27) | file_id
+ *      in HBM next to its chunk id, so a file/language filter is a PREDICATE evaluated on the device before a row is
+ *      read — the host ships at most a per-FILE bitmap (~37x smaller than a per-chunk one; chunker: ~37 chunks per
+ *      file) instead of walking ChunkMetadata to build an N-bit map per query. lang_id follows the declaration order
+ *      of `Language` (src/file/language.rs:5-29: Rust = 0 ... Unknown = 22; detection src/file/language.rs:31-88);
+ *      file_id is a dense per-file number the host assigns (FileMetaStore, src/cache/file_meta.rs). The reference reads
+ *      `primary_language` but never writes it (src/search/mod.rs:120-124 vs src/index/mod.rs:882-887) and only
+ *      post-filters paths on the host (src/search/mod.rs:727-737, src/server/mod.rs:553-559); this is the new
+ *      capability that replaces both. Rows appended with csgpu_append carry CSGPU_TAG_NONE. Tags follow their rows
+ *      through csgpu_build / csgpu_remove / csgpu_save / csgpu_load. */
+#define CSGPU_TAG_LANG_SHIFT 27u
+#define CSGPU_TAG_FILE_MASK  0x07FFFFFFu
+#define CSGPU_TAG_NONE       0xFFFFFFFFu   /* lang 31 (never a Language variant), file 0x7FFFFFF */
+#define CSGPU_TAG(lang, file) ((((uint32_t)(lang) & 31u) << CSGPU_TAG_LANG_SHIFT) | ((uint32_t)(file) & CSGPU_TAG_FILE_MASK))
+
+/* A row passes iff  (lang_mask >> lang_id) & 1   AND   file_lo <= file_id <= file_hi
+ *                   AND (file_bitmap == NULL  OR  (file_id < n_file_bits AND bit file_id of file_bitmap is set)).
+ * lang_mask = 0xFFFFFFFF, file_lo = 0, file_hi = 0xFFFFFFFF, file_bitmap = NULL passes every row (including
+ * untagged ones). A path-prefix filter is a file range when the host numbers files in path order, a file bitmap
+ * otherwise. file_bitmap is a HOST pointer for csgpu_search_tagged and a DEVICE pointer for the *_device call. */
+typedef struct csgpu_predicate_t {
+    uint32_t lang_mask;
+    uint32_t file_lo, file_hi;
+    uint32_t reserved;
+    const uint64_t *file_bitmap;
+    uint64_t n_file_bits;
+} csgpu_predicate_t;
+
+/* csgpu_append + one tag per row (CSGPU_TAG(lang_id, file_id)). */
+int  csgpu_append_tagged(csgpu_index *ix, const float *rows, const uint32_t *ids, const uint32_t *tags, uint64_t n);
+
+/* Exact top-k over the rows that pass `pred` (same semantics as csgpu_search_filtered with the equivalent id
+ * bitmap; rows that fail are never read from HBM). */
+int  csgpu_search_tagged(const csgpu_index *ix, const float *q, uint32_t q_len, uint32_t k,
+                         const csgpu_predicate_t *pred,
+                         uint32_t *out_ids, float *out_dist, uint32_t *out_n);
+
+/* Reads back the tags of `n` chunk ids (CSGPU_TAG_NONE for ids that are not live). Test/introspection helper. */
+int  csgpu_get_tags(const csgpu_index *ix, const uint32_t *ids, uint64_t n, uint32_t *out_tags);
+
 /* ---- device-resident entry points (single-device index; for hosts that already hold the
  *      query on the GPU, and for rank-per-GPU sharding under torch.distributed) -----------
  * All pointers are DEVICE pointers on the index's device; `stream` is a cudaStream_t (NULL
@@ -183,6 +223,13 @@ int  csgpu_search_keys_exchange_device(const csgpu_index *ix, const float *q_dev
 int  csgpu_exchange_status(const csgpu_index *ix, uint32_t *timed_out);
 void csgpu_exchange_destroy(csgpu_index *ix);
 
+/* Device-resident predicate search: local top-k (exchange = 0) or, with a connected exchange, the GLOBAL top-k over
+ * all ranks in the same kernel (exchange = 1; BASELINE configs[4]: filter mask + 8 GPUs). pred->file_bitmap is a
+ * device pointer that must stay valid until `stream` drains. */
+int  csgpu_search_tagged_keys_device(const csgpu_index *ix, const float *q_dev, uint32_t k,
+                                     const csgpu_predicate_t *pred, uint32_t exchange,
+                                     uint64_t *out_keys_dev /*[k]*/, void *stream);
+
 /* Host-side: keys -> (ids, distances); returns the number of non-empty slots in *out_n. */
 void csgpu_decode_keys(const uint64_t *keys, uint32_t k, uint32_t *out_ids, float *out_dist,
                        uint32_t *out_n);
@@ -192,6 +239,10 @@ void csgpu_decode_keys(const uint64_t *keys, uint32_t k, uint32_t *out_ids, floa
  * spec in codesearch_b200/csrc/synth.cuh), chunk id = (uint32_t)global row index + id_base. */
 int  csgpu_append_synthetic(csgpu_index *ix, uint64_t seed, uint64_t first_row, uint64_t n,
                             uint32_t id_base);
+/* Same rows, plus synthetic tags: file_id = global_row / 37, lang_id = fmix32(file_id) % 23
+ * (fmix32 = MurmurHash3's 32-bit finaliser; 23 = `Language` variants, src/file/language.rs:5-29). */
+int  csgpu_append_synthetic_tagged(csgpu_index *ix, uint64_t seed, uint64_t first_row, uint64_t n,
+                                   uint32_t id_base);
 /* The same generator into a host buffer via the device (for cross-checking the generators). */
 int  csgpu_synth_rows_host(const csgpu_index *ix, uint64_t seed, uint64_t first_row, uint64_t n,
                            float *out_rows /*[n, dim] host*/);

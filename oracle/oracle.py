@@ -312,3 +312,64 @@ def score_from_distance(distance):
 def rrf_scores(ranked_ids, k_rrf: float = 60.0):
     """rerank/mod.rs:57-59 — consumer contract: position in the list is the rank."""
     return {int(i): 1.0 / (k_rrf + r + 1.0) for r, i in enumerate(ranked_ids)}
+
+
+# ---- row tags and the file/language predicate (SURVEY.md §8f N4) -------------------------------------------------
+# Independent restatement (the product's host half is codesearch_b200/tags.py, its device half csrc/scan.cuh).
+# lang_id = position in `enum Language` (/root/reference/src/file/language.rs:5-29).
+LANGUAGE_ORDER = ["Rust", "Python", "JavaScript", "TypeScript", "Go", "Java", "C", "Cpp", "CSharp", "Ruby", "Php",
+                  "Swift", "Kotlin", "Shell", "Markdown", "Json", "Yaml", "Toml", "Sql", "Html", "Css", "Xml", "Unknown"]
+
+
+def language_from_path(path: str) -> str:
+    """`Language::from_path` (src/file/language.rs:31-44): `from_extension` (:60-88, lower-cased) first, then
+    `from_filename` (:47-57) on the exact file name. Path::extension is the text after the last dot of the file
+    name, where a leading dot does not start an extension."""
+    name = path.replace("\\", "/").rstrip("/").split("/")[-1]
+    body = name[1:] if name.startswith(".") else name
+    ext = body.rsplit(".", 1)[1].lower() if "." in body else ""
+    table = [("Rust", ["rs"]), ("Python", ["py", "pyw", "pyi"]), ("JavaScript", ["js", "mjs", "cjs"]),
+             ("TypeScript", ["ts", "mts", "cts", "tsx", "jsx"]), ("Go", ["go"]), ("Java", ["java"]), ("C", ["c", "h"]),
+             ("Cpp", ["cpp", "cc", "cxx", "hpp", "hxx"]), ("CSharp", ["cs"]), ("Ruby", ["rb", "rake"]), ("Php", ["php"]),
+             ("Swift", ["swift"]), ("Kotlin", ["kt", "kts"]), ("Shell", ["sh", "bash", "zsh"]),
+             ("Markdown", ["md", "markdown", "txt"]), ("Json", ["json"]), ("Yaml", ["yaml", "yml"]), ("Toml", ["toml"]),
+             ("Sql", ["sql"]), ("Html", ["html", "htm"]), ("Css", ["css", "scss", "sass", "less"]),
+             ("Xml", ["xml", "csproj", "props", "targets", "resx", "config"])]
+    for lang, exts in table:
+        if ext in exts:
+            return lang
+    if name in ("Dockerfile", "Containerfile", "Makefile", "GNUmakefile", "makefile", ".env", ".envrc", "CMakeLists"):
+        return "Shell"
+    if name in ("Jenkinsfile", "Vagrantfile", "Fastfile", "Appfile", "Podfile"):
+        return "Ruby"
+    return "Unknown"
+
+
+def synth_tags(first_row: int, n: int) -> np.ndarray:
+    """SURVEY.md §8d C5: file_id = row // 37, lang_id = fmix32(file_id) % 23 (MurmurHash3 32-bit finaliser);
+    tag = lang_id << 27 | file_id. Pure-Python integers (slow, small n only) so it shares nothing with the product."""
+    out = np.empty(n, dtype=np.uint32)
+    for i in range(n):
+        f = ((first_row + i) // 37) & 0x07FFFFFF
+        h = f
+        h ^= h >> 16
+        h = (h * 0x85EBCA6B) & 0xFFFFFFFF
+        h ^= h >> 13
+        h = (h * 0xC2B2AE35) & 0xFFFFFFFF
+        h ^= h >> 16
+        out[i] = ((h % 23) << 27) | f
+    return out
+
+
+def tag_predicate_mask(tags, lang_mask=0xFFFFFFFF, file_lo=0, file_hi=0xFFFFFFFF, file_bitmap=None, n_file_bits=0):
+    """Row passes iff language bit set AND file_lo <= file <= file_hi AND (no bitmap OR file bit set)
+    (include/csgpu.h csgpu_predicate_t). The reference's equivalents are host post-filters: path prefix
+    src/search/mod.rs:727-737, path substring src/server/mod.rs:553-559."""
+    out = np.zeros(len(tags), dtype=bool)
+    for i, t in enumerate(np.asarray(tags, dtype=np.uint64).tolist()):
+        lang, f = t >> 27, t & 0x07FFFFFF
+        ok = ((lang_mask >> lang) & 1) == 1 and file_lo <= f <= file_hi
+        if ok and file_bitmap is not None:
+            ok = f < n_file_bits and ((int(file_bitmap[f >> 6]) >> (f & 63)) & 1) == 1
+        out[i] = ok
+    return out
