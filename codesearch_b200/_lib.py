@@ -42,6 +42,8 @@ class Stats(ctypes.Structure):
         ("rows_per_device", ctypes.c_uint64 * 8),
         ("coalesced_passes", ctypes.c_uint64),
         ("coalesced_queries", ctypes.c_uint64),
+        ("prefilter_rescored", ctypes.c_uint64),
+        ("shadow_bytes", ctypes.c_uint64),
     ]
 
 
@@ -76,6 +78,7 @@ SIGNATURES = {
     "csgpu_load": (ctypes.c_int, [_vp, ctypes.c_char_p]),
     "csgpu_search": (ctypes.c_int, [_vp, _f32p, ctypes.c_uint32, ctypes.c_uint32, _u32p, _f32p, _u32p]),
     "csgpu_set_coalescing": (ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32]),
+    "csgpu_set_tensor_prefilter": (ctypes.c_int, [_vp, ctypes.c_uint32]),
     "csgpu_search_batch": (ctypes.c_int, [_vp, _f32p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _u32p, _f32p, _u32p]),
     "csgpu_search_variants": (ctypes.c_int, [_vp, _f32p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _u32p, _f32p, _u32p]),
     "csgpu_search_filtered": (ctypes.c_int, [_vp, _f32p, ctypes.c_uint32, ctypes.c_uint32, _u64p, ctypes.c_uint64, _u32p, _f32p, _u32p]),

@@ -40,6 +40,7 @@ void count_launch(uint64_t n) { g_kernel_launches.fetch_add(n, std::memory_order
 // ---------------------------------------------------------------------------------------
 constexpr uint32_t MAX_GRID = 148 * 4;   // upper bound on persistent grid size we ever launch
 constexpr uint32_t MAX_BATCH = 16;       // queries per multi-query scan
+constexpr uint32_t PREFILTER_MIN_BATCH = 9;   // tensor prefilter on: batches beyond one multi-query pass (8) go to the tensor cores
 constexpr uint32_t GEMM_MIN_BATCH = 40;  // csgpu_search_batch switches to the SIMT GEMM path from here
 
 static int ctx_create(const csgpu_index *ix, Shard *sh, SearchCtx **out)
@@ -757,7 +758,7 @@ void csgpu_destroy(csgpu_index *ix)
         DeviceGuard dg(sh->device);
         for (SearchCtx *c : sh->all_ctx) ctx_destroy(c);
         batch_free_ctx(sh);
-        cudaFree(sh->rows_bf16); cudaFree(sh->stage);
+        cudaFree(sh->rows_bf16); cudaFree(sh->stage); cudaFree(sh->shadow_bf16);
         cudaFree(sh->rows); cudaFree(sh->ids); cudaFree(sh->status); cudaFree(sh->tags);
         if (sh->stream) cudaStreamDestroy(sh->stream);
         delete sh;
@@ -963,7 +964,8 @@ int csgpu_clear(csgpu_index *ix)
     for (Shard *sh : ix->shards) {
         DeviceGuard dg(sh->device);
         cudaFree(sh->rows); cudaFree(sh->ids); cudaFree(sh->status); cudaFree(sh->tags);
-        cudaFree(sh->rows_bf16); cudaFree(sh->stage);
+        cudaFree(sh->rows_bf16); cudaFree(sh->stage); cudaFree(sh->shadow_bf16);
+        sh->shadow_bf16 = nullptr; sh->shadow_valid = false; sh->shadow_rows = 0;
         sh->rows_bf16 = nullptr; sh->stage = nullptr; sh->stage_cap = 0; sh->map_valid = false;
         sh->rows = nullptr; sh->ids = nullptr; sh->status = nullptr; sh->tags = nullptr;
         sh->n_built = sh->n_total = sh->cap = 0;
@@ -1095,7 +1097,8 @@ int csgpu_search_batch(const csgpu_index *ix, const float *q, uint32_t q_len, ui
     if (ix->dtype == CSGPU_DTYPE_BF16) return batch_search(ix, q, b, k, out_ids, out_dist, out_n, nullptr);
     // large batches: register-tiled fp32 SIMT GEMM + fused threshold filter (gemm_simt.cuh). It pads to 128-query
     // blocks, so below ~40 queries the HBM-bound multi-query scan (8 queries per pass) is faster.
-    if (b >= GEMM_MIN_BATCH && batch_gemm_available(ix)) {
+    const bool prefilter = ix->tensor_prefilter && ix->shards.size() == 1 && ix->shards[0]->shadow_valid;
+    if ((b >= GEMM_MIN_BATCH || (prefilter && b >= PREFILTER_MIN_BATCH)) && batch_gemm_available(ix)) {
         std::vector<uint32_t> zero_q;
         rc = batch_search(ix, q, b, k, out_ids, out_dist, out_n, &zero_q);
         for (size_t z = 0; z < zero_q.size() && !rc; ++z) {   // zero-norm queries: distance 0.0 everywhere (scan kernel)
@@ -1123,6 +1126,18 @@ int csgpu_search_batch(const csgpu_index *ix, const float *q, uint32_t q_len, ui
             j += 1;
         }
     }
+    return CSGPU_OK;
+}
+
+int csgpu_set_tensor_prefilter(csgpu_index *ix, uint32_t enabled)
+{
+    if (!ix) return fail(CSGPU_ERR_ARG, "null index");
+    if (ix->dtype != CSGPU_DTYPE_F32) return fail(CSGPU_ERR_ARG, "the tensor prefilter belongs to an fp32 index (a bf16 index is already on the tensor cores)");
+    if (ix->shards.size() != 1) return fail(CSGPU_ERR_ARG, "tensor prefilter: multi-device index is not implemented yet");
+    if (enabled && !bf16_dim_supported(ix->dim)) return fail(CSGPU_ERR_ARG, "tensor prefilter needs dim % 64 == 0 and 64 <= dim <= 512");
+    ix->tensor_prefilter = enabled != 0;
+    if (ix->built)
+        for (Shard *sh : ix->shards) { int rc = shadow_refresh(ix, sh); if (rc) { ix->tensor_prefilter = false; return rc; } }
     return CSGPU_OK;
 }
 
@@ -1363,6 +1378,9 @@ int csgpu_stats(const csgpu_index *ix, csgpu_stats_t *out)
     out->live_rows += ix->zero_ids.size();
     out->coalesced_passes = ix->coalescer.passes.load();
     out->coalesced_queries = ix->coalescer.queries.load();
+    out->prefilter_rescored = ix->prefilter_rescored.load();
+    for (const Shard *sh : ix->shards) out->shadow_bytes += sh->shadow_rows * (uint64_t)ix->dim * 2;
+    out->bytes_on_device += out->shadow_bytes;
     return CSGPU_OK;
 }
 

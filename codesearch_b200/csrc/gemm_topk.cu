@@ -12,6 +12,7 @@
 #include "index.h"
 #include "gemm_simt.cuh"
 #include "gemm_topk.cuh"
+#include "rescore.cuh"
 #include "scan.cuh"
 #include "synth.cuh"
 
@@ -20,6 +21,13 @@ namespace csgpu {
 constexpr uint32_t BF_CAP = 8192;          // candidate slots per query
 constexpr uint32_t BF_MAX_QBLOCKS = 8;     // 1024 queries per pass
 constexpr uint32_t BF_PHASE_GROWTH = 8;
+
+// tensor-core contraction: the bf16 index itself, or the bf16 shadow of an fp32 index (rescore.cuh)
+static bool tc_path(const csgpu_index *ix, const Shard *sh)
+{
+    return ix->dtype == CSGPU_DTYPE_BF16 || (ix->tensor_prefilter && sh->shadow_valid);
+}
+static bool rescore_path(const csgpu_index *ix, const Shard *sh) { return ix->dtype == CSGPU_DTYPE_F32 && tc_path(ix, sh); }
 
 // ---------------------------------------------------------------------------------------------
 // kernels local to this file
@@ -31,14 +39,14 @@ constexpr uint32_t BF_PHASE_GROWTH = 8;
 template <bool BIG>
 __global__ void __launch_bounds__(SCAN_THREADS, 1)
 select_candidates_kernel(uint64_t *__restrict__ cand, unsigned *__restrict__ count, const unsigned *__restrict__ n_done,
-                         float *__restrict__ thr, const uint32_t *__restrict__ ids,
+                         float *__restrict__ thr, const uint32_t *__restrict__ ids, const uint8_t *__restrict__ flags,
                          uint32_t cap, uint32_t k, uint32_t kpad, uint32_t n_active,
                          const uint32_t *__restrict__ zero_ids, uint32_t n_zero, uint64_t *__restrict__ final_out)
 {
     extern __shared__ __align__(16) uint64_t smem[];
     const uint32_t q = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (q >= n_active) {
+    if (q >= n_active || flags[q]) {   // padding rows and zero-norm queries (answered by the scan kernel) stay inactive
         if (threadIdx.x == 0) { count[q] = 0; thr[q] = -1.f; }
         return;
     }
@@ -79,10 +87,10 @@ select_candidates_kernel(uint64_t *__restrict__ cand, unsigned *__restrict__ cou
     }
 }
 
-__global__ void init_thresholds_kernel(float *thr, unsigned *count, uint32_t n_active, uint32_t n_total)
+__global__ void init_thresholds_kernel(float *thr, unsigned *count, const uint8_t *flags, uint32_t n_active, uint32_t n_total)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_total) { thr[i] = (i < n_active) ? __int_as_float(0x7f800000) : -1.f; count[i] = 0; }
+    if (i < n_total) { thr[i] = (i < n_active && !flags[i]) ? __int_as_float(0x7f800000) : -1.f; count[i] = 0; }
 }
 
 __global__ void max_count_kernel(const unsigned *count, uint32_t n, unsigned *out)
@@ -233,11 +241,38 @@ int batch_after_build(const csgpu_index *ix, Shard *sh)
         if (!rc) rc = make_map(&sh->map_c2, sh->rows_bf16 ? sh->rows_bf16 : (void *)sh->ids, sh->n_built, ix->dim, GT_BLOCK_N / 2, false);
         if (rc) return rc;
     } else {
+        int rc = shadow_refresh(ix, sh);
+        if (rc) return rc;
         if (!batch_f32_dim_supported(ix->dim_pad) || sh->rows == nullptr) return CSGPU_OK;
-        int rc = make_map(&sh->map_c, sh->rows, sh->n_built, ix->dim_pad, GS_BN, true);
+        rc = make_map(&sh->map_c, sh->rows, sh->n_built, ix->dim_pad, GS_BN, true);
         if (rc) return rc;
     }
     sh->map_valid = true;
+    return CSGPU_OK;
+}
+
+// (re)build or drop the bf16 shadow of an fp32 shard's built rows (csgpu_set_tensor_prefilter; rescore.cuh)
+int shadow_refresh(const csgpu_index *ix, Shard *sh)
+{
+    DeviceGuard g(sh->device);
+    sh->shadow_valid = false;
+    cudaFree(sh->shadow_bf16);
+    sh->shadow_bf16 = nullptr;
+    sh->shadow_rows = 0;
+    if (!ix->tensor_prefilter || ix->dtype != CSGPU_DTYPE_F32 || sh->n_built == 0 || sh->rows == nullptr) return CSGPU_OK;
+    if (!bf16_dim_supported(ix->dim)) return fail(CSGPU_ERR_ARG, "tensor prefilter needs dim % 64 == 0 and 64 <= dim <= 512");
+    cudaError_t e = cudaMalloc(&sh->shadow_bf16, sh->n_built * (size_t)ix->dim * 2);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(CSGPU_ERR_OOM, "no room in HBM for the bf16 shadow of the fp32 rows (tensor prefilter needs +50 %)"); }
+    const uint64_t n4 = sh->n_built * (uint64_t)ix->dim4;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((n4 + 255) / 256, (uint64_t)sh->sm_count * 16);
+    shadow_from_rows_kernel<<<grid, 256, 0, sh->stream>>>(reinterpret_cast<const float4 *>(sh->rows), reinterpret_cast<uint2 *>(sh->shadow_bf16), n4);
+    count_launch();
+    CS_CUDA(cudaGetLastError());
+    CS_CUDA(cudaStreamSynchronize(sh->stream));
+    int rc = make_map(&sh->map_shadow, sh->shadow_bf16, sh->n_built, ix->dim, GT_BLOCK_N, false);
+    if (rc) return rc;
+    sh->shadow_rows = sh->n_built;
+    sh->shadow_valid = true;
     return CSGPU_OK;
 }
 
@@ -282,7 +317,7 @@ static int batch_ctx(const csgpu_index *ix, Shard *sh, BatchCtx **out)
 // ---------------------------------------------------------------------------------------------
 // search
 // ---------------------------------------------------------------------------------------------
-static uint32_t tile_rows_of(const csgpu_index *ix) { return ix->dtype == CSGPU_DTYPE_BF16 ? GT_BLOCK_N : GS_BN; }
+static uint32_t tile_rows_of(const csgpu_index *ix, const Shard *sh) { return tc_path(ix, sh) ? GT_BLOCK_N : GS_BN; }
 
 static int launch_gemm(const csgpu_index *ix, Shard *sh, BatchCtx *c, const CUtensorMap &map_q, uint32_t n_qblocks,
                        uint64_t t0, uint64_t t1)
@@ -302,7 +337,8 @@ static int launch_gemm(const csgpu_index *ix, Shard *sh, BatchCtx *c, const CUte
     a.prefetch_tiles = env_pf > 0 ? (uint32_t)env_pf : 0u;
     const uint64_t n_tiles = t1 - t0;
     cudaError_t e = cudaSuccess;
-    if (ix->dtype == CSGPU_DTYPE_BF16) {
+    if (tc_path(ix, sh)) {
+        const CUtensorMap &map_rows = ix->dtype == CSGPU_DTYPE_BF16 ? sh->map_c : sh->map_shadow;
         a.n_kchunks = ix->dim / GT_BLOCK_K;
         const size_t q_bytes = (size_t)a.n_kchunks * GT_QCHUNK_BYTES;
         const size_t avail = 227 * 1024 - 1024 /*alignment slack*/ - 256 /*static*/ - q_bytes;
@@ -312,7 +348,7 @@ static int launch_gemm(const csgpu_index *ix, Shard *sh, BatchCtx *c, const CUte
         // (profiles/r01_bf16_2cta.txt: 9.06 vs 8.44 ms at B=1024,k=100) — under the 1 kW cap the MMA rate, not the
         // operand stream, is what binds — so it is opt-in: CSGPU_BF16_2CTA=1
         static const int env_2cta = getenv("CSGPU_BF16_2CTA") ? atoi(getenv("CSGPU_BF16_2CTA")) : 0;
-        if (env_2cta && n_qblocks >= 2 && n_qblocks % 2 == 0) {
+        if (env_2cta && ix->dtype == CSGPU_DTYPE_BF16 && n_qblocks >= 2 && n_qblocks % 2 == 0) {
             const size_t avail2 = 227 * 1024 - 1024 - 512 - q_bytes;
             const int st2 = (int)std::min<size_t>(8, avail2 / GT2_STAGE_BYTES);
             if (st2 >= 4) {
@@ -340,7 +376,7 @@ static int launch_gemm(const csgpu_index *ix, Shard *sh, BatchCtx *c, const CUte
 #define CS_GT(S)                                                                                                   \
     case S:                                                                                                        \
         e = cudaFuncSetAttribute(gemm_topk_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
-        if (e == cudaSuccess) gemm_topk_kernel<S><<<grid, GT_THREADS, smem, c->stream>>>(map_q, sh->map_c, a);     \
+        if (e == cudaSuccess) gemm_topk_kernel<S><<<grid, GT_THREADS, smem, c->stream>>>(map_q, map_rows, a);      \
         break;
         switch (stages) { CS_GT(2) CS_GT(3) CS_GT(4) }
 #undef CS_GT
@@ -366,12 +402,39 @@ static int launch_select(const csgpu_index *ix, Shard *sh, BatchCtx *c, uint32_t
     const uint32_t *zi = final ? ix->zero_ids_dev : nullptr;
     const uint32_t nz = final ? (uint32_t)ix->zero_ids.size() : 0;
     cudaError_t e;
+    if (rescore_path(ix, sh)) {   // exact fp32 rescoring of the tensor-core filter's survivors (rescore.cuh)
+        RescoreArgs ra;
+        ra.rows = reinterpret_cast<const float4 *>(sh->rows); ra.ids = sh->ids; ra.dim4 = ix->dim4;
+        ra.q_raw = c->q_f32; ra.flags = c->flags; ra.cand = c->cand; ra.count = c->count; ra.n_done = c->count_saved;
+        ra.thr = c->thr; ra.cap = BF_CAP; ra.k = k; ra.kpad = kpad; ra.n_active = nq;
+        ra.zero_ids = zi; ra.n_zero = nz; ra.final_out = final ? c->out : nullptr;
+        ra.n_rescored = reinterpret_cast<unsigned long long *>(c->scalar + 2);
+        const uint32_t V = (ix->dim4 + 31) / 32;
+        const bool exact = ix->dim4 % 32 == 0;
+#define CS_RS(v, ex, bg)                                                                                                   \
+    do {                                                                                                                   \
+        e = cudaFuncSetAttribute(rescore_select_kernel<v, ex, bg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e == cudaSuccess) rescore_select_kernel<v, ex, bg><<<nq_pad, SCAN_THREADS, smem, c->stream>>>(ra);              \
+    } while (0)
+#define CS_RSV(v)                                                                            \
+    case v:                                                                                  \
+        if (exact) { if (big) CS_RS(v, true, true); else CS_RS(v, true, false); }            \
+        else       { if (big) CS_RS(v, false, true); else CS_RS(v, false, false); }          \
+        break;
+        switch (V) { CS_RSV(1) CS_RSV(2) CS_RSV(3) CS_RSV(4) default: return fail(CSGPU_ERR_ARG, "tensor prefilter: unsupported dim"); }
+#undef CS_RSV
+#undef CS_RS
+        count_launch();
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) return fail_cuda(e, "rescore_select_kernel launch", __FILE__, __LINE__);
+        return CSGPU_OK;
+    }
     if (big) {
         e = cudaFuncSetAttribute(select_candidates_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail_cuda(e, "select attr", __FILE__, __LINE__);
-        select_candidates_kernel<true><<<nq_pad, SCAN_THREADS, smem, c->stream>>>(c->cand, c->count, c->count_saved, c->thr, sh->ids, BF_CAP, k, kpad, nq, zi, nz, final ? c->out : nullptr);
+        select_candidates_kernel<true><<<nq_pad, SCAN_THREADS, smem, c->stream>>>(c->cand, c->count, c->count_saved, c->thr, sh->ids, c->flags, BF_CAP, k, kpad, nq, zi, nz, final ? c->out : nullptr);
     } else {
-        select_candidates_kernel<false><<<nq_pad, SCAN_THREADS, smem, c->stream>>>(c->cand, c->count, c->count_saved, c->thr, sh->ids, BF_CAP, k, kpad, nq, zi, nz, final ? c->out : nullptr);
+        select_candidates_kernel<false><<<nq_pad, SCAN_THREADS, smem, c->stream>>>(c->cand, c->count, c->count_saved, c->thr, sh->ids, c->flags, BF_CAP, k, kpad, nq, zi, nz, final ? c->out : nullptr);
     }
     count_launch();
     e = cudaGetLastError();
@@ -411,31 +474,32 @@ static int batch_search_shard(const csgpu_index *ix, Shard *sh, BatchCtx *c, con
                               const uint8_t **flags_out)
 {
     DeviceGuard g(sh->device);
-    const bool bf16 = ix->dtype == CSGPU_DTYPE_BF16;
+    const bool bf16 = tc_path(ix, sh);   // queries go to the tensor cores as bf16
     uint32_t n_qblocks = (nq + GT_BLOCK_M - 1) / GT_BLOCK_M;
     static const bool pad_even = getenv("CSGPU_BF16_2CTA") && atoi(getenv("CSGPU_BF16_2CTA")) != 0;
-    if (pad_even && bf16 && n_qblocks >= 2 && (n_qblocks & 1)) ++n_qblocks;   // CTA pairs take two query blocks each
+    if (pad_even && ix->dtype == CSGPU_DTYPE_BF16 && n_qblocks >= 2 && (n_qblocks & 1)) ++n_qblocks;   // CTA pairs take two query blocks each
     const uint32_t nq_pad = n_qblocks * GT_BLOCK_M;
+    CS_CUDA(cudaMemsetAsync(c->scalar, 0, 64, c->stream));
     memcpy(c->q_pin, q_host, (size_t)nq * ix->dim * sizeof(float));
     CS_CUDA(cudaMemcpyAsync(c->q_f32, c->q_pin, (size_t)nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     if (bf16)
         prep_queries_bf16_kernel<<<(nq_pad * 32 + 255) / 256, 256, 0, c->stream>>>(c->q_f32, nq, ix->dim, reinterpret_cast<__nv_bfloat16 *>(c->q_prep), nq_pad, c->flags);
     else
         prep_queries_f32_kernel<<<(nq_pad * 32 + 255) / 256, 256, 0, c->stream>>>(c->q_f32, nq, ix->dim, ix->dim_pad, reinterpret_cast<float *>(c->q_prep), nq_pad, c->flags);
-    init_thresholds_kernel<<<(nq_pad + 255) / 256, 256, 0, c->stream>>>(c->thr, c->count, nq, nq_pad);
+    init_thresholds_kernel<<<(nq_pad + 255) / 256, 256, 0, c->stream>>>(c->thr, c->count, c->flags, nq, nq_pad);
     count_launch(2);
     uint8_t *flags_host = reinterpret_cast<uint8_t *>(c->out_pin) + (size_t)BF_MAX_QBLOCKS * GT_BLOCK_M * CSGPU_MAX_K * sizeof(uint64_t);
     CS_CUDA(cudaMemcpyAsync(flags_host, c->flags, nq, cudaMemcpyDeviceToHost, c->stream));
     CS_CUDA(cudaStreamSynchronize(c->stream));
     *flags_out = flags_host;
-    if (bf16)
+    if (ix->dtype == CSGPU_DTYPE_BF16)
         for (uint32_t j = 0; j < nq; ++j)
             if (flags_host[j]) return fail(CSGPU_ERR_ARG, "zero-norm query is not supported on a bf16 index");
     CUtensorMap map_q;
     int rc = make_map(&map_q, c->q_prep, nq_pad, bf16 ? ix->dim : ix->dim_pad, GT_BLOCK_M, !bf16);
     if (rc) return rc;
 
-    const uint32_t tile_rows = tile_rows_of(ix);
+    const uint32_t tile_rows = tile_rows_of(ix, sh);
     const uint64_t n_tiles = (sh->n_built + tile_rows - 1) / tile_rows;
     // phase 0 lets everything through, so it must fit the buffer on its own: <= CAP/2 rows
     uint64_t done = 0;
@@ -449,7 +513,14 @@ static int batch_search_shard(const csgpu_index *ix, Shard *sh, BatchCtx *c, con
         next = done * (growth - 1);   // each phase scans (growth-1) x everything seen so far
     }
     CS_CUDA(cudaMemcpyAsync(c->count_saved, c->count, nq_pad * sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
-    return launch_select(ix, sh, c, nq_pad, nq, k, true);
+    rc = launch_select(ix, sh, c, nq_pad, nq, k, true);
+    if (!rc && rescore_path(ix, sh)) {
+        unsigned long long nres = 0;
+        CS_CUDA(cudaMemcpyAsync(&nres, c->scalar + 2, sizeof nres, cudaMemcpyDeviceToHost, c->stream));
+        CS_CUDA(cudaStreamSynchronize(c->stream));
+        ix->prefilter_rescored.store(nres);
+    }
+    return rc;
 }
 
 bool batch_gemm_available(const csgpu_index *ix)

@@ -499,6 +499,7 @@ static __global__ void prep_queries_bf16_kernel(const float *__restrict__ q, uin
     if (w >= b_pad) return;
     if (w >= b) {
         for (uint32_t c = lane; c < dim; c += 32) out[(size_t)w * dim + c] = __float2bfloat16(0.f);
+        if (lane == 0) flags[w] = 0;
         return;
     }
     double ss = 0.0;

@@ -116,6 +116,10 @@ struct Shard {
     CUtensorMap map_c;             // TMA map over the built rows (bf16 or fp32), re-encoded at every build
     CUtensorMap map_c2;            // bf16 only: same matrix, box = 128 rows (one CTA's half tile in the CTA-pair kernel)
     bool map_valid = false;
+    void *shadow_bf16 = nullptr;   // fp32 index + tensor prefilter: bf16 image of the built rows (rescore.cuh)
+    CUtensorMap map_shadow;        // TMA map over the shadow (box = GT_BLOCK_N rows)
+    bool shadow_valid = false;
+    uint64_t shadow_rows = 0;
     BatchCtx *batch = nullptr;
     std::mutex batch_mu;
     float *rows = nullptr;     // [cap, dim_pad] fp32; rows [0, n_built) are unit vectors
@@ -139,6 +143,7 @@ int bf16_reserve_stage(const csgpu_index *ix, Shard *sh, uint64_t pending);
 int bf16_convert_pending(const csgpu_index *ix, Shard *sh);
 bool batch_f32_dim_supported(uint32_t dim_pad);
 int batch_after_build(const csgpu_index *ix, Shard *sh);
+int shadow_refresh(const csgpu_index *ix, Shard *sh);
 void batch_free_ctx(Shard *sh);
 bool batch_gemm_available(const csgpu_index *ix);
 int batch_search(const csgpu_index *ix, const float *q, uint32_t b, uint32_t k,
@@ -165,6 +170,7 @@ struct csgpu_index {
     uint32_t dim = 0, dim_pad = 0, dim4 = 0;
     uint32_t dtype = 0;
     bool built = false;
+    bool tensor_prefilter = false;        // csgpu_set_tensor_prefilter: batches run tcgen05 on a bf16 shadow + exact fp32 rescoring
     std::vector<csgpu::Shard *> shards;
     std::vector<uint32_t> zero_ids;       // ascending; rows with |v| = 0 (host truth)
     std::vector<uint32_t> zero_tags;      // parallel to zero_ids
@@ -172,6 +178,7 @@ struct csgpu_index {
     uint64_t nonfinite_rows = 0;
     uint64_t tombstones = 0;
     mutable std::atomic<float> last_search_us{0.f};
+    mutable std::atomic<uint64_t> prefilter_rescored{0};   // fp32 rows read by the last tensor-prefilter batch chunk
     csgpu::Exchange *xchg = nullptr;      // rank-per-GPU fused exchange (csgpu_exchange_*)
     mutable csgpu::Coalescer coalescer;   // csgpu_set_coalescing
 };

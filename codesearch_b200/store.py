@@ -346,6 +346,11 @@ class VectorStore:
     def search_variants(self, queries, limit: int) -> list[SearchResult]:
         return self._join(*self.search_variants_ids(queries, limit))
 
+    def set_tensor_prefilter(self, enabled: bool) -> None:
+        """Opt-in (fp32 index): batches run on the tensor cores against a bf16 shadow as a filter, survivors are rescored
+        in fp32 with the single-query kernel's arithmetic — results bit-identical to search() (csrc/rescore.cuh)."""
+        _lib.check(self._lib.csgpu_set_tensor_prefilter(self._h, 1 if enabled else 0))
+
     def set_coalescing(self, enabled: bool, window_us: int = 0) -> None:
         """Host micro-batcher: concurrent search() calls with the same limit share one pass over the corpus."""
         _lib.check(self._lib.csgpu_set_coalescing(self._h, 1 if enabled else 0, int(window_us)))

@@ -76,6 +76,8 @@ typedef struct csgpu_stats_t {
     uint64_t rows_per_device[8];
     uint64_t coalesced_passes;   /* micro-batcher: corpus passes launched ...                       */
     uint64_t coalesced_queries;  /* ... for this many csgpu_search calls (csgpu_set_coalescing)     */
+    uint64_t prefilter_rescored; /* tensor prefilter: fp32 rows rescored by the last batch (<= 1024 queries) */
+    uint64_t shadow_bytes;       /* HBM held by the bf16 shadow (csgpu_set_tensor_prefilter), all devices   */
 } csgpu_stats_t;
 
 /* ---- lifecycle (VectorStore::new / open_readonly  store.rs:110-176,183-250) ------------ */
@@ -129,6 +131,14 @@ int  csgpu_set_coalescing(csgpu_index *ix, uint32_t enabled, uint32_t window_us)
  * <= 9 query variants of src/search/mod.rs:508-511 in one pass over the corpus. */
 int  csgpu_search_batch(const csgpu_index *ix, const float *q, uint32_t q_len, uint32_t b, uint32_t k,
                         uint32_t *out_ids, float *out_dist, uint32_t *out_n /*[b]*/);
+
+/* Opt-in, fp32 index only: exact fp32 results at tensor-core speed for batches. The index keeps a bf16 SHADOW of its
+ * unit rows (+50 % HBM; dim % 64 == 0, dim <= 512). csgpu_search_batch then contracts the batch on the tensor cores
+ * (tcgen05 / TMEM) against the shadow as a FILTER with a proven error margin, and rescores the survivors from the fp32
+ * rows with the single-query kernel's arithmetic: ids AND distances are bit-identical to csgpu_search on every query
+ * (codesearch_b200/csrc/rescore.cuh has the bound). Off by default: the register-tiled fp32 SIMT kernel stays the
+ * default batched path. May be called before or after csgpu_build; the shadow follows every later build / load. */
+int  csgpu_set_tensor_prefilter(csgpu_index *ix, uint32_t enabled);
 
 /* b (<= 16) query VARIANTS of one user query (query expansion, src/search/mod.rs:479-483), searched with the same
  * limit and merged on the device: per chunk id the best (smallest) distance over the variants, then the best k of

@@ -30,7 +30,7 @@ def test_header_symbols_all_exported_and_bound():
 def test_stats_struct_layout_matches_header():
     from codesearch_b200 import _lib
     # 6 u64 + 4 u32 + f32 + u32 + 8 u64
-    assert ctypes.sizeof(_lib.Stats) == 6 * 8 + 4 * 4 + 4 + 4 + 8 * 8 + 2 * 8   # ... + coalesced_passes, coalesced_queries
+    assert ctypes.sizeof(_lib.Stats) == 6 * 8 + 4 * 4 + 4 + 4 + 8 * 8 + 4 * 8   # ... + coalesced_passes, coalesced_queries, prefilter_rescored, shadow_bytes
 
 
 def test_decode_keys_is_pure_host():
