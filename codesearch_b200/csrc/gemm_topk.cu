@@ -32,72 +32,33 @@ static bool rescore_path(const csgpu_index *ix, const Shard *sh) { return ix->dt
 // ---------------------------------------------------------------------------------------------
 // kernels local to this file
 // ---------------------------------------------------------------------------------------------
-// One CTA per query: candidate buffer -> exact top-k (ascending (distance, id)) written back to the
-// front of the buffer, new threshold published. Entries [0, n_done[q]) are survivors of earlier
-// selects and already carry chunk ids; entries beyond carry ROW indices (the GEMM epilogues do no
-// dependent loads) and get ids[row] swapped in here, lanes in parallel.
-template <bool BIG>
-__global__ void __launch_bounds__(SCAN_THREADS, 1)
-select_candidates_kernel(uint64_t *__restrict__ cand, unsigned *__restrict__ count, const unsigned *__restrict__ n_done,
-                         float *__restrict__ thr, const uint32_t *__restrict__ ids, const uint8_t *__restrict__ flags,
-                         uint32_t cap, uint32_t k, uint32_t kpad, uint32_t n_active,
-                         const uint32_t *__restrict__ zero_ids, uint32_t n_zero, uint64_t *__restrict__ final_out)
-{
-    extern __shared__ __align__(16) uint64_t smem[];
-    const uint32_t q = blockIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (q >= n_active || flags[q]) {   // padding rows and zero-norm queries (answered by the scan kernel) stay inactive
-        if (threadIdx.x == 0) { count[q] = 0; thr[q] = -1.f; }
-        return;
-    }
-    using Sel = typename SelOf<BIG>::type;
-    Sel sel;
-    if constexpr (BIG) sel.init(smem + (size_t)warp * kpad, smem + (size_t)(SCAN_WARPS + warp) * kpad, k, kpad, lane);
-    else sel.init(k);
-    uint64_t *mine = cand + (size_t)q * cap;
-    const uint32_t n = min(count[q], cap);
-    const uint32_t done = min(n_done[q], n);
-    for (uint32_t b = warp * 32; b < n; b += SCAN_WARPS * 32) {
-        uint64_t key = KEY_EMPTY;
-        if (b + lane < n) {
-            key = mine[b + lane];
-            if (b + lane >= done) key = (key & 0xFFFFFFFF00000000ull) | ids[(uint32_t)key];
-        }
-        offer_lane_keys(sel, key, lane);
-    }
-    if (final_out != nullptr && warp == 0 && n_zero) {   // zero-norm rows: distance 0.0 (arroy pn*qn == 0)
-        uint32_t found = 0;
-        for (uint32_t b = 0; b < n_zero && found < k; b += 32) {
-            const uint64_t key = (b + lane < n_zero) ? make_key(0.f, zero_ids[b + lane]) : KEY_EMPTY;
-            found += __popc(__ballot_sync(FULL, key != KEY_EMPTY));
-            offer_lane_keys(sel, key, lane);
-        }
-    }
-    __syncthreads();   // every warp has finished reading cand[q] before it is overwritten
-    cta_reduce<BIG>(sel, smem, k, kpad, mine, warp, lane);
-    if (final_out != nullptr)
-        for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) final_out[(size_t)q * k + j] = mine[j];
-    if (threadIdx.x == 0) {
-        uint32_t m = 0;
-        while (m < k && mine[m] != KEY_EMPTY) ++m;
-        count[q] = m;
-        float t = __int_as_float(0x7f800000);  // +inf: everything passes until k candidates exist
-        if (m >= k) t = __uint_as_float(bits_from_okey((uint32_t)(mine[k - 1] >> 32)));
-        thr[q] = t;
-    }
-}
-
 __global__ void init_thresholds_kernel(float *thr, unsigned *count, const uint8_t *flags, uint32_t n_active, uint32_t n_total)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_total) { thr[i] = (i < n_active && !flags[i]) ? __int_as_float(0x7f800000) : -1.f; count[i] = 0; }
 }
 
-__global__ void max_count_kernel(const unsigned *count, uint32_t n, unsigned *out)
+// One thread per query: would this range's candidates overflow a segment, the SIMT buffer or the select kernel's
+// sort buffer? Sets *overflow (sticky). The single source of truth for the host's split-and-retry.
+__global__ void check_counts_kernel(const unsigned *__restrict__ count, const unsigned *__restrict__ count_saved,
+                                    const unsigned *__restrict__ seg_count, uint32_t n_seg, uint32_t seg_len, uint32_t cap,
+                                    uint32_t nq, unsigned *__restrict__ overflow)
 {
-    unsigned m = 0;
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) m = max(m, count[i]);
-    atomicMax(out, m);
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    bool over = false;
+    if (n_seg) {
+        unsigned total = 0;
+        for (uint32_t s = 0; s < n_seg; ++s) {
+            const unsigned c = seg_count[(size_t)q * n_seg + s];
+            over |= c > seg_len;
+            total += c;
+        }
+        over |= total > SEL_SORT_CAP;
+    } else {
+        over = count[q] > cap || count[q] - min(count[q], count_saved[q]) > SEL_SORT_CAP;
+    }
+    if (over) atomicExch(overflow, 1u);
 }
 
 // pending fp32 rows (stage) -> unit length (f64 norm) -> bf16 rows at [dst_first + i]; flags zero / non-finite
@@ -285,7 +246,7 @@ void batch_free_ctx(Shard *sh)
     BatchCtx *c = sh->batch;
     if (c->stream) cudaStreamDestroy(c->stream);
     cudaFree(c->q_f32); cudaFree(c->q_prep); cudaFree(c->flags); cudaFree(c->thr); cudaFree(c->count); cudaFree(c->count_saved);
-    cudaFree(c->cand); cudaFree(c->out); cudaFree(c->scalar);
+    cudaFree(c->cand); cudaFree(c->out); cudaFree(c->scalar); cudaFree(c->seg_count);
     cudaFreeHost(c->q_pin); cudaFreeHost(c->out_pin);
     delete c;
     sh->batch = nullptr;
@@ -308,6 +269,7 @@ static int batch_ctx(const csgpu_index *ix, Shard *sh, BatchCtx **out)
     CS_CUDA(cudaMalloc(&c->cand, nq * BF_CAP * sizeof(uint64_t)));
     CS_CUDA(cudaMalloc(&c->out, nq * CSGPU_MAX_K * sizeof(uint64_t)));
     CS_CUDA(cudaMalloc(&c->scalar, 64));
+    CS_CUDA(cudaMalloc(&c->seg_count, nq * 2 * 148 * sizeof(unsigned)));
     CS_CUDA(cudaHostAlloc(&c->q_pin, nq * ix->dim * sizeof(float), cudaHostAllocDefault));
     CS_CUDA(cudaHostAlloc(&c->out_pin, nq * CSGPU_MAX_K * sizeof(uint64_t) + nq, cudaHostAllocDefault));
     *out = c;
@@ -318,6 +280,29 @@ static int batch_ctx(const csgpu_index *ix, Shard *sh, BatchCtx **out)
 // search
 // ---------------------------------------------------------------------------------------------
 static uint32_t tile_rows_of(const csgpu_index *ix, const Shard *sh) { return tc_path(ix, sh) ? GT_BLOCK_N : GS_BN; }
+
+// epilogue shape of the tensor-core kernel: threads per query. CSGPU_TC_EPI=1 selects the 4-warp epilogue for experiments.
+static uint32_t tc_epi_halves()
+{
+    static const uint32_t h = (getenv("CSGPU_TC_EPI") && getenv("CSGPU_TC_EPI")[0] == '1') ? 1u : 2u;
+    return h;
+}
+
+// Candidate layout of one launch (tensor-core kernel: segments; SIMT kernel: one global-atomic buffer per query).
+struct CandLayout {
+    uint32_t stride, seg_len, n_seg, groups;
+};
+static CandLayout cand_layout(const csgpu_index *ix, const Shard *sh, uint32_t n_qblocks, uint64_t n_tiles)
+{
+    CandLayout l;
+    if (!tc_path(ix, sh)) { l.stride = BF_CAP; l.seg_len = 0; l.n_seg = 0; l.groups = 0; return l; }
+    const uint32_t nq_pad = n_qblocks * GT_BLOCK_M;
+    l.stride = (uint32_t)((uint64_t)BF_MAX_QBLOCKS * GT_BLOCK_M * BF_CAP / nq_pad);   // fewer queries -> longer blocks
+    l.groups = (uint32_t)std::min<uint64_t>(std::max<uint32_t>(std::min<uint32_t>(sh->sm_count, 148) / n_qblocks, 1), n_tiles);
+    l.n_seg = tc_epi_halves() * l.groups;
+    l.seg_len = std::min<uint32_t>((l.stride - GT_SURV) / l.n_seg, 4096);
+    return l;
+}
 
 static int launch_gemm(const csgpu_index *ix, Shard *sh, BatchCtx *c, const CUtensorMap &map_q, uint32_t n_qblocks,
                        uint64_t t0, uint64_t t1)
@@ -336,6 +321,10 @@ static int launch_gemm(const csgpu_index *ix, Shard *sh, BatchCtx *c, const CUte
     static const int env_pf = getenv("CSGPU_BF16_PREFETCH") ? atoi(getenv("CSGPU_BF16_PREFETCH")) : 0;
     a.prefetch_tiles = env_pf > 0 ? (uint32_t)env_pf : 0u;
     const uint64_t n_tiles = t1 - t0;
+    const CandLayout lay = cand_layout(ix, sh, n_qblocks, n_tiles);
+    a.stride = lay.stride; a.seg_len = lay.seg_len; a.n_seg = lay.n_seg;
+    a.seg_count = c->seg_count;
+    a.overflow = c->scalar;
     cudaError_t e = cudaSuccess;
     if (tc_path(ix, sh)) {
         const CUtensorMap &map_rows = ix->dtype == CSGPU_DTYPE_BF16 ? sh->map_c : sh->map_shadow;
@@ -344,42 +333,21 @@ static int launch_gemm(const csgpu_index *ix, Shard *sh, BatchCtx *c, const CUte
         const size_t avail = 227 * 1024 - 1024 /*alignment slack*/ - 256 /*static*/ - q_bytes;
         const int stages = (int)std::min<size_t>(4, avail / GT_STAGE_BYTES);
         if (stages < 2) return fail(CSGPU_ERR_ARG, "dim too large for the bf16 kernel's shared-memory plan");
-        // CTA-pair kernel (cta_group::2, M = 256): correct (same tests) but measured 4-7 % SLOWER than the one-CTA kernel
-        // (profiles/r01_bf16_2cta.txt: 9.06 vs 8.44 ms at B=1024,k=100) — under the 1 kW cap the MMA rate, not the
-        // operand stream, is what binds — so it is opt-in: CSGPU_BF16_2CTA=1
-        static const int env_2cta = getenv("CSGPU_BF16_2CTA") ? atoi(getenv("CSGPU_BF16_2CTA")) : 0;
-        if (env_2cta && ix->dtype == CSGPU_DTYPE_BF16 && n_qblocks >= 2 && n_qblocks % 2 == 0) {
-            const size_t avail2 = 227 * 1024 - 1024 - 512 - q_bytes;
-            const int st2 = (int)std::min<size_t>(8, avail2 / GT2_STAGE_BYTES);
-            if (st2 >= 4) {
-                const size_t smem2 = q_bytes + (size_t)st2 * GT2_STAGE_BYTES + 1024;
-                const uint32_t n_qpairs = n_qblocks / 2;
-                const uint32_t pairs = std::max<uint32_t>((uint32_t)sh->sm_count / 2, 1);
-                const uint32_t groups2 = (uint32_t)std::min<uint64_t>(std::max<uint32_t>(pairs / n_qpairs, 1), n_tiles);
-                const uint32_t grid2 = groups2 * n_qpairs * 2;
-#define CS_GT2(S)                                                                                                    \
-    case S:                                                                                                          \
-        e = cudaFuncSetAttribute(gemm_topk2_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);     \
-        if (e == cudaSuccess) gemm_topk2_kernel<S><<<grid2, GT_THREADS, smem2, c->stream>>>(map_q, sh->map_c2, a);   \
-        break;
-                switch (st2) { CS_GT2(4) CS_GT2(5) CS_GT2(6) CS_GT2(7) CS_GT2(8) }
-#undef CS_GT2
-                count_launch();
-                if (e == cudaSuccess) e = cudaGetLastError();
-                if (e != cudaSuccess) return fail_cuda(e, "gemm_topk2_kernel launch", __FILE__, __LINE__);
-                return CSGPU_OK;
-            }
-        }
         const size_t smem = q_bytes + (size_t)stages * GT_STAGE_BYTES + 1024;
-        const uint32_t groups = (uint32_t)std::min<uint64_t>(std::max<uint32_t>(sh->sm_count / n_qblocks, 1), n_tiles);
-        const uint32_t grid = groups * n_qblocks;
-#define CS_GT(S)                                                                                                   \
-    case S:                                                                                                        \
-        e = cudaFuncSetAttribute(gemm_topk_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
-        if (e == cudaSuccess) gemm_topk_kernel<S><<<grid, GT_THREADS, smem, c->stream>>>(map_q, map_rows, a);      \
-        break;
+        // cta_group::2 CTA pairs (M = 256) were built and measured 4-7 % slower than this one-CTA kernel
+        // (profiles/r01_bf16_2cta.txt; the variant lives in git history, commit a9ec50f)
+        const uint32_t grid = lay.groups * n_qblocks;
+        const uint32_t halves = tc_epi_halves();
+        const uint32_t threads = 64 + 128 * halves;
+#define CS_GTK(S, H)                                                                                                  \
+    do {                                                                                                              \
+        e = cudaFuncSetAttribute(gemm_topk_kernel<S, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+        if (e == cudaSuccess) gemm_topk_kernel<S, H><<<grid, threads, smem, c->stream>>>(map_q, map_rows, a);         \
+    } while (0)
+#define CS_GT(S) case S: if (halves == 2) CS_GTK(S, 2); else CS_GTK(S, 1); break;
         switch (stages) { CS_GT(2) CS_GT(3) CS_GT(4) }
 #undef CS_GT
+#undef CS_GTK
     } else {
         a.n_kchunks = (ix->dim_pad + GS_BK - 1) / GS_BK;
         constexpr int STAGES = 6;
@@ -394,78 +362,75 @@ static int launch_gemm(const csgpu_index *ix, Shard *sh, BatchCtx *c, const CUte
     return CSGPU_OK;
 }
 
-static int launch_select(const csgpu_index *ix, Shard *sh, BatchCtx *c, uint32_t nq_pad, uint32_t nq, uint32_t k, bool final)
+static int launch_select(const csgpu_index *ix, Shard *sh, BatchCtx *c, uint32_t nq_pad, uint32_t nq, uint32_t k, bool final,
+                         const CandLayout &lay)
 {
-    const bool big = k > 32;
-    const uint32_t kpad = big ? pow2_at_least(k, 64) : 32;
-    const size_t smem = big ? (size_t)2 * SCAN_WARPS * kpad * sizeof(uint64_t) : (size_t)SCAN_WARPS * 32 * sizeof(uint64_t);
-    const uint32_t *zi = final ? ix->zero_ids_dev : nullptr;
-    const uint32_t nz = final ? (uint32_t)ix->zero_ids.size() : 0;
-    cudaError_t e;
+    SelectArgs sa;
+    sa.cand = c->cand; sa.count = c->count; sa.n_done = c->count_saved;
+    sa.seg_count = lay.n_seg ? c->seg_count : nullptr;
+    sa.stride = lay.stride; sa.surv = GT_SURV; sa.seg_len = lay.seg_len; sa.n_seg = lay.n_seg;
+    sa.overflow = c->scalar; sa.thr = c->thr; sa.ids = sh->ids; sa.flags = c->flags; sa.k = k; sa.n_active = nq;
+    sa.zero_ids = final ? ix->zero_ids_dev : nullptr;
+    sa.n_zero = final ? (uint32_t)ix->zero_ids.size() : 0;
+    sa.final_out = final ? c->out : nullptr;
+    sa.rows = reinterpret_cast<const float4 *>(sh->rows); sa.dim4 = ix->dim4; sa.q_raw = c->q_f32;
+    sa.n_rescored = reinterpret_cast<unsigned long long *>(c->scalar + 2);
+    cudaError_t e = cudaSuccess;
     if (rescore_path(ix, sh)) {   // exact fp32 rescoring of the tensor-core filter's survivors (rescore.cuh)
-        RescoreArgs ra;
-        ra.rows = reinterpret_cast<const float4 *>(sh->rows); ra.ids = sh->ids; ra.dim4 = ix->dim4;
-        ra.q_raw = c->q_f32; ra.flags = c->flags; ra.cand = c->cand; ra.count = c->count; ra.n_done = c->count_saved;
-        ra.thr = c->thr; ra.cap = BF_CAP; ra.k = k; ra.kpad = kpad; ra.n_active = nq;
-        ra.zero_ids = zi; ra.n_zero = nz; ra.final_out = final ? c->out : nullptr;
-        ra.n_rescored = reinterpret_cast<unsigned long long *>(c->scalar + 2);
+        const size_t smem = (size_t)(SEL_BUF + 1024 + 4096) * sizeof(uint64_t);
         const uint32_t V = (ix->dim4 + 31) / 32;
         const bool exact = ix->dim4 % 32 == 0;
-#define CS_RS(v, ex, bg)                                                                                                   \
-    do {                                                                                                                   \
-        e = cudaFuncSetAttribute(rescore_select_kernel<v, ex, bg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e == cudaSuccess) rescore_select_kernel<v, ex, bg><<<nq_pad, SCAN_THREADS, smem, c->stream>>>(ra);              \
+#define CS_RS(v, ex)                                                                                                         \
+    do {                                                                                                                     \
+        e = cudaFuncSetAttribute(select_sorted_kernel<v, ex, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+        if (e == cudaSuccess) select_sorted_kernel<v, ex, true><<<nq_pad, SCAN_THREADS, smem, c->stream>>>(sa);               \
     } while (0)
-#define CS_RSV(v)                                                                            \
-    case v:                                                                                  \
-        if (exact) { if (big) CS_RS(v, true, true); else CS_RS(v, true, false); }            \
-        else       { if (big) CS_RS(v, false, true); else CS_RS(v, false, false); }          \
-        break;
+#define CS_RSV(v) case v: if (exact) CS_RS(v, true); else CS_RS(v, false); break;
         switch (V) { CS_RSV(1) CS_RSV(2) CS_RSV(3) CS_RSV(4) default: return fail(CSGPU_ERR_ARG, "tensor prefilter: unsupported dim"); }
 #undef CS_RSV
 #undef CS_RS
-        count_launch();
-        if (e == cudaSuccess) e = cudaGetLastError();
-        if (e != cudaSuccess) return fail_cuda(e, "rescore_select_kernel launch", __FILE__, __LINE__);
-        return CSGPU_OK;
-    }
-    if (big) {
-        e = cudaFuncSetAttribute(select_candidates_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail_cuda(e, "select attr", __FILE__, __LINE__);
-        select_candidates_kernel<true><<<nq_pad, SCAN_THREADS, smem, c->stream>>>(c->cand, c->count, c->count_saved, c->thr, sh->ids, c->flags, BF_CAP, k, kpad, nq, zi, nz, final ? c->out : nullptr);
     } else {
-        select_candidates_kernel<false><<<nq_pad, SCAN_THREADS, smem, c->stream>>>(c->cand, c->count, c->count_saved, c->thr, sh->ids, c->flags, BF_CAP, k, kpad, nq, zi, nz, final ? c->out : nullptr);
+        const size_t smem = (size_t)SEL_BUF * sizeof(uint64_t);
+        e = cudaFuncSetAttribute(select_sorted_kernel<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) select_sorted_kernel<1, true, false><<<nq_pad, SCAN_THREADS, smem, c->stream>>>(sa);
     }
     count_launch();
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return fail_cuda(e, "select_candidates_kernel launch", __FILE__, __LINE__);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(e, "select_sorted_kernel launch", __FILE__, __LINE__);
     return CSGPU_OK;
 }
 
-// scan tiles [t0, t1) with the current thresholds; on candidate-buffer overflow roll back and split.
+// scan tiles [t0, t1) with the current thresholds, then reduce every query to its exact top-k so far.
+// careful = false (the normal run): nothing is synchronised; an overflow only raises the sticky flag c->scalar[0],
+// which the caller reads once with the results and, if set, repeats the batch carefully.
+// careful = true: the flag is read after the contraction; on overflow the range is rolled back and split.
 // count_saved = entries per query before this range = the survivors of the previous select (they carry ids).
 static int run_range(const csgpu_index *ix, Shard *sh, BatchCtx *c, const CUtensorMap &map_q, uint32_t n_qblocks,
-                     uint32_t nq, uint32_t k, uint64_t t0, uint64_t t1, int depth)
+                     uint32_t nq, uint32_t k, uint64_t t0, uint64_t t1, uint64_t t_last, bool careful, int depth)
 {
     const uint32_t nq_pad = n_qblocks * GT_BLOCK_M;
+    const CandLayout lay = cand_layout(ix, sh, n_qblocks, t1 - t0);
     CS_CUDA(cudaMemcpyAsync(c->count_saved, c->count, nq_pad * sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
-    CS_CUDA(cudaMemsetAsync(c->scalar, 0, sizeof(unsigned), c->stream));
+    if (careful) CS_CUDA(cudaMemsetAsync(c->scalar, 0, sizeof(unsigned), c->stream));
     int rc = launch_gemm(ix, sh, c, map_q, n_qblocks, t0, t1);
     if (rc) return rc;
-    max_count_kernel<<<1, 256, 0, c->stream>>>(c->count, nq_pad, c->scalar);
+    check_counts_kernel<<<(nq_pad + 255) / 256, 256, 0, c->stream>>>(c->count, c->count_saved, lay.n_seg ? c->seg_count : nullptr,
+                                                                     lay.n_seg, lay.seg_len, BF_CAP, nq_pad, c->scalar);
     count_launch();
-    unsigned maxc = 0;
-    CS_CUDA(cudaMemcpyAsync(&maxc, c->scalar, sizeof maxc, cudaMemcpyDeviceToHost, c->stream));
-    CS_CUDA(cudaStreamSynchronize(c->stream));
-    if (maxc > BF_CAP) {
-        if (t1 - t0 <= 1 || depth > 40) return fail(CSGPU_ERR_CUDA, "candidate buffer overflow on a single tile (internal error)");
-        CS_CUDA(cudaMemcpyAsync(c->count, c->count_saved, nq_pad * sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
-        const uint64_t mid = t0 + (t1 - t0) / 2;
-        rc = run_range(ix, sh, c, map_q, n_qblocks, nq, k, t0, mid, depth + 1);
-        if (rc) return rc;
-        return run_range(ix, sh, c, map_q, n_qblocks, nq, k, mid, t1, depth + 1);
+    if (careful) {
+        unsigned over = 0;
+        CS_CUDA(cudaMemcpyAsync(&over, c->scalar, sizeof over, cudaMemcpyDeviceToHost, c->stream));
+        CS_CUDA(cudaStreamSynchronize(c->stream));
+        if (over) {
+            if (t1 - t0 <= 1 || depth > 40) return fail(CSGPU_ERR_CUDA, "candidate buffer overflow on a single tile (internal error)");
+            CS_CUDA(cudaMemcpyAsync(c->count, c->count_saved, nq_pad * sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
+            const uint64_t mid = t0 + (t1 - t0) / 2;
+            rc = run_range(ix, sh, c, map_q, n_qblocks, nq, k, t0, mid, t_last, true, depth + 1);
+            if (rc) return rc;
+            return run_range(ix, sh, c, map_q, n_qblocks, nq, k, mid, t1, t_last, true, depth + 1);
+        }
     }
-    return launch_select(ix, sh, c, nq_pad, nq, k, false);
+    return launch_select(ix, sh, c, nq_pad, nq, k, /*final=*/t1 == t_last, lay);   // the last range's select also writes the output
 }
 
 // Up to 1024 queries against one shard; final keys land in c->out [nq][k] (device); zero-norm query flags
@@ -501,26 +466,48 @@ static int batch_search_shard(const csgpu_index *ix, Shard *sh, BatchCtx *c, con
 
     const uint32_t tile_rows = tile_rows_of(ix, sh);
     const uint64_t n_tiles = (sh->n_built + tile_rows - 1) / tile_rows;
-    // phase 0 lets everything through, so it must fit the buffer on its own: <= CAP/2 rows
-    uint64_t done = 0;
-    uint64_t next = std::max<uint64_t>(1, (BF_CAP / 2) / tile_rows);
-    while (done < n_tiles) {
-        const uint64_t t1 = std::min(n_tiles, done + next);
-        rc = run_range(ix, sh, c, map_q, n_qblocks, nq, k, done, t1, 0);
-        if (rc) return rc;
-        done = t1;
-        static const uint64_t growth = getenv("CSGPU_BATCH_GROWTH") ? std::max(2, atoi(getenv("CSGPU_BATCH_GROWTH"))) : BF_PHASE_GROWTH;
-        next = done * (growth - 1);   // each phase scans (growth-1) x everything seen so far
-    }
-    CS_CUDA(cudaMemcpyAsync(c->count_saved, c->count, nq_pad * sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
-    rc = launch_select(ix, sh, c, nq_pad, nq, k, true);
-    if (!rc && rescore_path(ix, sh)) {
-        unsigned long long nres = 0;
-        CS_CUDA(cudaMemcpyAsync(&nres, c->scalar + 2, sizeof nres, cudaMemcpyDeviceToHost, c->stream));
+    // Each phase scans (growth-1) x everything seen so far, so ~ (growth-1) * k rows per query pass (x ~1.4 through the
+    // prefilter's margin); that has to stay well inside the select kernel's sort buffer.
+    static const int env_growth = getenv("CSGPU_BATCH_GROWTH") ? std::max(2, atoi(getenv("CSGPU_BATCH_GROWTH"))) : 0;
+    const double per_k = rescore_path(ix, sh) ? 2.8 : 1.5;
+    const uint64_t growth = env_growth ? (uint64_t)env_growth
+                                       : 1 + std::min<uint64_t>(BF_PHASE_GROWTH - 1, std::max<uint64_t>(1, (uint64_t)(SEL_SORT_CAP / (per_k * k))));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const bool careful = attempt == 1;
+        if (careful) {   // an overflow spoiled the optimistic run: start over, checking every range
+            init_thresholds_kernel<<<(nq_pad + 255) / 256, 256, 0, c->stream>>>(c->thr, c->count, c->flags, nq, nq_pad);
+            count_launch();
+        }
+        // phase 0 lets everything through, so it must fit a segment (128 rows per tile and column half) and the
+        // sort buffer on its own: <= CAP/2 rows
+        uint64_t done = 0;
+        uint64_t next = std::max<uint64_t>(1, (BF_CAP / 2) / tile_rows);
+        while (done < n_tiles) {
+            const uint64_t t1 = std::min(n_tiles, done + next);
+            rc = run_range(ix, sh, c, map_q, n_qblocks, nq, k, done, t1, n_tiles, careful, 0);
+            if (rc) return rc;
+            done = t1;
+            next = done * (growth - 1);
+        }
+        if (n_tiles == 0) {   // no rows in the matrix: the select still injects the zero-norm ids and writes the output
+            CS_CUDA(cudaMemcpyAsync(c->count_saved, c->count, nq_pad * sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
+            CandLayout fin = cand_layout(ix, sh, n_qblocks, 1);
+            fin.n_seg = 0;
+            rc = launch_select(ix, sh, c, nq_pad, nq, k, true, fin);
+            if (rc) return rc;
+        }
+        unsigned over = 0;
+        CS_CUDA(cudaMemcpyAsync(&over, c->scalar, sizeof over, cudaMemcpyDeviceToHost, c->stream));
         CS_CUDA(cudaStreamSynchronize(c->stream));
+        if (!over) break;
+        if (careful) return fail(CSGPU_ERR_CUDA, "candidate overflow in the careful pass (internal error)");
+    }
+    if (rescore_path(ix, sh)) {
+        unsigned long long nres = 0;
+        CS_CUDA(cudaMemcpy(&nres, c->scalar + 2, sizeof nres, cudaMemcpyDeviceToHost));
         ix->prefilter_rescored.store(nres);
     }
-    return rc;
+    return CSGPU_OK;
 }
 
 bool batch_gemm_available(const csgpu_index *ix)

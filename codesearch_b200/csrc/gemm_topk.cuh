@@ -11,19 +11,22 @@
 //         both in the canonical K-major SWIZZLE_128B layout that TMA writes and UMMA reads.
 //   TMEM: 2 accumulator buffers x 256 fp32 columns = all 512 columns (epilogue of tile i overlaps
 //         the MMAs of tile i+1).
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer (one elected
-// lane), warps 2-5 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31, i.e. 32 queries).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer (one elected
+// lane), warps 2-9 = epilogue: warp w reads TMEM lanes 32*(w%4)..+31 (32 queries) and the column half
+// (w-2)/4 of the accumulator (128 rows of the tile), so two threads share a query (measured 3 % faster at k = 100
+// than one thread per query, which CSGPU_TC_EPI=1 still selects).
 //
-// Epilogue = progressive-threshold filter. Each epilogue thread owns ONE query: it holds that
-// query's current threshold distance in a register, reads its lane's 256 scores with tcgen05.ld,
-// and appends (distance, id) keys that pass to the query's candidate buffer in HBM (atomic
-// counter). Between row phases (sizes growing geometrically) a select kernel reduces each buffer
-// to its exact top-k and publishes the new threshold, so after the first phases only
-// ~k * phase_growth rows per query pass. Exactness: the threshold is always the k-th best of a
-// SUBSET of the rows, hence never tighter than the final k-th best; ties pass (<=) and are
-// ordered by the full (distance, id) key in the select kernel. If a buffer overflows (adversarially
-// ordered data) the host halves the phase and retries, which terminates because a phase of
-// <= CAP - k rows cannot overflow.
+// Epilogue = progressive-threshold filter. Each epilogue thread holds its query's current threshold
+// distance in a register, reads its lane's 128 scores with tcgen05.ld, 32 columns at a time, and
+// appends the (distance, row) keys that pass to ITS OWN segment of
+// the query's candidate buffer in HBM: segment = (CTA group, column half), position counter in a
+// register — no atomics, no second pass over TMEM; the counts are written once when the kernel ends.
+// Between row phases (sizes growing geometrically) a select kernel reduces each query's segments to its
+// exact top-k and publishes the new threshold, so after the first phases only ~k * phase_growth rows per
+// query pass. Exactness: the threshold is always the k-th best of a SUBSET of the rows, hence never
+// tighter than the final k-th best; ties pass (<=) and are ordered by the full (distance, id) key in the
+// select kernel. If a segment overflows (adversarially ordered data) the host halves the range and
+// retries, which terminates because a range of one tile (128 rows per segment) cannot overflow.
 //
 // CTA -> work: query block qb = cta % QB, group = cta / QB; the QB CTAs of a group walk the same
 // tiles at the same time, so a corpus tile is read from HBM once and served to the other QB-1
@@ -41,7 +44,9 @@ constexpr int GT_BLOCK_M = 128;   // queries per CTA
 constexpr int GT_BLOCK_N = 256;   // corpus rows per tile
 constexpr int GT_BLOCK_K = 64;    // bf16 elements per K chunk (= 128 B = one swizzle row)
 constexpr int GT_UMMA_K = 16;
-constexpr int GT_THREADS = 192;
+
+
+constexpr uint32_t GT_SURV = 1024;   // slots at the front of a query's candidate block reserved for the survivors of the last select (= CSGPU_MAX_K)
 constexpr uint32_t GT_STAGE_BYTES = GT_BLOCK_N * GT_BLOCK_K * 2;   // 32 KB
 constexpr uint32_t GT_QCHUNK_BYTES = GT_BLOCK_M * GT_BLOCK_K * 2;  // 16 KB
 
@@ -55,6 +60,12 @@ struct GemmTopkArgs {
     unsigned *count;           // [QB*128] entries in cand (may exceed cap => overflow)
     uint32_t cap;
     uint32_t prefetch_tiles;   // bf16 kernel: L2 prefetch distance in tiles of a CTA's walk (0 = off)
+    // tensor-core kernel only — segmented candidate layout: query q owns cand[q * stride, +stride):
+    //   [0, GT_SURV)                     survivors of the previous select (exact keys with chunk ids; count[q] of them)
+    //   [GT_SURV + s * seg_len, +seg_len) segment s = group * 2 + column half, seg_count[q * n_seg + s] entries
+    unsigned *seg_count = nullptr;   // [QB*128][n_seg], WRITTEN (not accumulated) by every launch
+    unsigned *overflow = nullptr;    // set to 1 when a segment would overflow
+    uint32_t stride = 0, seg_len = 0, n_seg = 0;
 };
 
 // ---- tcgen05 wrappers ---------------------------------------------------------------------
@@ -86,9 +97,8 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
 {
-    uint32_t r[32];
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
@@ -99,8 +109,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // 2-D TMA tile load (inner coordinate = element column, outer = row), completes on an mbarrier
@@ -144,60 +152,36 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(uint32_t M, uint32_t 
     return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
-// Epilogue of one 128-query x 256-row accumulator tile, one thread = one query (its TMEM lane).
-__device__ __forceinline__ void gt_epilogue_tile(uint32_t taddr, uint64_t row0, float thr, uint64_t *my_cand, unsigned *my_count,
-                                                 const GemmTopkArgs &a)
+// One 32-column chunk of one thread's query: max -> one compare in the common case; a hit (lane-divergent, rare
+// after the first phases) appends the passing keys to the thread's own segment with branch-free predicated
+// stores. The key carries the ROW index; the select kernel swaps in the chunk id (no dependent load in here).
+__device__ __forceinline__ void gt_epilogue_chunk(const uint32_t (&r)[32], uint64_t row0, uint64_t n_rows, float thr,
+                                                  uint64_t *my_seg, uint32_t seg_len, uint32_t &pos)
 {
-    // pass 1: per 32-column chunk, max -> one compare; chunks where some lane passes are
-    // counted exactly. Common case (late phases): 8 x (LDTM + 31 FMNMX + vote).
-    uint32_t chunkmask = 0, cnt = 0;   // chunkmask is warp-uniform
-#pragma unroll 1
-    for (uint32_t c = 0; c < GT_BLOCK_N / 32; ++c) {
-        float v[32];
-        tmem_ld32(taddr + c * 32, v);
-        float best = v[0];
+    float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]), m2 = __uint_as_float(r[2]), m3 = __uint_as_float(r[3]);
 #pragma unroll
-        for (int j = 1; j < 32; ++j) best = fmaxf(best, v[j]);
-        const bool hit = fmaf(-0.5f, best, 0.5f) <= thr;
-        if (__any_sync(FULL, hit)) {
-            chunkmask |= 1u << c;
-            if (hit) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    cnt += (fmaf(-0.5f, v[j], 0.5f) <= thr && row0 + c * 32 + j < a.n_rows) ? 1u : 0u;
-            }
-        }
+    for (int j = 4; j < 32; j += 4) {   // four independent chains
+        m0 = fmaxf(m0, __uint_as_float(r[j])); m1 = fmaxf(m1, __uint_as_float(r[j + 1]));
+        m2 = fmaxf(m2, __uint_as_float(r[j + 2])); m3 = fmaxf(m3, __uint_as_float(r[j + 3]));
     }
-    // pass 2 (only if some query of this warp has candidates in the tile): ONE atomic per
-    // query per tile reserves the slots, then the hit chunks are re-read from TMEM and the
-    // keys written. The atomic's latency is exposed once per tile, not once per candidate.
-    if (chunkmask) {
-        unsigned pos = cnt ? atomicAdd(my_count, cnt) : 0u;
-#pragma unroll 1
-        for (uint32_t c = 0; c < GT_BLOCK_N / 32; ++c) {
-            if (!((chunkmask >> c) & 1u)) continue;
-            float v[32];
-            tmem_ld32(taddr + c * 32, v);
-            if (cnt) {
-                // branch-free: one predicated 8-byte store per column. The key carries the ROW index;
-                // select_candidates_kernel swaps in the chunk id (no dependent load in here).
-                const uint32_t rbase = (uint32_t)(row0 + c * 32);
-                const uint32_t lim = (uint32_t)min((uint64_t)32, a.n_rows - min(a.n_rows, row0 + c * 32));
+    const float best = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+    if (fmaf(-0.5f, best, 0.5f) <= thr) {
+        const uint32_t rbase = (uint32_t)row0;
+        const uint32_t lim = (uint32_t)min((uint64_t)32, n_rows - min(n_rows, row0));
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float dist = fmaf(-0.5f, v[j], 0.5f);
-                    const bool pass = (dist <= thr) & ((uint32_t)j < lim);
-                    st_global_pred(my_cand + min(pos, a.cap - 1), make_key(dist, rbase + j), pass & (pos < a.cap));
-                    pos += pass ? 1u : 0u;
-                }
-            }
+        for (int j = 0; j < 32; ++j) {
+            const float dist = fmaf(-0.5f, __uint_as_float(r[j]), 0.5f);
+            const bool pass = (dist <= thr) & ((uint32_t)j < lim);
+            st_global_pred(my_seg + min(pos, seg_len - 1), make_key(dist, rbase + j), pass & (pos < seg_len));
+            pos += pass ? 1u : 0u;
         }
     }
 }
 
 // dynamic smem: [n_kchunks][16 KB] queries | [STAGES][32 KB] corpus ring   (1024-B aligned)
-template <int STAGES>
-__global__ void __launch_bounds__(GT_THREADS, 1)
+// HALVES = threads per query in the epilogue (1: warps 2-5, 192 threads; 2: warps 2-9, 320 threads, column halves).
+template <int STAGES, int HALVES>
+__global__ void __launch_bounds__(64 + 128 * HALVES, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c, const GemmTopkArgs a)
 {
     extern __shared__ __align__(1024) unsigned char gt_smem_raw[];
@@ -218,7 +202,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(&q_bar, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4 * HALVES); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(&tmem_base_s, 512);
@@ -288,25 +272,36 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             }
             __syncwarp();
         } else {
-            // ================= epilogue: one thread = one query =================
+            // ================= epilogue: two threads (column halves) per query =================
             const uint32_t quarter = warp & 3;                       // TMEM lane quarter this warp may access
-            const uint32_t q_local = quarter * 32 + lane;
-            const uint32_t q_glob = qb * GT_BLOCK_M + q_local;
+            const uint32_t half = (uint32_t)(warp - 2) >> 2;         // column block of the accumulator this thread reads
+            const uint32_t q_glob = qb * GT_BLOCK_M + quarter * 32 + lane;
             const float thr = a.thr[q_glob];
-            uint64_t *my_cand = a.cand + (size_t)q_glob * a.cap;
-            unsigned *my_count = a.count + q_glob;
+            const uint32_t seg = group * HALVES + half;
+            uint64_t *my_seg = a.cand + (size_t)q_glob * a.stride + GT_SURV + (size_t)seg * a.seg_len;
+            uint32_t pos = 0;
             uint32_t tile_it = 0;
+            constexpr uint32_t NCH = GT_BLOCK_N / HALVES / 32;       // chunks of 32 columns per thread per tile
             for (uint64_t t = a.tile_begin + group; t < a.tile_end; t += n_groups, ++tile_it) {
                 const uint32_t acc = tile_it & 1;
                 mbar_wait(&tfull_bar[acc], (tile_it >> 1) & 1);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * GT_BLOCK_N;
-                const uint64_t row0 = t * GT_BLOCK_N;
-                gt_epilogue_tile(taddr, row0, thr, my_cand, my_count, a);
+                const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * GT_BLOCK_N + half * (GT_BLOCK_N / HALVES);
+                const uint64_t row0 = t * GT_BLOCK_N + half * (GT_BLOCK_N / HALVES);
+                // One chunk at a time: keeping the tcgen05.ld of chunk c+1 in flight while chunk c is tested was
+                // measured 40-120 % SLOWER (profiles/r01_bf16_epilogue_modes.txt), so the load is waited for at once.
+#pragma unroll 1
+                for (uint32_t c = 0; c < NCH; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c * 32, r);
+                    gt_epilogue_chunk(r, row0 + c * 32, a.n_rows, thr, my_seg, a.seg_len, pos);
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             }
+            a.seg_count[(size_t)q_glob * a.n_seg + seg] = pos;
+            if (pos > a.seg_len) atomicExch(a.overflow, 1u);
         }
     }
     tc_fence_before();
@@ -314,180 +309,6 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-
-// ---- cta_group::2 (CTA pair) variants ----------------------------------------------------------------------
-__device__ __forceinline__ uint32_t cluster_ctarank()
-{
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of `p` (a shared::cta address of this CTA) in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t mapa_u32(const void *p, uint32_t rank)
-{
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
-{
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc2(uint32_t *smem_dst, uint32_t ncols)
-{
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols)
-{
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// M = 256 MMA over the CTA pair: each CTA supplies 128 rows of A and N/2 rows of B from its own smem (same offsets)
-__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// arrive on the barrier at this smem offset in BOTH CTAs of the pair once the issued MMAs have completed
-__device__ __forceinline__ void umma2_commit_mc(uint64_t *bar)
-{
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-// TMA tile load into THIS CTA's smem whose completion is signalled on a barrier of the pair's leader CTA
-__device__ __forceinline__ void tma_load_2d_2sm(void *smem_dst, const CUtensorMap *map, uint32_t leader_bar_cluster_addr,
-                                                int32_t c_inner, int32_t c_outer)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(leader_bar_cluster_addr), "r"(c_inner), "r"(c_outer)
-        : "memory");
-}
-
-constexpr uint32_t GT2_STAGE_BYTES = (GT_BLOCK_N / 2) * GT_BLOCK_K * 2;   // 16 KB: this CTA's half of a row tile
-
-// CTA-pair version of gemm_topk_kernel (cluster 2x1x1). The pair computes 256 queries x 256 rows per tile with
-// tcgen05.mma.cta_group::2 (M = 256): CTA r keeps its own 128 queries resident and loads only rows
-// [256 t + 128 r, +128) of every tile, so the L2 -> SM operand stream per SM (the measured limiter of the one-CTA
-// kernel) and the smem operand reads per MMA are halved, and the ring is twice as deep in tiles.
-//   leader (rank 0): full[s] / q_bar collect the TMA bytes of BOTH CTAs; issues every MMA; its commits arrive on
-//   empty[s] and tfull[acc] in both CTAs (multicast); tempty[acc] counts the 8 epilogue warps of the pair.
-// map_c2: box = [128 rows][64]. n_qblocks must be even.
-template <int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GT_THREADS, 1)
-gemm_topk2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c2, const GemmTopkArgs a)
-{
-    extern __shared__ __align__(1024) unsigned char gt_smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], q_bar, tfull_bar[2], tempty_bar[2];
-    __shared__ uint32_t tmem_base_s;
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const bool leader = rank == 0;
-    unsigned char *base = gt_smem_raw + ((1024u - (smem_u32(gt_smem_raw) & 1023u)) & 1023u);
-    unsigned char *q_smem = base;
-    unsigned char *ring = base + (size_t)a.n_kchunks * GT_QCHUNK_BYTES;
-
-    const uint32_t n_qpairs = a.n_qblocks / 2;
-    const uint32_t pair = blockIdx.x / 2;
-    const uint32_t qpair = pair % n_qpairs;
-    const uint32_t group = pair / n_qpairs;
-    const uint32_t n_groups = (gridDim.x / 2) / n_qpairs;
-    const uint32_t qb = 2 * qpair + rank;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&q_bar, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) tmem_alloc2(&tmem_base_s, 512);
-    tc_fence_before();
-    cluster_sync_all();   // barriers of both CTAs are initialised before any remote arrive / complete_tx
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_base_s;
-
-    if (warp == 0) {
-        // ================= TMA producer (both CTAs; bytes are counted on the leader's barriers) =================
-        if (lane == 0) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c2) : "memory");
-            const uint32_t qbar_l = mapa_u32(&q_bar, 0);
-            if (leader) mbar_expect_tx(&q_bar, 2u * a.n_kchunks * GT_QCHUNK_BYTES);
-            for (uint32_t kc = 0; kc < a.n_kchunks; ++kc)
-                tma_load_2d_2sm(q_smem + (size_t)kc * GT_QCHUNK_BYTES, &map_q, qbar_l, (int32_t)(kc * GT_BLOCK_K), (int32_t)(qb * GT_BLOCK_M));
-            uint32_t it = 0;
-            for (uint64_t t = a.tile_begin + group; t < a.tile_end; t += n_groups) {
-                for (uint32_t kc = 0; kc < a.n_kchunks; ++kc, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait_backoff(&empty_bar[s], ph ^ 1, 64);
-                    if (leader) mbar_expect_tx(&full_bar[s], 2u * GT2_STAGE_BYTES);
-                    tma_load_2d_2sm(ring + (size_t)s * GT2_STAGE_BYTES, &map_c2, mapa_u32(&full_bar[s], 0), (int32_t)(kc * GT_BLOCK_K),
-                                    (int32_t)(t * GT_BLOCK_N + rank * (GT_BLOCK_N / 2)));
-                }
-            }
-        }
-        __syncwarp();
-    } else if (warp == 1) {
-        // ================= MMA issuer (leader only) =================
-        if (leader && lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16_f32(2 * GT_BLOCK_M, GT_BLOCK_N);
-            mbar_wait(&q_bar, 0);
-            tc_fence_after();
-            uint32_t it = 0, tile_it = 0;
-            for (uint64_t t = a.tile_begin + group; t < a.tile_end; t += n_groups, ++tile_it) {
-                const uint32_t acc = tile_it & 1;
-                mbar_wait(&tempty_bar[acc], ((tile_it >> 1) & 1) ^ 1);   // both CTAs' epilogues drained this buffer
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * GT_BLOCK_N;
-                for (uint32_t kc = 0; kc < a.n_kchunks; ++kc, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&full_bar[s], ph);
-                    tc_fence_after();
-                    const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(q_smem + (size_t)kc * GT_QCHUNK_BYTES));
-                    const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(ring + (size_t)s * GT2_STAGE_BYTES));
-#pragma unroll
-                    for (uint32_t k = 0; k < GT_BLOCK_K / GT_UMMA_K; ++k)
-                        umma2_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) ? 1u : 0u);
-                    umma2_commit_mc(&empty_bar[s]);          // both CTAs' slots are reusable once these MMAs retire
-                }
-                umma2_commit_mc(&tfull_bar[acc]);            // accumulators (one half in each CTA's TMEM) are ready
-            }
-        }
-        __syncwarp();
-    } else {
-        // ================= epilogue (both CTAs): one thread = one query =================
-        const uint32_t quarter = warp & 3;
-        const uint32_t q_glob = qb * GT_BLOCK_M + quarter * 32 + lane;
-        const float thr = a.thr[q_glob];
-        uint64_t *my_cand = a.cand + (size_t)q_glob * a.cap;
-        unsigned *my_count = a.count + q_glob;
-        uint32_t tile_it = 0;
-        for (uint64_t t = a.tile_begin + group; t < a.tile_end; t += n_groups, ++tile_it) {
-            const uint32_t acc = tile_it & 1;
-            mbar_wait(&tfull_bar[acc], (tile_it >> 1) & 1);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * GT_BLOCK_N;
-            gt_epilogue_tile(taddr, t * GT_BLOCK_N, thr, my_cand, my_count, a);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0));
-        }
-    }
-    tc_fence_before();
-    cluster_sync_all();   // the peer may still be signalling this CTA's barriers / reading its smem
-    if (warp == 1) tmem_dealloc2(tmem_base, 512);
-}
 
 // ---- query prep: fp32 [b][dim] -> unit length -> bf16 [QB*128][dim] (rows >= b zero) -------------
 // flags[q] = 1 if the query has zero norm.

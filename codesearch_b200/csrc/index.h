@@ -66,7 +66,8 @@ struct BatchCtx {
     unsigned *count = nullptr, *count_saved = nullptr;
     uint64_t *cand = nullptr;      // [1024][BF_CAP]
     uint64_t *out = nullptr;       // [1024][CSGPU_MAX_K]
-    unsigned *scalar = nullptr;
+    unsigned *scalar = nullptr;     // [0] sticky overflow flag, [2..3] rows rescored (u64)
+    unsigned *seg_count = nullptr;  // [1024][2 * 148] per-(query, segment) candidate counts of the tensor-core kernel
     float *q_pin = nullptr;
     uint64_t *out_pin = nullptr;
 };

@@ -18,7 +18,7 @@
 // TC_MARGIN = 2.1e-3 (distance units) leaves slack for the two final roundings. Exactness of the filter:
 //   * a row of the final top-k has d_f32 <= T_final <= T (the exact k-th best so far, never tighter than final), so
 //     d_tc <= d_f32 + MARGIN <= T + MARGIN: it passes the epilogue (which tests d_tc <= thr with thr = T + MARGIN);
-//   * here a candidate is skipped unread only if d_tc - MARGIN > T_warp >= T_final, i.e. d_f32 > T_final.
+//   * the select kernel drops a candidate unread only if d_tc - MARGIN > T' for some exact T' >= T_final, i.e. d_f32 > T_final.
 // tests/test_gpu_prefilter.py checks bit-equality with the single-query kernel, and adversarial inputs (many near-ties
 // inside the margin) exercise the overflow path.
 #pragma once
@@ -28,129 +28,222 @@ namespace csgpu {
 
 constexpr float TC_MARGIN = 2.1e-3f;
 
-struct RescoreArgs {
-    const float4 *rows;        // [n_rows, dim4] fp32 unit rows
+// ---------------------------------------------------------------------------------------------------------------
+// select_sorted_kernel — the per-query reduction between the row phases of every GEMM-shaped batch kernel
+// (gemm_topk.cu): candidates -> exact top-k (ascending (distance, id)), written to the front of the query's block,
+// new threshold published. One CTA per query; everything happens in shared memory around CTA-wide bitonic sorts.
+//
+// Inputs per query (see GemmTopkArgs): part 1 = cand[q*stride + 0 .. count[q])  — entries below n_done[q] are
+// survivors of the previous select (exact keys carrying chunk ids), entries above are fresh candidates carrying ROW
+// indices (SIMT kernel, global-atomic layout); part 2 = the tensor-core kernel's segments (all fresh candidates).
+//
+// RESCORE = false (bf16 index, fp32 SIMT kernel): candidate distances are final; swap ids in, one sort, keep k.
+// RESCORE = true  (tensor prefilter): candidate distances are bf16 estimates d_tc. Sort the candidates by d_tc, then
+//   stage A  rescore the best-looking a = max(32, k rounded up to 32) of them from the fp32 rows (exact keys, in place),
+//            T_A = k-th smallest exact key of survivors U stage A  (a valid upper bound of the final k-th best);
+//   stage B  keep rescoring down the sorted list while d_tc - MARGIN <= T_A can still hold (a prefix: the list is
+//            sorted), drop everything behind it unread;
+//   final    sort survivors U rescored, keep k, publish thr = exact k-th distance + MARGIN.
+//   About 1.5 k rows are read per query and phase instead of every candidate the margin let through.
+struct SelectArgs {
+    uint64_t *cand;            // [nq][stride]
+    unsigned *count;           // [nq] in: entries of part 1; out: survivors
+    const unsigned *n_done;    // [nq] part 1: entries below this are survivors (already exact, with ids)
+    const unsigned *seg_count; // [nq][n_seg] or nullptr
+    uint32_t stride, surv, seg_len, n_seg;
+    unsigned *overflow;        // set to 1 if a query holds more candidates than the sort buffer (host splits the range)
+    float *thr;                // [nq] out
     const uint32_t *ids;       // [n_rows]
-    uint32_t dim4;
-    const float *q_raw;        // [nq][dim4*4] raw queries (normalised in the prologue, exactly like the scan kernel)
     const uint8_t *flags;      // [nq] zero-norm query flags (such queries are answered by the scan kernel instead)
-    uint64_t *cand;            // [nq][cap]; entries [0, n_done[q]) = exact keys with chunk ids (survivors of earlier
-                               // selects), entries beyond = (okey(d_tc) << 32 | ROW index) from the GEMM epilogue
-    unsigned *count;           // [nq]
-    const unsigned *n_done;    // [nq]
-    float *thr;                // [nq] out: exact k-th best distance + TC_MARGIN (+inf until k rows are known)
-    uint32_t cap, k, kpad, n_active;
+    uint32_t k, n_active;
     const uint32_t *zero_ids;  // final pass only
     uint32_t n_zero;
     uint64_t *final_out;       // [nq][k] or nullptr
-    unsigned long long *n_rescored;   // optional statistics: rows actually read
+    // RESCORE only
+    const float4 *rows;        // [n_rows, dim4] fp32 unit rows
+    uint32_t dim4;
+    const float *q_raw;        // [nq][dim4*4] raw queries (normalised in the prologue, exactly like the scan kernel)
+    unsigned long long *n_rescored;   // statistics: rows actually read
 };
 
-// One CTA per query. V/EXACT as in scan_topk_kernel; R candidate rows in flight per warp.
-template <int V, bool EXACT, bool BIG>
-__global__ void __launch_bounds__(SCAN_THREADS, 2) rescore_select_kernel(const RescoreArgs a)
+constexpr uint32_t SEL_BUF = 8192;                       // sort buffer (keys) = the largest bitonic sort a query needs
+constexpr uint32_t SEL_SORT_CAP = SEL_BUF - 2 * 1024;    // fresh candidates per query; the rest holds survivors + zero-norm ids
+
+// Exact distances of candidates C[lo, hi) (keys carrying row indices) from the fp32 rows, in place; a candidate whose
+// lower bound d_tc - MARGIN already exceeds `bound32` (okey of an exact upper bound of the final k-th distance) is
+// dropped unread. 8 warps x R rows in flight. Same arithmetic as scan_topk_kernel, operation for operation.
+template <int V, bool EXACT>
+__device__ __forceinline__ unsigned rescore_range(const SelectArgs &a, const float4 (&qv)[V], uint64_t *C, uint32_t lo, uint32_t hi,
+                                                  uint32_t bound32, int warp, int lane)
+{
+    constexpr int R = 4;
+    unsigned read_rows = 0;
+    for (uint32_t i0 = lo + (uint32_t)warp * R; i0 < hi; i0 += SCAN_WARPS * R) {
+        uint32_t row[R];
+        bool live[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint32_t i = i0 + r;
+            const uint64_t key = i < hi ? C[i] : KEY_EMPTY;
+            live[r] = false;
+            if (key != KEY_EMPTY) {
+                const float d_tc = __uint_as_float(bits_from_okey((uint32_t)(key >> 32)));
+                live[r] = okey(d_tc - TC_MARGIN) <= bound32;
+            }
+            row[r] = (uint32_t)key;
+        }
+        float4 x[R][V];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float4 *p = a.rows + (size_t)row[r] * a.dim4 + lane;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                if (live[r] && (EXACT || lane + 32 * j < a.dim4)) x[r][j] = __ldg(p + 32 * j);
+                else x[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                acc = fmaf(x[r][j].x, qv[j].x, acc); acc = fmaf(x[r][j].y, qv[j].y, acc);
+                acc = fmaf(x[r][j].z, qv[j].z, acc); acc = fmaf(x[r][j].w, qv[j].w, acc);
+            }
+            acc = warp_sum_tree(acc);
+            const float dist = fmaf(-0.5f, acc, 0.5f);
+            if (i0 + r < hi && lane == 0) C[i0 + r] = live[r] ? make_key(dist, __ldg(a.ids + row[r])) : KEY_EMPTY;
+            read_rows += live[r] ? 1u : 0u;
+        }
+    }
+    return read_rows;
+}
+
+// dynamic smem: C[SEL_BUF] | S[1024] | T[4096]   (u64 each; S and T only when RESCORE)
+template <int V, bool EXACT, bool RESCORE>
+__global__ void __launch_bounds__(SCAN_THREADS, 2) select_sorted_kernel(const SelectArgs a)
 {
     extern __shared__ __align__(16) uint64_t smem[];
-    constexpr int R = 4;
-    const uint32_t q = blockIdx.x;
+    __shared__ unsigned s_n, s_pref[2 * 148 + 8], s_end;
+    uint64_t *C = smem, *S = smem + SEL_BUF, *T = S + 1024;
+    const uint32_t q = blockIdx.x, k = a.k;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (q >= a.n_active || a.flags[q]) {
+    if (q >= a.n_active || a.flags[q]) {   // padding rows and zero-norm queries stay inactive
         if (threadIdx.x == 0) { a.count[q] = 0; a.thr[q] = -1.f; }
         return;
     }
-    using Sel = typename SelOf<BIG>::type;
-    Sel sel;
-    if constexpr (BIG) sel.init(smem + (size_t)warp * a.kpad, smem + (size_t)(SCAN_WARPS + warp) * a.kpad, a.k, a.kpad, lane);
-    else sel.init(a.k);
+    uint64_t *mine = a.cand + (size_t)q * a.stride;
+    const uint32_t n1 = min(a.count[q], a.n_seg ? a.surv : a.stride);
+    const uint32_t done = a.n_seg ? n1 : min(a.n_done[q], n1);
 
-    // ---- query -> registers, scaled to unit length: the scan kernel's prologue, operation for operation ----
-    float4 qv[V];
-    float ss = 0.f;
-    const float4 *qp = reinterpret_cast<const float4 *>(a.q_raw) + (size_t)q * a.dim4;
-#pragma unroll
-    for (int j = 0; j < V; ++j) {
-        const uint32_t c = lane + 32 * j;
-        if (EXACT || c < a.dim4) qv[j] = qp[c];
-        else qv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        ss = fmaf(qv[j].x, qv[j].x, ss); ss = fmaf(qv[j].y, qv[j].y, ss);
-        ss = fmaf(qv[j].z, qv[j].z, ss); ss = fmaf(qv[j].w, qv[j].w, ss);
+    // ---- gather: survivors -> S (RESCORE) or C; fresh candidates -> C ----
+    for (uint32_t s = threadIdx.x; s < a.n_seg; s += blockDim.x) s_pref[s] = min(a.seg_count[(size_t)q * a.n_seg + s], a.seg_len);
+    __syncthreads();
+    if (threadIdx.x == 0) {   // exclusive prefix of the segment counts (n_seg <= 2 * 148)
+        unsigned run = n1 - done;
+        for (uint32_t s = 0; s < a.n_seg; ++s) {
+            const unsigned c = s_pref[s];
+            s_pref[s] = run;
+            run += c;
+        }
+        s_pref[a.n_seg] = run;
+        if (run > SEL_SORT_CAP) { atomicExch(a.overflow, 1u); run = SEL_SORT_CAP; }
+        s_n = run;
     }
-    ss = warp_sum_tree(ss);
-    const float qinv = 1.0f / sqrtf(ss);   // ss > 0: zero-norm queries were filtered out above
+    __syncthreads();
+    const uint32_t n_c = s_n;                       // fresh candidates
+    const uint32_t n_s = done;                      // survivors (<= k <= 1024), ascending
+    for (uint32_t t = threadIdx.x; t < n1 - done; t += blockDim.x) {
+        if (t < n_c) {
+            uint64_t key = mine[done + t];
+            if (!RESCORE) key = (key & 0xFFFFFFFF00000000ull) | a.ids[(uint32_t)key];
+            C[t] = key;
+        }
+    }
+    if (a.n_seg) {   // flat over all fresh candidates (every load in flight at once): entry t lives in the segment s with
+                     // s_pref[s] <= t < s_pref[s + 1]
+        for (uint32_t t = (n1 - done) + threadIdx.x; t < n_c; t += blockDim.x) {
+            uint32_t lo = 0, hi = a.n_seg;   // last s with s_pref[s] <= t
+            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_pref[mid] <= t) lo = mid; else hi = mid; }
+            uint64_t key = mine[a.surv + (size_t)lo * a.seg_len + (t - s_pref[lo])];
+            if (!RESCORE) key = (key & 0xFFFFFFFF00000000ull) | a.ids[(uint32_t)key];
+            C[t] = key;
+        }
+    }
+    uint32_t n_all;   // entries of C that take part in the final sort
+    if constexpr (!RESCORE) {
+        for (uint32_t t = threadIdx.x; t < n_s; t += blockDim.x) C[n_c + t] = mine[t];
+        n_all = n_c + n_s;
+    } else {
+        for (uint32_t t = threadIdx.x; t < 1024; t += blockDim.x) S[t] = t < n_s ? mine[t] : KEY_EMPTY;
+        // ---- query -> registers, scaled to unit length: the scan kernel's prologue, operation for operation ----
+        float4 qv[V];
+        float ss = 0.f;
+        const float4 *qp = reinterpret_cast<const float4 *>(a.q_raw) + (size_t)q * a.dim4;
 #pragma unroll
-    for (int j = 0; j < V; ++j) { qv[j].x *= qinv; qv[j].y *= qinv; qv[j].z *= qinv; qv[j].w *= qinv; }
+        for (int j = 0; j < V; ++j) {
+            const uint32_t c = lane + 32 * j;
+            if (EXACT || c < a.dim4) qv[j] = qp[c];
+            else qv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            ss = fmaf(qv[j].x, qv[j].x, ss); ss = fmaf(qv[j].y, qv[j].y, ss);
+            ss = fmaf(qv[j].z, qv[j].z, ss); ss = fmaf(qv[j].w, qv[j].w, ss);
+        }
+        ss = warp_sum_tree(ss);
+        const float qinv = 1.0f / sqrtf(ss);   // ss > 0: zero-norm queries were filtered out above
+#pragma unroll
+        for (int j = 0; j < V; ++j) { qv[j].x *= qinv; qv[j].y *= qinv; qv[j].z *= qinv; qv[j].w *= qinv; }
 
-    uint64_t *mine = a.cand + (size_t)q * a.cap;
-    const uint32_t n = min(a.count[q], a.cap);
-    const uint32_t done = min(a.n_done[q], n);
-    unsigned read_rows = 0;
-    for (uint32_t b = warp * 32; b < n; b += SCAN_WARPS * 32) {
-        uint64_t key = (b + lane < n) ? mine[b + lane] : KEY_EMPTY;
-        bool todo = false;
-        if (b + lane >= done && key != KEY_EMPTY) {
-            // candidate from the tensor-core filter: can it still make the warp's top-k?  d_f32 >= d_tc - MARGIN
-            const float d_tc = __uint_as_float(bits_from_okey((uint32_t)(key >> 32)));
-            todo = okey(d_tc - TC_MARGIN) <= (uint32_t)(sel.thr >> 32);
-            if (!todo) key = KEY_EMPTY;
+        // candidates ascending by d_tc
+        const uint32_t npad = pow2_at_least(n_c, 32);
+        for (uint32_t t = n_c + threadIdx.x; t < npad; t += blockDim.x) C[t] = KEY_EMPTY;
+        cta_sort(C, npad);
+        // stage A
+        const uint32_t a_end = min(n_c, max(32u, (k + 31u) & ~31u));
+        const uint32_t bound0 = n_s >= k ? (uint32_t)(S[k - 1] >> 32) : 0xFFFFFFFFu;
+        unsigned read_rows = rescore_range<V, EXACT>(a, qv, C, 0, a_end, bound0, warp, lane);
+        __syncthreads();
+        // T_A = k-th smallest exact key of survivors U stage A
+        const uint32_t tpad = pow2_at_least(n_s + a_end, 32);   // <= 1024 + 1024 + 32 -> 4096
+        for (uint32_t t = threadIdx.x; t < tpad; t += blockDim.x)
+            T[t] = t < n_s ? S[t] : (t - n_s < a_end ? C[t - n_s] : KEY_EMPTY);
+        cta_sort(T, tpad);
+        const uint32_t bound_a = (k - 1 < tpad) ? (uint32_t)(T[k - 1] >> 32) : 0xFFFFFFFFu;   // EMPTY -> 0xFFFFFFFF: no pruning
+        // stage B: the sorted prefix that can still beat T_A
+        if (threadIdx.x == 0) s_end = n_c;
+        __syncthreads();
+        for (uint32_t t = a_end + threadIdx.x; t < n_c; t += blockDim.x) {
+            const float d_tc = __uint_as_float(bits_from_okey((uint32_t)(C[t] >> 32)));
+            if (okey(d_tc - TC_MARGIN) > bound_a) atomicMin(&s_end, t);
         }
-        unsigned m = __ballot_sync(FULL, todo);
-        const uint32_t my_row = (uint32_t)key;
-        while (m) {
-            int src[R];
-            uint32_t row[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                src[r] = m ? (__ffs(m) - 1) : -1;
-                m &= m - 1;
-                row[r] = __shfl_sync(FULL, my_row, src[r] < 0 ? 0 : src[r]);
-            }
-            float4 x[R][V];
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const float4 *p = a.rows + (size_t)row[r] * a.dim4 + lane;
-#pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    if (src[r] >= 0 && (EXACT || lane + 32 * j < a.dim4)) x[r][j] = __ldg(p + 32 * j);
-                    else x[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                float acc = 0.f;
-#pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    acc = fmaf(x[r][j].x, qv[j].x, acc); acc = fmaf(x[r][j].y, qv[j].y, acc);
-                    acc = fmaf(x[r][j].z, qv[j].z, acc); acc = fmaf(x[r][j].w, qv[j].w, acc);
-                }
-                acc = warp_sum_tree(acc);
-                const float dist = fmaf(-0.5f, acc, 0.5f);
-                if (src[r] >= 0) {
-                    ++read_rows;
-                    if (lane == src[r]) key = make_key(dist, __ldg(a.ids + row[r]));
-                }
-            }
-        }
-        offer_lane_keys(sel, key, lane);
+        __syncthreads();
+        const uint32_t b_end = s_end;
+        read_rows += rescore_range<V, EXACT>(a, qv, C, a_end, b_end, bound_a, warp, lane);
+        if (a.n_rescored != nullptr && lane == 0 && read_rows) atomicAdd(a.n_rescored, (unsigned long long)read_rows);
+        __syncthreads();
+        for (uint32_t t = threadIdx.x; t < n_s; t += blockDim.x) C[b_end + t] = S[t];
+        n_all = b_end + n_s;
     }
-    if (a.final_out != nullptr && warp == 0 && a.n_zero) {   // zero-norm rows: distance 0.0 (arroy pn*qn == 0)
-        uint32_t found = 0;
-        for (uint32_t b = 0; b < a.n_zero && found < a.k; b += 32) {
-            const uint64_t key = (b + lane < a.n_zero) ? make_key(0.f, a.zero_ids[b + lane]) : KEY_EMPTY;
-            found += __popc(__ballot_sync(FULL, key != KEY_EMPTY));
-            offer_lane_keys(sel, key, lane);
-        }
+    __syncthreads();
+    if (a.final_out != nullptr && a.n_zero) {   // zero-norm rows: distance 0.0 (arroy pn*qn == 0); the first k ids suffice
+        const uint32_t nz = min(a.n_zero, k);
+        for (uint32_t t = threadIdx.x; t < nz; t += blockDim.x) C[n_all + t] = make_key(0.f, a.zero_ids[t]);
+        n_all += nz;
     }
-    if (a.n_rescored != nullptr && lane == 0 && read_rows) atomicAdd(a.n_rescored, (unsigned long long)read_rows);
-    __syncthreads();   // every warp has finished reading cand[q] before it is overwritten
-    cta_reduce<BIG>(sel, smem, a.k, a.kpad, mine, warp, lane);
-    if (a.final_out != nullptr)
-        for (uint32_t j = threadIdx.x; j < a.k; j += blockDim.x) a.final_out[(size_t)q * a.k + j] = mine[j];
+    const uint32_t fpad = pow2_at_least(n_all, 32);
+    for (uint32_t t = n_all + threadIdx.x; t < fpad; t += blockDim.x) C[t] = KEY_EMPTY;
+    cta_sort(C, fpad);
+    // ---- survivors to the front of the block, threshold ----
+    for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) {
+        const uint64_t key = j < fpad ? C[j] : KEY_EMPTY;
+        mine[j] = key;
+        if (a.final_out != nullptr) a.final_out[(size_t)q * k + j] = key;
+    }
     if (threadIdx.x == 0) {
-        uint32_t mcount = 0;
-        while (mcount < a.k && mine[mcount] != KEY_EMPTY) ++mcount;
-        a.count[q] = mcount;
+        uint32_t m = min(n_all, k);
+        while (m > 0 && C[m - 1] == KEY_EMPTY) --m;   // dropped candidates sort to the end
+        a.count[q] = m;
         float t = __int_as_float(0x7f800000);  // +inf: everything passes until k rows are known
-        if (mcount >= a.k) t = __uint_as_float(bits_from_okey((uint32_t)(mine[a.k - 1] >> 32))) + TC_MARGIN;
+        if (m >= k) t = __uint_as_float(bits_from_okey((uint32_t)(C[k - 1] >> 32))) + (RESCORE ? TC_MARGIN : 0.f);
         a.thr[q] = t;
     }
 }
