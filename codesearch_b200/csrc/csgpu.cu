@@ -40,7 +40,8 @@ void count_launch(uint64_t n) { g_kernel_launches.fetch_add(n, std::memory_order
 // ---------------------------------------------------------------------------------------
 constexpr uint32_t MAX_GRID = 148 * 4;   // upper bound on persistent grid size we ever launch
 constexpr uint32_t MAX_BATCH = 16;       // queries per multi-query scan
-constexpr uint32_t PREFILTER_MIN_BATCH = 9;   // tensor prefilter on: batches beyond one multi-query pass (8) go to the tensor cores
+constexpr uint32_t PREFILTER_MIN_BATCH = 2;   // tensor prefilter on: every batch goes to the tensor cores (9 queries: 1.56 ms vs two
+                                              // multi-query passes at 3 ms each; it reads the 2-byte shadow, not the 4-byte rows)
 constexpr uint32_t GEMM_MIN_BATCH = 40;  // csgpu_search_batch switches to the SIMT GEMM path from here
 
 static int ctx_create(const csgpu_index *ix, Shard *sh, SearchCtx **out)

@@ -45,7 +45,8 @@ def _assert_batch_equals_single(st, qs, k):
     (50_000, 128, 64, 33),
     (30_000, 320, 40, 200),      # dim4 = 80: predicated lanes (not a multiple of 32 float4)
     (30_000, 512, 17, 1000),
-    (5_000, 64, 9, 10),          # smallest batch routed to the tensor cores
+    (5_000, 64, 9, 10),
+    (5_000, 64, 2, 10),          # smallest batch routed to the tensor cores
     (300, 384, 50, 500),         # k > rows
 ])
 def test_prefilter_bit_identical_to_single_query(cs, oracle, n, d, b, k):
