@@ -13,8 +13,9 @@ kill $SMI
 timeout 600 python bench.py --impl reference --steps 20 --warmup 3 2>&1 | grep '^{' > $O/${R}_bench_reference.json; cat $O/${R}_bench_reference.json
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${R}_launches_bench_n1.csv python bench.py --steps 20 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:scan_topk -s 5 -c 2 -o $O/${R}_scan_k10 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2>&1
-( timeout 300 python tools/bench_batch.py --dtype fp32 --cases 1:10,8:10,9:200,8:100,16:100,64:100,128:100,1024:100,1024:10 --reps 4; timeout 300 python tools/bench_batch.py --dtype bf16 --cases 1:10,128:100,1024:100,1024:10 --reps 4 --recall ) > $O/${R}_bench_batch.txt 2>&1; cat $O/${R}_bench_batch.txt
+( timeout 300 python tools/bench_batch.py --dtype fp32 --cases 1:10,8:10,9:200,8:100,16:100,64:100,128:100,1024:100,1024:10 --reps 4; timeout 300 python tools/bench_batch.py --dtype bf16 --cases 1:10,128:100,1024:100,1024:10 --reps 4 --recall; timeout 300 python tools/bench_batch.py --dtype fp32 --prefilter --cases 9:200,64:100,128:100,1024:100,1024:10 --reps 6 ) > $O/${R}_bench_batch.txt 2>&1; cat $O/${R}_bench_batch.txt
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm_simt -s 4 -c 1 -o $O/${R}_simt_main python tools/bench_batch.py --dtype fp32 --cases 1024:100 --reps 1 > /dev/null 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm_topk_kernel -s 4 -c 1 -o $O/${R}_bf16_main python tools/bench_batch.py --dtype bf16 --cases 1024:100 --reps 1 > /dev/null 2>&1
-( timeout 300 python tools/bench_single.py --dim 384 --rows 10000000 --ks 10,100,200,1000 --densities 1.0,0.25,0.01; timeout 300 python tools/bench_single.py --dim 768 --rows 5000000 --ks 10,200 --densities 1.0,0.25,0.01 ) > $O/${R}_bench_single_k_filter.txt 2>&1; cat $O/${R}_bench_single_k_filter.txt
+( timeout 300 python tools/bench_single.py --dim 384 --rows 10000000 --ks 10,100,200,1000 --densities 1.0,0.25,0.01; timeout 300 python tools/bench_single.py --dim 768 --rows 5000000 --ks 10,200 --densities 1.0,0.25,0.01; timeout 300 python tools/bench_hybrid.py ) > $O/${R}_bench_single_k_filter.txt 2>&1; cat $O/${R}_bench_single_k_filter.txt
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:select_sorted -s 3 -c 1 -o $O/${R}_select_rescore python tools/bench_batch.py --dtype fp32 --prefilter --cases 1024:100 --reps 1 > /dev/null 2>&1
 ls -la $O | tail -20
