@@ -42,7 +42,7 @@ constexpr uint32_t MAX_GRID = 148 * 4;   // upper bound on persistent grid size 
 constexpr uint32_t MAX_BATCH = 16;       // queries per multi-query scan
 constexpr uint32_t PREFILTER_MIN_BATCH = 2;   // tensor prefilter on: every batch goes to the tensor cores (9 queries: 1.56 ms vs two
                                               // multi-query passes at 3 ms each; it reads the 2-byte shadow, not the 4-byte rows)
-constexpr uint32_t GEMM_MIN_BATCH = 40;  // csgpu_search_batch switches to the SIMT GEMM path from here
+constexpr uint32_t GEMM_MIN_BATCH = 48;  // csgpu_search_batch switches to the SIMT GEMM path from here
 
 static int ctx_create(const csgpu_index *ix, Shard *sh, SearchCtx **out)
 {
@@ -216,7 +216,7 @@ static int enqueue_scan_multi(const csgpu_index *ix, const Shard *sh, SearchCtx 
     a.q = q_dev;
     a.nq = nq;
     a.k = k;
-    a.kpad = pow2_at_least(k, 32);
+    a.kpad = k > 32 ? ctabuf_cap(k) : 32;   // k > 32: capacity of the per-(CTA, query) candidate buffer
     a.bitmap = nullptr;
     a.n_bits = 0;
     a.zero_ids = with_zero_ids ? ix->zero_ids_dev : nullptr;
@@ -1097,7 +1097,8 @@ int csgpu_search_batch(const csgpu_index *ix, const float *q, uint32_t q_len, ui
     if (k == 0 || b == 0) return CSGPU_OK;
     if (ix->dtype == CSGPU_DTYPE_BF16) return batch_search(ix, q, b, k, out_ids, out_dist, out_n, nullptr);
     // large batches: register-tiled fp32 SIMT GEMM + fused threshold filter (gemm_simt.cuh). It pads to 128-query
-    // blocks, so below ~40 queries the HBM-bound multi-query scan (8 queries per pass) is faster.
+    // blocks (20.5 ms per block at 10M x 384), so below 48 queries the HBM-bound multi-query scan (8 queries per
+    // 3.2 ms pass at k = 100) is faster.
     const bool prefilter = ix->tensor_prefilter && ix->shards.size() == 1 && ix->shards[0]->shadow_valid;
     if ((b >= GEMM_MIN_BATCH || (prefilter && b >= PREFILTER_MIN_BATCH)) && batch_gemm_available(ix)) {
         std::vector<uint32_t> zero_q;

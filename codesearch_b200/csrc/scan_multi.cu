@@ -22,16 +22,24 @@ static cudaError_t launch_one(const MultiArgs &a, uint32_t grid, cudaStream_t st
     return cudaGetLastError();
 }
 
+// k > 32: one CTA-shared candidate buffer per query (a.kpad = its capacity)
+template <int V, int R>
+static cudaError_t launch_cta(const MultiArgs &a, uint32_t grid, cudaStream_t st)
+{
+    auto kern = scan_multi_cta_topk_kernel<V, R, MQ>;
+    const size_t smem = (size_t)MQ * a.dim4 * sizeof(float4) + (size_t)MQ * a.kpad * sizeof(uint64_t);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, SCAN_THREADS, smem, st>>>(a);
+    g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
 template <int V, int R>
 static cudaError_t launch_e(const MultiArgs &a, uint32_t grid, cudaStream_t st)
 {
-    switch (a.kpad / 32) {
-        case 1: return launch_one<V, R, 1>(a, grid, st);
-        case 2: return launch_one<V, R, 2>(a, grid, st);
-        case 4: return launch_one<V, R, 4>(a, grid, st);
-        case 8: return launch_one<V, R, 8>(a, grid, st);
-        default: return cudaErrorInvalidValue;
-    }
+    if (a.k > 32) return launch_cta<V, R>(a, grid, st);
+    return launch_one<V, R, 1>(a, grid, st);
 }
 
 bool multi_scan_supported(uint32_t dim4, uint32_t k)
@@ -43,7 +51,7 @@ bool multi_scan_supported(uint32_t dim4, uint32_t k)
 
 uint32_t multi_scan_max_queries() { return MQ; }
 
-uint32_t multi_scan_ctas_per_sm(uint32_t kpad) { return (kpad / 32 <= 4) ? 2 : 1; }
+uint32_t multi_scan_ctas_per_sm(uint32_t) { return 2; }
 
 cudaError_t launch_scan_multi(const MultiArgs &a, uint32_t grid, cudaStream_t st)
 {

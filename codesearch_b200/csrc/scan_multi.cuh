@@ -302,4 +302,182 @@ __global__ void __launch_bounds__(SCAN_THREADS, (E <= 4) ? 2 : 1) scan_multi_top
     if (threadIdx.x == 0) *a.ticket = 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// 32 < k <= 256: the same pass with ONE candidate buffer per (CTA, query) — the CtaBuf of topk.cuh, as the
+// single-query kernel uses for big k — instead of a sorted list per (warp, query). A (row, query) result that beats
+// its query's threshold is appended by the lane that owns it with one shared-memory atomic (no warp-serialised
+// insertion, no per-warp merges: 8 queries x k = 100 cost 4.0 ms per pass with the per-warp lists, of which 1.3 ms
+// was selection); every 8 iterations the CTA checks whether a buffer is within `slack` of full and, if so, sorts it,
+// keeps the best k and tightens the threshold. a.kpad = capacity of one buffer (ctabuf_cap(k)).
+// smem: queries [MQ][dim4] float4 | buffers [MQ][cap] keys.
+template <int V, int R, int MQ>
+__global__ void __launch_bounds__(SCAN_THREADS, 2) scan_multi_cta_topk_kernel(const MultiArgs a)
+{
+    constexpr bool EXACT = true;
+    constexpr int NV = R * MQ;
+    constexpr int SH = (NV == 32) ? 0 : (NV == 16 ? 1 : 2);
+    static_assert(NV == 32 || NV == 16 || NV == 8, "R*MQ must be 8, 16 or 32");
+    constexpr uint32_t SLACK = 8 * R * SCAN_WARPS;   // most keys one query can receive between two sync points
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ bool is_last;
+    __shared__ unsigned cnt_s[MQ];
+    __shared__ uint64_t thr_s[MQ];
+    __shared__ float qflag[MQ];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t dim4 = a.dim4, cap = a.kpad, k = a.k;
+    float4 *qs = reinterpret_cast<float4 *>(smem_raw);
+    uint64_t *bufs = reinterpret_cast<uint64_t *>(smem_raw + (size_t)MQ * dim4 * sizeof(float4));
+
+    for (int b = warp; b < MQ; b += SCAN_WARPS) {   // queries -> smem, unit-normalised exactly as scan.cuh does it
+        float4 t[V];
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const uint32_t c = lane + 32 * j;
+            if ((uint32_t)b < a.nq && (EXACT || c < dim4)) t[j] = reinterpret_cast<const float4 *>(a.q)[(size_t)b * dim4 + c];
+            else t[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            ss = fmaf(t[j].x, t[j].x, ss); ss = fmaf(t[j].y, t[j].y, ss);
+            ss = fmaf(t[j].z, t[j].z, ss); ss = fmaf(t[j].w, t[j].w, ss);
+        }
+        ss = warp_sum_tree(ss);
+        const bool qzero = !(ss > 0.f);
+        const float qinv = qzero ? 0.f : 1.0f / sqrtf(ss);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const uint32_t c = lane + 32 * j;
+            if (EXACT || c < dim4) qs[(size_t)b * dim4 + c] = make_float4(t[j].x * qinv, t[j].y * qinv, t[j].z * qinv, t[j].w * qinv);
+        }
+        if (lane == 0) qflag[b] = qzero ? 1.f : 0.f;
+    }
+    if (threadIdx.x < MQ) { cnt_s[threadIdx.x] = 0; thr_s[threadIdx.x] = KEY_EMPTY; }
+    __syncthreads();
+
+    const int own = lane >> SH;
+    const bool owner = (lane & ((1 << SH) - 1)) == 0;
+    const int my_b = own % MQ, my_r = own / MQ;
+    const bool my_active = owner && (uint32_t)my_b < a.nq;
+    const bool my_qzero = qflag[my_b] != 0.f;
+    uint64_t thr = my_active ? KEY_EMPTY : 0ull;
+    uint64_t *my_buf = bufs + (size_t)my_b * cap;
+
+    // CTA-uniform: compact every buffer that could overflow before the next sync point, refresh the thresholds
+    auto sync_point = [&]() {
+        bool maybe = false;
+#pragma unroll
+        for (int b = 0; b < MQ; ++b) maybe |= *reinterpret_cast<volatile unsigned *>(&cnt_s[b]) + SLACK > cap;
+        if (__syncthreads_or(maybe)) {   // nobody appends while the CTA is in here, so the counts are stable
+            for (int b = 0; b < MQ; ++b)
+                if (*reinterpret_cast<volatile unsigned *>(&cnt_s[b]) + SLACK > cap)
+                    cta_buf_compact(bufs + (size_t)b * cap, &cnt_s[b], &thr_s[b], cap, k);
+        }
+        if (my_active) thr = *reinterpret_cast<volatile uint64_t *>(&thr_s[my_b]);
+    };
+
+    const uint64_t n = a.n_rows;
+    const uint64_t gw = (uint64_t)blockIdx.x * SCAN_WARPS + warp;
+    const uint64_t n_warps = (uint64_t)gridDim.x * SCAN_WARPS;
+    const uint64_t n_groups = (n + R - 1) / R, g_first = (uint64_t)blockIdx.x * SCAN_WARPS;
+    const uint64_t n_iters = g_first < n_groups ? (n_groups - g_first + n_warps - 1) / n_warps : 0;   // same for every warp of the CTA
+    for (uint64_t it = 0; it < n_iters; ++it) {
+        const uint64_t base = (gw + it * n_warps) * R;
+        float4 x[R][V];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint64_t row = base + r;
+            const float4 *p = a.rows + row * dim4 + lane;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                if (row < n && (EXACT || lane + 32 * j < dim4)) x[r][j] = ldg_stream<0>(p + 32 * j);
+                else x[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+#pragma unroll
+            for (int b = 0; b < MQ; ++b) {
+                float4 qq = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (EXACT || lane + 32 * j < dim4) qq = qs[(size_t)b * dim4 + lane + 32 * j];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    float acc = v[r * MQ + b];
+                    acc = fmaf(x[r][j].x, qq.x, acc); acc = fmaf(x[r][j].y, qq.y, acc);
+                    acc = fmaf(x[r][j].z, qq.z, acc); acc = fmaf(x[r][j].w, qq.w, acc);
+                    v[r * MQ + b] = acc;
+                }
+            }
+        }
+        butterfly_level<NV, 16>(v, lane);
+        butterfly_level<(NV / 2 > 0 ? NV / 2 : 1), 8>(v, lane);
+        butterfly_level<(NV / 4 > 0 ? NV / 4 : 1), 4>(v, lane);
+        butterfly_level<(NV / 8 > 0 ? NV / 8 : 1), 2>(v, lane);
+        butterfly_level<(NV / 16 > 0 ? NV / 16 : 1), 1>(v, lane);
+        const float dist = my_qzero ? 0.f : fmaf(-0.5f, v[0], 0.5f);
+        const uint64_t row = base + my_r;
+        if (my_active && row < n && okey(dist) <= (uint32_t)(thr >> 32)) {
+            const uint32_t id = a.ids[row];
+            const uint64_t kk = make_key(dist, id);
+            if (kk < thr && id_allowed(a.bitmap, a.n_bits, id)) my_buf[atomicAdd(&cnt_s[my_b], 1u)] = kk;
+        }
+        if ((it & 7) == 7) sync_point();
+    }
+
+    // ---- per query: CTA top-k -> cand[b][cta][k] ----
+    for (int b = 0; b < (int)a.nq; ++b) {
+        cta_buf_compact(bufs + (size_t)b * cap, &cnt_s[b], &thr_s[b], cap, k);
+        uint64_t *dst = a.cand + ((size_t)b * gridDim.x + blockIdx.x) * k;
+        for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) dst[j] = bufs[(size_t)b * cap + j];
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(a.ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+
+    // ---- last CTA: merge across CTAs, column-wise over the sorted per-CTA lists (see scan.cuh) ----
+    const uint32_t L = gridDim.x;
+    const uint64_t total = (uint64_t)L * k;
+    for (int b = 0; b < (int)a.nq; ++b) {
+        uint64_t *buf = bufs + (size_t)b * cap;
+        const volatile uint64_t *cand = a.cand + (size_t)b * total;
+        if (threadIdx.x == 0) { cnt_s[b] = 0; thr_s[b] = KEY_EMPTY; }
+        __syncthreads();
+        volatile uint64_t *thr_b = &thr_s[b];
+        for (uint32_t j = 0; j < k; ++j) {
+            bool passed = false;
+            for (uint32_t c = threadIdx.x; c < L; c += blockDim.x) {
+                const uint64_t key = cand[(size_t)c * k + j];
+                if (key < *thr_b) { buf[atomicAdd(&cnt_s[b], 1u)] = key; passed = true; }
+            }
+            if (!__syncthreads_or(passed)) break;
+            const unsigned cnt = *reinterpret_cast<volatile unsigned *>(&cnt_s[b]);
+            const bool need = cnt + L > cap || (*thr_b == KEY_EMPTY && cnt >= k);
+            if (__syncthreads_or(need)) cta_buf_compact(buf, &cnt_s[b], thr_b, cap, k);
+        }
+        uint32_t found = 0;   // zero-norm rows: distance 0.0, ascending id; the first k allowed ones suffice
+        for (uint32_t o = 0; o < a.n_zero && found < k; o += blockDim.x) {
+            uint64_t key = KEY_EMPTY;
+            if (o + threadIdx.x < a.n_zero) {
+                const uint32_t id = a.zero_ids[o + threadIdx.x];
+                if (id_allowed(a.bitmap, a.n_bits, id)) key = make_key(0.f, id);
+            }
+            found += __syncthreads_count(key != KEY_EMPTY);
+            if (key < *thr_b) buf[atomicAdd(&cnt_s[b], 1u)] = key;
+            if (__syncthreads_or(*reinterpret_cast<volatile unsigned *>(&cnt_s[b]) + blockDim.x > cap))
+                cta_buf_compact(buf, &cnt_s[b], thr_b, cap, k);
+        }
+        cta_buf_compact(buf, &cnt_s[b], thr_b, cap, k);
+        for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) a.out_keys[(size_t)b * k + j] = buf[j];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *a.ticket = 0;
+}
+
+
 }  // namespace csgpu
