@@ -6,6 +6,8 @@ row-sharded over N GPUs (one rank per GPU, fused exchange), fed into a host RRF 
   torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/bench_hybrid.py
 
 Per GPU: rows-per-gpu x 768 fp32 synthetic rows with synthetic tags (file_id = row / 37, lang_id = fmix32(file_id) % 23).
+Rows are dealt to the ranks in blocks of 1024 files (37,888 rows) round-robin, so that a path-prefix-like filter (a
+contiguous file range) loads every GPU equally instead of landing on one contiguous row shard.
 The filter is the device-side row-tag predicate (csgpu_search_tagged_keys_device): "lang in S and file_id in range",
 chosen to hit the target densities. Masked rows are never read, so two byte counts are reported:
 dense (N x D x 4 + 4 B tag per row) and effective (passing rows x D x 4 + 4 B tag per row).
@@ -40,9 +42,13 @@ if world > 1:
 lib = _lib.load()
 n, d, k = args.rows_per_gpu, args.dim, args.k
 N = n * world
+BLOCK = 37 * 1024                                     # rows per block = 1024 whole files
+n_blocks = (N + BLOCK - 1) // BLOCK
+my_blocks = [b for b in range(n_blocks) if b % world == rank]
 st = cs.VectorStore.new(None, d, devices=[local])
-st.reserve(n)
-st.append_synthetic(1234, rank * n, n, 0, tagged=True)
+st.reserve(sum(min(BLOCK, N - b * BLOCK) for b in my_blocks))
+for b in my_blocks:
+    st.append_synthetic(1234, b * BLOCK, min(BLOCK, N - b * BLOCK), 0, tagged=True)   # chunk id = global row index
 st.build_index()
 searcher = ShardedSearcher(st, exchange=args.exchange)
 qs = np.empty((64, d), np.float32)
@@ -77,10 +83,13 @@ for dens in (float(x) for x in args.densities.split(",")):
         lang_mask, file_hi = (1 << n_lang) - 1, max(1, int(frac_files * n_files))
         pred = _lib.Predicate(lang_mask, 0, file_hi - 1, 0, None, 0)
     # passing rows of this rank (host, numpy — not timed)
-    files = np.arange(rank * n // 37, (rank * n + n - 1) // 37 + 1, dtype=np.uint64)
-    f_ok = ((np.uint64(lang_mask) >> (fmix32(files.astype(np.uint32)) % np.uint32(23)).astype(np.uint64)) & np.uint64(1)).astype(bool) & (files < file_hi)
-    lo = np.maximum(files * 37, rank * n); hi = np.minimum(files * 37 + 37, rank * n + n)
-    passing = int(((hi - lo) * f_ok).sum())
+    passing = 0
+    for b in my_blocks:
+        r0, r1 = b * BLOCK, min(N, (b + 1) * BLOCK)
+        files = np.arange(r0 // 37, (r1 - 1) // 37 + 1, dtype=np.uint64)
+        f_ok = ((np.uint64(lang_mask) >> (fmix32(files.astype(np.uint32)) % np.uint32(23)).astype(np.uint64)) & np.uint64(1)).astype(bool) & (files < file_hi)
+        lo = np.maximum(files * 37, r0); hi = np.minimum(files * 37 + 37, r1)
+        passing += int(((hi - lo) * f_ok).sum())
     dev_ms, e2e_ms = [], []
     for i in range(args.reps + 3):
         q = qs[i % 64]
