@@ -707,7 +707,6 @@ int csgpu_create(csgpu_index **out, uint32_t dim, uint32_t dtype, const int32_t 
     if (((dim + 3) / 4 + 31) / 32 > 8) return fail(CSGPU_ERR_ARG, "dim > 1024 is not supported by the scan kernels yet");
     if (dtype != CSGPU_DTYPE_F32 && dtype != CSGPU_DTYPE_BF16) return fail(CSGPU_ERR_ARG, "dtype must be CSGPU_DTYPE_F32 or CSGPU_DTYPE_BF16");
     if (dtype == CSGPU_DTYPE_BF16 && !bf16_dim_supported(dim)) return fail(CSGPU_ERR_ARG, "bf16 index needs dim % 64 == 0 and 64 <= dim <= 512");
-    if (dtype == CSGPU_DTYPE_BF16 && n_devices > 1) return fail(CSGPU_ERR_ARG, "bf16 index: multi-device sharding is not implemented yet");
     if (n_devices == 0) n_devices = 1;
     if (n_devices > 8) return fail(CSGPU_ERR_ARG, "n_devices must be <= 8");
     int count = 0;
@@ -1099,7 +1098,8 @@ int csgpu_search_batch(const csgpu_index *ix, const float *q, uint32_t q_len, ui
     // large batches: register-tiled fp32 SIMT GEMM + fused threshold filter (gemm_simt.cuh). It pads to 128-query
     // blocks (20.5 ms per block at 10M x 384), so below 48 queries the HBM-bound multi-query scan (8 queries per
     // 3.2 ms pass at k = 100) is faster.
-    const bool prefilter = ix->tensor_prefilter && ix->shards.size() == 1 && ix->shards[0]->shadow_valid;
+    bool prefilter = ix->tensor_prefilter;
+    for (const Shard *sh : ix->shards) prefilter = prefilter && (sh->shadow_valid || sh->n_built == 0);
     if ((b >= GEMM_MIN_BATCH || (prefilter && b >= PREFILTER_MIN_BATCH)) && batch_gemm_available(ix)) {
         std::vector<uint32_t> zero_q;
         rc = batch_search(ix, q, b, k, out_ids, out_dist, out_n, &zero_q);
@@ -1135,7 +1135,6 @@ int csgpu_set_tensor_prefilter(csgpu_index *ix, uint32_t enabled)
 {
     if (!ix) return fail(CSGPU_ERR_ARG, "null index");
     if (ix->dtype != CSGPU_DTYPE_F32) return fail(CSGPU_ERR_ARG, "the tensor prefilter belongs to an fp32 index (a bf16 index is already on the tensor cores)");
-    if (ix->shards.size() != 1) return fail(CSGPU_ERR_ARG, "tensor prefilter: multi-device index is not implemented yet");
     if (enabled && !bf16_dim_supported(ix->dim)) return fail(CSGPU_ERR_ARG, "tensor prefilter needs dim % 64 == 0 and 64 <= dim <= 512");
     ix->tensor_prefilter = enabled != 0;
     if (ix->built)

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <thread>
 
 #include "index.h"
 #include "gemm_simt.cuh"
@@ -370,8 +371,9 @@ static int launch_select(const csgpu_index *ix, Shard *sh, BatchCtx *c, uint32_t
     sa.seg_count = lay.n_seg ? c->seg_count : nullptr;
     sa.stride = lay.stride; sa.surv = GT_SURV; sa.seg_len = lay.seg_len; sa.n_seg = lay.n_seg;
     sa.overflow = c->scalar; sa.thr = c->thr; sa.ids = sh->ids; sa.flags = c->flags; sa.k = k; sa.n_active = nq;
-    sa.zero_ids = final ? ix->zero_ids_dev : nullptr;
-    sa.n_zero = final ? (uint32_t)ix->zero_ids.size() : 0;
+    const bool inject_zero = final && sh == ix->shards[0];   // the zero-norm id list lives on (and is injected by) shard 0 only
+    sa.zero_ids = inject_zero ? ix->zero_ids_dev : nullptr;
+    sa.n_zero = inject_zero ? (uint32_t)ix->zero_ids.size() : 0;
     sa.final_out = final ? c->out : nullptr;
     sa.rows = reinterpret_cast<const float4 *>(sh->rows); sa.dim4 = ix->dim4; sa.q_raw = c->q_f32;
     sa.n_rescored = reinterpret_cast<unsigned long long *>(c->scalar + 2);
@@ -505,51 +507,97 @@ static int batch_search_shard(const csgpu_index *ix, Shard *sh, BatchCtx *c, con
     if (rescore_path(ix, sh)) {
         unsigned long long nres = 0;
         CS_CUDA(cudaMemcpy(&nres, c->scalar + 2, sizeof nres, cudaMemcpyDeviceToHost));
-        ix->prefilter_rescored.store(nres);
+        ix->prefilter_rescored.fetch_add(nres);   // summed over the shards of a multi-device index (reset per chunk by batch_search)
     }
     return CSGPU_OK;
 }
 
 bool batch_gemm_available(const csgpu_index *ix)
 {
-    return ix->shards.size() == 1 && ix->shards[0]->map_valid;
+    for (const Shard *sh : ix->shards)
+        if (!sh->map_valid) return false;
+    return !ix->shards.empty();
 }
 
-// b queries through the GEMM-shaped path of a single-shard index. zero_queries (fp32 index only) receives the
-// batch positions of zero-norm queries, whose outputs are left untouched for the caller to fill in.
+// b queries through the GEMM-shaped path. zero_queries (fp32 index only) receives the batch positions of zero-norm
+// queries, whose outputs are left untouched for the caller to fill in.
+// Multi-device index: every shard runs the whole batch against its rows concurrently (one host thread per device:
+// the phase loop reads an overflow flag back at its end), the per-shard [nq][k] lists are gathered on device 0 over
+// NVLink peer copies and merged there by key — the same k-way merge as the single-query path.
 int batch_search(const csgpu_index *ix, const float *q, uint32_t b, uint32_t k,
                  uint32_t *out_ids, float *out_dist, uint32_t *out_n, std::vector<uint32_t> *zero_queries)
 {
-    if (ix->shards.size() != 1) return fail(CSGPU_ERR_ARG, "batched GEMM path: multi-device sharding is not implemented yet");
-    Shard *sh = ix->shards[0];
-    if (!sh->map_valid) return fail(CSGPU_ERR_ARG, "batched GEMM path is unavailable for this index");
-    std::lock_guard<std::mutex> lk(sh->batch_mu);   // one GEMM batch at a time per index
-    BatchCtx *c = nullptr;
-    int rc = batch_ctx(ix, sh, &c);
-    if (rc) return rc;
-    DeviceGuard g(sh->device);
+    const size_t G = ix->shards.size();
+    if (!batch_gemm_available(ix)) return fail(CSGPU_ERR_ARG, "batched GEMM path is unavailable for this index");
+    std::vector<std::unique_lock<std::mutex>> locks;   // one GEMM batch at a time per index; shards are locked in order
+    std::vector<BatchCtx *> ctx(G, nullptr);
+    for (size_t g = 0; g < G; ++g) {
+        locks.emplace_back(ix->shards[g]->batch_mu);
+        int rc = batch_ctx(ix, ix->shards[g], &ctx[g]);
+        if (rc) return rc;
+    }
+    Shard *sh0 = ix->shards[0];
+    BatchCtx *c0 = ctx[0];
+    DeviceGuard g0(sh0->device);
     const uint32_t chunk = BF_MAX_QBLOCKS * GT_BLOCK_M;
     cudaEvent_t e0, e1;
     CS_CUDA(cudaEventCreate(&e0)); CS_CUDA(cudaEventCreate(&e1));
-    CS_CUDA(cudaEventRecord(e0, c->stream));
-    for (uint32_t j = 0; j < b; j += chunk) {
+    CS_CUDA(cudaEventRecord(e0, c0->stream));
+    uint64_t *gather = nullptr;
+    if (G > 1) CS_CUDA(cudaMalloc(&gather, G * (size_t)std::min(chunk, b) * k * sizeof(uint64_t)));
+    int rc = CSGPU_OK;
+    for (uint32_t j = 0; j < b && !rc; j += chunk) {
         const uint32_t nq = std::min(chunk, b - j);
-        const uint8_t *flags = nullptr;
-        rc = batch_search_shard(ix, sh, c, q + (size_t)j * ix->dim, nq, k, &flags);
+        ix->prefilter_rescored.store(0);
+        std::vector<const uint8_t *> flags(G, nullptr);
+        if (G == 1) {
+            rc = batch_search_shard(ix, sh0, c0, q + (size_t)j * ix->dim, nq, k, &flags[0]);
+        } else {
+            std::vector<int> rcs(G, CSGPU_OK);
+            std::vector<std::string> errs(G);
+            std::vector<std::thread> th;
+            for (size_t g = 0; g < G; ++g)
+                th.emplace_back([&, g]() {
+                    rcs[g] = batch_search_shard(ix, ix->shards[g], ctx[g], q + (size_t)j * ix->dim, nq, k, &flags[g]);
+                    if (rcs[g]) errs[g] = csgpu_last_error();   // the error text is thread-local: carry it over
+                });
+            for (auto &t : th) t.join();
+            for (size_t g = 0; g < G && !rc; ++g)
+                if (rcs[g]) rc = fail(rcs[g], errs[g]);
+        }
         if (rc) break;
-        std::vector<uint8_t> zf(flags, flags + nq);   // out_pin is reused for the results below
-        CS_CUDA(cudaMemcpyAsync(c->out_pin, c->out, (size_t)nq * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
-        CS_CUDA(cudaStreamSynchronize(c->stream));
+        std::vector<uint8_t> zf(flags[0], flags[0] + nq);   // out_pin is reused for the results below
+        if (G > 1) {   // every shard's stream is idle here (batch_search_shard ends synchronised)
+            for (size_t g = 0; g < G; ++g)
+                CS_CUDA(cudaMemcpyPeerAsync(gather + g * (size_t)nq * k, sh0->device, ctx[g]->out, ix->shards[g]->device,
+                                            (size_t)nq * k * sizeof(uint64_t), c0->stream));
+            const bool big = k > 32;
+            const uint32_t kpad = big ? pow2_at_least(k, 64) : 32;
+            const size_t smem = big ? (size_t)2 * SCAN_WARPS * kpad * sizeof(uint64_t) : (size_t)SCAN_WARPS * 32 * sizeof(uint64_t);
+            cudaError_t e = cudaSuccess;
+            if (big) {
+                e = cudaFuncSetAttribute(merge_keys_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e == cudaSuccess) merge_keys_kernel<true><<<nq, SCAN_THREADS, smem, c0->stream>>>(gather, (uint32_t)G, k, kpad, c0->out);
+            } else {
+                merge_keys_kernel<false><<<nq, SCAN_THREADS, smem, c0->stream>>>(gather, (uint32_t)G, k, kpad, c0->out);
+            }
+            count_launch();
+            if (e == cudaSuccess) e = cudaGetLastError();
+            if (e != cudaSuccess) { rc = fail_cuda(e, "merge_keys_kernel launch", __FILE__, __LINE__); break; }
+        }
+        CS_CUDA(cudaMemcpyAsync(c0->out_pin, c0->out, (size_t)nq * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, c0->stream));
+        CS_CUDA(cudaStreamSynchronize(c0->stream));
         for (uint32_t i = 0; i < nq; ++i) {
             if (zf[i]) { if (zero_queries) zero_queries->push_back(j + i); continue; }
-            decode_keys(c->out_pin + (size_t)i * k, k, out_ids + (size_t)(j + i) * k, out_dist + (size_t)(j + i) * k, out_n ? out_n + j + i : nullptr);
+            decode_keys(c0->out_pin + (size_t)i * k, k, out_ids + (size_t)(j + i) * k, out_dist + (size_t)(j + i) * k, out_n ? out_n + j + i : nullptr);
         }
     }
-    cudaEventRecord(e1, c->stream);
-    cudaStreamSynchronize(c->stream);
+    cudaEventRecord(e1, c0->stream);
+    cudaStreamSynchronize(c0->stream);
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) ix->last_search_us.store(ms * 1000.f);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(gather);
     return rc;
 }
 

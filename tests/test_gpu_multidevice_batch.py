@@ -1,0 +1,57 @@
+"""In-process multi-device index (csgpu_create with n devices) on the batched paths: every shard contracts the whole
+batch against its rows concurrently, per-shard lists are gathered on device 0 and merged by key. Results must equal the
+single-device index bit for bit (each (query, row) score is position-independent). Needs >= 2 GPUs."""
+import numpy as np
+import pytest
+
+from parity import check_topk
+
+pytestmark = pytest.mark.gpu
+
+MARGIN = 8
+
+
+@pytest.fixture(scope="module")
+def cs():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import codesearch_b200 as m
+    m.load_library()
+    return m
+
+
+def _pair(cs, rows, dtype="fp32", prefilter=False):
+    out = []
+    for devs in ([0], [0, 1]):
+        st = cs.VectorStore.new(None, rows.shape[1], devices=devs, dtype=dtype)
+        st.append_rows(rows, np.arange(rows.shape[0], dtype=np.uint32))
+        if prefilter:
+            st.set_tensor_prefilter(True)
+        st.build_index()
+        out.append(st)
+    return out
+
+
+@pytest.mark.parametrize("mode", ["simt", "prefilter", "bf16"])
+def test_multidevice_batch_equals_single_device(cs, oracle, mode):
+    rng = np.random.default_rng({"simt": 1, "prefilter": 2, "bf16": 3}[mode])
+    n, d, b, k = 60_000, 384, 130, 50
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    rows[[5, 40_000]] = 0.0 if mode != "bf16" else rows[[5, 40_000]]     # zero-norm rows (fp32 index only)
+    one, two = _pair(cs, rows, dtype="bf16" if mode == "bf16" else "fp32", prefilter=mode == "prefilter")
+    assert two.device_stats().n_devices == 2 and min(two.device_stats().rows_per_device[:2]) > 0
+    qs = rng.standard_normal((b, d)).astype(np.float32)
+    a = one.search_batch_ids(qs, k)
+    c = two.search_batch_ids(qs, k)
+    assert np.array_equal(a[2], c[2])
+    assert np.array_equal(a[0], c[0]) and np.array_equal(a[1].view(np.uint32), c[1].view(np.uint32))
+    if mode != "bf16":
+        for j in (0, b - 1):
+            ri, rd, r64 = oracle.np_search(rows, qs[j], k + MARGIN)
+            check_topk(c[0][j], c[1][j], ri, rd, r64, k)
+        gi, gd = two.search_ids(qs[3], k)                                    # single-query path of the 2-device index
+        assert np.array_equal(gi, c[0][3])
+    else:
+        gi, gd = two.search_ids(qs[3], k)                                    # bf16 single query = a batch of one
+        assert np.array_equal(gi, c[0][3]) and np.array_equal(gd, c[1][3])
