@@ -158,8 +158,20 @@ def extras_batch(store, q_host, lib, n, d):
         for j in range(0, b, 128):
             gi, gd = store.search_ids(qs[j], k)
             same = same and np.array_equal(oi[j], gi) and np.array_equal(od[j].view(np.uint32), gd.view(np.uint32))
+        # one query at a time through the same path (csgpu_search_batch with b = 1): reads the 2-byte shadow + ~160 fp32 rows
+        for i in range(3):
+            store.search_batch_ids(qs[i:i + 1], 10)
+        t0 = time.perf_counter()
+        for i in range(50):
+            s_i, s_d, _ = store.search_batch_ids(qs[i:i + 1], 10)
+        dt1 = (time.perf_counter() - t0) / 50
+        gi, gd = store.search_ids(qs[49], 10)
+        same1 = bool(np.array_equal(s_i[0], gi) and np.array_equal(s_d[0].view(np.uint32), gd.view(np.uint32)))
         store.set_tensor_prefilter(False)
-        return {"batch_fp32_tensor_prefilter": {
+        return {"single_query_top10_via_tensor_prefilter": {
+            "workload": f"{n}x{d} fp32 index, one query per call, top-10, csgpu_search_batch(b=1) with the tensor prefilter on",
+            "ms_per_query": round(dt1 * 1e3, 3), "qps": round(1.0 / dt1, 1), "bit_identical_to_single_query_kernel": same1},
+                "batch_fp32_tensor_prefilter": {
             "workload": f"{n}x{d} fp32 index, batch {b} x top-{k} (BASELINE configs[2]), csgpu_search_batch, host buffers",
             "ms_per_batch": round(dt * 1e3, 3), "qps": round(b / dt, 1), "TFLOPs": round(2.0 * n * d * b / dt / 1e12, 1),
             "gpu_launches_per_batch": int(launches),

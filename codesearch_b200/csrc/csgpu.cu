@@ -40,8 +40,9 @@ void count_launch(uint64_t n) { g_kernel_launches.fetch_add(n, std::memory_order
 // ---------------------------------------------------------------------------------------
 constexpr uint32_t MAX_GRID = 148 * 4;   // upper bound on persistent grid size we ever launch
 constexpr uint32_t MAX_BATCH = 16;       // queries per multi-query scan
-constexpr uint32_t PREFILTER_MIN_BATCH = 2;   // tensor prefilter on: every batch goes to the tensor cores (9 queries: 1.56 ms vs two
-                                              // multi-query passes at 3 ms each; it reads the 2-byte shadow, not the 4-byte rows)
+constexpr uint32_t PREFILTER_MIN_BATCH = 1;   // tensor prefilter on: every csgpu_search_batch goes to the tensor cores (9 queries:
+                                              // 1.56 ms vs two multi-query passes at 3 ms each; it reads the 2-byte shadow, not the
+                                              // 4-byte rows). csgpu_search itself always stays on the fp32 scan kernel.
 constexpr uint32_t GEMM_MIN_BATCH = 48;  // csgpu_search_batch switches to the SIMT GEMM path from here
 
 static int ctx_create(const csgpu_index *ix, Shard *sh, SearchCtx **out)
