@@ -88,6 +88,25 @@ def test_prefilter_near_ties_inside_the_margin(cs, oracle):
     assert st.device_stats().prefilter_rescored > 50 * 300     # the margin really let the clusters through
 
 
+def test_prefilter_huge_cluster_takes_the_careful_path(cs, oracle):
+    """Boilerplate-like corpus: 20 000 near-duplicate rows (licence headers, generated code) all inside the bf16 margin of
+    a query. Far more candidates than a segment or the sort buffer holds: the optimistic run raises the overflow flag and
+    the batch is repeated in the careful mode (ranges halved until they fit). Slow, but exact."""
+    rng = np.random.default_rng(17)
+    d, n_dup, n_other = 384, 20_000, 30_000
+    centre = rng.standard_normal(d).astype(np.float32)
+    dup = (centre + 0.02 * rng.standard_normal((n_dup, d))).astype(np.float32)
+    rows = np.concatenate([dup, rng.standard_normal((n_other, d)).astype(np.float32)])
+    rows = rows[rng.permutation(rows.shape[0])]
+    st = _store(cs, rows)
+    qs = np.concatenate([(centre + 0.02 * rng.standard_normal((8, d))), rng.standard_normal((8, d))]).astype(np.float32)
+    for k in (10, 100):
+        oi, od, on = _assert_batch_equals_single(st, qs, k)
+        for j in (0, 12):
+            ri, rd, r64 = oracle.np_search(rows, qs[j], k + 64)
+            check_topk(oi[j, : on[j]], od[j, : on[j]], ri, rd, r64, k)
+
+
 def test_prefilter_zero_norm_rows_and_queries(cs, oracle):
     rng = np.random.default_rng(8)
     n, d = 20_000, 384

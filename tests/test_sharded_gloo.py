@@ -93,3 +93,50 @@ def test_shard_range_partitions_exactly():
             for (f0, c0), (f1, _) in zip(spans, spans[1:]):
                 assert f0 + c0 == f1
             assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+
+
+def _worker_tagged(rank, world, port, n, d, k, ret):
+    """BASELINE configs[4] host logic: rows dealt to the ranks in blocks of whole files round-robin (tools/bench_hybrid.py),
+    a language + file-range predicate applied per shard before the top-k, one all-gather, merge by key."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle as O
+        from codesearch_b200.sharded import allgather_keys
+        O.set_threads(1)
+        block = 37 * 8
+        n_blocks = (n + block - 1) // block
+        mine = [b for b in range(n_blocks) if b % world == rank]
+        ids = np.concatenate([np.arange(b * block, min(n, (b + 1) * block), dtype=np.uint32) for b in mine])
+        rows = np.concatenate([O.synth_rows(1234, b * block, min(block, n - b * block), d) for b in mine])
+        tags = np.concatenate([O.synth_tags(b * block, min(block, n - b * block)) for b in mine])
+        lang_mask, file_lo, file_hi = (1 << 0) | (1 << 3) | (1 << 7) | (1 << 11) | (1 << 20), 5, (n // 37) // 2
+        ok_rows = O.tag_predicate_mask(tags, lang_mask, file_lo, file_hi)
+        q = O.synth_rows(4321, 1, 1, d)[0]
+        li, ld, _ = O.search(rows[ok_rows], q, k, ids=ids[ok_rows]) if ok_rows.any() else (np.zeros(0, np.uint32), np.zeros(0, np.float32), None)
+        local = torch.from_numpy(encode_keys(li, ld, k).view(np.int64))
+        merged = np.sort(allgather_keys(local, world).numpy().view(np.uint64))[:k]
+        all_rows = O.synth_rows(1234, 0, n, d)
+        all_ok = O.tag_predicate_mask(O.synth_tags(0, n), lang_mask, file_lo, file_hi)
+        gi, gd, _ = O.search(all_rows[all_ok], q, k, ids=np.arange(n, dtype=np.uint32)[all_ok])
+        want = encode_keys(gi, gd, k)
+        # balanced: a contiguous file range loads every rank (the point of dealing whole-file blocks round-robin)
+        share = torch.tensor([float(ok_rows.sum())])
+        shares = [torch.zeros(1) for _ in range(world)]
+        dist.all_gather(shares, share)
+        tot = sum(s.item() for s in shares)
+        ret[rank] = bool(np.array_equal(merged, want) and all(s.item() > 0.5 * tot / world for s in shares))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,k", [(2, 6000, 200), (3, 5000, 10)])
+def test_sharded_tagged_filter_gloo(world, n, k):
+    from oracle import oracle as O
+    O.build()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_tagged, args=(world, _free_port(), n, 64, k, ret), nprocs=world, join=True)
+    assert dict(ret) == {r: True for r in range(world)}
