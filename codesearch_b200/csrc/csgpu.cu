@@ -43,7 +43,8 @@ constexpr uint32_t MAX_BATCH = 16;       // queries per multi-query scan
 constexpr uint32_t PREFILTER_MIN_BATCH = 1;   // tensor prefilter on: every csgpu_search_batch goes to the tensor cores (9 queries:
                                               // 1.56 ms vs two multi-query passes at 3 ms each; it reads the 2-byte shadow, not the
                                               // 4-byte rows). csgpu_search itself always stays on the fp32 scan kernel.
-constexpr uint32_t GEMM_MIN_BATCH = 48;  // csgpu_search_batch switches to the SIMT GEMM path from here
+constexpr uint32_t GEMM_MIN_BATCH = 48;
+constexpr uint32_t GEMM_MIN_BATCH_NO_MULTI = 10;  // csgpu_search_batch switches to the SIMT GEMM path from here
 
 static int ctx_create(const csgpu_index *ix, Shard *sh, SearchCtx **out)
 {
@@ -1101,7 +1102,10 @@ int csgpu_search_batch(const csgpu_index *ix, const float *q, uint32_t q_len, ui
     // 3.2 ms pass at k = 100) is faster.
     bool prefilter = ix->tensor_prefilter;
     for (const Shard *sh : ix->shards) prefilter = prefilter && (sh->shadow_valid || sh->n_built == 0);
-    if ((b >= GEMM_MIN_BATCH || (prefilter && b >= PREFILTER_MIN_BATCH)) && batch_gemm_available(ix)) {
+    // where the multi-query scan cannot serve (dim % 128 != 0 or k > 256) the alternative is one 2 ms scan per query,
+    // which a 128-query SIMT block (20 ms) beats from ~10 queries on
+    const uint32_t gemm_min = multi_scan_supported(ix->dim4, k) ? GEMM_MIN_BATCH : GEMM_MIN_BATCH_NO_MULTI;
+    if ((b >= gemm_min || (prefilter && b >= PREFILTER_MIN_BATCH)) && batch_gemm_available(ix)) {
         std::vector<uint32_t> zero_q;
         rc = batch_search(ix, q, b, k, out_ids, out_dist, out_n, &zero_q);
         for (size_t z = 0; z < zero_q.size() && !rc; ++z) {   // zero-norm queries: distance 0.0 everywhere (scan kernel)

@@ -92,6 +92,9 @@ __device__ __forceinline__ unsigned rescore_range(const SelectArgs &a, const flo
             }
             row[r] = (uint32_t)key;
         }
+        uint32_t idv[R];   // chunk ids ride along with the row loads (no dependent load after the reduction)
+#pragma unroll
+        for (int r = 0; r < R; ++r) idv[r] = live[r] ? __ldg(a.ids + row[r]) : 0u;
         float4 x[R][V];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -112,7 +115,7 @@ __device__ __forceinline__ unsigned rescore_range(const SelectArgs &a, const flo
             }
             acc = warp_sum_tree(acc);
             const float dist = fmaf(-0.5f, acc, 0.5f);
-            if (i0 + r < hi && lane == 0) C[i0 + r] = live[r] ? make_key(dist, __ldg(a.ids + row[r])) : KEY_EMPTY;
+            if (i0 + r < hi && lane == 0) C[i0 + r] = live[r] ? make_key(dist, idv[r]) : KEY_EMPTY;
             read_rows += live[r] ? 1u : 0u;
         }
     }
