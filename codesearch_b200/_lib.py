@@ -89,6 +89,8 @@ SIGNATURES = {
     "csgpu_append_synthetic_tagged": (ctypes.c_int, [_vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32]),
     "csgpu_search_keys_device": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, _vp, _vp]),
     "csgpu_merge_keys_device": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp]),
+    "csgpu_merge_keys_batch_device": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp]),
+    "csgpu_encode_keys": (None, [_u32p, _f32p, ctypes.c_uint32, ctypes.c_uint32, _u64p]),
     "csgpu_exchange_create": (ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32, _vp]),
     "csgpu_exchange_connect": (ctypes.c_int, [_vp, _vp]),
     "csgpu_exchange_connect_local": (ctypes.c_int, [_vp, ctypes.POINTER(_vp)]),

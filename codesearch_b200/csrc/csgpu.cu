@@ -1192,6 +1192,26 @@ int csgpu_merge_keys_device(const csgpu_index *ix, const uint64_t *keys_dev, uin
     return enqueue_merge(keys_dev, n_lists, 1, k, out_keys_dev, (cudaStream_t)stream);
 }
 
+int csgpu_merge_keys_batch_device(const csgpu_index *ix, const uint64_t *keys_dev, uint32_t n_lists, uint32_t nq, uint32_t k,
+                                  uint64_t *out_keys_dev, void *stream)
+{
+    if (!ix) return fail(CSGPU_ERR_ARG, "null index");
+    if (!keys_dev || !out_keys_dev) return fail(CSGPU_ERR_ARG, "null device pointer");
+    if (k == 0 || k > CSGPU_MAX_K || n_lists == 0 || nq == 0) return fail(CSGPU_ERR_ARG, "bad k / n_lists / nq");
+    DeviceGuard dg(ix->shards[0]->device);
+    return enqueue_merge(keys_dev, n_lists, nq, k, out_keys_dev, (cudaStream_t)stream);
+}
+
+void csgpu_encode_keys(const uint32_t *ids, const float *dist, uint32_t n, uint32_t k, uint64_t *out_keys)
+{
+    for (uint32_t i = 0; i < k; ++i) {
+        if (i >= n) { out_keys[i] = KEY_EMPTY; continue; }
+        uint32_t bits;
+        memcpy(&bits, &dist[i], sizeof bits);
+        out_keys[i] = ((uint64_t)okey_from_bits(bits) << 32) | ids[i];
+    }
+}
+
 void csgpu_decode_keys(const uint64_t *keys, uint32_t k, uint32_t *out_ids, float *out_dist, uint32_t *out_n)
 {
     decode_keys(keys, k, out_ids, out_dist, out_n);

@@ -120,6 +120,32 @@ class ShardedSearcher:
         return decode_keys(self.out_pin[:k].numpy())
 
 
+    # -- batches: every rank answers the whole batch over its shard (csgpu_search_batch picks the kernel: multi-query
+    #    scan, SIMT GEMM, tcgen05 on a bf16 index or behind the tensor prefilter), ONE all-gather of [b, k] keys, one
+    #    batched merge kernel. Returns (ids [b, k], distances [b, k], n [b]) — identical on every rank.
+    def search_batch(self, queries, k: int):
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        b = q.shape[0]
+        oi, od, on = self.store.search_batch_ids(q, k)
+        keys = np.empty((b, k), dtype=np.uint64)
+        for j in range(b):
+            self.lib.csgpu_encode_keys(oi[j].ctypes.data_as(_lib._u32p), od[j].ctypes.data_as(_lib._f32p), int(on[j]), k,
+                                       keys[j].ctypes.data_as(_lib._u64p))
+        if self.world == 1:
+            return oi[:, :k], od[:, :k], on
+        local = torch.from_numpy(keys.view(np.int64)).to(self.dev)
+        gathered = allgather_keys(local.reshape(-1), self.world, self.group)          # [world][b][k]
+        out = torch.empty(b * k, dtype=torch.int64, device=self.dev)
+        _lib.check(self.lib.csgpu_merge_keys_batch_device(self.store.handle, gathered.data_ptr(), self.world, b, k,
+                                                          out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        merged = out.cpu().numpy().reshape(b, k)
+        ids = np.zeros((b, k), np.uint32); dd = np.zeros((b, k), np.float32); n = np.zeros(b, np.uint32)
+        for j in range(b):
+            i_j, d_j = decode_keys(merged[j])
+            n[j] = len(i_j); ids[j, : n[j]] = i_j; dd[j, : n[j]] = d_j
+        return ids, dd, n
+
+
 def decode_keys(keys_i64: np.ndarray):
     lib = _lib.load()
     keys = np.ascontiguousarray(keys_i64).view(np.uint64)

@@ -212,6 +212,11 @@ int  csgpu_search_keys_device(const csgpu_index *ix, const float *q_dev, uint32_
 int  csgpu_merge_keys_device(const csgpu_index *ix, const uint64_t *keys_dev, uint32_t n_lists,
                              uint32_t k, uint64_t *out_keys_dev /*[k]*/, void *stream);
 
+/* Batched form: keys_dev [n_lists][nq][k] (e.g. the all-gathered per-rank results of csgpu_search_batch, re-encoded
+ * with csgpu_encode_keys) -> out_keys_dev [nq][k], one CTA per query. */
+int  csgpu_merge_keys_batch_device(const csgpu_index *ix, const uint64_t *keys_dev, uint32_t n_lists, uint32_t nq,
+                                   uint32_t k, uint64_t *out_keys_dev /*[nq][k]*/, void *stream);
+
 /* ---- fused cross-GPU exchange: rank-per-GPU sharding without a collective library on the data path.
  * Each rank (one process per GPU) owns a slot block in its HBM that its peers write over NVLink. The scan
  * kernel's last CTA stores the rank's k local keys straight into every peer's block, raises a sequence
@@ -239,6 +244,9 @@ void csgpu_exchange_destroy(csgpu_index *ix);
 int  csgpu_search_tagged_keys_device(const csgpu_index *ix, const float *q_dev, uint32_t k,
                                      const csgpu_predicate_t *pred, uint32_t exchange,
                                      uint64_t *out_keys_dev /*[k]*/, void *stream);
+
+/* Host-side inverse of csgpu_decode_keys: n (<= k) results -> k keys, padded with empty slots. */
+void csgpu_encode_keys(const uint32_t *ids, const float *dist, uint32_t n, uint32_t k, uint64_t *out_keys);
 
 /* Host-side: keys -> (ids, distances); returns the number of non-empty slots in *out_n. */
 void csgpu_decode_keys(const uint64_t *keys, uint32_t k, uint32_t *out_ids, float *out_dist,

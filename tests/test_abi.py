@@ -82,3 +82,19 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dp, f), errors="replace").read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f
+
+
+def test_encode_decode_keys_round_trip():
+    import numpy as np
+    from codesearch_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    ids = rng.integers(0, 2**32, size=37, dtype=np.uint64).astype(np.uint32)
+    dist = np.sort(rng.random(37).astype(np.float32))
+    keys = np.zeros(50, np.uint64)
+    lib.csgpu_encode_keys(ids.ctypes.data_as(_lib._u32p), dist.ctypes.data_as(_lib._f32p), 37, 50, keys.ctypes.data_as(_lib._u64p))
+    assert (keys[37:] == np.uint64(0xFFFFFFFFFFFFFFFF)).all()
+    assert (np.diff(keys[:37].astype(np.float64)) >= 0).all()          # ascending distance <=> ascending key
+    oi = np.zeros(50, np.uint32); od = np.zeros(50, np.float32); n = ctypes.c_uint32()
+    lib.csgpu_decode_keys(keys.ctypes.data_as(_lib._u64p), 50, oi.ctypes.data_as(_lib._u32p), od.ctypes.data_as(_lib._f32p), ctypes.byref(n))
+    assert n.value == 37 and np.array_equal(oi[:37], ids) and np.array_equal(od[:37], dist)

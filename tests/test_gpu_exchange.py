@@ -105,6 +105,54 @@ def _rank_main(rank, world, port, n, d, ks, ret):
     dist.destroy_process_group()
 
 
+def _rank_batch(rank, world, port, n, d, b, k, mode, ret):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import codesearch_b200 as cs
+    from codesearch_b200.sharded import ShardedSearcher, shard_range
+    first, cnt = shard_range(n, rank, world)
+    st = cs.VectorStore.new(None, d, devices=[rank])
+    st.append_synthetic(1234, first, cnt, 0)
+    if mode == "prefilter":
+        st.set_tensor_prefilter(True)
+    st.build_index()
+    s = ShardedSearcher(st, exchange="nccl")
+    from oracle import oracle as O
+    qs = O.synth_rows(4321, 0, b, d)
+    ids, dd, nn = s.search_batch(qs, k)
+    if rank == 0:
+        ret.put((ids.tolist(), dd.tolist(), nn.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode,b", [("scan", 9), ("prefilter", 70)])
+def test_sharded_batch_two_gpus(cs, oracle, mode, b):
+    """Rank-per-GPU batches: local csgpu_search_batch, one all-gather of [b, k] keys, batched merge kernel."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    n, d, k = 200_000, 384, 20
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_rank_batch, args=(r, 2, 29537, n, d, b, k, mode, ret)) for r in range(2)]
+    [p.start() for p in procs]
+    ids, dd, nn = ret.get(timeout=300)
+    [p.join(timeout=120) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    rows = oracle.synth_rows(1234, 0, n, d)
+    qs = oracle.synth_rows(4321, 0, b, d)
+    for j in (0, b // 2, b - 1):
+        oi, od, o64 = oracle.search(rows, qs[j], k + MARGIN)
+        assert nn[j] == k
+        check_topk(np.array(ids[j], np.uint32), np.array(dd[j], np.float32), oi, od, o64, k)
+
+
 def test_fused_exchange_two_gpus(cs, oracle):
     import torch
     if torch.cuda.device_count() < 2:
