@@ -379,7 +379,7 @@ static int launch_select(const csgpu_index *ix, Shard *sh, BatchCtx *c, uint32_t
     sa.n_rescored = reinterpret_cast<unsigned long long *>(c->scalar + 2);
     cudaError_t e = cudaSuccess;
     if (rescore_path(ix, sh)) {   // exact fp32 rescoring of the tensor-core filter's survivors (rescore.cuh)
-        const size_t smem = (size_t)(SEL_BUF + 1024 + 4096) * sizeof(uint64_t);
+        const size_t smem = (size_t)(SEL_BUF + 1024) * sizeof(uint64_t);
         const uint32_t V = (ix->dim4 + 31) / 32;
         const bool exact = ix->dim4 % 32 == 0;
 #define CS_RS(v, ex)                                                                                                         \

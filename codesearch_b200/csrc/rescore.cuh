@@ -39,7 +39,7 @@ constexpr float TC_MARGIN = 2.1e-3f;
 //
 // RESCORE = false (bf16 index, fp32 SIMT kernel): candidate distances are final; swap ids in, one sort, keep k.
 // RESCORE = true  (tensor prefilter): candidate distances are bf16 estimates d_tc. Sort the candidates by d_tc, then
-//   stage A  rescore the best-looking a = max(32, k rounded up to 32) of them from the fp32 rows (exact keys, in place),
+//   stage A  rescore the best-looking a = pow2 >= max(32, k) of them from the fp32 rows (exact keys, in place, then sorted),
 //            T_A = k-th smallest exact key of survivors U stage A  (a valid upper bound of the final k-th best);
 //   stage B  keep rescoring down the sorted list while d_tc - MARGIN <= T_A can still hold (a prefix: the list is
 //            sorted), drop everything behind it unread;
@@ -122,13 +122,13 @@ __device__ __forceinline__ unsigned rescore_range(const SelectArgs &a, const flo
     return read_rows;
 }
 
-// dynamic smem: C[SEL_BUF] | S[1024] | T[4096]   (u64 each; S and T only when RESCORE)
+// dynamic smem: C[SEL_BUF] | S[1024]   (u64 each; S only when RESCORE) — 72 KB, three CTAs per SM
 template <int V, bool EXACT, bool RESCORE>
-__global__ void __launch_bounds__(SCAN_THREADS, 2) select_sorted_kernel(const SelectArgs a)
+__global__ void __launch_bounds__(SCAN_THREADS, 3) select_sorted_kernel(const SelectArgs a)
 {
     extern __shared__ __align__(16) uint64_t smem[];
-    __shared__ unsigned s_n, s_pref[2 * 148 + 8], s_end;
-    uint64_t *C = smem, *S = smem + SEL_BUF, *T = S + 1024;
+    __shared__ unsigned s_n, s_pref[2 * 148 + 8], s_end, s_bound;
+    uint64_t *C = smem, *S = smem + SEL_BUF;
     const uint32_t q = blockIdx.x, k = a.k;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (q >= a.n_active || a.flags[q]) {   // padding rows and zero-norm queries stay inactive
@@ -200,20 +200,34 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) select_sorted_kernel(const Se
         const uint32_t npad = pow2_at_least(n_c, 32);
         for (uint32_t t = n_c + threadIdx.x; t < npad; t += blockDim.x) C[t] = KEY_EMPTY;
         cta_sort(C, npad);
-        // stage A
-        const uint32_t a_end = min(n_c, max(32u, (k + 31u) & ~31u));
+        // stage A: a power of two (so the rescored keys can be sorted in place without touching stage B's part of C)
+        const uint32_t a_pow = pow2_at_least(k, 32);
+        const uint32_t a_end = min(n_c, a_pow);
+        const uint32_t a_pad = n_c < a_pow ? npad : a_pow;      // n_c < a_pow: everything is stage A, C[n_c, npad) is EMPTY
         const uint32_t bound0 = n_s >= k ? (uint32_t)(S[k - 1] >> 32) : 0xFFFFFFFFu;
         unsigned read_rows = rescore_range<V, EXACT>(a, qv, C, 0, a_end, bound0, warp, lane);
+        cta_sort(C, a_pad);   // exact keys ascending, dropped ones (EMPTY) last
+        // T_A = k-th smallest exact key of survivors U stage A: both lists are sorted, so it is the k-th element of their
+        // merge — found by one thread with a binary search over how many of the k come from S
+        if (threadIdx.x == 0) {
+            uint32_t n_a = a_end;
+            while (n_a > 0 && C[n_a - 1] == KEY_EMPTY) --n_a;
+            uint32_t bound = 0xFFFFFFFFu;   // fewer than k exact keys known: no pruning
+            if (n_s + n_a >= k) {
+                uint32_t lo = k > n_a ? k - n_a : 0, hi = min(k, n_s);   // i = number taken from S
+                while (lo < hi) {
+                    const uint32_t i = (lo + hi) >> 1;                    // take i from S, k - i from A
+                    if (S[i] < C[k - i - 1]) lo = i + 1; else hi = i;     // S[i] would also belong to the k smallest
+                }
+                const uint64_t from_s = lo > 0 ? S[lo - 1] : 0ull, from_a = k - lo > 0 ? C[k - lo - 1] : 0ull;
+                bound = (uint32_t)(umax64(from_s, from_a) >> 32);
+            }
+            s_bound = bound;
+            s_end = n_c;
+        }
         __syncthreads();
-        // T_A = k-th smallest exact key of survivors U stage A
-        const uint32_t tpad = pow2_at_least(n_s + a_end, 32);   // <= 1024 + 1024 + 32 -> 4096
-        for (uint32_t t = threadIdx.x; t < tpad; t += blockDim.x)
-            T[t] = t < n_s ? S[t] : (t - n_s < a_end ? C[t - n_s] : KEY_EMPTY);
-        cta_sort(T, tpad);
-        const uint32_t bound_a = (k - 1 < tpad) ? (uint32_t)(T[k - 1] >> 32) : 0xFFFFFFFFu;   // EMPTY -> 0xFFFFFFFF: no pruning
+        const uint32_t bound_a = s_bound;
         // stage B: the sorted prefix that can still beat T_A
-        if (threadIdx.x == 0) s_end = n_c;
-        __syncthreads();
         for (uint32_t t = a_end + threadIdx.x; t < n_c; t += blockDim.x) {
             const float d_tc = __uint_as_float(bits_from_okey((uint32_t)(C[t] >> 32)));
             if (okey(d_tc - TC_MARGIN) > bound_a) atomicMin(&s_end, t);
