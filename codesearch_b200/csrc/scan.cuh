@@ -59,7 +59,7 @@ struct ScanArgs {
 };
 
 // LD selects the load flavour (tuned on B200, see profiles/): 0 = ld.global.nc.L1::no_allocate,
-// 1 = plain ld.global.nc (__ldg), 2 = ld.global.cs (streaming / evict-first).
+// 1 = plain ld.global.nc (__ldg), 2 = ld.global.cs (streaming / evict-first), 3-5 = flavour 0 with L2 hints.
 template <int LD>
 __device__ __forceinline__ float4 ldg_stream(const float4 *p)
 {
@@ -69,8 +69,20 @@ __device__ __forceinline__ float4 ldg_stream(const float4 *p)
                      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     } else if constexpr (LD == 1) {
         v = __ldg(p);
-    } else {
+    } else if constexpr (LD == 2) {
         v = __ldcs(p);
+    } else if constexpr (LD == 3) {   // + 256-byte L2 prefetch granularity
+        asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    } else {   // 4: + evict-first L2 policy (the corpus is streamed once per query); 5: policy + 256-byte prefetch
+        uint64_t pol;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+        if constexpr (LD == 4)
+            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+        else
+            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.L2::256B.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
     }
     return v;
 }
