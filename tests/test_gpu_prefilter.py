@@ -160,3 +160,26 @@ def test_prefilter_rejects_unsupported(cs):
     st = cs.VectorStore.new(None, 384, dtype="bf16")
     with pytest.raises(cs.CsgpuError):
         st.set_tensor_prefilter(True)
+
+
+def test_prefilter_full_size_10m(cs, oracle):
+    """BASELINE configs[2] at full size: 10M x 384 fp32 index + tensor prefilter, 256 queries x top-100 in one batch.
+    Size-independent property: every query's batch result is bit-identical to the single-query scan kernel; two queries
+    are also held to the streaming f64 oracle over the same counter-based corpus."""
+    n, d, b, k = 10_000_000, 384, 256, 100
+    st = cs.VectorStore.new(None, d)
+    st.reserve(n)
+    st.append_synthetic(1234, 0, n)
+    st.set_tensor_prefilter(True)
+    st.build_index()
+    assert st.device_stats().shadow_bytes == n * d * 2
+    qs = oracle.synth_rows(4321, 0, b, d)
+    oi, od, on = st.search_batch_ids(qs, k)
+    assert (on == k).all()
+    for j in range(0, b, 16):
+        gi, gd = st.search_ids(qs[j], k)
+        assert np.array_equal(oi[j], gi) and np.array_equal(od[j].view(np.uint32), gd.view(np.uint32)), j
+    ri, rd, r64, rn = oracle.search_synth(1234, 0, n, d, qs[:2], k + MARGIN)
+    for j in range(2):
+        check_topk(oi[j], od[j], ri[j], rd[j], r64[j], k)
+    assert 100 < st.device_stats().prefilter_rescored / b < 2000      # ~640 fp32 rows read per query, not the corpus
