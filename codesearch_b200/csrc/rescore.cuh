@@ -92,6 +92,7 @@ __device__ __forceinline__ unsigned rescore_range(const SelectArgs &a, const flo
             }
             row[r] = (uint32_t)key;
         }
+        __syncwarp();      // every lane has read C[i0 .. i0+R) before lane 0 overwrites those slots below
         uint32_t idv[R];   // chunk ids ride along with the row loads (no dependent load after the reduction)
 #pragma unroll
         for (int r = 0; r < R; ++r) idv[r] = live[r] ? __ldg(a.ids + row[r]) : 0u;

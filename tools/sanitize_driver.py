@@ -1,0 +1,79 @@
+#!/usr/bin/env python
+"""Small end-to-end exercise of every kernel family, meant to run under compute-sanitizer
+(tools/sanitize.sh: memcheck, racecheck, synccheck). Sizes are tiny: the sanitizer slows kernels 10-100x."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import codesearch_b200 as cs
+from codesearch_b200.tags import TagPredicate, synth_tags
+
+rng = np.random.default_rng(1)
+n, d = 6000, 384
+rows = rng.standard_normal((n, d)).astype(np.float32)
+rows[17] = 0.0
+ids = np.arange(n, dtype=np.uint32)
+tags = synth_tags(0, n)
+
+st = cs.VectorStore.new(None, d)
+st.append_rows(rows, ids, tags)
+st.build_index()
+q = rng.standard_normal(d).astype(np.float32)
+for k in (10, 100, 1000):                                   # single-query scan: register selector, CTA buffer, column merge
+    i, _ = st.search_ids(q, k)
+    assert len(i) == k
+st.search_ids(q, 50, cs.RowFilter.from_mask(rng.random(n) < 0.3))                      # id-bitmap filter
+st.search_tagged_ids(q, 50, TagPredicate(lang_mask=0x3F, file_lo=3, file_hi=120))     # row-tag predicate
+qs = rng.standard_normal((70, d)).astype(np.float32)
+st.search_batch_ids(qs[:8], 10)                             # multi-query scan, per-warp lists
+st.search_batch_ids(qs[:8], 100)                            # multi-query scan, CTA buffers
+st.search_variants_ids(qs[:5], 20)                          # device-side dedup of variants
+st.search_batch_ids(qs, 20)                                 # fp32 SIMT GEMM + select
+st.set_tensor_prefilter(True)
+a = st.search_batch_ids(qs, 20)                             # tcgen05 filter + rescoring select
+for j in (0, 69):
+    gi, gd = st.search_ids(qs[j], 20)
+    assert np.array_equal(a[0][j], gi) and np.array_equal(a[1][j], gd)
+st.delete_chunks(ids[::7])
+st.build_index()                                            # compaction + shadow rebuild
+st.search_batch_ids(qs[:3], 5)
+bf = cs.VectorStore.new(None, d, dtype="bf16")
+bf.append_rows(rows, ids)
+bf.build_index()
+bf.search_batch_ids(qs, 20)                                 # bf16 index on tcgen05
+# fused cross-GPU exchange, three "ranks" on one device (three streams), with and without the tag predicate
+import ctypes
+import torch
+from codesearch_b200 import _lib
+from codesearch_b200.sharded import decode_keys
+lib = _lib.load()
+W, bounds = 3, [0, 1500, 4000, n]
+stores = []
+for a0, b0 in zip(bounds, bounds[1:]):
+    s_ = cs.VectorStore.new(None, d)
+    s_.append_rows(rows[a0:b0], ids[a0:b0], tags[a0:b0])
+    s_.build_index()
+    stores.append(s_)
+for r, s_ in enumerate(stores):
+    h = (ctypes.c_ubyte * 64)()
+    _lib.check(lib.csgpu_exchange_create(s_.handle, W, r, h))
+peers = (ctypes.c_void_p * W)(*[s_.handle for s_ in stores])
+for s_ in stores:
+    _lib.check(lib.csgpu_exchange_connect_local(s_.handle, peers))
+streams = [torch.cuda.Stream() for _ in range(W)]
+qd = torch.from_numpy(q).cuda()
+pred = _lib.Predicate(0xFFFF, 0, 0xFFFFFFFF, 0, None, 0)
+for k, tagged in ((10, False), (100, False), (50, True)):
+    outs = [torch.empty(k, dtype=torch.int64, device="cuda") for _ in range(W)]
+    torch.cuda.synchronize()
+    for r, s_ in enumerate(stores):
+        if tagged:
+            _lib.check(lib.csgpu_search_tagged_keys_device(s_.handle, qd.data_ptr(), k, ctypes.byref(pred), 1, outs[r].data_ptr(), streams[r].cuda_stream))
+        else:
+            _lib.check(lib.csgpu_search_keys_exchange_device(s_.handle, qd.data_ptr(), k, outs[r].data_ptr(), streams[r].cuda_stream))
+    torch.cuda.synchronize()
+    first = decode_keys(outs[0].cpu().numpy())
+    for r in range(1, W):
+        other = decode_keys(outs[r].cpu().numpy())
+        assert np.array_equal(first[0], other[0])
+print("sanitize driver ok")
