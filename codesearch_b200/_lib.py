@@ -44,6 +44,11 @@ class Stats(ctypes.Structure):
         ("coalesced_queries", ctypes.c_uint64),
         ("prefilter_rescored", ctypes.c_uint64),
         ("shadow_bytes", ctypes.c_uint64),
+        ("byte_shadow_bytes", ctypes.c_uint64),
+        ("byte_searches", ctypes.c_uint64),
+        ("byte_fallbacks", ctypes.c_uint64),
+        ("byte_candidates", ctypes.c_uint64),
+        ("byte_rescored", ctypes.c_uint64),
     ]
 
 
@@ -79,6 +84,7 @@ SIGNATURES = {
     "csgpu_search": (ctypes.c_int, [_vp, _f32p, ctypes.c_uint32, ctypes.c_uint32, _u32p, _f32p, _u32p]),
     "csgpu_set_coalescing": (ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32]),
     "csgpu_set_tensor_prefilter": (ctypes.c_int, [_vp, ctypes.c_uint32]),
+    "csgpu_set_byte_prefilter": (ctypes.c_int, [_vp, ctypes.c_uint32]),
     "csgpu_search_batch": (ctypes.c_int, [_vp, _f32p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _u32p, _f32p, _u32p]),
     "csgpu_search_variants": (ctypes.c_int, [_vp, _f32p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _u32p, _f32p, _u32p]),
     "csgpu_search_filtered": (ctypes.c_int, [_vp, _f32p, ctypes.c_uint32, ctypes.c_uint32, _u64p, ctypes.c_uint64, _u32p, _f32p, _u32p]),

@@ -77,6 +77,7 @@ static void ctx_destroy(SearchCtx *c)
     if (c->ev1) cudaEventDestroy(c->ev1);
     cudaFree(c->q_dev); cudaFreeHost(c->q_pin); cudaFree(c->cand); cudaFree(c->gather); cudaFree(c->ticket);
     cudaFree(c->out_dev); cudaFreeHost(c->out_pin); cudaFree(c->bitmap_dev);
+    i8_free_ctx(c);
     delete c;
 }
 
@@ -464,6 +465,9 @@ void decode_keys(const uint64_t *keys, uint32_t k, uint32_t *out_ids, float *out
 static int search_one(const csgpu_index *ix, const float *q, uint32_t k, const uint64_t *bitmap, uint64_t n_bits,
                       uint32_t *out_ids, float *out_dist, uint32_t *out_n, const csgpu_predicate_t *pred = nullptr)
 {
+    // byte prefilter on (csgpu_set_byte_prefilter): the unfiltered query streams the int8 shadow and rescoring makes it
+    // exact (scan_i8.cuh); if that launch reports a case it cannot bound, the query is answered again by the fp32 scan
+    bool use_i8 = bitmap == nullptr && pred == nullptr && i8_eligible(ix, k);
     if (pred) { bitmap = pred->file_bitmap; n_bits = pred->file_bitmap ? pred->n_file_bits : 0; }
     const size_t G = ix->shards.size();
     std::vector<SearchCtx *> ctx(G, nullptr);
@@ -495,7 +499,8 @@ static int search_one(const csgpu_index *ix, const float *q, uint32_t k, const u
             }
             if (g == 0) CS_CUDA(cudaEventRecord(c->ev0, c->stream));
             uint64_t *dst = (G == 1) ? c->out_pin : c->out_dev;
-            int r = enqueue_scan(ix, sh, c, c->q_dev, k, bm_dev, n_bits, /*with_zero_ids=*/g == 0, dst, c->stream, nullptr, 0, pred);
+            int r = use_i8 ? enqueue_scan_i8(ix, sh, c, c->q_dev, k, /*with_zero_ids=*/g == 0, dst, c->stream)
+                           : enqueue_scan(ix, sh, c, c->q_dev, k, bm_dev, n_bits, /*with_zero_ids=*/g == 0, dst, c->stream, nullptr, 0, pred);
             if (r) return r;
         }
         SearchCtx *c0 = ctx[0];
@@ -521,10 +526,24 @@ static int search_one(const csgpu_index *ix, const float *q, uint32_t k, const u
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, c0->ev0, c0->ev1) == cudaSuccess) ix->last_search_us.store(ms * 1000.f);
         }
+        if (use_i8) {
+            bool again = false;
+            uint64_t cand = 0, resc = 0;
+            for (size_t g = 0; g < G; ++g) {
+                again = again || ctx[g]->i8_status[0] != 0;
+                cand += ctx[g]->i8_status[1] & 0xFFFFFFFFull;
+                resc += ctx[g]->i8_status[1] >> 32;
+            }
+            ix->byte_searches.fetch_add(1, std::memory_order_relaxed);
+            ix->byte_candidates.store(cand, std::memory_order_relaxed);
+            ix->byte_rescored.store(resc, std::memory_order_relaxed);
+            if (again) { ix->byte_fallbacks.fetch_add(1, std::memory_order_relaxed); return -1; }
+        }
         decode_keys(c0->out_pin, k, out_ids, out_dist, out_n);
         return CSGPU_OK;
     };
     rc = body();
+    if (rc == -1) { use_i8 = false; rc = body(); }
     if (rc) for (size_t g = 0; g < G; ++g) { DeviceGuard dg(ix->shards[g]->device); cudaStreamSynchronize(ctx[g]->stream); }
     release_all();
     return rc;
@@ -760,6 +779,7 @@ void csgpu_destroy(csgpu_index *ix)
         DeviceGuard dg(sh->device);
         for (SearchCtx *c : sh->all_ctx) ctx_destroy(c);
         batch_free_ctx(sh);
+        i8_free_shard(sh);
         cudaFree(sh->rows_bf16); cudaFree(sh->stage); cudaFree(sh->shadow_bf16);
         cudaFree(sh->rows); cudaFree(sh->ids); cudaFree(sh->status); cudaFree(sh->tags);
         if (sh->stream) cudaStreamDestroy(sh->stream);
@@ -955,6 +975,7 @@ int csgpu_build(csgpu_index *ix)
     int rc = upload_zero_ids(ix);
     if (rc) return rc;
     for (Shard *sh : ix->shards) if ((rc = batch_after_build(ix, sh))) return rc;
+    for (Shard *sh : ix->shards) if ((rc = i8_refresh(ix, sh))) return rc;
     ix->tombstones = 0;
     ix->built = true;
     return CSGPU_OK;
@@ -968,6 +989,7 @@ int csgpu_clear(csgpu_index *ix)
         cudaFree(sh->rows); cudaFree(sh->ids); cudaFree(sh->status); cudaFree(sh->tags);
         cudaFree(sh->rows_bf16); cudaFree(sh->stage); cudaFree(sh->shadow_bf16);
         sh->shadow_bf16 = nullptr; sh->shadow_valid = false; sh->shadow_rows = 0;
+        i8_free_shard(sh);
         sh->rows_bf16 = nullptr; sh->stage = nullptr; sh->stage_cap = 0; sh->map_valid = false;
         sh->rows = nullptr; sh->ids = nullptr; sh->status = nullptr; sh->tags = nullptr;
         sh->n_built = sh->n_total = sh->cap = 0;
@@ -1147,6 +1169,17 @@ int csgpu_set_tensor_prefilter(csgpu_index *ix, uint32_t enabled)
     return CSGPU_OK;
 }
 
+int csgpu_set_byte_prefilter(csgpu_index *ix, uint32_t enabled)
+{
+    if (!ix) return fail(CSGPU_ERR_ARG, "null index");
+    if (ix->dtype != CSGPU_DTYPE_F32) return fail(CSGPU_ERR_ARG, "the byte prefilter belongs to an fp32 index");
+    if (enabled && ix->dim_pad > 1024) return fail(CSGPU_ERR_ARG, "byte prefilter needs dim <= 1024");
+    ix->byte_prefilter = enabled != 0;
+    if (ix->built)
+        for (Shard *sh : ix->shards) { int rc = i8_refresh(ix, sh); if (rc) { ix->byte_prefilter = false; return rc; } }
+    return CSGPU_OK;
+}
+
 int csgpu_search_variants(const csgpu_index *ix, const float *q, uint32_t q_len, uint32_t b, uint32_t k,
                           uint32_t *out_ids, float *out_dist, uint32_t *out_n)
 {
@@ -1223,6 +1256,7 @@ static int load_finish(csgpu_index *ix)
     int rc = upload_zero_ids(ix);
     if (rc) return rc;
     for (Shard *sh : ix->shards) if ((rc = batch_after_build(ix, sh))) return rc;
+    for (Shard *sh : ix->shards) if ((rc = i8_refresh(ix, sh))) return rc;
     ix->tombstones = 0;
     ix->built = true;
     return CSGPU_OK;
@@ -1407,6 +1441,12 @@ int csgpu_stats(const csgpu_index *ix, csgpu_stats_t *out)
     out->prefilter_rescored = ix->prefilter_rescored.load();
     for (const Shard *sh : ix->shards) out->shadow_bytes += sh->shadow_rows * (uint64_t)ix->dim * 2;
     out->bytes_on_device += out->shadow_bytes;
+    for (const Shard *sh : ix->shards) out->byte_shadow_bytes += sh->i8_rows * ((uint64_t)((ix->dim4 + 31) / 32) * 128 + sizeof(uint32_t));
+    out->bytes_on_device += out->byte_shadow_bytes;
+    out->byte_searches = ix->byte_searches.load();
+    out->byte_fallbacks = ix->byte_fallbacks.load();
+    out->byte_candidates = ix->byte_candidates.load();
+    out->byte_rescored = ix->byte_rescored.load();
     return CSGPU_OK;
 }
 

@@ -54,6 +54,8 @@ struct SearchCtx {
     uint64_t *bitmap_dev = nullptr; // filter bitmap staging
     size_t bitmap_cap = 0;          // in u64 words
     size_t cand_cap = 0;            // in keys
+    void *i8_scratch = nullptr;     // byte prefilter (scan_i8.cu): per-warp minima, counters, candidate regions; lazily allocated
+    uint64_t *i8_status = nullptr;  // pinned, device-mapped: [0] fallback flag, [1] statistics of the last launch
 };
 
 // Scratch of the batched GEMM-shaped path (gemm_topk.cu): one per shard, serialised by Shard::batch_mu.
@@ -121,6 +123,10 @@ struct Shard {
     CUtensorMap map_shadow;        // TMA map over the shadow (box = GT_BLOCK_N rows)
     bool shadow_valid = false;
     uint64_t shadow_rows = 0;
+    uint8_t *shadow_i8 = nullptr;  // fp32 index + byte prefilter: int8 image of the built rows, [n_built][128 * ceil(dim/128)] (scan_i8.cuh)
+    uint32_t *meta_i8 = nullptr;   // [n_built] half2(scale, error bound) per row
+    bool i8_valid = false;
+    uint64_t i8_rows = 0;
     BatchCtx *batch = nullptr;
     std::mutex batch_mu;
     float *rows = nullptr;     // [cap, dim_pad] fp32; rows [0, n_built) are unit vectors
@@ -149,6 +155,14 @@ void batch_free_ctx(Shard *sh);
 bool batch_gemm_available(const csgpu_index *ix);
 int batch_search(const csgpu_index *ix, const float *q, uint32_t b, uint32_t k,
                  uint32_t *out_ids, float *out_dist, uint32_t *out_n, std::vector<uint32_t> *zero_queries);
+
+// scan_i8.cu (byte prefilter of the single-query path)
+int i8_refresh(const csgpu_index *ix, Shard *sh);
+void i8_free_shard(Shard *sh);
+void i8_free_ctx(SearchCtx *c);
+bool i8_eligible(const csgpu_index *ix, uint32_t k);
+int enqueue_scan_i8(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const float *q_dev, uint32_t k,
+                    bool with_zero_ids, uint64_t *out_keys, cudaStream_t st);
 
 // snapshot.cu
 int snapshot_save(const csgpu_index *ix, const char *dir);
@@ -180,6 +194,8 @@ struct csgpu_index {
     uint64_t tombstones = 0;
     mutable std::atomic<float> last_search_us{0.f};
     mutable std::atomic<uint64_t> prefilter_rescored{0};   // fp32 rows read by the last tensor-prefilter batch chunk
+    bool byte_prefilter = false;          // csgpu_set_byte_prefilter: csgpu_search streams an int8 shadow + exact fp32 rescoring
+    mutable std::atomic<uint64_t> byte_searches{0}, byte_fallbacks{0}, byte_candidates{0}, byte_rescored{0};
     csgpu::Exchange *xchg = nullptr;      // rank-per-GPU fused exchange (csgpu_exchange_*)
     mutable csgpu::Coalescer coalescer;   // csgpu_set_coalescing
 };

@@ -1,0 +1,138 @@
+// scan_i8.cu — host side of the byte prefilter (scan_i8.cuh): the int8 shadow of a shard's built rows, the
+// per-context scratch, and the launcher. Own translation unit so the library builds in parallel.
+#include <algorithm>
+#include <cstdlib>
+
+#include "index.h"
+#include "scan_i8.cuh"
+
+namespace csgpu {
+
+// below this many rows per shard the fp32 scan is < 60 us and the threshold has too few warps to feed on
+// (CSGPU_I8_MIN_ROWS overrides it: the tests exercise the kernel on small corpora)
+static uint64_t i8_min_rows()
+{
+    static const uint64_t v = [] {
+        const char *e = getenv("CSGPU_I8_MIN_ROWS");
+        return e && *e ? (uint64_t)strtoull(e, nullptr, 10) : (uint64_t)262144;
+    }();
+    return v;
+}
+constexpr uint32_t I8_MAX_GRID = I8_MAX_WARPS / I8_WARPS;
+
+static inline uint32_t i8_lines(uint32_t dim4) { return (dim4 + 31) / 32; }   // 128-byte lines per shadow row (= V)
+
+void i8_free_shard(Shard *sh)
+{
+    DeviceGuard g(sh->device);
+    cudaFree(sh->shadow_i8); cudaFree(sh->meta_i8);
+    sh->shadow_i8 = nullptr; sh->meta_i8 = nullptr; sh->i8_valid = false; sh->i8_rows = 0;
+}
+
+void i8_free_ctx(SearchCtx *c)
+{
+    cudaFree(c->i8_scratch);
+    if (c->i8_status) cudaFreeHost(c->i8_status);
+    c->i8_scratch = nullptr; c->i8_status = nullptr;
+}
+
+// (re)build or drop the int8 shadow of an fp32 shard's built rows (csgpu_set_byte_prefilter)
+int i8_refresh(const csgpu_index *ix, Shard *sh)
+{
+    i8_free_shard(sh);
+    if (!ix->byte_prefilter || ix->dtype != CSGPU_DTYPE_F32 || sh->n_built == 0 || sh->rows == nullptr) return CSGPU_OK;
+    const uint32_t V = i8_lines(ix->dim4);
+    if (V > 8) return fail(CSGPU_ERR_ARG, "byte prefilter needs dim <= 1024");
+    DeviceGuard g(sh->device);
+    const size_t d8 = (size_t)V * 128;
+    cudaError_t e = cudaMalloc(&sh->shadow_i8, sh->n_built * d8);
+    if (e == cudaSuccess) e = cudaMalloc(&sh->meta_i8, sh->n_built * sizeof(uint32_t));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        i8_free_shard(sh);
+        return fail(CSGPU_ERR_OOM, "no room in HBM for the int8 shadow of the fp32 rows (byte prefilter needs +25 %)");
+    }
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((sh->n_built + 7) / 8, (uint64_t)sh->sm_count * 8);
+    shadow_i8_from_rows_kernel<<<grid, 256, 0, sh->stream>>>(reinterpret_cast<const float4 *>(sh->rows),
+                                                            reinterpret_cast<uint32_t *>(sh->shadow_i8), sh->meta_i8, 0, sh->n_built,
+                                                            ix->dim4, (uint32_t)d8);
+    count_launch();
+    CS_CUDA(cudaGetLastError());
+    CS_CUDA(cudaStreamSynchronize(sh->stream));
+    sh->i8_rows = sh->n_built;
+    sh->i8_valid = true;
+    return CSGPU_OK;
+}
+
+bool i8_eligible(const csgpu_index *ix, uint32_t k)
+{
+    if (!ix->byte_prefilter || ix->dtype != CSGPU_DTYPE_F32 || k == 0 || k > I8_MAX_K) return false;
+    for (const Shard *sh : ix->shards)
+        if (!sh->i8_valid || sh->i8_rows != sh->n_built || sh->n_built < i8_min_rows()) return false;
+    return true;
+}
+
+struct I8Scratch {   // one cudaMalloc block per SearchCtx
+    uint32_t warp_min[I8_MAX_WARPS];
+    unsigned counters[8];
+    uint64_t final_list[I8_TAIL_CAP];
+    uint64_t region[(size_t)I8_MAX_GRID * I8_REGION];
+};
+
+template <int V, bool EXACT>
+static cudaError_t launch_i8_v(const I8Args &a, uint32_t grid, cudaStream_t st)
+{
+    constexpr int R = (V <= 2) ? 8 : (V <= 4 ? 4 : 2);
+    auto kern = scan_i8_kernel<V, EXACT, R>;
+    const size_t smem = (size_t)I8_TAIL_CAP * sizeof(uint64_t);
+    kern<<<grid, I8_THREADS, smem, st>>>(a);
+    count_launch();
+    return cudaGetLastError();
+}
+
+int enqueue_scan_i8(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const float *q_dev, uint32_t k,
+                    bool with_zero_ids, uint64_t *out_keys, cudaStream_t st)
+{
+    if (c->i8_scratch == nullptr) {
+        CS_CUDA(cudaMalloc(&c->i8_scratch, sizeof(I8Scratch)));
+        CS_CUDA(cudaMemsetAsync(c->i8_scratch, 0xFF, sizeof(uint32_t) * I8_MAX_WARPS, st));
+        CS_CUDA(cudaMemsetAsync(reinterpret_cast<I8Scratch *>(c->i8_scratch)->counters, 0, sizeof(unsigned) * 8, st));
+        CS_CUDA(cudaHostAlloc(&c->i8_status, 8 * sizeof(uint64_t), cudaHostAllocMapped | cudaHostAllocPortable));
+    }
+    I8Scratch *s = reinterpret_cast<I8Scratch *>(c->i8_scratch);
+    const uint32_t V = i8_lines(ix->dim4);
+    I8Args a;
+    a.shadow = sh->shadow_i8;
+    a.meta = sh->meta_i8;
+    a.rows = reinterpret_cast<const float4 *>(sh->rows);
+    a.ids = sh->ids;
+    a.n_rows = sh->n_built;
+    a.dim4 = ix->dim4;
+    a.d8 = V * 128;
+    a.q = q_dev;
+    a.k = k;
+    a.zero_ids = with_zero_ids ? ix->zero_ids_dev : nullptr;
+    a.n_zero = with_zero_ids ? (uint32_t)ix->zero_ids.size() : 0;
+    a.warp_min = s->warp_min;
+    a.region = s->region;
+    a.final_list = s->final_list;
+    a.counters = s->counters;
+    a.out_keys = out_keys;
+    a.status = c->i8_status;
+    c->i8_status[0] = 1;   // a launch that never runs must not look like a success
+    const uint32_t R = (V <= 2) ? 8 : (V <= 4 ? 4 : 2);
+    const uint64_t want = (sh->n_built + (uint64_t)I8_WARPS * 4 * R - 1) / ((uint64_t)I8_WARPS * 4 * R);
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(std::min<uint64_t>((uint64_t)sh->sm_count * 2, I8_MAX_GRID), std::max<uint64_t>(want, 1));
+    const bool exact = (ix->dim4 % 32) == 0;
+    cudaError_t e;
+#define CS_CASE(v) case v: e = exact ? launch_i8_v<v, true>(a, grid, st) : launch_i8_v<v, false>(a, grid, st); break;
+    switch (V) {
+        CS_CASE(1) CS_CASE(2) CS_CASE(3) CS_CASE(4) CS_CASE(5) CS_CASE(6) CS_CASE(7) CS_CASE(8)
+        default: e = cudaErrorInvalidValue;
+    }
+#undef CS_CASE
+    if (e != cudaSuccess) return fail_cuda(e, "scan_i8_kernel launch", __FILE__, __LINE__);
+    return CSGPU_OK;
+}
+
+}  // namespace csgpu

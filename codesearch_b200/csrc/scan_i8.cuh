@@ -1,0 +1,463 @@
+// scan_i8.cuh — the opt-in "byte prefilter" of an fp32 index (csgpu_set_byte_prefilter): exact fp32 single-query
+// results from ONE pass over a 1-byte-per-element shadow of the corpus instead of the 4-byte rows.
+//
+// Same contract as the tensor prefilter (rescore.cuh), aimed at the single-query path of
+// /root/reference/src/vectordb/store.rs:446-459: the shadow is only a FILTER with a PROVEN per-row error bound; the
+// rows that survive it (a few hundred of 10M) are rescored from the fp32 rows with exactly the arithmetic of
+// scan_topk_kernel (same query normalisation, FMA chain, xor-shuffle tree, distance = fma(-0.5, cos, 0.5)) and the
+// top-k is selected on those exact keys. Ids AND distances are therefore bit-identical to csgpu_search, while the
+// kernel moves dim + 4 bytes per row instead of 4 * dim: the HBM floor drops from 2.14 ms to ~0.55 ms at 10M x 384.
+//
+// Shadow layout (HBM): row r = d8 = 128 * ceil(dim / 128) signed bytes (zero padded), xi = rint(x / s_r) in
+// [-127, 127] with a per-row scale s_r; meta[r] = half2(s_r, e_r), e_r >= ||x - s_r * xi||_2 (computed in f64 at
+// build, rounded UP to half). A row is 3 full 128-byte lines at dim = 384.
+//
+// Error bound. q = the fp32 unit query exactly as scan_topk_kernel holds it; q^ = s_q * qi its int8 image with
+// e_q >= ||q - q^||_2. For a row x with image x^ = s_r * xi:
+//     q.x - q^.x^ = (q - q^).x + q^.(x - x^)        |.| <= e_q ||x|| + ||q^|| e_r  =: M_r           (Cauchy-Schwarz)
+// q^.x^ = s_q s_r * (integer dot product, exact in int32: 1024 * 127^2 < 2^24). Stored rows are unit vectors to
+// within 1e-6 (normalise_rows_kernel), covered by the factor folded into e_q. The scan kernel's own fp32 result differs
+// from the real-number q.x by <= (4V + 5) 2^-24 (its longest FMA/add chain) < 2.3e-6 at V = 8, i.e. 1.2e-6 in
+// distance; I8_SLACK = 3e-6 (distance units) covers that plus the handful of roundings below. Hence for every row
+//     lb_r = d^_r - M_r/2 - SLACK  <=  d_fp32(r)  <=  d^_r + M_r/2 + SLACK = ub_r.
+//
+// Threshold without a global selector. Every streaming warp publishes the smallest ub it has seen (one u32 per warp
+// in HBM/L2). A helper warp per CTA keeps recomputing G = the k-th smallest of those per-warp minima: k DISTINCT rows
+// have d_fp32 <= ub <= G, so a row with lb > G is strictly behind k rows and can never be in the top-k. Because the
+// top-k rows of 10M almost surely sit in k different warps' slices (2368 warps), G converges to the true k-th best ub.
+// Rows with lb <= G are appended to the CTA's candidate region (a burst while G is still +inf, then a trickle); at its
+// end each CTA re-filters its region against the now almost final G and appends the survivors to one global list. The
+// last CTA sorts that list by lb, rescores the best-looking a >= k rows (exact upper bound T_A of the final k-th
+// distance), then only the sorted prefix with lb <= T_A, and selects. One kernel launch per query.
+//
+// Anything the fast path cannot bound — zero-norm query, candidate overflow (adversarial order / massive near-ties) —
+// raises the status word next to the result; the host then answers the query with scan_topk_kernel (still the GPU:
+// there is no CPU fallback). tests/test_gpu_byte_prefilter.py asserts bit-equality with csgpu_search.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "scan.cuh"
+
+namespace csgpu {
+
+constexpr int I8_WARPS = 8;                          // streaming warps; warp I8_WARPS is the helper
+constexpr int I8_THREADS = (I8_WARPS + 1) * 32;
+constexpr uint32_t I8_REGION = 4096;                 // candidate slots per CTA
+constexpr uint32_t I8_TAIL_CAP = 4096;               // keys the last CTA sorts (32 KB of shared memory)
+constexpr uint32_t I8_MAX_K = 128;
+constexpr uint32_t I8_LIST_CAP = I8_TAIL_CAP - I8_MAX_K;   // candidates on the global list (room for the zero-norm ids)
+constexpr uint32_t I8_MAX_WARPS = 148 * 2 * I8_WARPS;   // per-warp minima staged in shared memory by the helper
+constexpr float I8_SLACK = 3e-6f;
+constexpr int I8_SEARCH_BITS = 20;                   // bits of the k-th-smallest search (the rest is rounded up)
+
+struct I8Args {
+    const uint8_t *shadow;      // [n_rows][d8] int8
+    const uint32_t *meta;       // [n_rows] half2: lo = s_r, hi = e_r
+    const float4 *rows;         // [n_rows][dim4] fp32 unit rows (rescoring only)
+    const uint32_t *ids;        // [n_rows]
+    uint64_t n_rows;
+    uint32_t dim4, d8;
+    const float *q;             // [dim4*4] raw query (device)
+    uint32_t k;
+    const uint32_t *zero_ids;
+    uint32_t n_zero;
+    uint32_t *warp_min;         // [gridDim.x * I8_WARPS] okey(ub); 0xFFFFFFFF between launches
+    uint64_t *region;           // [gridDim.x][I8_REGION]
+    uint64_t *final_list;       // [I8_TAIL_CAP]
+    unsigned *counters;         // [0] ticket, [1] final count, [2] overflow flag — all 0 between launches
+    uint64_t *out_keys;         // [k] result keys
+    uint64_t *status;           // [0]: 0 = out_keys valid, 1 = answer with the exact scan instead;
+                                // [1]: (fp32 rows rescored << 32) | candidates on the final list
+};
+
+__device__ __forceinline__ uint4 ldg_stream_u4(const uint8_t *p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ uint32_t pack_i8x4(int a, int b, int c, int d)
+{
+    return (uint32_t)(a & 0xFF) | ((uint32_t)(b & 0xFF) << 8) | ((uint32_t)(c & 0xFF) << 16) | ((uint32_t)(d & 0xFF) << 24);
+}
+
+// k-th smallest (1-based) of vals[0..n4*4) held in shared memory (padded with 0xFFFFFFFF), searched on the top
+// I8_SEARCH_BITS bits and rounded UP (so the result is >= the true k-th smallest: still a valid bound). One warp.
+__device__ __forceinline__ uint32_t warp_kth_smallest(const uint4 *vals4, uint32_t n4, uint32_t k, int lane)
+{
+    uint32_t ans = 0;
+    for (int b = 31; b >= 32 - I8_SEARCH_BITS; --b) {
+        const uint32_t cand = ans | ((1u << b) - 1u);   // bit b clear, everything below set
+        unsigned c = 0;
+        for (uint32_t t = lane; t < n4; t += 32) {
+            const uint4 v = vals4[t];
+            c += (v.x <= cand ? 1u : 0u) + (v.y <= cand ? 1u : 0u) + (v.z <= cand ? 1u : 0u) + (v.w <= cand ? 1u : 0u);
+        }
+        c = __reduce_add_sync(FULL, c);
+        if (c < k) ans |= 1u << b;
+    }
+    return ans | ((1u << (32 - I8_SEARCH_BITS)) - 1u);
+}
+
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// The fp32 query exactly as scan_topk_kernel holds it: lane owns float4 lane + 32 j, scaled by 1/||q||. Returns ss.
+template <int V, bool EXACT>
+__device__ __forceinline__ float load_unit_query(const float *q, uint32_t dim4, float4 (&qv)[V], int lane)
+{
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const uint32_t c = lane + 32 * j;
+        if (EXACT || c < dim4) qv[j] = reinterpret_cast<const float4 *>(q)[c];
+        else qv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ss = fmaf(qv[j].x, qv[j].x, ss); ss = fmaf(qv[j].y, qv[j].y, ss);
+        ss = fmaf(qv[j].z, qv[j].z, ss); ss = fmaf(qv[j].w, qv[j].w, ss);
+    }
+    ss = warp_sum_tree(ss);
+    if (ss > 0.f) {
+        const float qinv = 1.0f / sqrtf(ss);
+#pragma unroll
+        for (int j = 0; j < V; ++j) { qv[j].x *= qinv; qv[j].y *= qinv; qv[j].z *= qinv; qv[j].w *= qinv; }
+    }
+    return ss;
+}
+
+// V = float4 per lane of the fp32 query (ceil(dim4/32)) = 128-byte lines per shadow row; EXACT: dim4 == 32 V;
+// R = 4-row groups in flight per warp iteration (a warp streams 4 R rows = R x V x 512 B at a time).
+template <int V, bool EXACT, int R>
+__global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
+{
+    constexpr int ROWS_PER_ITER = 4 * R;
+    extern __shared__ __align__(16) uint64_t smem[];          // helper: per-warp minima (u32); tail: candidate keys
+    __shared__ unsigned s_cnt, s_done, s_last, s_end, s_bound, s_read;
+    __shared__ volatile uint32_t s_G;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & 7;
+    const uint32_t k = a.k;
+    if (threadIdx.x == 0) { s_cnt = 0; s_done = 0; s_read = 0; s_G = 0xFFFFFFFFu; }
+
+    float s_q, EQ, QN;
+    uint4 qw[V];
+    {
+    // ---- query -> registers, scaled to unit length: scan_topk_kernel's prologue, operation for operation ----
+    float4 qv[V];
+    const float ss = load_unit_query<V, EXACT>(a.q, a.dim4, qv, lane);
+    if (!(ss > 0.f)) {   // zero-norm query (every distance is 0.0): the exact kernel answers it
+        if (blockIdx.x == 0 && threadIdx.x == 0) { a.status[0] = 1ull; a.status[1] = 0ull; }
+        return;
+    }
+
+    // ---- int8 image of the unit query + its error terms (every warp computes the same values) ----
+    float amax = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) amax = fmaxf(amax, fmaxf(fmaxf(fabsf(qv[j].x), fabsf(qv[j].y)), fmaxf(fabsf(qv[j].z), fabsf(qv[j].w))));
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) amax = fmaxf(amax, __shfl_xor_sync(FULL, amax, m));
+    s_q = amax * (1.0f / 127.0f);   // amax > 0 (ss > 0)
+    const float inv_sq = 1.0f / s_q;
+    uint32_t w[V];
+    float res2 = 0.f;
+    int qq = 0;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const int ix = max(-127, min(127, __float2int_rn(qv[j].x * inv_sq))), iy = max(-127, min(127, __float2int_rn(qv[j].y * inv_sq)));
+        const int iz = max(-127, min(127, __float2int_rn(qv[j].z * inv_sq))), iw = max(-127, min(127, __float2int_rn(qv[j].w * inv_sq)));
+        w[j] = pack_i8x4(ix, iy, iz, iw);
+        const float rx = fmaf(-s_q, (float)ix, qv[j].x), ry = fmaf(-s_q, (float)iy, qv[j].y);
+        const float rz = fmaf(-s_q, (float)iz, qv[j].z), rw = fmaf(-s_q, (float)iw, qv[j].w);
+        res2 = fmaf(rx, rx, res2); res2 = fmaf(ry, ry, res2); res2 = fmaf(rz, rz, res2); res2 = fmaf(rw, rw, res2);
+        qq += ix * ix + iy * iy + iz * iz + iw * iw;
+    }
+    res2 = warp_sum_tree(res2);
+    qq = __reduce_add_sync(FULL, qq);
+    // e_q (x 1 + 1e-3: fp32 summation error, ||x|| <= 1 + 1e-6) and ||q^|| (x 1 + 1e-5), both rounded generously up
+    EQ = sqrtf(res2) * 1.001f + 1e-9f;
+    QN = s_q * sqrtf((float)qq) * 1.00001f;
+    // lane layout of the streamed rows: 8 lanes per row, lane `sub` owns bytes [128 i + 16 sub, +16) of every line i —
+    // i.e. the packed words of lanes 4 sub .. 4 sub + 3 (float4 index lane + 32 j <-> byte 16 (lane + 32 j))
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        qw[j].x = __shfl_sync(FULL, w[j], 4 * sub + 0); qw[j].y = __shfl_sync(FULL, w[j], 4 * sub + 1);
+        qw[j].z = __shfl_sync(FULL, w[j], 4 * sub + 2); qw[j].w = __shfl_sync(FULL, w[j], 4 * sub + 3);
+    }
+    }
+    __syncthreads();
+
+    const uint64_t n = a.n_rows;
+    const uint32_t n_warps = gridDim.x * I8_WARPS;
+    uint64_t *region = a.region + (size_t)blockIdx.x * I8_REGION;
+
+    if (warp == I8_WARPS) {
+        // ---- helper warp: G = k-th smallest of the per-warp minima, refreshed until the CTA's rows are done ----
+        uint32_t *vals = reinterpret_cast<uint32_t *>(smem);
+        const uint32_t n_pad = (n_warps + 127u) & ~127u;   // whole uint4 per lane in the search
+        while (*reinterpret_cast<volatile unsigned *>(&s_done) == 0) {
+            for (uint32_t t0 = 0; t0 < n_pad; t0 += 32 * 8) {   // 8 independent L2 loads in flight per lane
+                uint32_t v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t t = t0 + u * 32 + lane;
+                    v[u] = t < n_warps ? ld_cg_u32(a.warp_min + t) : 0xFFFFFFFFu;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t t = t0 + u * 32 + lane;
+                    if (t < n_pad) vals[t] = v[u];
+                }
+            }
+            __syncwarp();
+            const uint32_t g = warp_kth_smallest(reinterpret_cast<const uint4 *>(vals), n_pad / 4, k, lane);
+            if (lane == 0) s_G = g;
+            __syncwarp();
+            __nanosleep(200);
+        }
+    } else {
+        // ---- streaming warps ----
+        const uint64_t gw = (uint64_t)blockIdx.x * I8_WARPS + warp;
+        const uint64_t n_groups = (n + ROWS_PER_ITER - 1) / ROWS_PER_ITER;
+        uint32_t wmin = 0xFFFFFFFFu;
+        const float sq_scale = s_q;
+        const int my_g = sub % R, my_r4 = lane >> 3;          // lanes with sub < R each finish one of the 4 R rows
+        for (uint64_t grp = gw; grp < n_groups; grp += n_warps) {
+            const uint64_t base = grp * ROWS_PER_ITER;
+            uint4 x[R][V];
+#pragma unroll
+            for (int g = 0; g < R; ++g) {
+                const uint64_t row = base + g * 4 + (lane >> 3);
+                const uint8_t *p = a.shadow + row * a.d8 + sub * 16;
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    if (row < n) x[g][j] = ldg_stream_u4(p + 128 * j);
+                    else x[g][j] = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+            uint32_t mt = 0;
+            if (lane < ROWS_PER_ITER && base + lane < n) mt = __ldg(a.meta + base + lane);
+            const uint32_t G = s_G;
+            int mine = 0;
+#pragma unroll
+            for (int g = 0; g < R; ++g) {
+                int acc = 0;
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    acc = __dp4a((int)x[g][j].x, (int)qw[j].x, acc); acc = __dp4a((int)x[g][j].y, (int)qw[j].y, acc);
+                    acc = __dp4a((int)x[g][j].z, (int)qw[j].z, acc); acc = __dp4a((int)x[g][j].w, (int)qw[j].w, acc);
+                }
+                acc += __shfl_xor_sync(FULL, acc, 4);
+                acc += __shfl_xor_sync(FULL, acc, 2);
+                acc += __shfl_xor_sync(FULL, acc, 1);
+                if (my_g == g) mine = acc;
+            }
+            // lane (r4, sub < R) now owns row base + 4 sub + r4; its meta word sits in lane 4 sub + r4
+            const uint32_t m = __shfl_sync(FULL, mt, 4 * my_g + my_r4);
+            const uint64_t row = base + 4 * my_g + my_r4;
+            const bool live = sub < R && row < n;
+            const float s_r = __half2float(__ushort_as_half((unsigned short)(m & 0xFFFFu)));
+            const float e_r = __half2float(__ushort_as_half((unsigned short)(m >> 16)));
+            const float c_hat = (float)mine * (sq_scale * s_r);
+            const float M = fmaf(QN, e_r, EQ);
+            const float lb = fmaf(-0.5f, c_hat + M, 0.5f) - I8_SLACK;
+            const float ub = fmaf(-0.5f, c_hat - M, 0.5f) + I8_SLACK;
+            const uint32_t lbk = okey(lb), ubk = live ? okey(ub) : 0xFFFFFFFFu;
+            const bool hit = live && lbk <= G;
+            const unsigned hm = __ballot_sync(FULL, hit);
+            if (hm) {   // warp-uniform, rare once G is live
+                unsigned pos0 = 0;
+                if (lane == 0) pos0 = atomicAdd(&s_cnt, (unsigned)__popc(hm));
+                pos0 = __shfl_sync(FULL, pos0, 0);
+                if (hit) {
+                    const unsigned pos = pos0 + __popc(hm & ((1u << lane) - 1u));
+                    if (pos < I8_REGION) region[pos] = ((uint64_t)lbk << 32) | (uint32_t)row;
+                }
+            }
+            if (__any_sync(FULL, ubk < wmin)) {   // rare: ~ln(rows per warp) times
+                wmin = min(wmin, __reduce_min_sync(FULL, ubk));
+                if (lane == 0) *reinterpret_cast<volatile uint32_t *>(a.warp_min + gw) = wmin;
+            }
+        }
+        asm volatile("bar.sync 1, %0;" :: "n"(I8_WARPS * 32));
+        if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned *>(&s_done) = 1u;
+    }
+    __syncthreads();
+
+    // ---- CTA end: re-filter the region against the (almost final) G, survivors -> the global list ----
+    {
+        const unsigned cnt = s_cnt;
+        if (cnt > I8_REGION && threadIdx.x == 0) atomicExch(a.counters + 2, 1u);
+        const unsigned nreg = min(cnt, I8_REGION);
+        const uint32_t G = s_G;
+        for (unsigned t = threadIdx.x; t < nreg; t += blockDim.x) {
+            const uint64_t key = region[t];
+            if ((uint32_t)(key >> 32) <= G) {
+                const unsigned pos = atomicAdd(a.counters + 1, 1u);
+                if (pos < I8_LIST_CAP) a.final_list[pos] = key;
+            }
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(a.counters + 0, 1u);
+        s_last = (t == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+
+    // ---- last CTA: sort by lb, rescore in two stages from the fp32 rows, select ----
+    uint64_t *C = smem;
+    const unsigned total = *reinterpret_cast<volatile unsigned *>(a.counters + 1);
+    const bool overflow = total > I8_LIST_CAP || *reinterpret_cast<volatile unsigned *>(a.counters + 2) != 0;
+    // leave the scratch clean for the next launch (all other CTAs have retired their use of it)
+    for (uint32_t t = threadIdx.x; t < n_warps; t += blockDim.x) a.warp_min[t] = 0xFFFFFFFFu;
+    __syncthreads();
+    if (threadIdx.x == 0) { a.counters[0] = 0; a.counters[1] = 0; a.counters[2] = 0; }
+    if (overflow) {
+        if (threadIdx.x == 0) { a.status[0] = 1ull; a.status[1] = (uint64_t)min(total, 0xFFFFFFFFu); }
+        return;
+    }
+    float4 qv[V];   // the unit query again, for the exact arithmetic (not kept live through the streaming loop)
+    load_unit_query<V, EXACT>(a.q, a.dim4, qv, lane);
+    const uint32_t n_c = total;
+    const uint32_t npad = pow2_at_least(n_c, 32);
+    {
+        const volatile uint64_t *fl = a.final_list;
+        for (uint32_t t = threadIdx.x; t < npad; t += blockDim.x) C[t] = t < n_c ? fl[t] : KEY_EMPTY;
+    }
+    cta_sort(C, npad);   // ascending lb
+
+    auto rescore = [&](uint32_t lo, uint32_t hi, uint32_t bound32) -> unsigned {
+        // exact keys for C[lo, hi) in place (entries carry ROW indices); an entry whose lb exceeds bound32 is dropped
+        // unread. Same arithmetic as scan_topk_kernel (see rescore.cuh: rescore_range). Streaming warps only.
+        constexpr int RR = V <= 4 ? 4 : (V <= 6 ? 2 : 1);
+        unsigned read_rows = 0;
+        if (warp >= I8_WARPS) return 0;
+        for (uint32_t i0 = lo + (uint32_t)warp * RR; i0 < hi; i0 += I8_WARPS * RR) {
+            uint32_t rowi[RR];
+            bool lv[RR];
+#pragma unroll
+            for (int r = 0; r < RR; ++r) {
+                const uint32_t i = i0 + r;
+                const uint64_t key = i < hi ? C[i] : KEY_EMPTY;
+                lv[r] = key != KEY_EMPTY && (uint32_t)(key >> 32) <= bound32;
+                rowi[r] = (uint32_t)key;
+            }
+            __syncwarp();
+            uint32_t idv[RR];
+#pragma unroll
+            for (int r = 0; r < RR; ++r) idv[r] = lv[r] ? __ldg(a.ids + rowi[r]) : 0u;
+            float4 xr[RR][V];
+#pragma unroll
+            for (int r = 0; r < RR; ++r) {
+                const float4 *p = a.rows + (size_t)rowi[r] * a.dim4 + lane;
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    if (lv[r] && (EXACT || lane + 32 * j < a.dim4)) xr[r][j] = __ldg(p + 32 * j);
+                    else xr[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RR; ++r) {
+                float acc = 0.f;
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    acc = fmaf(xr[r][j].x, qv[j].x, acc); acc = fmaf(xr[r][j].y, qv[j].y, acc);
+                    acc = fmaf(xr[r][j].z, qv[j].z, acc); acc = fmaf(xr[r][j].w, qv[j].w, acc);
+                }
+                acc = warp_sum_tree(acc);
+                const float dist = fmaf(-0.5f, acc, 0.5f);
+                if (i0 + r < hi && lane == 0) C[i0 + r] = lv[r] ? make_key(dist, idv[r]) : KEY_EMPTY;
+                read_rows += lv[r] ? 1u : 0u;
+            }
+        }
+        return read_rows;
+    };
+
+    // stage A: the a = pow2 >= max(32, k) best-looking candidates -> exact keys, sorted; T_A = k-th of them
+    const uint32_t a_pow = pow2_at_least(k, 32);
+    const uint32_t a_end = min(n_c, a_pow);
+    const uint32_t a_pad = n_c < a_pow ? npad : a_pow;
+    unsigned read_rows = rescore(0, a_end, 0xFFFFFFFFu);
+    __syncthreads();
+    cta_sort(C, a_pad);
+    if (threadIdx.x == 0) {
+        s_bound = (a_end >= k && C[k - 1] != KEY_EMPTY) ? (uint32_t)(C[k - 1] >> 32) : 0xFFFFFFFFu;
+        s_end = n_c;
+    }
+    __syncthreads();
+    const uint32_t bound_a = s_bound;
+    // stage B: the (sorted) prefix of the rest whose lb can still beat T_A
+    for (uint32_t t = a_end + threadIdx.x; t < n_c; t += blockDim.x)
+        if ((uint32_t)(C[t] >> 32) > bound_a) atomicMin(&s_end, t);
+    __syncthreads();
+    const uint32_t b_end = s_end;
+    read_rows += rescore(a_end, b_end, bound_a);
+    if (lane == 0 && read_rows) atomicAdd(&s_read, read_rows);
+    __syncthreads();
+    uint32_t n_all = b_end;
+    if (a.n_zero) {   // zero-norm rows: distance 0.0 (arroy pn*qn == 0), ascending id; the first k suffice
+        const uint32_t nz = min(a.n_zero, k);
+        for (uint32_t t = threadIdx.x; t < nz; t += blockDim.x) C[n_all + t] = make_key(0.f, a.zero_ids[t]);
+        n_all += nz;
+    }
+    const uint32_t fpad = pow2_at_least(n_all, 32);
+    for (uint32_t t = n_all + threadIdx.x; t < fpad; t += blockDim.x) C[t] = KEY_EMPTY;
+    cta_sort(C, fpad);
+    for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) a.out_keys[j] = j < fpad ? C[j] : KEY_EMPTY;
+    if (threadIdx.x == 0) { a.status[0] = 0ull; a.status[1] = ((uint64_t)s_read << 32) | n_c; }
+}
+
+// fp32 unit rows -> int8 shadow + meta (one warp per row). s_r = max|x| / 127 rounded UP to half (so |x / s_r| <= 127),
+// xi = rint(x / s_r), e_r = ||x - s_r xi||_2 accumulated in f64 and rounded UP to half.
+static __global__ void shadow_i8_from_rows_kernel(const float4 *__restrict__ rows, uint32_t *__restrict__ shadow_words,
+                                                  uint32_t *__restrict__ meta, uint64_t first, uint64_t n, uint32_t dim4, uint32_t d8)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t w0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t words = d8 / 4;
+    for (uint64_t i = w0; i < n; i += nw) {
+        const uint64_t row = first + i;
+        const float4 *p = rows + row * dim4;
+        float amax = 0.f;
+        for (uint32_t c = lane; c < dim4; c += 32) {
+            const float4 v = p[c];
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, m));
+        __half sh = __float2half_ru(amax * (1.0f / 127.0f) * 1.0000002f);
+        if (__half2float(sh) < 6.2e-5f) sh = __float2half_ru(6.2e-5f);   // keep the scale a normal half
+        const float sf = __half2float(sh), inv = 1.0f / sf;
+        double e2 = 0.0;
+        for (uint32_t c = lane; c < words; c += 32) {
+            uint32_t wv = 0;
+            if (c < dim4) {
+                const float4 v = p[c];
+                const int ix = max(-127, min(127, __float2int_rn(v.x * inv))), iy = max(-127, min(127, __float2int_rn(v.y * inv)));
+                const int iz = max(-127, min(127, __float2int_rn(v.z * inv))), iw = max(-127, min(127, __float2int_rn(v.w * inv)));
+                wv = pack_i8x4(ix, iy, iz, iw);
+                const double rx = (double)v.x - (double)sf * ix, ry = (double)v.y - (double)sf * iy;
+                const double rz = (double)v.z - (double)sf * iz, rw = (double)v.w - (double)sf * iw;
+                e2 += rx * rx + ry * ry + rz * rz + rw * rw;
+            }
+            shadow_words[row * words + c] = wv;
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) e2 += __shfl_xor_sync(0xFFFFFFFFu, e2, m);
+        if (lane == 0) {
+            const float ef = (float)(sqrt(e2) * 1.000001) + 1e-12f;
+            const __half eh = __float2half_ru(ef * 1.0000002f);
+            meta[row] = ((uint32_t)__half_as_ushort(eh) << 16) | (uint32_t)__half_as_ushort(sh);
+        }
+    }
+}
+
+}  // namespace csgpu

@@ -351,6 +351,12 @@ class VectorStore:
         in fp32 with the single-query kernel's arithmetic — results bit-identical to search() (csrc/rescore.cuh)."""
         _lib.check(self._lib.csgpu_set_tensor_prefilter(self._h, 1 if enabled else 0))
 
+    def set_byte_prefilter(self, enabled: bool) -> None:
+        """Opt-in (fp32 index): search() streams a 1-byte-per-element shadow as a filter with a proven per-row bound and
+        rescores the survivors in fp32 inside the same launch — results bit-identical to the default path
+        (csrc/scan_i8.cuh), a quarter of the HBM bytes per query."""
+        _lib.check(self._lib.csgpu_set_byte_prefilter(self._h, 1 if enabled else 0))
+
     def set_coalescing(self, enabled: bool, window_us: int = 0) -> None:
         """Host micro-batcher: concurrent search() calls with the same limit share one pass over the corpus."""
         _lib.check(self._lib.csgpu_set_coalescing(self._h, 1 if enabled else 0, int(window_us)))

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define CSGPU_ABI_VERSION 3
+#define CSGPU_ABI_VERSION 4
 
 enum {
     CSGPU_OK            = 0,
@@ -78,6 +78,11 @@ typedef struct csgpu_stats_t {
     uint64_t coalesced_queries;  /* ... for this many csgpu_search calls (csgpu_set_coalescing)     */
     uint64_t prefilter_rescored; /* tensor prefilter: fp32 rows rescored by the last batch (<= 1024 queries) */
     uint64_t shadow_bytes;       /* HBM held by the bf16 shadow (csgpu_set_tensor_prefilter), all devices   */
+    uint64_t byte_shadow_bytes;  /* HBM held by the int8 shadow + per-row bounds (csgpu_set_byte_prefilter)  */
+    uint64_t byte_searches;      /* csgpu_search calls that streamed the int8 shadow ...                     */
+    uint64_t byte_fallbacks;     /* ... of which this many were answered again by the fp32 scan kernel       */
+    uint64_t byte_candidates;    /* last such search: rows that reached the final candidate list             */
+    uint64_t byte_rescored;      /* last such search: fp32 rows read for the exact rescoring                 */
 } csgpu_stats_t;
 
 /* ---- lifecycle (VectorStore::new / open_readonly  store.rs:110-176,183-250) ------------ */
@@ -139,6 +144,17 @@ int  csgpu_search_batch(const csgpu_index *ix, const float *q, uint32_t q_len, u
  * (codesearch_b200/csrc/rescore.cuh has the bound). Off by default: the register-tiled fp32 SIMT kernel stays the
  * default batched path. May be called before or after csgpu_build; the shadow follows every later build / load. */
 int  csgpu_set_tensor_prefilter(csgpu_index *ix, uint32_t enabled);
+
+/* Opt-in, fp32 index only: exact fp32 results for csgpu_search from ONE pass over a 1-byte-per-element shadow of
+ * the corpus (+25 % HBM; dim <= 1024) instead of the 4-byte rows. The shadow (per-row scaled int8 + a per-row error
+ * bound computed at build) is streamed as a FILTER with a proven bound (integer dot products, Cauchy-Schwarz on the
+ * two quantisation residuals); the few hundred rows it cannot exclude are rescored from the fp32 rows with the
+ * single-query kernel's arithmetic, in the same kernel launch. Ids AND distances are bit-identical to the default path
+ * (codesearch_b200/csrc/scan_i8.cuh has the bound); the kernel moves dim + 4 bytes per row, not 4 * dim. Applies to
+ * unfiltered csgpu_search with k <= 128 on shards of >= 262144 rows; everything else, and any query the filter
+ * cannot bound (zero-norm query, candidate overflow), runs the fp32 scan kernel. Off by default. May be called
+ * before or after csgpu_build; the shadow follows every later build / load. */
+int  csgpu_set_byte_prefilter(csgpu_index *ix, uint32_t enabled);
 
 /* b (<= 16) query VARIANTS of one user query (query expansion, src/search/mod.rs:479-483), searched with the same
  * limit and merged on the device: per chunk id the best (smallest) distance over the variants, then the best k of

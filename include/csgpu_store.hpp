@@ -345,6 +345,8 @@ class VectorStore {
     }
     // opt-in: batches at tensor-core speed with exact fp32 results (csgpu_set_tensor_prefilter)
     void set_tensor_prefilter(bool on) { check(csgpu_set_tensor_prefilter(ix_.get(), on ? 1 : 0)); }
+    // opt-in: single queries from a 1-byte shadow + exact fp32 rescoring, bit-identical results (csgpu_set_byte_prefilter)
+    void set_byte_prefilter(bool on) { check(csgpu_set_byte_prefilter(ix_.get(), on ? 1 : 0)); }
     csgpu_index *handle() const { return ix_.get(); }
 
    private:

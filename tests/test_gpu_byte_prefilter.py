@@ -1,0 +1,208 @@
+"""Byte prefilter on the fp32 index (csgpu_set_byte_prefilter, csrc/scan_i8.cuh): a single query streams a
+1-byte-per-element shadow of the corpus as a FILTER with a proven per-row bound; the rows it cannot exclude are rescored
+from the fp32 rows with the single-query kernel's arithmetic inside the same launch. The bar is the tensor
+prefilter's: ids AND distances bit-identical to the default csgpu_search on every query, oracle parity like every other
+fp32 path, and a correct answer (through the fp32 scan kernel) whenever the filter cannot bound a query. GPU box only.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from parity import check_topk
+
+pytestmark = pytest.mark.gpu
+
+MARGIN = 8
+os.environ.setdefault("CSGPU_I8_MIN_ROWS", "4096")   # read once by the library: lets small corpora take the int8 route
+
+
+@pytest.fixture(scope="module")
+def cs():
+    import codesearch_b200 as m
+    m.load_library()
+    return m
+
+
+def _pair(cs, rows, ids=None):
+    """(store with the byte prefilter, plain store) over the same rows."""
+    out = []
+    for on in (True, False):
+        st = cs.VectorStore.new(None, rows.shape[1])
+        st.append_rows(rows, np.arange(rows.shape[0], dtype=np.uint32) if ids is None else ids)
+        if on:
+            st.set_byte_prefilter(True)
+        st.build_index()
+        out.append(st)
+    return out
+
+
+def _assert_same(fast, plain, q, k):
+    gi, gd = fast.search_ids(q, k)
+    ri, rd = plain.search_ids(q, k)
+    assert np.array_equal(gi, ri), (k, gi[:8], ri[:8])
+    assert np.array_equal(gd.view(np.uint32), rd.view(np.uint32)), k     # bit-identical distances
+    return gi, gd
+
+
+@pytest.mark.parametrize("n,d,ks", [
+    (300_000, 384, (1, 10, 32, 100, 128)),     # the headline shape; above the default row threshold
+    (60_000, 128, (10, 33)),                   # V = 1: 32 rows per warp iteration
+    (40_000, 320, (10, 100)),                  # dim4 = 80: padded shadow lines, predicated fp32 lanes
+    (30_000, 768, (10, 128)),                  # V = 6 (BASELINE configs[4] width)
+    (20_000, 1024, (5, 64)),                   # V = 8
+    (9_000, 100, (7,)),                        # dim % 4 == 0 only
+    (5_000, 30, (3,)),                         # dim not a multiple of 4 (row padding)
+])
+def test_byte_prefilter_bit_identical(cs, oracle, n, d, ks):
+    rng = np.random.default_rng(n + d)
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    fast, plain = _pair(cs, rows)
+    s = fast.device_stats()
+    assert s.byte_shadow_bytes == n * (128 * ((d + 127) // 128) + 4)
+    qs = rng.standard_normal((6, d)).astype(np.float32)
+    for k in ks:
+        before = fast.device_stats()
+        for j in range(qs.shape[0]):
+            gi, gd = _assert_same(fast, plain, qs[j], k)
+            if j == 0:
+                ri, rd, r64 = oracle.np_search(rows, qs[j], k + MARGIN)
+                check_topk(gi, gd, ri, rd, r64, k)
+        after = fast.device_stats()
+        assert after.byte_searches - before.byte_searches == qs.shape[0]     # the int8 route really ran ...
+        assert after.byte_fallbacks == before.byte_fallbacks                 # ... and answered by itself
+        assert 0 < after.byte_rescored <= after.byte_candidates
+    # a query taken from the corpus (distance ~ 0 at rank 0), and a scaled query (normalised inside)
+    _assert_same(fast, plain, rows[123], ks[0])
+    _assert_same(fast, plain, 1e-3 * qs[0], ks[0])
+    _assert_same(fast, plain, 1e4 * qs[1], ks[0])
+
+
+def test_byte_prefilter_routes_what_it_does_not_cover(cs):
+    rng = np.random.default_rng(5)
+    rows = rng.standard_normal((20_000, 384)).astype(np.float32)
+    fast, plain = _pair(cs, rows)
+    q = rng.standard_normal(384).astype(np.float32)
+    b0 = fast.device_stats().byte_searches
+    _assert_same(fast, plain, q, 129)                                   # k above the int8 route's limit
+    _assert_same(fast, plain, q, 1000)
+    flt = cs.RowFilter.from_mask(np.arange(rows.shape[0]) % 3 == 0)     # filtered searches stay on the fp32 kernel
+    fi, fd = fast.search_ids(q, 10, flt)
+    pi, pd = plain.search_ids(q, 10, flt)
+    assert np.array_equal(fi, pi) and np.array_equal(fd.view(np.uint32), pd.view(np.uint32))
+    assert fast.device_stats().byte_searches == b0
+    # zero-norm query: the launch reports it, the fp32 kernel answers (every distance 0.0, ascending ids)
+    z = np.zeros(384, dtype=np.float32)
+    gi, gd = _assert_same(fast, plain, z, 10)
+    assert gi.tolist() == list(range(10)) and not gd.any()
+    s = fast.device_stats()
+    assert s.byte_searches == b0 + 1 and s.byte_fallbacks >= 1
+
+
+def test_byte_prefilter_adversarial_inputs(cs, oracle):
+    """Inputs the filter cannot prune: near-duplicate clusters far inside the int8 bound, exact duplicates (ties by id),
+    and a corpus sorted so that every row beats all earlier ones. Whatever the route, the answer is the exact one."""
+    rng = np.random.default_rng(11)
+    d = 384
+    centres = rng.standard_normal((30, d)).astype(np.float32)
+    rows = (np.repeat(centres, 700, axis=0) + 0.02 * rng.standard_normal((30 * 700, d))).astype(np.float32)
+    rows[100] = rows[99]
+    rows[5000] = rows[4999]
+    rows = rows[rng.permutation(rows.shape[0])]
+    fast, plain = _pair(cs, rows)
+    for c in (0, 7, 29):
+        q = (centres[c] + 0.01 * rng.standard_normal(d)).astype(np.float32)
+        for k in (10, 100):
+            gi, gd = _assert_same(fast, plain, q, k)
+            ri, rd, r64 = oracle.np_search(rows, q, k + MARGIN)
+            check_topk(gi, gd, ri, rd, r64, k)
+    # every row identical: 21000-way tie, ids decide; the candidate list overflows -> fp32 kernel
+    same = np.tile(rng.standard_normal((1, d)).astype(np.float32), (21_000, 1))
+    fast2, plain2 = _pair(cs, same)
+    gi, _ = _assert_same(fast2, plain2, same[0], 10)
+    assert gi.tolist() == list(range(10))
+    assert fast2.device_stats().byte_fallbacks >= 1
+    # rows ordered from the farthest to the nearest: the running threshold never helps
+    q = rng.standard_normal(d).astype(np.float32)
+    base = rng.standard_normal((30_000, d)).astype(np.float32)
+    cosv = (base @ q) / np.linalg.norm(base, axis=1)
+    srt = base[np.argsort(cosv)]
+    fast3, plain3 = _pair(cs, srt)
+    _assert_same(fast3, plain3, q, 10)
+    _assert_same(fast3, plain3, q, 128)
+
+
+def test_byte_prefilter_zero_rows_updates_snapshot_toggle(cs, oracle, tmp_path):
+    rng = np.random.default_rng(3)
+    n, d = 12_000, 384
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    rows[10] = 0.0                    # zero-norm rows: distance 0.0, injected by the tail
+    rows[7777] = 0.0
+    q = rng.standard_normal(d).astype(np.float32)
+    db = str(tmp_path / "db")
+    os.makedirs(db)
+    fast = cs.VectorStore.new(db, d)
+    fast.append_rows(rows, np.arange(n, dtype=np.uint32))
+    fast.build_index()
+    fast.set_byte_prefilter(True)                      # enabling after build creates the shadow now
+    assert fast.device_stats().byte_shadow_bytes == (n - 2) * (384 + 4)
+    plain = cs.VectorStore.new(None, d)
+    plain.append_rows(rows, np.arange(n, dtype=np.uint32))
+    plain.build_index()
+    gi, gd = _assert_same(fast, plain, q, 10)
+    assert gi[:2].tolist() == [10, 7777] and gd[0] == 0.0 and gd[1] == 0.0
+    # delete the current best rows + append new ones, rebuild: the shadow follows
+    kill = gi[2:6].tolist()
+    extra = rng.standard_normal((500, d)).astype(np.float32)
+    for st in (fast, plain):
+        st.delete_chunks(kill)
+        st.append_rows(extra, np.arange(n, n + 500, dtype=np.uint32))
+        st.build_index()
+    gi2, _ = _assert_same(fast, plain, q, 10)
+    assert not set(kill) & set(gi2.tolist())
+    assert fast.device_stats().byte_searches >= 2
+    # reopen from the snapshot (hydrated in the constructor), then switch the prefilter on
+    re = cs.VectorStore.new(db, d)
+    re.set_byte_prefilter(True)
+    b0 = re.device_stats().byte_searches
+    if not re.is_indexed():
+        pytest.skip("snapshot hydrate not available")
+    _assert_same(re, plain, q, 10)
+    assert re.device_stats().byte_shadow_bytes > 0
+    assert re.device_stats().byte_searches == b0 + 1
+    # toggle off: shadow dropped, same answers from the fp32 kernel
+    fast.set_byte_prefilter(False)
+    assert fast.device_stats().byte_shadow_bytes == 0
+    b1 = fast.device_stats().byte_searches
+    _assert_same(fast, plain, q, 10)
+    assert fast.device_stats().byte_searches == b1
+    # bf16 index: refused
+    bf = cs.VectorStore.new(None, 384, dtype="bf16")
+    with pytest.raises(cs.CsgpuError):
+        bf.set_byte_prefilter(True)
+
+
+def test_byte_prefilter_concurrent_searches(cs):
+    """csgpu_search is re-entrant (&self in the reference): searches from several host threads each take their own
+    context (scratch + status word) and all return the exact answer."""
+    import threading
+    rng = np.random.default_rng(21)
+    rows = rng.standard_normal((50_000, 384)).astype(np.float32)
+    fast, plain = _pair(cs, rows)
+    qs = rng.standard_normal((16, 384)).astype(np.float32)
+    want = [plain.search_ids(q, 10) for q in qs]
+    errs = []
+
+    def work(t):
+        try:
+            for rep in range(5):
+                for j in range(t, len(qs), 4):
+                    gi, gd = fast.search_ids(qs[j], 10)
+                    assert np.array_equal(gi, want[j][0]) and np.array_equal(gd.view(np.uint32), want[j][1].view(np.uint32))
+        except Exception as e:   # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs

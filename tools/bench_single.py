@@ -19,6 +19,8 @@ p.add_argument("--dim", type=int, default=384)
 p.add_argument("--ks", default="10,100,200")
 p.add_argument("--densities", default="", help="comma list of filter densities; mask = synthetic file/language predicate")
 p.add_argument("--reps", type=int, default=30)
+p.add_argument("--byte-prefilter", action="store_true",
+               help="csgpu_set_byte_prefilter: int8 shadow + exact rescoring; every timed query is first checked bit-identical to the fp32 scan")
 args = p.parse_args()
 lib = _lib.load()
 n, d = args.rows, args.dim
@@ -29,6 +31,14 @@ st.build_index()
 qs = np.empty((64, d), np.float32)
 _lib.check(lib.csgpu_synth_rows_host(st.handle, 4321, 0, 64, qs.ctypes.data_as(_lib._f32p)))
 bytes_scan = n * d * 4
+want = {}
+if args.byte_prefilter:
+    for k in (int(x) for x in args.ks.split(",")):
+        want[k] = [st.search_ids(qs[i], k) for i in range(64)]          # fp32 scan kernel, before the shadow exists
+    t0 = time.perf_counter()
+    st.set_byte_prefilter(True)
+    print(json.dumps({"byte_shadow_build_s": round(time.perf_counter() - t0, 3),
+                      "byte_shadow_bytes": int(st.device_stats().byte_shadow_bytes)}), flush=True)
 
 
 def run(k, flt, label):
@@ -41,8 +51,21 @@ def run(k, flt, label):
             wall.append((t1 - t0) * 1e3)
             dev.append(st.device_stats().last_search_us / 1e3)
     dm, wm = statistics.median(dev), statistics.median(wall)
-    print(json.dumps({"rows": n, "dim": d, "k": k, "filter": label, "device_ms": round(dm, 4), "e2e_ms": round(wm, 4),
-                      "scanned_GBps": round(bytes_scan / dm / 1e6, 1), "qps_e2e": round(1e3 / wm, 1)}), flush=True)
+    rec = {"rows": n, "dim": d, "k": k, "filter": label, "device_ms": round(dm, 4), "e2e_ms": round(wm, 4),
+           "scanned_GBps": round(bytes_scan / dm / 1e6, 1), "qps_e2e": round(1e3 / wm, 1)}
+    if args.byte_prefilter and flt is None:
+        s0 = st.device_stats()
+        same = 0
+        for i in range(64):
+            gi, gd = st.search_ids(qs[i], k)
+            same += int(np.array_equal(gi, want[k][i][0]) and np.array_equal(gd.view(np.uint32), want[k][i][1].view(np.uint32)))
+        s1 = st.device_stats()
+        shadow = int(s1.byte_shadow_bytes)
+        rec.update({"route": "byte prefilter (int8 shadow + fp32 rescoring)", "bit_identical_to_fp32_scan": f"{same}/64",
+                    "int8_searches": int(s1.byte_searches - s0.byte_searches), "fallbacks": int(s1.byte_fallbacks - s0.byte_fallbacks),
+                    "last_candidates": int(s1.byte_candidates), "last_rows_rescored": int(s1.byte_rescored),
+                    "shadow_GBps": round(shadow / dm / 1e6, 1), "equivalent_fp32_GBps": rec.pop("scanned_GBps")})
+    print(json.dumps(rec), flush=True)
 
 
 for k in (int(x) for x in args.ks.split(",")):
