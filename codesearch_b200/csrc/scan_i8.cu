@@ -1,7 +1,9 @@
 // scan_i8.cu — host side of the byte prefilter (scan_i8.cuh): the int8 shadow of a shard's built rows, the
 // per-context scratch, and the launcher. Own translation unit so the library builds in parallel.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "index.h"
 #include "scan_i8.cuh"
@@ -73,9 +75,10 @@ bool i8_eligible(const csgpu_index *ix, uint32_t k)
 }
 
 struct I8Scratch {   // one cudaMalloc block per SearchCtx
+    unsigned long long timing[(I8_MAX_GRID + 1) * 4];
     uint32_t warp_min[I8_MAX_WARPS];
     unsigned counters[8];
-    uint64_t final_list[I8_TAIL_CAP];
+    uint64_t final_list[I8_FINAL_CAP];
     uint64_t region[(size_t)I8_MAX_GRID * I8_REGION];
 };
 
@@ -95,7 +98,7 @@ int enqueue_scan_i8(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const 
 {
     if (c->i8_scratch == nullptr) {
         CS_CUDA(cudaMalloc(&c->i8_scratch, sizeof(I8Scratch)));
-        CS_CUDA(cudaMemsetAsync(c->i8_scratch, 0xFF, sizeof(uint32_t) * I8_MAX_WARPS, st));
+        CS_CUDA(cudaMemsetAsync(reinterpret_cast<I8Scratch *>(c->i8_scratch)->warp_min, 0xFF, sizeof(uint32_t) * I8_MAX_WARPS, st));
         CS_CUDA(cudaMemsetAsync(reinterpret_cast<I8Scratch *>(c->i8_scratch)->counters, 0, sizeof(unsigned) * 8, st));
         CS_CUDA(cudaHostAlloc(&c->i8_status, 8 * sizeof(uint64_t), cudaHostAllocMapped | cudaHostAllocPortable));
     }
@@ -119,6 +122,8 @@ int enqueue_scan_i8(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const 
     a.counters = s->counters;
     a.out_keys = out_keys;
     a.status = c->i8_status;
+    static const bool timing = getenv("CSGPU_I8_TIMING") != nullptr;
+    a.timing = timing ? s->timing : nullptr;
     c->i8_status[0] = 1;   // a launch that never runs must not look like a success
     const uint32_t R = (V <= 2) ? 8 : (V <= 4 ? 4 : 2);
     const uint64_t want = (sh->n_built + (uint64_t)I8_WARPS * 4 * R - 1) / ((uint64_t)I8_WARPS * 4 * R);
@@ -132,6 +137,18 @@ int enqueue_scan_i8(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const 
     }
 #undef CS_CASE
     if (e != cudaSuccess) return fail_cuda(e, "scan_i8_kernel launch", __FILE__, __LINE__);
+    if (timing) {   // diagnostic: per-CTA globaltimer stamps -> where a query's time goes (synchronises!)
+        std::vector<unsigned long long> t((grid + 1) * 4);
+        CS_CUDA(cudaStreamSynchronize(st));
+        CS_CUDA(cudaMemcpy(t.data(), s->timing, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        unsigned long long t0 = ~0ull, s_lo = ~0ull, s_hi = 0, e_hi = 0, st_hi = 0;
+        for (uint32_t b = 0; b < grid; ++b) {
+            t0 = std::min(t0, t[b * 4]); st_hi = std::max(st_hi, t[b * 4]);
+            s_lo = std::min(s_lo, t[b * 4 + 1]); s_hi = std::max(s_hi, t[b * 4 + 1]); e_hi = std::max(e_hi, t[b * 4 + 2]);
+        }
+        fprintf(stderr, "[i8 timing] grid %u: last CTA start +%.1f us | streaming ends first +%.1f last +%.1f | last ticket +%.1f | tail done +%.1f us\n",
+                grid, (st_hi - t0) / 1e3, (s_lo - t0) / 1e3, (s_hi - t0) / 1e3, (e_hi - t0) / 1e3, (t[grid * 4] - t0) / 1e3);
+    }
     return CSGPU_OK;
 }
 

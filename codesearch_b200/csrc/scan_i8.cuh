@@ -48,6 +48,8 @@ constexpr uint32_t I8_MAX_K = 128;
 constexpr uint32_t I8_LIST_CAP = I8_TAIL_CAP - I8_MAX_K;   // candidates on the global list (room for the zero-norm ids)
 constexpr uint32_t I8_MAX_WARPS = 148 * 2 * I8_WARPS;   // per-warp minima staged in shared memory by the helper
 constexpr float I8_SLACK = 3e-6f;
+constexpr int I8_CHUNK = 8;                          // row groups per grab of the work counter (shrinks near the end)
+constexpr uint32_t I8_FINAL_CAP = 65536;             // slots of the global candidate list (the tail re-filters it when long)
 constexpr int I8_SEARCH_BITS = 20;                   // bits of the k-th-smallest search (the rest is rounded up)
 
 struct I8Args {
@@ -63,9 +65,10 @@ struct I8Args {
     uint32_t n_zero;
     uint32_t *warp_min;         // [gridDim.x * I8_WARPS] okey(ub); 0xFFFFFFFF between launches
     uint64_t *region;           // [gridDim.x][I8_REGION]
-    uint64_t *final_list;       // [I8_TAIL_CAP]
-    unsigned *counters;         // [0] ticket, [1] final count, [2] overflow flag — all 0 between launches
+    uint64_t *final_list;       // [I8_FINAL_CAP]
+    unsigned *counters;         // [0] ticket, [1] final count, [2] overflow flag, [3] next row group — all 0 between launches
     uint64_t *out_keys;         // [k] result keys
+    unsigned long long *timing; // nullptr, or [gridDim.x + 1][4] globaltimer stamps (CSGPU_I8_TIMING=1: where the time goes)
     uint64_t *status;           // [0]: 0 = out_keys valid, 1 = answer with the exact scan instead;
                                 // [1]: (fp32 rows rescored << 32) | candidates on the final list
 };
@@ -85,10 +88,12 @@ __device__ __forceinline__ uint32_t pack_i8x4(int a, int b, int c, int d)
 
 // k-th smallest (1-based) of vals[0..n4*4) held in shared memory (padded with 0xFFFFFFFF), searched on the top
 // I8_SEARCH_BITS bits and rounded UP (so the result is >= the true k-th smallest: still a valid bound). One warp.
-__device__ __forceinline__ uint32_t warp_kth_smallest(const uint4 *vals4, uint32_t n4, uint32_t k, int lane)
+__device__ __forceinline__ uint32_t warp_kth_smallest(const uint4 *vals4, uint32_t n4, uint32_t k, int lane,
+                                                   const volatile unsigned *stop = nullptr)
 {
     uint32_t ans = 0;
     for (int b = 31; b >= 32 - I8_SEARCH_BITS; --b) {
+        if (stop != nullptr && *stop) return 0xFFFFFFFFu;   // the CTA is done: do not hold it up
         const uint32_t cand = ans | ((1u << b) - 1u);   // bit b clear, everything below set
         unsigned c = 0;
         for (uint32_t t = lane; t < n4; t += 32) {
@@ -99,6 +104,36 @@ __device__ __forceinline__ uint32_t warp_kth_smallest(const uint4 *vals4, uint32
         if (c < k) ans |= 1u << b;
     }
     return ans | ((1u << (32 - I8_SEARCH_BITS)) - 1u);
+}
+
+// CTA-wide ascending sort of n (pow2) keys in shared memory. Small lists (the common case: a few hundred candidates)
+// are sorted by rank — every element counts the keys below it and is scattered to that position: one pass of
+// broadcast reads and two barriers instead of log^2(n) barrier-separated bitonic steps. Equal keys (only KEY_EMPTY
+// padding) are ordered by position.
+__device__ __forceinline__ void cta_sort_fast(uint64_t *s, uint32_t n)
+{
+    if (n > 512) { cta_sort(s, n); return; }
+    uint64_t mine[2];
+    uint32_t rank[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const uint32_t i = threadIdx.x + e * blockDim.x;
+        mine[e] = KEY_EMPTY; rank[e] = 0;
+        if (i < n) {
+            const uint64_t v = s[i];
+            uint32_t r = 0;
+            for (uint32_t j = 0; j < n; ++j) {
+                const uint64_t o = s[j];
+                r += (o < v || (o == v && j < i)) ? 1u : 0u;
+            }
+            mine[e] = v; rank[e] = r;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+        if (threadIdx.x + e * blockDim.x < n) s[rank[e]] = mine[e];
+    __syncthreads();
 }
 
 __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t *p)
@@ -142,6 +177,7 @@ __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & 7;
     const uint32_t k = a.k;
     if (threadIdx.x == 0) { s_cnt = 0; s_done = 0; s_read = 0; s_G = 0xFFFFFFFFu; }
+    if (a.timing && threadIdx.x == 0) a.timing[blockIdx.x * 4 + 0] = global_timer_ns();
 
     float s_q, EQ, QN;
     uint4 qw[V];
@@ -198,6 +234,7 @@ __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
         // ---- helper warp: G = k-th smallest of the per-warp minima, refreshed until the CTA's rows are done ----
         uint32_t *vals = reinterpret_cast<uint32_t *>(smem);
         const uint32_t n_pad = (n_warps + 127u) & ~127u;   // whole uint4 per lane in the search
+        unsigned rounds = 0;
         while (*reinterpret_cast<volatile unsigned *>(&s_done) == 0) {
             for (uint32_t t0 = 0; t0 < n_pad; t0 += 32 * 8) {   // 8 independent L2 loads in flight per lane
                 uint32_t v[8];
@@ -213,20 +250,36 @@ __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
                 }
             }
             __syncwarp();
-            const uint32_t g = warp_kth_smallest(reinterpret_cast<const uint4 *>(vals), n_pad / 4, k, lane);
-            if (lane == 0) s_G = g;
+            // once a finite G is out, a refresh gives way as soon as the CTA's rows are done; the first one always completes
+            const uint32_t g = warp_kth_smallest(reinterpret_cast<const uint4 *>(vals), n_pad / 4, k, lane,
+                                                 s_G != 0xFFFFFFFFu ? &s_done : nullptr);
+            if (lane == 0 && g < s_G) s_G = g;
             __syncwarp();
-            __nanosleep(200);
+            // G settles within the first few rows of every warp: poll hard at first, then every ~4 us
+            if (++rounds < 16) __nanosleep(100);
+            else for (int w = 0; w < 16 && *reinterpret_cast<volatile unsigned *>(&s_done) == 0; ++w) __nanosleep(250);
         }
     } else {
         // ---- streaming warps ----
         const uint64_t gw = (uint64_t)blockIdx.x * I8_WARPS + warp;
-        const uint64_t n_groups = (n + ROWS_PER_ITER - 1) / ROWS_PER_ITER;
+        const uint32_t n_groups = (uint32_t)((n + ROWS_PER_ITER - 1) / ROWS_PER_ITER);
         uint32_t wmin = 0xFFFFFFFFu;
         const float sq_scale = s_q;
         const int my_g = sub % R, my_r4 = lane >> 3;          // lanes with sub < R each finish one of the 4 R rows
-        for (uint64_t grp = gw; grp < n_groups; grp += n_warps) {
-            const uint64_t base = grp * ROWS_PER_ITER;
+        // Dynamic work distribution: SMs stream at visibly different rates (a static split leaves the first CTA idle
+        // for the last 25 % of the kernel), so warps grab chunks of row groups from one global counter — up to
+        // I8_CHUNK groups while plenty is left, single groups near the end. The next grab is issued before the
+        // current chunk is processed, so its latency never shows.
+        uint32_t c_next = max(1u, min((uint32_t)I8_CHUNK, n_groups / (2u * n_warps))), nxt = 0;
+        if (lane == 0) nxt = atomicAdd(a.counters + 3, c_next);
+        for (;;) {
+        const uint32_t c_start = __shfl_sync(FULL, nxt, 0);
+        if (c_start >= n_groups) break;
+        const uint32_t c_end = min(c_start + c_next, n_groups);
+        c_next = max(1u, min((uint32_t)I8_CHUNK, (n_groups - c_start) / (2u * n_warps)));
+        if (lane == 0) nxt = atomicAdd(a.counters + 3, c_next);
+        for (uint32_t grp = c_start; grp < c_end; ++grp) {
+            const uint64_t base = (uint64_t)grp * ROWS_PER_ITER;
             uint4 x[R][V];
 #pragma unroll
             for (int g = 0; g < R; ++g) {
@@ -282,10 +335,12 @@ __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
                 if (lane == 0) *reinterpret_cast<volatile uint32_t *>(a.warp_min + gw) = wmin;
             }
         }
+        }
         asm volatile("bar.sync 1, %0;" :: "n"(I8_WARPS * 32));
         if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned *>(&s_done) = 1u;
     }
     __syncthreads();
+    if (a.timing && threadIdx.x == 0) a.timing[blockIdx.x * 4 + 1] = global_timer_ns();
 
     // ---- CTA end: re-filter the region against the (almost final) G, survivors -> the global list ----
     {
@@ -297,13 +352,14 @@ __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
             const uint64_t key = region[t];
             if ((uint32_t)(key >> 32) <= G) {
                 const unsigned pos = atomicAdd(a.counters + 1, 1u);
-                if (pos < I8_LIST_CAP) a.final_list[pos] = key;
+                if (pos < I8_FINAL_CAP) a.final_list[pos] = key;
             }
         }
     }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
+        if (a.timing) a.timing[blockIdx.x * 4 + 2] = global_timer_ns();
         const unsigned t = atomicAdd(a.counters + 0, 1u);
         s_last = (t == gridDim.x - 1) ? 1u : 0u;
     }
@@ -314,24 +370,55 @@ __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
     // ---- last CTA: sort by lb, rescore in two stages from the fp32 rows, select ----
     uint64_t *C = smem;
     const unsigned total = *reinterpret_cast<volatile unsigned *>(a.counters + 1);
-    const bool overflow = total > I8_LIST_CAP || *reinterpret_cast<volatile unsigned *>(a.counters + 2) != 0;
+    bool overflow = total > I8_FINAL_CAP || *reinterpret_cast<volatile unsigned *>(a.counters + 2) != 0;
+    // A long list (thresholds that were stale when the CTAs filtered: tiny corpora; or many near-ties) is filtered once
+    // more against the FINAL G — every warp's minimum is final now — while it is loaded.
+    uint32_t Gf = 0xFFFFFFFFu;
+    if (!overflow && total > 1024) {
+        if (warp == 0) {
+            uint32_t *vals = reinterpret_cast<uint32_t *>(smem);
+            const uint32_t n_pad = (n_warps + 127u) & ~127u;
+            for (uint32_t t = lane; t < n_pad; t += 32) vals[t] = t < n_warps ? ld_cg_u32(a.warp_min + t) : 0xFFFFFFFFu;
+            __syncwarp();
+            const uint32_t g = warp_kth_smallest(reinterpret_cast<const uint4 *>(vals), n_pad / 4, k, lane);
+            if (lane == 0) s_bound = g;
+        }
+        __syncthreads();
+        Gf = s_bound;
+    }
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
     // leave the scratch clean for the next launch (all other CTAs have retired their use of it)
     for (uint32_t t = threadIdx.x; t < n_warps; t += blockDim.x) a.warp_min[t] = 0xFFFFFFFFu;
-    __syncthreads();
-    if (threadIdx.x == 0) { a.counters[0] = 0; a.counters[1] = 0; a.counters[2] = 0; }
+    if (threadIdx.x == 0) { a.counters[0] = 0; a.counters[1] = 0; a.counters[2] = 0; a.counters[3] = 0; }
+    if (!overflow) {
+        const volatile uint64_t *fl = a.final_list;
+        if (total <= 1024) {
+            for (uint32_t t = threadIdx.x; t < total; t += blockDim.x) C[t] = fl[t];
+            if (threadIdx.x == 0) s_cnt = total;
+        } else {
+            for (uint32_t t = threadIdx.x; t < total; t += blockDim.x) {
+                const uint64_t key = fl[t];
+                if ((uint32_t)(key >> 32) <= Gf) {
+                    const unsigned pos = atomicAdd(&s_cnt, 1u);
+                    if (pos < I8_LIST_CAP) C[pos] = key;
+                }
+            }
+        }
+        __syncthreads();
+        overflow = s_cnt > I8_LIST_CAP;
+    }
     if (overflow) {
         if (threadIdx.x == 0) { a.status[0] = 1ull; a.status[1] = (uint64_t)min(total, 0xFFFFFFFFu); }
         return;
     }
     float4 qv[V];   // the unit query again, for the exact arithmetic (not kept live through the streaming loop)
     load_unit_query<V, EXACT>(a.q, a.dim4, qv, lane);
-    const uint32_t n_c = total;
+    const uint32_t n_c = s_cnt;
     const uint32_t npad = pow2_at_least(n_c, 32);
-    {
-        const volatile uint64_t *fl = a.final_list;
-        for (uint32_t t = threadIdx.x; t < npad; t += blockDim.x) C[t] = t < n_c ? fl[t] : KEY_EMPTY;
-    }
-    cta_sort(C, npad);   // ascending lb
+    for (uint32_t t = n_c + threadIdx.x; t < npad; t += blockDim.x) C[t] = KEY_EMPTY;
+    __syncthreads();
+    cta_sort_fast(C, npad);   // ascending lb
 
     auto rescore = [&](uint32_t lo, uint32_t hi, uint32_t bound32) -> unsigned {
         // exact keys for C[lo, hi) in place (entries carry ROW indices); an entry whose lb exceeds bound32 is dropped
@@ -386,7 +473,7 @@ __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
     const uint32_t a_pad = n_c < a_pow ? npad : a_pow;
     unsigned read_rows = rescore(0, a_end, 0xFFFFFFFFu);
     __syncthreads();
-    cta_sort(C, a_pad);
+    cta_sort_fast(C, a_pad);
     if (threadIdx.x == 0) {
         s_bound = (a_end >= k && C[k - 1] != KEY_EMPTY) ? (uint32_t)(C[k - 1] >> 32) : 0xFFFFFFFFu;
         s_end = n_c;
@@ -409,9 +496,13 @@ __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
     }
     const uint32_t fpad = pow2_at_least(n_all, 32);
     for (uint32_t t = n_all + threadIdx.x; t < fpad; t += blockDim.x) C[t] = KEY_EMPTY;
-    cta_sort(C, fpad);
+    __syncthreads();
+    cta_sort_fast(C, fpad);
     for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) a.out_keys[j] = j < fpad ? C[j] : KEY_EMPTY;
-    if (threadIdx.x == 0) { a.status[0] = 0ull; a.status[1] = ((uint64_t)s_read << 32) | n_c; }
+    if (threadIdx.x == 0) {
+        a.status[0] = 0ull; a.status[1] = ((uint64_t)s_read << 32) | n_c;
+        if (a.timing) { a.timing[gridDim.x * 4 + 0] = global_timer_ns(); a.timing[gridDim.x * 4 + 1] = blockIdx.x; }
+    }
 }
 
 // fp32 unit rows -> int8 shadow + meta (one warp per row). s_r = max|x| / 127 rounded UP to half (so |x / s_r| <= 127),

@@ -1,0 +1,11 @@
+import os, sys
+os.environ["CSGPU_I8_TIMING"] = "1"
+sys.path.insert(0, os.getcwd())
+import numpy as np
+import codesearch_b200 as cs
+from codesearch_b200 import _lib
+n = int(sys.argv[1]); k = int(sys.argv[2])
+st = cs.VectorStore.new(None, 384); st.reserve(n); st.append_synthetic(1234, 0, n); st.set_byte_prefilter(True); st.build_index()
+qs = np.empty((8, 384), np.float32)
+_lib.check(_lib.load().csgpu_synth_rows_host(st.handle, 4321, 0, 8, qs.ctypes.data_as(_lib._f32p)))
+for i in range(8): st.search_ids(qs[i], k)
