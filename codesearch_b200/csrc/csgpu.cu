@@ -108,11 +108,19 @@ static void ctx_release(Shard *sh, SearchCtx *c)
 // OCC = resident CTAs per SM. The scan needs ~96 KB of loads in flight per SM (profiles/r01_tune_scan.txt:
 // occupancy 1 loses 30 %); the big-k selector is one CTA-shared buffer of <= 4096 keys (32 KB), so every k runs
 // 2 CTAs/SM.
-template <int V, bool EXACT, bool BIG, int OCC>
-static cudaError_t launch_scan_v(const ScanArgs &a, uint32_t grid, size_t smem, cudaStream_t st)
+// CSGPU_SCAN_STATIC=1 (diagnostic, A/B runs): fixed-stride row split instead of the work counter (scan.cuh: DYN);
+// =2: fixed stride only for k > 32
+static int scan_static_mode()
+{
+    static const int v = [] { const char *e = getenv("CSGPU_SCAN_STATIC"); return e && *e ? atoi(e) : 0; }();
+    return v;
+}
+
+template <int V, bool EXACT, bool BIG, int OCC, bool DYN>
+static cudaError_t launch_scan_vd(const ScanArgs &a, uint32_t grid, size_t smem, cudaStream_t st)
 {
     constexpr int R = (V <= 2) ? 8 : (V <= 4 ? 4 : 2);
-    auto kern = scan_topk_kernel<V, EXACT, R, BIG, OCC>;
+    auto kern = scan_topk_kernel<V, EXACT, R, BIG, OCC, 0, false, DYN>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -120,6 +128,14 @@ static cudaError_t launch_scan_v(const ScanArgs &a, uint32_t grid, size_t smem, 
     kern<<<grid, SCAN_THREADS, smem, st>>>(a);
     count_launch();
     return cudaGetLastError();
+}
+
+template <int V, bool EXACT, bool BIG, int OCC>
+static cudaError_t launch_scan_v(const ScanArgs &a, uint32_t grid, size_t smem, cudaStream_t st)
+{
+    const int m = scan_static_mode();
+    if (m == 1 || (m == 2 && BIG)) return launch_scan_vd<V, EXACT, BIG, OCC, false>(a, grid, smem, st);
+    return launch_scan_vd<V, EXACT, BIG, OCC, true>(a, grid, smem, st);
 }
 
 template <bool BIG, int OCC>

@@ -308,13 +308,13 @@ __device__ __forceinline__ void scan_rows_filtered(const ScanArgs &a, const floa
     }
 }
 
-// DYN (k <= 32, unfiltered): warps take their row groups from a global work counter instead of a fixed stride. SMs
+// DYN (unfiltered scans): warps take their row groups from a global work counter instead of a fixed stride. SMs
 // stream at visibly different rates (per-CTA timestamps: with the fixed stride the first CTA is done 25 % before the
 // last), so the fixed split leaves bandwidth idle at the end of every query; chunks of up to SCAN_CHUNK groups, single
 // groups near the end, next grab issued before the current chunk is processed. Which warp scans a row does not change
 // its score, and selection is a total order, so results are bit-identical either way.
 constexpr int SCAN_CHUNK = 8;
-template <int V, bool EXACT, int R, bool BIG, int OCC = (BIG ? 1 : 2), int LD = 0, bool FILT = false, bool DYN = (!BIG && !FILT)>
+template <int V, bool EXACT, int R, bool BIG, int OCC = (BIG ? 1 : 2), int LD = 0, bool FILT = false, bool DYN = !FILT>
 __global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const ScanArgs a)
 {
     extern __shared__ __align__(16) uint64_t smem[];
@@ -357,54 +357,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const Scan
     // synchronises every 8 iterations
     const uint64_t n_groups = (n + R - 1) / R, g_first = (uint64_t)blockIdx.x * SCAN_WARPS;
     const uint64_t n_iters = g_first < n_groups ? (n_groups - g_first + n_warps - 1) / n_warps : 0;
-    if constexpr (FILT) scan_rows_filtered<V, EXACT, R, LD>(a, qv, qzero, sel, lane, gw, n_warps);
-    else if constexpr (DYN) {
-        static_assert(!BIG, "the CTA-shared selector synchronises inside the loop: fixed trip counts only");
-        const uint32_t n_grp = (uint32_t)n_groups, nw2 = 2u * (uint32_t)n_warps;   // n_rows < 2^32, R >= 2
-        unsigned *work = a.ticket + 1;
-        uint32_t c_next = max(1u, min((uint32_t)SCAN_CHUNK, n_grp / nw2)), nxt = 0;
-        if (lane == 0) nxt = atomicAdd(work, c_next);
-        for (;;) {
-            const uint32_t c_start = __shfl_sync(FULL, nxt, 0);
-            if (c_start >= n_grp) break;
-            const uint32_t c_end = min(c_start + c_next, n_grp);
-            c_next = max(1u, min((uint32_t)SCAN_CHUNK, (n_grp - c_start) / nw2));
-            if (lane == 0) nxt = atomicAdd(work, c_next);
-            for (uint32_t grp = c_start; grp < c_end; ++grp) {
-                const uint64_t base = (uint64_t)grp * R;
-                float4 x[R][V];
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const uint64_t row = base + r;
-                    const float4 *p = a.rows + row * a.dim4 + lane;
-#pragma unroll
-                    for (int j = 0; j < V; ++j) {
-                        if (row < n && (EXACT || lane + 32 * j < a.dim4)) x[r][j] = ldg_stream<LD>(p + 32 * j);
-                        else x[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    float acc = 0.f;
-#pragma unroll
-                    for (int j = 0; j < V; ++j) {
-                        acc = fmaf(x[r][j].x, qv[j].x, acc); acc = fmaf(x[r][j].y, qv[j].y, acc);
-                        acc = fmaf(x[r][j].z, qv[j].z, acc); acc = fmaf(x[r][j].w, qv[j].w, acc);
-                    }
-                    acc = warp_sum_tree(acc);
-                    const float dist = qzero ? 0.f : fmaf(-0.5f, acc, 0.5f);  // (1 - cos)/2
-                    const uint64_t row = base + r;
-                    if (row < n && okey(dist) <= (uint32_t)(sel.thr >> 32)) {  // warp-uniform, rare
-                        const uint32_t id = a.ids[row];
-                        const uint64_t key = make_key(dist, id);
-                        if (key < sel.thr) sel.insert(key, lane);
-                    }
-                }
-            }
-        }
-    } else
-    for (uint64_t it = 0; it < n_iters; ++it) {
-        const uint64_t base = (gw + it * n_warps) * R;
+    // one group = R consecutive rows of this warp: R x V independent 128-bit loads, then R fixed FMA chains + trees
+    auto scan_group = [&](uint64_t base) {
         float4 x[R][V];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -433,7 +387,46 @@ __global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const Scan
                 if (key < sel.thr) sel.insert(key, lane);
             }
         }
-        if constexpr (BIG) { if ((it & 7) == 7) sel.sync_point(8 * R * SCAN_WARPS); }
+    };
+    if constexpr (FILT) scan_rows_filtered<V, EXACT, R, LD>(a, qv, qzero, sel, lane, gw, n_warps);
+    else if constexpr (DYN && !BIG) {
+        // per-warp grabs of up to SCAN_CHUNK groups
+        const uint32_t n_grp = (uint32_t)n_groups, nw2 = 2u * (uint32_t)n_warps;   // n_rows < 2^32, R >= 2
+        unsigned *work = a.ticket + 1;
+        uint32_t c_next = max(1u, min((uint32_t)SCAN_CHUNK, n_grp / nw2)), nxt = 0;
+        if (lane == 0) nxt = atomicAdd(work, c_next);
+        for (;;) {
+            const uint32_t c_start = __shfl_sync(FULL, nxt, 0);
+            if (c_start >= n_grp) break;
+            const uint32_t c_end = min(c_start + c_next, n_grp);
+            c_next = max(1u, min((uint32_t)SCAN_CHUNK, (n_grp - c_start) / nw2));
+            if (lane == 0) nxt = atomicAdd(work, c_next);
+            for (uint32_t grp = c_start; grp < c_end; ++grp) scan_group((uint64_t)grp * R);
+        }
+    } else if constexpr (DYN) {
+        // CTA-shared selector: the CTA synchronises at every sync point anyway, so the whole CTA grabs up to SCAN_CHUNK
+        // "CTA iterations" (one group per warp) at a time; thread 0 issues the next grab before the chunk is processed
+        __shared__ uint32_t s_start;
+        const uint32_t n_cit = (uint32_t)((n_groups + SCAN_WARPS - 1) / SCAN_WARPS), g2 = 2u * gridDim.x;
+        unsigned *work = a.ticket + 1;
+        uint32_t c_next = max(1u, min((uint32_t)SCAN_CHUNK, n_cit / g2)), nxt = 0;
+        if (threadIdx.x == 0) nxt = atomicAdd(work, c_next);
+        for (;;) {
+            if (threadIdx.x == 0) s_start = nxt;
+            __syncthreads();
+            const uint32_t c_start = s_start;
+            if (c_start >= n_cit) break;
+            const uint32_t c_end = min(c_start + c_next, n_cit);
+            c_next = max(1u, min((uint32_t)SCAN_CHUNK, (n_cit - c_start) / g2));
+            if (threadIdx.x == 0) nxt = atomicAdd(work, c_next);
+            for (uint32_t it = c_start; it < c_end; ++it) scan_group(((uint64_t)it * SCAN_WARPS + warp) * R);
+            sel.sync_point(SCAN_CHUNK * R * SCAN_WARPS);   // barrier inside: s_start is free to be rewritten
+        }
+    } else {
+        for (uint64_t it = 0; it < n_iters; ++it) {
+            scan_group((gw + it * n_warps) * R);
+            if constexpr (BIG) { if ((it & 7) == 7) sel.sync_point(8 * R * SCAN_WARPS); }
+        }
     }
 
     // ---- CTA top-k -> cand[blockIdx.x] ---------------------------------------------------
