@@ -168,7 +168,9 @@ def extras_batch(store, q_host, lib, n, d):
         gi, gd = store.search_ids(qs[49], 10)
         same1 = bool(np.array_equal(s_i[0], gi) and np.array_equal(s_d[0].view(np.uint32), gd.view(np.uint32)))
         store.set_tensor_prefilter(False)
-        return {"single_query_top10_via_tensor_prefilter": {
+        byte = extras_byte_prefilter(store, qs, lib, n, d)
+        return {"single_query_top10_via_byte_prefilter": byte,
+                "single_query_top10_via_tensor_prefilter": {
             "workload": f"{n}x{d} fp32 index, one query per call, top-10, csgpu_search_batch(b=1) with the tensor prefilter on",
             "ms_per_query": round(dt1 * 1e3, 3), "qps": round(1.0 / dt1, 1), "bit_identical_to_single_query_kernel": same1},
                 "batch_fp32_tensor_prefilter": {
@@ -177,6 +179,40 @@ def extras_batch(store, q_host, lib, n, d):
             "gpu_launches_per_batch": int(launches),
             "bit_identical_to_single_query_kernel": bool(same), "queries_checked": b // 128}}
     except Exception as e:  # noqa: BLE001 — the headline line must not depend on the secondary measurement
+        return {"error": repr(e)}
+
+
+def extras_byte_prefilter(store, qs, lib, n, d):
+    """Secondary: the headline query (one query, top-10, host buffers in and out) through VectorStore.search_ids with the
+    opt-in byte prefilter (csgpu_set_byte_prefilter: int8 shadow streamed as a filter with a proven bound + exact fp32
+    rescoring in the same launch, csrc/scan_i8.cuh). Every timed query is compared bit for bit with the fp32 scan kernel."""
+    try:
+        k, nq = 10, 64
+        want = [store.search_ids(qs[i], k) for i in range(nq)]       # fp32 scan kernel (the shadow does not exist yet)
+        store.set_byte_prefilter(True)
+        st0 = store.device_stats()
+        got = [store.search_ids(qs[i], k) for i in range(nq)]
+        same = sum(int(np.array_equal(g[0], w[0]) and np.array_equal(g[1].view(np.uint32), w[1].view(np.uint32)))
+                   for g, w in zip(got, want))
+        t0 = time.perf_counter()
+        reps = 200
+        dev = []
+        for i in range(reps):
+            store.search_ids(qs[i % nq], k)
+            dev.append(store.device_stats().last_search_us)
+        dt = (time.perf_counter() - t0) / reps                        # includes the stats call: an upper bound
+        st1 = store.device_stats()
+        shadow = int(st1.byte_shadow_bytes)
+        dev_ms = float(np.median(dev)) / 1e3
+        store.set_byte_prefilter(False)
+        return {"workload": f"{n}x{d} fp32 index, one query per call, top-{k}, csgpu_search with the byte prefilter on (host buffers)",
+                "ms_per_query": round(dt * 1e3, 4), "qps": round(1.0 / dt, 1), "device_ms": round(dev_ms, 4),
+                "shadow_bytes": shadow, "shadow_GBps": round(shadow / dev_ms / 1e6, 1),
+                "equivalent_fp32_GBps": round(n * d * 4 / dev_ms / 1e6, 1),
+                "bit_identical_to_fp32_scan_kernel": f"{same}/{nq}",
+                "int8_searches": int(st1.byte_searches - st0.byte_searches), "answered_by_fp32_scan_instead": int(st1.byte_fallbacks - st0.byte_fallbacks),
+                "candidates_last_query": int(st1.byte_candidates), "fp32_rows_rescored_last_query": int(st1.byte_rescored)}
+    except Exception as e:  # noqa: BLE001
         return {"error": repr(e)}
 
 

@@ -16,7 +16,7 @@ static uint64_t i8_min_rows()
 {
     static const uint64_t v = [] {
         const char *e = getenv("CSGPU_I8_MIN_ROWS");
-        return e && *e ? (uint64_t)strtoull(e, nullptr, 10) : (uint64_t)262144;
+        return e && *e ? (uint64_t)strtoull(e, nullptr, 10) : (uint64_t)524288;
     }();
     return v;
 }
