@@ -163,9 +163,11 @@ static uint32_t rows_in_flight(uint32_t dim4)
 static int enqueue_scan(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const float *q_dev, uint32_t k,
                         const uint64_t *bitmap_dev, uint64_t n_bits, bool with_zero_ids, uint64_t *out_keys,
                         cudaStream_t st, const ExchangeDev *xchg = nullptr, uint32_t seq = 0,
-                        const csgpu_predicate_t *pred = nullptr /* row-tag predicate; bitmap_dev is then its FILE bitmap */)
+                        const csgpu_predicate_t *pred = nullptr /* row-tag predicate; bitmap_dev is then its FILE bitmap */,
+                        const unsigned *run_if = nullptr /* device word: the launch is a no-op while it is 0 */)
 {
     ScanArgs a;
+    a.run_if = run_if;
     a.rows = reinterpret_cast<const float4 *>(sh->rows);
     a.ids = sh->ids;
     a.n_rows = sh->n_built;
@@ -200,6 +202,42 @@ static int enqueue_scan(const csgpu_index *ix, const Shard *sh, SearchCtx *c, co
     cudaError_t e = !big ? launch_scan_b<false, 2>(a, grid, smem, st) : launch_scan_b<true, 2>(a, grid, smem, st);
     if (e != cudaSuccess) return fail_cuda(e, "scan_topk_kernel launch", __FILE__, __LINE__);
     return CSGPU_OK;
+}
+
+// The fused exchange as a launch of its own: `local` (this rank's sorted top-k, device) -> global top-k in out_keys.
+static int enqueue_exchange(SearchCtx *c, const uint64_t *local, uint32_t k, uint64_t *out_keys, cudaStream_t st,
+                            const ExchangeDev *xchg, uint32_t seq)
+{
+    ScanArgs a{};
+    a.k = k;
+    const bool big = k > 32;
+    a.kpad = big ? ctabuf_cap(k) : 32;
+    a.cand = c->cand;
+    a.out_keys = out_keys;
+    a.xchg = xchg;
+    a.seq = seq;
+    const size_t smem = big ? (size_t)a.kpad * sizeof(uint64_t) : (size_t)SCAN_WARPS * 32 * sizeof(uint64_t);
+    if (big) exchange_keys_kernel<true><<<1, SCAN_THREADS, smem, st>>>(a, local);
+    else exchange_keys_kernel<false><<<1, SCAN_THREADS, smem, st>>>(a, local);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(e, "exchange_keys_kernel launch", __FILE__, __LINE__);
+    return CSGPU_OK;
+}
+
+// Device-resident single query on one shard: local top-k (xchg == nullptr) or the global one. With the byte prefilter
+// on, the int8 kernel runs first; the fp32 scan is enqueued behind it as a launch that does nothing unless the int8
+// kernel raised its device-side status word (the host cannot look without synchronising), then the exchange.
+static int enqueue_keys_device(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const float *q_dev, uint32_t k,
+                               uint64_t *out_keys, cudaStream_t st, const ExchangeDev *xchg, uint32_t seq)
+{
+    if (!i8_eligible(ix, k)) return enqueue_scan(ix, sh, c, q_dev, k, nullptr, 0, true, out_keys, st, xchg, seq);
+    uint64_t *local = xchg ? c->out_dev : out_keys;
+    int rc = enqueue_scan_i8(ix, sh, c, q_dev, k, true, local, st, /*host_status=*/false);
+    if (!rc) rc = enqueue_scan(ix, sh, c, q_dev, k, nullptr, 0, true, local, st, nullptr, 0, nullptr, i8_status_dev(c));
+    if (!rc && xchg) rc = enqueue_exchange(c, local, k, out_keys, st, xchg, seq);
+    ix->byte_searches.fetch_add(1, std::memory_order_relaxed);
+    return rc;
 }
 
 static int enqueue_merge(const uint64_t *keys_dev, uint32_t n_lists, uint32_t nq, uint32_t k, uint64_t *out, cudaStream_t st)
@@ -1226,7 +1264,7 @@ int csgpu_search_keys_device(const csgpu_index *ix, const float *q_dev, uint32_t
     // NOTE: the scratch (cand/ticket) of this context is in flight until `stream` drains; the
     // context is returned to the pool immediately, so callers must not run two device-entry
     // searches of one index concurrently on different streams (documented in INTEGRATION.md).
-    rc = enqueue_scan(ix, sh, c, q_dev, k, nullptr, 0, true, out_keys_dev, (cudaStream_t)stream);
+    rc = enqueue_keys_device(ix, sh, c, q_dev, k, out_keys_dev, (cudaStream_t)stream, nullptr, 0);
     ctx_release(sh, c);
     return rc;
 }
@@ -1385,7 +1423,7 @@ int csgpu_search_keys_exchange_device(const csgpu_index *ix, const float *q_dev,
     if (rc) return rc;
     DeviceGuard dg(sh->device);
     const uint32_t seq = ix->xchg->seq.fetch_add(1) + 1;   // every rank issues the same sequence of searches
-    rc = enqueue_scan(ix, sh, c, q_dev, k, nullptr, 0, true, out_keys_dev, (cudaStream_t)stream, ix->xchg->dev, seq);
+    rc = enqueue_keys_device(ix, sh, c, q_dev, k, out_keys_dev, (cudaStream_t)stream, ix->xchg->dev, seq);
     ctx_release(sh, c);
     return rc;
 }

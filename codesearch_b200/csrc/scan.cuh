@@ -56,6 +56,8 @@ struct ScanArgs {
     uint64_t *out_keys;      // [k] final keys, ascending, KEY_EMPTY padded
     const ExchangeDev *xchg = nullptr;  // non-null: out_keys receives the GLOBAL top-k over all ranks
     uint32_t seq = 0;                   // exchange sequence number of this query (same on every rank, >= 1)
+    const unsigned *run_if = nullptr;   // non-null: the whole launch is a no-op unless *run_if != 0 (device-side fallback of
+                                        // the byte prefilter: the host cannot look at the status without synchronising)
 };
 
 // LD selects the load flavour (tuned on B200, see profiles/): 0 = ld.global.nc.L1::no_allocate,
@@ -319,6 +321,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const Scan
 {
     extern __shared__ __align__(16) uint64_t smem[];
     __shared__ bool is_last;
+    if (a.run_if != nullptr && *reinterpret_cast<const volatile unsigned *>(a.run_if) == 0) return;   // CTA-uniform
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // k <= 32: per-warp register selector. k > 32: ONE candidate buffer per CTA (a.kpad = its capacity) + threshold
     using Sel = typename ScanSelOf<BIG>::type;
@@ -518,6 +521,25 @@ __global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const Scan
         }
     }
     if (threadIdx.x == 0) { a.ticket[0] = 0; a.ticket[1] = 0; }
+}
+
+// The fused exchange on its own (one CTA): this rank's sorted local top-k `local[0..k)` -> peer stores, flags, wait,
+// global merge -> a.out_keys. Used when the local keys come from a kernel without the exchange in its tail (the byte
+// prefilter's scan_i8_kernel, possibly followed by the conditional fp32 scan).
+template <bool BIG>
+__global__ void __launch_bounds__(SCAN_THREADS, 1) exchange_keys_kernel(const ScanArgs a, const uint64_t *__restrict__ local)
+{
+    extern __shared__ __align__(16) uint64_t smem[];
+    __shared__ unsigned cb_cnt;
+    __shared__ uint64_t cb_thr;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    using Sel = typename ScanSelOf<BIG>::type;
+    Sel sel;
+    if constexpr (BIG) { sel.cb.buf = smem; sel.cb.cnt = &cb_cnt; sel.cb.thr = &cb_thr; sel.cap = a.kpad; sel.k = a.k; }
+    else sel.init(a.k);
+    for (uint32_t j = threadIdx.x; j < a.k; j += blockDim.x) smem[j] = local[j];
+    __syncthreads();
+    exchange_and_merge<BIG>(a, sel, smem, warp, lane);
 }
 
 // Generic k-way merge: for query b = blockIdx.x, n_lists lists of k keys -> top-k. One CTA per query.

@@ -93,8 +93,10 @@ static cudaError_t launch_i8_v(const I8Args &a, uint32_t grid, cudaStream_t st)
     return cudaGetLastError();
 }
 
+const unsigned *i8_status_dev(const SearchCtx *c) { return reinterpret_cast<const I8Scratch *>(c->i8_scratch)->counters + 4; }
+
 int enqueue_scan_i8(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const float *q_dev, uint32_t k,
-                    bool with_zero_ids, uint64_t *out_keys, cudaStream_t st)
+                    bool with_zero_ids, uint64_t *out_keys, cudaStream_t st, bool host_status)
 {
     if (c->i8_scratch == nullptr) {
         CS_CUDA(cudaMalloc(&c->i8_scratch, sizeof(I8Scratch)));
@@ -124,7 +126,7 @@ int enqueue_scan_i8(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const 
     a.status = c->i8_status;
     static const bool timing = getenv("CSGPU_I8_TIMING") != nullptr;
     a.timing = timing ? s->timing : nullptr;
-    c->i8_status[0] = 1;   // a launch that never runs must not look like a success
+    if (host_status) c->i8_status[0] = 1;   // a launch that never runs must not look like a success
     const uint32_t R = (V <= 2) ? 8 : (V <= 4 ? 4 : 2);
     const uint64_t want = (sh->n_built + (uint64_t)I8_WARPS * 4 * R - 1) / ((uint64_t)I8_WARPS * 4 * R);
     const uint32_t grid = (uint32_t)std::min<uint64_t>(std::min<uint64_t>((uint64_t)sh->sm_count * 2, I8_MAX_GRID), std::max<uint64_t>(want, 1));
@@ -137,7 +139,7 @@ int enqueue_scan_i8(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const 
     }
 #undef CS_CASE
     if (e != cudaSuccess) return fail_cuda(e, "scan_i8_kernel launch", __FILE__, __LINE__);
-    if (timing) {   // diagnostic: per-CTA globaltimer stamps -> where a query's time goes (synchronises!)
+    if (timing && host_status) {   // diagnostic: per-CTA globaltimer stamps -> where a query's time goes (synchronises!)
         std::vector<unsigned long long> t((grid + 1) * 4);
         CS_CUDA(cudaStreamSynchronize(st));
         CS_CUDA(cudaMemcpy(t.data(), s->timing, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));

@@ -66,7 +66,8 @@ struct I8Args {
     uint32_t *warp_min;         // [gridDim.x * I8_WARPS] okey(ub); 0xFFFFFFFF between launches
     uint64_t *region;           // [gridDim.x][I8_REGION]
     uint64_t *final_list;       // [I8_FINAL_CAP]
-    unsigned *counters;         // [0] ticket, [1] final count, [2] overflow flag, [3] next row group — all 0 between launches
+    unsigned *counters;         // [0] ticket, [1] final count, [2] overflow flag, [3] next row group — all 0 between launches;
+                                // [4] device copy of status[0], rewritten by every launch (ScanArgs::run_if reads it)
     uint64_t *out_keys;         // [k] result keys
     unsigned long long *timing; // nullptr, or [gridDim.x + 1][4] globaltimer stamps (CSGPU_I8_TIMING=1: where the time goes)
     uint64_t *status;           // [0]: 0 = out_keys valid, 1 = answer with the exact scan instead;
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
     float4 qv[V];
     const float ss = load_unit_query<V, EXACT>(a.q, a.dim4, qv, lane);
     if (!(ss > 0.f)) {   // zero-norm query (every distance is 0.0): the exact kernel answers it
-        if (blockIdx.x == 0 && threadIdx.x == 0) { a.status[0] = 1ull; a.status[1] = 0ull; }
+        if (blockIdx.x == 0 && threadIdx.x == 0) { a.status[0] = 1ull; a.status[1] = 0ull; a.counters[4] = 1u; }
         return;
     }
 
@@ -409,7 +410,7 @@ __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
         overflow = s_cnt > I8_LIST_CAP;
     }
     if (overflow) {
-        if (threadIdx.x == 0) { a.status[0] = 1ull; a.status[1] = (uint64_t)min(total, 0xFFFFFFFFu); }
+        if (threadIdx.x == 0) { a.status[0] = 1ull; a.status[1] = (uint64_t)min(total, 0xFFFFFFFFu); a.counters[4] = 1u; }
         return;
     }
     float4 qv[V];   // the unit query again, for the exact arithmetic (not kept live through the streaming loop)
@@ -500,7 +501,7 @@ __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
     cta_sort_fast(C, fpad);
     for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) a.out_keys[j] = j < fpad ? C[j] : KEY_EMPTY;
     if (threadIdx.x == 0) {
-        a.status[0] = 0ull; a.status[1] = ((uint64_t)s_read << 32) | n_c;
+        a.status[0] = 0ull; a.status[1] = ((uint64_t)s_read << 32) | n_c; a.counters[4] = 0u;
         if (a.timing) { a.timing[gridDim.x * 4 + 0] = global_timer_ns(); a.timing[gridDim.x * 4 + 1] = blockIdx.x; }
     }
 }

@@ -46,7 +46,7 @@ def _assert_same(fast, plain, q, k):
 
 
 @pytest.mark.parametrize("n,d,ks", [
-    (300_000, 384, (1, 10, 32, 100, 128)),     # the headline shape; above the default row threshold
+    (300_000, 384, (1, 10, 32, 100, 128)),     # the headline shape
     (60_000, 128, (10, 33)),                   # V = 1: 32 rows per warp iteration
     (40_000, 320, (10, 100)),                  # dim4 = 80: padded shadow lines, predicated fp32 lanes
     (30_000, 768, (10, 128)),                  # V = 6 (BASELINE configs[4] width)
@@ -206,3 +206,73 @@ def test_byte_prefilter_concurrent_searches(cs):
     [t.start() for t in th]
     [t.join() for t in th]
     assert not errs, errs
+
+
+def test_byte_prefilter_device_entry_points_and_fused_exchange(cs, oracle):
+    """The device-resident entry points (rank-per-GPU sharding) take the int8 route too: the fp32 scan is enqueued
+    behind it as a launch that only runs if the int8 kernel raised its device-side status word, then the exchange runs
+    as a launch of its own. Three "ranks" on one GPU (three streams), compared with the unsharded plain index."""
+    import ctypes
+    import torch
+    from codesearch_b200 import _lib
+    from codesearch_b200.sharded import decode_keys
+    lib = _lib.load()
+    rng = np.random.default_rng(41)
+    n, d = 60_000, 384
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    rows[5] = 0.0
+    bounds = [0, 15_000, 38_000, n]
+    W = 3
+    stores = []
+    for a, b in zip(bounds, bounds[1:]):
+        st = cs.VectorStore.new(None, d)
+        st.append_rows(rows[a:b], np.arange(a, b, dtype=np.uint32))
+        st.set_byte_prefilter(True)
+        st.build_index()
+        stores.append(st)
+    whole = cs.VectorStore.new(None, d)
+    whole.append_rows(rows, np.arange(n, dtype=np.uint32))
+    whole.build_index()
+    qs = rng.standard_normal((6, d)).astype(np.float32)
+    qs[4] = 0.0                                                  # zero-norm query: the conditional fp32 scan answers
+    # local keys of one rank through csgpu_search_keys_device == host search of the same shard, bit for bit
+    for qi, k in enumerate([10, 100, 128, 200, 10]):
+        qd = torch.from_numpy(qs[qi]).cuda()
+        out = torch.empty(k, dtype=torch.int64, device="cuda")
+        _lib.check(lib.csgpu_search_keys_device(stores[1].handle, qd.data_ptr(), k, out.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        ids, dist = decode_keys(out.cpu().numpy())
+        stores[1].set_byte_prefilter(False)
+        hi, hd = stores[1].search_ids(qs[qi], k)
+        stores[1].set_byte_prefilter(True)
+        assert np.array_equal(ids, hi) and np.array_equal(dist.view(np.uint32), hd.view(np.uint32)), (qi, k)
+    assert stores[1].device_stats().byte_searches >= 4
+    # fused exchange
+    for r, st in enumerate(stores):
+        h = (ctypes.c_ubyte * 64)()
+        _lib.check(lib.csgpu_exchange_create(st.handle, W, r, h))
+    peers = (ctypes.c_void_p * W)(*[st.handle for st in stores])
+    for st in stores:
+        _lib.check(lib.csgpu_exchange_connect_local(st.handle, peers))
+    streams = [torch.cuda.Stream() for _ in range(W)]
+    for qi, k in enumerate([10, 10, 32, 100, 10, 1000]):
+        qd = torch.from_numpy(qs[qi]).cuda()
+        outs = [torch.empty(k, dtype=torch.int64, device="cuda") for _ in range(W)]
+        torch.cuda.synchronize()
+        for r, st in enumerate(stores):
+            _lib.check(lib.csgpu_search_keys_exchange_device(st.handle, qd.data_ptr(), k, outs[r].data_ptr(),
+                                                             streams[r].cuda_stream))
+        torch.cuda.synchronize()
+        gi, gd = whole.search_ids(qs[qi], k)
+        for r in range(W):
+            ids, dist = decode_keys(outs[r].cpu().numpy())
+            assert np.array_equal(ids, gi) and np.array_equal(dist.view(np.uint32), gd.view(np.uint32)), (qi, k, r)
+        if qi != 4:
+            oi, od, o64 = oracle.np_search(rows, qs[qi], k + MARGIN)
+            check_topk(gi, gd, oi, od, o64, min(k, n))
+    for st in stores:
+        t = ctypes.c_uint32(7)
+        _lib.check(lib.csgpu_exchange_status(st.handle, ctypes.byref(t)))
+        assert t.value == 0
+        lib.csgpu_exchange_destroy(st.handle)
