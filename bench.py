@@ -403,6 +403,9 @@ def main():
             line["dtype"] = "s8 filter + f32 rescoring"
             line["config"]["workload"] += "; byte prefilter on (csgpu_set_byte_prefilter): results bit-identical to the fp32 scan"
             line["config"]["l2"] = f"no flush needed: {shadow / 1e9:.2f} GB of shadow scanned per GPU per step >> 126 MB L2"
+            if world > 1 and args.exchange == "fused":
+                line["config"]["parallelism"] = (f"row-shard x{world} + int8 kernel, conditional fp32 scan (no-op), then the exchange as "
+                                                 "its own one-CTA launch (peer stores over NVLink, flags, merge)")
             try:
                 with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
                     traffic = json.load(f).get(f"scan_i8_kernel<3,true,4>|rows={n}|dim={d}|k={k}", {}).get("traffic_bytes")

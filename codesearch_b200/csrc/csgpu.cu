@@ -247,10 +247,10 @@ static int enqueue_merge(const uint64_t *keys_dev, uint32_t n_lists, uint32_t nq
     const size_t smem = big ? (size_t)2 * SCAN_WARPS * kpad * sizeof(uint64_t) : (size_t)SCAN_WARPS * 32 * sizeof(uint64_t);
     cudaError_t e;
     if (big) {
-        if (smem > 48 * 1024) {
-            e = cudaFuncSetAttribute(merge_keys_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return fail_cuda(e, "merge attr", __FILE__, __LINE__);
-        }
+        // always the ceiling (k = 1024): the attribute is per function and device, so per-launch values set by concurrent
+        // callers (or a smaller one set elsewhere) must never undercut a launch in flight
+        e = cudaFuncSetAttribute(merge_keys_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MERGE_SMEM_MAX);
+        if (e != cudaSuccess) return fail_cuda(e, "merge attr", __FILE__, __LINE__);
         merge_keys_kernel<true><<<nq, SCAN_THREADS, smem, st>>>(keys_dev, n_lists, k, kpad, out);
     } else {
         merge_keys_kernel<false><<<nq, SCAN_THREADS, smem, st>>>(keys_dev, n_lists, k, kpad, out);
@@ -660,51 +660,77 @@ static int search_multi(const csgpu_index *ix, const float *q, uint32_t nq, uint
 }
 
 // b (<= MAX_BATCH) variants of one user query: searched in ceil(b/8) passes, lists kept on the device, deduplicated
-// by chunk id (best distance wins) and cut to the best k by dedup_variants_kernel. Single-device index.
+// by chunk id (best distance wins) and cut to the best k by dedup_variants_kernel. On a multi-device index every
+// shard does that for its own rows (a chunk id lives on exactly one shard, so per-shard dedup + a k-way merge of the
+// shards' lists on device 0 is the global dedup).
 static int search_variants(const csgpu_index *ix, const float *q, uint32_t b, uint32_t k,
                            uint32_t *out_ids, float *out_dist, uint32_t *out_n)
 {
-    Shard *sh = ix->shards[0];
-    SearchCtx *c = nullptr;
-    int rc = ctx_acquire(ix, sh, &c);
-    if (rc) return rc;
+    const size_t G = ix->shards.size();
+    std::vector<SearchCtx *> ctx(G, nullptr);
+    int rc = CSGPU_OK;
+    auto release_all = [&]() { for (size_t g = 0; g < G; ++g) if (ctx[g]) ctx_release(ix->shards[g], ctx[g]); };
+    for (size_t g = 0; g < G && !rc; ++g) rc = ctx_acquire(ix, ix->shards[g], &ctx[g]);
+    if (rc) { release_all(); return rc; }
     auto body = [&]() -> int {
-        DeviceGuard dg(sh->device);
         const size_t qbytes = (size_t)b * ix->dim_pad * sizeof(float);
-        memset(c->q_pin, 0, qbytes);
-        for (uint32_t j = 0; j < b; ++j) memcpy(c->q_pin + (size_t)j * ix->dim_pad, q + (size_t)j * ix->dim, (size_t)ix->dim * sizeof(float));
-        CS_CUDA(cudaMemcpyAsync(c->q_dev, c->q_pin, qbytes, cudaMemcpyHostToDevice, c->stream));
-        CS_CUDA(cudaEventRecord(c->ev0, c->stream));
         const uint32_t MQ = multi_scan_max_queries();
         const bool multi_ok = multi_scan_supported(ix->dim4, k);
-        for (uint32_t j = 0; j < b;) {
-            const uint32_t nq = std::min(MQ, b - j);
-            int r;
-            if (multi_ok && nq >= 2) {
-                r = enqueue_scan_multi(ix, sh, c, c->q_dev + (size_t)j * ix->dim_pad, nq, k, true, c->out_dev + (size_t)j * k, c->stream);
-                j += nq;
-            } else {
-                r = enqueue_scan(ix, sh, c, c->q_dev + (size_t)j * ix->dim_pad, k, nullptr, 0, true, c->out_dev + (size_t)j * k, c->stream);
-                j += 1;
-            }
-            if (r) return r;
-        }
         const uint32_t total = b * k, npad = pow2_at_least(total, 64);
         const size_t smem = (size_t)npad * sizeof(uint64_t);
-        if (smem > 48 * 1024) CS_CUDA(cudaFuncSetAttribute(dedup_variants_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dedup_variants_kernel<<<1, SCAN_THREADS, smem, c->stream>>>(c->out_dev, total, npad, k, c->out_pin);
-        count_launch();
-        CS_CUDA(cudaGetLastError());
-        CS_CUDA(cudaEventRecord(c->ev1, c->stream));
-        CS_CUDA(cudaStreamSynchronize(c->stream));
+        for (size_t g = 0; g < G; ++g) {
+            Shard *sh = ix->shards[g];
+            SearchCtx *c = ctx[g];
+            DeviceGuard dg(sh->device);
+            memset(c->q_pin, 0, qbytes);
+            for (uint32_t j = 0; j < b; ++j) memcpy(c->q_pin + (size_t)j * ix->dim_pad, q + (size_t)j * ix->dim, (size_t)ix->dim * sizeof(float));
+            CS_CUDA(cudaMemcpyAsync(c->q_dev, c->q_pin, qbytes, cudaMemcpyHostToDevice, c->stream));
+            if (g == 0) CS_CUDA(cudaEventRecord(c->ev0, c->stream));
+            for (uint32_t j = 0; j < b;) {
+                const uint32_t nq = std::min(MQ, b - j);
+                int r;
+                if (multi_ok && nq >= 2) {
+                    r = enqueue_scan_multi(ix, sh, c, c->q_dev + (size_t)j * ix->dim_pad, nq, k, g == 0, c->out_dev + (size_t)j * k, c->stream);
+                    j += nq;
+                } else {
+                    r = enqueue_scan(ix, sh, c, c->q_dev + (size_t)j * ix->dim_pad, k, nullptr, 0, g == 0, c->out_dev + (size_t)j * k, c->stream);
+                    j += 1;
+                }
+                if (r) return r;
+            }
+            // always the ceiling (16 variants x k = 1024 keys): per-launch values from concurrent callers must not undercut each other
+            CS_CUDA(cudaFuncSetAttribute(dedup_variants_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)((size_t)MAX_BATCH * CSGPU_MAX_K * sizeof(uint64_t))));
+            // one device: straight into the pinned result; several: the shard's deduplicated list parks in its scratch
+            dedup_variants_kernel<<<1, SCAN_THREADS, smem, c->stream>>>(c->out_dev, total, npad, k, G == 1 ? c->out_pin : c->cand);
+            count_launch();
+            CS_CUDA(cudaGetLastError());
+        }
+        SearchCtx *c0 = ctx[0];
+        if (G > 1) {
+            DeviceGuard dg(ix->shards[0]->device);
+            for (size_t g = 1; g < G; ++g) {
+                DeviceGuard dg2(ix->shards[g]->device);
+                CS_CUDA(cudaMemcpyPeerAsync(c0->gather + g * k, ix->shards[0]->device, ctx[g]->cand, ix->shards[g]->device,
+                                            (size_t)k * sizeof(uint64_t), ctx[g]->stream));
+                CS_CUDA(cudaEventRecord(ctx[g]->ev1, ctx[g]->stream));
+            }
+            for (size_t g = 1; g < G; ++g) CS_CUDA(cudaStreamWaitEvent(c0->stream, ctx[g]->ev1, 0));
+            CS_CUDA(cudaMemcpyAsync(c0->gather, c0->cand, (size_t)k * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c0->stream));
+            int r = enqueue_merge(c0->gather, (uint32_t)G, 1, k, c0->out_pin, c0->stream);
+            if (r) return r;
+        }
+        DeviceGuard dg(ix->shards[0]->device);
+        CS_CUDA(cudaEventRecord(c0->ev1, c0->stream));
+        CS_CUDA(cudaStreamSynchronize(c0->stream));
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) ix->last_search_us.store(ms * 1000.f);
-        decode_keys(c->out_pin, k, out_ids, out_dist, out_n);
+        if (cudaEventElapsedTime(&ms, c0->ev0, c0->ev1) == cudaSuccess) ix->last_search_us.store(ms * 1000.f);
+        decode_keys(c0->out_pin, k, out_ids, out_dist, out_n);
         return CSGPU_OK;
     };
     rc = body();
-    if (rc) { DeviceGuard dg(sh->device); cudaStreamSynchronize(c->stream); }
-    ctx_release(sh, c);
+    if (rc) for (size_t g = 0; g < G; ++g) { DeviceGuard dg(ix->shards[g]->device); cudaStreamSynchronize(ctx[g]->stream); }
+    release_all();
     return rc;
 }
 
@@ -1242,7 +1268,6 @@ int csgpu_search_variants(const csgpu_index *ix, const float *q, uint32_t q_len,
     if (rc) return rc;
     if (b == 0 || b > MAX_BATCH) return fail(CSGPU_ERR_ARG, "b must be in [1, 16] query variants");
     if (ix->dtype != CSGPU_DTYPE_F32) return fail(CSGPU_ERR_ARG, "csgpu_search_variants needs an fp32 index");
-    if (ix->shards.size() != 1) return fail(CSGPU_ERR_ARG, "csgpu_search_variants: multi-device index is not implemented yet");
     if (!all_finite(q, q_len * b)) return fail(CSGPU_ERR_ARG, "query contains NaN/Inf");
     if (k == 0) return CSGPU_OK;
     return search_variants(ix, q, b, k, out_ids, out_dist, out_n);

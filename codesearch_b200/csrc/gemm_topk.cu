@@ -576,7 +576,9 @@ int batch_search(const csgpu_index *ix, const float *q, uint32_t b, uint32_t k,
             const size_t smem = big ? (size_t)2 * SCAN_WARPS * kpad * sizeof(uint64_t) : (size_t)SCAN_WARPS * 32 * sizeof(uint64_t);
             cudaError_t e = cudaSuccess;
             if (big) {
-                e = cudaFuncSetAttribute(merge_keys_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                // always the ceiling (k = 1024), never this launch's own size: the attribute is per function and device, and
+                // a small value set here would make a later, larger merge launched from csgpu.cu fail with "invalid argument"
+                e = cudaFuncSetAttribute(merge_keys_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MERGE_SMEM_MAX);
                 if (e == cudaSuccess) merge_keys_kernel<true><<<nq, SCAN_THREADS, smem, c0->stream>>>(gather, (uint32_t)G, k, kpad, c0->out);
             } else {
                 merge_keys_kernel<false><<<nq, SCAN_THREADS, smem, c0->stream>>>(gather, (uint32_t)G, k, kpad, c0->out);

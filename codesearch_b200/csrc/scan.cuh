@@ -542,6 +542,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) exchange_keys_kernel(const Sc
     exchange_and_merge<BIG>(a, sel, smem, warp, lane);
 }
 
+constexpr size_t MERGE_SMEM_MAX = (size_t)2 * SCAN_WARPS * 1024 * sizeof(uint64_t);   // merge_keys_kernel<true> at k = 1024
+
 // Generic k-way merge: for query b = blockIdx.x, n_lists lists of k keys -> top-k. One CTA per query.
 // keys layout [n_lists][nq = gridDim.x][k]; out [nq][k]. Used for the cross-GPU merge.
 template <bool BIG>

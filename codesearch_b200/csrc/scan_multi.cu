@@ -1,5 +1,7 @@
 // scan_multi.cu — instantiations + launcher of the multi-query scan (own translation unit so the
 // library builds in parallel).
+#include <algorithm>
+
 #include "index.h"
 #include "scan_multi.cuh"
 
@@ -28,7 +30,10 @@ static cudaError_t launch_cta(const MultiArgs &a, uint32_t grid, cudaStream_t st
 {
     auto kern = scan_multi_cta_topk_kernel<V, R, MQ>;
     const size_t smem = (size_t)MQ * a.dim4 * sizeof(float4) + (size_t)MQ * a.kpad * sizeof(uint64_t);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // the ceiling of this instantiation (k = 256 -> kpad = 1024), not this launch's own size: the attribute is per
+    // function, and concurrent searches with different k must not undercut each other's launches
+    const size_t smem_max = (size_t)MQ * 32 * V * sizeof(float4) + (size_t)MQ * 1024 * sizeof(uint64_t);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, smem_max));
     if (e != cudaSuccess) return e;
     kern<<<grid, SCAN_THREADS, smem, st>>>(a);
     g_kernel_launches.fetch_add(1, std::memory_order_relaxed);

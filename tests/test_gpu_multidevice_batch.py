@@ -55,3 +55,22 @@ def test_multidevice_batch_equals_single_device(cs, oracle, mode):
     else:
         gi, gd = two.search_ids(qs[3], k)                                    # bf16 single query = a batch of one
         assert np.array_equal(gi, c[0][3]) and np.array_equal(gd, c[1][3])
+
+
+@pytest.mark.parametrize("b,k", [(9, 200), (3, 10), (16, 100)])
+def test_multidevice_search_variants_equals_single_device(cs, oracle, b, k):
+    """csgpu_search_variants on a 2-device index: per-shard dedup + k-way merge == the single-device dedup, bit for bit,
+    and == the oracle's restatement of the HashMap/BinaryHeap pass (search/mod.rs:513-590)."""
+    rng = np.random.default_rng(b * 1000 + k)
+    n, d = 40_000, 384
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    rows[7] = 0.0
+    one, two = _pair(cs, rows)
+    base = rng.standard_normal(d).astype(np.float32)
+    qs = np.stack([base] + [base + np.float32(0.3) * rng.standard_normal(d).astype(np.float32) for _ in range(b - 1)])
+    ai, ad = one.search_variants_ids(qs, k)
+    ci, cd = two.search_variants_ids(qs, k)
+    assert np.array_equal(ai, ci) and np.array_equal(ad.view(np.uint32), cd.view(np.uint32))
+    lists = [one.search_ids(q, k) for q in qs]
+    wi, wd = oracle.dedup_variants(lists, k)
+    assert np.array_equal(ci, wi) and np.array_equal(cd, wd)
