@@ -26,9 +26,10 @@
 // have d_fp32 <= ub <= G, so a row with lb > G is strictly behind k rows and can never be in the top-k. Because the
 // top-k rows of 10M almost surely sit in k different warps' slices (2368 warps), G converges to the true k-th best ub.
 // Rows with lb <= G are appended to the CTA's candidate region (a burst while G is still +inf, then a trickle); at its
-// end each CTA re-filters its region against the now almost final G and appends the survivors to one global list. The
-// last CTA sorts that list by lb, rescores the best-looking a >= k rows (exact upper bound T_A of the final k-th
-// distance), then only the sorted prefix with lb <= T_A, and selects. One kernel launch per query.
+// end each CTA re-filters its region against the now almost final G, RESCORES the survivors (a handful per CTA, all
+// CTAs in parallel) from the fp32 rows and appends them to one global list as exact (distance, id) keys. The last CTA
+// adds the zero-norm ids and selects the top-k of that list (one rank sort for the usual ~100 keys; the CTA-shared
+// streaming selector of the big-k scan for longer lists). One kernel launch per query.
 //
 // Anything the fast path cannot bound — zero-norm query, candidate overflow (adversarial order / massive near-ties) —
 // raises the status word next to the result; the host then answers the query with scan_topk_kernel (still the GPU:
@@ -44,8 +45,8 @@ constexpr int I8_WARPS = 8;                          // streaming warps; warp I8
 constexpr int I8_THREADS = (I8_WARPS + 1) * 32;
 constexpr uint32_t I8_REGION = 4096;                 // candidate slots per CTA
 constexpr uint32_t I8_TAIL_CAP = 4096;               // keys the last CTA sorts (32 KB of shared memory)
-constexpr uint32_t I8_MAX_K = 128;
-constexpr uint32_t I8_LIST_CAP = I8_TAIL_CAP - I8_MAX_K;   // candidates on the global list (room for the zero-norm ids)
+constexpr uint32_t I8_MAX_K = 256;
+constexpr uint32_t I8_CTA_CAP = 2048;                // survivors one CTA rescoring at its end can hold (shared memory)
 constexpr uint32_t I8_MAX_WARPS = 148 * 2 * I8_WARPS;   // per-warp minima staged in shared memory by the helper
 constexpr float I8_SLACK = 3e-6f;
 constexpr int I8_CHUNK = 8;                          // row groups per grab of the work counter (shrinks near the end)
@@ -166,6 +167,51 @@ __device__ __forceinline__ float load_unit_query(const float *q, uint32_t dim4, 
     return ss;
 }
 
+// Exact keys for buf[0, n) in place: entries carry ROW indices in their low word and come back as (distance, chunk id)
+// keys computed with scan_topk_kernel's arithmetic, operation for operation (see rescore.cuh: rescore_range). Streaming
+// warps only; the caller synchronises.
+template <int V, bool EXACT>
+__device__ __forceinline__ void i8_rescore(const I8Args &a, const float4 (&qv)[V], uint64_t *buf, uint32_t n, int warp, int lane)
+{
+    constexpr int RR = V <= 4 ? 4 : (V <= 6 ? 2 : 1);
+    if (warp >= I8_WARPS) return;
+    for (uint32_t i0 = (uint32_t)warp * RR; i0 < n; i0 += I8_WARPS * RR) {
+        uint32_t rowi[RR];
+        bool lv[RR];
+#pragma unroll
+        for (int r = 0; r < RR; ++r) {
+            lv[r] = i0 + r < n;
+            rowi[r] = lv[r] ? (uint32_t)buf[i0 + r] : 0u;
+        }
+        __syncwarp();      // every lane has read its slots before lane 0 overwrites them below
+        uint32_t idv[RR];  // chunk ids ride along with the row loads
+#pragma unroll
+        for (int r = 0; r < RR; ++r) idv[r] = lv[r] ? __ldg(a.ids + rowi[r]) : 0u;
+        float4 xr[RR][V];
+#pragma unroll
+        for (int r = 0; r < RR; ++r) {
+            const float4 *p = a.rows + (size_t)rowi[r] * a.dim4 + lane;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                if (lv[r] && (EXACT || lane + 32 * j < a.dim4)) xr[r][j] = __ldg(p + 32 * j);
+                else xr[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RR; ++r) {
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                acc = fmaf(xr[r][j].x, qv[j].x, acc); acc = fmaf(xr[r][j].y, qv[j].y, acc);
+                acc = fmaf(xr[r][j].z, qv[j].z, acc); acc = fmaf(xr[r][j].w, qv[j].w, acc);
+            }
+            acc = warp_sum_tree(acc);
+            const float dist = fmaf(-0.5f, acc, 0.5f);
+            if (lv[r] && lane == 0) buf[i0 + r] = make_key(dist, idv[r]);
+        }
+    }
+}
+
 // V = float4 per lane of the fp32 query (ceil(dim4/32)) = 128-byte lines per shadow row; EXACT: dim4 == 32 V;
 // R = 4-row groups in flight per warp iteration (a warp streams 4 R rows = R x V x 512 B at a time).
 template <int V, bool EXACT, int R>
@@ -173,11 +219,12 @@ __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
 {
     constexpr int ROWS_PER_ITER = 4 * R;
     extern __shared__ __align__(16) uint64_t smem[];          // helper: per-warp minima (u32); tail: candidate keys
-    __shared__ unsigned s_cnt, s_done, s_last, s_end, s_bound, s_read;
+    __shared__ unsigned s_cnt, s_done, s_last, s_end, s_ns;
+    __shared__ uint64_t s_thr;
     __shared__ volatile uint32_t s_G;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & 7;
     const uint32_t k = a.k;
-    if (threadIdx.x == 0) { s_cnt = 0; s_done = 0; s_read = 0; s_G = 0xFFFFFFFFu; }
+    if (threadIdx.x == 0) { s_cnt = 0; s_done = 0; s_ns = 0; s_G = 0xFFFFFFFFu; }
     if (a.timing && threadIdx.x == 0) a.timing[blockIdx.x * 4 + 0] = global_timer_ns();
 
     float s_q, EQ, QN;
@@ -273,9 +320,17 @@ __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
         // current chunk is processed, so its latency never shows.
         uint32_t c_next = max(1u, min((uint32_t)I8_CHUNK, n_groups / (2u * n_warps))), nxt = 0;
         if (lane == 0) nxt = atomicAdd(a.counters + 3, c_next);
+        int patience = 64;   // x 500 ns per warp, in total
         for (;;) {
         const uint32_t c_start = __shfl_sync(FULL, nxt, 0);
         if (c_start >= n_groups) break;
+        // While G is still +inf every row is a candidate. If the grid starts staggered (first launch, SMs busy with
+        // another stream) the CTAs that run first must not swallow chunk after chunk in that mode and overflow their
+        // region: with the region a quarter full they wait — briefly, bounded — for the threshold to come alive.
+        while (patience > 0 && s_G == 0xFFFFFFFFu && *reinterpret_cast<volatile unsigned *>(&s_cnt) > I8_REGION / 4) {
+            __nanosleep(500);
+            --patience;
+        }
         const uint32_t c_end = min(c_start + c_next, n_groups);
         c_next = max(1u, min((uint32_t)I8_CHUNK, (n_groups - c_start) / (2u * n_warps)));
         if (lane == 0) nxt = atomicAdd(a.counters + 3, c_next);
@@ -343,7 +398,9 @@ __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
     __syncthreads();
     if (a.timing && threadIdx.x == 0) a.timing[blockIdx.x * 4 + 1] = global_timer_ns();
 
-    // ---- CTA end: re-filter the region against the (almost final) G, survivors -> the global list ----
+    // ---- CTA end: re-filter the region against the (almost final) G; the survivors (a handful per CTA) are rescored
+    //      HERE, by every CTA for its own rows in parallel, and go to the global list as exact keys ----
+    uint64_t *S = smem + I8_TAIL_CAP - I8_CTA_CAP;   // behind the helper's staging area
     {
         const unsigned cnt = s_cnt;
         if (cnt > I8_REGION && threadIdx.x == 0) atomicExch(a.counters + 2, 1u);
@@ -352,9 +409,25 @@ __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
         for (unsigned t = threadIdx.x; t < nreg; t += blockDim.x) {
             const uint64_t key = region[t];
             if ((uint32_t)(key >> 32) <= G) {
-                const unsigned pos = atomicAdd(a.counters + 1, 1u);
-                if (pos < I8_FINAL_CAP) a.final_list[pos] = key;
+                const unsigned pos = atomicAdd(&s_ns, 1u);
+                if (pos < I8_CTA_CAP) S[pos] = key;
             }
+        }
+    }
+    __syncthreads();
+    {
+        unsigned n_s = s_ns;   // CTA-uniform
+        if (n_s > I8_CTA_CAP) { if (threadIdx.x == 0) atomicExch(a.counters + 2, 1u); n_s = I8_CTA_CAP; }
+        if (n_s) {
+            float4 qv[V];   // the unit query again, for the exact arithmetic (not kept live through the streaming loop)
+            load_unit_query<V, EXACT>(a.q, a.dim4, qv, lane);
+            i8_rescore<V, EXACT>(a, qv, S, n_s, warp, lane);
+            __syncthreads();
+            if (threadIdx.x == 0) s_end = atomicAdd(a.counters + 1, n_s);
+            __syncthreads();
+            const unsigned base = s_end;
+            for (unsigned t = threadIdx.x; t < n_s; t += blockDim.x)
+                if (base + t < I8_FINAL_CAP) a.final_list[base + t] = S[t];
         }
     }
     __threadfence();
@@ -368,140 +441,40 @@ __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
     if (!s_last) return;
     __threadfence();
 
-    // ---- last CTA: sort by lb, rescore in two stages from the fp32 rows, select ----
+    // ---- last CTA: the global list holds exact (distance, id) keys; add the zero-norm ids and select ----
     uint64_t *C = smem;
     const unsigned total = *reinterpret_cast<volatile unsigned *>(a.counters + 1);
-    bool overflow = total > I8_FINAL_CAP || *reinterpret_cast<volatile unsigned *>(a.counters + 2) != 0;
-    // A long list (thresholds that were stale when the CTAs filtered: tiny corpora; or many near-ties) is filtered once
-    // more against the FINAL G — every warp's minimum is final now — while it is loaded.
-    uint32_t Gf = 0xFFFFFFFFu;
-    if (!overflow && total > 1024) {
-        if (warp == 0) {
-            uint32_t *vals = reinterpret_cast<uint32_t *>(smem);
-            const uint32_t n_pad = (n_warps + 127u) & ~127u;
-            for (uint32_t t = lane; t < n_pad; t += 32) vals[t] = t < n_warps ? ld_cg_u32(a.warp_min + t) : 0xFFFFFFFFu;
-            __syncwarp();
-            const uint32_t g = warp_kth_smallest(reinterpret_cast<const uint4 *>(vals), n_pad / 4, k, lane);
-            if (lane == 0) s_bound = g;
-        }
-        __syncthreads();
-        Gf = s_bound;
-    }
-    if (threadIdx.x == 0) s_cnt = 0;
+    const bool overflow = total > I8_FINAL_CAP || *reinterpret_cast<volatile unsigned *>(a.counters + 2) != 0;
     __syncthreads();
     // leave the scratch clean for the next launch (all other CTAs have retired their use of it)
     for (uint32_t t = threadIdx.x; t < n_warps; t += blockDim.x) a.warp_min[t] = 0xFFFFFFFFu;
     if (threadIdx.x == 0) { a.counters[0] = 0; a.counters[1] = 0; a.counters[2] = 0; a.counters[3] = 0; }
-    if (!overflow) {
-        const volatile uint64_t *fl = a.final_list;
-        if (total <= 1024) {
-            for (uint32_t t = threadIdx.x; t < total; t += blockDim.x) C[t] = fl[t];
-            if (threadIdx.x == 0) s_cnt = total;
-        } else {
-            for (uint32_t t = threadIdx.x; t < total; t += blockDim.x) {
-                const uint64_t key = fl[t];
-                if ((uint32_t)(key >> 32) <= Gf) {
-                    const unsigned pos = atomicAdd(&s_cnt, 1u);
-                    if (pos < I8_LIST_CAP) C[pos] = key;
-                }
-            }
-        }
-        __syncthreads();
-        overflow = s_cnt > I8_LIST_CAP;
-    }
     if (overflow) {
         if (threadIdx.x == 0) { a.status[0] = 1ull; a.status[1] = (uint64_t)min(total, 0xFFFFFFFFu); a.counters[4] = 1u; }
         return;
     }
-    float4 qv[V];   // the unit query again, for the exact arithmetic (not kept live through the streaming loop)
-    load_unit_query<V, EXACT>(a.q, a.dim4, qv, lane);
-    const uint32_t n_c = s_cnt;
-    const uint32_t npad = pow2_at_least(n_c, 32);
-    for (uint32_t t = n_c + threadIdx.x; t < npad; t += blockDim.x) C[t] = KEY_EMPTY;
-    __syncthreads();
-    cta_sort_fast(C, npad);   // ascending lb
-
-    auto rescore = [&](uint32_t lo, uint32_t hi, uint32_t bound32) -> unsigned {
-        // exact keys for C[lo, hi) in place (entries carry ROW indices); an entry whose lb exceeds bound32 is dropped
-        // unread. Same arithmetic as scan_topk_kernel (see rescore.cuh: rescore_range). Streaming warps only.
-        constexpr int RR = V <= 4 ? 4 : (V <= 6 ? 2 : 1);
-        unsigned read_rows = 0;
-        if (warp >= I8_WARPS) return 0;
-        for (uint32_t i0 = lo + (uint32_t)warp * RR; i0 < hi; i0 += I8_WARPS * RR) {
-            uint32_t rowi[RR];
-            bool lv[RR];
-#pragma unroll
-            for (int r = 0; r < RR; ++r) {
-                const uint32_t i = i0 + r;
-                const uint64_t key = i < hi ? C[i] : KEY_EMPTY;
-                lv[r] = key != KEY_EMPTY && (uint32_t)(key >> 32) <= bound32;
-                rowi[r] = (uint32_t)key;
-            }
-            __syncwarp();
-            uint32_t idv[RR];
-#pragma unroll
-            for (int r = 0; r < RR; ++r) idv[r] = lv[r] ? __ldg(a.ids + rowi[r]) : 0u;
-            float4 xr[RR][V];
-#pragma unroll
-            for (int r = 0; r < RR; ++r) {
-                const float4 *p = a.rows + (size_t)rowi[r] * a.dim4 + lane;
-#pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    if (lv[r] && (EXACT || lane + 32 * j < a.dim4)) xr[r][j] = __ldg(p + 32 * j);
-                    else xr[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < RR; ++r) {
-                float acc = 0.f;
-#pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    acc = fmaf(xr[r][j].x, qv[j].x, acc); acc = fmaf(xr[r][j].y, qv[j].y, acc);
-                    acc = fmaf(xr[r][j].z, qv[j].z, acc); acc = fmaf(xr[r][j].w, qv[j].w, acc);
-                }
-                acc = warp_sum_tree(acc);
-                const float dist = fmaf(-0.5f, acc, 0.5f);
-                if (i0 + r < hi && lane == 0) C[i0 + r] = lv[r] ? make_key(dist, idv[r]) : KEY_EMPTY;
-                read_rows += lv[r] ? 1u : 0u;
-            }
-        }
-        return read_rows;
-    };
-
-    // stage A: the a = pow2 >= max(32, k) best-looking candidates -> exact keys, sorted; T_A = k-th of them
-    const uint32_t a_pow = pow2_at_least(k, 32);
-    const uint32_t a_end = min(n_c, a_pow);
-    const uint32_t a_pad = n_c < a_pow ? npad : a_pow;
-    unsigned read_rows = rescore(0, a_end, 0xFFFFFFFFu);
-    __syncthreads();
-    cta_sort_fast(C, a_pad);
-    if (threadIdx.x == 0) {
-        s_bound = (a_end >= k && C[k - 1] != KEY_EMPTY) ? (uint32_t)(C[k - 1] >> 32) : 0xFFFFFFFFu;
-        s_end = n_c;
+    const volatile uint64_t *fl = a.final_list;
+    const uint32_t nz = min(a.n_zero, k);   // zero-norm rows: distance 0.0 (arroy pn*qn == 0), ascending id; the first k suffice
+    if (total + nz <= 512) {
+        // the common case (~115 keys at k = 10): one rank sort
+        const uint32_t n_all = total + nz, fpad = pow2_at_least(n_all, 32);
+        for (uint32_t t = threadIdx.x; t < fpad; t += blockDim.x)
+            C[t] = t < total ? fl[t] : (t < n_all ? make_key(0.f, a.zero_ids[t - total]) : KEY_EMPTY);
+        __syncthreads();
+        cta_sort_fast(C, fpad);
+        for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) a.out_keys[j] = j < fpad ? C[j] : KEY_EMPTY;
+    } else {
+        // any number of keys through the CTA-shared streaming selector of the big-k scan (topk.cuh)
+        CtaSel sel;
+        sel.cb.buf = C; sel.cb.cnt = &s_cnt; sel.cb.thr = &s_thr; sel.cap = ctabuf_cap(k); sel.k = k;
+        sel.reset();
+        cta_buf_stream(sel.cb, sel.cap, k, total, [&](uint64_t t) { return fl[t]; });
+        if (nz) cta_buf_stream(sel.cb, sel.cap, k, nz, [&](uint64_t t) { return make_key(0.f, a.zero_ids[t]); });
+        sel.finish();
+        for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) a.out_keys[j] = C[j];
     }
-    __syncthreads();
-    const uint32_t bound_a = s_bound;
-    // stage B: the (sorted) prefix of the rest whose lb can still beat T_A
-    for (uint32_t t = a_end + threadIdx.x; t < n_c; t += blockDim.x)
-        if ((uint32_t)(C[t] >> 32) > bound_a) atomicMin(&s_end, t);
-    __syncthreads();
-    const uint32_t b_end = s_end;
-    read_rows += rescore(a_end, b_end, bound_a);
-    if (lane == 0 && read_rows) atomicAdd(&s_read, read_rows);
-    __syncthreads();
-    uint32_t n_all = b_end;
-    if (a.n_zero) {   // zero-norm rows: distance 0.0 (arroy pn*qn == 0), ascending id; the first k suffice
-        const uint32_t nz = min(a.n_zero, k);
-        for (uint32_t t = threadIdx.x; t < nz; t += blockDim.x) C[n_all + t] = make_key(0.f, a.zero_ids[t]);
-        n_all += nz;
-    }
-    const uint32_t fpad = pow2_at_least(n_all, 32);
-    for (uint32_t t = n_all + threadIdx.x; t < fpad; t += blockDim.x) C[t] = KEY_EMPTY;
-    __syncthreads();
-    cta_sort_fast(C, fpad);
-    for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) a.out_keys[j] = j < fpad ? C[j] : KEY_EMPTY;
     if (threadIdx.x == 0) {
-        a.status[0] = 0ull; a.status[1] = ((uint64_t)s_read << 32) | n_c; a.counters[4] = 0u;
+        a.status[0] = 0ull; a.status[1] = ((uint64_t)total << 32) | total; a.counters[4] = 0u;
         if (a.timing) { a.timing[gridDim.x * 4 + 0] = global_timer_ns(); a.timing[gridDim.x * 4 + 1] = blockIdx.x; }
     }
 }
