@@ -121,6 +121,7 @@ static cudaError_t launch_scan_vd(const ScanArgs &a, uint32_t grid, size_t smem,
 {
     constexpr int R = (V <= 2) ? 8 : (V <= 4 ? 4 : 2);
     auto kern = scan_topk_kernel<V, EXACT, R, BIG, OCC, 0, false, DYN>;
+    if (grid == 0) { cudaFuncAttributes fa; return cudaFuncGetAttributes(&fa, kern); }   // preload only (preload_exchange_kernels)
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -202,6 +203,28 @@ static int enqueue_scan(const csgpu_index *ix, const Shard *sh, SearchCtx *c, co
     cudaError_t e = !big ? launch_scan_b<false, 2>(a, grid, smem, st) : launch_scan_b<true, 2>(a, grid, smem, st);
     if (e != cudaSuccess) return fail_cuda(e, "scan_topk_kernel launch", __FILE__, __LINE__);
     return CSGPU_OK;
+}
+
+// CUDA loads a kernel lazily at its first launch, and that load can wait for running kernels. A rank whose scan kernel
+// is already spinning in the exchange (waiting for a peer's flag) therefore must never be the reason a peer in the SAME
+// process cannot load the kernel it needs to answer — that is a 4-second timeout. Everything an exchange search can
+// launch is loaded up front, when the exchange (or the byte prefilter) is set up.
+static void preload_exchange_kernels(const csgpu_index *ix)
+{
+    for (const Shard *sh : ix->shards) {
+        DeviceGuard dg(sh->device);
+        ScanArgs a{};
+        a.dim4 = ix->dim4;
+        launch_scan_b<false, 2>(a, 0, 0, nullptr);
+        launch_scan_b<true, 2>(a, 0, 0, nullptr);
+        a.k = 10;  launch_scan_filtered(a, 0, 0, nullptr);
+        a.k = 100; launch_scan_filtered(a, 0, 0, nullptr);
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, exchange_keys_kernel<true>);
+        cudaFuncGetAttributes(&fa, exchange_keys_kernel<false>);
+        i8_preload(ix);
+        cudaGetLastError();
+    }
 }
 
 // The fused exchange as a launch of its own: `local` (this rank's sorted top-k, device) -> global top-k in out_keys.
@@ -1257,6 +1280,7 @@ int csgpu_set_byte_prefilter(csgpu_index *ix, uint32_t enabled)
     ix->byte_prefilter = enabled != 0;
     if (ix->built)
         for (Shard *sh : ix->shards) { int rc = i8_refresh(ix, sh); if (rc) { ix->byte_prefilter = false; return rc; } }
+    if (enabled) preload_exchange_kernels(ix);
     return CSGPU_OK;
 }
 
@@ -1392,6 +1416,7 @@ static int exchange_finish_connect(csgpu_index *ix)
     d.world = x->world; d.rank = x->rank; d.kmax = x->kmax;
     DeviceGuard dg(ix->shards[0]->device);
     CS_CUDA(cudaMemcpy(x->dev, &d, sizeof d, cudaMemcpyHostToDevice));
+    preload_exchange_kernels(ix);
     x->connected = true;
     return CSGPU_OK;
 }

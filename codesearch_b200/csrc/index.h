@@ -163,6 +163,7 @@ void i8_free_ctx(SearchCtx *c);
 bool i8_eligible(const csgpu_index *ix, uint32_t k);
 int enqueue_scan_i8(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const float *q_dev, uint32_t k,
                     bool with_zero_ids, uint64_t *out_keys, cudaStream_t st, bool host_status = true);
+void i8_preload(const csgpu_index *ix);
 const unsigned *i8_status_dev(const SearchCtx *c);   // device word: != 0 after a launch that needs the fp32 scan instead
 
 // snapshot.cu

@@ -11,6 +11,7 @@ static cudaError_t launch_f_v(const ScanArgs &a, uint32_t grid, size_t smem, cud
 {
     constexpr int R = (V <= 2) ? 8 : (V <= 4 ? 4 : 2);
     auto kern = scan_topk_kernel<V, EXACT, R, BIG, OCC, 0, true>;
+    if (grid == 0) { cudaFuncAttributes fa; return cudaFuncGetAttributes(&fa, kern); }   // preload only
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

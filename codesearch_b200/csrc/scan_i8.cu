@@ -87,6 +87,7 @@ static cudaError_t launch_i8_v(const I8Args &a, uint32_t grid, cudaStream_t st)
 {
     constexpr int R = (V <= 2) ? 8 : (V <= 4 ? 4 : 2);
     auto kern = scan_i8_kernel<V, EXACT, R>;
+    if (grid == 0) { cudaFuncAttributes fa; return cudaFuncGetAttributes(&fa, kern); }   // preload only
     const size_t smem = (size_t)I8_TAIL_CAP * sizeof(uint64_t);
     kern<<<grid, I8_THREADS, smem, st>>>(a);
     count_launch();
@@ -94,6 +95,21 @@ static cudaError_t launch_i8_v(const I8Args &a, uint32_t grid, cudaStream_t st)
 }
 
 const unsigned *i8_status_dev(const SearchCtx *c) { return reinterpret_cast<const I8Scratch *>(c->i8_scratch)->counters + 4; }
+
+// force-load this index's instantiation (see preload_exchange_kernels in csgpu.cu)
+void i8_preload(const csgpu_index *ix)
+{
+    const uint32_t V = i8_lines(ix->dim4);
+    const bool exact = (ix->dim4 % 32) == 0;
+    I8Args a{};
+#define CS_CASE(v) case v: if (exact) launch_i8_v<v, true>(a, 0, nullptr); else launch_i8_v<v, false>(a, 0, nullptr); break;
+    switch (V) {
+        CS_CASE(1) CS_CASE(2) CS_CASE(3) CS_CASE(4) CS_CASE(5) CS_CASE(6) CS_CASE(7) CS_CASE(8)
+        default: break;
+    }
+#undef CS_CASE
+    cudaGetLastError();
+}
 
 int enqueue_scan_i8(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const float *q_dev, uint32_t k,
                     bool with_zero_ids, uint64_t *out_keys, cudaStream_t st, bool host_status)

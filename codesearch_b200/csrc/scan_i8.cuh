@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
             // once a finite G is out, a refresh gives way as soon as the CTA's rows are done; the first one always completes
             const uint32_t g = warp_kth_smallest(reinterpret_cast<const uint4 *>(vals), n_pad / 4, k, lane,
                                                  s_G != 0xFFFFFFFFu ? &s_done : nullptr);
-            if (lane == 0 && g < s_G) s_G = g;
+            if (lane == 0) atomicMin(const_cast<uint32_t *>(&s_G), g);
             __syncwarp();
             // G settles within the first few rows of every warp: poll hard at first, then every ~4 us
             if (++rounds < 16) __nanosleep(100);
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
         }
         }
         asm volatile("bar.sync 1, %0;" :: "n"(I8_WARPS * 32));
-        if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned *>(&s_done) = 1u;
+        if (threadIdx.x == 0) atomicExch(&s_done, 1u);
     }
     __syncthreads();
     if (a.timing && threadIdx.x == 0) a.timing[blockIdx.x * 4 + 1] = global_timer_ns();

@@ -210,8 +210,12 @@ def test_byte_prefilter_concurrent_searches(cs):
     assert not errs, errs
 
 
-def test_byte_prefilter_device_entry_points_and_fused_exchange(cs, oracle):
-    """The device-resident entry points (rank-per-GPU sharding) take the int8 route too: the fp32 scan is enqueued
+@pytest.mark.parametrize("which", [(0, 1, 2), (1,)])
+def test_byte_prefilter_device_entry_points_and_fused_exchange(cs, oracle, which):
+    """`which` = the ranks with the byte prefilter on. Mixed ranks launch DIFFERENT kernels for the same query: a rank
+    already spinning in the exchange must not stall a peer's first (lazily loaded) launch — every kernel an exchange
+    search can use is loaded when the exchange / the prefilter is set up (preload_exchange_kernels).
+    The device-resident entry points (rank-per-GPU sharding) take the int8 route too: the fp32 scan is enqueued
     behind it as a launch that only runs if the int8 kernel raised its device-side status word, then the exchange runs
     as a launch of its own. Three "ranks" on one GPU (three streams), compared with the unsharded plain index."""
     import ctypes
@@ -229,7 +233,8 @@ def test_byte_prefilter_device_entry_points_and_fused_exchange(cs, oracle):
     for a, b in zip(bounds, bounds[1:]):
         st = cs.VectorStore.new(None, d)
         st.append_rows(rows[a:b], np.arange(a, b, dtype=np.uint32))
-        st.set_byte_prefilter(True)
+        if len(stores) in which:
+            st.set_byte_prefilter(True)
         st.build_index()
         stores.append(st)
     whole = cs.VectorStore.new(None, d)

@@ -2,6 +2,7 @@
 """Small end-to-end exercise of every kernel family, meant to run under compute-sanitizer
 (tools/sanitize.sh: memcheck, racecheck, synccheck). Sizes are tiny: the sanitizer slows kernels 10-100x."""
 import os, sys
+os.environ.setdefault("CSGPU_I8_MIN_ROWS", "1024")          # let the tiny corpora below take the byte-prefilter route
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -37,6 +38,16 @@ for j in (0, 69):
 st.delete_chunks(ids[::7])
 st.build_index()                                            # compaction + shadow rebuild
 st.search_batch_ids(qs[:3], 5)
+st.set_byte_prefilter(True)                                 # int8 shadow build + scan_i8_kernel (helper warp, CTA-end rescoring, tail)
+for k in (10, 100, 256):
+    gi, gd = st.search_ids(q, k)
+    st.set_byte_prefilter(False)
+    hi, hd = st.search_ids(q, k)
+    st.set_byte_prefilter(True)
+    assert np.array_equal(gi, hi) and np.array_equal(gd, hd)
+st.search_ids(np.zeros(d, np.float32), 10)                  # zero-norm query: status word -> fp32 kernel
+assert st.device_stats().byte_searches >= 4
+st.set_byte_prefilter(False)
 bf = cs.VectorStore.new(None, d, dtype="bf16")
 bf.append_rows(rows, ids)
 bf.build_index()
@@ -54,6 +65,7 @@ for a0, b0 in zip(bounds, bounds[1:]):
     s_.append_rows(rows[a0:b0], ids[a0:b0], tags[a0:b0])
     s_.build_index()
     stores.append(s_)
+stores[1].set_byte_prefilter(True)                          # one rank on the int8 route (+ conditional scan + exchange_keys_kernel)
 for r, s_ in enumerate(stores):
     h = (ctypes.c_ubyte * 64)()
     _lib.check(lib.csgpu_exchange_create(s_.handle, W, r, h))
