@@ -203,8 +203,39 @@ static void test_additive_methods()
     CHECK(language_from_path("noext") == Language::Unknown && language_from_path("C:\\r\\a.CPP") == Language::Cpp);
 }
 
+// opt-in byte prefilter (csgpu_set_byte_prefilter): same results, bit for bit, through the mirror
+static void test_byte_prefilter()
+{
+    const size_t d = 96, n = 6000;
+    VectorStore store = VectorStore::create("", d);
+    std::vector<EmbeddedChunk> chunks;
+    uint32_t state = 777u;
+    auto rnd = [&]() { state = state * 1664525u + 1013904223u; return ((state >> 8) & 0xFFFF) / 65535.0f - 0.5f; };
+    for (size_t i = 0; i < n; ++i) {
+        std::vector<float> e(d);
+        for (auto &x : e) x = rnd();
+        chunks.emplace_back(fn_chunk("chunk " + std::to_string(i), i, i + 1, "/r/a.rs"), e);
+    }
+    store.insert_chunks(chunks);
+    store.build_index();
+    std::vector<float> q(d);
+    for (auto &x : q) x = rnd();
+    auto plain = store.search(q, 50);
+    store.set_byte_prefilter(true);
+    auto fast = store.search(q, 50);
+    csgpu_stats_t st;
+    CHECK(csgpu_stats(store.handle(), &st) == CSGPU_OK);
+    CHECK(st.byte_searches == 1 && st.byte_fallbacks == 0 && st.byte_shadow_bytes == n * (128 + 4));
+    CHECK(fast.size() == plain.size());
+    for (size_t i = 0; i < std::min(fast.size(), plain.size()); ++i)
+        CHECK(fast[i].id == plain[i].id && fast[i].distance == plain[i].distance && fast[i].score == plain[i].score);
+    store.set_byte_prefilter(false);
+    CHECK(csgpu_stats(store.handle(), &st) == CSGPU_OK && st.byte_shadow_bytes == 0);
+}
+
 int main(int argc, char **argv)
 {
+    setenv("CSGPU_I8_MIN_ROWS", "1024", 0);   // read once by the library: lets test_byte_prefilter's small corpus take the int8 route
     if (argc > 1 && std::string(argv[1]) == "--expect-no-gpu") {
         try {
             VectorStore::create("", 4);
@@ -220,6 +251,7 @@ int main(int argc, char **argv)
         {"test_vector_store_creation", test_vector_store_creation}, {"test_insert_and_search", test_insert_and_search},
         {"test_stats", test_stats}, {"test_clear", test_clear}, {"test_get_chunk", test_get_chunk},
         {"test_persistence", test_persistence}, {"test_guards", test_guards}, {"test_additive_methods", test_additive_methods},
+        {"test_byte_prefilter", test_byte_prefilter},
     };
     for (auto &t : tests) {
         const int before = g_fail;

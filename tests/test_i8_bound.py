@@ -1,0 +1,135 @@
+"""CPU check of the byte prefilter's error bound (codesearch_b200/csrc/scan_i8.cuh) — the arithmetic of the proof, not
+the kernel: a numpy restatement of the shadow quantiser (per-row scale rounded UP to half, e_r = ||x - s_r xi||_2 rounded
+UP to half), of the query quantiser (e_q, ||q^||) and of the per-row bounds lb / ub, checked against the f64 distance
+and against the oracle's f32 / f64 evaluations of the same distance on random, clustered and degenerate rows. The GPU
+tests (tests/test_gpu_byte_prefilter.py) check the kernel's RESULTS; this file checks that the inequality the kernel relies on,  lb <= d_fp32 <= ub  for every row, holds with the constants the kernel uses.
+"""
+import zlib
+
+import numpy as np
+import pytest
+
+I8_SLACK = np.float32(3e-6)
+
+
+def _half_ru(x):
+    """float32 array -> float16 rounded toward +inf (CUDA __float2half_ru)."""
+    x = np.asarray(x, dtype=np.float32)
+    h = x.astype(np.float16)
+    low = h.astype(np.float32) < x
+    h = np.where(low, np.nextafter(h, np.float16(np.inf)), h)
+    return h.astype(np.float16)
+
+
+def quantise_rows(rows):
+    """shadow_i8_from_rows_kernel: (xi int8 [n, d], s_r f32 [n], e_r f32 [n]) from fp32 unit rows."""
+    rows = np.asarray(rows, dtype=np.float32)
+    amax = np.abs(rows).max(axis=1)
+    s = _half_ru(amax * np.float32(1.0 / 127.0) * np.float32(1.0000002))
+    s = np.maximum(s, _half_ru(np.float32(6.2e-5)))
+    sf = s.astype(np.float32)
+    inv = (np.float32(1.0) / sf).astype(np.float32)
+    xi = np.clip(np.rint(rows * inv[:, None]), -127, 127).astype(np.int32)
+    res = rows.astype(np.float64) - sf.astype(np.float64)[:, None] * xi
+    e = np.sqrt((res * res).sum(axis=1))
+    ef = (e * 1.000001).astype(np.float32) + np.float32(1e-12)
+    eh = _half_ru(ef * np.float32(1.0000002))
+    return xi, sf, eh.astype(np.float32)
+
+
+def quantise_query(qn):
+    """scan_i8_kernel prologue on the unit query qn (fp32): (qi, s_q, EQ, QN)."""
+    qn = np.asarray(qn, dtype=np.float32)
+    amax = np.abs(qn).max()
+    s_q = np.float32(amax * np.float32(1.0 / 127.0))
+    inv = np.float32(1.0) / s_q
+    qi = np.clip(np.rint(qn * inv), -127, 127).astype(np.int32)
+    r = (qn - s_q * qi.astype(np.float32)).astype(np.float32)
+    res2 = np.float32((r.astype(np.float32) ** 2).sum(dtype=np.float32))
+    EQ = np.float32(np.sqrt(res2) * np.float32(1.001) + np.float32(1e-9))
+    QN = np.float32(s_q * np.sqrt(np.float32((qi.astype(np.int64) ** 2).sum())) * np.float32(1.00001))
+    return qi, s_q, EQ, QN
+
+
+def bounds(rows, q):
+    rows = np.asarray(rows, dtype=np.float32)
+    nrm = np.sqrt((rows.astype(np.float64) ** 2).sum(axis=1))
+    unit = (rows / nrm[:, None]).astype(np.float32)                       # normalise_rows_kernel (f64 norm, f32 store)
+    q = np.asarray(q, dtype=np.float32)
+    qn = (q * (np.float32(1.0) / np.sqrt(np.float32((q * q).sum(dtype=np.float32))))).astype(np.float32)
+    xi, s_r, e_r = quantise_rows(unit)
+    qi, s_q, EQ, QN = quantise_query(qn)
+    idot = (xi.astype(np.int64) @ qi.astype(np.int64)).astype(np.float32)  # exact in int32 on the device
+    c_hat = idot * (s_q * s_r).astype(np.float32)
+    M = (QN * e_r + EQ).astype(np.float32)
+    lb = (np.float32(0.5) - np.float32(0.5) * (c_hat + M)).astype(np.float32) - I8_SLACK
+    ub = (np.float32(0.5) - np.float32(0.5) * (c_hat - M)).astype(np.float32) + I8_SLACK
+    d64 = 0.5 - 0.5 * (unit.astype(np.float64) @ qn.astype(np.float64))    # the real-number distance of the stored operands
+    return lb, ub, d64, unit, qn, M
+
+
+def _corpora():
+    rng = np.random.default_rng(2024)
+    out = []
+    for d in (384, 768, 1024, 100, 30):
+        out.append((f"gauss{d}", rng.standard_normal((4000, d)).astype(np.float32)))
+    c = rng.standard_normal((8, 384)).astype(np.float32)
+    out.append(("clusters", (np.repeat(c, 500, axis=0) + 0.02 * rng.standard_normal((4000, 384))).astype(np.float32)))
+    onehot = np.zeros((384, 384), np.float32)
+    onehot[np.arange(384), np.arange(384)] = 1.0
+    out.append(("onehot", onehot))
+    spiky = rng.standard_normal((1000, 384)).astype(np.float32) * 1e-3
+    spiky[np.arange(1000), rng.integers(0, 384, 1000)] = 5.0               # one dominant coordinate: the scale is set by it
+    out.append(("spiky", spiky))
+    out.append(("constant", np.ones((16, 384), np.float32) * np.linspace(1e-6, 1e3, 16, dtype=np.float32)[:, None]))
+    out.append(("tiny", (rng.standard_normal((500, 384)) * 1e-20).astype(np.float32)))
+    heavy = rng.standard_t(2, size=(2000, 384)).astype(np.float32)         # heavy tails: poor int8 resolution for the bulk
+    out.append(("heavy", heavy))
+    return out
+
+
+@pytest.mark.parametrize("name,rows", _corpora(), ids=[n for n, _ in _corpora()])
+def test_bounds_hold_for_every_row(oracle, name, rows):
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    d = rows.shape[1]
+    queries = [rng.standard_normal(d).astype(np.float32), rows[0] * np.float32(3.0), -rows[min(5, len(rows) - 1)],
+               (rows[:8].sum(axis=0) + 1e-3 * rng.standard_normal(d)).astype(np.float32)]
+    onehot_q = np.zeros(d, np.float32)
+    onehot_q[d // 2] = 1.0
+    queries.append(onehot_q)
+    for q in queries:
+        if not np.isfinite(q).all() or not (q.astype(np.float64) ** 2).sum() > 0:
+            continue
+        lb, ub, d64, unit, qn, M = bounds(rows, q)
+        assert np.all(lb <= ub)
+        assert np.all(lb.astype(np.float64) <= d64 + 1e-12), (name, float((lb - d64).max()))
+        assert np.all(d64 - 1e-12 <= ub.astype(np.float64)), (name, float((d64 - ub).max()))
+        # an fp32 evaluation of the same distance must sit inside [lb, ub] too — that is what I8_SLACK pays for: the
+        # oracle's strict sequential-f32 restatement (mode 0: one long f32 chain, a worse summation order than the
+        # kernel's 12-FMA chains + shuffle tree) and its f64 referee, both on the best-looking rows
+        for mode in (0, 1):
+            ids, d32, _ = oracle.search(unit, qn, min(64, len(rows)), mode=mode)
+            assert np.all(lb[ids] <= d32) and np.all(d32 <= ub[ids]), (name, mode)
+        # and the margin is useful, not vacuous: far below the spread of distances on ordinary data
+        if name.startswith("gauss") and d >= 384:
+            assert float(np.median(M)) < 0.03
+
+
+def test_threshold_argument_never_drops_a_top_k_row():
+    """The selection argument on top of the bound: G = k-th smallest ub over ANY k distinct rows; a row with lb > G is
+    strictly behind those k rows, so the exact top-k (ties by id) is contained in {rows with lb <= G}."""
+    rng = np.random.default_rng(5)
+    rows = rng.standard_normal((20000, 384)).astype(np.float32)
+    rows[100] = rows[99]
+    q = rng.standard_normal(384).astype(np.float32)
+    lb, ub, d64, unit, qn, _ = bounds(rows, q)
+    order = np.lexsort((np.arange(len(d64)), d64))
+    for k in (1, 10, 100, 256):
+        # the kernel's G: k-th smallest of per-warp minima = some k distinct rows' ub; the loosest legal choice of all
+        # is the k-th smallest ub overall... and ANY superset choice is looser still: emulate 2368 "warps" by striding
+        warp_min = np.array([ub[w::2368].min() for w in range(2368)])
+        G = np.sort(warp_min)[k - 1]
+        assert G >= np.sort(ub)[k - 1]                                    # never tighter than the true k-th smallest ub
+        survivors = set(np.nonzero(lb <= G)[0].tolist())
+        assert set(order[:k].tolist()) <= survivors
+        assert len(survivors) < 40 * k + 200                               # and it prunes: a few hundred of 20 000
