@@ -408,12 +408,12 @@ def main():
                                                  "its own one-CTA launch (peer stores over NVLink, flags, merge)")
             try:
                 with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-                    traffic = json.load(f).get(f"scan_i8_kernel<3,true,4>|rows={n}|dim={d}|k={k}", {}).get("traffic_bytes")
+                    traffic = json.load(f).get(f"scan_i8_kernel<3,true,6>|rows={n}|dim={d}|k={k}", {}).get("traffic_bytes")
             except Exception:  # noqa: BLE001
                 traffic = None
             line["roofline"].update({"achieved": round(shadow / (kern_ms * 1e-3) / 1e9, 1),
                                      "frac": round(shadow / (kern_ms * 1e-3) / 1e9 / peak, 4), "traffic": traffic,
-                                     "kernel": "scan_i8_kernel<3,true,4> (+ no-op conditional scan" + (" + exchange_keys_kernel)" if world > 1 and args.exchange == "fused" else ")"),
+                                     "kernel": "scan_i8_kernel<3,true,6> (+ no-op conditional scan" + (" + exchange_keys_kernel)" if world > 1 and args.exchange == "fused" else ")"),
                                      "algorithmic_bytes_per_launch": shadow,
                                      "frac_of_nominal_8TBps": round(shadow / (kern_ms * 1e-3) / 1e9 / 8000.0, 4),
                                      "equivalent_fp32_GBps_per_gpu": round(achieved, 1)})

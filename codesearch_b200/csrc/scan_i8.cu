@@ -82,16 +82,44 @@ struct I8Scratch {   // one cudaMalloc block per SearchCtx
     uint64_t region[(size_t)I8_MAX_GRID * I8_REGION];
 };
 
-template <int V, bool EXACT>
-static cudaError_t launch_i8_v(const I8Args &a, uint32_t grid, cudaStream_t st)
+static int i8_rows_override()   // CSGPU_I8_R (diagnostic): 4-row groups in flight per warp iteration, 0 = the tuned default
 {
-    constexpr int R = (V <= 2) ? 8 : (V <= 4 ? 4 : 2);
+    static const int v = [] { const char *e = getenv("CSGPU_I8_R"); return e && *e ? atoi(e) : 0; }();
+    return v;
+}
+
+template <int V, bool EXACT, int R>
+static cudaError_t launch_i8_vr(const I8Args &a, uint32_t grid, cudaStream_t st)
+{
     auto kern = scan_i8_kernel<V, EXACT, R>;
     if (grid == 0) { cudaFuncAttributes fa; return cudaFuncGetAttributes(&fa, kern); }   // preload only
     const size_t smem = (size_t)I8_TAIL_CAP * sizeof(uint64_t);
     kern<<<grid, I8_THREADS, smem, st>>>(a);
     count_launch();
     return cudaGetLastError();
+}
+
+// R per V. V = 3 (dim 384): 24 rows = 9 KB per warp iteration; measured on one box, A/B/A/B: R = 4 / 5 / 6 ->
+// 558 / 553-558 / 549-553 us per 10M-row query (more bytes in flight across the longer compute phase of this kernel).
+template <int V>
+constexpr int i8_default_r() { return (V <= 2) ? 8 : (V == 3 ? 6 : (V == 4 ? 4 : 2)); }
+
+static uint32_t i8_rows_per_iter(uint32_t V)
+{
+    const int o = i8_rows_override();
+    if (V == 3 && (o == 4 || o == 5)) return 4u * o;
+    return 4u * ((V <= 2) ? 8 : (V == 3 ? 6 : (V == 4 ? 4 : 2)));
+}
+
+template <int V, bool EXACT>
+static cudaError_t launch_i8_v(const I8Args &a, uint32_t grid, cudaStream_t st)
+{
+    if constexpr (V == 3) {
+        const int o = i8_rows_override();
+        if (o == 4) return launch_i8_vr<V, EXACT, 4>(a, grid, st);
+        if (o == 5) return launch_i8_vr<V, EXACT, 5>(a, grid, st);
+    }
+    return launch_i8_vr<V, EXACT, i8_default_r<V>()>(a, grid, st);
 }
 
 const unsigned *i8_status_dev(const SearchCtx *c) { return reinterpret_cast<const I8Scratch *>(c->i8_scratch)->counters + 4; }
@@ -143,8 +171,8 @@ int enqueue_scan_i8(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const 
     static const bool timing = getenv("CSGPU_I8_TIMING") != nullptr;
     a.timing = timing ? s->timing : nullptr;
     if (host_status) c->i8_status[0] = 1;   // a launch that never runs must not look like a success
-    const uint32_t R = (V <= 2) ? 8 : (V <= 4 ? 4 : 2);
-    const uint64_t want = (sh->n_built + (uint64_t)I8_WARPS * 4 * R - 1) / ((uint64_t)I8_WARPS * 4 * R);
+    const uint64_t per_cta = (uint64_t)I8_WARPS * i8_rows_per_iter(V);
+    const uint64_t want = (sh->n_built + per_cta - 1) / per_cta;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(std::min<uint64_t>((uint64_t)sh->sm_count * 2, I8_MAX_GRID), std::max<uint64_t>(want, 1));
     const bool exact = (ix->dim4 % 32) == 0;
     cudaError_t e;

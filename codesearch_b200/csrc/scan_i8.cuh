@@ -303,9 +303,14 @@ __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
                                                  s_G != 0xFFFFFFFFu ? &s_done : nullptr);
             if (lane == 0) atomicMin(const_cast<uint32_t *>(&s_G), g);
             __syncwarp();
-            // G settles within the first few rows of every warp: poll hard at first, then every ~4 us
+            // G settles within the first few rows of every warp: refresh back to back at first, then back off
+            // geometrically (4 us, 8 us, ... 64 us between refreshes) — a refresh is ~4k instructions on a scheduler the
+            // streaming warps share, and a slightly stale G only lets a few more candidates through
             if (++rounds < 16) __nanosleep(100);
-            else for (int w = 0; w < 16 && *reinterpret_cast<volatile unsigned *>(&s_done) == 0; ++w) __nanosleep(250);
+            else {
+                const int naps = min(256, 16 << min(rounds - 16, 4u));
+                for (int w = 0; w < naps && *reinterpret_cast<volatile unsigned *>(&s_done) == 0; ++w) __nanosleep(250);
+            }
         }
     } else {
         // ---- streaming warps ----
