@@ -192,6 +192,9 @@ int enqueue_scan_i8(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const 
             t0 = std::min(t0, t[b * 4]); st_hi = std::max(st_hi, t[b * 4]);
             s_lo = std::min(s_lo, t[b * 4 + 1]); s_hi = std::max(s_hi, t[b * 4 + 1]); e_hi = std::max(e_hi, t[b * 4 + 2]);
         }
+        unsigned n_inf = 0; unsigned long long surv = 0, surv_max = 0;
+        for (uint32_t b = 0; b < grid; ++b) { n_inf += (uint32_t)t[b * 4 + 3] == 0xFFFFFFFFu; surv += t[b * 4 + 3] >> 32; surv_max = std::max(surv_max, t[b * 4 + 3] >> 32); }
+        fprintf(stderr, "[i8 timing] CTAs whose G was still +inf at their end: %u of %u; survivors rescored: %llu (max %llu in one CTA)\n", n_inf, grid, surv, surv_max);
         fprintf(stderr, "[i8 timing] grid %u: last CTA start +%.1f us | streaming ends first +%.1f last +%.1f | last ticket +%.1f | tail done +%.1f us\n",
                 grid, (st_hi - t0) / 1e3, (s_lo - t0) / 1e3, (s_hi - t0) / 1e3, (e_hi - t0) / 1e3, (t[grid * 4] - t0) / 1e3);
     }

@@ -51,6 +51,7 @@ constexpr uint32_t I8_MAX_WARPS = 148 * 2 * I8_WARPS;   // per-warp minima stage
 constexpr float I8_SLACK = 3e-6f;
 constexpr int I8_CHUNK = 8;                          // row groups per grab of the work counter (shrinks near the end)
 constexpr uint32_t I8_FINAL_CAP = 65536;             // slots of the global candidate list (the tail re-filters it when long)
+constexpr int I8_HELPER_BATCH = 38;                  // warp-minima loads a helper lane keeps in flight (2 batches cover 2432)
 constexpr int I8_SEARCH_BITS = 20;                   // bits of the k-th-smallest search (the rest is rounded up)
 
 struct I8Args {
@@ -284,15 +285,17 @@ __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
         const uint32_t n_pad = (n_warps + 127u) & ~127u;   // whole uint4 per lane in the search
         unsigned rounds = 0;
         while (*reinterpret_cast<volatile unsigned *>(&s_done) == 0) {
-            for (uint32_t t0 = 0; t0 < n_pad; t0 += 32 * 8) {   // 8 independent L2 loads in flight per lane
-                uint32_t v[8];
+            // all of a lane's loads are issued before the first one is consumed: under the streaming load an L2 round
+            // trip is 2-3 us, and ten dependent batches made one refresh ~25 us (short scans then ended with G still +inf)
+            for (uint32_t t0 = 0; t0 < n_pad; t0 += 32 * I8_HELPER_BATCH) {
+                uint32_t v[I8_HELPER_BATCH];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < I8_HELPER_BATCH; ++u) {
                     const uint32_t t = t0 + u * 32 + lane;
                     v[u] = t < n_warps ? ld_cg_u32(a.warp_min + t) : 0xFFFFFFFFu;
                 }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < I8_HELPER_BATCH; ++u) {
                     const uint32_t t = t0 + u * 32 + lane;
                     if (t < n_pad) vals[t] = v[u];
                 }
@@ -406,6 +409,19 @@ __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
     // ---- CTA end: re-filter the region against the (almost final) G; the survivors (a handful per CTA) are rescored
     //      HERE, by every CTA for its own rows in parallel, and go to the global list as exact keys ----
     uint64_t *S = smem + I8_TAIL_CAP - I8_CTA_CAP;   // behind the helper's staging area
+    if (s_G == 0xFFFFFFFFu) {   // CTA-uniform (read after the barrier)
+        // A short scan can end before the helper has produced a finite G. Every warp of the grid that had rows has
+        // published its minimum by now, so the whole CTA fetches them in one round trip and warp 0 searches.
+        uint32_t *vals = reinterpret_cast<uint32_t *>(smem);
+        const uint32_t n_pad = (n_warps + 127u) & ~127u;
+        for (uint32_t t = threadIdx.x; t < n_pad; t += blockDim.x) vals[t] = t < n_warps ? ld_cg_u32(a.warp_min + t) : 0xFFFFFFFFu;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t g = warp_kth_smallest(reinterpret_cast<const uint4 *>(vals), n_pad / 4, k, lane);
+            if (lane == 0) s_G = g;
+        }
+        __syncthreads();
+    }
     {
         const unsigned cnt = s_cnt;
         if (cnt > I8_REGION && threadIdx.x == 0) atomicExch(a.counters + 2, 1u);
@@ -438,7 +454,7 @@ __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (a.timing) a.timing[blockIdx.x * 4 + 2] = global_timer_ns();
+        if (a.timing) { a.timing[blockIdx.x * 4 + 2] = global_timer_ns(); a.timing[blockIdx.x * 4 + 3] = ((unsigned long long)s_ns << 32) | s_G; }
         const unsigned t = atomicAdd(a.counters + 0, 1u);
         s_last = (t == gridDim.x - 1) ? 1u : 0u;
     }
