@@ -43,6 +43,7 @@ constexpr uint32_t MAX_BATCH = 16;       // queries per multi-query scan
 constexpr uint32_t PREFILTER_MIN_BATCH = 1;   // tensor prefilter on: every csgpu_search_batch goes to the tensor cores (9 queries:
                                               // 1.56 ms vs two multi-query passes at 3 ms each; it reads the 2-byte shadow, not the
                                               // 4-byte rows). csgpu_search itself always stays on the fp32 scan kernel.
+constexpr uint32_t I8_BEATS_MULTI = 4;        // byte prefilter on: this many single int8 queries beat one fp32 multi-query pass
 constexpr uint32_t GEMM_MIN_BATCH = 48;
 constexpr uint32_t GEMM_MIN_BATCH_NO_MULTI = 10;  // csgpu_search_batch switches to the SIMT GEMM path from here
 
@@ -783,9 +784,14 @@ static int search_coalesced(const csgpu_index *ix, const float *q, uint32_t k, u
         lk.unlock();
         int rc;
         const uint32_t nb = (uint32_t)batch.size();
-        if (nb == 1) {
-            PendingSearch *r = batch[0];
-            rc = search_one(ix, r->q, bk, nullptr, 0, r->out_ids, r->out_dist, r->out_n);
+        // byte prefilter on: up to I8_BEATS_MULTI queries are faster one after the other through the int8 kernel
+        // (0.57 ms each at 10M x 384) than together in one fp32 multi-query pass (2.3-2.6 ms for 2-4 queries)
+        if (nb == 1 || (nb <= I8_BEATS_MULTI && i8_eligible(ix, bk))) {
+            rc = CSGPU_OK;
+            for (uint32_t j = 0; j < nb && !rc; ++j) {
+                PendingSearch *r = batch[j];
+                rc = search_one(ix, r->q, bk, nullptr, 0, r->out_ids, r->out_dist, r->out_n);
+            }
         } else {
             std::vector<float> qs((size_t)nb * ix->dim);
             std::vector<uint32_t> ids((size_t)nb * bk), ns(nb);
@@ -1246,7 +1252,7 @@ int csgpu_search_batch(const csgpu_index *ix, const float *q, uint32_t q_len, ui
     const bool multi_ok = multi_scan_supported(ix->dim4, k);
     for (uint32_t j = 0; j < b;) {
         const uint32_t nq = std::min(MQ, b - j);
-        if (multi_ok && nq >= 2) {
+        if (multi_ok && nq >= 2 && !(nq <= I8_BEATS_MULTI && i8_eligible(ix, k))) {
             rc = search_multi(ix, q + (size_t)j * q_len, nq, k, out_ids + (size_t)j * k, out_dist + (size_t)j * k,
                               out_n ? out_n + j : nullptr);
             if (rc) return rc;

@@ -283,3 +283,18 @@ def test_byte_prefilter_device_entry_points_and_fused_exchange(cs, oracle, which
         _lib.check(lib.csgpu_exchange_status(st.handle, ctypes.byref(t)))
         assert t.value == 0
         lib.csgpu_exchange_destroy(st.handle)
+
+
+def test_byte_prefilter_small_groups_prefer_the_int8_kernel(cs):
+    """Host routing: with the prefilter on, up to 4 queries of a batch (or of a coalesced group) run one after the other
+    through the int8 kernel — faster than one fp32 multi-query pass — and larger groups keep the multi-query scan."""
+    rng = np.random.default_rng(9)
+    rows = rng.standard_normal((30_000, 384)).astype(np.float32)
+    fast, plain = _pair(cs, rows)
+    qs = rng.standard_normal((8, 384)).astype(np.float32)
+    for b, via_int8 in ((3, True), (4, True), (8, False)):
+        s0 = fast.device_stats().byte_searches
+        a = fast.search_batch_ids(qs[:b], 10)
+        c = plain.search_batch_ids(qs[:b], 10)
+        assert np.array_equal(a[0], c[0]) and np.array_equal(a[1].view(np.uint32), c[1].view(np.uint32)) and np.array_equal(a[2], c[2])
+        assert fast.device_stats().byte_searches - s0 == (b if via_int8 else 0), b

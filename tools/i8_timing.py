@@ -1,3 +1,8 @@
+#!/usr/bin/env python
+"""Where a byte-prefilter query's time goes: CSGPU_I8_TIMING=1 makes scan_i8_kernel stamp %globaltimer per CTA (start,
+end of streaming, ticket) and the library print, per launch, when the first / last CTA finished streaming, when the last
+ticket was taken, when the tail was done, and how many CTAs still had G = +inf at their end. (It synchronises after every
+launch: a diagnostic, never a benchmark.)   python tools/i8_timing.py <rows> <k>"""
 import os, sys
 os.environ["CSGPU_I8_TIMING"] = "1"
 sys.path.insert(0, os.getcwd())
