@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "index.h"
@@ -142,11 +143,21 @@ void i8_preload(const csgpu_index *ix)
 int enqueue_scan_i8(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const float *q_dev, uint32_t k,
                     bool with_zero_ids, uint64_t *out_keys, cudaStream_t st, bool host_status)
 {
-    if (c->i8_scratch == nullptr) {
-        CS_CUDA(cudaMalloc(&c->i8_scratch, sizeof(I8Scratch)));
-        CS_CUDA(cudaMemsetAsync(reinterpret_cast<I8Scratch *>(c->i8_scratch)->warp_min, 0xFF, sizeof(uint32_t) * I8_MAX_WARPS, st));
-        CS_CUDA(cudaMemsetAsync(reinterpret_cast<I8Scratch *>(c->i8_scratch)->counters, 0, sizeof(unsigned) * 8, st));
-        CS_CUDA(cudaHostAlloc(&c->i8_status, 8 * sizeof(uint64_t), cudaHostAllocMapped | cudaHostAllocPortable));
+    if (c->i8_scratch == nullptr) {   // first use of this context: both blocks or neither
+        void *scratch = nullptr;
+        uint64_t *status = nullptr;
+        cudaError_t ea = cudaMalloc(&scratch, sizeof(I8Scratch));
+        if (ea == cudaSuccess) ea = cudaHostAlloc(&status, 8 * sizeof(uint64_t), cudaHostAllocMapped | cudaHostAllocPortable);
+        if (ea == cudaSuccess) ea = cudaMemsetAsync(reinterpret_cast<I8Scratch *>(scratch)->warp_min, 0xFF, sizeof(uint32_t) * I8_MAX_WARPS, st);
+        if (ea == cudaSuccess) ea = cudaMemsetAsync(reinterpret_cast<I8Scratch *>(scratch)->counters, 0, sizeof(unsigned) * 8, st);
+        if (ea != cudaSuccess) {
+            cudaFree(scratch);
+            if (status) cudaFreeHost(status);
+            return fail_cuda(ea, "byte prefilter scratch", __FILE__, __LINE__);
+        }
+        memset(status, 0, 8 * sizeof(uint64_t));
+        c->i8_scratch = scratch;
+        c->i8_status = status;
     }
     I8Scratch *s = reinterpret_cast<I8Scratch *>(c->i8_scratch);
     const uint32_t V = i8_lines(ix->dim4);
