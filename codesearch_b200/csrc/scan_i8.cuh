@@ -234,7 +234,8 @@ __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
     // ---- query -> registers, scaled to unit length: scan_topk_kernel's prologue, operation for operation ----
     float4 qv[V];
     const float ss = load_unit_query<V, EXACT>(a.q, a.dim4, qv, lane);
-    if (!(ss > 0.f)) {   // zero-norm query (every distance is 0.0): the exact kernel answers it
+    if (!(ss > 0.f) || !(ss < 3.0e38f)) {   // zero-norm query (every distance is 0.0), or |q|^2 overflows fp32 (the scan
+                                            // kernel then scores every row 0.5): the exact kernel answers it
         if (blockIdx.x == 0 && threadIdx.x == 0) { a.status[0] = 1ull; a.status[1] = 0ull; a.counters[4] = 1u; }
         return;
     }

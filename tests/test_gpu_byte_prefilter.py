@@ -97,6 +97,14 @@ def test_byte_prefilter_routes_what_it_does_not_cover(cs):
     assert gi.tolist() == list(range(10)) and not gd.any()
     s = fast.device_stats()
     assert s.byte_searches == b0 + 1 and s.byte_fallbacks >= 1
+    # |q|^2 overflows fp32 (finite elements): the scan kernel's 1/sqrt(inf) = 0 scores every row 0.5 — same answer here
+    f0 = s.byte_fallbacks
+    big = (q * np.float32(1e19)).astype(np.float32)
+    assert np.isfinite(big).all()
+    _assert_same(fast, plain, big, 10)
+    assert fast.device_stats().byte_fallbacks == f0 + 1
+    _assert_same(fast, plain, (q * np.float32(1e-22)).astype(np.float32), 10)    # tiny but normalisable: the int8 route
+    assert fast.device_stats().byte_fallbacks == f0 + 1
 
 
 def test_byte_prefilter_adversarial_inputs(cs, oracle):

@@ -133,3 +133,36 @@ def test_threshold_argument_never_drops_a_top_k_row():
         survivors = set(np.nonzero(lb <= G)[0].tolist())
         assert set(order[:k].tolist()) <= survivors
         assert len(survivors) < 40 * k + 200                               # and it prunes: a few hundred of 20 000
+
+
+def test_bounds_hold_on_random_shapes_and_scales():
+    """Property test (hypothesis): any dim 1..1024, any row / query scale, sparse or dense, the inequality holds."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(d=st.integers(1, 1024), seed=st.integers(0, 2**31 - 1), log_scale=st.floats(-20, 20),
+           sparsity=st.floats(0.0, 0.98), qkind=st.sampled_from(["gauss", "row", "neg", "spike"]))
+    def prop(d, seed, log_scale, sparsity, qkind):
+        rng = np.random.default_rng(seed)
+        rows = (rng.standard_normal((64, d)) * np.exp(log_scale)).astype(np.float32)
+        rows[rng.random((64, d)) < sparsity] = 0.0
+        rows = rows[np.abs(rows).max(axis=1) > 0]                 # zero-norm rows never reach the shadow (compacted at build)
+        rows = rows[np.isfinite(rows).all(axis=1) & np.isfinite((rows.astype(np.float64) ** 2).sum(axis=1))]
+        if len(rows) == 0:
+            return
+        if qkind == "gauss":
+            q = rng.standard_normal(d).astype(np.float32)
+        elif qkind == "row":
+            q = rows[0].copy()
+        elif qkind == "neg":
+            q = -rows[-1]
+        else:
+            q = np.zeros(d, np.float32)
+            q[rng.integers(0, d)] = np.float32(np.exp(rng.uniform(-10, 10)))
+        ss = np.float32((q * q).sum(dtype=np.float32))
+        if not (np.isfinite(ss) and ss > 0):                      # the kernel hands zero-norm / overflowing queries to the fp32 scan
+            return
+        lb, ub, d64, *_ = bounds(rows, q)
+        assert np.all(lb.astype(np.float64) <= d64 + 1e-12) and np.all(d64 - 1e-12 <= ub.astype(np.float64))
+
+    prop()
