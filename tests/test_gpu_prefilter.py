@@ -183,3 +183,28 @@ def test_prefilter_full_size_10m(cs, oracle):
     for j in range(2):
         check_topk(oi[j], od[j], ri[j], rd[j], r64[j], k)
     assert 100 < st.device_stats().prefilter_rescored / b < 2000      # ~640 fp32 rows read per query, not the corpus
+
+
+@pytest.mark.parametrize("b,k", [(9, 200), (2, 10), (16, 100)])
+def test_prefilter_search_variants_equals_the_scan_route(cs, oracle, b, k):
+    """csgpu_search_variants with the tensor prefilter on: the variants run as one tensor-core batch and are deduplicated
+    on the host — same result, bit for bit, as the multi-query-scan + device-dedup route (and as the oracle's
+    restatement of src/search/mod.rs:513-590)."""
+    rng = np.random.default_rng(b * 100 + k)
+    n, d = 60_000, 384
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    rows[11] = 0.0
+    fast = _store(cs, rows, prefilter=True)
+    plain = _store(cs, rows, prefilter=False)
+    base = rng.standard_normal(d).astype(np.float32)
+    qs = np.stack([base] + [base + np.float32(0.3) * rng.standard_normal(d).astype(np.float32) for _ in range(b - 1)])
+    if b == 16:
+        qs[5] = 0.0                                              # a zero-norm variant: every distance 0.0, ids ascending
+    r0 = fast.device_stats().prefilter_rescored
+    gi, gd = fast.search_variants_ids(qs, k)
+    pi, pd = plain.search_variants_ids(qs, k)
+    assert np.array_equal(gi, pi) and np.array_equal(gd.view(np.uint32), pd.view(np.uint32))
+    assert fast.device_stats().prefilter_rescored != r0 or b == 16   # the tensor route really ran
+    lists = [plain.search_ids(q, k) for q in qs]
+    wi, wd = oracle.dedup_variants(lists, k)
+    assert np.array_equal(gi, wi) and np.array_equal(gd, wd)
