@@ -821,20 +821,18 @@ static int search_coalesced(const csgpu_index *ix, const float *q, uint32_t k, u
         lk.unlock();
         int rc;
         const uint32_t nb = (uint32_t)batch.size();
-        // byte prefilter on: up to I8_BEATS_MULTI queries are faster one after the other through the int8 kernel
-        // (0.57 ms each at 10M x 384) than together in one fp32 multi-query pass (2.3-2.6 ms for 2-4 queries)
-        if (nb == 1 || (nb <= I8_BEATS_MULTI && i8_eligible(ix, bk))) {
-            rc = CSGPU_OK;
-            for (uint32_t j = 0; j < nb && !rc; ++j) {
-                PendingSearch *r = batch[j];
-                rc = search_one(ix, r->q, bk, nullptr, 0, r->out_ids, r->out_dist, r->out_n);
-            }
+        if (nb == 1) {
+            PendingSearch *r = batch[0];
+            rc = search_one(ix, r->q, bk, nullptr, 0, r->out_ids, r->out_dist, r->out_n);
         } else {
+            // the group is a small batch: csgpu_search_batch picks the route (one multi-query pass; with the byte
+            // prefilter on, <= 4 queries one after the other through the int8 kernel; with the tensor prefilter on, one
+            // tensor-core batch) — every route returns what csgpu_search would
             std::vector<float> qs((size_t)nb * ix->dim);
             std::vector<uint32_t> ids((size_t)nb * bk), ns(nb);
             std::vector<float> dd((size_t)nb * bk);
             for (uint32_t j = 0; j < nb; ++j) memcpy(qs.data() + (size_t)j * ix->dim, batch[j]->q, (size_t)ix->dim * sizeof(float));
-            rc = search_multi(ix, qs.data(), nb, bk, ids.data(), dd.data(), ns.data());
+            rc = csgpu_search_batch(ix, qs.data(), ix->dim, nb, bk, ids.data(), dd.data(), ns.data());
             for (uint32_t j = 0; j < nb && !rc; ++j) {
                 memcpy(batch[j]->out_ids, ids.data() + (size_t)j * bk, (size_t)ns[j] * sizeof(uint32_t));
                 memcpy(batch[j]->out_dist, dd.data() + (size_t)j * bk, (size_t)ns[j] * sizeof(float));

@@ -30,13 +30,21 @@ def make_store(cs, rows, ids=None):
     return st
 
 
-def test_coalescing_concurrent_searches_bit_identical(cs, oracle):
+@pytest.mark.parametrize("shadow", ["none", "byte", "tensor"])
+def test_coalescing_concurrent_searches_bit_identical(cs, oracle, shadow):
+    """`shadow`: which opt-in shadow is on while the callers are coalesced — a coalesced group is a small batch and takes
+    whatever route csgpu_search_batch picks for it (multi-query scan / int8 singles / one tensor-core batch); every
+    route must hand each caller exactly what its own uncoalesced csgpu_search returns."""
     rng = np.random.default_rng(51)
     n, d, k = 400_000, 384, 200                                  # hybrid default retrieval limit (search/mod.rs:498-501)
     rows = rng.standard_normal((n, d)).astype(np.float32)
     st = make_store(cs, rows)
     qs = rng.standard_normal((9, d)).astype(np.float32)          # <= 9 query variants
-    want = [st.search_ids(q, k) for q in qs]                     # uncoalesced, one scan each
+    want = [st.search_ids(q, k) for q in qs]                     # uncoalesced, one fp32 scan each
+    if shadow == "byte":
+        st.set_byte_prefilter(True)
+    elif shadow == "tensor":
+        st.set_tensor_prefilter(True)
     st.set_coalescing(True)
     s0 = st.device_stats()
     got = [None] * 9
