@@ -20,6 +20,11 @@ static void launch_ldg(const ScanArgs &a, int sms, cudaStream_t st)
 {
     scan_topk_kernel<3, true, R, false, OCC, LD><<<sms * OCC, SCAN_THREADS, SCAN_WARPS * 32 * 8, st>>>(a);
 }
+template <int R, int OCC, int LD>
+static void launch_ldg_static(const ScanArgs &a, int sms, cudaStream_t st)   // fixed-stride row split (DYN = false)
+{
+    scan_topk_kernel<3, true, R, false, OCC, LD, false, false><<<sms * OCC, SCAN_THREADS, SCAN_WARPS * 32 * 8, st>>>(a);
+}
 template <int TILE, int STAGES>
 static void launch_tma(const ScanArgs &a, int sms, cudaStream_t st)
 {
@@ -60,6 +65,9 @@ int main(int argc, char **argv)
 
     std::vector<Variant> vs = {
         {"ldg R4 occ2 ld0 (baseline)", launch_ldg<4, 2, 0>},
+        {"static R4 occ2 ld0", launch_ldg_static<4, 2, 0>},
+        {"static R6 occ2 ld0", launch_ldg_static<6, 2, 0>},
+        {"ldg R5 occ2 ld0", launch_ldg<5, 2, 0>},
         {"ldg R4 occ2 ld1", launch_ldg<4, 2, 1>},
         {"ldg R4 occ2 ld2", launch_ldg<4, 2, 2>},
         {"ldg R4 occ2 ld3 (L2::256B)", launch_ldg<4, 2, 3>},
@@ -83,6 +91,8 @@ int main(int argc, char **argv)
         {"tma tile32 x3 occ1", launch_tma<32, 3>},
         {"tma tile16 x4 occ2", launch_tma2<16, 4>},
         {"tma tile8 x8 occ2", launch_tma2<8, 8>},
+        {"ldg R4 occ2 ld0 (baseline again)", launch_ldg<4, 2, 0>},
+        {"ldg R6 occ2 ld0 (again)", launch_ldg<6, 2, 0>},
     };
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     std::vector<uint64_t> href(k), hout(k);
