@@ -166,3 +166,35 @@ def test_bounds_hold_on_random_shapes_and_scales():
         assert np.all(lb.astype(np.float64) <= d64 + 1e-12) and np.all(d64 - 1e-12 <= ub.astype(np.float64))
 
     prop()
+
+
+def test_kth_smallest_bit_search_is_an_upper_bound_within_its_resolution():
+    """warp_kth_smallest (scan_i8.cuh) restated: greedy search on the top 20 bits of the order-preserving keys, low 12
+    bits set — the result must never be below the true k-th smallest (validity of G) and at most 2^12 - 1 key steps
+    above it (its resolution), for any multiset incl. unpublished (+inf) entries."""
+    def kth(vals, k, bits=20):
+        ans = 0
+        for b in range(31, 31 - bits, -1):
+            cand = ans | ((1 << b) - 1)
+            if int((vals <= cand).sum()) < k:
+                ans |= 1 << b
+        return ans | ((1 << (32 - bits)) - 1)
+
+    def okey(f):
+        u = np.asarray(f, dtype=np.float32).view(np.uint32).astype(np.uint64)
+        return np.where(u >> 31, u ^ 0xFFFFFFFF, u ^ 0x80000000).astype(np.uint64)
+
+    rng = np.random.default_rng(8)
+    for trial in range(200):
+        n = int(rng.integers(1, 2400))
+        d = (0.5 - 0.5 * rng.standard_normal(n) * 0.05).astype(np.float32)          # distances around 0.5
+        vals = okey(d)
+        vals[rng.random(n) < rng.random()] = 0xFFFFFFFF                              # warps that have not published yet
+        vals = np.concatenate([vals, np.full((-n) % 128, 0xFFFFFFFF, np.uint64)])    # the kernel's padding
+        for k in (1, 10, 100, 256):
+            g = kth(vals, k)
+            true = int(np.sort(vals)[k - 1]) if k <= len(vals) else 0xFFFFFFFF
+            assert g >= true
+            assert g - true < (1 << 12) or true == 0xFFFFFFFF
+            if true == 0xFFFFFFFF:
+                assert g == 0xFFFFFFFF                                               # fewer than k published: G stays +inf
