@@ -93,7 +93,7 @@ def test_two_shards_byte_prefilter(pair):
         for j, k in enumerate((10, 1, 100, 128, 10)):
             assert _same(two.search_ids(qs[j], k), one.search_ids(qs[j], k)), k
         s1 = two.device_stats()
-        assert s1.byte_searches - s0.byte_searches == 5 and s1.byte_fallbacks == s0.byte_fallbacks
+        assert s1.byte_searches - s0.byte_searches == 5 and s1.byte_fallbacks - s0.byte_fallbacks <= 1
         z = np.zeros(d, np.float32)                              # zero-norm query: both shards report it, fp32 kernel answers
         assert _same(two.search_ids(z, 10), one.search_ids(z, 10))
         assert two.device_stats().byte_fallbacks == s1.byte_fallbacks + 1
