@@ -102,6 +102,8 @@ SIGNATURES = {
     "csgpu_exchange_connect_local": (ctypes.c_int, [_vp, ctypes.POINTER(_vp)]),
     "csgpu_search_keys_exchange_device": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, _vp, _vp]),
     "csgpu_exchange_status": (ctypes.c_int, [_vp, _u32p]),
+    "csgpu_exchange_set_timeout_ms": (ctypes.c_int, [_vp, ctypes.c_uint32]),
+    "csgpu_exchange_wait_stats": (ctypes.c_int, [_vp, _u64p, ctypes.c_uint32, _u32p]),
     "csgpu_exchange_destroy": (None, [_vp]),
     "csgpu_decode_keys": (None, [_u64p, ctypes.c_uint32, _u32p, _f32p, _u32p]),
     "csgpu_append_synthetic": (ctypes.c_int, [_vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32]),

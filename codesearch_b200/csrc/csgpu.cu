@@ -33,6 +33,7 @@ int fail_cuda(cudaError_t e, const char *what, const char *file, int line)
     return (e == cudaErrorMemoryAllocation) ? CSGPU_ERR_OOM : CSGPU_ERR_CUDA;
 }
 
+
 void count_launch(uint64_t n) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ---------------------------------------------------------------------------------------
@@ -51,8 +52,10 @@ static int ctx_create(const csgpu_index *ix, Shard *sh, SearchCtx **out)
 {
     DeviceGuard g(sh->device);
     SearchCtx *c = new SearchCtx();
+    *out = c;   // set before the first fallible call: the caller destroys a partially built context
     c->device = sh->device;
     CS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CS_CUDA(cudaEventCreateWithFlags(&c->busy, cudaEventDisableTiming));
     CS_CUDA(cudaEventCreate(&c->ev0));
     CS_CUDA(cudaEventCreate(&c->ev1));
     CS_CUDA(cudaMalloc(&c->q_dev, (size_t)MAX_BATCH * ix->dim_pad * sizeof(float)));
@@ -65,7 +68,7 @@ static int ctx_create(const csgpu_index *ix, Shard *sh, SearchCtx **out)
     CS_CUDA(cudaMalloc(&c->out_dev, (size_t)MAX_BATCH * CSGPU_MAX_K * sizeof(uint64_t)));
     CS_CUDA(cudaHostAlloc(&c->out_pin, (size_t)MAX_BATCH * CSGPU_MAX_K * sizeof(uint64_t),
                           cudaHostAllocMapped | cudaHostAllocPortable));
-    *out = c;
+    if (ix->byte_prefilter) return i8_prepare_ctx(c);   // the scratch is born with the context, not inside its first search
     return CSGPU_OK;
 }
 
@@ -76,6 +79,7 @@ static void ctx_destroy(SearchCtx *c)
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->busy) cudaEventDestroy(c->busy);
     cudaFree(c->q_dev); cudaFreeHost(c->q_pin); cudaFree(c->cand); cudaFree(c->gather); cudaFree(c->ticket);
     cudaFree(c->out_dev); cudaFreeHost(c->out_pin); cudaFree(c->bitmap_dev);
     i8_free_ctx(c);
@@ -90,17 +94,68 @@ static int ctx_acquire(const csgpu_index *ix, Shard *sh, SearchCtx **out)
     }
     SearchCtx *c = nullptr;
     int rc = ctx_create(ix, sh, &c);
-    if (rc) { ctx_destroy(c); return rc; }
+    if (rc) { ctx_destroy(c); *out = nullptr; return rc; }
     std::lock_guard<std::mutex> lk(sh->ctx_mu);
     sh->all_ctx.push_back(c);
     *out = c;
     return CSGPU_OK;
 }
 
+// Device entry points (csgpu_search_keys_device & co) only ENQUEUE on the caller's stream, so the context's scratch
+// (cand / ticket / work counter / int8 scratch) is in flight after the call returns. They therefore use one dedicated
+// context per shard that the host-pointer searches never touch, and order successive uses with an event: the next
+// device-entry call makes ITS stream wait for the previous call's work, whatever stream that was on. (Round-1 advisor
+// finding: the context went back to the shared pool while its kernels were still running.) dev_ctx_begin returns with
+// sh->dev_mu held; dev_ctx_end records the event and unlocks.
+static int dev_ctx_begin(const csgpu_index *ix, Shard *sh, cudaStream_t st, SearchCtx **out)
+{
+    sh->dev_mu.lock();
+    if (sh->dev_ctx == nullptr) {
+        SearchCtx *c = nullptr;
+        int rc = ctx_create(ix, sh, &c);
+        if (rc) { ctx_destroy(c); sh->dev_mu.unlock(); return rc; }
+        sh->dev_ctx = c;
+    }
+    SearchCtx *c = sh->dev_ctx;
+    if (ix->byte_prefilter && c->i8_scratch == nullptr) {
+        DeviceGuard g(sh->device);
+        int rc = i8_prepare_ctx(c);
+        if (rc) { sh->dev_mu.unlock(); return rc; }
+    }
+    if (c->busy_recorded) {
+        DeviceGuard g(sh->device);
+        cudaError_t e = cudaStreamWaitEvent(st, c->busy, 0);
+        if (e != cudaSuccess) { sh->dev_mu.unlock(); return fail_cuda(e, "cudaStreamWaitEvent", __FILE__, __LINE__); }
+    }
+    *out = c;
+    return CSGPU_OK;
+}
+
+static void dev_ctx_end(Shard *sh, SearchCtx *c, cudaStream_t st)
+{
+    {
+        DeviceGuard g(sh->device);
+        if (cudaEventRecord(c->busy, st) == cudaSuccess) c->busy_recorded = true; else cudaGetLastError();
+    }
+    sh->dev_mu.unlock();
+}
+
 static void ctx_release(Shard *sh, SearchCtx *c)
 {
     std::lock_guard<std::mutex> lk(sh->ctx_mu);
     sh->free_ctx.push_back(c);
+}
+
+// one search context per shard with its int8 scratch allocated, parked in the pool: the first query pays no cudaMalloc
+static int warm_i8_contexts(csgpu_index *ix)
+{
+    for (Shard *sh : ix->shards) {
+        SearchCtx *c = nullptr;
+        int rc = ctx_acquire(ix, sh, &c);
+        if (!rc) { DeviceGuard dg(sh->device); rc = i8_prepare_ctx(c); ctx_release(sh, c); }
+        if (rc) return rc;
+    }
+    return CSGPU_OK;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -307,7 +362,9 @@ static int enqueue_scan_multi(const csgpu_index *ix, const Shard *sh, SearchCtx 
     a.out_keys = out_keys;
     const uint32_t R = (ix->dim4 / 32 <= 4) ? 4 : 2;
     const uint64_t want = (sh->n_built + SCAN_WARPS * R - 1) / (SCAN_WARPS * R);
-    const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sh->sm_count * multi_scan_ctas_per_sm(a.kpad), std::max<uint64_t>(want, 1));
+    uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sh->sm_count * multi_scan_ctas_per_sm(a.kpad), std::max<uint64_t>(want, 1));
+    // cand holds nq x grid x k keys: never launch more CTAs than the scratch was sized for (a part with more SMs than 148)
+    grid = (uint32_t)std::min<uint64_t>(grid, std::max<uint64_t>(c->cand_cap / ((uint64_t)nq * std::max(k, 1u)), 1));
     cudaError_t e = launch_scan_multi(a, grid, st);
     if (e != cudaSuccess) return fail_cuda(e, "scan_multi_topk_kernel launch", __FILE__, __LINE__);
     return CSGPU_OK;
@@ -539,6 +596,182 @@ void decode_keys(const uint64_t *keys, uint32_t k, uint32_t *out_ids, float *out
     if (out_n) *out_n = m;
 }
 
+// ---------------------------------------------------------------------------------------
+// in-process multi-device search: wired context groups (GroupCtx in index.h)
+// ---------------------------------------------------------------------------------------
+static uint64_t default_exchange_timeout_ns()
+{
+    static const uint64_t v = [] {
+        const char *e = getenv("CSGPU_EXCHANGE_TIMEOUT_MS");
+        const uint64_t ms = e && *e ? (uint64_t)strtoull(e, nullptr, 10) : 4000;
+        return std::max<uint64_t>(ms, 1) * 1000000ull;
+    }();
+    return v;
+}
+
+// every pair of shard devices can reach each other's HBM (or is the same device)? CSGPU_NO_FUSED_LOCAL=1 forces the
+// peer-copy + merge-launch route for A/B runs.
+static bool fused_local_ok(const csgpu_index *ix)
+{
+    int v = ix->fused_local.load(std::memory_order_relaxed);
+    if (v >= 0) return v != 0;
+    bool ok = getenv("CSGPU_NO_FUSED_LOCAL") == nullptr && ix->dtype == CSGPU_DTYPE_F32;
+    for (const Shard *a : ix->shards)
+        for (const Shard *b : ix->shards) {
+            if (a->device == b->device) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, a->device, b->device);
+            ok = ok && can;
+        }
+    ix->fused_local.store(ok ? 1 : 0, std::memory_order_relaxed);
+    return ok;
+}
+
+static void group_destroy(GroupCtx *g)
+{
+    if (!g) return;
+    for (size_t s = 0; s < g->ctx.size(); ++s) {
+        if (g->ctx[s]) {
+            DeviceGuard dg(g->ctx[s]->device);
+            cudaStreamSynchronize(g->ctx[s]->stream);
+            cudaFree(g->xbase[s]);
+            cudaFree(g->xdev[s]);
+        }
+        ctx_destroy(g->ctx[s]);
+    }
+    if (g->status_pin) cudaFreeHost(g->status_pin);
+    delete g;
+}
+
+static int group_create(const csgpu_index *ix, GroupCtx *g)
+{
+    const size_t G = ix->shards.size();
+    g->ctx.assign(G, nullptr); g->xbase.assign(G, nullptr); g->xdev.assign(G, nullptr);
+    Exchange geo;   // geometry only
+    geo.world = (uint32_t)G;
+    {
+        DeviceGuard dg(ix->shards[0]->device);
+        CS_CUDA(cudaHostAlloc(&g->status_pin, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(g->status_pin, 0, 64);
+    }
+    for (size_t s = 0; s < G; ++s) {
+        Shard *sh = ix->shards[s];
+        int rc = ctx_create(ix, sh, &g->ctx[s]);
+        if (rc) return rc;
+        DeviceGuard dg(sh->device);
+        CS_CUDA(cudaMalloc(&g->xbase[s], geo.block_bytes()));
+        CS_CUDA(cudaMemset(g->xbase[s], 0, geo.block_bytes()));
+        CS_CUDA(cudaMalloc(reinterpret_cast<void **>(&g->xdev[s]), sizeof(ExchangeDev)));
+    }
+    for (size_t s = 0; s < G; ++s) {
+        ExchangeDev d;
+        memset(&d, 0, sizeof d);
+        for (size_t p = 0; p < G; ++p) {
+            d.slots[p] = reinterpret_cast<uint64_t *>(g->xbase[p]);
+            d.flags[p] = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(g->xbase[p]) + geo.slots_bytes());
+        }
+        DeviceGuard dg(ix->shards[s]->device);
+        void *st_dev = nullptr;
+        CS_CUDA(cudaHostGetDevicePointer(&st_dev, g->status_pin, 0));
+        d.status = reinterpret_cast<unsigned *>(st_dev);
+        d.wait_ring = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(g->xbase[s]) + geo.stats_off());
+        d.timeout_ns = ix->exchange_timeout_ns ? ix->exchange_timeout_ns : default_exchange_timeout_ns();
+        d.world = (uint32_t)G; d.rank = (uint32_t)s; d.kmax = geo.kmax;
+        d.root = 0;
+        CS_CUDA(cudaMemcpy(g->xdev[s], &d, sizeof d, cudaMemcpyHostToDevice));
+    }
+    preload_exchange_kernels(ix);
+    return CSGPU_OK;
+}
+
+static int group_acquire(const csgpu_index *ix, GroupCtx **out)
+{
+    {
+        std::lock_guard<std::mutex> lk(ix->group_mu);
+        if (!ix->free_groups.empty()) { *out = ix->free_groups.back(); ix->free_groups.pop_back(); return CSGPU_OK; }
+    }
+    GroupCtx *g = new GroupCtx();
+    int rc = group_create(ix, g);
+    if (rc) { group_destroy(g); *out = nullptr; return rc; }
+    std::lock_guard<std::mutex> lk(ix->group_mu);
+    ix->all_groups.push_back(g);
+    *out = g;
+    return CSGPU_OK;
+}
+
+static void group_release(const csgpu_index *ix, GroupCtx *g)
+{
+    std::lock_guard<std::mutex> lk(ix->group_mu);
+    ix->free_groups.push_back(g);
+}
+
+// One query on a multi-device index, fused: N concurrent scan launches (one per shard, each on its own stream); the
+// tails of shards 1..N-1 store their k keys into shard 0's exchange block over NVLink and raise a flag, shard 0's last
+// CTA waits for the flags, merges and writes the global top-k straight into mapped host memory. No cudaMemcpyPeer, no
+// merge launch; the host synchronises ONE stream. A group whose exchange failed (launch error part-way, timed-out
+// wait) is retired, never reused: its sequence numbers are out of step.
+static int search_one_fused(const csgpu_index *ix, const float *q, uint32_t k, const uint64_t *bitmap, uint64_t n_bits,
+                            uint32_t *out_ids, float *out_dist, uint32_t *out_n, const csgpu_predicate_t *pred)
+{
+    const size_t G = ix->shards.size();
+    GroupCtx *grp = nullptr;
+    int rc = group_acquire(ix, &grp);
+    if (rc) return rc;
+    const size_t qbytes = (size_t)ix->dim_pad * sizeof(float);
+    const size_t bm_words = bitmap ? (size_t)((n_bits + 63) / 64) : 0;
+    const uint32_t seq = ++grp->seq;
+    SearchCtx *c0 = grp->ctx[0];
+    // test hook (tests/test_gpu_multishard_one_gpu.py): CSGPU_FAULT_SKIP_SHARD=<g> drops shard g's launch, which is what a
+    // lost device looks like to the root's wait
+    const char *fault = getenv("CSGPU_FAULT_SKIP_SHARD");
+    const long skip = fault && *fault ? strtol(fault, nullptr, 10) : -1;
+    auto body = [&]() -> int {
+        memset(c0->q_pin, 0, qbytes);
+        memcpy(c0->q_pin, q, (size_t)ix->dim * sizeof(float));   // one pinned copy feeds every device's H2D
+        for (size_t g = 0; g < G; ++g) {
+            if ((long)g == skip) continue;
+            Shard *sh = ix->shards[g];
+            SearchCtx *c = grp->ctx[g];
+            DeviceGuard dg(sh->device);
+            CS_CUDA(cudaMemcpyAsync(c->q_dev, c0->q_pin, qbytes, cudaMemcpyHostToDevice, c->stream));
+            const uint64_t *bm_dev = nullptr;
+            if (bitmap) {
+                if (c->bitmap_dev == nullptr || c->bitmap_cap < bm_words) {
+                    CS_CUDA(cudaStreamSynchronize(c->stream));
+                    cudaFree(c->bitmap_dev); c->bitmap_dev = nullptr; c->bitmap_cap = 0;
+                    CS_CUDA(cudaMalloc(&c->bitmap_dev, std::max<size_t>(bm_words, 1) * sizeof(uint64_t)));
+                    c->bitmap_cap = std::max<size_t>(bm_words, 1);
+                }
+                if (bm_words) CS_CUDA(cudaMemcpyAsync(c->bitmap_dev, bitmap, bm_words * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+                bm_dev = c->bitmap_dev;
+            }
+            if (g == 0) CS_CUDA(cudaEventRecord(c->ev0, c->stream));
+            int r = enqueue_scan(ix, sh, c, c->q_dev, k, bm_dev, n_bits, /*with_zero_ids=*/g == 0, g == 0 ? c->out_pin : c->out_dev,
+                                 c->stream, grp->xdev[g], seq, pred);
+            if (r) return r;
+        }
+        DeviceGuard dg(ix->shards[0]->device);
+        CS_CUDA(cudaEventRecord(c0->ev1, c0->stream));
+        CS_CUDA(cudaStreamSynchronize(c0->stream));
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c0->ev0, c0->ev1) == cudaSuccess) ix->last_search_us.store(ms * 1000.f);
+        if (*reinterpret_cast<volatile unsigned *>(grp->status_pin) != 0)
+            return fail(CSGPU_ERR_NCCL, "cross-GPU exchange timed out: a shard's scan never delivered its keys (device lost or hung)");
+        decode_keys(c0->out_pin, k, out_ids, out_dist, out_n);
+        return CSGPU_OK;
+    };
+    rc = body();
+    if (rc) {   // drain what was launched (the root gives up after the exchange timeout) and retire the group
+        const std::string keep = t_error;
+        for (size_t g = 0; g < G; ++g) { DeviceGuard dg(ix->shards[g]->device); cudaStreamSynchronize(grp->ctx[g]->stream); }
+        cudaGetLastError();
+        t_error = keep;
+        return rc;
+    }
+    group_release(ix, grp);
+    return rc;
+}
+
 // One query (optionally filtered) through every shard; result keys land in ctx0->out_pin[0..k).
 static int search_one(const csgpu_index *ix, const float *q, uint32_t k, const uint64_t *bitmap, uint64_t n_bits,
                       uint32_t *out_ids, float *out_dist, uint32_t *out_n, const csgpu_predicate_t *pred = nullptr)
@@ -548,6 +781,7 @@ static int search_one(const csgpu_index *ix, const float *q, uint32_t k, const u
     bool use_i8 = bitmap == nullptr && pred == nullptr && i8_eligible(ix, k);
     if (pred) { bitmap = pred->file_bitmap; n_bits = pred->file_bitmap ? pred->n_file_bits : 0; }
     const size_t G = ix->shards.size();
+    if (G > 1 && !use_i8 && fused_local_ok(ix)) return search_one_fused(ix, q, k, bitmap, n_bits, out_ids, out_dist, out_n, pred);
     std::vector<SearchCtx *> ctx(G, nullptr);
     int rc = CSGPU_OK;
     auto release_all = [&]() { for (size_t g = 0; g < G; ++g) if (ctx[g]) ctx_release(ix->shards[g], ctx[g]); };
@@ -566,7 +800,7 @@ static int search_one(const csgpu_index *ix, const float *q, uint32_t k, const u
             CS_CUDA(cudaMemcpyAsync(c->q_dev, c->q_pin, qbytes, cudaMemcpyHostToDevice, c->stream));
             const uint64_t *bm_dev = nullptr;
             if (bitmap) {
-                if (c->bitmap_cap < bm_words) {
+                if (c->bitmap_dev == nullptr || c->bitmap_cap < bm_words) {   // n_bits == 0 still needs a (never read) non-null pointer: it selects the filtered kernel, which then excludes every id
                     CS_CUDA(cudaStreamSynchronize(c->stream));
                     cudaFree(c->bitmap_dev); c->bitmap_dev = nullptr; c->bitmap_cap = 0;
                     CS_CUDA(cudaMalloc(&c->bitmap_dev, std::max<size_t>(bm_words, 1) * sizeof(uint64_t)));
@@ -914,14 +1148,17 @@ int csgpu_create(csgpu_index **out, uint32_t dim, uint32_t dtype, const int32_t 
 }
 
 static void exchange_free(csgpu_index *ix);
+static int exchange_healthy(const csgpu_index *ix);
 
 void csgpu_destroy(csgpu_index *ix)
 {
     if (!ix) return;
     exchange_free(ix);
+    for (GroupCtx *g : ix->all_groups) group_destroy(g);
     for (Shard *sh : ix->shards) {
         DeviceGuard dg(sh->device);
         for (SearchCtx *c : sh->all_ctx) ctx_destroy(c);
+        ctx_destroy(sh->dev_ctx);
         batch_free_ctx(sh);
         i8_free_shard(sh);
         cudaFree(sh->rows_bf16); cudaFree(sh->stage); cudaFree(sh->shadow_bf16);
@@ -1120,6 +1357,7 @@ int csgpu_build(csgpu_index *ix)
     if (rc) return rc;
     for (Shard *sh : ix->shards) if ((rc = batch_after_build(ix, sh))) return rc;
     for (Shard *sh : ix->shards) if ((rc = i8_refresh(ix, sh))) return rc;
+    if (ix->byte_prefilter && (rc = warm_i8_contexts(ix))) return rc;
     ix->tombstones = 0;
     ix->built = true;
     return CSGPU_OK;
@@ -1321,7 +1559,11 @@ int csgpu_set_byte_prefilter(csgpu_index *ix, uint32_t enabled)
     ix->byte_prefilter = enabled != 0;
     if (ix->built)
         for (Shard *sh : ix->shards) { int rc = i8_refresh(ix, sh); if (rc) { ix->byte_prefilter = false; return rc; } }
-    if (enabled) preload_exchange_kernels(ix);
+    if (enabled) {
+        preload_exchange_kernels(ix);
+        int rc = warm_i8_contexts(ix);
+        if (rc) return rc;
+    }
     return CSGPU_OK;
 }
 
@@ -1351,14 +1593,13 @@ int csgpu_search_keys_device(const csgpu_index *ix, const float *q_dev, uint32_t
     if (k == 0 || k > CSGPU_MAX_K) return fail(CSGPU_ERR_ARG, "k must be in [1, 1024]");
     Shard *sh = ix->shards[0];
     SearchCtx *c = nullptr;
-    int rc = ctx_acquire(ix, sh, &c);
+    int rc = dev_ctx_begin(ix, sh, (cudaStream_t)stream, &c);
     if (rc) return rc;
-    DeviceGuard dg(sh->device);
-    // NOTE: the scratch (cand/ticket) of this context is in flight until `stream` drains; the
-    // context is returned to the pool immediately, so callers must not run two device-entry
-    // searches of one index concurrently on different streams (documented in INTEGRATION.md).
-    rc = enqueue_keys_device(ix, sh, c, q_dev, k, out_keys_dev, (cudaStream_t)stream, nullptr, 0);
-    ctx_release(sh, c);
+    {
+        DeviceGuard dg(sh->device);
+        rc = enqueue_keys_device(ix, sh, c, q_dev, k, out_keys_dev, (cudaStream_t)stream, nullptr, 0);
+    }
+    dev_ctx_end(sh, c, (cudaStream_t)stream);
     return rc;
 }
 
@@ -1404,6 +1645,7 @@ static int load_finish(csgpu_index *ix)
     if (rc) return rc;
     for (Shard *sh : ix->shards) if ((rc = batch_after_build(ix, sh))) return rc;
     for (Shard *sh : ix->shards) if ((rc = i8_refresh(ix, sh))) return rc;
+    if (ix->byte_prefilter && (rc = warm_i8_contexts(ix))) return rc;
     ix->tombstones = 0;
     ix->built = true;
     return CSGPU_OK;
@@ -1423,8 +1665,20 @@ static void exchange_free(csgpu_index *ix)
         if (x->peer_ipc[p] && x->peer_base[p]) cudaIpcCloseMemHandle(x->peer_base[p]);
     cudaFree(x->dev);
     cudaFree(x->base);
+    if (x->status_pin) cudaFreeHost(x->status_pin);
     delete x;
     ix->xchg = nullptr;
+}
+
+// A timed-out wait leaves the ranks' sequence numbers out of step and the results undefined: every later exchange
+// search fails with CSGPU_ERR_NCCL until the exchange is set up again (the FFI returns errors, never aborts).
+static int exchange_healthy(const csgpu_index *ix)
+{
+    const Exchange *x = ix->xchg;
+    if (x && x->status_pin && *reinterpret_cast<volatile unsigned *>(x->status_pin) != 0)
+        return fail(CSGPU_ERR_NCCL, "cross-GPU exchange timed out earlier (a peer rank never delivered its keys); "
+                                    "results since then are undefined — csgpu_exchange_create/connect again on every rank");
+    return CSGPU_OK;
 }
 
 int csgpu_exchange_create(csgpu_index *ix, uint32_t world, uint32_t rank, void *out_handle)
@@ -1440,6 +1694,9 @@ int csgpu_exchange_create(csgpu_index *ix, uint32_t world, uint32_t rank, void *
     CS_CUDA(cudaMalloc(&x->base, x->block_bytes()));
     CS_CUDA(cudaMemset(x->base, 0, x->block_bytes()));
     CS_CUDA(cudaMalloc(&x->dev, sizeof(ExchangeDev)));
+    CS_CUDA(cudaHostAlloc(&x->status_pin, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(x->status_pin, 0, 64);
+    x->timeout_ns = ix->exchange_timeout_ns ? ix->exchange_timeout_ns : default_exchange_timeout_ns();
     static_assert(sizeof(cudaIpcMemHandle_t) == CSGPU_EXCHANGE_HANDLE_BYTES, "handle size");
     cudaIpcMemHandle_t h;
     CS_CUDA(cudaIpcGetMemHandle(&h, x->base));
@@ -1456,9 +1713,14 @@ static int exchange_finish_connect(csgpu_index *ix)
         d.slots[p] = reinterpret_cast<uint64_t *>(x->peer_base[p]);
         d.flags[p] = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(x->peer_base[p]) + x->slots_bytes());
     }
-    d.status = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(x->base) + x->slots_bytes() + (size_t)2 * x->world * sizeof(unsigned));
-    d.world = x->world; d.rank = x->rank; d.kmax = x->kmax;
     DeviceGuard dg(ix->shards[0]->device);
+    void *st_dev = nullptr;
+    CS_CUDA(cudaHostGetDevicePointer(&st_dev, x->status_pin, 0));
+    d.status = reinterpret_cast<unsigned *>(st_dev);
+    d.wait_ring = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(x->base) + x->stats_off());
+    d.timeout_ns = x->timeout_ns;
+    d.world = x->world; d.rank = x->rank; d.kmax = x->kmax;
+    d.root = -1;   // rank-per-GPU processes: every rank ends with the global top-k
     CS_CUDA(cudaMemcpy(x->dev, &d, sizeof d, cudaMemcpyHostToDevice));
     preload_exchange_kernels(ix);
     x->connected = true;
@@ -1511,14 +1773,17 @@ int csgpu_search_keys_exchange_device(const csgpu_index *ix, const float *q_dev,
     if (ix->dtype != CSGPU_DTYPE_F32) return fail(CSGPU_ERR_ARG, "device entry points need an fp32 index");
     if (!q_dev || !out_keys_dev) return fail(CSGPU_ERR_ARG, "null device pointer");
     if (k == 0 || k > CSGPU_MAX_K) return fail(CSGPU_ERR_ARG, "k must be in [1, 1024]");
+    if (int rc = exchange_healthy(ix)) return rc;
     Shard *sh = ix->shards[0];
     SearchCtx *c = nullptr;
-    int rc = ctx_acquire(ix, sh, &c);
+    int rc = dev_ctx_begin(ix, sh, (cudaStream_t)stream, &c);
     if (rc) return rc;
-    DeviceGuard dg(sh->device);
-    const uint32_t seq = ix->xchg->seq.fetch_add(1) + 1;   // every rank issues the same sequence of searches
-    rc = enqueue_keys_device(ix, sh, c, q_dev, k, out_keys_dev, (cudaStream_t)stream, ix->xchg->dev, seq);
-    ctx_release(sh, c);
+    {
+        DeviceGuard dg(sh->device);
+        const uint32_t seq = ix->xchg->seq.fetch_add(1) + 1;   // every rank issues the same sequence of searches
+        rc = enqueue_keys_device(ix, sh, c, q_dev, k, out_keys_dev, (cudaStream_t)stream, ix->xchg->dev, seq);
+    }
+    dev_ctx_end(sh, c, (cudaStream_t)stream);
     return rc;
 }
 
@@ -1533,27 +1798,68 @@ int csgpu_search_tagged_keys_device(const csgpu_index *ix, const float *q_dev, u
     if (!q_dev || !out_keys_dev || !pred) return fail(CSGPU_ERR_ARG, "null pointer");
     if (k == 0 || k > CSGPU_MAX_K) return fail(CSGPU_ERR_ARG, "k must be in [1, 1024]");
     if (pred->file_bitmap && pred->n_file_bits == 0) return fail(CSGPU_ERR_ARG, "file_bitmap with n_file_bits == 0");
+    if (exchange) if (int rc = exchange_healthy(ix)) return rc;
     Shard *sh = ix->shards[0];
     SearchCtx *c = nullptr;
-    int rc = ctx_acquire(ix, sh, &c);
+    int rc = dev_ctx_begin(ix, sh, (cudaStream_t)stream, &c);
     if (rc) return rc;
-    DeviceGuard dg(sh->device);
-    const uint32_t seq = exchange ? ix->xchg->seq.fetch_add(1) + 1 : 0;
-    rc = enqueue_scan(ix, sh, c, q_dev, k, pred->file_bitmap, pred->file_bitmap ? pred->n_file_bits : 0, true, out_keys_dev,
-                      (cudaStream_t)stream, exchange ? ix->xchg->dev : nullptr, seq, pred);
-    ctx_release(sh, c);
+    {
+        DeviceGuard dg(sh->device);
+        const uint32_t seq = exchange ? ix->xchg->seq.fetch_add(1) + 1 : 0;
+        rc = enqueue_scan(ix, sh, c, q_dev, k, pred->file_bitmap, pred->file_bitmap ? pred->n_file_bits : 0, true, out_keys_dev,
+                          (cudaStream_t)stream, exchange ? ix->xchg->dev : nullptr, seq, pred);
+    }
+    dev_ctx_end(sh, c, (cudaStream_t)stream);
     return rc;
 }
 
 int csgpu_exchange_status(const csgpu_index *ix, uint32_t *timed_out)
 {
     if (!ix || !ix->xchg || !timed_out) return fail(CSGPU_ERR_ARG, "no exchange");
+    *timed_out = *reinterpret_cast<volatile unsigned *>(ix->xchg->status_pin);   // pinned host word the kernel writes: no device round trip
+    return CSGPU_OK;
+}
+
+int csgpu_exchange_set_timeout_ms(csgpu_index *ix, uint32_t ms)
+{
+    if (!ix) return fail(CSGPU_ERR_ARG, "null index");
+    ix->exchange_timeout_ns = (uint64_t)std::max(ms, 1u) * 1000000ull;
+    Exchange *x = ix->xchg;
+    if (x) {
+        x->timeout_ns = ix->exchange_timeout_ns;
+        if (x->connected) {   // live exchange: patch the device copy of the table (callers quiesce searches first, as for connect)
+            DeviceGuard dg(ix->shards[0]->device);
+            CS_CUDA(cudaMemcpy(reinterpret_cast<char *>(x->dev) + offsetof(ExchangeDev, timeout_ns), &x->timeout_ns,
+                               sizeof x->timeout_ns, cudaMemcpyHostToDevice));
+        }
+    }
+    // in-process groups are re-created with the new bound
+    std::lock_guard<std::mutex> lk(ix->group_mu);
+    for (GroupCtx *g : ix->free_groups) {
+        ix->all_groups.erase(std::find(ix->all_groups.begin(), ix->all_groups.end(), g));
+        group_destroy(g);
+    }
+    ix->free_groups.clear();
+    return CSGPU_OK;
+}
+
+int csgpu_exchange_wait_stats(const csgpu_index *ix, uint64_t *out_ns, uint32_t max_queries, uint32_t *n_queries)
+{
+    if (!ix || !ix->xchg || !out_ns || !n_queries) return fail(CSGPU_ERR_ARG, "no exchange / null argument");
     const Exchange *x = ix->xchg;
+    const uint32_t seq = x->seq.load();
+    const uint32_t n = std::min(std::min(seq, (uint32_t)XCHG_STATS_RING), max_queries);
+    *n_queries = n;
+    if (n == 0) return CSGPU_OK;
+    std::vector<unsigned long long> ring((size_t)XCHG_STATS_RING * XCHG_MAX_WORLD);
     DeviceGuard dg(ix->shards[0]->device);
-    unsigned v = 0;
-    CS_CUDA(cudaMemcpy(&v, reinterpret_cast<const char *>(x->base) + x->slots_bytes() + (size_t)2 * x->world * sizeof(unsigned),
-                       sizeof v, cudaMemcpyDeviceToHost));
-    *timed_out = v;
+    CS_CUDA(cudaMemcpy(ring.data(), reinterpret_cast<const char *>(x->base) + x->stats_off(), ring.size() * sizeof(unsigned long long),
+                       cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < n; ++i) {   // oldest first: queries seq-n+1 .. seq (1-based), ring slot = (query - 1) % RING
+        const uint32_t query = seq - n + 1 + i;
+        for (uint32_t p = 0; p < x->world; ++p)
+            out_ns[(size_t)i * x->world + p] = ring[(size_t)((query - 1) % XCHG_STATS_RING) * XCHG_MAX_WORLD + p];
+    }
     return CSGPU_OK;
 }
 

@@ -62,6 +62,41 @@ __global__ void check_counts_kernel(const unsigned *__restrict__ count, const un
     if (over) atomicExch(overflow, 1u);
 }
 
+// Zero-norm query on the bf16 index (contract, include/csgpu.h: "a zero-norm query or row has distance 0.0"; arroy's
+// pn*qn == 0 branch): every live row ties at distance 0.0, so the answer is the k smallest chunk ids — of this shard's
+// rows plus (shard 0) the zero-norm side list. One pass over ids[] (4 B per row); per-CTA selection in a CtaBuf, the last
+// CTA re-selects over the CTAs' lists. The fp32 index gets the same answer from scan_topk_kernel's qzero branch.
+__global__ void __launch_bounds__(SCAN_THREADS, 1)
+zero_query_ids_kernel(const uint32_t *__restrict__ ids, uint64_t n, const uint32_t *__restrict__ zero_ids, uint32_t n_zero,
+                      uint32_t k, uint32_t cap, uint64_t *__restrict__ cand, unsigned *__restrict__ ticket, uint64_t *__restrict__ out)
+{
+    extern __shared__ __align__(16) uint64_t smem[];
+    __shared__ unsigned cb_cnt;
+    __shared__ uint64_t cb_thr;
+    __shared__ bool is_last;
+    CtaSel sel;
+    sel.cb.buf = smem; sel.cb.cnt = &cb_cnt; sel.cb.thr = &cb_thr; sel.cap = cap; sel.k = k;
+    sel.reset();
+    const uint64_t per = (n + gridDim.x - 1) / gridDim.x;
+    const uint64_t lo = min(n, per * blockIdx.x), hi = min(n, lo + per);
+    cta_buf_stream(sel.cb, cap, k, hi - lo, [&](uint64_t t) { return make_key(0.f, ids[lo + t]); });
+    sel.finish();
+    for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) cand[(size_t)blockIdx.x * k + j] = smem[j];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    sel.reset();
+    const volatile uint64_t *cv = cand;
+    cta_buf_stream(sel.cb, cap, k, (uint64_t)gridDim.x * k, [&](uint64_t t) { return cv[t]; });
+    cta_buf_stream(sel.cb, cap, k, (uint64_t)min(n_zero, k), [&](uint64_t t) { return make_key(0.f, zero_ids[t]); });   // ascending: the first k suffice
+    sel.finish();
+    for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) out[j] = smem[j];
+    if (threadIdx.x == 0) *ticket = 0;
+}
+
 // pending fp32 rows (stage) -> unit length (f64 norm) -> bf16 rows at [dst_first + i]; flags zero / non-finite
 __global__ void normalise_to_bf16_kernel(const float *__restrict__ stage, __nv_bfloat16 *__restrict__ rows,
                                          uint8_t *__restrict__ status, uint64_t dst_first, uint64_t n, uint32_t dim)
@@ -459,9 +494,6 @@ static int batch_search_shard(const csgpu_index *ix, Shard *sh, BatchCtx *c, con
     CS_CUDA(cudaMemcpyAsync(flags_host, c->flags, nq, cudaMemcpyDeviceToHost, c->stream));
     CS_CUDA(cudaStreamSynchronize(c->stream));
     *flags_out = flags_host;
-    if (ix->dtype == CSGPU_DTYPE_BF16)
-        for (uint32_t j = 0; j < nq; ++j)
-            if (flags_host[j]) return fail(CSGPU_ERR_ARG, "zero-norm query is not supported on a bf16 index");
     CUtensorMap map_q;
     int rc = make_map(&map_q, c->q_prep, nq_pad, bf16 ? ix->dim : ix->dim_pad, GT_BLOCK_M, !bf16);
     if (rc) return rc;
@@ -503,6 +535,24 @@ static int batch_search_shard(const csgpu_index *ix, Shard *sh, BatchCtx *c, con
         CS_CUDA(cudaStreamSynchronize(c->stream));
         if (!over) break;
         if (careful) return fail(CSGPU_ERR_CUDA, "candidate overflow in the careful pass (internal error)");
+    }
+    if (ix->dtype == CSGPU_DTYPE_BF16) {   // zero-norm queries: distance 0.0 everywhere -> the k smallest ids (after the final select wrote its empty lists)
+        bool any = false;
+        for (uint32_t j = 0; j < nq; ++j) {
+            if (!flags_host[j]) continue;
+            const uint32_t cap = ctabuf_cap(k);
+            const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sh->sm_count, (sh->n_built + 8191) / 8192));
+            const bool root = sh == ix->shards[0];
+            cudaError_t e = cudaFuncSetAttribute(zero_query_ids_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctabuf_cap(CSGPU_MAX_K) * sizeof(uint64_t)));
+            if (e != cudaSuccess) return fail_cuda(e, "zero_query_ids_kernel attr", __FILE__, __LINE__);
+            zero_query_ids_kernel<<<grid, SCAN_THREADS, (size_t)cap * sizeof(uint64_t), c->stream>>>(
+                sh->ids, sh->n_built, root ? ix->zero_ids_dev : nullptr, root ? (uint32_t)ix->zero_ids.size() : 0u, k, cap, c->cand,
+                c->scalar + 8, c->out + (size_t)j * k);
+            count_launch();
+            CS_CUDA(cudaGetLastError());
+            any = true;
+        }
+        if (any) CS_CUDA(cudaStreamSynchronize(c->stream));
     }
     if (rescore_path(ix, sh)) {
         unsigned long long nres = 0;
@@ -590,7 +640,7 @@ int batch_search(const csgpu_index *ix, const float *q, uint32_t b, uint32_t k,
         CS_CUDA(cudaMemcpyAsync(c0->out_pin, c0->out, (size_t)nq * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, c0->stream));
         CS_CUDA(cudaStreamSynchronize(c0->stream));
         for (uint32_t i = 0; i < nq; ++i) {
-            if (zf[i]) { if (zero_queries) zero_queries->push_back(j + i); continue; }
+            if (zf[i] && zero_queries) { zero_queries->push_back(j + i); continue; }   // fp32 index: the caller runs the scan kernel (qzero)
             decode_keys(c0->out_pin + (size_t)i * k, k, out_ids + (size_t)(j + i) * k, out_dist + (size_t)(j + i) * k, out_n ? out_n + j + i : nullptr);
         }
     }

@@ -54,8 +54,25 @@ struct SearchCtx {
     uint64_t *bitmap_dev = nullptr; // filter bitmap staging
     size_t bitmap_cap = 0;          // in u64 words
     size_t cand_cap = 0;            // in keys
-    void *i8_scratch = nullptr;     // byte prefilter (scan_i8.cu): per-warp minima, counters, candidate regions; lazily allocated
+    void *i8_scratch = nullptr;     // byte prefilter (scan_i8.cu): per-warp minima, counters, candidate regions; allocated with the
+                                    // context when the prefilter is on (csgpu_set_byte_prefilter warms one per shard)
     uint64_t *i8_status = nullptr;  // pinned, device-mapped: [0] fallback flag, [1] statistics of the last launch
+    cudaEvent_t busy = nullptr;     // device entry points: recorded on the caller's stream after the enqueue, waited on by the next
+    bool busy_recorded = false;
+};
+
+// In-process multi-device search (csgpu_create with n_devices > 1, the one-process host of the reference:
+// /root/reference/src/search/mod.rs:508-511, src/server/mod.rs:27): one SearchCtx per shard wired together by exchange
+// blocks in every shard's HBM, so a query is N concurrent scan launches whose tails push their k keys into the ROOT
+// shard's block over NVLink; the root's last CTA merges and writes the global top-k straight into mapped host memory.
+// One group per concurrent host search (pooled like SearchCtx).
+struct ExchangeDev;
+struct GroupCtx {
+    std::vector<SearchCtx *> ctx;         // [n_shards]
+    std::vector<void *> xbase;            // [n_shards] exchange block on shard g's device
+    std::vector<ExchangeDev *> xdev;      // [n_shards] device copy of the pointer table as seen from shard g
+    unsigned *status_pin = nullptr;       // pinned, device-mapped: != 0 after a timed-out wait (sticky)
+    uint32_t seq = 0;
 };
 
 // Scratch of the batched GEMM-shaped path (gemm_topk.cu): one per shard, serialised by Shard::batch_mu.
@@ -76,9 +93,10 @@ struct BatchCtx {
 
 // Fused cross-GPU exchange state of a single-device index (scan.cuh: ExchangeDev). One cudaMalloc block:
 // [2][world][kmax] keys, then [2][world] flags, then one status word — shared with peers through cudaIpc.
-struct ExchangeDev;
 struct Exchange {
     uint32_t world = 0, rank = 0, kmax = CSGPU_MAX_K;
+    unsigned *status_pin = nullptr;       // pinned, device-mapped status word: the host reads it without a device round trip
+    uint64_t timeout_ns = 4000000000ull;  // bound of the in-kernel flag wait (csgpu_exchange_set_timeout_ms / CSGPU_EXCHANGE_TIMEOUT_MS)
     void *base = nullptr;                 // local block
     void *peer_base[8] = {};              // peers' blocks as mapped here (own entry = base)
     bool peer_ipc[8] = {};                // opened with cudaIpcOpenMemHandle (needs cudaIpcCloseMemHandle)
@@ -86,7 +104,9 @@ struct Exchange {
     bool connected = false;
     std::atomic<uint32_t> seq{0};
     size_t slots_bytes() const { return (size_t)2 * world * kmax * sizeof(uint64_t); }
-    size_t block_bytes() const { return slots_bytes() + (size_t)2 * world * sizeof(unsigned) + 64; }
+    size_t flags_bytes() const { return (size_t)2 * world * sizeof(unsigned) + 64; }
+    size_t stats_off() const { return slots_bytes() + flags_bytes(); }   // [XCHG_STATS_RING] u64 wait times (ns) of the last queries
+    size_t block_bytes() const { return stats_off() + (size_t)1024 * sizeof(uint64_t); }
 };
 
 // Host micro-batcher in front of csgpu_search. Concurrent single-query searches with the same k
@@ -141,6 +161,8 @@ struct Shard {
     std::mutex ctx_mu;
     std::vector<SearchCtx *> free_ctx;
     std::vector<SearchCtx *> all_ctx;
+    SearchCtx *dev_ctx = nullptr;   // device entry points only (never in free_ctx): its scratch is in flight on the CALLER's stream
+    std::mutex dev_mu;
 };
 
 // gemm_topk.cu (batched GEMM-shaped path for both index dtypes + bf16 storage hooks)
@@ -164,6 +186,7 @@ bool i8_eligible(const csgpu_index *ix, uint32_t k);
 int enqueue_scan_i8(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const float *q_dev, uint32_t k,
                     bool with_zero_ids, uint64_t *out_keys, cudaStream_t st, bool host_status = true);
 void i8_preload(const csgpu_index *ix);
+int i8_prepare_ctx(SearchCtx *c);   // allocates the context's scratch (device of the current context = c->device)
 const unsigned *i8_status_dev(const SearchCtx *c);   // device word: != 0 after a launch that needs the fp32 scan instead
 
 // snapshot.cu
@@ -199,5 +222,9 @@ struct csgpu_index {
     bool byte_prefilter = false;          // csgpu_set_byte_prefilter: csgpu_search streams an int8 shadow + exact fp32 rescoring
     mutable std::atomic<uint64_t> byte_searches{0}, byte_fallbacks{0}, byte_candidates{0}, byte_rescored{0};
     csgpu::Exchange *xchg = nullptr;      // rank-per-GPU fused exchange (csgpu_exchange_*)
+    mutable std::mutex group_mu;          // in-process multi-device search: pool of wired context groups
+    mutable std::vector<csgpu::GroupCtx *> free_groups, all_groups;
+    uint64_t exchange_timeout_ns = 0;     // csgpu_exchange_set_timeout_ms; 0 = default (CSGPU_EXCHANGE_TIMEOUT_MS or 4 s)
+    mutable std::atomic<int> fused_local{-1};   // -1 unknown, 0 = no peer access between some pair (peer copies + merge launch), 1 = fused
     mutable csgpu::Coalescer coalescer;   // csgpu_set_coalescing
 };

@@ -31,11 +31,19 @@ constexpr int SCAN_THREADS = SCAN_WARPS * 32;
 // separate merge launch. Slots/flags are double-buffered by sequence parity: a rank can be at most one
 // query ahead of a peer, because finishing query s needs the peer's keys of query s.
 constexpr int XCHG_MAX_WORLD = 8;
+constexpr int XCHG_STATS_RING = 128;   // queries whose per-peer wait times are kept (diagnostic: cross-rank skew)
 struct ExchangeDev {
     uint64_t *slots[XCHG_MAX_WORLD];   // slots[p]: rank p's array [2][world][kmax], as mapped on THIS device
     unsigned *flags[XCHG_MAX_WORLD];   // flags[p]: rank p's flags [2][world]
-    unsigned *status;                  // local: set to 1 if a wait timed out
+    unsigned *status;                  // pinned, device-mapped host word: set to 1 if a wait timed out (sticky; the host reads
+                                       // it without touching the device and fails the next call with CSGPU_ERR_NCCL)
+    unsigned long long *wait_ring;     // local [XCHG_STATS_RING][XCHG_MAX_WORLD]: ns between this rank's publish and the arrival
+                                       // of peer p's keys, per query (ring by sequence number) — the per-step skew, measured
+    unsigned long long timeout_ns;     // bound of the flag wait
     uint32_t world, rank, kmax;
+    int32_t root;                      // < 0: all-to-all, every rank ends with the global top-k (rank-per-GPU processes);
+                                       // >= 0: gather — ranks push their keys to `root` only and leave, `root` alone waits,
+                                       // merges and writes the result (in-process multi-device index: one host reads one list)
 };
 
 struct ScanArgs {
@@ -183,22 +191,43 @@ __device__ __forceinline__ void exchange_and_merge(const ScanArgs &a, Sel &sel, 
 {
     const ExchangeDev &x = *a.xchg;   // pointer table stays in global memory (no local copy)
     const uint32_t par = a.seq & 1u, W = x.world, R = x.rank, KM = x.kmax, k = a.k;
-    // my k keys -> slot [par][R] of every rank (own copy included): peer stores over NVLink
-    for (uint32_t t = threadIdx.x; t < W * k; t += blockDim.x) {
-        const uint32_t p = t / k, j = t - p * k;
+    const bool gather = x.root >= 0;
+    if (gather && R != (uint32_t)x.root) {
+        // gather mode, not the root: k keys -> my slot in the root's block (peer stores over NVLink), flag, done
+        uint64_t *dst = x.slots[x.root] + ((size_t)par * W + R) * KM;
+        for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) dst[j] = smem[j];
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned *>(x.flags[x.root] + par * W + R) = a.seq;
+        }
+        return;
+    }
+    // my k keys -> slot [par][R] of every rank (own copy included; gather mode: own copy only)
+    const uint32_t n_dst = gather ? 1u : W;
+    for (uint32_t t = threadIdx.x; t < n_dst * k; t += blockDim.x) {
+        const uint32_t p = gather ? R : t / k, j = gather ? t : t - p * k;
         x.slots[p][((size_t)par * W + R) * KM + j] = smem[j];
     }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x < W) {
         __threadfence_system();
-        *reinterpret_cast<volatile unsigned *>(x.flags[threadIdx.x] + par * W + R) = a.seq;   // publish to rank threadIdx.x
+        if (!gather || threadIdx.x == R)
+            *reinterpret_cast<volatile unsigned *>(x.flags[threadIdx.x] + par * W + R) = a.seq;   // publish to rank threadIdx.x
         // wait until rank threadIdx.x's keys of this query have landed in MY memory
         const volatile unsigned *f = x.flags[R] + par * W + threadIdx.x;
-        const unsigned long long t0 = global_timer_ns();
+        const unsigned long long t0 = global_timer_ns(), limit = x.timeout_ns;
+        unsigned long long waited = 0;
         while (*f != a.seq) {
-            if (global_timer_ns() - t0 > 4000000000ull) { atomicExch(x.status, 1u); break; }   // 4 s: a peer died
+            waited = global_timer_ns() - t0;
+            if (waited > limit) {   // a peer died or never launched: results are undefined, the host is told
+                *reinterpret_cast<volatile unsigned *>(x.status) = 1u;
+                break;
+            }
         }
+        if (x.wait_ring != nullptr) x.wait_ring[(size_t)((a.seq - 1u) % XCHG_STATS_RING) * XCHG_MAX_WORLD + threadIdx.x] = waited;
         __threadfence_system();
     }
     __syncthreads();

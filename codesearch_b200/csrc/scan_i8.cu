@@ -140,25 +140,33 @@ void i8_preload(const csgpu_index *ix)
     cudaGetLastError();
 }
 
+// The context's scratch: both blocks or neither. Called when a context is created on an index with the prefilter on,
+// and for the warm contexts of csgpu_set_byte_prefilter / csgpu_build — not from inside a search (round 1 paid a
+// multi-millisecond cudaMalloc in the first query).
+int i8_prepare_ctx(SearchCtx *c)
+{
+    if (c->i8_scratch != nullptr) return CSGPU_OK;
+    void *scratch = nullptr;
+    uint64_t *status = nullptr;
+    cudaError_t ea = cudaMalloc(&scratch, sizeof(I8Scratch));
+    if (ea == cudaSuccess) ea = cudaHostAlloc(&status, 8 * sizeof(uint64_t), cudaHostAllocMapped | cudaHostAllocPortable);
+    if (ea == cudaSuccess) ea = cudaMemset(reinterpret_cast<I8Scratch *>(scratch)->warp_min, 0xFF, sizeof(uint32_t) * I8_MAX_WARPS);
+    if (ea == cudaSuccess) ea = cudaMemset(reinterpret_cast<I8Scratch *>(scratch)->counters, 0, sizeof(unsigned) * 8);
+    if (ea != cudaSuccess) {
+        cudaFree(scratch);
+        if (status) cudaFreeHost(status);
+        return fail_cuda(ea, "byte prefilter scratch", __FILE__, __LINE__);
+    }
+    memset(status, 0, 8 * sizeof(uint64_t));
+    c->i8_scratch = scratch;
+    c->i8_status = status;
+    return CSGPU_OK;
+}
+
 int enqueue_scan_i8(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const float *q_dev, uint32_t k,
                     bool with_zero_ids, uint64_t *out_keys, cudaStream_t st, bool host_status)
 {
-    if (c->i8_scratch == nullptr) {   // first use of this context: both blocks or neither
-        void *scratch = nullptr;
-        uint64_t *status = nullptr;
-        cudaError_t ea = cudaMalloc(&scratch, sizeof(I8Scratch));
-        if (ea == cudaSuccess) ea = cudaHostAlloc(&status, 8 * sizeof(uint64_t), cudaHostAllocMapped | cudaHostAllocPortable);
-        if (ea == cudaSuccess) ea = cudaMemsetAsync(reinterpret_cast<I8Scratch *>(scratch)->warp_min, 0xFF, sizeof(uint32_t) * I8_MAX_WARPS, st);
-        if (ea == cudaSuccess) ea = cudaMemsetAsync(reinterpret_cast<I8Scratch *>(scratch)->counters, 0, sizeof(unsigned) * 8, st);
-        if (ea != cudaSuccess) {
-            cudaFree(scratch);
-            if (status) cudaFreeHost(status);
-            return fail_cuda(ea, "byte prefilter scratch", __FILE__, __LINE__);
-        }
-        memset(status, 0, 8 * sizeof(uint64_t));
-        c->i8_scratch = scratch;
-        c->i8_status = status;
-    }
+    if (int rc = i8_prepare_ctx(c)) return rc;   // contexts that predate csgpu_set_byte_prefilter
     I8Scratch *s = reinterpret_cast<I8Scratch *>(c->i8_scratch);
     const uint32_t V = i8_lines(ix->dim4);
     I8Args a;

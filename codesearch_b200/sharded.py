@@ -117,7 +117,19 @@ class ShardedSearcher:
         keys = self.search_keys_device(self.q_dev, k, pred)
         self.out_pin[:k].copy_(keys, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        self.check_exchange()
         return decode_keys(self.out_pin[:k].numpy())
+
+    def check_exchange(self) -> None:
+        """Raises CsgpuError(ERR_NCCL) if an in-kernel wait for a peer's keys ever timed out on this rank: the keys of that
+        search (and of every later one) are undefined. The status word is pinned host memory — no device round trip."""
+        if self.exchange != "fused":
+            return
+        t = ctypes.c_uint32(0)
+        _lib.check(self.lib.csgpu_exchange_status(self.store.handle, ctypes.byref(t)))
+        if t.value:
+            raise _lib.CsgpuError(_lib.ERR_NCCL, "cross-GPU exchange timed out: a peer rank never delivered its keys; "
+                                                 "results are undefined until the exchange is connected again")
 
 
     # -- batches: every rank answers the whole batch over its shard (csgpu_search_batch picks the kernel: multi-query

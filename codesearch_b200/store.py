@@ -141,8 +141,15 @@ class VectorStore:
                         rec = json.loads(line)
                         cid = int(rec.pop("id"))
                         self._chunks[cid] = Chunk(**rec)
-                for cid in sorted(self._chunks):   # same first-seen order as the inserts that wrote the tags
-                    self.files.file_id(self._chunks[cid].path)
+                # the tags in <db>/gpu/tags.u32 carry the file ids assigned at INSERT time; after delete + re-insert
+                # cycles those are not re-derivable from the surviving chunks, so the table is persisted verbatim
+                files_json = os.path.join(db_path, "files.json")
+                if os.path.exists(files_json):
+                    with open(files_json) as f:
+                        self.files = FileTable.from_paths(json.load(f)["paths"])
+                else:   # snapshot written before the table was persisted: first-seen order over surviving chunks
+                    for cid in sorted(self._chunks):
+                        self.files.file_id(self._chunks[cid].path)
                 if self._chunks:
                     self.next_id = max(self._chunks) + 1
 
@@ -257,6 +264,10 @@ class VectorStore:
             for i in sorted(self._chunks):
                 f.write(json.dumps({"id": i, **asdict(self._chunks[i])}) + "\n")
         os.replace(tmp, os.path.join(self.db_path, "chunks.jsonl"))
+        tmp = os.path.join(self.db_path, "files.json.tmp")
+        with open(tmp, "w") as f:   # path list in file-id order: the row tags in HBM / tags.u32 index into it
+            json.dump({"paths": self.files.paths}, f)
+        os.replace(tmp, os.path.join(self.db_path, "files.json"))
         _lib.check(self._lib.csgpu_save(self._h, self._gpu_dir().encode()))
 
     def clear(self) -> None:
@@ -266,7 +277,7 @@ class VectorStore:
         self.files = FileTable()
         self.next_id = 0
         if self.db_path is not None:   # store.rs:690-706 clears both LMDB tables
-            for name in ("gpu/meta.json", "gpu/ids.u32", "gpu/rows.f32", "gpu/rows.bf16", "gpu/tags.u32", "gpu/zero.u32", "chunks.jsonl"):
+            for name in ("gpu/meta.json", "gpu/ids.u32", "gpu/rows.f32", "gpu/rows.bf16", "gpu/tags.u32", "gpu/zero.u32", "chunks.jsonl", "files.json"):
                 try:
                     os.remove(os.path.join(self.db_path, name))
                 except FileNotFoundError:

@@ -134,6 +134,17 @@ class FileTable:
             self.langs.append(language_from_path(key))
         return fid
 
+    @staticmethod
+    def from_paths(paths: Sequence[str]) -> "FileTable":
+        """Rebuild the table from its persisted path list (file id = position), verbatim."""
+        t = FileTable()
+        for p in paths:
+            key = normalize_path_str(p)
+            t.ids.setdefault(key, len(t.paths))   # a duplicate entry keeps its slot so later ids do not shift
+            t.paths.append(key)
+            t.langs.append(language_from_path(key))
+        return t
+
     def tag(self, path: str) -> int:
         fid = self.file_id(path)
         return make_tag(self.langs[fid], fid)

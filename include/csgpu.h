@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define CSGPU_ABI_VERSION 4
+#define CSGPU_ABI_VERSION 5
 
 enum {
     CSGPU_OK            = 0,
@@ -87,7 +87,12 @@ typedef struct csgpu_stats_t {
 
 /* ---- lifecycle (VectorStore::new / open_readonly  store.rs:110-176,183-250) ------------ */
 
-/* devices == NULL => device 0. n_devices in {1,2,4,8}: rows are sharded row-wise. */
+/* devices == NULL => device 0. n_devices in [1, 8]: rows are sharded row-wise over the devices of this ONE process
+ * (the reference is one process: rayon inside it, src/search/mod.rs:508-511; one RwLock, src/server/mod.rs:27).
+ * csgpu_search / csgpu_search_filtered / csgpu_search_tagged on such an index are n concurrent scan launches whose tails
+ * push their k keys into device 0's HBM over NVLink; device 0's last CTA merges and writes the global top-k into mapped
+ * host memory (no peer memcpy, no merge launch, one stream synchronised). A shard that never delivers makes the call
+ * fail with CSGPU_ERR_NCCL after the exchange timeout (csgpu_exchange_set_timeout_ms). */
 int  csgpu_create(csgpu_index **out, uint32_t dim, uint32_t dtype,
                   const int32_t *devices, uint32_t n_devices);
 void csgpu_destroy(csgpu_index *ix);
@@ -104,8 +109,9 @@ int  csgpu_remove(csgpu_index *ix, const uint32_t *ids, uint64_t n, uint64_t *n_
  * more than half of HBM). Optional. */
 int  csgpu_reserve(csgpu_index *ix, uint64_t total_rows);
 
-/* Normalises new rows to unit length, applies tombstones/replacements, rebalances shards;
- * index becomes searchable (store.rs:422-430: indexed=true). */
+/* Normalises new rows to unit length, applies tombstones/replacements and compacts every shard in place (rows never
+ * move between shards: large appends are split evenly, small ones go to the least-loaded shard); the index becomes
+ * searchable (store.rs:422-430: indexed=true). */
 int  csgpu_build(csgpu_index *ix);
 
 /* Drops every row; index is empty and NOT built (store.rs:690-706). */
@@ -243,8 +249,10 @@ int  csgpu_merge_keys_batch_device(const csgpu_index *ix, const uint64_t *keys_d
  *   2. all-gather the handles (torch.distributed / MPI / a file: host side, once)
  *   3. csgpu_exchange_connect with all world handles (cudaIpcOpenMemHandle on the peers' blocks)
  * csgpu_exchange_connect_local wires indexes that live in ONE process (several GPUs, or tests).
- * A peer that never arrives makes the wait time out after 4 s: results are then undefined and
- * csgpu_exchange_status reports it. */
+ * A peer that never arrives makes the wait time out (4 s by default; csgpu_exchange_set_timeout_ms, or the environment
+ * variable CSGPU_EXCHANGE_TIMEOUT_MS): that query's keys are undefined, csgpu_exchange_status reports 1, and EVERY later
+ * exchange search on this rank returns CSGPU_ERR_NCCL until csgpu_exchange_create/connect are run again. The status
+ * word lives in pinned host memory, so checking it never touches the device. */
 #define CSGPU_EXCHANGE_HANDLE_BYTES 64
 int  csgpu_exchange_create(csgpu_index *ix, uint32_t world, uint32_t rank, void *out_handle /*[64]*/);
 int  csgpu_exchange_connect(csgpu_index *ix, const void *handles /*[world][64]; own entry ignored*/);
@@ -252,6 +260,14 @@ int  csgpu_exchange_connect_local(csgpu_index *ix, csgpu_index *const *peers /*[
 int  csgpu_search_keys_exchange_device(const csgpu_index *ix, const float *q_dev, uint32_t k,
                                        uint64_t *out_keys_dev /*[k] global top-k*/, void *stream);
 int  csgpu_exchange_status(const csgpu_index *ix, uint32_t *timed_out);
+/* Bound of the in-kernel wait for the peers' keys, for the rank-per-GPU exchange and for the in-process multi-device
+ * index alike. Call it while no search is in flight. */
+int  csgpu_exchange_set_timeout_ms(csgpu_index *ix, uint32_t ms);
+/* Skew diagnostic: for the most recent n (<= 128, <= max_queries) exchange searches of this rank, oldest first,
+ * out_ns[i * world + p] = nanoseconds between this rank publishing its keys and rank p's keys landing here (0 = they
+ * were already there). Synchronise the search stream first. */
+int  csgpu_exchange_wait_stats(const csgpu_index *ix, uint64_t *out_ns /*[max_queries][world]*/, uint32_t max_queries,
+                               uint32_t *n_queries);
 void csgpu_exchange_destroy(csgpu_index *ix);
 
 /* Device-resident predicate search: local top-k (exchange = 0) or, with a connected exchange, the GLOBAL top-k over

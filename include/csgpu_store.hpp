@@ -231,7 +231,7 @@ class VectorStore {
         file_paths_.clear();
         next_id_ = 0;
         if (!db_path_.empty())
-            for (const char *nm : {"gpu/meta.json", "gpu/ids.u32", "gpu/rows.f32", "gpu/rows.bf16", "gpu/tags.u32", "gpu/zero.u32", "chunks.bin"})
+            for (const char *nm : {"gpu/meta.json", "gpu/ids.u32", "gpu/rows.f32", "gpu/rows.bf16", "gpu/tags.u32", "gpu/zero.u32", "chunks.bin", "files.bin"})
                 std::remove((db_path_ + "/" + nm).c_str());
     }
 
@@ -452,6 +452,16 @@ class VectorStore {
         }
         fclose(f);
         if (std::rename(tmp.c_str(), (db_path_ + "/chunks.bin").c_str()) != 0) throw Error(CSGPU_ERR_ARG, "cannot publish chunks.bin");
+        // the file table, verbatim in file-id order: the row tags (HBM, gpu/tags.u32) index into it, and after delete +
+        // re-insert cycles it cannot be re-derived from the surviving chunks
+        const std::string ftmp = db_path_ + "/files.bin.tmp";
+        FILE *ff = fopen(ftmp.c_str(), "wb");
+        if (!ff) throw Error(CSGPU_ERR_ARG, "cannot write " + ftmp);
+        const uint64_t nf = file_paths_.size();
+        fwrite(&nf, sizeof nf, 1, ff);
+        for (const std::string &p : file_paths_) put_str(ff, p);
+        fclose(ff);
+        if (std::rename(ftmp.c_str(), (db_path_ + "/files.bin").c_str()) != 0) throw Error(CSGPU_ERR_ARG, "cannot publish files.bin");
         check(csgpu_save(ix_.get(), (db_path_ + "/gpu").c_str()));
     }
     void load_chunks()
@@ -473,7 +483,19 @@ class VectorStore {
         }
         fclose(f);
         if (!ok) throw Error(CSGPU_ERR_ARG, "chunks.bin is truncated or corrupt");
-        for (const auto &kv : chunks_) tag_of(kv.second.path);   // same first-seen order as the inserts that wrote the tags
+        if (FILE *ff = fopen((db_path_ + "/files.bin").c_str(), "rb")) {
+            uint64_t nf = 0;
+            bool fok = fread(&nf, sizeof nf, 1, ff) == 1 && nf <= (uint64_t)CSGPU_TAG_FILE_MASK + 1;
+            for (uint64_t i = 0; fok && i < nf; ++i) {
+                std::string p;
+                fok = get_str(ff, &p);
+                if (fok) { files_.emplace(p, (uint32_t)file_paths_.size()); file_paths_.push_back(std::move(p)); }
+            }
+            fclose(ff);
+            if (!fok) throw Error(CSGPU_ERR_ARG, "files.bin is truncated or corrupt");
+        } else {
+            for (const auto &kv : chunks_) tag_of(kv.second.path);   // snapshot older than files.bin: first-seen order over surviving chunks
+        }
         if (!chunks_.empty()) next_id_ = chunks_.rbegin()->first + 1;   // store.rs:141-144
     }
 

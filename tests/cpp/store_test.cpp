@@ -118,6 +118,44 @@ static void test_persistence()
     }
 }
 
+// incremental reindex (delete a file's chunks, re-insert, reopen): the persisted file table keeps the file ids the row
+// tags were written with (round-1 advisor finding: re-deriving them from the surviving chunks renumbers files)
+static void test_file_table_reopen()
+{
+    const std::string db = temp_db("files.db");
+    std::vector<uint32_t> a2, b;
+    {
+        VectorStore store = VectorStore::create(db, 4);
+        auto a = store.insert_chunks_with_ids({EmbeddedChunk(fn_chunk("fn a() {}", 0, 1, "src/a.rs"), {1.f, 0.f, 0.f, 0.f})});
+        b = store.insert_chunks_with_ids({EmbeddedChunk(fn_chunk("def b(): pass", 0, 1, "lib/b.py"), {0.f, 1.f, 0.f, 0.f})});
+        store.build_index();
+        CHECK(store.delete_chunks(a) == 1);
+        a2 = store.insert_chunks_with_ids({EmbeddedChunk(fn_chunk("fn a2() {}", 0, 1, "src/a.rs"), {0.9f, 0.1f, 0.f, 0.f})});
+        store.build_index();
+    }
+    {
+        VectorStore store = VectorStore::create(db, 4);
+        TagFilter fa, fb;
+        fa.path_prefix = "src/";
+        fb.path_prefix = "lib/";
+        auto ra = store.search_tagged({0.5f, 0.5f, 0.f, 0.f}, 5, fa);
+        auto rb = store.search_tagged({0.5f, 0.5f, 0.f, 0.f}, 5, fb);
+        CHECK(ra.size() == 1 && ra[0].id == a2[0] && ra[0].path == "src/a.rs");
+        CHECK(rb.size() == 1 && rb[0].id == b[0] && rb[0].path == "lib/b.py");
+        store.delete_chunks(a2);   // every chunk of the first file gone: the second keeps its id
+        store.build_index();
+    }
+    {
+        VectorStore store = VectorStore::create(db, 4);
+        TagFilter fa, fb;
+        fa.path_prefix = "src/";
+        fb.path_prefix = "lib/";
+        CHECK(store.search_tagged({0.5f, 0.5f, 0.f, 0.f}, 5, fa).empty());
+        auto rb = store.search_tagged({0.5f, 0.5f, 0.f, 0.f}, 5, fb);
+        CHECK(rb.size() == 1 && rb[0].id == b[0]);
+    }
+}
+
 // guards, store.rs:432-444: literal messages
 static void test_guards()
 {
@@ -250,7 +288,7 @@ int main(int argc, char **argv)
     struct { const char *name; void (*fn)(); } tests[] = {
         {"test_vector_store_creation", test_vector_store_creation}, {"test_insert_and_search", test_insert_and_search},
         {"test_stats", test_stats}, {"test_clear", test_clear}, {"test_get_chunk", test_get_chunk},
-        {"test_persistence", test_persistence}, {"test_guards", test_guards}, {"test_additive_methods", test_additive_methods},
+        {"test_persistence", test_persistence}, {"test_file_table_reopen", test_file_table_reopen}, {"test_guards", test_guards}, {"test_additive_methods", test_additive_methods},
         {"test_byte_prefilter", test_byte_prefilter},
     };
     for (auto &t : tests) {

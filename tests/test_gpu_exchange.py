@@ -76,6 +76,115 @@ def test_fused_exchange_three_ranks_one_gpu(cs, oracle):
         lib.csgpu_exchange_destroy(st.handle)
 
 
+def test_exchange_missing_rank_is_an_error_not_garbage(cs):
+    """SURVEY.md §5 "FFI must return errors (never abort)": only 2 of 3 ranks search. Their in-kernel wait gives up after
+    the configured bound, the status word (pinned host memory) is raised, and every later exchange search on those ranks
+    returns CSGPU_ERR_NCCL instead of undefined keys — until the exchange is created and connected again."""
+    import torch
+    from codesearch_b200 import _lib
+    from codesearch_b200.sharded import decode_keys
+    lib = _lib.load()
+    rng = np.random.default_rng(32)
+    n, d, W, k = 6000, 64, 3, 10
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    stores = []
+    for r in range(W):
+        st = cs.VectorStore.new(None, d)
+        st.append_rows(rows[r * 2000:(r + 1) * 2000], np.arange(r * 2000, (r + 1) * 2000, dtype=np.uint32))
+        st.build_index()
+        _lib.check(lib.csgpu_exchange_set_timeout_ms(st.handle, 100))
+        stores.append(st)
+
+    def connect():
+        for r, st in enumerate(stores):
+            h = (ctypes.c_ubyte * 64)()
+            _lib.check(lib.csgpu_exchange_create(st.handle, W, r, h))
+        peers = (ctypes.c_void_p * W)(*[st.handle for st in stores])
+        for st in stores:
+            _lib.check(lib.csgpu_exchange_connect_local(st.handle, peers))
+
+    connect()
+    streams = [torch.cuda.Stream() for _ in range(W)]
+    qd = torch.from_numpy(rng.standard_normal(d).astype(np.float32)).cuda()
+    outs = [torch.empty(k, dtype=torch.int64, device="cuda") for _ in range(W)]
+    torch.cuda.synchronize()
+    for r in (0, 1):                                             # rank 2 never launches
+        _lib.check(lib.csgpu_search_keys_exchange_device(stores[r].handle, qd.data_ptr(), k, outs[r].data_ptr(), streams[r].cuda_stream))
+    torch.cuda.synchronize()                                    # returns after ~0.1 s, not 4 s and not never
+    for r in (0, 1):
+        t = ctypes.c_uint32(0)
+        _lib.check(lib.csgpu_exchange_status(stores[r].handle, ctypes.byref(t)))
+        assert t.value == 1
+        rc = lib.csgpu_search_keys_exchange_device(stores[r].handle, qd.data_ptr(), k, outs[r].data_ptr(), streams[r].cuda_stream)
+        assert rc == _lib.ERR_NCCL and "timed out" in _lib.last_error()
+    t = ctypes.c_uint32(9)
+    _lib.check(lib.csgpu_exchange_status(stores[2].handle, ctypes.byref(t)))
+    assert t.value == 0
+    connect()                                                   # a fresh exchange heals all three
+    whole = cs.VectorStore.new(None, d)
+    whole.append_rows(rows, np.arange(n, dtype=np.uint32))
+    whole.build_index()
+    for r in range(W):
+        _lib.check(lib.csgpu_search_keys_exchange_device(stores[r].handle, qd.data_ptr(), k, outs[r].data_ptr(), streams[r].cuda_stream))
+    torch.cuda.synchronize()
+    gi, gd = whole.search_ids(qd.cpu().numpy(), k)
+    for r in range(W):
+        ids, dist = decode_keys(outs[r].cpu().numpy())
+        assert np.array_equal(ids, gi) and np.array_equal(dist, gd)
+    # skew diagnostic: one query since the reconnect, world entries, all far below the bound
+    ns = np.zeros(8 * W, dtype=np.uint64)
+    nq = ctypes.c_uint32(0)
+    _lib.check(lib.csgpu_exchange_wait_stats(stores[0].handle, ns.ctypes.data_as(_lib._u64p), 8, ctypes.byref(nq)))
+    assert nq.value == 1 and int(ns[:W].max()) < 100_000_000
+    for st in stores:
+        lib.csgpu_exchange_destroy(st.handle)
+
+
+def test_device_entry_points_two_streams_share_no_scratch(cs):
+    """Round-1 advisor finding: the device entry points returned their context to the shared pool while its scratch was in
+    flight. They now own a dedicated context and order successive calls with an event, so alternating streams without any
+    synchronisation in between — and host-pointer searches from another thread meanwhile — stay bit-identical."""
+    import threading
+    import torch
+    from codesearch_b200 import _lib
+    from codesearch_b200.sharded import decode_keys
+    lib = _lib.load()
+    rng = np.random.default_rng(33)
+    n, d, k = 300_000, 128, 10
+    st = cs.VectorStore.new(None, d)
+    st.append_synthetic(99, 0, n, 0)
+    st.build_index()
+    qs = rng.standard_normal((16, d)).astype(np.float32)
+    want = [st.search_ids(q, k) for q in qs]
+    qd = torch.from_numpy(qs).cuda()
+    outs = torch.empty((64, k), dtype=torch.int64, device="cuda")
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    stop = threading.Event()
+    bad = []
+
+    def host_searches():
+        i = 0
+        while not stop.is_set():
+            g = st.search_ids(qs[i % 16], k)
+            if not (np.array_equal(g[0], want[i % 16][0]) and np.array_equal(g[1], want[i % 16][1])):
+                bad.append(i)
+            i += 1
+
+    th = threading.Thread(target=host_searches)
+    th.start()
+    for i in range(64):
+        _lib.check(lib.csgpu_search_keys_device(st.handle, qd[i % 16].data_ptr(), k, outs[i].data_ptr(), streams[i & 1].cuda_stream))
+    torch.cuda.synchronize()
+    stop.set()
+    th.join()
+    assert not bad
+    got = outs.cpu().numpy()
+    for i in range(64):
+        ids, dist = decode_keys(got[i])
+        assert np.array_equal(ids, want[i % 16][0]) and np.array_equal(dist, want[i % 16][1]), i
+
+
 def _rank_main(rank, world, port, n, d, ks, ret):
     import torch
     import torch.distributed as dist

@@ -312,6 +312,30 @@ def test_filtered_parity(cs, oracle, density):
 
 
 # ---- batch -------------------------------------------------------------------------------------
+def test_empty_filters_allow_nothing_on_a_fresh_store(cs):
+    """Round-1 advisor finding: with n_bits == 0 (or a file bitmap of 0 bits) nothing was uploaded, a fresh context had no
+    bitmap pointer, and the launch silently took the UNFILTERED path. The header's contract: an empty filter allows no row
+    (ids >= n_bits are excluded) — on a fresh context and on one that held a bitmap before alike, zero-norm rows included."""
+    from codesearch_b200.tags import TagPredicate
+    rng = np.random.default_rng(5)
+    rows = rng.standard_normal((3000, 32)).astype(np.float32)
+    rows[7] = 0.0
+    for warm in (False, True):
+        st = cs.VectorStore.new(None, 32)
+        st.append_rows(rows, np.arange(3000, dtype=np.uint32), np.full(3000, 5, dtype=np.uint32))
+        st.build_index()
+        q = rng.standard_normal(32).astype(np.float32)
+        if warm:
+            assert len(st.search_ids(q, 10, cs.RowFilter.from_mask(np.ones(3000, bool)))[0]) == 10
+        ids, dist = st.search_ids(q, 10, cs.RowFilter(np.zeros(0, dtype=np.uint64), 0))
+        assert len(ids) == 0 and len(dist) == 0
+        ids, _ = st.search_ids(q, 10, cs.RowFilter(np.zeros(1, dtype=np.uint64), 0))
+        assert len(ids) == 0
+        ids, _ = st.search_tagged_ids(q, 10, TagPredicate(file_bitmap=np.zeros(1, dtype=np.uint64), n_file_bits=0))
+        assert len(ids) == 0
+        assert len(st.search_ids(q, 10)[0]) == 10
+
+
 def test_batch_matches_single(cs, oracle):
     rng = np.random.default_rng(12)
     n, d = 10000, 384

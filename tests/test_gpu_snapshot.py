@@ -45,6 +45,40 @@ def test_persistence(cs, tmp_path):
     assert st4.stats().total_chunks == 0 and not st4.is_indexed()
 
 
+def test_file_table_survives_delete_reinsert_reopen(cs, tmp_path):
+    """The row tags carry the file ids assigned at insert time. The reference's incremental reindex flow (delete a
+    file's chunks, re-insert them: src/index/mod.rs refresh path over store.rs:548-610,618-686) must not renumber files
+    on reopen, or a path filter selects the wrong files' rows (round-1 advisor finding)."""
+    db = str(tmp_path / "files.db")
+    st = cs.VectorStore.new(db, 4)
+    a = st.insert_chunks_with_ids([cs.EmbeddedChunk(cs.Chunk("fn a() {}", 0, 1, "Function", "src/a.rs"), [1.0, 0.0, 0.0, 0.0])])
+    b = st.insert_chunks_with_ids([cs.EmbeddedChunk(cs.Chunk("def b(): pass", 0, 1, "Function", "lib/b.py"), [0.0, 1.0, 0.0, 0.0])])
+    st.build_index()
+    assert st.delete_chunks(a) == 1
+    a2 = st.insert_chunks_with_ids([cs.EmbeddedChunk(cs.Chunk("fn a2() {}", 0, 1, "Function", "src/a.rs"), [0.9, 0.1, 0.0, 0.0])])
+    st.build_index()
+    want_a = [r.id for r in st.search_tagged([0.5, 0.5, 0.0, 0.0], 5, path_prefix="src/")]
+    want_b = [r.id for r in st.search_tagged([0.5, 0.5, 0.0, 0.0], 5, path_prefix="lib/")]
+    assert want_a == a2 and want_b == b
+    st.close()
+    st2 = cs.VectorStore.new(db, 4)
+    assert st2.files.paths == ["src/a.rs", "lib/b.py"]
+    assert [r.id for r in st2.search_tagged([0.5, 0.5, 0.0, 0.0], 5, path_prefix="src/")] == a2
+    assert [r.id for r in st2.search_tagged([0.5, 0.5, 0.0, 0.0], 5, path_prefix="lib/")] == b
+    assert [r.path for r in st2.search_tagged([0.5, 0.5, 0.0, 0.0], 5, languages=["Python"])] == ["lib/b.py"]
+    # every chunk of the FIRST file gone: the second file must keep id 1
+    st2.delete_chunks(a2)
+    st2.build_index()
+    st2.close()
+    st3 = cs.VectorStore.new(db, 4)
+    assert [r.id for r in st3.search_tagged([0.5, 0.5, 0.0, 0.0], 5, path_prefix="lib/")] == b
+    assert st3.search_tagged([0.5, 0.5, 0.0, 0.0], 5, path_prefix="src/") == []
+    c = st3.insert_chunks_with_ids([cs.EmbeddedChunk(cs.Chunk("x", 0, 1, "Function", "src/c.rs"), [0.0, 0.0, 1.0, 0.0])])
+    st3.build_index()
+    assert [r.id for r in st3.search_tagged([0.5, 0.5, 0.5, 0.0], 5, path_prefix="src/")] == c
+    st3.close()
+
+
 @pytest.mark.parametrize("dtype,d", [("fp32", 384), ("fp32", 100), ("bf16", 384)])
 def test_snapshot_roundtrip_bit_identical(cs, tmp_path, dtype, d):
     rng = np.random.default_rng(41)
