@@ -116,8 +116,16 @@ def test_bf16_lifecycle_and_errors(cs, oracle):
     check_bf16(gi, gd, ri, rd, r64, 20)
     with pytest.raises(cs.CsgpuError):
         cs.VectorStore.new(None, 100, dtype="bf16")           # dim % 64 != 0
-    with pytest.raises(cs.CsgpuError):
-        st.search_ids(np.zeros(384, np.float32), 5)           # zero-norm query unsupported on bf16
+    # zero-norm query: the contract's "distance 0.0" for every live row (arroy pn*qn == 0; include/csgpu.h) -> the k
+    # smallest live chunk ids, zero-norm row 17 included, deleted ids 5-7 excluded — same answer as the fp32 index gives
+    live = np.arange(3000, dtype=np.uint32)[keep]
+    for k in (5, 40, 300):
+        zi, zd = st.search_ids(np.zeros(384, np.float32), k)
+        assert np.array_equal(zi, live[:k]) and not zd.any(), k
+    bi, bd, bn = st.search_batch_ids(np.stack([q, np.zeros(384, np.float32), q]), 20)   # mixed into a batch
+    assert bn.tolist() == [20, 20, 20]
+    assert np.array_equal(bi[1], live[:20]) and not bd[1].any()
+    assert np.array_equal(bi[0], gi) and np.array_equal(bi[2], gi)
 
 
 def test_bf16_recall_reported(cs, oracle, capsys):
