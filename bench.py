@@ -984,6 +984,7 @@ def extras_c4(cs, _lib, lib, torch, dist, rank, world, local_rank, args, gather_
     sync_all()
     fused_ms = max_over_ranks(ev[2].elapsed_time(ev[3]) / steps)
     clk = smp.stop() if smp else None
+    sync_all()   # the ranks leave the sampler / gathers at different times: start the host-timed loop together
     t0 = time.perf_counter()
     for i in range(steps):
         searcher.search(qs[i % N_QUERIES], k)
