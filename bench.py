@@ -718,7 +718,7 @@ def extras_batch(store, lib, n, d, peaks_json, want):
                 gi, gd = store.search_ids(qs[j], k)
                 same = same and np.array_equal(res[0][j], gi) and bool(np.abs(res[1][j] - gd).max() <= 1e-6)
             small = {}
-            for bb in (16, 64, 128):
+            for bb in (16, 32, 64, 128):
                 dts, _, _, _ = _time_batches(store, lib, qs[:bb], k, 3)
                 small[str(bb)] = round(dts * 1e3, 3)
             return {"workload": f"{n}x{d} fp32 index, batch {b} x top-{k} (BASELINE configs[2], fp32 SIMT = the default route), host buffers",

@@ -45,7 +45,8 @@ constexpr uint32_t PREFILTER_MIN_BATCH = 1;   // tensor prefilter on: every csgp
                                               // 1.56 ms vs two multi-query passes at 3 ms each; it reads the 2-byte shadow, not the
                                               // 4-byte rows). csgpu_search itself always stays on the fp32 scan kernel.
 constexpr uint32_t I8_BEATS_MULTI = 4;        // byte prefilter on: this many single int8 queries beat one fp32 multi-query pass
-constexpr uint32_t GEMM_MIN_BATCH = 48;
+constexpr uint32_t GEMM_MIN_BATCH = 25;       // round 2: the 64-query SIMT tile answers <= 64 queries in 10.8 ms flat (10M x 384); three
+                                              // 8-query passes (24 queries) take 9.3 ms, four take 12.4 (profiles/r02_bench_batch_simt.txt)
 constexpr uint32_t GEMM_MIN_BATCH_NO_MULTI = 10;  // csgpu_search_batch switches to the SIMT GEMM path from here
 
 static int ctx_create(const csgpu_index *ix, Shard *sh, SearchCtx **out)
@@ -172,6 +173,12 @@ static int scan_static_mode()
     return v;
 }
 
+static bool scan_dynamic_all()
+{
+    static const bool v = [] { const char *e = getenv("CSGPU_SCAN_DYNAMIC_ALL"); return e && *e && atoi(e) != 0; }();
+    return v;
+}
+
 template <int V, bool EXACT, bool BIG, int OCC, bool DYN>
 static cudaError_t launch_scan_vd(const ScanArgs &a, uint32_t grid, size_t smem, cudaStream_t st)
 {
@@ -243,6 +250,11 @@ static int enqueue_scan(const csgpu_index *ix, const Shard *sh, SearchCtx *c, co
     a.xchg = xchg;
     a.seq = seq;
     if (pred) { a.tags = sh->tags; a.lang_mask = pred->lang_mask; a.file_lo = pred->file_lo; a.file_hi = pred->file_hi; }
+    // filtered scans keep the fixed-stride block split: the work counter was built and measured for them in round 2 and is
+    // NOT faster (768-d, top-200, density 1.0: 2.152 vs 2.141 ms; density 0.25: 0.70 vs 0.62 ms — most blocks are masked out
+    // and cost one tag load, so the grabs' atomics and the pipeline refill at chunk boundaries outweigh the balancing;
+    // profiles/r02_static_vs_dynamic_filtered_multi.txt). CSGPU_SCAN_DYNAMIC_ALL=1 switches it on for A/B runs.
+    a.static_split = scan_dynamic_all() ? 0u : 1u;
     const uint32_t per_cta_rows = SCAN_WARPS * rows_in_flight(ix->dim4);
     uint64_t want = (sh->n_built + per_cta_rows - 1) / per_cta_rows;
     if (bitmap_dev != nullptr || pred != nullptr) {   // filtered: pre-filter variant (scan_filtered.cu)
@@ -360,6 +372,9 @@ static int enqueue_scan_multi(const csgpu_index *ix, const Shard *sh, SearchCtx 
     a.cand = c->cand;
     a.ticket = c->ticket;
     a.out_keys = out_keys;
+    // measured (same file): the work counter is worth ~1.5 % with the CTA-shared buffers (8 queries x top-100: 3.26 vs
+    // 3.31 ms) and costs ~2 % with the per-warp lists (top-10: 2.81 vs 2.74 ms), so each kernel gets what is faster
+    a.static_split = scan_static_mode() == 1 ? 1u : (scan_dynamic_all() ? 0u : (k > 32 ? 0u : 1u));
     const uint32_t R = (ix->dim4 / 32 <= 4) ? 4 : 2;
     const uint64_t want = (sh->n_built + SCAN_WARPS * R - 1) / (SCAN_WARPS * R);
     uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sh->sm_count * multi_scan_ctas_per_sm(a.kpad), std::max<uint64_t>(want, 1));
@@ -1501,14 +1516,15 @@ int csgpu_search_batch(const csgpu_index *ix, const float *q, uint32_t q_len, ui
     if (!all_finite(q, q_len * b)) return fail(CSGPU_ERR_ARG, "query contains NaN/Inf");
     if (k == 0 || b == 0) return CSGPU_OK;
     if (ix->dtype == CSGPU_DTYPE_BF16) return batch_search(ix, q, b, k, out_ids, out_dist, out_n, nullptr);
-    // large batches: register-tiled fp32 SIMT GEMM + fused threshold filter (gemm_simt.cuh). It pads to 128-query
-    // blocks (20.5 ms per block at 10M x 384), so below 48 queries the HBM-bound multi-query scan (8 queries per
-    // 3.2 ms pass at k = 100) is faster.
+    // large batches: register-tiled fp32 SIMT GEMM + fused threshold filter (gemm_simt.cuh): 128-query blocks, or one
+    // 64-query block for <= 64 queries; below 25 queries the HBM-bound multi-query scan (8 queries per 3.1 ms pass at
+    // k = 100) is faster.
     bool prefilter = ix->tensor_prefilter;
     for (const Shard *sh : ix->shards) prefilter = prefilter && (sh->shadow_valid || sh->n_built == 0);
     // where the multi-query scan cannot serve (dim % 128 != 0 or k > 256) the alternative is one 2 ms scan per query,
     // which a 128-query SIMT block (20 ms) beats from ~10 queries on
-    const uint32_t gemm_min = multi_scan_supported(ix->dim4, k) ? GEMM_MIN_BATCH : GEMM_MIN_BATCH_NO_MULTI;
+    static const uint32_t env_min = [] { const char *e = getenv("CSGPU_GEMM_MIN_BATCH"); return e && *e ? (uint32_t)atoi(e) : 0u; }();   // tuning runs
+    const uint32_t gemm_min = env_min ? env_min : (multi_scan_supported(ix->dim4, k) ? GEMM_MIN_BATCH : GEMM_MIN_BATCH_NO_MULTI);
     if ((b >= gemm_min || (prefilter && b >= PREFILTER_MIN_BATCH)) && batch_gemm_available(ix)) {
         std::vector<uint32_t> zero_q;
         rc = batch_search(ix, q, b, k, out_ids, out_dist, out_n, &zero_q);

@@ -241,7 +241,8 @@ int batch_after_build(const csgpu_index *ix, Shard *sh)
         int rc = shadow_refresh(ix, sh);
         if (rc) return rc;
         if (!batch_f32_dim_supported(ix->dim_pad) || sh->rows == nullptr) return CSGPU_OK;
-        rc = make_map(&sh->map_c, sh->rows, sh->n_built, ix->dim_pad, GS_BN, true);
+        rc = make_map(&sh->map_c, sh->rows, sh->n_built, ix->dim_pad, GS_BN, true);                 // 128-query tile: 192 rows
+        if (!rc) rc = make_map(&sh->map_c2, sh->rows, sh->n_built, ix->dim_pad, GS_BN_SMALL, true);  // 64-query tile: 256 rows
         if (rc) return rc;
     }
     sh->map_valid = true;
@@ -315,7 +316,12 @@ static int batch_ctx(const csgpu_index *ix, Shard *sh, BatchCtx **out)
 // ---------------------------------------------------------------------------------------------
 // search
 // ---------------------------------------------------------------------------------------------
-static uint32_t tile_rows_of(const csgpu_index *ix, const Shard *sh) { return tc_path(ix, sh) ? GT_BLOCK_N : GS_BN; }
+// the SIMT kernel has two tile shapes: <= 64 queries take the 64-query x 256-row tile instead of a half-empty 128-query one
+static bool simt_small(uint32_t nq) { return nq <= (uint32_t)GS_BM_SMALL; }
+static uint32_t tile_rows_of(const csgpu_index *ix, const Shard *sh, uint32_t nq)
+{
+    return tc_path(ix, sh) ? GT_BLOCK_N : (simt_small(nq) ? GS_BN_SMALL : GS_BN);
+}
 
 // epilogue shape of the tensor-core kernel: threads per query. CSGPU_TC_EPI=1 selects the 4-warp epilogue for experiments.
 static uint32_t tc_epi_halves()
@@ -340,7 +346,7 @@ static CandLayout cand_layout(const csgpu_index *ix, const Shard *sh, uint32_t n
     return l;
 }
 
-static int launch_gemm(const csgpu_index *ix, Shard *sh, BatchCtx *c, const CUtensorMap &map_q, uint32_t n_qblocks,
+static int launch_gemm(const csgpu_index *ix, Shard *sh, BatchCtx *c, const CUtensorMap &map_q, uint32_t n_qblocks, uint32_t nq,
                        uint64_t t0, uint64_t t1)
 {
     GemmTopkArgs a;
@@ -386,11 +392,21 @@ static int launch_gemm(const csgpu_index *ix, Shard *sh, BatchCtx *c, const CUte
 #undef CS_GTK
     } else {
         a.n_kchunks = (ix->dim_pad + GS_BK - 1) / GS_BK;
-        constexpr int STAGES = 6;
-        const size_t smem = (size_t)STAGES * GS_STAGE_BYTES + 1024;
-        const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sh->sm_count, n_tiles * n_qblocks);
-        e = cudaFuncSetAttribute(gemm_simt_topk_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) gemm_simt_topk_kernel<STAGES><<<grid, GS_THREADS, smem, c->stream>>>(map_q, sh->map_c, a);
+        constexpr int STAGES = 5;   // 5 x 40 KB
+        if (simt_small(nq)) {
+            a.n_qblocks = 1;        // one 64-query block (the q map's box is 64 rows)
+            const size_t smem = (size_t)STAGES * gs_stage_bytes(GS_TM_SMALL, GS_TN_SMALL) + 1024;
+            const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sh->sm_count, n_tiles);
+            auto kern = gemm_simt_topk_kernel<GS_TM_SMALL, GS_TN_SMALL, STAGES>;
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) kern<<<grid, GS_THREADS, smem, c->stream>>>(map_q, sh->map_c2, a);
+        } else {
+            const size_t smem = (size_t)STAGES * gs_stage_bytes(GS_TM, GS_TN) + 1024;
+            const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sh->sm_count, n_tiles * n_qblocks);
+            auto kern = gemm_simt_topk_kernel<GS_TM, GS_TN, STAGES>;
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) kern<<<grid, GS_THREADS, smem, c->stream>>>(map_q, sh->map_c, a);
+        }
     }
     count_launch();
     if (e == cudaSuccess) e = cudaGetLastError();
@@ -449,7 +465,7 @@ static int run_range(const csgpu_index *ix, Shard *sh, BatchCtx *c, const CUtens
     const CandLayout lay = cand_layout(ix, sh, n_qblocks, t1 - t0);
     CS_CUDA(cudaMemcpyAsync(c->count_saved, c->count, nq_pad * sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
     if (careful) CS_CUDA(cudaMemsetAsync(c->scalar, 0, sizeof(unsigned), c->stream));
-    int rc = launch_gemm(ix, sh, c, map_q, n_qblocks, t0, t1);
+    int rc = launch_gemm(ix, sh, c, map_q, n_qblocks, nq, t0, t1);
     if (rc) return rc;
     check_counts_kernel<<<(nq_pad + 255) / 256, 256, 0, c->stream>>>(c->count, c->count_saved, lay.n_seg ? c->seg_count : nullptr,
                                                                      lay.n_seg, lay.seg_len, BF_CAP, nq_pad, c->scalar);
@@ -495,10 +511,11 @@ static int batch_search_shard(const csgpu_index *ix, Shard *sh, BatchCtx *c, con
     CS_CUDA(cudaStreamSynchronize(c->stream));
     *flags_out = flags_host;
     CUtensorMap map_q;
-    int rc = make_map(&map_q, c->q_prep, nq_pad, bf16 ? ix->dim : ix->dim_pad, GT_BLOCK_M, !bf16);
+    const uint32_t q_box = (!bf16 && simt_small(nq)) ? (uint32_t)GS_BM_SMALL : (uint32_t)GT_BLOCK_M;
+    int rc = make_map(&map_q, c->q_prep, nq_pad, bf16 ? ix->dim : ix->dim_pad, q_box, !bf16);
     if (rc) return rc;
 
-    const uint32_t tile_rows = tile_rows_of(ix, sh);
+    const uint32_t tile_rows = tile_rows_of(ix, sh, nq);
     const uint64_t n_tiles = (sh->n_built + tile_rows - 1) / tile_rows;
     // Each phase scans (growth-1) x everything seen so far, so ~ (growth-1) * k rows per query pass (x ~1.4 through the
     // prefilter's margin); that has to stay well inside the select kernel's sort buffer.

@@ -66,6 +66,7 @@ struct ScanArgs {
     uint32_t seq = 0;                   // exchange sequence number of this query (same on every rank, >= 1)
     const unsigned *run_if = nullptr;   // non-null: the whole launch is a no-op unless *run_if != 0 (device-side fallback of
                                         // the byte prefilter: the host cannot look at the status without synchronising)
+    uint32_t static_split = 0;          // filtered scans: 1 = fixed-stride block split instead of the work counter (CSGPU_SCAN_STATIC)
 };
 
 // LD selects the load flavour (tuned on B200, see profiles/): 0 = ld.global.nc.L1::no_allocate,
@@ -260,9 +261,68 @@ __device__ __forceinline__ void exchange_and_merge(const ScanArgs &a, Sel &sel, 
 // word (id-indexed, L2-resident: 1.25 MB per 10M ids); the ballot of allowed lanes is then consumed R rows at a time
 // with the same per-row FMA chain + shuffle tree as the unfiltered body (bit-identical scores). The id and bitmap
 // loads run two / one blocks ahead so their latency stays off the critical path.
+// Which 32-row block a warp takes next. Fixed stride (a.static_split, A/B runs): block gw + i * n_warps. Otherwise from the
+// global work counter (a.ticket + 1), in chunks of up to SCAN_CHUNK consecutive blocks while plenty is left and single
+// blocks near the end, the next grab issued before the current chunk is consumed — SMs stream at visibly different
+// rates, and the fixed split leaves bandwidth idle at the end of every query (the unfiltered scan's DYN path, below,
+// measured 1.5-2.8 %). Per-warp grabs for the per-warp register selector; for the CTA-shared selector (k > 32) the CTA
+// grabs "CTA iterations" (one block per warp) so that every warp runs the same number of iterations — the selector
+// synchronises inside the loop. `live` is false once there is nothing left (CTA-uniform for the CTA-shared selector).
+constexpr int SCAN_CHUNK = 8;
+template <bool CTA_SHARED>
+struct BlockCursor {
+    uint64_t n_blocks, gw, n_warps, i = 0, n_iters;
+    uint32_t cur = 0, end = 0, c_next, nxt = 0, n_units, div;
+    unsigned *work;
+    uint32_t *s_start;
+    bool dynamic, done = false;
+    int lane, warp;
+
+    __device__ __forceinline__ void init(const unsigned *run_static, unsigned *work_, uint32_t *s_start_, uint64_t n_blocks_, uint64_t gw_,
+                                         uint64_t n_warps_, int lane_, int warp_, bool dynamic_)
+    {
+        (void)run_static;
+        n_blocks = n_blocks_; gw = gw_; n_warps = n_warps_; work = work_; s_start = s_start_; lane = lane_; warp = warp_; dynamic = dynamic_;
+        const uint64_t b_first = gw - (gw % SCAN_WARPS);   // same trip count for every warp of the CTA
+        n_iters = b_first < n_blocks ? (n_blocks - b_first + n_warps - 1) / n_warps : 0;
+        n_units = CTA_SHARED ? (uint32_t)((n_blocks + SCAN_WARPS - 1) / SCAN_WARPS) : (uint32_t)n_blocks;
+        div = 2u * (uint32_t)(CTA_SHARED ? n_warps / SCAN_WARPS : n_warps);
+        c_next = max(1u, min((uint32_t)SCAN_CHUNK, n_units / div));
+        if (dynamic && (CTA_SHARED ? threadIdx.x == 0 : lane == 0)) nxt = atomicAdd(work, c_next);
+    }
+    // returns the block index (>= n_blocks: nothing to do for this warp) and sets live
+    __device__ __forceinline__ uint64_t next(bool &live)
+    {
+        if (!dynamic) {
+            live = i < n_iters;
+            return live ? gw + (i++) * n_warps : n_blocks;
+        }
+        if (cur >= end) {
+            if (done) { live = false; return n_blocks; }
+            uint32_t s;
+            if constexpr (CTA_SHARED) {
+                if (threadIdx.x == 0) *s_start = nxt;
+                __syncthreads();
+                s = *s_start;
+                __syncthreads();   // nobody still reads s_start when thread 0 rewrites it at the next boundary
+            } else {
+                s = __shfl_sync(FULL, nxt, 0);
+            }
+            if (s >= n_units) { done = true; live = false; return n_blocks; }
+            cur = s;
+            end = min(s + c_next, n_units);
+            c_next = max(1u, min((uint32_t)SCAN_CHUNK, (n_units - s) / div));
+            if (CTA_SHARED ? threadIdx.x == 0 : lane == 0) nxt = atomicAdd(work, c_next);
+        }
+        live = true;
+        const uint32_t u = cur++;
+        return CTA_SHARED ? (uint64_t)u * SCAN_WARPS + warp : (uint64_t)u;
+    }
+};
+
 template <int V, bool EXACT, int R, int LD, class Sel>
-__device__ __forceinline__ void scan_rows_filtered(const ScanArgs &a, const float4 (&qv)[V], bool qzero, Sel &sel, int lane,
-                                                   uint64_t gw, uint64_t n_warps)
+__device__ __forceinline__ void scan_rows_filtered(const ScanArgs &a, const float4 (&qv)[V], bool qzero, Sel &sel, int lane, int warp,
+                                                   uint64_t gw, uint64_t n_warps, uint32_t *s_start)
 {
     const uint64_t n = a.n_rows;
     const uint64_t n_blocks = (n + 31) / 32;
@@ -285,18 +345,20 @@ __device__ __forceinline__ void scan_rows_filtered(const ScanArgs &a, const floa
         if (tagmode && !have_bm) return valid ? ~0ull : 0ull;
         return (valid && (uint64_t)id < a.n_bits) ? __ldg(reinterpret_cast<const unsigned long long *>(a.bitmap) + (id >> 6)) : 0ull;
     };
-    bool v_cur, v_nxt, v_nx2;
-    uint32_t id_cur = load_id(gw, v_cur);
+    BlockCursor<Sel::CTA_SHARED> cursor;
+    cursor.init(nullptr, a.ticket + 1, s_start, n_blocks, gw, n_warps, lane, warp, a.static_split == 0);
+    // software pipeline: the id / tag of a block is loaded two blocks ahead of its use, the bitmap word one block ahead
+    bool v_cur, v_nxt, v_nx2, l_cur, l_nxt, l_nx2;
+    uint64_t b_cur = cursor.next(l_cur);
+    uint32_t id_cur = load_id(b_cur, v_cur);
     uint64_t w_cur = load_word(id_cur, v_cur);
-    uint32_t id_nxt = load_id(gw + n_warps, v_nxt);
-    // the trip count is the same for every warp of the CTA (the CTA-shared selector synchronises inside the loop);
-    // blocks past the end are fully predicated off by load_id
-    const uint64_t b_first = gw - (gw % SCAN_WARPS);
-    const uint64_t n_iters = b_first < n_blocks ? (n_blocks - b_first + n_warps - 1) / n_warps : 0;
-    uint64_t b = gw;
-    for (uint64_t it = 0; it < n_iters; ++it, b += n_warps) {
+    uint64_t b_nxt = cursor.next(l_nxt);
+    uint32_t id_nxt = load_id(b_nxt, v_nxt);
+    for (uint32_t it = 0; l_cur; ++it) {
         const uint64_t w_nxt = load_word(id_nxt, v_nxt);
-        const uint32_t id_nx2 = load_id(b + 2 * n_warps, v_nx2);
+        const uint64_t b_nx2 = cursor.next(l_nx2);
+        const uint32_t id_nx2 = load_id(b_nx2, v_nx2);
+        const uint64_t b = b_cur;
         unsigned m = __ballot_sync(FULL, (w_cur >> (id_cur & 63)) & 1ull);
         const float4 *blk = a.rows + b * 32 * a.dim4 + lane;
         while (m) {
@@ -333,8 +395,8 @@ __device__ __forceinline__ void scan_rows_filtered(const ScanArgs &a, const floa
                 }
             }
         }
-        id_cur = id_nxt; v_cur = v_nxt; w_cur = w_nxt;
-        id_nxt = id_nx2; v_nxt = v_nx2;
+        b_cur = b_nxt; l_cur = l_nxt; id_cur = id_nxt; v_cur = v_nxt; w_cur = w_nxt;
+        b_nxt = b_nx2; l_nxt = l_nx2; id_nxt = id_nx2; v_nxt = v_nx2;
         if constexpr (Sel::CTA_SHARED) { if (it & 1) sel.sync_point(2 * 32 * SCAN_WARPS); }
     }
 }
@@ -344,7 +406,6 @@ __device__ __forceinline__ void scan_rows_filtered(const ScanArgs &a, const floa
 // last), so the fixed split leaves bandwidth idle at the end of every query; chunks of up to SCAN_CHUNK groups, single
 // groups near the end, next grab issued before the current chunk is processed. Which warp scans a row does not change
 // its score, and selection is a total order, so results are bit-identical either way.
-constexpr int SCAN_CHUNK = 8;
 template <int V, bool EXACT, int R, bool BIG, int OCC = (BIG ? 1 : 2), int LD = 0, bool FILT = false, bool DYN = !FILT>
 __global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const ScanArgs a)
 {
@@ -420,7 +481,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const Scan
             }
         }
     };
-    if constexpr (FILT) scan_rows_filtered<V, EXACT, R, LD>(a, qv, qzero, sel, lane, gw, n_warps);
+    __shared__ uint32_t s_start;   // CTA-level work grabs (dynamic split with the CTA-shared selector)
+    if constexpr (FILT) scan_rows_filtered<V, EXACT, R, LD>(a, qv, qzero, sel, lane, warp, gw, n_warps, &s_start);
     else if constexpr (DYN && !BIG) {
         // per-warp grabs of up to SCAN_CHUNK groups
         const uint32_t n_grp = (uint32_t)n_groups, nw2 = 2u * (uint32_t)n_warps;   // n_rows < 2^32, R >= 2
@@ -438,7 +500,6 @@ __global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const Scan
     } else if constexpr (DYN) {
         // CTA-shared selector: the CTA synchronises at every sync point anyway, so the whole CTA grabs up to SCAN_CHUNK
         // "CTA iterations" (one group per warp) at a time; thread 0 issues the next grab before the chunk is processed
-        __shared__ uint32_t s_start;
         const uint32_t n_cit = (uint32_t)((n_groups + SCAN_WARPS - 1) / SCAN_WARPS), g2 = 2u * gridDim.x;
         unsigned *work = a.ticket + 1;
         uint32_t c_next = max(1u, min((uint32_t)SCAN_CHUNK, n_cit / g2)), nxt = 0;

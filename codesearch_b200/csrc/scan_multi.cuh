@@ -31,8 +31,9 @@ struct MultiArgs {
     const uint32_t *zero_ids;
     uint32_t n_zero;
     uint64_t *cand;        // [MQ][gridDim.x][k]
-    unsigned *ticket;
+    unsigned *ticket;      // [0] last-CTA ticket, [1] work counter of the dynamic row split (both self-resetting)
     uint64_t *out_keys;    // [nq][k]
+    uint32_t static_split = 0;   // 1 = fixed-stride row split (CSGPU_SCAN_STATIC=1, A/B runs)
 };
 
 template <int NV, int O>
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, (E <= 4) ? 2 : 1) scan_multi_top
     const uint64_t n = a.n_rows;
     const uint64_t gw = (uint64_t)blockIdx.x * SCAN_WARPS + warp;
     const uint64_t stride = (uint64_t)gridDim.x * SCAN_WARPS * R;
-    for (uint64_t base = gw * R; base < n; base += stride) {
+    auto scan_group = [&](uint64_t base) {
         float4 x[R][V];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -233,6 +234,23 @@ __global__ void __launch_bounds__(SCAN_THREADS, (E <= 4) ? 2 : 1) scan_multi_top
                 if (kk < sel.thr_of(b)) sel.append(b, kk, lane);
             }
             if (my_active) thr = sel.thr_of(my_b);
+        }
+    };
+    if (a.static_split) {
+        for (uint64_t base = gw * R; base < n; base += stride) scan_group(base);
+    } else {
+        // dynamic row split (see scan.cuh DYN): per-warp grabs of up to SCAN_CHUNK groups of R rows from a global counter
+        const uint32_t n_grp = (uint32_t)((n + R - 1) / R), nw2 = 2u * gridDim.x * SCAN_WARPS;
+        unsigned *work = a.ticket + 1;
+        uint32_t c_next = max(1u, min((uint32_t)SCAN_CHUNK, n_grp / nw2)), nxt = 0;
+        if (lane == 0) nxt = atomicAdd(work, c_next);
+        for (;;) {
+            const uint32_t c_start = __shfl_sync(FULL, nxt, 0);
+            if (c_start >= n_grp) break;
+            const uint32_t c_end = min(c_start + c_next, n_grp);
+            c_next = max(1u, min((uint32_t)SCAN_CHUNK, (n_grp - c_start) / nw2));
+            if (lane == 0) nxt = atomicAdd(work, c_next);
+            for (uint32_t grp = c_start; grp < c_end; ++grp) scan_group((uint64_t)grp * R);
         }
     }
 
@@ -299,7 +317,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, (E <= 4) ? 2 : 1) scan_multi_top
         }
         reduce_query(b, a.out_keys + (size_t)b * a.k);
     }
-    if (threadIdx.x == 0) *a.ticket = 0;
+    if (threadIdx.x == 0) { a.ticket[0] = 0; a.ticket[1] = 0; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -378,8 +396,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_multi_cta_topk_kernel(co
     const uint64_t n_warps = (uint64_t)gridDim.x * SCAN_WARPS;
     const uint64_t n_groups = (n + R - 1) / R, g_first = (uint64_t)blockIdx.x * SCAN_WARPS;
     const uint64_t n_iters = g_first < n_groups ? (n_groups - g_first + n_warps - 1) / n_warps : 0;   // same for every warp of the CTA
-    for (uint64_t it = 0; it < n_iters; ++it) {
-        const uint64_t base = (gw + it * n_warps) * R;
+    auto scan_group = [&](uint64_t base) {
         float4 x[R][V];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -421,7 +438,32 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_multi_cta_topk_kernel(co
             const uint64_t kk = make_key(dist, id);
             if (kk < thr && id_allowed(a.bitmap, a.n_bits, id)) my_buf[atomicAdd(&cnt_s[my_b], 1u)] = kk;
         }
-        if ((it & 7) == 7) sync_point();
+    };
+    if (a.static_split) {
+        for (uint64_t it = 0; it < n_iters; ++it) {
+            scan_group((gw + it * n_warps) * R);
+            if ((it & 7) == 7) sync_point();
+        }
+    } else {
+        // dynamic row split: the CTA synchronises at its sync points anyway, so the whole CTA grabs up to SCAN_CHUNK (= 8,
+        // the sync interval SLACK is sized for) "CTA iterations" (one group of R rows per warp) at a time from a global
+        // counter; thread 0 issues the next grab before the chunk is processed (see scan.cuh, DYN && BIG)
+        __shared__ uint32_t s_start;
+        const uint32_t n_cit = (uint32_t)((n_groups + SCAN_WARPS - 1) / SCAN_WARPS), g2 = 2u * gridDim.x;
+        unsigned *work = a.ticket + 1;
+        uint32_t c_next = max(1u, min((uint32_t)SCAN_CHUNK, n_cit / g2)), nxt = 0;
+        if (threadIdx.x == 0) nxt = atomicAdd(work, c_next);
+        for (;;) {
+            if (threadIdx.x == 0) s_start = nxt;
+            __syncthreads();
+            const uint32_t c_start = s_start;
+            if (c_start >= n_cit) break;
+            const uint32_t c_end = min(c_start + c_next, n_cit);
+            c_next = max(1u, min((uint32_t)SCAN_CHUNK, (n_cit - c_start) / g2));
+            if (threadIdx.x == 0) nxt = atomicAdd(work, c_next);
+            for (uint32_t it = c_start; it < c_end; ++it) scan_group(((uint64_t)it * SCAN_WARPS + warp) * R);
+            sync_point();   // barrier inside: s_start is free to be rewritten
+        }
     }
 
     // ---- per query: CTA top-k -> cand[b][cta][k] ----
@@ -476,7 +518,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_multi_cta_topk_kernel(co
         for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) a.out_keys[(size_t)b * k + j] = buf[j];
         __syncthreads();
     }
-    if (threadIdx.x == 0) *a.ticket = 0;
+    if (threadIdx.x == 0) { a.ticket[0] = 0; a.ticket[1] = 0; }
 }
 
 
