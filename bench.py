@@ -327,7 +327,8 @@ def main():
     cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        cpu_group = dist.new_group(backend="gloo")   # host-side barriers / gathers that must not put kernels on the GPUs
+        from datetime import timedelta
+        cpu_group = dist.new_group(backend="gloo", timeout=timedelta(seconds=600))   # host-side barriers / gathers that must not put kernels on the GPUs
     assert world == args.gpus or world == 1 and args.gpus == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
     import codesearch_b200 as cs

@@ -467,10 +467,10 @@ static int run_range(const csgpu_index *ix, Shard *sh, BatchCtx *c, const CUtens
     if (careful) CS_CUDA(cudaMemsetAsync(c->scalar, 0, sizeof(unsigned), c->stream));
     int rc = launch_gemm(ix, sh, c, map_q, n_qblocks, nq, t0, t1);
     if (rc) return rc;
-    check_counts_kernel<<<(nq_pad + 255) / 256, 256, 0, c->stream>>>(c->count, c->count_saved, lay.n_seg ? c->seg_count : nullptr,
-                                                                     lay.n_seg, lay.seg_len, BF_CAP, nq_pad, c->scalar);
-    count_launch();
-    if (careful) {
+    if (careful) {   // the optimistic run leaves these checks to the select kernel (same conditions, same sticky flag)
+        check_counts_kernel<<<(nq_pad + 255) / 256, 256, 0, c->stream>>>(c->count, c->count_saved, lay.n_seg ? c->seg_count : nullptr,
+                                                                         lay.n_seg, lay.seg_len, BF_CAP, nq_pad, c->scalar);
+        count_launch();
         unsigned over = 0;
         CS_CUDA(cudaMemcpyAsync(&over, c->scalar, sizeof over, cudaMemcpyDeviceToHost, c->stream));
         CS_CUDA(cudaStreamSynchronize(c->stream));
@@ -500,12 +500,12 @@ static int batch_search_shard(const csgpu_index *ix, Shard *sh, BatchCtx *c, con
     CS_CUDA(cudaMemsetAsync(c->scalar, 0, 64, c->stream));
     memcpy(c->q_pin, q_host, (size_t)nq * ix->dim * sizeof(float));
     CS_CUDA(cudaMemcpyAsync(c->q_f32, c->q_pin, (size_t)nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    // query prep also initialises the per-query threshold (+inf, or -1 for padding / zero-norm queries) and candidate count
     if (bf16)
-        prep_queries_bf16_kernel<<<(nq_pad * 32 + 255) / 256, 256, 0, c->stream>>>(c->q_f32, nq, ix->dim, reinterpret_cast<__nv_bfloat16 *>(c->q_prep), nq_pad, c->flags);
+        prep_queries_bf16_kernel<<<(nq_pad * 32 + 255) / 256, 256, 0, c->stream>>>(c->q_f32, nq, ix->dim, reinterpret_cast<__nv_bfloat16 *>(c->q_prep), nq_pad, c->flags, c->thr, c->count);
     else
-        prep_queries_f32_kernel<<<(nq_pad * 32 + 255) / 256, 256, 0, c->stream>>>(c->q_f32, nq, ix->dim, ix->dim_pad, reinterpret_cast<float *>(c->q_prep), nq_pad, c->flags);
-    init_thresholds_kernel<<<(nq_pad + 255) / 256, 256, 0, c->stream>>>(c->thr, c->count, c->flags, nq, nq_pad);
-    count_launch(2);
+        prep_queries_f32_kernel<<<(nq_pad * 32 + 255) / 256, 256, 0, c->stream>>>(c->q_f32, nq, ix->dim, ix->dim_pad, reinterpret_cast<float *>(c->q_prep), nq_pad, c->flags, c->thr, c->count);
+    count_launch();
     uint8_t *flags_host = reinterpret_cast<uint8_t *>(c->out_pin) + (size_t)BF_MAX_QBLOCKS * GT_BLOCK_M * CSGPU_MAX_K * sizeof(uint64_t);
     CS_CUDA(cudaMemcpyAsync(flags_host, c->flags, nq, cudaMemcpyDeviceToHost, c->stream));
     CS_CUDA(cudaStreamSynchronize(c->stream));

@@ -313,14 +313,15 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 // ---- query prep: fp32 [b][dim] -> unit length -> bf16 [QB*128][dim] (rows >= b zero) -------------
 // flags[q] = 1 if the query has zero norm.
 static __global__ void prep_queries_bf16_kernel(const float *__restrict__ q, uint32_t b, uint32_t dim,
-                                         __nv_bfloat16 *__restrict__ out, uint32_t b_pad, uint8_t *__restrict__ flags)
+                                         __nv_bfloat16 *__restrict__ out, uint32_t b_pad, uint8_t *__restrict__ flags,
+                                         float *__restrict__ thr, unsigned *__restrict__ count)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= b_pad) return;
     if (w >= b) {
         for (uint32_t c = lane; c < dim; c += 32) out[(size_t)w * dim + c] = __float2bfloat16(0.f);
-        if (lane == 0) flags[w] = 0;
+        if (lane == 0) { flags[w] = 0; thr[w] = -1.f; count[w] = 0; }
         return;
     }
     double ss = 0.0;
@@ -330,7 +331,7 @@ static __global__ void prep_queries_bf16_kernel(const float *__restrict__ q, uin
     const bool zero = !(ss > 0.0);
     const double inv = zero ? 0.0 : 1.0 / sqrt(ss);
     for (uint32_t c = lane; c < dim; c += 32) out[(size_t)w * dim + c] = __float2bfloat16((float)(q[(size_t)w * dim + c] * inv));
-    if (lane == 0) flags[w] = zero ? 1 : 0;
+    if (lane == 0) { flags[w] = zero ? 1 : 0; thr[w] = zero ? -1.f : __int_as_float(0x7f800000); count[w] = 0; }
 }
 
 }  // namespace csgpu

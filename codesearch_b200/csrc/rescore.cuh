@@ -141,7 +141,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) select_sorted_kernel(const Se
     const uint32_t done = a.n_seg ? n1 : min(a.n_done[q], n1);
 
     // ---- gather: survivors -> S (RESCORE) or C; fresh candidates -> C ----
-    for (uint32_t s = threadIdx.x; s < a.n_seg; s += blockDim.x) s_pref[s] = min(a.seg_count[(size_t)q * a.n_seg + s], a.seg_len);
+    // (the overflow checks that used to be a launch of their own — check_counts_kernel — ride along here: a segment or the
+    //  SIMT buffer holding more than it can, or more fresh candidates than the sort buffer takes, raises the sticky flag)
+    for (uint32_t s = threadIdx.x; s < a.n_seg; s += blockDim.x) {
+        const unsigned c = a.seg_count[(size_t)q * a.n_seg + s];
+        if (c > a.seg_len) atomicExch(a.overflow, 1u);
+        s_pref[s] = min(c, a.seg_len);
+    }
+    if (threadIdx.x == 0 && !a.n_seg && a.count[q] > a.stride) atomicExch(a.overflow, 1u);
     __syncthreads();
     if (threadIdx.x == 0) {   // exclusive prefix of the segment counts (n_seg <= 2 * 148)
         unsigned run = n1 - done;
