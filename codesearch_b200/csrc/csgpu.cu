@@ -45,8 +45,9 @@ constexpr uint32_t PREFILTER_MIN_BATCH = 1;   // tensor prefilter on: every csgp
                                               // 1.56 ms vs two multi-query passes at 3 ms each; it reads the 2-byte shadow, not the
                                               // 4-byte rows). csgpu_search itself always stays on the fp32 scan kernel.
 constexpr uint32_t I8_BEATS_MULTI = 4;        // byte prefilter on: this many single int8 queries beat one fp32 multi-query pass
-constexpr uint32_t GEMM_MIN_BATCH = 25;       // round 2: the 64-query SIMT tile answers <= 64 queries in 10.8 ms flat (10M x 384); three
-                                              // 8-query passes (24 queries) take 9.3 ms, four take 12.4 (profiles/r02_bench_batch_simt.txt)
+constexpr uint32_t GEMM_MIN_BATCH = 33;       // round 2: the 64-query SIMT tile answers <= 64 queries in 10.2 ms flat (10M x 384, top-100);
+                                              // two 16-query passes (<= 32 queries) take 9.8 ms, three 14.6
+                                              // (profiles/r02_bench_batch_simt.txt, r02_bench_multi16.txt)
 constexpr uint32_t GEMM_MIN_BATCH_NO_MULTI = 10;  // csgpu_search_batch switches to the SIMT GEMM path from here
 
 static int ctx_create(const csgpu_index *ix, Shard *sh, SearchCtx **out)
@@ -61,7 +62,7 @@ static int ctx_create(const csgpu_index *ix, Shard *sh, SearchCtx **out)
     CS_CUDA(cudaEventCreate(&c->ev1));
     CS_CUDA(cudaMalloc(&c->q_dev, (size_t)MAX_BATCH * ix->dim_pad * sizeof(float)));
     CS_CUDA(cudaHostAlloc(&c->q_pin, (size_t)MAX_BATCH * ix->dim_pad * sizeof(float), cudaHostAllocDefault));
-    c->cand_cap = (size_t)MAX_GRID * CSGPU_MAX_K;
+    c->cand_cap = (size_t)MAX_GRID * CSGPU_MAX_K * 2;   // single query: grid x k <= 592 x 1024; 16-query pass: 16 x 296 x 256
     CS_CUDA(cudaMalloc(&c->cand, c->cand_cap * sizeof(uint64_t)));
     CS_CUDA(cudaMalloc(&c->gather, (size_t)8 * 2 * CSGPU_MAX_K * sizeof(uint64_t)));
     CS_CUDA(cudaMalloc(&c->ticket, 64 * sizeof(unsigned)));
@@ -364,7 +365,6 @@ static int enqueue_scan_multi(const csgpu_index *ix, const Shard *sh, SearchCtx 
     a.q = q_dev;
     a.nq = nq;
     a.k = k;
-    a.kpad = k > 32 ? ctabuf_cap(k) : 32;   // k > 32: capacity of the per-(CTA, query) candidate buffer
     a.bitmap = nullptr;
     a.n_bits = 0;
     a.zero_ids = with_zero_ids ? ix->zero_ids_dev : nullptr;
@@ -372,12 +372,18 @@ static int enqueue_scan_multi(const csgpu_index *ix, const Shard *sh, SearchCtx 
     a.cand = c->cand;
     a.ticket = c->ticket;
     a.out_keys = out_keys;
-    // measured (same file): the work counter is worth ~1.5 % with the CTA-shared buffers (8 queries x top-100: 3.26 vs
-    // 3.31 ms) and costs ~2 % with the per-warp lists (top-10: 2.81 vs 2.74 ms), so each kernel gets what is faster
+    // measured (profiles/r02_static_vs_dynamic_filtered_multi.txt): the work counter is worth ~1.5 % with the CTA-shared
+    // buffers (8 queries x top-100: 3.26 vs 3.31 ms) and costs ~2 % with the per-warp lists (top-10: 2.81 vs 2.74 ms), so
+    // each kernel gets what is faster
     a.static_split = scan_static_mode() == 1 ? 1u : (scan_dynamic_all() ? 0u : (k > 32 ? 0u : 1u));
-    const uint32_t R = (ix->dim4 / 32 <= 4) ? 4 : 2;
+    const uint32_t R = multi_scan_rows_per_iter(ix->dim4, nq);
     const uint64_t want = (sh->n_built + SCAN_WARPS * R - 1) / (SCAN_WARPS * R);
-    uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sh->sm_count * multi_scan_ctas_per_sm(a.kpad), std::max<uint64_t>(want, 1));
+    // the buffer capacity depends on the grid (the last CTA takes one key per CTA and column) and the grid on what fits an SM
+    uint32_t per_sm = 2;
+    a.kpad = multi_scan_cap(k, nq, (uint32_t)sh->sm_count * per_sm);
+    per_sm = multi_scan_ctas_per_sm(ix->dim4, k, nq, a.kpad);
+    if (per_sm == 1) a.kpad = multi_scan_cap(k, nq, (uint32_t)sh->sm_count);
+    uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sh->sm_count * per_sm, std::max<uint64_t>(want, 1));
     // cand holds nq x grid x k keys: never launch more CTAs than the scratch was sized for (a part with more SMs than 148)
     grid = (uint32_t)std::min<uint64_t>(grid, std::max<uint64_t>(c->cand_cap / ((uint64_t)nq * std::max(k, 1u)), 1));
     cudaError_t e = launch_scan_multi(a, grid, st);
@@ -1517,8 +1523,8 @@ int csgpu_search_batch(const csgpu_index *ix, const float *q, uint32_t q_len, ui
     if (k == 0 || b == 0) return CSGPU_OK;
     if (ix->dtype == CSGPU_DTYPE_BF16) return batch_search(ix, q, b, k, out_ids, out_dist, out_n, nullptr);
     // large batches: register-tiled fp32 SIMT GEMM + fused threshold filter (gemm_simt.cuh): 128-query blocks, or one
-    // 64-query block for <= 64 queries; below 25 queries the HBM-bound multi-query scan (8 queries per 3.1 ms pass at
-    // k = 100) is faster.
+    // 64-query block for <= 64 queries; up to 32 queries the multi-query scan (8 queries per 3.0 ms pass, 9..16 per 4.9 ms
+    // pass at k = 100) is faster.
     bool prefilter = ix->tensor_prefilter;
     for (const Shard *sh : ix->shards) prefilter = prefilter && (sh->shadow_valid || sh->n_built == 0);
     // where the multi-query scan cannot serve (dim % 128 != 0 or k > 256) the alternative is one 2 ms scan per query,
@@ -1535,7 +1541,7 @@ int csgpu_search_batch(const csgpu_index *ix, const float *q, uint32_t q_len, ui
         }
         return rc;
     }
-    // chunks of up to 8 queries share ONE pass over the corpus (scan_multi.cuh); leftovers of one query,
+    // chunks of up to 16 queries share ONE pass over the corpus (scan_multi.cuh); leftovers of one query,
     // k > 256 or dims that are not a multiple of 128 take the single-query kernel.
     const uint32_t MQ = multi_scan_max_queries();
     const bool multi_ok = multi_scan_supported(ix->dim4, k);

@@ -201,7 +201,9 @@ cudaError_t launch_scan_filtered(const ScanArgs &a, uint32_t grid, size_t smem, 
 struct MultiArgs;
 bool multi_scan_supported(uint32_t dim4, uint32_t k);
 uint32_t multi_scan_max_queries();
-uint32_t multi_scan_ctas_per_sm(uint32_t kpad);
+uint32_t multi_scan_ctas_per_sm(uint32_t dim4, uint32_t k, uint32_t nq, uint32_t kpad);
+uint32_t multi_scan_rows_per_iter(uint32_t dim4, uint32_t nq);
+uint32_t multi_scan_cap(uint32_t k, uint32_t nq, uint32_t grid);
 cudaError_t launch_scan_multi(const MultiArgs &a, uint32_t grid, cudaStream_t st);
 
 }  // namespace csgpu

@@ -119,15 +119,20 @@ struct MultiSel {
     }
 };
 
-// smem per CTA: queries MQ*dim4 float4 | per warp: MQ*KPAD + MQ*32 keys + MQ u32 | sort buffer WARPS*KPAD keys
+// smem per CTA: queries MQT*dim4 float4 | per warp: MQT*KPAD + MQT*32 keys + MQT u32 | sort buffer WARPS*KPAD keys
 template <int E>
 __host__ __device__ constexpr size_t multi_warp_keys(int mq) { return (size_t)mq * (32 * E) + (size_t)mq * 32; }
 
-template <int V, int R, int MQ, int E>
+// NG (round 2): query groups per pass. The rows a warp has loaded are scored against NG groups of MQ queries one after the
+// other (same registers, same per-(row, query) arithmetic), so 9..16 queries cost ONE pass over HBM and twice the FMA
+// work, at the same LDS : FFMA ratio as the 8-query kernel. (A 16-query x 2-row variant was built first and measured no
+// faster than two 8-query passes — 5.4 ms: each query float4 read from shared memory fed only 8 FMAs.)
+template <int V, int R, int MQ, int NG, int E>
 __global__ void __launch_bounds__(SCAN_THREADS, (E <= 4) ? 2 : 1) scan_multi_topk_kernel(const MultiArgs a)
 {
     constexpr bool EXACT = true;   // dim % 128 == 0 only (other dims: per-query loop of scan.cuh)
-    constexpr int NV = R * MQ;     // 8, 16 or 32 results per warp iteration
+    constexpr int MQT = MQ * NG;   // queries per pass
+    constexpr int NV = R * MQ;     // 8, 16 or 32 results per warp iteration and query group
     constexpr int SH = (NV == 32) ? 0 : (NV == 16 ? 1 : 2);
     static_assert(NV == 32 || NV == 16 || NV == 8, "R*MQ must be 8, 16 or 32");
     constexpr uint32_t KPAD = 32u * E;
@@ -136,16 +141,16 @@ __global__ void __launch_bounds__(SCAN_THREADS, (E <= 4) ? 2 : 1) scan_multi_top
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t dim4 = a.dim4;
 
-    float4 *qs = reinterpret_cast<float4 *>(smem_raw);                                   // [MQ][dim4]
-    uint64_t *keys0 = reinterpret_cast<uint64_t *>(smem_raw + (size_t)MQ * dim4 * sizeof(float4));
-    const size_t wkeys = multi_warp_keys<E>(MQ);
+    float4 *qs = reinterpret_cast<float4 *>(smem_raw);                                   // [MQT][dim4]
+    uint64_t *keys0 = reinterpret_cast<uint64_t *>(smem_raw + (size_t)MQT * dim4 * sizeof(float4));
+    const size_t wkeys = multi_warp_keys<E>(MQT);
     uint64_t *wbase = keys0 + (size_t)warp * wkeys;
     uint64_t *sortbuf = keys0 + (size_t)SCAN_WARPS * wkeys;                              // [WARPS*KPAD]
-    uint32_t *np_all = reinterpret_cast<uint32_t *>(sortbuf + (size_t)SCAN_WARPS * KPAD); // [WARPS][MQ]
-    __shared__ float qflag[MQ];  // 1.0f if the query has zero norm (distance 0.0 everywhere)
+    uint32_t *np_all = reinterpret_cast<uint32_t *>(sortbuf + (size_t)SCAN_WARPS * KPAD); // [WARPS][MQT]
+    __shared__ float qflag[MQT];  // 1.0f if the query has zero norm (distance 0.0 everywhere)
 
     // ---- queries -> smem, unit-normalised exactly as scan.cuh does it (warp w handles query w) ----
-    for (int b = warp; b < MQ; b += SCAN_WARPS) {
+    for (int b = warp; b < MQT; b += SCAN_WARPS) {
         float4 t[V];
         float ss = 0.f;
 #pragma unroll
@@ -167,16 +172,21 @@ __global__ void __launch_bounds__(SCAN_THREADS, (E <= 4) ? 2 : 1) scan_multi_top
         if (lane == 0) qflag[b] = qzero ? 1.f : 0.f;
     }
     MultiSel<E> sel;
-    sel.init(wbase, wbase + (size_t)MQ * KPAD, np_all + warp * MQ, a.k, MQ, lane);
+    sel.init(wbase, wbase + (size_t)MQT * KPAD, np_all + warp * MQT, a.k, MQT, lane);
     __syncthreads();
 
-    // lane -> (row slot, query) ownership after the butterfly
+    // lane -> (row slot, query) ownership after the butterfly, one query per group
     const int own = lane >> SH;
     const bool owner = (lane & ((1 << SH) - 1)) == 0;
     const int my_b = own % MQ, my_r = own / MQ;
-    const bool my_active = owner && (uint32_t)my_b < a.nq;
-    const bool my_qzero = qflag[my_b] != 0.f;
-    uint64_t thr = my_active ? KEY_EMPTY : 0ull;  // inactive lanes never pass
+    bool my_active[NG], my_qzero[NG];
+    uint64_t thr[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        my_active[g] = owner && (uint32_t)(my_b + g * MQ) < a.nq;
+        my_qzero[g] = qflag[my_b + g * MQ] != 0.f;
+        thr[g] = my_active[g] ? KEY_EMPTY : 0ull;  // inactive lanes never pass
+    }
 
     const uint64_t n = a.n_rows;
     const uint64_t gw = (uint64_t)blockIdx.x * SCAN_WARPS + warp;
@@ -193,47 +203,51 @@ __global__ void __launch_bounds__(SCAN_THREADS, (E <= 4) ? 2 : 1) scan_multi_top
                 else x[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-        float v[32];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) v[i] = 0.f;
+        for (int g = 0; g < NG; ++g) {
+            if (g > 0 && (uint32_t)(g * MQ) >= a.nq) break;   // warp-uniform: no query in this group
+            float v[32];
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
+            for (int i = 0; i < NV; ++i) v[i] = 0.f;
 #pragma unroll
-            for (int b = 0; b < MQ; ++b) {
-                float4 qq = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (EXACT || lane + 32 * j < dim4) qq = qs[(size_t)b * dim4 + lane + 32 * j];
+            for (int j = 0; j < V; ++j) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    float acc = v[r * MQ + b];
-                    acc = fmaf(x[r][j].x, qq.x, acc); acc = fmaf(x[r][j].y, qq.y, acc);
-                    acc = fmaf(x[r][j].z, qq.z, acc); acc = fmaf(x[r][j].w, qq.w, acc);
-                    v[r * MQ + b] = acc;
+                for (int b = 0; b < MQ; ++b) {
+                    float4 qq = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (EXACT || lane + 32 * j < dim4) qq = qs[(size_t)(g * MQ + b) * dim4 + lane + 32 * j];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        float acc = v[r * MQ + b];
+                        acc = fmaf(x[r][j].x, qq.x, acc); acc = fmaf(x[r][j].y, qq.y, acc);
+                        acc = fmaf(x[r][j].z, qq.z, acc); acc = fmaf(x[r][j].w, qq.w, acc);
+                        v[r * MQ + b] = acc;
+                    }
                 }
             }
-        }
-        butterfly_level<NV, 16>(v, lane);
-        butterfly_level<(NV / 2 > 0 ? NV / 2 : 1), 8>(v, lane);
-        butterfly_level<(NV / 4 > 0 ? NV / 4 : 1), 4>(v, lane);
-        butterfly_level<(NV / 8 > 0 ? NV / 8 : 1), 2>(v, lane);
-        butterfly_level<(NV / 16 > 0 ? NV / 16 : 1), 1>(v, lane);
-        const float dist = my_qzero ? 0.f : fmaf(-0.5f, v[0], 0.5f);
-        const uint64_t row = base + my_r;
-        uint64_t key = KEY_EMPTY;
-        if (my_active && row < n && okey(dist) <= (uint32_t)(thr >> 32)) {
-            const uint32_t id = a.ids[row];
-            const uint64_t kk = make_key(dist, id);
-            if (kk < thr && id_allowed(a.bitmap, a.n_bits, id)) key = kk;
-        }
-        unsigned m = __ballot_sync(FULL, key != KEY_EMPTY);
-        if (m) {
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const uint64_t kk = shfl64(key, src);
-                const int b = (src >> SH) % MQ;
-                if (kk < sel.thr_of(b)) sel.append(b, kk, lane);
+            butterfly_level<NV, 16>(v, lane);
+            butterfly_level<(NV / 2 > 0 ? NV / 2 : 1), 8>(v, lane);
+            butterfly_level<(NV / 4 > 0 ? NV / 4 : 1), 4>(v, lane);
+            butterfly_level<(NV / 8 > 0 ? NV / 8 : 1), 2>(v, lane);
+            butterfly_level<(NV / 16 > 0 ? NV / 16 : 1), 1>(v, lane);
+            const float dist = my_qzero[g] ? 0.f : fmaf(-0.5f, v[0], 0.5f);
+            const uint64_t row = base + my_r;
+            uint64_t key = KEY_EMPTY;
+            if (my_active[g] && row < n && okey(dist) <= (uint32_t)(thr[g] >> 32)) {
+                const uint32_t id = a.ids[row];
+                const uint64_t kk = make_key(dist, id);
+                if (kk < thr[g] && id_allowed(a.bitmap, a.n_bits, id)) key = kk;
             }
-            if (my_active) thr = sel.thr_of(my_b);
+            unsigned m = __ballot_sync(FULL, key != KEY_EMPTY);
+            if (m) {
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint64_t kk = shfl64(key, src);
+                    const int b = (src >> SH) % MQ + g * MQ;
+                    if (kk < sel.thr_of(b)) sel.append(b, kk, lane);
+                }
+                if (my_active[g]) thr[g] = sel.thr_of(my_b + g * MQ);
+            }
         }
     };
     if (a.static_split) {
@@ -274,7 +288,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, (E <= 4) ? 2 : 1) scan_multi_top
     if (!is_last) return;
     __threadfence();
 
-    sel.init(wbase, wbase + (size_t)MQ * KPAD, np_all + warp * MQ, a.k, MQ, lane);
+    sel.init(wbase, wbase + (size_t)MQT * KPAD, np_all + warp * MQT, a.k, MQT, lane);
     const uint64_t total = (uint64_t)gridDim.x * a.k;
     for (int b = 0; b < (int)a.nq; ++b) {
         const volatile uint64_t *cand = a.cand + (size_t)b * total;
@@ -327,26 +341,28 @@ __global__ void __launch_bounds__(SCAN_THREADS, (E <= 4) ? 2 : 1) scan_multi_top
 // insertion, no per-warp merges: 8 queries x k = 100 cost 4.0 ms per pass with the per-warp lists, of which 1.3 ms
 // was selection); every 8 iterations the CTA checks whether a buffer is within `slack` of full and, if so, sorts it,
 // keeps the best k and tightens the threshold. a.kpad = capacity of one buffer (ctabuf_cap(k)).
-// smem: queries [MQ][dim4] float4 | buffers [MQ][cap] keys.
-template <int V, int R, int MQ>
+// smem: queries [MQT][dim4] float4 | buffers [MQT][cap] keys.
+template <int V, int R, int MQ, int NG>
 __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_multi_cta_topk_kernel(const MultiArgs a)
 {
     constexpr bool EXACT = true;
+    constexpr int MQT = MQ * NG;   // queries per pass (NG groups of MQ share the rows a warp has loaded, see above)
     constexpr int NV = R * MQ;
     constexpr int SH = (NV == 32) ? 0 : (NV == 16 ? 1 : 2);
     static_assert(NV == 32 || NV == 16 || NV == 8, "R*MQ must be 8, 16 or 32");
-    constexpr uint32_t SLACK = 8 * R * SCAN_WARPS;   // most keys one query can receive between two sync points
+    constexpr uint32_t SYNC_IT = NG == 1 ? 8 : 4;            // iterations between two sync points (NG = 2: smaller buffers)
+    constexpr uint32_t SLACK = SYNC_IT * R * SCAN_WARPS;     // most keys one query can receive between two sync points
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ bool is_last;
-    __shared__ unsigned cnt_s[MQ];
-    __shared__ uint64_t thr_s[MQ];
-    __shared__ float qflag[MQ];
+    __shared__ unsigned cnt_s[MQT];
+    __shared__ uint64_t thr_s[MQT];
+    __shared__ float qflag[MQT];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t dim4 = a.dim4, cap = a.kpad, k = a.k;
     float4 *qs = reinterpret_cast<float4 *>(smem_raw);
-    uint64_t *bufs = reinterpret_cast<uint64_t *>(smem_raw + (size_t)MQ * dim4 * sizeof(float4));
+    uint64_t *bufs = reinterpret_cast<uint64_t *>(smem_raw + (size_t)MQT * dim4 * sizeof(float4));
 
-    for (int b = warp; b < MQ; b += SCAN_WARPS) {   // queries -> smem, unit-normalised exactly as scan.cuh does it
+    for (int b = warp; b < MQT; b += SCAN_WARPS) {   // queries -> smem, unit-normalised exactly as scan.cuh does it
         float4 t[V];
         float ss = 0.f;
 #pragma unroll
@@ -367,28 +383,34 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_multi_cta_topk_kernel(co
         }
         if (lane == 0) qflag[b] = qzero ? 1.f : 0.f;
     }
-    if (threadIdx.x < MQ) { cnt_s[threadIdx.x] = 0; thr_s[threadIdx.x] = KEY_EMPTY; }
+    if (threadIdx.x < MQT) { cnt_s[threadIdx.x] = 0; thr_s[threadIdx.x] = KEY_EMPTY; }
     __syncthreads();
 
     const int own = lane >> SH;
     const bool owner = (lane & ((1 << SH) - 1)) == 0;
     const int my_b = own % MQ, my_r = own / MQ;
-    const bool my_active = owner && (uint32_t)my_b < a.nq;
-    const bool my_qzero = qflag[my_b] != 0.f;
-    uint64_t thr = my_active ? KEY_EMPTY : 0ull;
-    uint64_t *my_buf = bufs + (size_t)my_b * cap;
+    bool my_active[NG], my_qzero[NG];
+    uint64_t thr[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        my_active[g] = owner && (uint32_t)(my_b + g * MQ) < a.nq;
+        my_qzero[g] = qflag[my_b + g * MQ] != 0.f;
+        thr[g] = my_active[g] ? KEY_EMPTY : 0ull;
+    }
 
     // CTA-uniform: compact every buffer that could overflow before the next sync point, refresh the thresholds
     auto sync_point = [&]() {
         bool maybe = false;
 #pragma unroll
-        for (int b = 0; b < MQ; ++b) maybe |= *reinterpret_cast<volatile unsigned *>(&cnt_s[b]) + SLACK > cap;
+        for (int b = 0; b < MQT; ++b) maybe |= *reinterpret_cast<volatile unsigned *>(&cnt_s[b]) + SLACK > cap;
         if (__syncthreads_or(maybe)) {   // nobody appends while the CTA is in here, so the counts are stable
-            for (int b = 0; b < MQ; ++b)
+            for (int b = 0; b < MQT; ++b)
                 if (*reinterpret_cast<volatile unsigned *>(&cnt_s[b]) + SLACK > cap)
                     cta_buf_compact(bufs + (size_t)b * cap, &cnt_s[b], &thr_s[b], cap, k);
         }
-        if (my_active) thr = *reinterpret_cast<volatile uint64_t *>(&thr_s[my_b]);
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+            if (my_active[g]) thr[g] = *reinterpret_cast<volatile uint64_t *>(&thr_s[my_b + g * MQ]);
     };
 
     const uint64_t n = a.n_rows;
@@ -408,50 +430,55 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_multi_cta_topk_kernel(co
                 else x[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-        float v[32];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) v[i] = 0.f;
+        for (int g = 0; g < NG; ++g) {
+            if (g > 0 && (uint32_t)(g * MQ) >= a.nq) break;   // CTA-uniform: no query in this group
+            float v[32];
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
+            for (int i = 0; i < NV; ++i) v[i] = 0.f;
 #pragma unroll
-            for (int b = 0; b < MQ; ++b) {
-                float4 qq = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (EXACT || lane + 32 * j < dim4) qq = qs[(size_t)b * dim4 + lane + 32 * j];
+            for (int j = 0; j < V; ++j) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    float acc = v[r * MQ + b];
-                    acc = fmaf(x[r][j].x, qq.x, acc); acc = fmaf(x[r][j].y, qq.y, acc);
-                    acc = fmaf(x[r][j].z, qq.z, acc); acc = fmaf(x[r][j].w, qq.w, acc);
-                    v[r * MQ + b] = acc;
+                for (int b = 0; b < MQ; ++b) {
+                    float4 qq = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (EXACT || lane + 32 * j < dim4) qq = qs[(size_t)(g * MQ + b) * dim4 + lane + 32 * j];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        float acc = v[r * MQ + b];
+                        acc = fmaf(x[r][j].x, qq.x, acc); acc = fmaf(x[r][j].y, qq.y, acc);
+                        acc = fmaf(x[r][j].z, qq.z, acc); acc = fmaf(x[r][j].w, qq.w, acc);
+                        v[r * MQ + b] = acc;
+                    }
                 }
             }
-        }
-        butterfly_level<NV, 16>(v, lane);
-        butterfly_level<(NV / 2 > 0 ? NV / 2 : 1), 8>(v, lane);
-        butterfly_level<(NV / 4 > 0 ? NV / 4 : 1), 4>(v, lane);
-        butterfly_level<(NV / 8 > 0 ? NV / 8 : 1), 2>(v, lane);
-        butterfly_level<(NV / 16 > 0 ? NV / 16 : 1), 1>(v, lane);
-        const float dist = my_qzero ? 0.f : fmaf(-0.5f, v[0], 0.5f);
-        const uint64_t row = base + my_r;
-        if (my_active && row < n && okey(dist) <= (uint32_t)(thr >> 32)) {
-            const uint32_t id = a.ids[row];
-            const uint64_t kk = make_key(dist, id);
-            if (kk < thr && id_allowed(a.bitmap, a.n_bits, id)) my_buf[atomicAdd(&cnt_s[my_b], 1u)] = kk;
+            butterfly_level<NV, 16>(v, lane);
+            butterfly_level<(NV / 2 > 0 ? NV / 2 : 1), 8>(v, lane);
+            butterfly_level<(NV / 4 > 0 ? NV / 4 : 1), 4>(v, lane);
+            butterfly_level<(NV / 8 > 0 ? NV / 8 : 1), 2>(v, lane);
+            butterfly_level<(NV / 16 > 0 ? NV / 16 : 1), 1>(v, lane);
+            const float dist = my_qzero[g] ? 0.f : fmaf(-0.5f, v[0], 0.5f);
+            const uint64_t row = base + my_r;
+            if (my_active[g] && row < n && okey(dist) <= (uint32_t)(thr[g] >> 32)) {
+                const uint32_t id = a.ids[row];
+                const uint64_t kk = make_key(dist, id);
+                if (kk < thr[g] && id_allowed(a.bitmap, a.n_bits, id))
+                    bufs[(size_t)(my_b + g * MQ) * cap + atomicAdd(&cnt_s[my_b + g * MQ], 1u)] = kk;
+            }
         }
     };
     if (a.static_split) {
         for (uint64_t it = 0; it < n_iters; ++it) {
             scan_group((gw + it * n_warps) * R);
-            if ((it & 7) == 7) sync_point();
+            if ((it % SYNC_IT) == SYNC_IT - 1) sync_point();
         }
     } else {
-        // dynamic row split: the CTA synchronises at its sync points anyway, so the whole CTA grabs up to SCAN_CHUNK (= 8,
-        // the sync interval SLACK is sized for) "CTA iterations" (one group of R rows per warp) at a time from a global
-        // counter; thread 0 issues the next grab before the chunk is processed (see scan.cuh, DYN && BIG)
+        // dynamic row split: the CTA synchronises at its sync points anyway, so the whole CTA grabs up to SYNC_IT (the
+        // interval SLACK is sized for) "CTA iterations" (one group of R rows per warp) at a time from a global counter;
+        // thread 0 issues the next grab before the chunk is processed (see scan.cuh, DYN && BIG)
         __shared__ uint32_t s_start;
         const uint32_t n_cit = (uint32_t)((n_groups + SCAN_WARPS - 1) / SCAN_WARPS), g2 = 2u * gridDim.x;
         unsigned *work = a.ticket + 1;
-        uint32_t c_next = max(1u, min((uint32_t)SCAN_CHUNK, n_cit / g2)), nxt = 0;
+        uint32_t c_next = max(1u, min(SYNC_IT, n_cit / g2)), nxt = 0;
         if (threadIdx.x == 0) nxt = atomicAdd(work, c_next);
         for (;;) {
             if (threadIdx.x == 0) s_start = nxt;
@@ -459,7 +486,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_multi_cta_topk_kernel(co
             const uint32_t c_start = s_start;
             if (c_start >= n_cit) break;
             const uint32_t c_end = min(c_start + c_next, n_cit);
-            c_next = max(1u, min((uint32_t)SCAN_CHUNK, (n_cit - c_start) / g2));
+            c_next = max(1u, min(SYNC_IT, (n_cit - c_start) / g2));
             if (threadIdx.x == 0) nxt = atomicAdd(work, c_next);
             for (uint32_t it = c_start; it < c_end; ++it) scan_group(((uint64_t)it * SCAN_WARPS + warp) * R);
             sync_point();   // barrier inside: s_start is free to be rewritten

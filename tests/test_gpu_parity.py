@@ -369,8 +369,8 @@ def test_batch_parity(cs, oracle, n, d, b, k):
     launches0 = _lib.load().csgpu_kernel_launches()
     oi, od, on = st.search_batch_ids(qs, k)
     launches = _lib.load().csgpu_kernel_launches() - launches0
-    if d % 128 == 0 and k <= 256:                                # one pass per <= 8 queries
-        assert launches == (b // 8) + (1 if b % 8 else 0)
+    if d % 128 == 0 and k <= 256:                                # one pass per <= 16 queries (8-query kernel up to 8, 16-query kernel above)
+        assert launches == (b // 16) + (1 if b % 16 else 0)
     k_eff = min(k, n)
     for j in range(b):
         ri, rd, r64 = oracle.np_search(rows, qs[j], k + MARGIN, ids=ids)
@@ -378,6 +378,39 @@ def test_batch_parity(cs, oracle, n, d, b, k):
         check_topk(oi[j, :k_eff], od[j, :k_eff], ri, rd, r64, k_eff)
         gi, gd = st.search_ids(qs[j], k)
         assert np.array_equal(oi[j, :k_eff], gi) and np.array_equal(od[j, :k_eff], gd)
+
+
+@pytest.mark.parametrize("d", [128, 384, 768])
+def test_sixteen_query_pass_bit_identical_to_single(cs, d):
+    """Round 2: 9..16 queries share ONE pass (scan_multi.cuh, MQ = 16 x R = 2) — the reference's default hybrid search is
+    <= 9 query variants x limit 200 (src/search/mod.rs:498-511). Same FMA chain and shuffle tree per (row, query), so every
+    list is bit-identical to csgpu_search, for the per-warp lists (k <= 32) and the CTA buffers (k > 32) alike."""
+    from codesearch_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(900 + d)
+    n = 60_000
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    rows[[3, 40_000]] = 0.0
+    st = make_store(cs, rows)
+    qs = rng.standard_normal((16, d)).astype(np.float32)
+    qs[5] = 0.0
+    for b, k in ((9, 200), (16, 10), (12, 32), (10, 33), (16, 256), (13, 100), (16, 1)):
+        l0 = lib.csgpu_kernel_launches()
+        oi, od, on = st.search_batch_ids(qs[:b], k)
+        assert lib.csgpu_kernel_launches() - l0 == 1, (b, k)
+        for j in range(b):
+            gi, gd = st.search_ids(qs[j], k)
+            assert on[j] == len(gi) and np.array_equal(oi[j, : on[j]], gi) and np.array_equal(od[j, : on[j]].view(np.uint32), gd.view(np.uint32)), (b, k, j)
+    # the variants entry point: 9 variants x top-200 = one pass + the dedup kernel
+    l0 = lib.csgpu_kernel_launches()
+    vi, vd = st.search_variants_ids(qs[6:15], 200)
+    assert lib.csgpu_kernel_launches() - l0 == 2
+    best = {}
+    for q in qs[6:15]:
+        for i, x in zip(*st.search_ids(q, 200)):
+            best[int(i)] = min(best.get(int(i), 9.0), float(x))
+    want = sorted(best.items(), key=lambda t: (t[1], t[0]))[:200]
+    assert [int(i) for i in vi] == [w[0] for w in want]
 
 
 # ---- device entry points + cross-shard merge ---------------------------------------------------
