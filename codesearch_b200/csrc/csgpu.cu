@@ -749,7 +749,9 @@ static int search_one_fused(const csgpu_index *ix, const float *q, uint32_t k, c
     auto body = [&]() -> int {
         memset(c0->q_pin, 0, qbytes);
         memcpy(c0->q_pin, q, (size_t)ix->dim * sizeof(float));   // one pinned copy feeds every device's H2D
-        for (size_t g = 0; g < G; ++g) {
+        for (size_t gi = 0; gi < G; ++gi) {
+            const size_t g = G - 1 - gi;   // the root (shard 0) last: should anything serialise the launches (a debugger, the
+                                           // sanitizer, time slicing), the kernel that waits finds the others' keys already there
             if ((long)g == skip) continue;
             Shard *sh = ix->shards[g];
             SearchCtx *c = grp->ctx[g];

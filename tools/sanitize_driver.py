@@ -29,7 +29,11 @@ qs = rng.standard_normal((70, d)).astype(np.float32)
 st.search_batch_ids(qs[:8], 10)                             # multi-query scan, per-warp lists
 st.search_batch_ids(qs[:8], 100)                            # multi-query scan, CTA buffers
 st.search_variants_ids(qs[:5], 20)                          # device-side dedup of variants
-st.search_batch_ids(qs, 20)                                 # fp32 SIMT GEMM + select
+st.search_batch_ids(qs[:12], 10)                            # 9..16 queries in one pass (two query groups), per-warp lists
+st.search_batch_ids(qs[:16], 200)                           # ... and CTA buffers
+st.search_variants_ids(qs[:9], 200)                         # the reference's hybrid shape: 9 variants x limit 200
+st.search_batch_ids(qs[:40], 20)                            # fp32 SIMT GEMM, 64-query tile (setmaxnreg warp specialisation)
+st.search_batch_ids(qs, 20)                                 # fp32 SIMT GEMM, 128-query tile + select
 st.set_tensor_prefilter(True)
 a = st.search_batch_ids(qs, 20)                             # tcgen05 filter + rescoring select
 for j in (0, 69):
@@ -52,6 +56,18 @@ bf = cs.VectorStore.new(None, d, dtype="bf16")
 bf.append_rows(rows, ids)
 bf.build_index()
 bf.search_batch_ids(qs, 20)                                 # bf16 index on tcgen05
+zq = qs[:3].copy(); zq[1] = 0.0
+zi, zd, zn = bf.search_batch_ids(zq, 7)                     # zero-norm query on the bf16 index: zero_query_ids_kernel
+assert np.array_equal(zi[1], np.arange(7, dtype=np.uint32)) and not zd[1].any()
+# in-process multi-device index, both shards on this device: N scan launches with the gather exchange fused into their tails
+two = cs.VectorStore.new(None, d, devices=[0, 0])
+two.append_rows(rows, ids, tags)
+two.build_index()
+for k in (10, 100):
+    a2 = two.search_ids(q, k)
+    assert len(a2[0]) == k and len(set(a2[0].tolist())) == k
+two.search_ids(q, 50, cs.RowFilter.from_mask(rng.random(n) < 0.3))
+two.search_tagged_ids(q, 50, TagPredicate(lang_mask=0x3F, file_lo=3, file_hi=120))
 # fused cross-GPU exchange, three "ranks" on one device (three streams), with and without the tag predicate
 import ctypes
 import torch
