@@ -461,7 +461,8 @@ def main():
                "qps": round(1e3 / e2e_ms, 3), "ms_per_step": round(e2e_ms, 4),
                "h2d_bytes_per_step": d * 4, "d2h_bytes_per_step": k * 8,
                "api": "VectorStore.search_ids -> csgpu_search (host pointers)" if world == 1 else
-                      ("ShardedSearcher.search (pinned H2D, csgpu_search_keys_exchange_device: fused scan + peer-memory exchange + merge, D2H)"
+                      ("ShardedSearcher.search -> csgpu_search_exchange (host pointers: pinned H2D, ONE fused launch = scan + peer-memory exchange + "
+                       "merge, its last CTA writes the keys into mapped host memory)"
                        if args.exchange == "fused" else
                        "ShardedSearcher.search (pinned H2D, csgpu_search_keys_device, NCCL all-gather, csgpu_merge_keys_device, D2H)")}
 

@@ -101,6 +101,7 @@ SIGNATURES = {
     "csgpu_exchange_connect": (ctypes.c_int, [_vp, _vp]),
     "csgpu_exchange_connect_local": (ctypes.c_int, [_vp, ctypes.POINTER(_vp)]),
     "csgpu_search_keys_exchange_device": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, _vp, _vp]),
+    "csgpu_search_exchange": (ctypes.c_int, [_vp, _f32p, ctypes.c_uint32, ctypes.c_uint32, _u32p, _f32p, _u32p]),
     "csgpu_exchange_status": (ctypes.c_int, [_vp, _u32p]),
     "csgpu_exchange_set_timeout_ms": (ctypes.c_int, [_vp, ctypes.c_uint32]),
     "csgpu_exchange_wait_stats": (ctypes.c_int, [_vp, _u64p, ctypes.c_uint32, _u32p]),

@@ -1811,6 +1811,48 @@ int csgpu_search_keys_exchange_device(const csgpu_index *ix, const float *q_dev,
     return rc;
 }
 
+// Host-pointer form of the exchange search for rank-per-GPU processes: pinned staging of the query, ONE fused launch
+// (scan + peer stores + flag wait + global merge) whose last CTA writes the global top-k into mapped host memory, one
+// stream synchronised. A collective: every rank calls it for every query, in the same order, one call at a time per rank.
+int csgpu_search_exchange(const csgpu_index *ix, const float *q, uint32_t q_len, uint32_t k,
+                          uint32_t *out_ids, float *out_dist, uint32_t *out_n)
+{
+    if (out_n) *out_n = 0;
+    int rc = check_search_args(ix, q, q_len, k);
+    if (rc) return rc;
+    if (ix->shards.size() != 1) return fail(CSGPU_ERR_ARG, "csgpu_search_exchange needs a single-device index (one rank per GPU)");
+    if (ix->dtype != CSGPU_DTYPE_F32) return fail(CSGPU_ERR_ARG, "the exchange needs an fp32 index");
+    if (!ix->xchg || !ix->xchg->connected) return fail(CSGPU_ERR_ARG, "exchange is not connected (csgpu_exchange_create/connect)");
+    if (!all_finite(q, q_len)) return fail(CSGPU_ERR_ARG, "query contains NaN/Inf");
+    if (k == 0) return CSGPU_OK;
+    if ((rc = exchange_healthy(ix))) return rc;
+    Shard *sh = ix->shards[0];
+    SearchCtx *c = nullptr;
+    if ((rc = ctx_acquire(ix, sh, &c))) return rc;
+    auto body = [&]() -> int {
+        DeviceGuard dg(sh->device);
+        const size_t qbytes = (size_t)ix->dim_pad * sizeof(float);
+        memset(c->q_pin, 0, qbytes);
+        memcpy(c->q_pin, q, (size_t)ix->dim * sizeof(float));
+        CS_CUDA(cudaMemcpyAsync(c->q_dev, c->q_pin, qbytes, cudaMemcpyHostToDevice, c->stream));
+        CS_CUDA(cudaEventRecord(c->ev0, c->stream));
+        const uint32_t seq = ix->xchg->seq.fetch_add(1) + 1;
+        int r = enqueue_keys_device(ix, sh, c, c->q_dev, k, c->out_pin, c->stream, ix->xchg->dev, seq);
+        if (r) return r;
+        CS_CUDA(cudaEventRecord(c->ev1, c->stream));
+        CS_CUDA(cudaStreamSynchronize(c->stream));
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) ix->last_search_us.store(ms * 1000.f);
+        if ((r = exchange_healthy(ix))) return r;
+        decode_keys(c->out_pin, k, out_ids, out_dist, out_n);
+        return CSGPU_OK;
+    };
+    rc = body();
+    if (rc) { DeviceGuard dg(sh->device); cudaStreamSynchronize(c->stream); }
+    ctx_release(sh, c);
+    return rc;
+}
+
 int csgpu_search_tagged_keys_device(const csgpu_index *ix, const float *q_dev, uint32_t k, const csgpu_predicate_t *pred,
                                     uint32_t exchange, uint64_t *out_keys_dev, void *stream)
 {

@@ -112,6 +112,13 @@ class ShardedSearcher:
         if q.size != self.store.dimensions:
             raise _lib.CsgpuError(_lib.ERR_DIM, f"Query embedding dimension mismatch: expected "
                                                 f"{self.store.dimensions}, got {q.size}")
+        if pred is None and self.exchange == "fused":
+            # the C ABI's host-pointer form: staging, the one fused launch and the read-back of the k keys (written by the
+            # kernel straight into mapped host memory) happen inside the library
+            oi = np.empty(max(k, 1), np.uint32); od = np.empty(max(k, 1), np.float32); on = ctypes.c_uint32(0)
+            _lib.check(self.lib.csgpu_search_exchange(self.store.handle, q.ctypes.data_as(_lib._f32p), q.size, k,
+                                                      oi.ctypes.data_as(_lib._u32p), od.ctypes.data_as(_lib._f32p), ctypes.byref(on)))
+            return oi[: on.value], od[: on.value]
         self.q_pin[: q.size].copy_(torch.from_numpy(q))
         self.q_dev.copy_(self.q_pin, non_blocking=True)
         keys = self.search_keys_device(self.q_dev, k, pred)

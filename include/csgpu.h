@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define CSGPU_ABI_VERSION 5
+#define CSGPU_ABI_VERSION 6
 
 enum {
     CSGPU_OK            = 0,
@@ -259,6 +259,11 @@ int  csgpu_exchange_connect(csgpu_index *ix, const void *handles /*[world][64]; 
 int  csgpu_exchange_connect_local(csgpu_index *ix, csgpu_index *const *peers /*[world]*/);
 int  csgpu_search_keys_exchange_device(const csgpu_index *ix, const float *q_dev, uint32_t k,
                                        uint64_t *out_keys_dev /*[k] global top-k*/, void *stream);
+/* The same search with HOST pointers (what csgpu_search is to a single index): pinned staging of the query, the one
+ * fused launch, the global top-k written by its last CTA straight into mapped host memory, one stream synchronised.
+ * Collective like the device form: every rank calls it for every query in the same order, one call at a time per rank. */
+int  csgpu_search_exchange(const csgpu_index *ix, const float *q, uint32_t q_len, uint32_t k,
+                           uint32_t *out_ids /*[k]*/, float *out_dist /*[k]*/, uint32_t *out_n);
 int  csgpu_exchange_status(const csgpu_index *ix, uint32_t *timed_out);
 /* Bound of the in-kernel wait for the peers' keys, for the rank-per-GPU exchange and for the in-process multi-device
  * index alike. Call it while no search is in flight. */

@@ -18,7 +18,7 @@ use std::ffi::{CStr, CString};
 use std::os::raw::{c_char, c_int, c_void};
 use std::path::Path;
 
-pub const CSGPU_ABI_VERSION: u32 = 5;
+pub const CSGPU_ABI_VERSION: u32 = 6;
 pub const CSGPU_OK: c_int = 0;
 pub const CSGPU_ERR_DIM: c_int = 1; // "Query embedding dimension mismatch: expected {}, got {}"   store.rs:432-438
 pub const CSGPU_ERR_NOT_BUILT: c_int = 2; // "Index not built. Call build_index() after inserting chunks."   store.rs:440-444
@@ -109,6 +109,7 @@ extern "C" {
     pub fn csgpu_exchange_connect(ix: *mut CsgpuIndex, handles: *const c_void) -> c_int;
     pub fn csgpu_exchange_connect_local(ix: *mut CsgpuIndex, peers: *const *mut CsgpuIndex) -> c_int;
     pub fn csgpu_search_keys_exchange_device(ix: *const CsgpuIndex, q_dev: *const f32, k: u32, out_keys_dev: *mut u64, stream: *mut c_void) -> c_int;
+    pub fn csgpu_search_exchange(ix: *const CsgpuIndex, q: *const f32, q_len: u32, k: u32, out_ids: *mut u32, out_dist: *mut f32, out_n: *mut u32) -> c_int;
     pub fn csgpu_exchange_status(ix: *const CsgpuIndex, timed_out: *mut u32) -> c_int;
     pub fn csgpu_exchange_set_timeout_ms(ix: *mut CsgpuIndex, ms: u32) -> c_int;
     pub fn csgpu_exchange_wait_stats(ix: *const CsgpuIndex, out_ns: *mut u64, max_queries: u32, n_queries: *mut u32) -> c_int;
@@ -418,6 +419,17 @@ impl GpuIndex {
 
     pub fn exchange_destroy(&mut self) {
         unsafe { csgpu_exchange_destroy(self.raw) }
+    }
+
+    /// Host-pointer exchange search (rank-per-GPU processes): the GLOBAL top-k over all ranks, one fused launch per rank.
+    /// A collective: every rank calls it for every query, in the same order.
+    pub fn search_exchange(&self, q: &[f32], limit: usize) -> Result<Vec<(u32, f32)>> {
+        let cap = limit.max(1);
+        let (mut ids, mut dist, mut n) = (vec![0u32; cap], vec![0f32; cap], 0u32);
+        check(unsafe {
+            csgpu_search_exchange(self.raw, q.as_ptr(), q.len() as u32, limit as u32, ids.as_mut_ptr(), dist.as_mut_ptr(), &mut n)
+        })?;
+        Ok(Self::collect(ids, dist, n))
     }
 
     /// # Safety
