@@ -366,7 +366,11 @@ def main():
     store = cs.VectorStore.new(None, d, devices=[local_rank])
     store.reserve(n)
     store.append_synthetic(SEED_CORPUS, rank * n, n, 0)   # chunk id = global row index
-    store.build_index()
+    torch.cuda.synchronize()
+    t_build = time.perf_counter()
+    store.build_index()                                   # normalise to unit length (f64 norms), drop dead / zero / non-finite rows
+    torch.cuda.synchronize()
+    build_ms = (time.perf_counter() - t_build) * 1e3      # what replaces the reference's arroy tree build (store.rs:386-430)
     if args.byte_prefilter:
         store.set_byte_prefilter(True)
     searcher = ShardedSearcher(store, k_max=max(k, 16), exchange=args.exchange)
@@ -506,6 +510,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "parity": parity,
+            "build_index_ms": round(build_ms, 2),   # csgpu_build of this rank's rows (the reference: arroy tree build, 10-30 s on
+                                                    # large sets by its own comment, src/index/mod.rs:773); not part of any timing above
         }
         if skew is not None:
             line["skew"] = skew

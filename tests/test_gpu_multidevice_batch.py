@@ -74,3 +74,56 @@ def test_multidevice_search_variants_equals_single_device(cs, oracle, b, k):
     lists = [one.search_ids(q, k) for q in qs]
     wi, wd = oracle.dedup_variants(lists, k)
     assert np.array_equal(ci, wi) and np.array_equal(cd, wd)
+
+
+def test_multidevice_fused_single_query_on_two_real_gpus(cs, oracle):
+    """Round 2: csgpu_search / _filtered / _tagged on a 2-device index are two scan launches with the gather exchange fused
+    into their tails (peer stores from device 1 into device 0's HBM over NVLink, device 0 merges and writes mapped host
+    memory). Bit-identical to the single-device index; exactly one launch per device; concurrent host threads."""
+    import threading
+    from codesearch_b200 import _lib
+    from codesearch_b200 import tags as T
+    lib = _lib.load()
+    rng = np.random.default_rng(2024)
+    n, d = 120_000, 384
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    rows[[9, 100_000]] = 0.0
+    tg = T.synth_tags(0, n)
+    pair = []
+    for devs in ([0], [0, 1]):
+        st = cs.VectorStore.new(None, d, devices=devs)
+        st.append_rows(rows, np.arange(n, dtype=np.uint32), tg)
+        st.build_index()
+        pair.append(st)
+    one, two = pair
+    qs = rng.standard_normal((8, d)).astype(np.float32)
+    two.search_ids(qs[0], 10)
+    for k in (1, 10, 100, 1000):
+        l0 = lib.csgpu_kernel_launches()
+        g = two.search_ids(qs[1], k)
+        assert lib.csgpu_kernel_launches() - l0 == 2
+        h = one.search_ids(qs[1], k)
+        assert np.array_equal(g[0], h[0]) and np.array_equal(g[1].view(np.uint32), h[1].view(np.uint32)), k
+    ri, rd, r64 = oracle.np_search(rows, qs[1], 100 + MARGIN)
+    g = two.search_ids(qs[1], 100)
+    check_topk(g[0], g[1], ri, rd, r64, 100)
+    flt = cs.RowFilter.from_mask(np.arange(n) % 4 != 0)
+    a, b = two.search_ids(qs[2], 50, flt), one.search_ids(qs[2], 50, flt)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    pred = T.TagPredicate(lang_mask=0x00FF, file_lo=5, file_hi=2500)
+    a, b = two.search_tagged_ids(qs[3], 200, pred), one.search_tagged_ids(qs[3], 200, pred)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    want = [one.search_ids(q, 20) for q in qs]
+    bad = []
+
+    def worker(t):
+        for rep in range(20):
+            j = (t + rep) % 8
+            g = two.search_ids(qs[j], 20)
+            if not (np.array_equal(g[0], want[j][0]) and np.array_equal(g[1], want[j][1])):
+                bad.append((t, rep))
+
+    ths = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    assert not bad

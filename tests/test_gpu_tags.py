@@ -209,3 +209,38 @@ def test_tagged_device_entry_with_fused_exchange(cs, oracle):
         check_topk(first[0], first[1], oi, od, o64, min(k, int(ok.sum())))
     for st in stores:
         lib.csgpu_exchange_destroy(st.handle)
+
+
+def test_filtered_scan_work_counter_split_matches_fixed_stride(cs):
+    """The work-counter row split of the filtered scan (BlockCursor, scan.cuh) is off by default — measured not faster,
+    profiles/r02_static_vs_dynamic_filtered_multi.txt — but it ships behind CSGPU_SCAN_DYNAMIC_ALL=1, so it is tested: a
+    child process with the switch on must return, bit for bit, what this process (fixed stride) returns, for the id bitmap
+    and the tag predicate, with the per-warp selector (k <= 32) and the CTA-shared one (k > 32), and for the 8-query pass."""
+    import json, os, subprocess, sys
+    code = r'''
+import json, sys, numpy as np
+sys.path.insert(0, %r)
+import codesearch_b200 as cs
+from codesearch_b200.tags import TagPredicate
+st = cs.VectorStore.new(None, 128)
+st.append_synthetic(77, 0, 90_000, 0, tagged=True)
+st.build_index()
+rng = np.random.default_rng(5)
+qs = rng.standard_normal((8, 128)).astype(np.float32)
+flt = cs.RowFilter.from_mask(np.arange(90_000) %% 3 != 1)
+pred = TagPredicate(lang_mask=0x0FFF, file_lo=100, file_hi=2000)
+out = []
+for k in (10, 100):
+    for r in (st.search_ids(qs[0], k, flt), st.search_tagged_ids(qs[1], k, pred)):
+        out.append([r[0].tolist(), r[1].view(np.uint32).tolist()])
+    b = st.search_batch_ids(qs, k)
+    out.append([b[0].tolist(), b[1].view(np.uint32).tolist()])
+print("RESULT" + json.dumps(out))
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = []
+    for dyn in ("0", "1"):
+        env = dict(os.environ, CSGPU_SCAN_DYNAMIC_ALL=dyn)
+        p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stderr[-2000:]
+        res.append(json.loads(p.stdout.split("RESULT", 1)[1]))
+    assert res[0] == res[1]
