@@ -742,10 +742,11 @@ static int search_one_fused(const csgpu_index *ix, const float *q, uint32_t k, c
     const size_t bm_words = bitmap ? (size_t)((n_bits + 63) / 64) : 0;
     const uint32_t seq = ++grp->seq;
     SearchCtx *c0 = grp->ctx[0];
-    // test hook (tests/test_gpu_multishard_one_gpu.py): CSGPU_FAULT_SKIP_SHARD=<g> drops shard g's launch, which is what a
-    // lost device looks like to the root's wait
+    // test hook (tests/test_gpu_multishard_one_gpu.py): CSGPU_FAULT_SKIP_SHARD=<g>, g >= 1, drops shard g's launch, which is
+    // what a lost device looks like to the root's wait
     const char *fault = getenv("CSGPU_FAULT_SKIP_SHARD");
-    const long skip = fault && *fault ? strtol(fault, nullptr, 10) : -1;
+    long skip = fault && *fault ? strtol(fault, nullptr, 10) : -1;
+    if (skip == 0) skip = -1;   // the root itself cannot be skipped: nobody would be left to notice
     auto body = [&]() -> int {
         memset(c0->q_pin, 0, qbytes);
         memcpy(c0->q_pin, q, (size_t)ix->dim * sizeof(float));   // one pinned copy feeds every device's H2D
@@ -784,10 +785,16 @@ static int search_one_fused(const csgpu_index *ix, const float *q, uint32_t k, c
         return CSGPU_OK;
     };
     rc = body();
-    if (rc) {   // drain what was launched (the root gives up after the exchange timeout) and retire the group
+    if (rc) {   // drain what was launched (the root gives up after the exchange timeout), then retire the group for good
         const std::string keep = t_error;
         for (size_t g = 0; g < G; ++g) { DeviceGuard dg(ix->shards[g]->device); cudaStreamSynchronize(grp->ctx[g]->stream); }
         cudaGetLastError();
+        {
+            std::lock_guard<std::mutex> lk(ix->group_mu);
+            auto it = std::find(ix->all_groups.begin(), ix->all_groups.end(), grp);
+            if (it != ix->all_groups.end()) ix->all_groups.erase(it);
+        }
+        group_destroy(grp);
         t_error = keep;
         return rc;
     }
