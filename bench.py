@@ -929,6 +929,7 @@ def extras_c5(cs, _lib, lib, torch, dist, rank, world, local_rank, gather_obj, s
     qd = torch.from_numpy(qs).cuda()
     n_files = (N + 36) // 37
     out = {"rows_total": N, "dim": d, "k": k, "n_gpus": world, "densities": {}}
+    preds, answers = [], []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for dens in (1.0, 0.25, 0.01):
         if dens >= 1.0:
@@ -947,6 +948,30 @@ def extras_c5(cs, _lib, lib, torch, dist, rank, world, local_rank, gather_obj, s
         sync_all()
         ms = max(gather_obj(ev0.elapsed_time(ev1) / reps))
         out["densities"][str(dens)] = {"device_ms": round(ms, 4), "dense_GBps": round(N * (d * 4 + 4) / ms / 1e6, 1)}
+        preds.append(pred)
+        answers.append(searcher.search_keys_device(qd[0], k, pred).cpu().numpy().copy())
+    # the same three searches with the opt-in byte prefilter (round 2: the int8 kernel's FILT instantiation streams only row
+    # groups the predicate allows; survivors are rescored in fp32 in the same launch) — every answer must stay bit-identical
+    st.set_byte_prefilter(True)
+    out["with_byte_prefilter"] = {"what": "csgpu_set_byte_prefilter on every rank: int8 shadow under the same predicate + exact fp32 rescoring"
+                                          + ("" if world == 1 else ", then the exchange as its own launch"), "densities": {}}
+    same = True
+    for dens, pred, want in zip((1.0, 0.25, 0.01), preds, answers):
+        for i in range(3):
+            searcher.search_keys_device(qd[i], k, pred)
+        sync_all()
+        ev0.record()
+        for i in range(reps):
+            searcher.search_keys_device(qd[i % 16], k, pred)
+        ev1.record()
+        sync_all()
+        ms = max(gather_obj(ev0.elapsed_time(ev1) / reps))
+        got = searcher.search_keys_device(qd[0], k, pred).cpu().numpy()
+        same = same and bool(np.array_equal(got, want))
+        out["with_byte_prefilter"]["densities"][str(dens)] = {"device_ms": round(ms, 4)}
+    sd = st.device_stats()
+    out["with_byte_prefilter"]["bit_identical_to_fp32_filtered_scan"] = all(gather_obj(same))
+    out["with_byte_prefilter"]["answered_by_fp32_scan_instead"] = int(sum(gather_obj(int(sd.byte_fallbacks))))
     st.close()
     return out
 

@@ -321,12 +321,13 @@ static int enqueue_exchange(SearchCtx *c, const uint64_t *local, uint32_t k, uin
 // on, the int8 kernel runs first; the fp32 scan is enqueued behind it as a launch that does nothing unless the int8
 // kernel raised its device-side status word (the host cannot look without synchronising), then the exchange.
 static int enqueue_keys_device(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const float *q_dev, uint32_t k,
-                               uint64_t *out_keys, cudaStream_t st, const ExchangeDev *xchg, uint32_t seq)
+                               uint64_t *out_keys, cudaStream_t st, const ExchangeDev *xchg, uint32_t seq,
+                               const uint64_t *bitmap_dev = nullptr, uint64_t n_bits = 0, const csgpu_predicate_t *pred = nullptr)
 {
-    if (!i8_eligible(ix, k)) return enqueue_scan(ix, sh, c, q_dev, k, nullptr, 0, true, out_keys, st, xchg, seq);
+    if (!i8_eligible(ix, k)) return enqueue_scan(ix, sh, c, q_dev, k, bitmap_dev, n_bits, true, out_keys, st, xchg, seq, pred);
     uint64_t *local = xchg ? c->out_dev : out_keys;
-    int rc = enqueue_scan_i8(ix, sh, c, q_dev, k, true, local, st, /*host_status=*/false);
-    if (!rc) rc = enqueue_scan(ix, sh, c, q_dev, k, nullptr, 0, true, local, st, nullptr, 0, nullptr, i8_status_dev(c));
+    int rc = enqueue_scan_i8(ix, sh, c, q_dev, k, true, local, st, /*host_status=*/false, bitmap_dev, n_bits, pred);
+    if (!rc) rc = enqueue_scan(ix, sh, c, q_dev, k, bitmap_dev, n_bits, true, local, st, nullptr, 0, pred, i8_status_dev(c));
     if (!rc && xchg) rc = enqueue_exchange(c, local, k, out_keys, st, xchg, seq);
     ix->byte_searches.fetch_add(1, std::memory_order_relaxed);
     return rc;
@@ -808,7 +809,9 @@ static int search_one(const csgpu_index *ix, const float *q, uint32_t k, const u
 {
     // byte prefilter on (csgpu_set_byte_prefilter): the unfiltered query streams the int8 shadow and rescoring makes it
     // exact (scan_i8.cuh); if that launch reports a case it cannot bound, the query is answered again by the fp32 scan
-    bool use_i8 = bitmap == nullptr && pred == nullptr && i8_eligible(ix, k);
+    // (round 2: filtered and tagged searches too — the int8 kernel's FILT instantiation streams only row groups the filter
+    //  allows, so they move a quarter of the fp32 filtered scan's bytes at every density)
+    bool use_i8 = i8_eligible(ix, k);
     if (pred) { bitmap = pred->file_bitmap; n_bits = pred->file_bitmap ? pred->n_file_bits : 0; }
     const size_t G = ix->shards.size();
     if (G > 1 && !use_i8 && fused_local_ok(ix)) return search_one_fused(ix, q, k, bitmap, n_bits, out_ids, out_dist, out_n, pred);
@@ -841,7 +844,7 @@ static int search_one(const csgpu_index *ix, const float *q, uint32_t k, const u
             }
             if (g == 0) CS_CUDA(cudaEventRecord(c->ev0, c->stream));
             uint64_t *dst = (G == 1) ? c->out_pin : c->out_dev;
-            int r = use_i8 ? enqueue_scan_i8(ix, sh, c, c->q_dev, k, /*with_zero_ids=*/g == 0, dst, c->stream)
+            int r = use_i8 ? enqueue_scan_i8(ix, sh, c, c->q_dev, k, /*with_zero_ids=*/g == 0, dst, c->stream, /*host_status=*/true, bm_dev, n_bits, pred)
                            : enqueue_scan(ix, sh, c, c->q_dev, k, bm_dev, n_bits, /*with_zero_ids=*/g == 0, dst, c->stream, nullptr, 0, pred);
             if (r) return r;
         }
@@ -1879,8 +1882,8 @@ int csgpu_search_tagged_keys_device(const csgpu_index *ix, const float *q_dev, u
     {
         DeviceGuard dg(sh->device);
         const uint32_t seq = exchange ? ix->xchg->seq.fetch_add(1) + 1 : 0;
-        rc = enqueue_scan(ix, sh, c, q_dev, k, pred->file_bitmap, pred->file_bitmap ? pred->n_file_bits : 0, true, out_keys_dev,
-                          (cudaStream_t)stream, exchange ? ix->xchg->dev : nullptr, seq, pred);
+        rc = enqueue_keys_device(ix, sh, c, q_dev, k, out_keys_dev, (cudaStream_t)stream, exchange ? ix->xchg->dev : nullptr, seq,
+                                 pred->file_bitmap, pred->file_bitmap ? pred->n_file_bits : 0, pred);
     }
     dev_ctx_end(sh, c, (cudaStream_t)stream);
     return rc;

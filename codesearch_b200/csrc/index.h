@@ -184,7 +184,9 @@ void i8_free_shard(Shard *sh);
 void i8_free_ctx(SearchCtx *c);
 bool i8_eligible(const csgpu_index *ix, uint32_t k);
 int enqueue_scan_i8(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const float *q_dev, uint32_t k,
-                    bool with_zero_ids, uint64_t *out_keys, cudaStream_t st, bool host_status = true);
+                    bool with_zero_ids, uint64_t *out_keys, cudaStream_t st, bool host_status = true,
+                    const uint64_t *bitmap_dev = nullptr, uint64_t n_bits = 0,
+                    const csgpu_predicate_t *pred = nullptr /* filters as in enqueue_scan: id bitmap, or tag predicate (+ file bitmap) */);
 void i8_preload(const csgpu_index *ix);
 int i8_prepare_ctx(SearchCtx *c);   // allocates the context's scratch (device of the current context = c->device)
 const unsigned *i8_status_dev(const SearchCtx *c);   // device word: != 0 after a launch that needs the fp32 scan instead

@@ -83,19 +83,23 @@ struct I8Scratch {   // one cudaMalloc block per SearchCtx
     uint64_t region[(size_t)I8_MAX_GRID * I8_REGION];
 };
 
-static int i8_rows_override()   // CSGPU_I8_R (diagnostic): 4-row groups in flight per warp iteration, 0 = the tuned default
-{
-    static const int v = [] { const char *e = getenv("CSGPU_I8_R"); return e && *e ? atoi(e) : 0; }();
-    return v;
-}
+// rows per 4-row group count of the FILT instantiation: 4 R must divide a 32-row block (R = 6 at dim 384 does not: R = 4)
+template <int R>
+constexpr int i8_filt_r() { return R == 6 ? 4 : R; }
 
 template <int V, bool EXACT, int R>
-static cudaError_t launch_i8_vr(const I8Args &a, uint32_t grid, cudaStream_t st)
+static cudaError_t launch_i8_vr(const I8Args &a, uint32_t grid, cudaStream_t st, bool filtered)
 {
-    auto kern = scan_i8_kernel<V, EXACT, R>;
-    if (grid == 0) { cudaFuncAttributes fa; return cudaFuncGetAttributes(&fa, kern); }   // preload only
+    auto kern = scan_i8_kernel<V, EXACT, R, false>;
+    auto kern_f = scan_i8_kernel<V, EXACT, i8_filt_r<R>(), true>;
+    if (grid == 0) {   // preload only
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+        return e == cudaSuccess ? cudaFuncGetAttributes(&fa, kern_f) : e;
+    }
     const size_t smem = (size_t)I8_TAIL_CAP * sizeof(uint64_t);
-    kern<<<grid, I8_THREADS, smem, st>>>(a);
+    if (filtered) kern_f<<<grid, I8_THREADS, smem, st>>>(a);
+    else kern<<<grid, I8_THREADS, smem, st>>>(a);
     count_launch();
     return cudaGetLastError();
 }
@@ -107,20 +111,13 @@ constexpr int i8_default_r() { return (V <= 2) ? 8 : (V == 3 ? 6 : (V == 4 ? 4 :
 
 static uint32_t i8_rows_per_iter(uint32_t V)
 {
-    const int o = i8_rows_override();
-    if (V == 3 && (o == 4 || o == 5)) return 4u * o;
     return 4u * ((V <= 2) ? 8 : (V == 3 ? 6 : (V == 4 ? 4 : 2)));
 }
 
 template <int V, bool EXACT>
-static cudaError_t launch_i8_v(const I8Args &a, uint32_t grid, cudaStream_t st)
+static cudaError_t launch_i8_v(const I8Args &a, uint32_t grid, cudaStream_t st, bool filtered)
 {
-    if constexpr (V == 3) {
-        const int o = i8_rows_override();
-        if (o == 4) return launch_i8_vr<V, EXACT, 4>(a, grid, st);
-        if (o == 5) return launch_i8_vr<V, EXACT, 5>(a, grid, st);
-    }
-    return launch_i8_vr<V, EXACT, i8_default_r<V>()>(a, grid, st);
+    return launch_i8_vr<V, EXACT, i8_default_r<V>()>(a, grid, st, filtered);
 }
 
 const unsigned *i8_status_dev(const SearchCtx *c) { return reinterpret_cast<const I8Scratch *>(c->i8_scratch)->counters + 4; }
@@ -131,7 +128,7 @@ void i8_preload(const csgpu_index *ix)
     const uint32_t V = i8_lines(ix->dim4);
     const bool exact = (ix->dim4 % 32) == 0;
     I8Args a{};
-#define CS_CASE(v) case v: if (exact) launch_i8_v<v, true>(a, 0, nullptr); else launch_i8_v<v, false>(a, 0, nullptr); break;
+#define CS_CASE(v) case v: if (exact) launch_i8_v<v, true>(a, 0, nullptr, false); else launch_i8_v<v, false>(a, 0, nullptr, false); break;
     switch (V) {
         CS_CASE(1) CS_CASE(2) CS_CASE(3) CS_CASE(4) CS_CASE(5) CS_CASE(6) CS_CASE(7) CS_CASE(8)
         default: break;
@@ -164,7 +161,8 @@ int i8_prepare_ctx(SearchCtx *c)
 }
 
 int enqueue_scan_i8(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const float *q_dev, uint32_t k,
-                    bool with_zero_ids, uint64_t *out_keys, cudaStream_t st, bool host_status)
+                    bool with_zero_ids, uint64_t *out_keys, cudaStream_t st, bool host_status,
+                    const uint64_t *bitmap_dev, uint64_t n_bits, const csgpu_predicate_t *pred)
 {
     if (int rc = i8_prepare_ctx(c)) return rc;   // contexts that predate csgpu_set_byte_prefilter
     I8Scratch *s = reinterpret_cast<I8Scratch *>(c->i8_scratch);
@@ -187,6 +185,12 @@ int enqueue_scan_i8(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const 
     a.counters = s->counters;
     a.out_keys = out_keys;
     a.status = c->i8_status;
+    const bool filtered = bitmap_dev != nullptr || pred != nullptr;
+    if (filtered) {   // same conventions as enqueue_scan: with pred, bitmap_dev is its per-FILE bitmap (or nullptr)
+        a.bitmap = bitmap_dev;
+        a.n_bits = n_bits;
+        if (pred) { a.tags = sh->tags; a.lang_mask = pred->lang_mask; a.file_lo = pred->file_lo; a.file_hi = pred->file_hi; }
+    }
     static const bool timing = getenv("CSGPU_I8_TIMING") != nullptr;
     a.timing = timing ? s->timing : nullptr;
     if (host_status) c->i8_status[0] = 1;   // a launch that never runs must not look like a success
@@ -195,7 +199,7 @@ int enqueue_scan_i8(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const 
     const uint32_t grid = (uint32_t)std::min<uint64_t>(std::min<uint64_t>((uint64_t)sh->sm_count * 2, I8_MAX_GRID), std::max<uint64_t>(want, 1));
     const bool exact = (ix->dim4 % 32) == 0;
     cudaError_t e;
-#define CS_CASE(v) case v: e = exact ? launch_i8_v<v, true>(a, grid, st) : launch_i8_v<v, false>(a, grid, st); break;
+#define CS_CASE(v) case v: e = exact ? launch_i8_v<v, true>(a, grid, st, filtered) : launch_i8_v<v, false>(a, grid, st, filtered); break;
     switch (V) {
         CS_CASE(1) CS_CASE(2) CS_CASE(3) CS_CASE(4) CS_CASE(5) CS_CASE(6) CS_CASE(7) CS_CASE(8)
         default: e = cudaErrorInvalidValue;

@@ -74,6 +74,12 @@ struct I8Args {
     unsigned long long *timing; // nullptr, or [gridDim.x + 1][4] globaltimer stamps (CSGPU_I8_TIMING=1: where the time goes)
     uint64_t *status;           // [0]: 0 = out_keys valid, 1 = answer with the exact scan instead;
                                 // [1]: (fp32 rows rescored << 32) | candidates on the final list
+    // FILT instantiation only (round 2): the same filters as the fp32 filtered scan (scan.cuh scan_rows_filtered) —
+    // id-indexed allow bitmap (tags == nullptr) or row-tag predicate with an optional per-FILE bitmap (tags != nullptr)
+    const uint32_t *tags = nullptr;
+    const uint64_t *bitmap = nullptr;
+    uint64_t n_bits = 0;
+    uint32_t lang_mask = 0xFFFFFFFFu, file_lo = 0, file_hi = 0xFFFFFFFFu;
 };
 
 __device__ __forceinline__ uint4 ldg_stream_u4(const uint8_t *p)
@@ -215,7 +221,13 @@ __device__ __forceinline__ void i8_rescore(const I8Args &a, const float4 (&qv)[V
 
 // V = float4 per lane of the fp32 query (ceil(dim4/32)) = 128-byte lines per shadow row; EXACT: dim4 == 32 V;
 // R = 4-row groups in flight per warp iteration (a warp streams 4 R rows = R x V x 512 B at a time).
-template <int V, bool EXACT, int R>
+// FILT (round 2): the byte prefilter under a filter. A row group (4 R consecutive rows) is only streamed if the filter
+// allows at least one of its rows, and only allowed rows may publish a bound or become candidates — so, like the fp32
+// filtered scan, masked rows cost no shadow bytes (a file / language predicate masks runs of ~37 chunks, i.e. whole
+// groups), and G stays the k-th smallest upper bound of k distinct ALLOWED rows. The unit of work is a 32-row block (one
+// filter word — tag or chunk id — per lane, loaded two blocks ahead of its use, the bitmap word one block ahead); the
+// block's 32 / (4 R) row groups are streamed only where the filter allows a row (FILT needs 4 R | 32: R = 4 at dim 384).
+template <int V, bool EXACT, int R, bool FILT = false>
 __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
 {
     constexpr int ROWS_PER_ITER = 4 * R;
@@ -327,9 +339,107 @@ __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
         // for the last 25 % of the kernel), so warps grab chunks of row groups from one global counter — up to
         // I8_CHUNK groups while plenty is left, single groups near the end. The next grab is issued before the
         // current chunk is processed, so its latency never shows.
+        int patience = 64;   // x 500 ns per warp, in total
+        if constexpr (FILT) {
+            const bool tagmode = a.tags != nullptr, have_bm = a.bitmap != nullptr;
+            static_assert(32 % ROWS_PER_ITER == 0, "FILT: a 32-row block must be a whole number of row groups");
+            const uint64_t n_blocks = (n + 31) / 32;
+            auto load_fw = [&](uint64_t blk, bool &valid) -> uint32_t {   // filter word of row blk * 32 + lane
+                const uint64_t row = blk * 32 + lane;
+                valid = blk < n_blocks && row < n;
+                if (!valid) return 0u;
+                if (!tagmode) return __ldg(a.ids + row);
+                const uint32_t tag = __ldg(a.tags + row);
+                valid = tag_pass_static(tag, a.lang_mask, a.file_lo, a.file_hi);
+                return tag & 0x07FFFFFFu;
+            };
+            auto load_bw = [&](uint32_t id, bool valid) -> uint64_t {
+                if (tagmode && !have_bm) return valid ? ~0ull : 0ull;
+                return (valid && (uint64_t)id < a.n_bits) ? __ldg(reinterpret_cast<const unsigned long long *>(a.bitmap) + (id >> 6)) : 0ull;
+            };
+            BlockCursor<false> cursor;
+            cursor.init(nullptr, a.counters + 3, nullptr, n_blocks, gw, n_warps, lane, warp, true);
+            bool v_cur, v_nxt, v_nx2, l_cur, l_nxt, l_nx2;
+            uint64_t g_cur = cursor.next(l_cur);
+            uint32_t f_cur = load_fw(g_cur, v_cur);
+            uint64_t w_cur = load_bw(f_cur, v_cur);
+            uint64_t g_nxt = cursor.next(l_nxt);
+            uint32_t f_nxt = load_fw(g_nxt, v_nxt);
+            while (l_cur) {
+                const uint64_t w_nxt = load_bw(f_nxt, v_nxt);
+                const uint64_t g_nx2 = cursor.next(l_nx2);
+                const uint32_t f_nx2 = load_fw(g_nx2, v_nx2);
+                const unsigned am32 = __ballot_sync(FULL, (w_cur >> (f_cur & 63)) & 1ull);   // bit i: row 32 blk + i is allowed
+#pragma unroll 1
+                for (int w = 0; w < 32 / ROWS_PER_ITER; ++w) {
+                    const unsigned am = ROWS_PER_ITER == 32 ? am32 : ((am32 >> (w * ROWS_PER_ITER)) & ((1u << (ROWS_PER_ITER & 31)) - 1u));
+                    if (!am) continue;   // bit i: row base + i is allowed
+                    while (patience > 0 && s_G == 0xFFFFFFFFu && *reinterpret_cast<volatile unsigned *>(&s_cnt) > I8_REGION / 4) {
+                        __nanosleep(500);
+                        --patience;
+                    }
+                    const uint64_t base = g_cur * 32 + (uint64_t)w * ROWS_PER_ITER;
+                    uint4 x[R][V];
+#pragma unroll
+                    for (int g = 0; g < R; ++g) {
+                        const uint64_t row = base + g * 4 + (lane >> 3);
+                        const uint8_t *p = a.shadow + row * a.d8 + sub * 16;
+                        const bool on = row < n && ((am >> (g * 4 + (lane >> 3))) & 1u);
+#pragma unroll
+                        for (int j = 0; j < V; ++j) {
+                            if (on) x[g][j] = ldg_stream_u4(p + 128 * j);
+                            else x[g][j] = make_uint4(0u, 0u, 0u, 0u);
+                        }
+                    }
+                    uint32_t mt = 0;
+                    if (lane < ROWS_PER_ITER && base + lane < n) mt = __ldg(a.meta + base + lane);
+                    const uint32_t G = s_G;
+                    int mine = 0;
+#pragma unroll
+                    for (int g = 0; g < R; ++g) {
+                        int acc = 0;
+#pragma unroll
+                        for (int j = 0; j < V; ++j) {
+                            acc = __dp4a((int)x[g][j].x, (int)qw[j].x, acc); acc = __dp4a((int)x[g][j].y, (int)qw[j].y, acc);
+                            acc = __dp4a((int)x[g][j].z, (int)qw[j].z, acc); acc = __dp4a((int)x[g][j].w, (int)qw[j].w, acc);
+                        }
+                        acc += __shfl_xor_sync(FULL, acc, 4);
+                        acc += __shfl_xor_sync(FULL, acc, 2);
+                        acc += __shfl_xor_sync(FULL, acc, 1);
+                        if (my_g == g) mine = acc;
+                    }
+                    const uint32_t m = __shfl_sync(FULL, mt, 4 * my_g + my_r4);
+                    const uint64_t row = base + 4 * my_g + my_r4;
+                    const bool live = sub < R && row < n && ((am >> (4 * my_g + my_r4)) & 1u);
+                    const float s_r = __half2float(__ushort_as_half((unsigned short)(m & 0xFFFFu)));
+                    const float e_r = __half2float(__ushort_as_half((unsigned short)(m >> 16)));
+                    const float c_hat = (float)mine * (sq_scale * s_r);
+                    const float M = fmaf(QN, e_r, EQ);
+                    const float lb = fmaf(-0.5f, c_hat + M, 0.5f) - I8_SLACK;
+                    const float ub = fmaf(-0.5f, c_hat - M, 0.5f) + I8_SLACK;
+                    const uint32_t lbk = okey(lb), ubk = live ? okey(ub) : 0xFFFFFFFFu;
+                    const bool hit = live && lbk <= G;
+                    const unsigned hm = __ballot_sync(FULL, hit);
+                    if (hm) {
+                        unsigned pos0 = 0;
+                        if (lane == 0) pos0 = atomicAdd(&s_cnt, (unsigned)__popc(hm));
+                        pos0 = __shfl_sync(FULL, pos0, 0);
+                        if (hit) {
+                            const unsigned pos = pos0 + __popc(hm & ((1u << lane) - 1u));
+                            if (pos < I8_REGION) region[pos] = ((uint64_t)lbk << 32) | (uint32_t)row;
+                        }
+                    }
+                    if (__any_sync(FULL, ubk < wmin)) {
+                        wmin = min(wmin, __reduce_min_sync(FULL, ubk));
+                        if (lane == 0) *reinterpret_cast<volatile uint32_t *>(a.warp_min + gw) = wmin;
+                    }
+                }
+                g_cur = g_nxt; l_cur = l_nxt; f_cur = f_nxt; v_cur = v_nxt; w_cur = w_nxt;
+                g_nxt = g_nx2; l_nxt = l_nx2; f_nxt = f_nx2; v_nxt = v_nx2;
+            }
+        } else {
         uint32_t c_next = max(1u, min((uint32_t)I8_CHUNK, n_groups / (2u * n_warps))), nxt = 0;
         if (lane == 0) nxt = atomicAdd(a.counters + 3, c_next);
-        int patience = 64;   // x 500 ns per warp, in total
         for (;;) {
         const uint32_t c_start = __shfl_sync(FULL, nxt, 0);
         if (c_start >= n_groups) break;
@@ -399,6 +509,7 @@ __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
                 wmin = min(wmin, __reduce_min_sync(FULL, ubk));
                 if (lane == 0) *reinterpret_cast<volatile uint32_t *>(a.warp_min + gw) = wmin;
             }
+        }
         }
         }
         asm volatile("bar.sync 1, %0;" :: "n"(I8_WARPS * 32));
@@ -476,12 +587,20 @@ __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
         return;
     }
     const volatile uint64_t *fl = a.final_list;
-    const uint32_t nz = min(a.n_zero, k);   // zero-norm rows: distance 0.0 (arroy pn*qn == 0), ascending id; the first k suffice
+    // zero-norm rows: distance 0.0 (arroy pn*qn == 0), ascending id; the first k suffice — under a filter the first k ALLOWED
+    // ones, so every entry of the side list is looked at (disallowed ones become empty slots)
+    const uint32_t nz = FILT ? a.n_zero : min(a.n_zero, k);
+    auto zero_key = [&](uint32_t i) -> uint64_t {
+        if constexpr (FILT) {
+            if (!zero_row_allowed(a.bitmap, a.n_bits, a.tags, a.lang_mask, a.file_lo, a.file_hi, a.zero_ids, a.n_zero, i)) return KEY_EMPTY;
+        }
+        return make_key(0.f, a.zero_ids[i]);
+    };
     if (total + nz <= 512) {
         // the common case (~115 keys at k = 10): one rank sort
         const uint32_t n_all = total + nz, fpad = pow2_at_least(n_all, 32);
         for (uint32_t t = threadIdx.x; t < fpad; t += blockDim.x)
-            C[t] = t < total ? fl[t] : (t < n_all ? make_key(0.f, a.zero_ids[t - total]) : KEY_EMPTY);
+            C[t] = t < total ? fl[t] : (t < n_all ? zero_key(t - total) : KEY_EMPTY);
         __syncthreads();
         cta_sort_fast(C, fpad);
         for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) a.out_keys[j] = j < fpad ? C[j] : KEY_EMPTY;
@@ -491,7 +610,7 @@ __global__ void __launch_bounds__(I8_THREADS, 2) scan_i8_kernel(const I8Args a)
         sel.cb.buf = C; sel.cb.cnt = &s_cnt; sel.cb.thr = &s_thr; sel.cap = ctabuf_cap(k); sel.k = k;
         sel.reset();
         cta_buf_stream(sel.cb, sel.cap, k, total, [&](uint64_t t) { return fl[t]; });
-        if (nz) cta_buf_stream(sel.cb, sel.cap, k, nz, [&](uint64_t t) { return make_key(0.f, a.zero_ids[t]); });
+        if (nz) cta_buf_stream(sel.cb, sel.cap, k, nz, [&](uint64_t t) { return zero_key((uint32_t)t); });
         sel.finish();
         for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) a.out_keys[j] = C[j];
     }

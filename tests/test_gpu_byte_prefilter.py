@@ -88,9 +88,9 @@ def test_byte_prefilter_routes_what_it_does_not_cover(cs):
     b0 = fast.device_stats().byte_searches
     _assert_same(fast, plain, q, 257)                                   # k above the int8 route's limit
     _assert_same(fast, plain, q, 1000)
-    flt = cs.RowFilter.from_mask(np.arange(rows.shape[0]) % 3 == 0)     # filtered searches stay on the fp32 kernel
-    fi, fd = fast.search_ids(q, 10, flt)
-    pi, pd = plain.search_ids(q, 10, flt)
+    flt = cs.RowFilter.from_mask(np.arange(rows.shape[0]) % 3 == 0)     # k above the limit under a filter: fp32 filtered scan
+    fi, fd = fast.search_ids(q, 300, flt)
+    pi, pd = plain.search_ids(q, 300, flt)
     assert np.array_equal(fi, pi) and np.array_equal(fd.view(np.uint32), pd.view(np.uint32))
     assert fast.device_stats().byte_searches == b0
     # zero-norm query: the launch reports it, the fp32 kernel answers (every distance 0.0, ascending ids)
@@ -107,6 +107,67 @@ def test_byte_prefilter_routes_what_it_does_not_cover(cs):
     assert fast.device_stats().byte_fallbacks == f0 + 1
     _assert_same(fast, plain, (q * np.float32(1e-22)).astype(np.float32), 10)    # tiny but normalisable: the int8 route
     assert fast.device_stats().byte_fallbacks <= f0 + 2                          # (normally f0 + 1: answered by itself)
+
+
+@pytest.mark.parametrize("n,d", [(200_000, 384), (60_000, 768), (30_000, 100)])
+def test_byte_prefilter_under_filters_bit_identical(cs, oracle, n, d):
+    """Round 2: filtered and tagged searches take the int8 route too (scan_i8_kernel FILT: only row groups the filter allows
+    are streamed, only allowed rows publish bounds or become candidates). Same bar: ids AND distances bit-identical to the
+    fp32 filtered scan — id bitmaps at several densities, tag predicates (language mask, file range, per-file bitmap),
+    zero-norm rows inside and outside the filter, k up to 256, and an empty filter."""
+    from codesearch_b200 import tags as T
+    rng = np.random.default_rng(n * 3 + d)
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    rows[[11, 5000, n - 3]] = 0.0
+    ids = np.arange(n, dtype=np.uint32)
+    tg = T.synth_tags(0, n)
+    pair = []
+    for on in (True, False):
+        st = cs.VectorStore.new(None, d)
+        st.append_rows(rows, ids, tg)
+        if on:
+            st.set_byte_prefilter(True)
+        st.build_index()
+        pair.append(st)
+    fast, plain = pair
+    qs = rng.standard_normal((4, d)).astype(np.float32)
+
+    def same(a, b, what):
+        assert np.array_equal(a[0], b[0]), (what, a[0][:6], b[0][:6])
+        assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32)), what
+
+    b0 = fast.device_stats()
+    n_calls = 0
+    for dens in (0.9, 0.3, 0.02):
+        mask = rng.random(n) < dens
+        mask[11] = True; mask[5000] = False                      # one zero-norm row allowed, one masked
+        flt = cs.RowFilter.from_mask(mask)
+        for k in (10, 100, 256):
+            got = fast.search_ids(qs[0], k, flt)
+            same(got, plain.search_ids(qs[0], k, flt), ("bitmap", dens, k))
+            n_calls += 1
+            if k == 10:
+                ri, rd, r64 = oracle.search(rows, qs[0], k + MARGIN, bitmap=flt.bitmap, n_bits=flt.n_bits)
+                check_topk(got[0], got[1], ri, rd, r64, k)
+    n_files = (n + 36) // 37
+    fbm = np.zeros((n_files + 63) // 64, dtype=np.uint64)
+    for f in range(0, n_files, 3):
+        fbm[f >> 6] |= np.uint64(1) << np.uint64(f & 63)
+    preds = [T.TagPredicate(lang_mask=0x0000FFFF), T.TagPredicate(file_lo=100, file_hi=n_files // 2),
+             T.TagPredicate(lang_mask=0x7F0, file_lo=7, file_hi=n_files - 9, file_bitmap=fbm, n_file_bits=n_files),
+             T.TagPredicate(file_bitmap=fbm, n_file_bits=n_files), T.TagPredicate(file_lo=3, file_hi=3)]
+    for pi_, pred in enumerate(preds):
+        for k in (10, 200):
+            same(fast.search_tagged_ids(qs[1], k, pred), plain.search_tagged_ids(qs[1], k, pred), ("tags", pi_, k))
+            n_calls += 1
+    s1 = fast.device_stats()
+    assert s1.byte_searches - b0.byte_searches == n_calls          # the int8 route really ran for every one of them ...
+    assert s1.byte_fallbacks - b0.byte_fallbacks <= 3               # ... and (almost) always answered by itself
+    ei, ed = fast.search_ids(qs[2], 10, cs.RowFilter(np.zeros(1, dtype=np.uint64), 0))   # an empty filter allows nothing
+    assert len(ei) == 0
+    z = np.zeros(d, np.float32)                                      # zero-norm query under a filter: handed to the fp32 kernel
+    flt = cs.RowFilter.from_mask(np.arange(n) % 5 == 0)
+    same(fast.search_ids(z, 10, flt), plain.search_ids(z, 10, flt), "zero query")
 
 
 def test_byte_prefilter_adversarial_inputs(cs, oracle):

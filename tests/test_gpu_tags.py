@@ -6,6 +6,7 @@ predicate restatement allows and (ii) csgpu_search_filtered with the equivalent 
 GPU box only.
 """
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -13,6 +14,7 @@ import pytest
 from parity import check_topk
 
 pytestmark = pytest.mark.gpu
+os.environ.setdefault("CSGPU_I8_MIN_ROWS", "4096")   # read once by the library: lets small shards take the int8 route
 
 MARGIN = 8
 
@@ -160,8 +162,10 @@ def test_search_tagged_by_path_and_language(cs):
     assert st.search_tagged(q, 10, languages=["Go"]) == []
 
 
-def test_tagged_device_entry_with_fused_exchange(cs, oracle):
-    """BASELINE configs[4] shape on one GPU: 3 'ranks', predicate filter + fused exchange in the same kernel."""
+@pytest.mark.parametrize("byte_prefilter", [False, True])
+def test_tagged_device_entry_with_fused_exchange(cs, oracle, byte_prefilter):
+    """BASELINE configs[4] shape on one GPU: 3 'ranks', predicate filter + fused exchange in the same kernel. With the byte
+    prefilter on (round 2): int8 FILT kernel -> conditional fp32 filtered scan (no-op) -> exchange_keys_kernel per rank."""
     import torch
     from codesearch_b200 import _lib
     from codesearch_b200.sharded import decode_keys
@@ -176,6 +180,8 @@ def test_tagged_device_entry_with_fused_exchange(cs, oracle):
     for a, b in zip(bounds, bounds[1:]):
         st = cs.VectorStore.new(None, d)
         st.append_rows(rows[a:b], ids[a:b], tags[a:b])
+        if byte_prefilter:
+            st.set_byte_prefilter(True)
         st.build_index()
         stores.append(st)
     for r, st in enumerate(stores):
@@ -184,6 +190,7 @@ def test_tagged_device_entry_with_fused_exchange(cs, oracle):
     peers = (ctypes.c_void_p * W)(*[st.handle for st in stores])
     for st in stores:
         _lib.check(lib.csgpu_exchange_connect_local(st.handle, peers))
+    searches0 = sum(st.device_stats().byte_searches for st in stores)
     n_files = n // 37 + 1
     fmask = rng.random(n_files) < 0.25
     bm_dev = torch.from_numpy(_bitmap(fmask).view(np.int64)).cuda()
@@ -207,6 +214,7 @@ def test_tagged_device_entry_with_fused_exchange(cs, oracle):
             ri, rd = decode_keys(outs[r].cpu().numpy())
             assert np.array_equal(ri, first[0]) and np.array_equal(rd, first[1])
         check_topk(first[0], first[1], oi, od, o64, min(k, int(ok.sum())))
+    assert sum(st.device_stats().byte_searches for st in stores) - searches0 == (9 if byte_prefilter else 0)
     for st in stores:
         lib.csgpu_exchange_destroy(st.handle)
 
