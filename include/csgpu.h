@@ -157,9 +157,10 @@ int  csgpu_set_tensor_prefilter(csgpu_index *ix, uint32_t enabled);
  * two quantisation residuals); the few hundred rows it cannot exclude are rescored from the fp32 rows with the
  * single-query kernel's arithmetic, in the same kernel launch. Ids AND distances are bit-identical to the default path
  * (codesearch_b200/csrc/scan_i8.cuh has the bound); the kernel moves dim + 4 bytes per row, not 4 * dim. Applies to
- * unfiltered csgpu_search with k <= 256 on shards of >= 524288 rows; everything else, and any query the filter
- * cannot bound (zero-norm query, candidate overflow), runs the fp32 scan kernel. Off by default. May be called
- * before or after csgpu_build; the shadow follows every later build / load. */
+ * csgpu_search, csgpu_search_filtered and csgpu_search_tagged (and the device entry points) with k <= 256 on shards of
+ * >= 524288 rows — under a filter only row groups the filter allows are streamed, so masked rows still cost nothing;
+ * everything else, and any query the filter cannot bound (zero-norm query, candidate overflow), runs the fp32 scan
+ * kernels. Off by default. May be called before or after csgpu_build; the shadow follows every later build / load. */
 int  csgpu_set_byte_prefilter(csgpu_index *ix, uint32_t enabled);
 
 /* b (<= 16) query VARIANTS of one user query (query expansion, src/search/mod.rs:479-483), searched with the same
