@@ -278,10 +278,9 @@ struct BlockCursor {
     bool dynamic, done = false;
     int lane, warp;
 
-    __device__ __forceinline__ void init(const unsigned *run_static, unsigned *work_, uint32_t *s_start_, uint64_t n_blocks_, uint64_t gw_,
+    __device__ __forceinline__ void init(const void *, unsigned *work_, uint32_t *s_start_, uint64_t n_blocks_, uint64_t gw_,
                                          uint64_t n_warps_, int lane_, int warp_, bool dynamic_)
     {
-        (void)run_static;
         n_blocks = n_blocks_; gw = gw_; n_warps = n_warps_; work = work_; s_start = s_start_; lane = lane_; warp = warp_; dynamic = dynamic_;
         const uint64_t b_first = gw - (gw % SCAN_WARPS);   // same trip count for every warp of the CTA
         n_iters = b_first < n_blocks ? (n_blocks - b_first + n_warps - 1) / n_warps : 0;

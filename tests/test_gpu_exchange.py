@@ -14,6 +14,7 @@ import pytest
 from parity import check_topk
 
 pytestmark = pytest.mark.gpu
+os.environ.setdefault("CSGPU_I8_MIN_ROWS", "4096")   # read once by the library: lets small shards take the int8 route
 
 MARGIN = 8
 
@@ -73,6 +74,67 @@ def test_fused_exchange_three_ranks_one_gpu(cs, oracle):
         t = ctypes.c_uint32(7)
         _lib.check(lib.csgpu_exchange_status(st.handle, ctypes.byref(t)))
         assert t.value == 0
+        lib.csgpu_exchange_destroy(st.handle)
+
+
+def test_host_pointer_exchange_search_three_ranks_one_gpu(cs, oracle):
+    """csgpu_search_exchange: the exchange search with HOST pointers (what csgpu_search is to a single index). It blocks until
+    the global top-k is back, so the three 'ranks' call it from three host threads, as three processes would; every rank must
+    return the unsharded index's answer bit for bit — with the fp32 scan and with the byte prefilter on one of the ranks."""
+    import threading
+    from codesearch_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(35)
+    n, d, W = 36000, 384, 3
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    rows[7] = 0.0
+    bounds = [0, 10000, 26000, n]
+    stores = []
+    for r, (a, b) in enumerate(zip(bounds, bounds[1:])):
+        st = cs.VectorStore.new(None, d)
+        st.append_rows(rows[a:b], np.arange(a, b, dtype=np.uint32))
+        if r == 1:
+            st.set_byte_prefilter(True)                          # mixed routes: int8 kernel + exchange_keys_kernel on this rank
+        st.build_index()
+        stores.append(st)
+    for r, st in enumerate(stores):
+        h = (ctypes.c_ubyte * 64)()
+        _lib.check(lib.csgpu_exchange_create(st.handle, W, r, h))
+    peers = (ctypes.c_void_p * W)(*[st.handle for st in stores])
+    for st in stores:
+        _lib.check(lib.csgpu_exchange_connect_local(st.handle, peers))
+    whole = cs.VectorStore.new(None, d)
+    whole.append_rows(rows, np.arange(n, dtype=np.uint32))
+    whole.build_index()
+    qs = rng.standard_normal((6, d)).astype(np.float32)
+    ks = [10, 100, 10, 1, 256, 32]
+    got = [[None] * len(ks) for _ in range(W)]
+    errs = []
+
+    def rank_main(r):
+        try:
+            for j, k in enumerate(ks):
+                oi = np.empty(k, np.uint32); od = np.empty(k, np.float32); on = ctypes.c_uint32(0)
+                _lib.check(lib.csgpu_search_exchange(stores[r].handle, qs[j].ctypes.data_as(_lib._f32p), d, k,
+                                                     oi.ctypes.data_as(_lib._u32p), od.ctypes.data_as(_lib._f32p), ctypes.byref(on)))
+                got[r][j] = (oi[: on.value].copy(), od[: on.value].copy())
+        except Exception as e:  # noqa: BLE001
+            errs.append((r, repr(e)))
+
+    ths = [threading.Thread(target=rank_main, args=(r,)) for r in range(W)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    assert not errs, errs
+    for j, k in enumerate(ks):
+        wi, wd = whole.search_ids(qs[j], k)
+        for r in range(W):
+            assert np.array_equal(got[r][j][0], wi) and np.array_equal(got[r][j][1].view(np.uint32), wd.view(np.uint32)), (j, r)
+    # guard clauses verbatim through this entry point too
+    oi = np.empty(4, np.uint32); od = np.empty(4, np.float32); on = ctypes.c_uint32(0)
+    rc = lib.csgpu_search_exchange(stores[0].handle, qs[0].ctypes.data_as(_lib._f32p), d - 1, 4, oi.ctypes.data_as(_lib._u32p),
+                                   od.ctypes.data_as(_lib._f32p), ctypes.byref(on))
+    assert rc == _lib.ERR_DIM and _lib.last_error() == f"Query embedding dimension mismatch: expected {d}, got {d - 1}"
+    for st in stores:
         lib.csgpu_exchange_destroy(st.handle)
 
 
