@@ -41,6 +41,7 @@ void count_launch(uint64_t n) { g_kernel_launches.fetch_add(n, std::memory_order
 // ---------------------------------------------------------------------------------------
 constexpr uint32_t MAX_GRID = 148 * 4;   // upper bound on persistent grid size we ever launch
 constexpr uint32_t MAX_BATCH = 16;       // queries per multi-query scan
+constexpr size_t GATHER_KEYS_PER_SHARD = 16 * 256 > 2 * CSGPU_MAX_K ? 16 * 256 : 2 * CSGPU_MAX_K;   // SearchCtx::gather
 constexpr uint32_t PREFILTER_MIN_BATCH = 1;   // tensor prefilter on: every csgpu_search_batch goes to the tensor cores (9 queries:
                                               // 1.56 ms vs two multi-query passes at 3 ms each; it reads the 2-byte shadow, not the
                                               // 4-byte rows). csgpu_search itself always stays on the fp32 scan kernel.
@@ -64,7 +65,9 @@ static int ctx_create(const csgpu_index *ix, Shard *sh, SearchCtx **out)
     CS_CUDA(cudaHostAlloc(&c->q_pin, (size_t)MAX_BATCH * ix->dim_pad * sizeof(float), cudaHostAllocDefault));
     c->cand_cap = (size_t)MAX_GRID * CSGPU_MAX_K * 2;   // single query: grid x k <= 592 x 1024; 16-query pass: 16 x 296 x 256
     CS_CUDA(cudaMalloc(&c->cand, c->cand_cap * sizeof(uint64_t)));
-    CS_CUDA(cudaMalloc(&c->gather, (size_t)8 * 2 * CSGPU_MAX_K * sizeof(uint64_t)));
+    // per-shard results gathered on shard 0 (peer-copy route): up to 8 shards x max(one list of 1024 keys, a 16-query pass of
+    // 256 keys each) — the 16-query pass of round 2 doubled what the multi-query route can bring back per shard
+    CS_CUDA(cudaMalloc(&c->gather, (size_t)8 * GATHER_KEYS_PER_SHARD * sizeof(uint64_t)));
     CS_CUDA(cudaMalloc(&c->ticket, 64 * sizeof(unsigned)));
     CS_CUDA(cudaMemset(c->ticket, 0, 64 * sizeof(unsigned)));
     CS_CUDA(cudaMalloc(&c->out_dev, (size_t)MAX_BATCH * CSGPU_MAX_K * sizeof(uint64_t)));

@@ -47,7 +47,7 @@ struct SearchCtx {
     float *q_dev = nullptr;         // [max_b * dim_pad]
     float *q_pin = nullptr;         // pinned staging for the query
     uint64_t *cand = nullptr;       // [grid_max * CSGPU_MAX_K]
-    uint64_t *gather = nullptr;     // [8 * 2 * CSGPU_MAX_K] per-shard results gathered for the cross-GPU merge
+    uint64_t *gather = nullptr;     // [8 * 4096] per-shard results gathered for the cross-GPU merge (peer-copy route)
     unsigned *ticket = nullptr;
     uint64_t *out_dev = nullptr;    // [max_b * CSGPU_MAX_K]
     uint64_t *out_pin = nullptr;    // pinned, device-mapped; kernels write results straight here

@@ -170,6 +170,12 @@ class VectorStore {
     // VectorStore::new (store.rs:110-176): creates the directory, hydrates the device index from <db>/gpu when a
     // snapshot exists (next_id = last key + 1, indexed = snapshot present). db_path may be empty (in-memory store).
     static VectorStore create(const std::string &db_path, size_t dimensions) { return VectorStore(db_path, dimensions, false); }
+    // The same store over several GPUs of this process (additive; knob CODESEARCH_GPU_DEVICES in the Rust patch): rows are
+    // sharded row-wise, search() is one fused launch per device (include/csgpu.h, csgpu_create).
+    static VectorStore create(const std::string &db_path, size_t dimensions, const std::vector<int32_t> &devices)
+    {
+        return VectorStore(db_path, dimensions, false, devices);
+    }
     // open_readonly (store.rs:183-250): searches while another process writes; mutations are refused.
     static VectorStore open_readonly(const std::string &db_path, size_t dimensions) { return VectorStore(db_path, dimensions, true); }
 
@@ -499,10 +505,12 @@ class VectorStore {
         if (!chunks_.empty()) next_id_ = chunks_.rbegin()->first + 1;   // store.rs:141-144
     }
 
-    VectorStore(const std::string &db_path, size_t dims, bool read_only) : dimensions(dims), db_path_(db_path), read_only_(read_only)
+    VectorStore(const std::string &db_path, size_t dims, bool read_only, const std::vector<int32_t> &devices = {})
+        : dimensions(dims), db_path_(db_path), read_only_(read_only)
     {
         csgpu_index *raw = nullptr;
-        check(csgpu_create(&raw, (uint32_t)dims, CSGPU_DTYPE_F32, nullptr, 1));
+        check(csgpu_create(&raw, (uint32_t)dims, CSGPU_DTYPE_F32, devices.empty() ? nullptr : devices.data(),
+                           devices.empty() ? 1u : (uint32_t)devices.size()));
         ix_.reset(raw);
         if (!db_path_.empty()) {
             mkdir(db_path_.c_str(), 0755);   // store.rs:116 create_dir_all

@@ -156,6 +156,46 @@ static void test_file_table_reopen()
     }
 }
 
+// one process, several devices (here: two shards on device 0, which csgpu_create accepts — the one-GPU box covers the whole
+// multi-shard path): search() = one fused launch per shard, identical results, snapshot reopens under another device count
+static void test_multi_device_store()
+{
+    const std::string db = temp_db("multi.db");
+    std::vector<EmbeddedChunk> chunks;
+    for (int i = 0; i < 6000; ++i) {
+        std::vector<float> e(8);
+        for (int c = 0; c < 8; ++c) e[c] = std::sin(0.37f * (float)(i + 1) * (float)(c + 1)) + (c == i % 8 ? 0.5f : 0.f);
+        chunks.push_back(EmbeddedChunk(fn_chunk("fn f" + std::to_string(i) + "() {}", (size_t)i, (size_t)i + 1, "src/m" + std::to_string(i / 40) + ".rs"), e));
+    }
+    std::vector<float> q = {0.3f, -0.2f, 0.9f, 0.1f, 0.0f, 0.4f, -0.7f, 0.2f};
+    std::vector<SearchResult> one_r, two_r;
+    {
+        VectorStore one = VectorStore::create("", 8);
+        one.insert_chunks(chunks);
+        one.build_index();
+        one_r = one.search(q, 50);
+    }
+    {
+        VectorStore two = VectorStore::create(db, 8, {0, 0});
+        two.insert_chunks(chunks);
+        two.build_index();
+        csgpu_stats_t s;
+        CHECK(csgpu_stats(two.handle(), &s) == CSGPU_OK && s.n_devices == 2 && s.rows_per_device[0] > 0 && s.rows_per_device[1] > 0);
+        const uint64_t l0 = csgpu_kernel_launches();
+        two_r = two.search(q, 50);
+        CHECK(csgpu_kernel_launches() - l0 == 2);   // one fused scan per shard, no merge launch
+    }
+    CHECK(one_r.size() == 50 && two_r.size() == 50);
+    for (size_t i = 0; i < one_r.size() && i < two_r.size(); ++i)
+        CHECK(one_r[i].id == two_r[i].id && one_r[i].distance == two_r[i].distance && one_r[i].path == two_r[i].path);
+    {
+        VectorStore again = VectorStore::create(db, 8);   // the two-shard snapshot under one device
+        auto r = again.search(q, 50);
+        CHECK(r.size() == 50);
+        for (size_t i = 0; i < r.size() && i < one_r.size(); ++i) CHECK(r[i].id == one_r[i].id && r[i].distance == one_r[i].distance);
+    }
+}
+
 // guards, store.rs:432-444: literal messages
 static void test_guards()
 {
@@ -288,7 +328,7 @@ int main(int argc, char **argv)
     struct { const char *name; void (*fn)(); } tests[] = {
         {"test_vector_store_creation", test_vector_store_creation}, {"test_insert_and_search", test_insert_and_search},
         {"test_stats", test_stats}, {"test_clear", test_clear}, {"test_get_chunk", test_get_chunk},
-        {"test_persistence", test_persistence}, {"test_file_table_reopen", test_file_table_reopen}, {"test_guards", test_guards}, {"test_additive_methods", test_additive_methods},
+        {"test_persistence", test_persistence}, {"test_file_table_reopen", test_file_table_reopen}, {"test_multi_device_store", test_multi_device_store}, {"test_guards", test_guards}, {"test_additive_methods", test_additive_methods},
         {"test_byte_prefilter", test_byte_prefilter},
     };
     for (auto &t : tests) {

@@ -56,7 +56,7 @@ def test_two_shards_every_search_entry_point(pair, oracle):
         assert _same(g, h), k
         oi, od, o64 = oracle.np_search(rows, qs[1], k + MARGIN)
         check_topk(g[0], g[1], oi, od, o64, k)
-    for b, k in ((8, 10), (5, 100), (9, 256)):                  # multi-query scan, 8 + 1 split
+    for b, k in ((8, 10), (5, 100), (9, 256), (16, 256), (12, 10), (24, 100)):   # multi-query scan: 8- and 16-query passes, 16 + 8
         a = one.search_batch_ids(qs[:b], k)
         c = two.search_batch_ids(qs[:b], k)
         assert np.array_equal(a[2], c[2]) and _same(a, c), (b, k)

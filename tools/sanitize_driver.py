@@ -49,6 +49,15 @@ for k in (10, 100, 256):
     hi, hd = st.search_ids(q, k)
     st.set_byte_prefilter(True)
     assert np.array_equal(gi, hi) and np.array_equal(gd, hd)
+flt8 = cs.RowFilter.from_mask(rng.random(st.device_stats().live_rows + 2000) < 0.4)     # scan_i8_kernel FILT: id bitmap ...
+for k in (10, 100):
+    gi, gd = st.search_ids(q, k, flt8)
+    ti, td = st.search_tagged_ids(q, k, TagPredicate(lang_mask=0x3FF, file_lo=2, file_hi=140))   # ... and tag predicate
+    st.set_byte_prefilter(False)
+    hi, hd = st.search_ids(q, k, flt8)
+    ui, ud = st.search_tagged_ids(q, k, TagPredicate(lang_mask=0x3FF, file_lo=2, file_hi=140))
+    st.set_byte_prefilter(True)
+    assert np.array_equal(gi, hi) and np.array_equal(gd, hd) and np.array_equal(ti, ui) and np.array_equal(td, ud)
 st.search_ids(np.zeros(d, np.float32), 10)                  # zero-norm query: status word -> fp32 kernel
 assert st.device_stats().byte_searches >= 4
 st.set_byte_prefilter(False)
