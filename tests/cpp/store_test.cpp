@@ -162,7 +162,7 @@ static void test_multi_device_store()
 {
     const std::string db = temp_db("multi.db");
     std::vector<EmbeddedChunk> chunks;
-    for (int i = 0; i < 6000; ++i) {
+    for (int i = 0; i < 9000; ++i) {   // >= 4096 per device: one insert is split evenly over the shards
         std::vector<float> e(8);
         for (int c = 0; c < 8; ++c) e[c] = std::sin(0.37f * (float)(i + 1) * (float)(c + 1)) + (c == i % 8 ? 0.5f : 0.f);
         chunks.push_back(EmbeddedChunk(fn_chunk("fn f" + std::to_string(i) + "() {}", (size_t)i, (size_t)i + 1, "src/m" + std::to_string(i / 40) + ".rs"), e));
