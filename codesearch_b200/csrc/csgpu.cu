@@ -86,7 +86,7 @@ static void ctx_destroy(SearchCtx *c)
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->busy) cudaEventDestroy(c->busy);
     cudaFree(c->q_dev); cudaFreeHost(c->q_pin); cudaFree(c->cand); cudaFree(c->gather); cudaFree(c->ticket);
-    cudaFree(c->out_dev); cudaFreeHost(c->out_pin); cudaFree(c->bitmap_dev);
+    cudaFree(c->out_dev); cudaFreeHost(c->out_pin); cudaFree(c->bitmap_dev); cudaFree(c->timing);
     i8_free_ctx(c);
     delete c;
 }
@@ -259,6 +259,11 @@ static int enqueue_scan(const csgpu_index *ix, const Shard *sh, SearchCtx *c, co
     // and cost one tag load, so the grabs' atomics and the pipeline refill at chunk boundaries outweigh the balancing;
     // profiles/r02_static_vs_dynamic_filtered_multi.txt). CSGPU_SCAN_DYNAMIC_ALL=1 switches it on for A/B runs.
     a.static_split = scan_dynamic_all() ? 0u : 1u;
+    static const bool timing = getenv("CSGPU_SCAN_TIMING") != nullptr;   // diagnostic: where a scan's time goes (see scan_timing_report)
+    if (timing) {
+        if (c->timing == nullptr) cudaMalloc(&c->timing, (size_t)(MAX_GRID + 1) * 4 * sizeof(unsigned long long));
+        a.timing = c->timing;
+    }
     const uint32_t per_cta_rows = SCAN_WARPS * rows_in_flight(ix->dim4);
     uint64_t want = (sh->n_built + per_cta_rows - 1) / per_cta_rows;
     if (bitmap_dev != nullptr || pred != nullptr) {   // filtered: pre-filter variant (scan_filtered.cu)
@@ -586,6 +591,27 @@ static int shard_build(csgpu_index *ix, Shard *sh, std::vector<std::pair<uint32_
     return CSGPU_OK;
 }
 
+// CSGPU_SCAN_TIMING=1: after a host-pointer single-device search, print when (relative to the first CTA's start) the last CTA
+// started, the first / last CTA finished streaming, the last CTA list was written, the last ticket was taken, the last
+// CTA had merged, and the kernel was done. The search has been synchronised; a diagnostic, never a benchmark.
+static void scan_timing_report(const Shard *sh, SearchCtx *c, uint64_t n_rows, uint32_t k)
+{
+    if (c->timing == nullptr) return;
+    const uint32_t per_cta_rows = SCAN_WARPS * 4;
+    uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sh->sm_count * 2, std::max<uint64_t>((n_rows + per_cta_rows - 1) / per_cta_rows, 1));
+    std::vector<unsigned long long> t((size_t)(MAX_GRID + 1) * 4);
+    if (cudaMemcpy(t.data(), c->timing, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+    unsigned long long t0 = ~0ull, st_hi = 0, s_lo = ~0ull, s_hi = 0, w_hi = 0;
+    for (uint32_t b = 0; b < grid; ++b) {
+        t0 = std::min(t0, t[b * 4]); st_hi = std::max(st_hi, t[b * 4]);
+        s_lo = std::min(s_lo, t[b * 4 + 1]); s_hi = std::max(s_hi, t[b * 4 + 1]); w_hi = std::max(w_hi, t[b * 4 + 2]);
+    }
+    fprintf(stderr, "[scan timing] rows %llu k %u grid %u: last CTA start +%.1f us | streaming ends first +%.1f last +%.1f | last CTA list +%.1f | "
+                    "last ticket seen +%.1f | merged +%.1f | done +%.1f us\n",
+            (unsigned long long)n_rows, k, grid, (st_hi - t0) / 1e3, (s_lo - t0) / 1e3, (s_hi - t0) / 1e3, (w_hi - t0) / 1e3,
+            (t[grid * 4] - t0) / 1e3, (t[grid * 4 + 1] - t0) / 1e3, (t[grid * 4 + 2] - t0) / 1e3);
+}
+
 static bool all_finite(const float *q, uint32_t n)
 {
     for (uint32_t i = 0; i < n; ++i) if (!std::isfinite(q[i])) return false;
@@ -888,6 +914,7 @@ static int search_one(const csgpu_index *ix, const float *q, uint32_t k, const u
             if (again) { ix->byte_fallbacks.fetch_add(1, std::memory_order_relaxed); return -1; }
         }
         decode_keys(c0->out_pin, k, out_ids, out_dist, out_n);
+        if (G == 1 && !use_i8 && bitmap == nullptr && pred == nullptr) scan_timing_report(ix->shards[0], c0, ix->shards[0]->n_built, k);
         return CSGPU_OK;
     };
     rc = body();

@@ -57,6 +57,7 @@ struct SearchCtx {
     void *i8_scratch = nullptr;     // byte prefilter (scan_i8.cu): per-warp minima, counters, candidate regions; allocated with the
                                     // context when the prefilter is on (csgpu_set_byte_prefilter warms one per shard)
     uint64_t *i8_status = nullptr;  // pinned, device-mapped: [0] fallback flag, [1] statistics of the last launch
+    unsigned long long *timing = nullptr;   // CSGPU_SCAN_TIMING=1: per-CTA globaltimer stamps of the last fp32 scan (diagnostic)
     cudaEvent_t busy = nullptr;     // device entry points: recorded on the caller's stream after the enqueue, waited on by the next
     bool busy_recorded = false;
 };

@@ -67,6 +67,8 @@ struct ScanArgs {
     const unsigned *run_if = nullptr;   // non-null: the whole launch is a no-op unless *run_if != 0 (device-side fallback of
                                         // the byte prefilter: the host cannot look at the status without synchronising)
     uint32_t static_split = 0;          // filtered scans: 1 = fixed-stride block split instead of the work counter (CSGPU_SCAN_STATIC)
+    unsigned long long *timing = nullptr;   // diagnostic (CSGPU_SCAN_TIMING=1): [gridDim.x + 1][4] globaltimer stamps — per CTA
+                                            // start / streaming done / CTA list written; last CTA: ticket taken / merged / done
 };
 
 // LD selects the load flavour (tuned on B200, see profiles/): 0 = ld.global.nc.L1::no_allocate,
@@ -168,6 +170,53 @@ __device__ __forceinline__ void cta_reduce(Sel &sel, uint64_t *smem, uint32_t k,
     __syncthreads();
 }
 
+// k <= 32, round 2. Every warp holds a sorted list of 32 keys (one per lane, ascending, KEY_EMPTY padded): the CTA's best
+// 32 by a three-level tree of warp merges through shared memory (smem: [SCAN_WARPS * 32] keys) — five barriers and three
+// 5-stage shuffle networks instead of the 36 barrier-separated stages of a 256-key bitonic sort (measured with
+// CSGPU_SCAN_TIMING: 4.2 us -> the tail of EVERY query pays it twice). dst[0..k) and smem[0..32) receive the result.
+__device__ __forceinline__ void cta_merge_lists32(uint64_t v, uint64_t *smem, uint32_t k, uint64_t *dst, int warp, int lane)
+{
+    smem[warp * 32 + lane] = v;
+    __syncthreads();
+#pragma unroll
+    for (int half = SCAN_WARPS / 2; half >= 1; half >>= 1) {
+        if (warp < half) v = warp_merge_low32(v, smem[(warp + half) * 32 + lane], lane);
+        __syncthreads();                       // everyone has read its partner's list ...
+        if (warp < half) smem[warp * 32 + lane] = v;
+        __syncthreads();                       // ... before the survivors overwrite theirs
+    }
+    if (warp == 0 && (uint32_t)lane < k) dst[lane] = v;
+    __syncthreads();
+}
+
+// This warp's share of n keys (key = load(i); batches of 32 dealt round-robin over the CTA's warps) folded into its
+// running sorted list: each batch is sorted across the warp (15 shuffle stages) and merged in (5) — no data-dependent
+// insertion loop. Eight batches per step: their loads are all in flight before the first one is used (one L2 round trip
+// per 2048 keys of the CTA instead of one per batch) and the eight independent sorts overlap their shuffle latencies.
+template <class F>
+__device__ __forceinline__ uint64_t warp_fold_keys32(uint64_t run, uint64_t n, F load, int warp, int lane)
+{
+    constexpr int NB = 8;
+    for (uint64_t b0 = (uint64_t)warp * 32; b0 < n; b0 += (uint64_t)NB * SCAN_WARPS * 32) {
+        uint64_t kk[NB];
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const uint64_t i = b0 + (uint64_t)u * SCAN_WARPS * 32 + lane;
+            kk[u] = i < n ? load(i) : KEY_EMPTY;
+        }
+#pragma unroll
+        for (int u = 0; u < NB; ++u) kk[u] = warp_sort32(kk[u], lane);   // no guard for empty batches: straight-line code lets the
+                                                                         // eight shuffle networks interleave (a guarded version ran them
+                                                                         // one after the other: 4 us per step instead of ~1)
+#pragma unroll
+        for (int s = 1; s < NB; s <<= 1)
+#pragma unroll
+            for (int u = 0; u + s < NB; u += 2 * s) kk[u] = warp_merge_low32(kk[u], kk[u + s], lane);
+        run = warp_merge_low32(run, kk[0], lane);
+    }
+    return run;
+}
+
 __device__ __forceinline__ unsigned long long global_timer_ns()
 {
     unsigned long long t;
@@ -241,16 +290,11 @@ __device__ __forceinline__ void exchange_and_merge(const ScanArgs &a, Sel &sel, 
         for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) a.out_keys[j] = smem[j];
         __syncthreads();
     } else {
-        sel.init(a.k);
-        for (uint32_t b = (uint32_t)warp * 32; b < total; b += SCAN_WARPS * 32) {
-            uint64_t key = KEY_EMPTY;
-            if (b + lane < total) {
-                const uint32_t t = b + lane, r = t / k, j = t - r * k;
-                key = mine[(size_t)r * KM + j];
-            }
-            offer_lane_keys(sel, key, lane);
-        }
-        cta_reduce<false>(sel, smem, a.k, a.kpad, a.out_keys, warp, lane);
+        const uint64_t run = warp_fold_keys32(KEY_EMPTY, total, [&](uint64_t t) {
+            const uint32_t r = (uint32_t)t / k, j = (uint32_t)t - r * k;
+            return mine[(size_t)r * KM + j];
+        }, warp, lane);
+        cta_merge_lists32(run, smem, a.k, a.out_keys, warp, lane);
     }
 }
 
@@ -412,6 +456,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const Scan
     __shared__ bool is_last;
     if (a.run_if != nullptr && *reinterpret_cast<const volatile unsigned *>(a.run_if) == 0) return;   // CTA-uniform
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (a.timing && threadIdx.x == 0) a.timing[blockIdx.x * 4 + 0] = global_timer_ns();
     // k <= 32: per-warp register selector. k > 32: ONE candidate buffer per CTA (a.kpad = its capacity) + threshold
     using Sel = typename ScanSelOf<BIG>::type;
     __shared__ unsigned cb_cnt;
@@ -522,24 +567,27 @@ __global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const Scan
     }
 
     // ---- CTA top-k -> cand[blockIdx.x] ---------------------------------------------------
+    if (a.timing) { __syncthreads(); if (threadIdx.x == 0) a.timing[blockIdx.x * 4 + 1] = global_timer_ns(); }
     if constexpr (BIG) {
         sel.finish();
         uint64_t *dst = a.cand + (size_t)blockIdx.x * a.k;
         for (uint32_t j = threadIdx.x; j < a.k; j += blockDim.x) dst[j] = smem[j];
         __syncthreads();
     } else {
-        cta_reduce<false>(sel, smem, a.k, a.kpad, a.cand + (size_t)blockIdx.x * a.k, warp, lane);
+        cta_merge_lists32(sel.v, smem, a.k, a.cand + (size_t)blockIdx.x * a.k, warp, lane);   // the selector keeps v sorted by lane
     }
 
     // ---- last CTA merges all CTAs' results (threadfence-reduction pattern) ---------------
     __threadfence();
     if (threadIdx.x == 0) {
+        if (a.timing) a.timing[blockIdx.x * 4 + 2] = global_timer_ns();
         unsigned t = atomicAdd(a.ticket, 1u);
         is_last = (t == gridDim.x - 1);
     }
     __syncthreads();
     if (!is_last) return;
     __threadfence();
+    if (a.timing && threadIdx.x == 0) a.timing[gridDim.x * 4 + 0] = global_timer_ns();
 
     const uint64_t total = (uint64_t)gridDim.x * a.k;
     const volatile uint64_t *cand = a.cand;
@@ -583,33 +631,33 @@ __global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const Scan
             exchange_and_merge<true>(a, sel, smem, warp, lane);
         }
     } else {
-        sel.init(a.k);
-        for (uint64_t b = (uint64_t)warp * 32; b < total; b += SCAN_WARPS * 32) {
-            uint64_t key = (b + lane < total) ? cand[b + lane] : KEY_EMPTY;
-            offer_lane_keys(sel, key, lane);
-        }
-        if (warp == 0 && a.n_zero) {  // zero-norm rows: distance 0.0, ascending id; first k allowed suffice
+        // 2 x SMs lists of k keys: folded batch-wise into one sorted list per warp, then the CTA-wide merge tree (round 2:
+        // the data-dependent insertion loop this replaces took 9 us for 296 x 10 keys — CSGPU_SCAN_TIMING)
+        uint64_t run = warp_fold_keys32(KEY_EMPTY, total, [&](uint64_t t) { return cand[t]; }, warp, lane);
+        if (a.n_zero) {   // zero-norm rows: distance 0.0, ascending id; the first k allowed ones suffice (CTA-uniform loop)
             uint32_t found = 0;
-            for (uint32_t b = 0; b < a.n_zero && found < a.k; b += 32) {
+            for (uint32_t b = 0; b < a.n_zero && found < a.k; b += SCAN_WARPS * 32) {
                 uint64_t key = KEY_EMPTY;
-                if (b + lane < a.n_zero) {
-                    uint32_t id = a.zero_ids[b + lane];
-                    if (zero_row_allowed(a.bitmap, a.n_bits, a.tags, a.lang_mask, a.file_lo, a.file_hi, a.zero_ids, a.n_zero, b + lane))
-                        key = make_key(0.f, id);
-                }
-                found += __popc(__ballot_sync(FULL, key != KEY_EMPTY));
-                offer_lane_keys(sel, key, lane);
+                const uint32_t i = b + threadIdx.x;
+                if (i < a.n_zero && zero_row_allowed(a.bitmap, a.n_bits, a.tags, a.lang_mask, a.file_lo, a.file_hi, a.zero_ids, a.n_zero, i))
+                    key = make_key(0.f, a.zero_ids[i]);
+                found += __syncthreads_count(key != KEY_EMPTY);
+                run = warp_merge_low32(run, warp_sort32(key, lane), lane);
             }
         }
+        if (a.timing && threadIdx.x == 0) a.timing[gridDim.x * 4 + 1] = global_timer_ns();
         if (a.xchg == nullptr) {
-            cta_reduce<false>(sel, smem, a.k, a.kpad, a.out_keys, warp, lane);
+            cta_merge_lists32(run, smem, a.k, a.out_keys, warp, lane);
         } else {
             // local top-k stays in smem[0..k) (cand[0] is a scratch destination), then exchange + global merge
-            cta_reduce<false>(sel, smem, a.k, a.kpad, a.cand, warp, lane);
+            cta_merge_lists32(run, smem, a.k, a.cand, warp, lane);
             exchange_and_merge<false>(a, sel, smem, warp, lane);
         }
     }
-    if (threadIdx.x == 0) { a.ticket[0] = 0; a.ticket[1] = 0; }
+    if (threadIdx.x == 0) {
+        a.ticket[0] = 0; a.ticket[1] = 0;
+        if (a.timing) a.timing[gridDim.x * 4 + 2] = global_timer_ns();
+    }
 }
 
 // The fused exchange on its own (one CTA): this rank's sorted local top-k `local[0..k)` -> peer stores, flags, wait,
@@ -642,25 +690,24 @@ merge_keys_kernel(const uint64_t *__restrict__ keys, uint32_t n_lists, uint32_t 
 {
     extern __shared__ __align__(16) uint64_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    using Sel = typename SelOf<BIG>::type;
-    Sel sel;
-    if constexpr (BIG) {
-        sel.init(smem + (size_t)warp * kpad, smem + (size_t)(SCAN_WARPS + warp) * kpad, k, kpad, lane);
-    } else {
-        sel.init(k);
-    }
     const uint64_t total = (uint64_t)n_lists * k;
     const size_t list_stride = (size_t)gridDim.x * k, q_off = (size_t)blockIdx.x * k;
-    for (uint64_t b = (uint64_t)warp * 32; b < total; b += SCAN_WARPS * 32) {
-        uint64_t key = KEY_EMPTY;
-        if (b + lane < total) {
-            const uint64_t t = b + lane;
-            const uint64_t l = t / k, i = t - l * k;
-            key = keys[l * list_stride + q_off + i];
+    auto load = [&](uint64_t t) {
+        const uint64_t l = t / k, i = t - l * k;
+        return keys[l * list_stride + q_off + i];
+    };
+    if constexpr (!BIG) {
+        const uint64_t run = warp_fold_keys32(KEY_EMPTY, total, load, warp, lane);
+        cta_merge_lists32(run, smem, k, out + q_off, warp, lane);
+    } else {
+        WarpSelBig sel;
+        sel.init(smem + (size_t)warp * kpad, smem + (size_t)(SCAN_WARPS + warp) * kpad, k, kpad, lane);
+        for (uint64_t b = (uint64_t)warp * 32; b < total; b += SCAN_WARPS * 32) {
+            const uint64_t key = b + lane < total ? load(b + lane) : KEY_EMPTY;
+            offer_lane_keys(sel, key, lane);
         }
-        offer_lane_keys(sel, key, lane);
+        cta_reduce<true>(sel, smem, k, kpad, out + q_off, warp, lane);
     }
-    cta_reduce<BIG>(sel, smem, k, kpad, out + q_off, warp, lane);
 }
 
 // Device-side dedup of the per-variant lists of one user query (the HashMap + BinaryHeap pass at

@@ -65,6 +65,19 @@ __device__ __forceinline__ uint64_t warp_sort32(uint64_t v, int lane)
     return v;
 }
 
+// a, b: one key per lane, each ascending by lane -> the 32 smallest of the 64, ascending by lane. min(a[i], b[31 - i]) is a
+// bitonic sequence holding exactly those 32; five compare-exchange stages sort it.
+__device__ __forceinline__ uint64_t warp_merge_low32(uint64_t a, uint64_t b, int lane)
+{
+    uint64_t v = umin64(a, shfl64(b, 31 - lane));
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const uint64_t o = shfl64_xor(v, j);
+        v = ((lane & j) == 0) ? umin64(v, o) : umax64(v, o);
+    }
+    return v;
+}
+
 // ----------------------------------------------------------------------------------------
 // k <= 32: the warp's best 32 keys live one per lane, ascending; exact threshold after
 // every insertion. Insertion is 1 ballot + 2 shuffles; it only runs for rows that beat the
