@@ -269,14 +269,14 @@ static int enqueue_scan(const csgpu_index *ix, const Shard *sh, SearchCtx *c, co
     if (bitmap_dev != nullptr || pred != nullptr) {   // filtered: pre-filter variant (scan_filtered.cu)
         const uint64_t want32 = (sh->n_built + 32 * SCAN_WARPS - 1) / (32 * SCAN_WARPS);
         const uint32_t gridf = (uint32_t)std::min<uint64_t>((uint64_t)sh->sm_count * 2, std::max<uint64_t>(want32, 1));
-        const size_t smemf = big ? (size_t)a.kpad * sizeof(uint64_t) : (size_t)SCAN_WARPS * 32 * sizeof(uint64_t);
+        const size_t smemf = big ? (size_t)a.kpad * sizeof(uint64_t) : SCAN_SMALL_SMEM;
         cudaError_t ef = launch_scan_filtered(a, gridf, smemf, st);
         if (ef != cudaSuccess) return fail_cuda(ef, "scan_topk_kernel (filtered) launch", __FILE__, __LINE__);
         return CSGPU_OK;
     }
     uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sh->sm_count * 2, std::max<uint64_t>(want, 1));
     if (grid > MAX_GRID) grid = MAX_GRID;
-    const size_t smem = big ? (size_t)a.kpad * sizeof(uint64_t) : (size_t)SCAN_WARPS * 32 * sizeof(uint64_t);
+    const size_t smem = big ? (size_t)a.kpad * sizeof(uint64_t) : SCAN_SMALL_SMEM;
     cudaError_t e = !big ? launch_scan_b<false, 2>(a, grid, smem, st) : launch_scan_b<true, 2>(a, grid, smem, st);
     if (e != cudaSuccess) return fail_cuda(e, "scan_topk_kernel launch", __FILE__, __LINE__);
     return CSGPU_OK;
@@ -316,7 +316,7 @@ static int enqueue_exchange(SearchCtx *c, const uint64_t *local, uint32_t k, uin
     a.out_keys = out_keys;
     a.xchg = xchg;
     a.seq = seq;
-    const size_t smem = big ? (size_t)a.kpad * sizeof(uint64_t) : (size_t)SCAN_WARPS * 32 * sizeof(uint64_t);
+    const size_t smem = big ? (size_t)a.kpad * sizeof(uint64_t) : SCAN_SMALL_SMEM;
     if (big) exchange_keys_kernel<true><<<1, SCAN_THREADS, smem, st>>>(a, local);
     else exchange_keys_kernel<false><<<1, SCAN_THREADS, smem, st>>>(a, local);
     count_launch();

@@ -23,6 +23,9 @@ namespace csgpu {
 
 constexpr int SCAN_WARPS = 8;
 constexpr int SCAN_THREADS = SCAN_WARPS * 32;
+// dynamic shared memory of the k <= 32 scan kernels: [SCAN_WARPS * 32] keys for the merge trees + as many for the
+// last CTA's list of survivors (cta_topk_of_lists32)
+constexpr size_t SCAN_SMALL_SMEM = (size_t)2 * SCAN_WARPS * 32 * sizeof(uint64_t);
 
 // Cross-GPU exchange fused into the scan kernel (rank-per-GPU sharding). Every rank owns a
 // slot array + flags in its HBM that all peers can write over NVLink (cudaIpc-mapped, or plain pointers in
@@ -185,7 +188,7 @@ __device__ __forceinline__ void cta_merge_lists32(uint64_t v, uint64_t *smem, ui
         if (warp < half) smem[warp * 32 + lane] = v;
         __syncthreads();                       // ... before the survivors overwrite theirs
     }
-    if (warp == 0 && (uint32_t)lane < k) dst[lane] = v;
+    if (warp == 0 && dst != nullptr && (uint32_t)lane < k) dst[lane] = v;
     __syncthreads();
 }
 
@@ -193,10 +196,9 @@ __device__ __forceinline__ void cta_merge_lists32(uint64_t v, uint64_t *smem, ui
 // running sorted list: each batch is sorted across the warp (15 shuffle stages) and merged in (5) — no data-dependent
 // insertion loop. Eight batches per step: their loads are all in flight before the first one is used (one L2 round trip
 // per 2048 keys of the CTA instead of one per batch) and the eight independent sorts overlap their shuffle latencies.
-template <class F>
+template <int NB = 8, class F>
 __device__ __forceinline__ uint64_t warp_fold_keys32(uint64_t run, uint64_t n, F load, int warp, int lane)
 {
-    constexpr int NB = 8;
     for (uint64_t b0 = (uint64_t)warp * 32; b0 < n; b0 += (uint64_t)NB * SCAN_WARPS * 32) {
         uint64_t kk[NB];
 #pragma unroll
@@ -205,9 +207,7 @@ __device__ __forceinline__ uint64_t warp_fold_keys32(uint64_t run, uint64_t n, F
             kk[u] = i < n ? load(i) : KEY_EMPTY;
         }
 #pragma unroll
-        for (int u = 0; u < NB; ++u) kk[u] = warp_sort32(kk[u], lane);   // no guard for empty batches: straight-line code lets the
-                                                                         // eight shuffle networks interleave (a guarded version ran them
-                                                                         // one after the other: 4 us per step instead of ~1)
+        for (int u = 0; u < NB; ++u) kk[u] = warp_sort32(kk[u], lane);
 #pragma unroll
         for (int s = 1; s < NB; s <<= 1)
 #pragma unroll
@@ -215,6 +215,61 @@ __device__ __forceinline__ uint64_t warp_fold_keys32(uint64_t run, uint64_t n, F
         run = warp_merge_low32(run, kk[0], lane);
     }
     return run;
+}
+
+// The last CTA's job for k <= 32: L sorted lists of k keys (cand[c * k + j]) -> the best k, ascending, in dst[0..k) and
+// smem[0..32). Sorting every key costs ~2 shuffles per key and stage on the ONE SM this CTA runs on (measured: 7.6 us for
+// 296 x 10 keys, 19 us for 296 x 32 — shuffle-throughput bound), so the keys are filtered first: T = the k-th smallest of
+// the lists' MINIMA is an upper bound of the global k-th best (the minima are L distinct keys), and only keys <= T —
+// at least k, typically a few dozen, at most k per list of the k lists with the smallest minima — are collected
+// (ballot-compacted into shared memory) and sorted. More than 256 survivors (never seen; possible when fewer than k
+// lists are non-empty) fall back to folding everything. `extra` = this thread's optional extra key (zero-norm ids).
+// smem: [2 * SCAN_WARPS * 32] keys (SCAN_SMALL_SMEM).
+__device__ __forceinline__ void cta_topk_of_lists32(const volatile uint64_t *cand, uint32_t L, uint32_t k, uint64_t extra_run,
+                                                    uint64_t *smem, uint64_t *dst, int warp, int lane)
+{
+    __shared__ unsigned s_nsurv;
+    const uint64_t total = (uint64_t)L * k;
+    uint64_t *surv = smem + SCAN_WARPS * 32;
+    if (threadIdx.x == 0) s_nsurv = 0;
+    // 1. T: k-th smallest of the L minima
+    const uint64_t mins = warp_fold_keys32<2>(KEY_EMPTY, L, [&](uint64_t c) { return cand[c * k]; }, warp, lane);
+    cta_merge_lists32(mins, smem, 0, nullptr, warp, lane);
+    const uint64_t T = smem[k - 1];
+    __syncthreads();
+    // 2. survivors: keys <= T, four loads per thread in flight
+    for (uint64_t t0 = 0; t0 < total; t0 += 4 * SCAN_THREADS) {
+        uint64_t key[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint64_t t = t0 + (uint64_t)u * SCAN_THREADS + threadIdx.x;
+            key[u] = t < total ? cand[t] : KEY_EMPTY;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const bool pass = key[u] <= T && key[u] != KEY_EMPTY;
+            const unsigned m = __ballot_sync(FULL, pass);
+            if (m) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(&s_nsurv, (unsigned)__popc(m));
+                base = __shfl_sync(FULL, base, 0);
+                const unsigned pos = base + __popc(m & ((1u << lane) - 1u));
+                if (pass && pos < SCAN_WARPS * 32) surv[pos] = key[u];
+            }
+        }
+    }
+    __syncthreads();
+    const unsigned n = s_nsurv;
+    uint64_t run;
+    if (n <= SCAN_WARPS * 32) {   // one batch per warp
+        const unsigned i = warp * 32 + lane;
+        run = warp_sort32(i < n ? surv[i] : KEY_EMPTY, lane);
+    } else {
+        run = warp_fold_keys32<8>(KEY_EMPTY, total, [&](uint64_t t) { return cand[t]; }, warp, lane);
+    }
+    run = warp_merge_low32(run, extra_run, lane);
+    __syncthreads();
+    cta_merge_lists32(run, smem, k, dst, warp, lane);
 }
 
 __device__ __forceinline__ unsigned long long global_timer_ns()
@@ -631,10 +686,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const Scan
             exchange_and_merge<true>(a, sel, smem, warp, lane);
         }
     } else {
-        // 2 x SMs lists of k keys: folded batch-wise into one sorted list per warp, then the CTA-wide merge tree (round 2:
-        // the data-dependent insertion loop this replaces took 9 us for 296 x 10 keys — CSGPU_SCAN_TIMING)
-        uint64_t run = warp_fold_keys32(KEY_EMPTY, total, [&](uint64_t t) { return cand[t]; }, warp, lane);
-        if (a.n_zero) {   // zero-norm rows: distance 0.0, ascending id; the first k allowed ones suffice (CTA-uniform loop)
+        // zero-norm rows: distance 0.0, ascending id; the first k allowed ones suffice (CTA-uniform loop) -> one sorted list per warp
+        uint64_t zrun = KEY_EMPTY;
+        if (a.n_zero) {
             uint32_t found = 0;
             for (uint32_t b = 0; b < a.n_zero && found < a.k; b += SCAN_WARPS * 32) {
                 uint64_t key = KEY_EMPTY;
@@ -642,15 +696,17 @@ __global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const Scan
                 if (i < a.n_zero && zero_row_allowed(a.bitmap, a.n_bits, a.tags, a.lang_mask, a.file_lo, a.file_hi, a.zero_ids, a.n_zero, i))
                     key = make_key(0.f, a.zero_ids[i]);
                 found += __syncthreads_count(key != KEY_EMPTY);
-                run = warp_merge_low32(run, warp_sort32(key, lane), lane);
+                zrun = warp_merge_low32(zrun, warp_sort32(key, lane), lane);
             }
         }
-        if (a.timing && threadIdx.x == 0) a.timing[gridDim.x * 4 + 1] = global_timer_ns();
+        // 2 x SMs lists of k keys -> the best k (threshold from the lists' minima, survivors sorted; cta_topk_of_lists32)
         if (a.xchg == nullptr) {
-            cta_merge_lists32(run, smem, a.k, a.out_keys, warp, lane);
+            cta_topk_of_lists32(cand, gridDim.x, a.k, zrun, smem, a.out_keys, warp, lane);
+            if (a.timing && threadIdx.x == 0) a.timing[gridDim.x * 4 + 1] = global_timer_ns();
         } else {
             // local top-k stays in smem[0..k) (cand[0] is a scratch destination), then exchange + global merge
-            cta_merge_lists32(run, smem, a.k, a.cand, warp, lane);
+            cta_topk_of_lists32(cand, gridDim.x, a.k, zrun, smem, a.cand, warp, lane);
+            if (a.timing && threadIdx.x == 0) a.timing[gridDim.x * 4 + 1] = global_timer_ns();
             exchange_and_merge<false>(a, sel, smem, warp, lane);
         }
     }

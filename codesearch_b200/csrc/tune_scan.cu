@@ -18,12 +18,12 @@ struct Variant { std::string name; void (*launch)(const ScanArgs &, int sms, cud
 template <int R, int OCC, int LD>
 static void launch_ldg(const ScanArgs &a, int sms, cudaStream_t st)
 {
-    scan_topk_kernel<3, true, R, false, OCC, LD><<<sms * OCC, SCAN_THREADS, SCAN_WARPS * 32 * 8, st>>>(a);
+    scan_topk_kernel<3, true, R, false, OCC, LD><<<sms * OCC, SCAN_THREADS, SCAN_SMALL_SMEM, st>>>(a);
 }
 template <int R, int OCC, int LD>
 static void launch_ldg_static(const ScanArgs &a, int sms, cudaStream_t st)   // fixed-stride row split (DYN = false)
 {
-    scan_topk_kernel<3, true, R, false, OCC, LD, false, false><<<sms * OCC, SCAN_THREADS, SCAN_WARPS * 32 * 8, st>>>(a);
+    scan_topk_kernel<3, true, R, false, OCC, LD, false, false><<<sms * OCC, SCAN_THREADS, SCAN_SMALL_SMEM, st>>>(a);
 }
 template <int TILE, int STAGES>
 static void launch_tma(const ScanArgs &a, int sms, cudaStream_t st)
