@@ -49,6 +49,8 @@ class Stats(ctypes.Structure):
         ("byte_fallbacks", ctypes.c_uint64),
         ("byte_candidates", ctypes.c_uint64),
         ("byte_rescored", ctypes.c_uint64),
+        ("batch_route", ctypes.c_uint32),
+        ("filter_max_err", ctypes.c_float),
     ]
 
 

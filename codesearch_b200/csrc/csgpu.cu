@@ -1571,7 +1571,8 @@ int csgpu_search_batch(const csgpu_index *ix, const float *q, uint32_t q_len, ui
     for (const Shard *sh : ix->shards) prefilter = prefilter && (sh->shadow_valid || sh->n_built == 0);
     // where the multi-query scan cannot serve (dim % 128 != 0 or k > 256) the alternative is one 2 ms scan per query,
     // which a 128-query SIMT block (20 ms) beats from ~10 queries on
-    static const uint32_t env_min = [] { const char *e = getenv("CSGPU_GEMM_MIN_BATCH"); return e && *e ? (uint32_t)atoi(e) : 0u; }();   // tuning runs
+    const char *env_s = getenv("CSGPU_GEMM_MIN_BATCH");   // tuning runs and tests; read per call
+    const uint32_t env_min = env_s && *env_s ? (uint32_t)atoi(env_s) : 0u;
     const uint32_t gemm_min = env_min ? env_min : (multi_scan_supported(ix->dim4, k) ? GEMM_MIN_BATCH : GEMM_MIN_BATCH_NO_MULTI);
     if ((b >= gemm_min || (prefilter && b >= PREFILTER_MIN_BATCH)) && batch_gemm_available(ix)) {
         std::vector<uint32_t> zero_q;
@@ -2007,6 +2008,8 @@ int csgpu_stats(const csgpu_index *ix, csgpu_stats_t *out)
     out->byte_fallbacks = ix->byte_fallbacks.load();
     out->byte_candidates = ix->byte_candidates.load();
     out->byte_rescored = ix->byte_rescored.load();
+    out->batch_route = ix->batch_route.load();
+    out->filter_max_err = ix->filter_max_err.load();
     return CSGPU_OK;
 }
 

@@ -191,7 +191,7 @@ gemm_simt_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 
 // ---- query prep: fp32 [b][dim] -> unit length (f64 norm, as csgpu_build does for rows) -> [b_pad][dim_pad]
 // (rows >= b and columns >= dim are zero). flags[q] = 1 if the query has zero norm.
-static __global__ void prep_queries_f32_kernel(const float *__restrict__ q, uint32_t b, uint32_t dim, uint32_t dim_pad,
+static __global__ void prep_queries_f32_kernel(const float *__restrict__ q, uint32_t q_pitch, uint32_t b, uint32_t dim, uint32_t dim_pad,
                                                float *__restrict__ out, uint32_t b_pad, uint8_t *__restrict__ flags,
                                                float *__restrict__ thr, unsigned *__restrict__ count)
 {
@@ -204,13 +204,13 @@ static __global__ void prep_queries_f32_kernel(const float *__restrict__ q, uint
         return;
     }
     double ss = 0.0;
-    for (uint32_t c = lane; c < dim; c += 32) { const float x = q[(size_t)w * dim + c]; ss += (double)x * x; }
+    for (uint32_t c = lane; c < dim; c += 32) { const float x = q[(size_t)w * q_pitch + c]; ss += (double)x * x; }
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) ss += __shfl_xor_sync(FULL, ss, m);
     const bool zero = !(ss > 0.0);
     const double inv = zero ? 0.0 : 1.0 / sqrt(ss);
     for (uint32_t c = lane; c < dim_pad; c += 32)
-        out[(size_t)w * dim_pad + c] = c < dim ? (float)(q[(size_t)w * dim + c] * inv) : 0.f;
+        out[(size_t)w * dim_pad + c] = c < dim ? (float)(q[(size_t)w * q_pitch + c] * inv) : 0.f;
     if (lane == 0) { flags[w] = zero ? 1 : 0; thr[w] = zero ? -1.f : __int_as_float(0x7f800000); count[w] = 0; }
 }
 

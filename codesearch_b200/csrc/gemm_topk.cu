@@ -13,6 +13,7 @@
 #include "index.h"
 #include "gemm_simt.cuh"
 #include "gemm_topk.cuh"
+#include "gemm_tf32.cuh"
 #include "rescore.cuh"
 #include "scan.cuh"
 #include "synth.cuh"
@@ -23,12 +24,28 @@ constexpr uint32_t BF_CAP = 8192;          // candidate slots per query
 constexpr uint32_t BF_MAX_QBLOCKS = 8;     // 1024 queries per pass
 constexpr uint32_t BF_PHASE_GROWTH = 8;
 
-// tensor-core contraction: the bf16 index itself, or the bf16 shadow of an fp32 index (rescore.cuh)
-static bool tc_path(const csgpu_index *ix, const Shard *sh)
+// Which contraction answers a batch on this shard:
+//   TC_BF16  tcgen05 kind::f16 over bf16 rows — the bf16 index itself, or the bf16 shadow of an fp32 index (opt-in tensor
+//            prefilter, rescore.cuh);
+//   TC_TF32  tcgen05 kind::tf32 straight off the fp32 rows (gemm_tf32.cuh) — the DEFAULT for an fp32 index (round 2): a
+//            filter, rescored exactly, so results stay bit-identical to csgpu_search;
+//   SIMT     the register-tiled FP32 kernel (gemm_simt.cuh): dim > 1024, or CSGPU_BATCH_SIMT=1 (A/B runs, tests).
+enum class Contraction { SIMT, TC_BF16, TC_TF32 };
+static bool simt_forced()
 {
-    return ix->dtype == CSGPU_DTYPE_BF16 || (ix->tensor_prefilter && sh->shadow_valid);
+    const char *e = getenv("CSGPU_BATCH_SIMT");   // read per batch (not cached): tests flip it inside one process
+    return e != nullptr && e[0] == '1';
 }
+static Contraction contraction_of(const csgpu_index *ix, const Shard *sh)
+{
+    if (ix->dtype == CSGPU_DTYPE_BF16 || (ix->tensor_prefilter && sh->shadow_valid)) return Contraction::TC_BF16;
+    if (ix->dim_pad <= TF_MAX_DIM && !simt_forced()) return Contraction::TC_TF32;
+    return Contraction::SIMT;
+}
+static bool tc_path(const csgpu_index *ix, const Shard *sh) { return contraction_of(ix, sh) != Contraction::SIMT; }
 static bool rescore_path(const csgpu_index *ix, const Shard *sh) { return ix->dtype == CSGPU_DTYPE_F32 && tc_path(ix, sh); }
+// query rows the tf32 kernel loads per K chunk: all 128 of a block, or only the (8-row groups of) queries there are
+static uint32_t tf32_q_rows(uint32_t nq) { return nq >= (uint32_t)GT_BLOCK_M ? (uint32_t)GT_BLOCK_M : std::max<uint32_t>(8, (nq + 7) & ~7u); }
 
 // ---------------------------------------------------------------------------------------------
 // kernels local to this file
@@ -297,7 +314,7 @@ static int batch_ctx(const csgpu_index *ix, Shard *sh, BatchCtx **out)
     sh->batch = c;
     const size_t nq = (size_t)BF_MAX_QBLOCKS * GT_BLOCK_M;
     CS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CS_CUDA(cudaMalloc(&c->q_f32, nq * ix->dim * sizeof(float)));
+    CS_CUDA(cudaMalloc(&c->q_f32, nq * ix->dim_pad * sizeof(float)));   // raw queries, row pitch dim_pad (zero-padded like the scan kernel's query)
     CS_CUDA(cudaMalloc(&c->q_prep, nq * ix->dim_pad * sizeof(float)));   // bf16 uses half of it
     CS_CUDA(cudaMalloc(&c->flags, nq));
     CS_CUDA(cudaMalloc(&c->thr, nq * sizeof(float)));
@@ -307,7 +324,7 @@ static int batch_ctx(const csgpu_index *ix, Shard *sh, BatchCtx **out)
     CS_CUDA(cudaMalloc(&c->out, nq * CSGPU_MAX_K * sizeof(uint64_t)));
     CS_CUDA(cudaMalloc(&c->scalar, 64));
     CS_CUDA(cudaMalloc(&c->seg_count, nq * 2 * 148 * sizeof(unsigned)));
-    CS_CUDA(cudaHostAlloc(&c->q_pin, nq * ix->dim * sizeof(float), cudaHostAllocDefault));
+    CS_CUDA(cudaHostAlloc(&c->q_pin, nq * ix->dim_pad * sizeof(float), cudaHostAllocDefault));
     CS_CUDA(cudaHostAlloc(&c->out_pin, nq * CSGPU_MAX_K * sizeof(uint64_t) + nq, cudaHostAllocDefault));
     *out = c;
     return CSGPU_OK;
@@ -368,7 +385,23 @@ static int launch_gemm(const csgpu_index *ix, Shard *sh, BatchCtx *c, const CUte
     a.seg_count = c->seg_count;
     a.overflow = c->scalar;
     cudaError_t e = cudaSuccess;
-    if (tc_path(ix, sh)) {
+    const Contraction con = contraction_of(ix, sh);
+    if (con == Contraction::TC_TF32) {
+        a.n_kchunks = (ix->dim_pad + TF_BLOCK_K - 1) / TF_BLOCK_K;
+        a.q_rows = n_qblocks == 1 ? tf32_q_rows(nq) : (uint32_t)GT_BLOCK_M;
+        constexpr int STAGES = 4;   // 4 x 48 KB
+        const size_t smem = (size_t)STAGES * TF_STAGE_BYTES + 1024;
+        const uint32_t grid = lay.groups * n_qblocks;
+        const uint32_t halves = tc_epi_halves();
+        const uint32_t threads = 64 + 128 * halves;
+        if (halves == 2) {
+            e = cudaFuncSetAttribute(gemm_tf32_topk_kernel<STAGES, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) gemm_tf32_topk_kernel<STAGES, 2><<<grid, threads, smem, c->stream>>>(map_q, sh->map_c2, a);
+        } else {
+            e = cudaFuncSetAttribute(gemm_tf32_topk_kernel<STAGES, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) gemm_tf32_topk_kernel<STAGES, 1><<<grid, threads, smem, c->stream>>>(map_q, sh->map_c2, a);
+        }
+    } else if (con == Contraction::TC_BF16) {
         const CUtensorMap &map_rows = ix->dtype == CSGPU_DTYPE_BF16 ? sh->map_c : sh->map_shadow;
         a.n_kchunks = ix->dim / GT_BLOCK_K;
         const size_t q_bytes = (size_t)a.n_kchunks * GT_QCHUNK_BYTES;
@@ -428,6 +461,8 @@ static int launch_select(const csgpu_index *ix, Shard *sh, BatchCtx *c, uint32_t
     sa.final_out = final ? c->out : nullptr;
     sa.rows = reinterpret_cast<const float4 *>(sh->rows); sa.dim4 = ix->dim4; sa.q_raw = c->q_f32;
     sa.n_rescored = reinterpret_cast<unsigned long long *>(c->scalar + 2);
+    sa.margin = contraction_of(ix, sh) == Contraction::TC_TF32 ? TF_MARGIN : TC_MARGIN;
+    sa.max_err = c->scalar + 4;
     cudaError_t e = cudaSuccess;
     if (rescore_path(ix, sh)) {   // exact fp32 rescoring of the tensor-core filter's survivors (rescore.cuh)
         const size_t smem = (size_t)(SEL_BUF + 1024) * sizeof(uint64_t);
@@ -439,7 +474,10 @@ static int launch_select(const csgpu_index *ix, Shard *sh, BatchCtx *c, uint32_t
         if (e == cudaSuccess) select_sorted_kernel<v, ex, true><<<nq_pad, SCAN_THREADS, smem, c->stream>>>(sa);               \
     } while (0)
 #define CS_RSV(v) case v: if (exact) CS_RS(v, true); else CS_RS(v, false); break;
-        switch (V) { CS_RSV(1) CS_RSV(2) CS_RSV(3) CS_RSV(4) default: return fail(CSGPU_ERR_ARG, "tensor prefilter: unsupported dim"); }
+        switch (V) {
+            CS_RSV(1) CS_RSV(2) CS_RSV(3) CS_RSV(4) CS_RSV(5) CS_RSV(6) CS_RSV(7) CS_RSV(8)
+            default: return fail(CSGPU_ERR_ARG, "tensor-core filter: unsupported dim");
+        }
 #undef CS_RSV
 #undef CS_RS
     } else {
@@ -492,26 +530,35 @@ static int batch_search_shard(const csgpu_index *ix, Shard *sh, BatchCtx *c, con
                               const uint8_t **flags_out)
 {
     DeviceGuard g(sh->device);
-    const bool bf16 = tc_path(ix, sh);   // queries go to the tensor cores as bf16
+    const Contraction con = contraction_of(ix, sh);
+    const bool bf16 = con == Contraction::TC_BF16;   // queries go to the tensor cores as bf16
     uint32_t n_qblocks = (nq + GT_BLOCK_M - 1) / GT_BLOCK_M;
     static const bool pad_even = getenv("CSGPU_BF16_2CTA") && atoi(getenv("CSGPU_BF16_2CTA")) != 0;
     if (pad_even && ix->dtype == CSGPU_DTYPE_BF16 && n_qblocks >= 2 && (n_qblocks & 1)) ++n_qblocks;   // CTA pairs take two query blocks each
     const uint32_t nq_pad = n_qblocks * GT_BLOCK_M;
     CS_CUDA(cudaMemsetAsync(c->scalar, 0, 64, c->stream));
-    memcpy(c->q_pin, q_host, (size_t)nq * ix->dim * sizeof(float));
-    CS_CUDA(cudaMemcpyAsync(c->q_f32, c->q_pin, (size_t)nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    // raw queries on the device with a row pitch of dim_pad floats, zero-padded: what scan_topk_kernel is given, so the
+    // rescoring prologue (select_sorted_kernel) normalises exactly the same numbers
+    if (ix->dim_pad == ix->dim) {
+        memcpy(c->q_pin, q_host, (size_t)nq * ix->dim * sizeof(float));
+    } else {
+        memset(c->q_pin, 0, (size_t)nq * ix->dim_pad * sizeof(float));
+        for (uint32_t j = 0; j < nq; ++j) memcpy(c->q_pin + (size_t)j * ix->dim_pad, q_host + (size_t)j * ix->dim, (size_t)ix->dim * sizeof(float));
+    }
+    CS_CUDA(cudaMemcpyAsync(c->q_f32, c->q_pin, (size_t)nq * ix->dim_pad * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     // query prep also initialises the per-query threshold (+inf, or -1 for padding / zero-norm queries) and candidate count
     if (bf16)
-        prep_queries_bf16_kernel<<<(nq_pad * 32 + 255) / 256, 256, 0, c->stream>>>(c->q_f32, nq, ix->dim, reinterpret_cast<__nv_bfloat16 *>(c->q_prep), nq_pad, c->flags, c->thr, c->count);
+        prep_queries_bf16_kernel<<<(nq_pad * 32 + 255) / 256, 256, 0, c->stream>>>(c->q_f32, nq, ix->dim /* == dim_pad: bf16 kernels need dim % 64 == 0 */, reinterpret_cast<__nv_bfloat16 *>(c->q_prep), nq_pad, c->flags, c->thr, c->count);
     else
-        prep_queries_f32_kernel<<<(nq_pad * 32 + 255) / 256, 256, 0, c->stream>>>(c->q_f32, nq, ix->dim, ix->dim_pad, reinterpret_cast<float *>(c->q_prep), nq_pad, c->flags, c->thr, c->count);
+        prep_queries_f32_kernel<<<(nq_pad * 32 + 255) / 256, 256, 0, c->stream>>>(c->q_f32, ix->dim_pad, nq, ix->dim, ix->dim_pad, reinterpret_cast<float *>(c->q_prep), nq_pad, c->flags, c->thr, c->count);
     count_launch();
     uint8_t *flags_host = reinterpret_cast<uint8_t *>(c->out_pin) + (size_t)BF_MAX_QBLOCKS * GT_BLOCK_M * CSGPU_MAX_K * sizeof(uint64_t);
     CS_CUDA(cudaMemcpyAsync(flags_host, c->flags, nq, cudaMemcpyDeviceToHost, c->stream));
     CS_CUDA(cudaStreamSynchronize(c->stream));
     *flags_out = flags_host;
     CUtensorMap map_q;
-    const uint32_t q_box = (!bf16 && simt_small(nq)) ? (uint32_t)GS_BM_SMALL : (uint32_t)GT_BLOCK_M;
+    const uint32_t q_box = con == Contraction::TC_TF32 ? (n_qblocks == 1 ? tf32_q_rows(nq) : (uint32_t)GT_BLOCK_M)
+                           : (!bf16 && simt_small(nq)) ? (uint32_t)GS_BM_SMALL : (uint32_t)GT_BLOCK_M;
     int rc = make_map(&map_q, c->q_prep, nq_pad, bf16 ? ix->dim : ix->dim_pad, q_box, !bf16);
     if (rc) return rc;
 
@@ -571,10 +618,16 @@ static int batch_search_shard(const csgpu_index *ix, Shard *sh, BatchCtx *c, con
         }
         if (any) CS_CUDA(cudaStreamSynchronize(c->stream));
     }
+    ix->batch_route.store(con == Contraction::TC_TF32 ? CSGPU_ROUTE_TC_TF32 : con == Contraction::TC_BF16 ? CSGPU_ROUTE_TC_BF16 : CSGPU_ROUTE_SIMT_F32);
     if (rescore_path(ix, sh)) {
+        unsigned st[4] = {0, 0, 0, 0};   // [0..1] rows rescored (u64), [2] float bits of the largest |d_filter - d_f32|
+        CS_CUDA(cudaMemcpy(st, c->scalar + 2, 3 * sizeof(unsigned), cudaMemcpyDeviceToHost));
         unsigned long long nres = 0;
-        CS_CUDA(cudaMemcpy(&nres, c->scalar + 2, sizeof nres, cudaMemcpyDeviceToHost));
+        memcpy(&nres, st, sizeof nres);
         ix->prefilter_rescored.fetch_add(nres);   // summed over the shards of a multi-device index (reset per chunk by batch_search)
+        float err = 0.f, seen = ix->filter_max_err.load();
+        memcpy(&err, st + 2, sizeof err);
+        while (err > seen && !ix->filter_max_err.compare_exchange_weak(seen, err)) {}
     }
     return CSGPU_OK;
 }
@@ -616,6 +669,7 @@ int batch_search(const csgpu_index *ix, const float *q, uint32_t b, uint32_t k,
     for (uint32_t j = 0; j < b && !rc; j += chunk) {
         const uint32_t nq = std::min(chunk, b - j);
         ix->prefilter_rescored.store(0);
+        ix->filter_max_err.store(0.f);
         std::vector<const uint8_t *> flags(G, nullptr);
         if (G == 1) {
             rc = batch_search_shard(ix, sh0, c0, q + (size_t)j * ix->dim, nq, k, &flags[0]);

@@ -66,6 +66,7 @@ struct GemmTopkArgs {
     unsigned *seg_count = nullptr;   // [QB*128][n_seg], WRITTEN (not accumulated) by every launch
     unsigned *overflow = nullptr;    // set to 1 when a segment would overflow
     uint32_t stride = 0, seg_len = 0, n_seg = 0;
+    uint32_t q_rows = GT_BLOCK_M;    // tf32 kernel: query rows per chunk load (gemm_tf32.cuh)
 };
 
 // ---- tcgen05 wrappers ---------------------------------------------------------------------

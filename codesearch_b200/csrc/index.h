@@ -223,6 +223,8 @@ struct csgpu_index {
     uint64_t nonfinite_rows = 0;
     uint64_t tombstones = 0;
     mutable std::atomic<float> last_search_us{0.f};
+    mutable std::atomic<uint32_t> batch_route{0};          // CSGPU_ROUTE_* of the last GEMM-shaped batch
+    mutable std::atomic<float> filter_max_err{0.f};        // largest |d_filter - d_f32| its rescoring saw
     mutable std::atomic<uint64_t> prefilter_rescored{0};   // fp32 rows read by the last tensor-prefilter batch chunk
     bool byte_prefilter = false;          // csgpu_set_byte_prefilter: csgpu_search streams an int8 shadow + exact fp32 rescoring
     mutable std::atomic<uint64_t> byte_searches{0}, byte_fallbacks{0}, byte_candidates{0}, byte_rescored{0};

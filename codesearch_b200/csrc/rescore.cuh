@@ -64,6 +64,8 @@ struct SelectArgs {
     uint32_t dim4;
     const float *q_raw;        // [nq][dim4*4] raw queries (normalised in the prologue, exactly like the scan kernel)
     unsigned long long *n_rescored;   // statistics: rows actually read
+    float margin;              // proven bound of |d_filter - d_f32|: TC_MARGIN (bf16 shadow) or TF_MARGIN (tf32 off the fp32 rows, gemm_tf32.cuh)
+    unsigned *max_err;         // optional statistics: float bits of the largest |d_filter - d_f32| seen (atomicMax on non-negative floats)
 };
 
 constexpr uint32_t SEL_BUF = 8192;                       // sort buffer (keys) = the largest bitonic sort a query needs
@@ -76,7 +78,7 @@ template <int V, bool EXACT>
 __device__ __forceinline__ unsigned rescore_range(const SelectArgs &a, const float4 (&qv)[V], uint64_t *C, uint32_t lo, uint32_t hi,
                                                   uint32_t bound32, int warp, int lane)
 {
-    constexpr int R = 4;
+    constexpr int R = V <= 4 ? 4 : 2;   // rows in flight per warp (registers: R x V float4)
     unsigned read_rows = 0;
     for (uint32_t i0 = lo + (uint32_t)warp * R; i0 < hi; i0 += SCAN_WARPS * R) {
         uint32_t row[R];
@@ -88,7 +90,7 @@ __device__ __forceinline__ unsigned rescore_range(const SelectArgs &a, const flo
             live[r] = false;
             if (key != KEY_EMPTY) {
                 const float d_tc = __uint_as_float(bits_from_okey((uint32_t)(key >> 32)));
-                live[r] = okey(d_tc - TC_MARGIN) <= bound32;
+                live[r] = okey(d_tc - a.margin) <= bound32;
             }
             row[r] = (uint32_t)key;
         }
@@ -116,7 +118,13 @@ __device__ __forceinline__ unsigned rescore_range(const SelectArgs &a, const flo
             }
             acc = warp_sum_tree(acc);
             const float dist = fmaf(-0.5f, acc, 0.5f);
-            if (i0 + r < hi && lane == 0) C[i0 + r] = live[r] ? make_key(dist, idv[r]) : KEY_EMPTY;
+            if (i0 + r < hi && lane == 0) {
+                if (a.max_err != nullptr && live[r]) {
+                    const float d_tc = __uint_as_float(bits_from_okey((uint32_t)(C[i0 + r] >> 32)));
+                    atomicMax(a.max_err, __float_as_uint(fabsf(d_tc - dist)));
+                }
+                C[i0 + r] = live[r] ? make_key(dist, idv[r]) : KEY_EMPTY;
+            }
             read_rows += live[r] ? 1u : 0u;
         }
     }
@@ -125,7 +133,7 @@ __device__ __forceinline__ unsigned rescore_range(const SelectArgs &a, const flo
 
 // dynamic smem: C[SEL_BUF] | S[1024]   (u64 each; S only when RESCORE) — 72 KB, three CTAs per SM
 template <int V, bool EXACT, bool RESCORE>
-__global__ void __launch_bounds__(SCAN_THREADS, 3) select_sorted_kernel(const SelectArgs a)
+__global__ void __launch_bounds__(SCAN_THREADS, (V <= 4 ? 3 : 2)) select_sorted_kernel(const SelectArgs a)
 {
     extern __shared__ __align__(16) uint64_t smem[];
     __shared__ unsigned s_n, s_pref[2 * 148 + 8], s_end, s_bound;
@@ -238,7 +246,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) select_sorted_kernel(const Se
         // stage B: the sorted prefix that can still beat T_A
         for (uint32_t t = a_end + threadIdx.x; t < n_c; t += blockDim.x) {
             const float d_tc = __uint_as_float(bits_from_okey((uint32_t)(C[t] >> 32)));
-            if (okey(d_tc - TC_MARGIN) > bound_a) atomicMin(&s_end, t);
+            if (okey(d_tc - a.margin) > bound_a) atomicMin(&s_end, t);
         }
         __syncthreads();
         const uint32_t b_end = s_end;
@@ -268,7 +276,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) select_sorted_kernel(const Se
         while (m > 0 && C[m - 1] == KEY_EMPTY) --m;   // dropped candidates sort to the end
         a.count[q] = m;
         float t = __int_as_float(0x7f800000);  // +inf: everything passes until k rows are known
-        if (m >= k) t = __uint_as_float(bits_from_okey((uint32_t)(C[k - 1] >> 32))) + (RESCORE ? TC_MARGIN : 0.f);
+        if (m >= k) t = __uint_as_float(bits_from_okey((uint32_t)(C[k - 1] >> 32))) + (RESCORE ? a.margin : 0.f);
         a.thr[q] = t;
     }
 }

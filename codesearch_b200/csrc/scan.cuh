@@ -644,7 +644,6 @@ __global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const Scan
     __threadfence();
     if (a.timing && threadIdx.x == 0) a.timing[gridDim.x * 4 + 0] = global_timer_ns();
 
-    const uint64_t total = (uint64_t)gridDim.x * a.k;
     const volatile uint64_t *cand = a.cand;
     if constexpr (BIG) {
         sel.reset();

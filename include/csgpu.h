@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define CSGPU_ABI_VERSION 6
+#define CSGPU_ABI_VERSION 7
 
 enum {
     CSGPU_OK            = 0,
@@ -83,7 +83,12 @@ typedef struct csgpu_stats_t {
     uint64_t byte_fallbacks;     /* ... of which this many were answered again by the fp32 scan kernel       */
     uint64_t byte_candidates;    /* last such search: rows that reached the final candidate list             */
     uint64_t byte_rescored;      /* last such search: fp32 rows read for the exact rescoring                 */
+    uint32_t batch_route;        /* contraction of the last GEMM-shaped batch: CSGPU_ROUTE_* (0 until one ran)          */
+    float    filter_max_err;     /* largest |d_filter - d_f32| the rescoring of that batch saw (tensor-core filters)     */
 } csgpu_stats_t;
+
+/* csgpu_stats_t.batch_route */
+enum { CSGPU_ROUTE_NONE = 0, CSGPU_ROUTE_SIMT_F32 = 1, CSGPU_ROUTE_TC_BF16 = 2, CSGPU_ROUTE_TC_TF32 = 3 };
 
 /* ---- lifecycle (VectorStore::new / open_readonly  store.rs:110-176,183-250) ------------ */
 

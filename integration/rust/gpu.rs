@@ -18,7 +18,7 @@ use std::ffi::{CStr, CString};
 use std::os::raw::{c_char, c_int, c_void};
 use std::path::Path;
 
-pub const CSGPU_ABI_VERSION: u32 = 6;
+pub const CSGPU_ABI_VERSION: u32 = 7;
 pub const CSGPU_OK: c_int = 0;
 pub const CSGPU_ERR_DIM: c_int = 1; // "Query embedding dimension mismatch: expected {}, got {}"   store.rs:432-438
 pub const CSGPU_ERR_NOT_BUILT: c_int = 2; // "Index not built. Call build_index() after inserting chunks."   store.rs:440-444
@@ -66,6 +66,10 @@ pub struct CsgpuStats {
     pub byte_fallbacks: u64,
     pub byte_candidates: u64,
     pub byte_rescored: u64,
+    /// contraction of the last GEMM-shaped batch: 0 none, 1 fp32 SIMT, 2 tcgen05 bf16, 3 tcgen05 tf32 off the fp32 rows
+    pub batch_route: u32,
+    /// largest |d_filter - d_f32| the exact rescoring of that batch saw
+    pub filter_max_err: f32,
 }
 
 /// `csgpu_predicate_t`: a row passes iff its language bit is set AND file_lo <= file_id <= file_hi AND (file_bitmap is

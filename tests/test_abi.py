@@ -24,13 +24,13 @@ def test_header_symbols_all_exported_and_bound():
         assert hasattr(lib, n), f"libcsgpu.so does not export {n}"
         assert n in _lib.SIGNATURES, f"{n} is declared in csgpu.h but not bound in _lib.SIGNATURES"
     assert set(_lib.SIGNATURES) == set(names)
-    assert lib.csgpu_abi_version() == 6
+    assert lib.csgpu_abi_version() == 7
 
 
 def test_stats_struct_layout_matches_header():
     from codesearch_b200 import _lib
     # 6 u64 + 4 u32 + f32 + u32 + 8 u64
-    assert ctypes.sizeof(_lib.Stats) == 6 * 8 + 4 * 4 + 4 + 4 + 8 * 8 + 4 * 8 + 5 * 8   # ... + coalesced_passes, coalesced_queries, prefilter_rescored, shadow_bytes + 5 byte-prefilter counters
+    assert ctypes.sizeof(_lib.Stats) == 6 * 8 + 4 * 4 + 4 + 4 + 8 * 8 + 4 * 8 + 5 * 8 + 4 + 4   # ... + coalesced_passes, coalesced_queries, prefilter_rescored, shadow_bytes + 5 byte-prefilter counters + batch_route, filter_max_err
 
 
 def test_decode_keys_is_pure_host():
