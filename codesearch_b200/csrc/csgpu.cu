@@ -1555,6 +1555,37 @@ int csgpu_get_tags(const csgpu_index *ix, const uint32_t *ids, uint64_t n, uint3
     return CSGPU_OK;
 }
 
+// fp32 index, tf32 route available: does the tensor-core filter (+ exact rescoring) beat the scan kernels for b queries?
+// A cost model fitted to measurements on one B200 (profiles/r02_tf32_probe_*.txt), times in us, sizes in MB per device:
+//   tensor-core route  ~230 us fixed (query prep, 3-5 phases of contraction + select, three host round trips) + one pass over
+//                      the rows at ~6.4 TB/s per <= 128 queries; above, every further 128-query block re-reads the row tiles
+//                      from L2 (1024 queries: 12.0 ms at 15.36 GB);
+//   multi-query scan   one launch (~45 us) per pass of <= 16 queries: <= 8 queries stream at ~5.6 TB/s, 9-16 at ~3.4 TB/s;
+//   single-query scan  ~30 us + the rows at ~7.2 TB/s.
+// At 10M x 384 the tensor cores win from 2 queries on (2.36 vs 2.51 ms; 16 queries: 2.4 vs 4.6 ms); at the reference's own
+// scale (100k rows, src/constants.rs:93-95) a handful of query variants stays one multi-query launch.
+static bool tf32_route_is_faster(const csgpu_index *ix, uint32_t b, uint32_t k)
+{
+    if (b < 2) return false;
+    uint64_t rows = 0;
+    for (const Shard *sh : ix->shards) rows = std::max<uint64_t>(rows, sh->n_built);
+    const double mb = (double)rows * ix->dim_pad * sizeof(float) / 1e6;
+    const uint32_t nqb = (b + 127) / 128;
+    const double t_tc = 230.0 + mb / 6.4 * (nqb == 1 ? 1.0 : 0.3 + 0.57 * nqb);
+    double t_scan = 0.0;
+    if (multi_scan_supported(ix->dim4, k)) {
+        const uint32_t MQ = multi_scan_max_queries();
+        for (uint32_t j = 0; j < b; j += MQ) {
+            const uint32_t nq = std::min(MQ, b - j);
+            t_scan += nq == 1 ? 30.0 + mb / 7.2 : 45.0 + mb / (nq <= 8 ? 5.6 : 3.4) * (k > 32 ? 1.1 : 1.0);
+        }
+    } else {
+        t_scan = b * (30.0 + mb / 7.2);
+    }
+    if (i8_eligible(ix, k)) t_scan = std::min(t_scan, b * (60.0 + mb / 4.0 / 6.5));   // byte prefilter on: int8 singles, a quarter of the bytes each
+    return t_tc < t_scan;
+}
+
 int csgpu_search_batch(const csgpu_index *ix, const float *q, uint32_t q_len, uint32_t b, uint32_t k,
                        uint32_t *out_ids, float *out_dist, uint32_t *out_n)
 {
@@ -1574,7 +1605,10 @@ int csgpu_search_batch(const csgpu_index *ix, const float *q, uint32_t q_len, ui
     const char *env_s = getenv("CSGPU_GEMM_MIN_BATCH");   // tuning runs and tests; read per call
     const uint32_t env_min = env_s && *env_s ? (uint32_t)atoi(env_s) : 0u;
     const uint32_t gemm_min = env_min ? env_min : (multi_scan_supported(ix->dim4, k) ? GEMM_MIN_BATCH : GEMM_MIN_BATCH_NO_MULTI);
-    if ((b >= gemm_min || (prefilter && b >= PREFILTER_MIN_BATCH)) && batch_gemm_available(ix)) {
+    // round 2: without a shadow the GEMM-shaped route is the tf32 tensor-core filter straight off the fp32 rows (gemm_tf32.cuh),
+    // which takes over wherever the cost model says so — from 2 queries on at 10M rows
+    const bool tf32 = !prefilter && !env_min && batch_tf32_route(ix) && tf32_route_is_faster(ix, b, k);
+    if ((b >= gemm_min || tf32 || (prefilter && b >= PREFILTER_MIN_BATCH)) && batch_gemm_available(ix)) {
         std::vector<uint32_t> zero_q;
         rc = batch_search(ix, q, b, k, out_ids, out_dist, out_n, &zero_q);
         for (size_t z = 0; z < zero_q.size() && !rc; ++z) {   // zero-norm queries: distance 0.0 everywhere (scan kernel)
@@ -1645,6 +1679,11 @@ int csgpu_search_variants(const csgpu_index *ix, const float *q, uint32_t q_len,
     bool prefilter = ix->tensor_prefilter && b >= 2;
     for (const Shard *sh : ix->shards) prefilter = prefilter && (sh->shadow_valid || sh->n_built == 0);
     if (prefilter && batch_gemm_available(ix)) return search_variants_prefiltered(ix, q, b, k, out_ids, out_dist, out_n);
+    // no shadow: the tf32 tensor-core filter answers the variants as one batch where it beats the multi-query passes
+    // (9 variants x top-200 over 10M x 384: 2.5 ms instead of 4.8); same lists bit for bit, deduplicated on the host
+    const char *env_s = getenv("CSGPU_GEMM_MIN_BATCH");
+    const bool tf32 = b >= 2 && batch_tf32_route(ix) && (env_s && *env_s ? b >= (uint32_t)atoi(env_s) : tf32_route_is_faster(ix, b, k));
+    if (tf32) return search_variants_prefiltered(ix, q, b, k, out_ids, out_dist, out_n);
     return search_variants(ix, q, b, k, out_ids, out_dist, out_n);
 }
 

@@ -639,6 +639,14 @@ bool batch_gemm_available(const csgpu_index *ix)
     return !ix->shards.empty();
 }
 
+bool batch_tf32_route(const csgpu_index *ix)
+{
+    if (!batch_gemm_available(ix)) return false;
+    for (const Shard *sh : ix->shards)
+        if (contraction_of(ix, sh) != Contraction::TC_TF32) return false;
+    return true;
+}
+
 // b queries through the GEMM-shaped path. zero_queries (fp32 index only) receives the batch positions of zero-norm
 // queries, whose outputs are left untouched for the caller to fill in.
 // Multi-device index: every shard runs the whole batch against its rows concurrently (one host thread per device:

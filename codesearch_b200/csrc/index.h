@@ -176,6 +176,7 @@ int batch_after_build(const csgpu_index *ix, Shard *sh);
 int shadow_refresh(const csgpu_index *ix, Shard *sh);
 void batch_free_ctx(Shard *sh);
 bool batch_gemm_available(const csgpu_index *ix);
+bool batch_tf32_route(const csgpu_index *ix);   // fp32 index whose batches run the tf32 tensor-core filter (gemm_tf32.cuh)
 int batch_search(const csgpu_index *ix, const float *q, uint32_t b, uint32_t k,
                  uint32_t *out_ids, float *out_dist, uint32_t *out_n, std::vector<uint32_t> *zero_queries);
 

@@ -5,7 +5,12 @@ Bar: the same as the single-query path — ids identical to the exact-cosine ora
 (a swap only inside an f64 near-tie of < 4e-7), |distance - oracle| <= 1e-5. The GEMM kernel sums k = 0..dim-1
 in one chain per (query, row), the scan kernels use a lane-strided chain + shuffle tree, so the two fp32
 paths may differ in the last ulp of a distance; both are held to the oracle, and to each other within 2e-6.
+
+Round 2: the default batch route of an fp32 index is the tf32 tensor-core filter + exact rescoring
+(tests/test_gpu_tf32_batch.py); this file pins the SIMT kernel — the route for dim > 1024 — with CSGPU_BATCH_SIMT=1.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -21,6 +26,17 @@ def cs():
     import codesearch_b200 as m
     m.load_library()
     return m
+
+
+@pytest.fixture(autouse=True)
+def simt_route():
+    old = os.environ.get("CSGPU_BATCH_SIMT")
+    os.environ["CSGPU_BATCH_SIMT"] = "1"
+    yield
+    if old is None:
+        os.environ.pop("CSGPU_BATCH_SIMT", None)
+    else:
+        os.environ["CSGPU_BATCH_SIMT"] = old
 
 
 def make_store(cs, rows, ids=None):
