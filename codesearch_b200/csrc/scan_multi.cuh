@@ -277,9 +277,24 @@ __global__ void __launch_bounds__(SCAN_THREADS, (E <= 4) ? 2 : 1) scan_multi_top
         for (uint32_t j = threadIdx.x; j < a.k; j += blockDim.x) dst[j] = sortbuf[j];
         __syncthreads();
     };
-    for (int b = 0; b < (int)a.nq; ++b) reduce_query(b, a.cand + ((size_t)b * gridDim.x + blockIdx.x) * a.k);
+    if constexpr (E == 1) {
+        // k <= 32 (round 2): every warp's list of a query is 32 sorted keys, so warp w merges query w's (and w + 8's) eight
+        // lists with seven 5-stage shuffle merges — all queries at once, two barriers — instead of one 256-key bitonic sort
+        // (36 barrier-separated stages) per query: that sort was ~3 us per query in EVERY CTA, 25 us of an 8-query pass
+        for (int b = 0; b < (int)a.nq; ++b) sel.flush(b, lane);
+        __syncthreads();
+        for (int b = warp; b < (int)a.nq; b += SCAN_WARPS) {
+            uint64_t run = keys0[(size_t)b * KPAD + lane];
+#pragma unroll 1
+            for (int w2 = 1; w2 < SCAN_WARPS; ++w2) run = warp_merge_low32(run, keys0[(size_t)w2 * wkeys + (size_t)b * KPAD + lane], lane);
+            if ((uint32_t)lane < a.k) a.cand[((size_t)b * gridDim.x + blockIdx.x) * a.k + lane] = run;
+        }
+    } else {
+        for (int b = 0; b < (int)a.nq; ++b) reduce_query(b, a.cand + ((size_t)b * gridDim.x + blockIdx.x) * a.k);
+    }
 
     __threadfence();
+    __syncthreads();
     if (threadIdx.x == 0) {
         unsigned t = atomicAdd(a.ticket, 1u);
         is_last = (t == gridDim.x - 1);
@@ -288,8 +303,32 @@ __global__ void __launch_bounds__(SCAN_THREADS, (E <= 4) ? 2 : 1) scan_multi_top
     if (!is_last) return;
     __threadfence();
 
-    sel.init(wbase, wbase + (size_t)MQT * KPAD, np_all + warp * MQT, a.k, MQT, lane);
     const uint64_t total = (uint64_t)gridDim.x * a.k;
+    if constexpr (E == 1) {
+        // the last CTA, k <= 32: per query the scan kernel's tail (cta_topk_of_lists32: threshold = k-th smallest of the
+        // CTAs' minima, only the survivors are sorted). Zero-norm rows (distance 0.0, ascending id; the first k allowed ones
+        // suffice) are the same list for every query: built once. Scratch: the warps' selection state, no longer needed.
+        uint64_t zrun = KEY_EMPTY;
+        if (a.n_zero) {
+            uint32_t found = 0;
+            for (uint32_t o = 0; o < a.n_zero && found < a.k; o += SCAN_WARPS * 32) {   // CTA-uniform loop; warp w sorts its 32 ids of the batch (the lists are merged across warps below)
+                uint64_t key = KEY_EMPTY;
+                const uint32_t i = o + threadIdx.x;
+                if (i < a.n_zero) {
+                    const uint32_t id = a.zero_ids[i];
+                    if (id_allowed(a.bitmap, a.n_bits, id)) key = make_key(0.f, id);
+                }
+                found += __syncthreads_count(key != KEY_EMPTY);
+                zrun = warp_merge_low32(zrun, warp_sort32(key, lane), lane);
+            }
+        }
+        static_assert(SCAN_WARPS * multi_warp_keys<E>(MQT) >= 2 * SCAN_WARPS * 32, "scratch of cta_topk_of_lists32");
+        for (int b = 0; b < (int)a.nq; ++b) {
+            cta_topk_of_lists32(a.cand + (size_t)b * total, gridDim.x, a.k, zrun, keys0, a.out_keys + (size_t)b * a.k, warp, lane);
+            __syncthreads();
+        }
+    } else {
+    sel.init(wbase, wbase + (size_t)MQT * KPAD, np_all + warp * MQT, a.k, MQT, lane);
     for (int b = 0; b < (int)a.nq; ++b) {
         const volatile uint64_t *cand = a.cand + (size_t)b * total;
         // Every CTA's list is sorted ascending: a warp walks ITS lists (CTA c = 32 w + lane, + 256, ...) column by
@@ -330,6 +369,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, (E <= 4) ? 2 : 1) scan_multi_top
             }
         }
         reduce_query(b, a.out_keys + (size_t)b * a.k);
+    }
     }
     if (threadIdx.x == 0) { a.ticket[0] = 0; a.ticket[1] = 0; }
 }
