@@ -717,25 +717,59 @@ def extras_batch(store, lib, n, d, peaks_json, want):
     fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
     flop = 2.0 * n * d * b
     if "batch" in want:
-        def simt():
+        def tf32():
+            os.environ.pop("CSGPU_BATCH_SIMT", None)
             smp = ClockSampler(0).start()
-            dt, dev_ms, launches, res = _time_batches(store, lib, qs, k, 3)
+            dt, dev_ms, launches, res = _time_batches(store, lib, qs, k, 5)
             clk = smp.stop()
+            st = store.device_stats()
             same = True
-            for j in range(0, b, 128):
+            for j in range(0, b, 64):
                 gi, gd = store.search_ids(qs[j], k)
-                same = same and np.array_equal(res[0][j], gi) and bool(np.abs(res[1][j] - gd).max() <= 1e-6)
+                same = same and np.array_equal(res[0][j], gi) and np.array_equal(res[1][j].view(np.uint32), gd.view(np.uint32))
             small = {}
-            for bb in (16, 32, 64, 128):
-                dts, _, _, _ = _time_batches(store, lib, qs[:bb], k, 3)
-                small[str(bb)] = round(dts * 1e3, 3)
-            return {"workload": f"{n}x{d} fp32 index, batch {b} x top-{k} (BASELINE configs[2], fp32 SIMT = the default route), host buffers",
+            for bb in (2, 8, 16, 32, 64, 128, 256):
+                dts, dvs, _, _ = _time_batches(store, lib, qs[:bb], k, 5)
+                small[str(bb)] = {"ms": round(dts * 1e3, 3), "device_ms": round(dvs, 3)}
+            tf_peak = float(peaks_json.get("bf16_tflops", 0) or 0) / 2.0
+            return {"workload": f"{n}x{d} fp32 index, batch {b} x top-{k} (BASELINE configs[2]), csgpu_search_batch on the DEFAULT index: "
+                                "tcgen05 kind::tf32 straight off the fp32 rows as a filter + exact fp32 rescoring (csrc/gemm_tf32.cuh), host buffers",
+                    "route": {1: "simt_f32", 2: "tc_bf16", 3: "tc_tf32"}.get(int(st.batch_route), str(st.batch_route)),
+                    "ms_per_batch": round(dt * 1e3, 3), "device_ms": round(dev_ms, 3), "qps": round(b / dt, 1),
+                    "TFLOPs_device": round(flop / (dev_ms * 1e-3) / 1e12, 1),
+                    "bound": "L2 -> SM bandwidth above 128 queries (every 128-query block re-reads the row tiles), HBM up to 128",
+                    "L2_to_SM_GBps": round(((b + 127) // 128) * (n * d * 4.0 + n / 256.0 * 128 * d * 4.0) / (dev_ms * 1e-3) / 1e9, 1),
+                    "frac_of_tf32_tensor_peak": (round(flop / (dev_ms * 1e-3) / 1e12 / tf_peak, 4) if tf_peak else None),
+                    "tf32_peak_TFLOPs": (round(tf_peak, 1) if tf_peak else None),
+                    "peak_source": "half of MEASURED_PEAKS.json bf16_tflops (tf32 runs at half the bf16 rate)",
+                    "shadow_bytes": int(st.shadow_bytes), "gpu_launches_per_batch": launches,
+                    "fp32_rows_rescored_per_query": round(int(st.prefilter_rescored) / b, 1),
+                    "filter_max_err": float(st.filter_max_err), "filter_margin": 1.1e-3,
+                    "bit_identical_to_single_query_kernel": bool(same), "queries_checked": b // 64,
+                    "by_batch_size_top100": small, "clocks": clk}
+        out["batch_fp32_default_tf32_filter"] = guarded(tf32)
+
+        def simt():
+            os.environ["CSGPU_BATCH_SIMT"] = "1"     # the SIMT kernel: the route for dim > 1024, kept measured
+            try:
+                smp = ClockSampler(0).start()
+                dt, dev_ms, launches, res = _time_batches(store, lib, qs, k, 2)
+                clk = smp.stop()
+                st = store.device_stats()
+                same = True
+                for j in range(0, b, 128):
+                    gi, gd = store.search_ids(qs[j], k)
+                    same = same and np.array_equal(res[0][j], gi) and bool(np.abs(res[1][j] - gd).max() <= 1e-6)
+            finally:
+                os.environ.pop("CSGPU_BATCH_SIMT", None)
+            return {"workload": f"{n}x{d} fp32 index, batch {b} x top-{k} (BASELINE configs[2]), register-tiled fp32 SIMT kernel (CSGPU_BATCH_SIMT=1; the route for dim > 1024), host buffers",
+                    "route": {1: "simt_f32", 2: "tc_bf16", 3: "tc_tf32"}.get(int(st.batch_route), str(st.batch_route)),
                     "ms_per_batch": round(dt * 1e3, 2), "device_ms": round(dev_ms, 2), "qps": round(b / dt, 1),
                     "TFLOPs": round(flop / dt / 1e12, 2), "bound": "fp32 FMA pipe",
                     "peak_TFLOPs": round(fp32_peak, 1), "frac": round(flop / (dev_ms * 1e-3) / 1e12 / fp32_peak, 4),
                     "peak_source": f"148 SM x 128 lanes x 2 flop x {sm_max:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz)",
                     "gpu_launches_per_batch": launches, "ids_equal_single_query_kernel": bool(same), "queries_checked": b // 128,
-                    "ms_by_batch_size_top100": small, "clocks": clk}
+                    "clocks": clk}
         out["batch_fp32_simt"] = guarded(simt)
     if "prefilter" in want:
         def pref():

@@ -1556,14 +1556,16 @@ int csgpu_get_tags(const csgpu_index *ix, const uint32_t *ids, uint64_t n, uint3
 }
 
 // fp32 index, tf32 route available: does the tensor-core filter (+ exact rescoring) beat the scan kernels for b queries?
-// A cost model fitted to measurements on one B200 (profiles/r02_tf32_probe_*.txt), times in us, sizes in MB per device:
-//   tensor-core route  ~230 us fixed (query prep, 3-5 phases of contraction + select, three host round trips) + one pass over
-//                      the rows at ~6.4 TB/s per <= 128 queries; above, every further 128-query block re-reads the row tiles
-//                      from L2 (1024 queries: 12.0 ms at 15.36 GB);
-//   multi-query scan   one launch (~45 us) per pass of <= 16 queries: <= 8 queries stream at ~5.6 TB/s, 9-16 at ~3.4 TB/s;
+// A cost model fitted to measurements on one B200 (profiles/r02_tf32_probe_*.txt, r02_multi_tail_ab.txt), times in us, sizes
+// in MB per device:
+//   tensor-core route  ~205 us fixed (260 for k > 32: query prep, 3-5 phases of contraction + select, one host round trip)
+//                      + one pass over the rows at ~6.4 TB/s per <= 128 queries; above, the tensor pipe is the bound
+//                      (1024 queries: 12.0 ms at 15.36 GB);
+//   multi-query scan   one launch per pass of <= 16 queries: ~45 us + ~8 us per query of tail; <= 8 queries stream at
+//                      ~6.3 TB/s, 9-16 at ~3.7 TB/s (issue-bound);
 //   single-query scan  ~30 us + the rows at ~7.2 TB/s.
-// At 10M x 384 the tensor cores win from 2 queries on (2.36 vs 2.51 ms; 16 queries: 2.4 vs 4.6 ms); at the reference's own
-// scale (100k rows, src/constants.rs:93-95) a handful of query variants stays one multi-query launch.
+// At 10M x 384 the tensor cores win from 2 queries on (2.36 vs 2.43 ms; 16 queries: 2.4 vs 4.3 ms); at the reference's own
+// scale (100k rows, src/constants.rs:93-95) up to 16 query variants stay one multi-query launch (8 variants: 103 us).
 static bool tf32_route_is_faster(const csgpu_index *ix, uint32_t b, uint32_t k)
 {
     if (b < 2) return false;
@@ -1571,13 +1573,13 @@ static bool tf32_route_is_faster(const csgpu_index *ix, uint32_t b, uint32_t k)
     for (const Shard *sh : ix->shards) rows = std::max<uint64_t>(rows, sh->n_built);
     const double mb = (double)rows * ix->dim_pad * sizeof(float) / 1e6;
     const uint32_t nqb = (b + 127) / 128;
-    const double t_tc = 230.0 + mb / 6.4 * (nqb == 1 ? 1.0 : 0.3 + 0.57 * nqb);
+    const double t_tc = (k > 32 ? 260.0 : 205.0) + mb / 6.4 * (nqb == 1 ? 1.0 : 0.3 + 0.57 * nqb);
     double t_scan = 0.0;
     if (multi_scan_supported(ix->dim4, k)) {
         const uint32_t MQ = multi_scan_max_queries();
         for (uint32_t j = 0; j < b; j += MQ) {
             const uint32_t nq = std::min(MQ, b - j);
-            t_scan += nq == 1 ? 30.0 + mb / 7.2 : 45.0 + mb / (nq <= 8 ? 5.6 : 3.4) * (k > 32 ? 1.1 : 1.0);
+            t_scan += nq == 1 ? 30.0 + mb / 7.2 : 45.0 + 8.0 * nq + mb / (nq <= 8 ? 6.3 : 3.7) * (k > 32 ? 1.2 : 1.0);
         }
     } else {
         t_scan = b * (30.0 + mb / 7.2);

@@ -553,8 +553,7 @@ static int batch_search_shard(const csgpu_index *ix, Shard *sh, BatchCtx *c, con
         prep_queries_f32_kernel<<<(nq_pad * 32 + 255) / 256, 256, 0, c->stream>>>(c->q_f32, ix->dim_pad, nq, ix->dim, ix->dim_pad, reinterpret_cast<float *>(c->q_prep), nq_pad, c->flags, c->thr, c->count);
     count_launch();
     uint8_t *flags_host = reinterpret_cast<uint8_t *>(c->out_pin) + (size_t)BF_MAX_QBLOCKS * GT_BLOCK_M * CSGPU_MAX_K * sizeof(uint64_t);
-    CS_CUDA(cudaMemcpyAsync(flags_host, c->flags, nq, cudaMemcpyDeviceToHost, c->stream));
-    CS_CUDA(cudaStreamSynchronize(c->stream));
+    CS_CUDA(cudaMemcpyAsync(flags_host, c->flags, nq, cudaMemcpyDeviceToHost, c->stream));   // read after the batch's final synchronisation
     *flags_out = flags_host;
     CUtensorMap map_q;
     const uint32_t q_box = con == Contraction::TC_TF32 ? (n_qblocks == 1 ? tf32_q_rows(nq) : (uint32_t)GT_BLOCK_M)
@@ -570,6 +569,7 @@ static int batch_search_shard(const csgpu_index *ix, Shard *sh, BatchCtx *c, con
     const double per_k = rescore_path(ix, sh) ? 2.8 : 1.5;
     const uint64_t growth = env_growth ? (uint64_t)env_growth
                                        : 1 + std::min<uint64_t>(BF_PHASE_GROWTH - 1, std::max<uint64_t>(1, (uint64_t)(SEL_SORT_CAP / (per_k * k))));
+    unsigned scalar_host[6] = {0, 0, 0, 0, 0, 0};
     for (int attempt = 0; attempt < 2; ++attempt) {
         const bool careful = attempt == 1;
         if (careful) {   // an overflow spoiled the optimistic run: start over, checking every range
@@ -594,10 +594,10 @@ static int batch_search_shard(const csgpu_index *ix, Shard *sh, BatchCtx *c, con
             rc = launch_select(ix, sh, c, nq_pad, nq, k, true, fin);
             if (rc) return rc;
         }
-        unsigned over = 0;
-        CS_CUDA(cudaMemcpyAsync(&over, c->scalar, sizeof over, cudaMemcpyDeviceToHost, c->stream));
+        // one read-back per attempt: [0] overflow flag, [2..3] rows rescored, [4] largest filter error
+        CS_CUDA(cudaMemcpyAsync(scalar_host, c->scalar, sizeof scalar_host, cudaMemcpyDeviceToHost, c->stream));
         CS_CUDA(cudaStreamSynchronize(c->stream));
-        if (!over) break;
+        if (!scalar_host[0]) break;
         if (careful) return fail(CSGPU_ERR_CUDA, "candidate overflow in the careful pass (internal error)");
     }
     if (ix->dtype == CSGPU_DTYPE_BF16) {   // zero-norm queries: distance 0.0 everywhere -> the k smallest ids (after the final select wrote its empty lists)
@@ -620,8 +620,7 @@ static int batch_search_shard(const csgpu_index *ix, Shard *sh, BatchCtx *c, con
     }
     ix->batch_route.store(con == Contraction::TC_TF32 ? CSGPU_ROUTE_TC_TF32 : con == Contraction::TC_BF16 ? CSGPU_ROUTE_TC_BF16 : CSGPU_ROUTE_SIMT_F32);
     if (rescore_path(ix, sh)) {
-        unsigned st[4] = {0, 0, 0, 0};   // [0..1] rows rescored (u64), [2] float bits of the largest |d_filter - d_f32|
-        CS_CUDA(cudaMemcpy(st, c->scalar + 2, 3 * sizeof(unsigned), cudaMemcpyDeviceToHost));
+        const unsigned *st = scalar_host + 2;   // [0..1] rows rescored (u64), [2] float bits of the largest |d_filter - d_f32|
         unsigned long long nres = 0;
         memcpy(&nres, st, sizeof nres);
         ix->prefilter_rescored.fetch_add(nres);   // summed over the shards of a multi-device index (reset per chunk by batch_search)

@@ -31,7 +31,7 @@ struct MultiArgs {
     const uint32_t *zero_ids;
     uint32_t n_zero;
     uint64_t *cand;        // [MQ][gridDim.x][k]
-    unsigned *ticket;      // [0] last-CTA ticket, [1] work counter of the dynamic row split (both self-resetting)
+    unsigned *ticket;      // [0] arrival ticket, [1] work counter of the dynamic row split, [2] finishers done (all self-resetting)
     uint64_t *out_keys;    // [nq][k]
     uint32_t static_split = 0;   // 1 = fixed-stride row split (CSGPU_SCAN_STATIC=1, A/B runs)
 };
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, (E <= 4) ? 2 : 1) scan_multi_top
     static_assert(NV == 32 || NV == 16 || NV == 8, "R*MQ must be 8, 16 or 32");
     constexpr uint32_t KPAD = 32u * E;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ bool is_last;
+    __shared__ unsigned s_ticket;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t dim4 = a.dim4;
 
@@ -268,110 +268,62 @@ __global__ void __launch_bounds__(SCAN_THREADS, (E <= 4) ? 2 : 1) scan_multi_top
         }
     }
 
-    // ---- per query: CTA top-k -> cand[b][cta][k]; last CTA merges across CTAs ----------------
-    auto reduce_query = [&](int b, uint64_t *dst) {
-        sel.flush(b, lane);
-        const uint64_t *L = sel.list + (size_t)b * KPAD;
-        for (uint32_t j = lane; j < KPAD; j += 32) sortbuf[(size_t)warp * KPAD + j] = L[j];
-        cta_sort(sortbuf, SCAN_WARPS * KPAD);
-        for (uint32_t j = threadIdx.x; j < a.k; j += blockDim.x) dst[j] = sortbuf[j];
-        __syncthreads();
-    };
-    if constexpr (E == 1) {
-        // k <= 32 (round 2): every warp's list of a query is 32 sorted keys, so warp w merges query w's (and w + 8's) eight
-        // lists with seven 5-stage shuffle merges — all queries at once, two barriers — instead of one 256-key bitonic sort
-        // (36 barrier-separated stages) per query: that sort was ~3 us per query in EVERY CTA, 25 us of an 8-query pass
-        for (int b = 0; b < (int)a.nq; ++b) sel.flush(b, lane);
-        __syncthreads();
-        for (int b = warp; b < (int)a.nq; b += SCAN_WARPS) {
-            uint64_t run = keys0[(size_t)b * KPAD + lane];
+    // ---- per query: CTA top-k -> cand[b][cta][k]; the last CTAs to arrive merge across CTAs, one query each ----------------
+    // k <= 32 (round 2): every warp's list of a query is 32 sorted keys, so warp w merges query w's (and w + 8's) eight lists
+    // with seven 5-stage shuffle merges — all queries at once, two barriers — instead of one 256-key bitonic sort (36
+    // barrier-separated stages) per query: that sort was ~3 us per query in EVERY CTA, 25 us of an 8-query pass.
+    static_assert(E == 1, "per-warp sorted lists of 32 keys (k <= 32); larger k: scan_multi_cta_topk_kernel");
+    for (int b = 0; b < (int)a.nq; ++b) sel.flush(b, lane);
+    __syncthreads();
+    for (int b = warp; b < (int)a.nq; b += SCAN_WARPS) {
+        uint64_t run = keys0[(size_t)b * KPAD + lane];
 #pragma unroll 1
-            for (int w2 = 1; w2 < SCAN_WARPS; ++w2) run = warp_merge_low32(run, keys0[(size_t)w2 * wkeys + (size_t)b * KPAD + lane], lane);
-            if ((uint32_t)lane < a.k) a.cand[((size_t)b * gridDim.x + blockIdx.x) * a.k + lane] = run;
-        }
-    } else {
-        for (int b = 0; b < (int)a.nq; ++b) reduce_query(b, a.cand + ((size_t)b * gridDim.x + blockIdx.x) * a.k);
+        for (int w2 = 1; w2 < SCAN_WARPS; ++w2) run = warp_merge_low32(run, keys0[(size_t)w2 * wkeys + (size_t)b * KPAD + lane], lane);
+        if ((uint32_t)lane < a.k) a.cand[((size_t)b * gridDim.x + blockIdx.x) * a.k + lane] = run;
     }
-
     __threadfence();
     __syncthreads();
+
+    // The LAST nq CTAs to arrive each finish one query (round 2; one last CTA used to finish them one after the other,
+    // ~6 us each — most of a small corpus's latency). A finisher waits until every CTA has delivered its lists: the CTAs
+    // still running are resident or become resident as the others exit, and at most nq <= 16 CTAs ever wait, so the spin
+    // cannot starve them. The last finisher to leave resets the counters for the next launch.
+    if (threadIdx.x == 0) s_ticket = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    const unsigned n_fin = min(a.nq, gridDim.x), first_fin = gridDim.x - n_fin;
+    if (s_ticket < first_fin) return;
+    const unsigned fin = s_ticket - first_fin;
     if (threadIdx.x == 0) {
-        unsigned t = atomicAdd(a.ticket, 1u);
-        is_last = (t == gridDim.x - 1);
+        const volatile unsigned *tk = a.ticket;
+        while (*tk < gridDim.x) {}
     }
     __syncthreads();
-    if (!is_last) return;
     __threadfence();
 
+    // Per query the scan kernel's tail (cta_topk_of_lists32: threshold = k-th smallest of the CTAs' minima, only the
+    // survivors are sorted). Zero-norm rows (distance 0.0, ascending id; the first k allowed ones suffice) are the same for
+    // every query. Scratch: the warps' selection state, no longer needed.
     const uint64_t total = (uint64_t)gridDim.x * a.k;
-    if constexpr (E == 1) {
-        // the last CTA, k <= 32: per query the scan kernel's tail (cta_topk_of_lists32: threshold = k-th smallest of the
-        // CTAs' minima, only the survivors are sorted). Zero-norm rows (distance 0.0, ascending id; the first k allowed ones
-        // suffice) are the same list for every query: built once. Scratch: the warps' selection state, no longer needed.
-        uint64_t zrun = KEY_EMPTY;
-        if (a.n_zero) {
-            uint32_t found = 0;
-            for (uint32_t o = 0; o < a.n_zero && found < a.k; o += SCAN_WARPS * 32) {   // CTA-uniform loop; warp w sorts its 32 ids of the batch (the lists are merged across warps below)
-                uint64_t key = KEY_EMPTY;
-                const uint32_t i = o + threadIdx.x;
-                if (i < a.n_zero) {
-                    const uint32_t id = a.zero_ids[i];
-                    if (id_allowed(a.bitmap, a.n_bits, id)) key = make_key(0.f, id);
-                }
-                found += __syncthreads_count(key != KEY_EMPTY);
-                zrun = warp_merge_low32(zrun, warp_sort32(key, lane), lane);
+    uint64_t zrun = KEY_EMPTY;
+    if (a.n_zero) {
+        uint32_t found = 0;
+        for (uint32_t o = 0; o < a.n_zero && found < a.k; o += SCAN_WARPS * 32) {   // CTA-uniform loop; warp w sorts its 32 ids of the batch (the lists are merged across warps below)
+            uint64_t key = KEY_EMPTY;
+            const uint32_t i = o + threadIdx.x;
+            if (i < a.n_zero) {
+                const uint32_t id = a.zero_ids[i];
+                if (id_allowed(a.bitmap, a.n_bits, id)) key = make_key(0.f, id);
             }
+            found += __syncthreads_count(key != KEY_EMPTY);
+            zrun = warp_merge_low32(zrun, warp_sort32(key, lane), lane);
         }
-        static_assert(SCAN_WARPS * multi_warp_keys<E>(MQT) >= 2 * SCAN_WARPS * 32, "scratch of cta_topk_of_lists32");
-        for (int b = 0; b < (int)a.nq; ++b) {
-            cta_topk_of_lists32(a.cand + (size_t)b * total, gridDim.x, a.k, zrun, keys0, a.out_keys + (size_t)b * a.k, warp, lane);
-            __syncthreads();
-        }
-    } else {
-    sel.init(wbase, wbase + (size_t)MQT * KPAD, np_all + warp * MQT, a.k, MQT, lane);
-    for (int b = 0; b < (int)a.nq; ++b) {
-        const volatile uint64_t *cand = a.cand + (size_t)b * total;
-        // Every CTA's list is sorted ascending: a warp walks ITS lists (CTA c = 32 w + lane, + 256, ...) column by
-        // column and stops at the first column in which none of them beats its threshold — ~k / 37 + a few rounds of
-        // one load latency each instead of gridDim.x * k / 256 (1 ms of tail per 8-query pass at k = 100).
-        for (uint32_t j = 0; j < a.k; ++j) {
-            bool any = false;
-            for (uint32_t c0 = (uint32_t)warp * 32; c0 < gridDim.x; c0 += SCAN_WARPS * 32) {
-                const uint32_t c = c0 + lane;
-                const uint64_t key = c < gridDim.x ? cand[(size_t)c * a.k + j] : KEY_EMPTY;
-                unsigned m = __ballot_sync(FULL, key < sel.thr_of(b));
-                any |= m != 0;
-                while (m) {
-                    const int src = __ffs(m) - 1;
-                    m &= m - 1;
-                    const uint64_t kk = shfl64(key, src);
-                    if (kk < sel.thr_of(b)) sel.append(b, kk, lane);
-                }
-            }
-            if (!any) break;   // warp-uniform
-        }
-        if (warp == 0 && a.n_zero) {
-            uint32_t found = 0;
-            for (uint32_t o = 0; o < a.n_zero && found < a.k; o += 32) {
-                uint64_t key = KEY_EMPTY;
-                if (o + lane < a.n_zero) {
-                    const uint32_t id = a.zero_ids[o + lane];
-                    if (id_allowed(a.bitmap, a.n_bits, id)) key = make_key(0.f, id);
-                }
-                unsigned m = __ballot_sync(FULL, key != KEY_EMPTY);
-                found += __popc(m);
-                while (m) {
-                    const int src = __ffs(m) - 1;
-                    m &= m - 1;
-                    const uint64_t kk = shfl64(key, src);
-                    if (kk < sel.thr_of(b)) sel.append(b, kk, lane);
-                }
-            }
-        }
-        reduce_query(b, a.out_keys + (size_t)b * a.k);
     }
+    static_assert(SCAN_WARPS * multi_warp_keys<E>(MQT) >= 2 * SCAN_WARPS * 32, "scratch of cta_topk_of_lists32");
+    for (unsigned b = fin; b < a.nq; b += n_fin) {
+        cta_topk_of_lists32(a.cand + (size_t)b * total, gridDim.x, a.k, zrun, keys0, a.out_keys + (size_t)b * a.k, warp, lane);
+        __syncthreads();
     }
-    if (threadIdx.x == 0) { a.ticket[0] = 0; a.ticket[1] = 0; }
+    if (threadIdx.x == 0 && atomicAdd(a.ticket + 2, 1u) == n_fin - 1) { a.ticket[0] = 0; a.ticket[1] = 0; a.ticket[2] = 0; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
