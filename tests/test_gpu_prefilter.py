@@ -72,7 +72,7 @@ def test_prefilter_near_ties_inside_the_margin(cs, oracle):
     d, n_clusters, per = 384, 40, 600
     centres = rng.standard_normal((n_clusters, d)).astype(np.float32)
     # noise 0.05: distances inside a cluster spread over ~5e-4 (resolvable in fp32, spacing >> 4e-7) yet all 600 rows
-    # of the query's cluster sit inside the 2.1e-3 bf16 margin of each other
+    # of the query's cluster sit inside the 4.0e-3 bf16 margin of each other
     rows = (np.repeat(centres, per, axis=0) + 0.05 * rng.standard_normal((n_clusters * per, d))).astype(np.float32)
     rows[100] = rows[99]                                       # exact duplicates: tie broken by id
     rows[5000] = rows[4999]
