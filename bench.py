@@ -737,8 +737,7 @@ def extras_batch(store, lib, n, d, peaks_json, want):
                     "route": {1: "simt_f32", 2: "tc_bf16", 3: "tc_tf32"}.get(int(st.batch_route), str(st.batch_route)),
                     "ms_per_batch": round(dt * 1e3, 3), "device_ms": round(dev_ms, 3), "qps": round(b / dt, 1),
                     "TFLOPs_device": round(flop / (dev_ms * 1e-3) / 1e12, 1),
-                    "bound": "L2 -> SM bandwidth above 128 queries (every 128-query block re-reads the row tiles), HBM up to 128",
-                    "L2_to_SM_GBps": round(((b + 127) // 128) * (n * d * 4.0 + n / 256.0 * 128 * d * 4.0) / (dev_ms * 1e-3) / 1e9, 1),
+                    "bound": "tensor (tf32 pipe: half the bf16 rate; ncu of the main phase: tensor pipe 80 % active, its memory side 88 %) above 128 queries; hbm up to 128 queries (ncu: 85 % of DRAM peak)",
                     "frac_of_tf32_tensor_peak": (round(flop / (dev_ms * 1e-3) / 1e12 / tf_peak, 4) if tf_peak else None),
                     "tf32_peak_TFLOPs": (round(tf_peak, 1) if tf_peak else None),
                     "peak_source": "half of MEASURED_PEAKS.json bf16_tflops (tf32 runs at half the bf16 rate)",
@@ -771,6 +770,42 @@ def extras_batch(store, lib, n, d, peaks_json, want):
                     "gpu_launches_per_batch": launches, "ids_equal_single_query_kernel": bool(same), "queries_checked": b // 128,
                     "clocks": clk}
         out["batch_fp32_simt"] = guarded(simt)
+    if "batch" in want:
+        def serving():
+            """Many concurrent callers of csgpu_search (the reference's server shape: `&self` from many threads,
+            src/server/mod.rs:545-548) with the micro-batcher on: a group of up to 128 callers rides one tf32 tensor-core batch."""
+            T, R, kk = 64, 12, 10
+            want_res = [store.search_ids(qs[j], kk) for j in range(T)]
+            t0 = time.perf_counter()
+            for j in range(16):
+                store.search_ids(qs[j], kk)
+            one = (time.perf_counter() - t0) / 16
+            store.set_coalescing(True)
+            try:
+                s0 = store.device_stats()
+                bad = []
+                start = threading.Barrier(T + 1)
+
+                def work(j):
+                    start.wait()
+                    for _ in range(R):
+                        gi, gd = store.search_ids(qs[j], kk)
+                        if not (np.array_equal(gi, want_res[j][0]) and np.array_equal(gd.view(np.uint32), want_res[j][1].view(np.uint32))):
+                            bad.append(j)
+                ts = [threading.Thread(target=work, args=(j,)) for j in range(T)]
+                [t.start() for t in ts]
+                start.wait()
+                t0 = time.perf_counter()
+                [t.join() for t in ts]
+                dt = time.perf_counter() - t0
+                s1 = store.device_stats()
+            finally:
+                store.set_coalescing(False)
+            return {"workload": f"{n}x{d} fp32 index, {T} host threads x {R} csgpu_search calls each (top-{kk}, host buffers), csgpu_set_coalescing on",
+                    "qps": round(T * R / dt, 1), "single_caller_qps": round(1.0 / one, 1),
+                    "searches": int(s1.coalesced_queries - s0.coalesced_queries), "corpus_passes": int(s1.coalesced_passes - s0.coalesced_passes),
+                    "every_answer_bit_identical_to_its_uncoalesced_search": not bad}
+        out["coalesced_serving_64_callers"] = guarded(serving)
     if "prefilter" in want:
         def pref():
             store.set_tensor_prefilter(True)
@@ -897,8 +932,17 @@ def extras_small(cs, _lib, lib, d, k):
         for i in range(50):
             st.search_ids(qs[i % N_QUERIES], k)
             dev.append(st.device_stats().last_search_us)
+        variants = {}
+        for nv in (2, 4, 9, 16):      # query variants of one search (search/mod.rs:498-511), one csgpu_search_batch call
+            for i in range(5):
+                st.search_batch_ids(qs[:nv], k)
+            t0 = time.perf_counter()
+            for i in range(100):
+                st.search_batch_ids(qs[:nv], k)
+            variants[str(nv)] = round((time.perf_counter() - t0) / 100 * 1e3, 4)
         out[f"{rows}_rows"] = {"e2e_ms_per_query": round(dt * 1e3, 4), "qps": round(1 / dt, 1),
-                               "device_us": round(float(np.median(dev)), 1), "top_ids_query0": [int(i) for i in st.search_ids(qs[0], k)[0]]}
+                               "device_us": round(float(np.median(dev)), 1), "top_ids_query0": [int(i) for i in st.search_ids(qs[0], k)[0]],
+                               "e2e_ms_per_batch_of_query_variants": variants}
         st.close()
     out["api"] = "VectorStore.search_ids -> csgpu_search, host pointers in and out, one query per call"
     return out

@@ -1099,7 +1099,9 @@ static int search_coalesced(const csgpu_index *ix, const float *q, uint32_t k, u
     PendingSearch me{q, k, out_ids, out_dist, out_n};
     std::unique_lock<std::mutex> lk(co.mu);
     co.queue.push_back(&me);
-    const uint32_t MQ = multi_scan_max_queries();
+    // group size: one multi-query pass (16), or — where the group becomes a tensor-core batch (tf32 filter of an fp32 index,
+    // gemm_tf32.cuh, or the tensor prefilter) — one 128-query block, which costs about as much as a single query at 10M rows
+    const uint32_t MQ = (ix->dtype == CSGPU_DTYPE_F32 && (batch_tf32_route(ix) || ix->tensor_prefilter)) ? 128u : multi_scan_max_queries();
     while (!me.done) {
         if (co.leader_active) { co.cv.wait(lk); continue; }
         co.leader_active = true;

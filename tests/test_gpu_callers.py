@@ -91,6 +91,46 @@ def test_coalescing_concurrent_searches_bit_identical(cs, oracle, shadow):
     check_topk(gi, gd, oi, od, o64, k)
 
 
+def test_coalescing_many_callers_share_one_tensor_core_batch(cs, oracle):
+    """Round 2: on an fp32 index whose batches run the tf32 tensor-core filter (csrc/gemm_tf32.cuh) a coalesced group is up
+    to 128 callers — one 128-query block costs about what one query costs. 48 threads hammer csgpu_search (the reference's
+    server shape: `&self` from many threads, src/server/mod.rs:545-548); every caller gets exactly what its own uncoalesced
+    search returns, and the searches ride in far fewer passes than a 16-wide group would allow."""
+    rng = np.random.default_rng(77)
+    n, d, k, T, R = 1_500_000, 384, 10, 48, 6
+    st = cs.VectorStore.new(None, d)
+    st.append_synthetic(99, 0, n)
+    st.build_index()
+    qs = rng.standard_normal((T, d)).astype(np.float32)
+    want = [st.search_ids(q, k) for q in qs]
+    st.set_coalescing(True)
+    s0 = st.device_stats()
+    errs = []
+    start = threading.Barrier(T)
+
+    def work(j):
+        try:
+            start.wait()
+            for _ in range(R):
+                gi, gd = st.search_ids(qs[j], k)
+                if not (np.array_equal(gi, want[j][0]) and np.array_equal(gd.view(np.uint32), want[j][1].view(np.uint32))):
+                    errs.append(j)
+        except Exception as e:  # noqa: BLE001
+            errs.append((j, e))
+    ts = [threading.Thread(target=work, args=(j,)) for j in range(T)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs[:3]
+    s1 = st.device_stats()
+    q_done = s1.coalesced_queries - s0.coalesced_queries
+    passes = s1.coalesced_passes - s0.coalesced_passes
+    print(f"coalescer: {q_done} searches in {passes} passes, last batch route {s1.batch_route}")
+    assert q_done == T * R
+    assert passes < q_done / 4, (passes, q_done)                  # groups well beyond a handful of callers
+    assert s1.batch_route == 3                                    # the groups ran as tf32 tensor-core batches
+    st.set_coalescing(False)
+
+
 @pytest.mark.parametrize("n,d,b,k", [(50000, 384, 9, 200), (50000, 384, 3, 10), (20000, 768, 16, 100),
                                      (5000, 100, 5, 50), (300, 384, 9, 1000), (20000, 384, 1, 25)])
 def test_search_variants_dedup(cs, oracle, n, d, b, k):
