@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_multi_cta_topk_kernel(co
     constexpr uint32_t SYNC_IT = NG == 1 ? 8 : 4;            // iterations between two sync points (NG = 2: smaller buffers)
     constexpr uint32_t SLACK = SYNC_IT * R * SCAN_WARPS;     // most keys one query can receive between two sync points
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ bool is_last;
+    __shared__ unsigned s_ticket;
     __shared__ unsigned cnt_s[MQT];
     __shared__ uint64_t thr_s[MQT];
     __shared__ float qflag[MQT];
@@ -493,18 +493,24 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_multi_cta_topk_kernel(co
     }
     __threadfence();
     __syncthreads();
+    // the LAST nq CTAs to arrive finish one query each (see scan_multi_topk_kernel: a finisher waits for every CTA's lists;
+    // at most nq <= 16 CTAs ever wait and all others exit, so the spin cannot starve them)
+    if (threadIdx.x == 0) s_ticket = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    const unsigned n_fin = min(a.nq, gridDim.x), first_fin = gridDim.x - n_fin;
+    if (s_ticket < first_fin) return;
+    const unsigned fin = s_ticket - first_fin;
     if (threadIdx.x == 0) {
-        unsigned t = atomicAdd(a.ticket, 1u);
-        is_last = (t == gridDim.x - 1);
+        const volatile unsigned *tk = a.ticket;
+        while (*tk < gridDim.x) {}
     }
     __syncthreads();
-    if (!is_last) return;
     __threadfence();
 
-    // ---- last CTA: merge across CTAs, column-wise over the sorted per-CTA lists (see scan.cuh) ----
+    // ---- finisher: merge one query across CTAs, column-wise over the sorted per-CTA lists (see scan.cuh) ----
     const uint32_t L = gridDim.x;
     const uint64_t total = (uint64_t)L * k;
-    for (int b = 0; b < (int)a.nq; ++b) {
+    for (unsigned b = fin; b < a.nq; b += n_fin) {
         uint64_t *buf = bufs + (size_t)b * cap;
         const volatile uint64_t *cand = a.cand + (size_t)b * total;
         if (threadIdx.x == 0) { cnt_s[b] = 0; thr_s[b] = KEY_EMPTY; }
@@ -537,7 +543,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_multi_cta_topk_kernel(co
         for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) a.out_keys[(size_t)b * k + j] = buf[j];
         __syncthreads();
     }
-    if (threadIdx.x == 0) { a.ticket[0] = 0; a.ticket[1] = 0; }
+    if (threadIdx.x == 0 && atomicAdd(a.ticket + 2, 1u) == n_fin - 1) { a.ticket[0] = 0; a.ticket[1] = 0; a.ticket[2] = 0; }
 }
 
 
