@@ -945,6 +945,14 @@ def extras_small(cs, _lib, lib, d, k):
                                "e2e_ms_per_batch_of_query_variants": variants}
         st.close()
     out["api"] = "VectorStore.search_ids -> csgpu_search, host pointers in and out, one query per call"
+    # the same calls without Python in the loop: a plain-C program over include/csgpu.h (tools/bench_c_abi.c, built by build())
+    exe = os.path.join(ROOT, "build", "bench_c_abi")
+    if os.path.exists(exe):
+        try:
+            r = subprocess.run([exe, "100000", "200000"], capture_output=True, text=True, timeout=120)
+            out["c_abi_latency_plain_c_host"] = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")] or {"error": r.stderr[-300:]}
+        except Exception as e:  # noqa: BLE001
+            out["c_abi_latency_plain_c_host"] = {"error": repr(e)[:200]}
     return out
 
 
