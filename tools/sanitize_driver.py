@@ -32,8 +32,23 @@ st.search_variants_ids(qs[:5], 20)                          # device-side dedup 
 st.search_batch_ids(qs[:12], 10)                            # 9..16 queries in one pass (two query groups), per-warp lists
 st.search_batch_ids(qs[:16], 200)                           # ... and CTA buffers
 st.search_variants_ids(qs[:9], 200)                         # the reference's hybrid shape: 9 variants x limit 200
+os.environ["CSGPU_BATCH_SIMT"] = "1"
 st.search_batch_ids(qs[:40], 20)                            # fp32 SIMT GEMM, 64-query tile (setmaxnreg warp specialisation)
 st.search_batch_ids(qs, 20)                                 # fp32 SIMT GEMM, 128-query tile + select
+assert st.device_stats().batch_route == 1
+os.environ["CSGPU_BATCH_SIMT"] = "0"
+os.environ["CSGPU_GEMM_MIN_BATCH"] = "2"
+for nb, kk in ((70, 20), (5, 10), (40, 200)):               # tcgen05 kind::tf32 filter off the fp32 rows + rescoring select
+    t = st.search_batch_ids(qs[:nb], kk)                    # (70: 128 query rows per chunk; 5 / 40: the small TMA box + zeroed rows)
+    assert st.device_stats().batch_route == 3
+    for j in (0, nb - 1):
+        gi, gd = st.search_ids(qs[j], kk)
+        assert np.array_equal(t[0][j], gi) and np.array_equal(t[1][j], gd)
+v1 = st.search_variants_ids(qs[:9], 50)                     # variants as one tf32 batch + host dedup ...
+os.environ["CSGPU_GEMM_MIN_BATCH"] = "100000"
+v2 = st.search_variants_ids(qs[:9], 50)                     # ... equal the multi-query scan + device dedup
+assert np.array_equal(v1[0], v2[0]) and np.array_equal(v1[1], v2[1])
+os.environ.pop("CSGPU_GEMM_MIN_BATCH")
 st.set_tensor_prefilter(True)
 a = st.search_batch_ids(qs, 20)                             # tcgen05 filter + rescoring select
 for j in (0, 69):
