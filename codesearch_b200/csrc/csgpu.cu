@@ -925,9 +925,29 @@ static int search_one(const csgpu_index *ix, const float *q, uint32_t k, const u
 }
 
 // nq (2..8) queries in ONE pass over every shard; results [nq][k] land in ctx0->out_pin.
+// Bounds the multi-query scans in flight on an index (csgpu_index::MULTI_SLOTS): held from before the first launch until the
+// results are back.
+struct MultiSlot {
+    const csgpu_index *ix;
+    explicit MultiSlot(const csgpu_index *ix_) : ix(ix_)
+    {
+        std::unique_lock<std::mutex> lk(ix->multi_mu);
+        ix->multi_cv.wait(lk, [&] { return ix->multi_running < csgpu_index::MULTI_SLOTS; });
+        ++ix->multi_running;
+    }
+    ~MultiSlot()
+    {
+        { std::lock_guard<std::mutex> lk(ix->multi_mu); --ix->multi_running; }
+        ix->multi_cv.notify_one();
+    }
+    MultiSlot(const MultiSlot &) = delete;
+    MultiSlot &operator=(const MultiSlot &) = delete;
+};
+
 static int search_multi(const csgpu_index *ix, const float *q, uint32_t nq, uint32_t k,
                         uint32_t *out_ids, float *out_dist, uint32_t *out_n)
 {
+    MultiSlot slot(ix);
     const size_t G = ix->shards.size();
     std::vector<SearchCtx *> ctx(G, nullptr);
     int rc = CSGPU_OK;
@@ -987,6 +1007,7 @@ static int search_multi(const csgpu_index *ix, const float *q, uint32_t nq, uint
 static int search_variants(const csgpu_index *ix, const float *q, uint32_t b, uint32_t k,
                            uint32_t *out_ids, float *out_dist, uint32_t *out_n)
 {
+    MultiSlot slot(ix);
     const size_t G = ix->shards.size();
     std::vector<SearchCtx *> ctx(G, nullptr);
     int rc = CSGPU_OK;

@@ -224,6 +224,13 @@ struct csgpu_index {
     uint64_t nonfinite_rows = 0;
     uint64_t tombstones = 0;
     mutable std::atomic<float> last_search_us{0.f};
+    // Multi-query scans in flight on this index (scan_multi.cuh). Their last nq <= 16 CTAs wait, resident, for the rest of
+    // their grid; with at most MULTI_SLOTS such kernels running at once the waiting CTAs can never fill a device's CTA slots
+    // (6 x 16 = 96 < 148 even at one CTA per SM), whatever else runs — so every grid always gets the slots it needs to finish.
+    static constexpr int MULTI_SLOTS = 6;
+    mutable std::mutex multi_mu;
+    mutable std::condition_variable multi_cv;
+    mutable int multi_running = 0;
     mutable std::atomic<uint32_t> batch_route{0};          // CSGPU_ROUTE_* of the last GEMM-shaped batch
     mutable std::atomic<float> filter_max_err{0.f};        // largest |d_filter - d_f32| its rescoring saw
     mutable std::atomic<uint64_t> prefilter_rescored{0};   // fp32 rows read by the last tensor-prefilter batch chunk

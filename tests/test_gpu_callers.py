@@ -91,6 +91,38 @@ def test_coalescing_concurrent_searches_bit_identical(cs, oracle, shadow):
     check_topk(gi, gd, oi, od, o64, k)
 
 
+def test_many_threads_of_multi_query_scans(cs):
+    """24 host threads run multi-query scans at once on one index. The scans' last CTAs wait, resident, for the rest of their
+    grid (scan_multi.cuh finishers), so the library bounds how many run at a time (MultiSlot): all of them finish, every
+    list equals the single-query kernel's."""
+    rng = np.random.default_rng(78)
+    n, d, T = 60_000, 384, 24
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    st = make_store(cs, rows)
+    qs = rng.standard_normal((T, 9, d)).astype(np.float32)
+    ks = [10, 50, 200]
+    want = {(j, k): [st.search_ids(qs[j, v], k) for v in range(9)] for j in range(0, T, 6) for k in ks}
+    errs = []
+
+    def work(j):
+        try:
+            for rep in range(6):
+                k = ks[(j + rep) % 3]
+                oi, od, on = st.search_batch_ids(qs[j], k)             # 9 queries: one 16-query pass (small corpus: scan route)
+                vi, vd = st.search_variants_ids(qs[j, :5], k)           # and the variants path
+                if (j, k) in want:
+                    for v in range(9):
+                        if not (np.array_equal(oi[v], want[(j, k)][v][0]) and np.array_equal(od[v].view(np.uint32), want[(j, k)][v][1].view(np.uint32))):
+                            errs.append((j, k, v))
+        except Exception as e:  # noqa: BLE001
+            errs.append((j, repr(e)))
+    ts = [threading.Thread(target=work, args=(j,), daemon=True) for j in range(T)]
+    [t.start() for t in ts]
+    [t.join(timeout=120) for t in ts]
+    assert not any(t.is_alive() for t in ts), "multi-query scans hung"
+    assert not errs, errs[:3]
+
+
 def test_coalescing_many_callers_share_one_tensor_core_batch(cs, oracle):
     """Round 2: on an fp32 index whose batches run the tf32 tensor-core filter (csrc/gemm_tf32.cuh) a coalesced group is up
     to 128 callers — one 128-query block costs about what one query costs. 48 threads hammer csgpu_search (the reference's
