@@ -8,8 +8,9 @@
 // Why this shape. kind::tf32 reads the 32-bit containers as they sit in HBM and uses sign + 8 exponent + 10 mantissa bits:
 // no shadow copy of the corpus (the bf16 tensor prefilter of rescore.cuh needs +50 % HBM), no conversion pass. The fp32
 // SIMT kernel (gemm_simt.cuh) is bound by the FP32 FMA pipe at ~52 TFLOP/s; the tensor pipe runs the same contraction
-// ~20x faster and leaves the pass bound by memory: HBM for up to 128 queries (one pass over the rows, ~2.2 ms at
-// 10M x 384), L2 -> SM bandwidth above (every 128-query block re-reads the row tiles from L2).
+// ~15x faster: up to 128 queries the pass is bound by HBM (one pass over the rows, ~2.3 ms at 10M x 384; ncu: 85 % of the
+// DRAM peak), above by the tf32 tensor pipe itself (half the bf16 rate; ncu at 1024 queries: pipe 80 % active, its memory
+// side 88 %, L2 -> SM ~10 TB/s because every 128-query block re-reads the row tiles from L2).
 //
 // One CTA = 128 queries (MMA M = 128, one TMEM lane per query) x a stream of 256-row tiles (MMA N = 256) x K = dim in
 // 32-float chunks (128 B = one swizzle row; UMMA_K = 8 -> 4 MMAs per chunk). 128 queries x 384 floats = 192 KB cannot
@@ -105,6 +106,9 @@ gemm_tf32_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
                 asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
                 uint32_t it = 0;
                 for (uint64_t t = a.tile_begin + group; t < a.tile_end; t += n_groups) {
+                    // (A contiguous cp.async.bulk.prefetch.L2 of the upcoming tile — DRAM streams it page by page, the strided
+                    //  128-byte boxes then hit L2 — was built and measured: 16 queries 2.34 -> 4.11 ms, 1024 queries 12.0 -> 15.3;
+                    //  profiles/r02_tf32_prefetch_ab.txt. Not in the code.)
                     for (uint32_t kc = 0; kc < a.n_kchunks; ++kc, ++it) {
                         const int s = it % STAGES;
                         const uint32_t ph = (it / STAGES) & 1;
