@@ -567,8 +567,14 @@ static int batch_search_shard(const csgpu_index *ix, Shard *sh, BatchCtx *c, con
     // prefilter's margin); that has to stay well inside the select kernel's sort buffer.
     static const int env_growth = getenv("CSGPU_BATCH_GROWTH") ? std::max(2, atoi(getenv("CSGPU_BATCH_GROWTH"))) : 0;
     const double per_k = rescore_path(ix, sh) ? 2.8 : 1.5;
-    const uint64_t growth = env_growth ? (uint64_t)env_growth
-                                       : 1 + std::min<uint64_t>(BF_PHASE_GROWTH - 1, std::max<uint64_t>(1, (uint64_t)(SEL_SORT_CAP / (per_k * k))));
+    uint64_t growth = env_growth ? (uint64_t)env_growth
+                                 : 1 + std::min<uint64_t>(BF_PHASE_GROWTH - 1, std::max<uint64_t>(1, (uint64_t)(SEL_SORT_CAP / (per_k * k))));
+    // Small corpora (<= 512k rows) are bound by the fixed cost of a phase (~40 us: launch, TMEM, pipeline fill, select), not by
+    // its rows: grow faster where the candidates still fit a 2048-key sort, so 100k rows are two phases instead of three
+    // (profiles/r02_growth_ab.txt: 16 queries x top-10 over 100k rows 0.25 -> 0.23 ms; at 10M rows the larger factor is no
+    // faster — 1024 queries: +2 % — so it stays 8 there)
+    if (!env_growth && sh->n_built <= 512 * 1024)
+        growth = std::max<uint64_t>(growth, 1 + std::min<uint64_t>(63, (uint64_t)(2048 / (per_k * k))));
     unsigned scalar_host[6] = {0, 0, 0, 0, 0, 0};
     for (int attempt = 0; attempt < 2; ++attempt) {
         const bool careful = attempt == 1;
