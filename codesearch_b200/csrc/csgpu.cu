@@ -1596,7 +1596,8 @@ static bool tf32_route_is_faster(const csgpu_index *ix, uint32_t b, uint32_t k)
     for (const Shard *sh : ix->shards) rows = std::max<uint64_t>(rows, sh->n_built);
     const double mb = (double)rows * ix->dim_pad * sizeof(float) / 1e6;
     const uint32_t nqb = (b + 127) / 128;
-    const double t_tc = (k > 32 ? 260.0 : 205.0) + mb / 6.4 * (nqb == 1 ? 1.0 : 0.3 + 0.57 * nqb);
+    const double t_tc = (k > 32 ? 260.0 : 205.0) - (rows <= 512 * 1024 ? 20.0 : 0.0) /* two phases instead of three */
+                        + mb / 6.4 * (nqb == 1 ? 1.0 : 0.3 + 0.57 * nqb);
     double t_scan = 0.0;
     if (multi_scan_supported(ix->dim4, k)) {
         const uint32_t MQ = multi_scan_max_queries();
