@@ -1,7 +1,9 @@
 // gemm_topk.cu — the batched search path (BASELINE config C3): TMA tensor maps, the phase loop around the
-// GEMM-shaped kernels and the per-query exact select kernel. Two contraction kernels share it:
-//   fp32 index (default): gemm_simt_topk_kernel  (gemm_simt.cuh, register-tiled FP32 SIMT)
-//   bf16 index (opt-in) : gemm_topk_kernel       (gemm_topk.cuh, tcgen05 / TMEM)
+// GEMM-shaped kernels and the per-query exact select kernel. Three contraction kernels share it:
+//   fp32 index (default) : gemm_tf32_topk_kernel (gemm_tf32.cuh, tcgen05 kind::tf32 straight off the fp32 rows, as a FILTER;
+//                          survivors rescored exactly by select_sorted_kernel<.., RESCORE>, rescore.cuh)
+//   fp32 index, dim > 1024 or CSGPU_BATCH_SIMT=1 : gemm_simt_topk_kernel (gemm_simt.cuh, register-tiled FP32 SIMT)
+//   bf16 index, or the opt-in bf16 shadow of an fp32 index : gemm_topk_kernel (gemm_topk.cuh, tcgen05 kind::f16 / TMEM)
 // plus the bf16 index's storage hooks. See gemm_topk.cuh for the progressive-threshold design.
 #include <algorithm>
 #include <cmath>

@@ -137,14 +137,24 @@ int  csgpu_search(const csgpu_index *ix, const float *q, uint32_t q_len, uint32_
                   uint32_t *out_ids /*[k]*/, float *out_dist /*[k]*/, uint32_t *out_n);
 
 /* Host micro-batcher (off by default). When enabled, concurrent csgpu_search calls with the same k are coalesced
- * into one multi-query pass over the corpus (up to 8 per pass) — the caller pattern of src/search/mod.rs:508-511
+ * into one csgpu_search_batch over the corpus (groups of up to 16 callers; up to 128 where the group runs as a tensor-core
+ * batch, see csgpu_search_batch) — the caller pattern of src/search/mod.rs:508-511
  * (rayon par_iter over <= 9 query variants) and of concurrent MCP/HTTP readers. Results are bit-identical to the
  * uncoalesced call. window_us > 0 lets a pass linger that long for company before launching (0 = never wait:
  * only requests that arrive while a pass is in flight get batched). */
 int  csgpu_set_coalescing(csgpu_index *ix, uint32_t enabled, uint32_t window_us);
 
 /* b queries [b, dim]; outputs [b, k] (row j holds out_n[j] valid entries). Serves the
- * <= 9 query variants of src/search/mod.rs:508-511 in one pass over the corpus. */
+ * <= 9 query variants of src/search/mod.rs:508-511 in one pass over the corpus, and batches of any size.
+ * fp32 index: every list is what csgpu_search returns for that query — ids AND distances bit for bit — on every route
+ * but the SIMT one. Routes, chosen by a measured cost model (csrc/csgpu.cu tf32_route_is_faster):
+ *   - a few queries over a small corpus: one multi-query scan launch (<= 16 queries per pass, scan_multi.cuh);
+ *   - otherwise (from 2 queries at 10M rows, ~17 at 100k rows): the tensor cores straight off the fp32 rows —
+ *     tcgen05.mma kind::tf32 as a FILTER with a proven margin (|d_tf32 - d_f32| < 1.1e-3 for dim <= 1024), survivors
+ *     rescored with the single-query kernel's arithmetic (gemm_tf32.cuh, rescore.cuh). No shadow copy, no opt-in;
+ *   - dim > 1024 (or CSGPU_BATCH_SIMT=1): the register-tiled fp32 SIMT kernel (gemm_simt.cuh; same ranking, distances may
+ *     differ from csgpu_search in the last ulp).
+ * csgpu_stats_t.batch_route reports the contraction the last GEMM-shaped batch used. */
 int  csgpu_search_batch(const csgpu_index *ix, const float *q, uint32_t q_len, uint32_t b, uint32_t k,
                         uint32_t *out_ids, float *out_dist, uint32_t *out_n /*[b]*/);
 
@@ -152,8 +162,10 @@ int  csgpu_search_batch(const csgpu_index *ix, const float *q, uint32_t q_len, u
  * unit rows (+50 % HBM; dim % 64 == 0, dim <= 512). csgpu_search_batch then contracts the batch on the tensor cores
  * (tcgen05 / TMEM) against the shadow as a FILTER with a proven error margin, and rescores the survivors from the fp32
  * rows with the single-query kernel's arithmetic: ids AND distances are bit-identical to csgpu_search on every query
- * (codesearch_b200/csrc/rescore.cuh has the bound). Off by default: the register-tiled fp32 SIMT kernel stays the
- * default batched path. May be called before or after csgpu_build; the shadow follows every later build / load. */
+ * (codesearch_b200/csrc/rescore.cuh has the bound). Off by default: the default batched path needs no shadow (tf32 off
+ * the fp32 rows, see csgpu_search_batch); this switch buys the bf16 rate of the tensor pipe for large batches (1024 x
+ * top-100 over 10M x 384: ~8 ms instead of 12). May be called before or after csgpu_build; the shadow follows every later
+ * build / load. */
 int  csgpu_set_tensor_prefilter(csgpu_index *ix, uint32_t enabled);
 
 /* Opt-in, fp32 index only: exact fp32 results for csgpu_search from ONE pass over a 1-byte-per-element shadow of
