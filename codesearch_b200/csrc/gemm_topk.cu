@@ -577,6 +577,18 @@ static int batch_search_shard(const csgpu_index *ix, Shard *sh, BatchCtx *c, con
     // faster — 1024 queries: +2 % — so it stays 8 there)
     if (!env_growth && sh->n_built <= 512 * 1024)
         growth = std::max<uint64_t>(growth, 1 + std::min<uint64_t>(63, (uint64_t)(2048 / (per_k * k))));
+    // Balanced phases: `growth` is the LARGEST factor the candidate buffers allow; the phase count it implies is kept, but the
+    // factor is lowered to the one that reaches the end of the corpus in exactly that many phases (10M rows: 5 phases need
+    // 7.03, not 8). Fewer candidates per phase then — for k = 100 they fit a 1024-key sort instead of a 2048-key one.
+    double growth_f = (double)growth;
+    {
+        const uint64_t first = std::max<uint64_t>(1, (BF_CAP / 2) / tile_rows);
+        if (!env_growth && n_tiles > first) {
+            const double ratio = (double)n_tiles / (double)first;
+            const double steps = std::ceil(std::log(ratio) / std::log((double)growth) - 1e-9);   // growth steps after phase 0
+            growth_f = std::min((double)growth, std::max(2.0, std::pow(ratio, 1.0 / std::max(1.0, steps)) * 1.0005));
+        }
+    }
     unsigned scalar_host[6] = {0, 0, 0, 0, 0, 0};
     for (int attempt = 0; attempt < 2; ++attempt) {
         const bool careful = attempt == 1;
@@ -593,7 +605,7 @@ static int batch_search_shard(const csgpu_index *ix, Shard *sh, BatchCtx *c, con
             rc = run_range(ix, sh, c, map_q, n_qblocks, nq, k, done, t1, n_tiles, careful, 0);
             if (rc) return rc;
             done = t1;
-            next = done * (growth - 1);
+            next = std::max<uint64_t>(1, (uint64_t)std::ceil((double)done * (growth_f - 1.0)));
         }
         if (n_tiles == 0) {   // no rows in the matrix: the select still injects the zero-norm ids and writes the output
             CS_CUDA(cudaMemcpyAsync(c->count_saved, c->count, nq_pad * sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
