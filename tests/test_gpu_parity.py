@@ -336,7 +336,21 @@ def test_empty_filters_allow_nothing_on_a_fresh_store(cs):
         assert len(st.search_ids(q, 10)[0]) == 10
 
 
-def test_batch_matches_single(cs, oracle):
+@pytest.fixture
+def scan_route():
+    """The tests below pin the multi-query SCAN kernels (scan_multi.cuh). On its own the library routes a batch by a cost
+    model and may answer it on the tensor cores instead (tests/test_gpu_tf32_batch.py covers that route)."""
+    import os
+    old = os.environ.get("CSGPU_GEMM_MIN_BATCH")
+    os.environ["CSGPU_GEMM_MIN_BATCH"] = "100000"
+    yield
+    if old is None:
+        os.environ.pop("CSGPU_GEMM_MIN_BATCH", None)
+    else:
+        os.environ["CSGPU_GEMM_MIN_BATCH"] = old
+
+
+def test_batch_matches_single(cs, oracle, scan_route):
     rng = np.random.default_rng(12)
     n, d = 10000, 384
     rows = rng.standard_normal((n, d)).astype(np.float32)
@@ -356,7 +370,7 @@ def test_batch_matches_single(cs, oracle):
     (20000, 384, 5, 256), (5000, 384, 4, 300), (5000, 768, 8, 200), (5000, 1024, 7, 25), (5000, 128, 16, 64),
     (5000, 256, 3, 10), (5000, 512, 8, 128), (3000, 100, 5, 10), (3, 384, 8, 10), (1, 384, 2, 1),
 ])
-def test_batch_parity(cs, oracle, n, d, b, k):
+def test_batch_parity(cs, oracle, scan_route, n, d, b, k):
     from codesearch_b200 import _lib
     rng = np.random.default_rng(n + d * 7 + b * 13 + k)
     rows = rng.standard_normal((n, d)).astype(np.float32)
@@ -381,7 +395,7 @@ def test_batch_parity(cs, oracle, n, d, b, k):
 
 
 @pytest.mark.parametrize("d", [128, 384, 768])
-def test_sixteen_query_pass_bit_identical_to_single(cs, d):
+def test_sixteen_query_pass_bit_identical_to_single(cs, scan_route, d):
     """Round 2: 9..16 queries share ONE pass (scan_multi.cuh, MQ = 16 x R = 2) — the reference's default hybrid search is
     <= 9 query variants x limit 200 (src/search/mod.rs:498-511). Same FMA chain and shuffle tree per (row, query), so every
     list is bit-identical to csgpu_search, for the per-warp lists (k <= 32) and the CTA buffers (k > 32) alike."""
