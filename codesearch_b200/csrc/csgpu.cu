@@ -202,7 +202,12 @@ template <int V, bool EXACT, bool BIG, int OCC>
 static cudaError_t launch_scan_v(const ScanArgs &a, uint32_t grid, size_t smem, cudaStream_t st)
 {
     const int m = scan_static_mode();
-    if (m == 1 || (m == 2 && BIG)) return launch_scan_vd<V, EXACT, BIG, OCC, false>(a, grid, smem, st);
+    // Small corpora (k <= 32): the fixed stride wins — every warp's first rows are in flight at once instead of behind a
+    // round trip to the work counter, and there is no long run for the faster SMs to steal. build/tune_scan on one B200
+    // (profiles/r02_tune_scan_small.txt): 50k / 100k / 200k / 400k rows static -10 / -9 / -7 / -2 %, 1M rows equal, from 2M
+    // rows on the counter is 1-2 % ahead (10M: 1.5-2.8 %, round 1). Crossover taken at 768 MB of rows per device.
+    const bool small = !BIG && m == 0 && (uint64_t)a.n_rows * a.dim4 * sizeof(float4) <= (768ull << 20);
+    if (m == 1 || (m == 2 && BIG) || small) return launch_scan_vd<V, EXACT, BIG, OCC, false>(a, grid, smem, st);
     return launch_scan_vd<V, EXACT, BIG, OCC, true>(a, grid, smem, st);
 }
 
