@@ -389,7 +389,9 @@ static int enqueue_scan_multi(const csgpu_index *ix, const Shard *sh, SearchCtx 
     // measured (profiles/r02_static_vs_dynamic_filtered_multi.txt): the work counter is worth ~1.5 % with the CTA-shared
     // buffers (8 queries x top-100: 3.26 vs 3.31 ms) and costs ~2 % with the per-warp lists (top-10: 2.81 vs 2.74 ms), so
     // each kernel gets what is faster
-    a.static_split = scan_static_mode() == 1 ? 1u : (scan_dynamic_all() ? 0u : (k > 32 ? 0u : 1u));
+    // k > 32 (CTA buffers): work counter, except on small corpora (same crossover as the single-query scan, launch_scan_v)
+    const bool small_corpus = (uint64_t)sh->n_built * ix->dim4 * sizeof(float4) <= (768ull << 20);
+    a.static_split = scan_static_mode() == 1 ? 1u : (scan_dynamic_all() ? 0u : ((k > 32 && !small_corpus) ? 0u : 1u));
     const uint32_t R = multi_scan_rows_per_iter(ix->dim4, nq);
     const uint64_t want = (sh->n_built + SCAN_WARPS * R - 1) / (SCAN_WARPS * R);
     // the buffer capacity depends on the grid (the last CTA takes one key per CTA and column) and the grid on what fits an SM
