@@ -102,6 +102,38 @@ def test_tf32_batch_bit_identical_to_single_query(cs, oracle, n, d, b, k):
         assert od[1, top3.index(a)] == od[1, top3.index(c)]
 
 
+def test_tf32_randomised_shapes_against_the_single_query_kernel(cs):
+    """Random (rows, dim, batch, k) — including rows < one tile, k > rows, duplicated and zero rows, zero and repeated queries,
+    dims that need the zero-filled last K chunk or padded columns: every list of every batch equals csgpu_search's."""
+    rng = np.random.default_rng(2024)
+    dims = [32, 36, 64, 100, 128, 200, 384, 385, 512, 768, 1000, 1024]
+    for it in range(14):
+        d = int(rng.choice(dims))
+        n = int(rng.choice([1, 7, 255, 256, 257, 1000, 4097, 20_000, 33_333]))
+        b = int(rng.choice([2, 3, 8, 9, 31, 127, 128, 129, 260]))
+        k = int(rng.choice([1, 2, 10, 32, 33, 100, 256, 257, 700]))
+        rows = rng.standard_normal((n, d)).astype(np.float32)
+        if n > 10:
+            rows[n // 2] = 0.0
+            rows[1] = rows[0]
+            rows[n - 1] = rows[0] * np.float32(3.0)            # same direction, other norm: equal distance up to rounding
+        ids = rng.permutation(3 * n)[:n].astype(np.uint32)
+        st = _store(cs, rows, ids)
+        qs = rng.standard_normal((b, d)).astype(np.float32)
+        qs[0] = rows[0]
+        if b > 2:
+            qs[2] = 0.0
+            qs[b - 1] = qs[1]
+        oi, od, on = st.search_batch_ids(qs, k)
+        s = st.device_stats()
+        assert s.batch_route == ROUTE_TF32 and s.filter_max_err < TF_MARGIN, (it, n, d, b, k, s.batch_route, s.filter_max_err)
+        for j in range(b):
+            gi, gd = st.search_ids(qs[j], k)
+            assert on[j] == len(gi), (it, n, d, b, k, j)
+            assert np.array_equal(oi[j, : on[j]], gi) and np.array_equal(od[j, : on[j]].view(np.uint32), gd.view(np.uint32)), (it, n, d, b, k, j)
+        st.close()
+
+
 def test_tf32_route_is_the_default_and_simt_is_the_override(cs):
     rng = np.random.default_rng(3)
     rows = rng.standard_normal((20_000, 384)).astype(np.float32)
