@@ -175,9 +175,12 @@ static int make_map(CUtensorMap *map, const void *base, uint64_t rows, uint32_t 
     const cuuint64_t gstride[1] = {(cuuint64_t)cols * esz};
     const cuuint32_t box[2] = {128 / esz, box_rows};
     const cuuint32_t estr[2] = {1, 1};
+    static const int env_promo = getenv("CSGPU_TMA_L2_PROMO") ? atoi(getenv("CSGPU_TMA_L2_PROMO")) : 3;   // experiments: 0 none, 1 64 B, 2 128 B, 3 256 B
+    const CUtensorMapL2promotion promo = env_promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : env_promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                         : env_promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base),
                     gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(CSGPU_ERR_CUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
     return CSGPU_OK;
 }
