@@ -98,3 +98,23 @@ def test_encode_decode_keys_round_trip():
     oi = np.zeros(50, np.uint32); od = np.zeros(50, np.float32); n = ctypes.c_uint32()
     lib.csgpu_decode_keys(keys.ctypes.data_as(_lib._u64p), 50, oi.ctypes.data_as(_lib._u32p), od.ctypes.data_as(_lib._f32p), ctypes.byref(n))
     assert n.value == 37 and np.array_equal(oi[:37], ids) and np.array_equal(od[:37], dist)
+
+
+def test_header_is_valid_c_and_the_c_host_compiles():
+    """include/csgpu.h is a C header (the reference's host is Rust over a C ABI): the plain-C latency bench that uses most of
+    it must compile as C11 with warnings as errors, and the header alone as C99 (no C++-isms, no torch types)."""
+    import os
+    import shutil
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gcc = shutil.which("gcc")
+    assert gcc, "gcc is part of the image"
+    inc = os.path.join(root, "include")
+    subprocess.check_call([gcc, "-std=c11", "-Wall", "-Werror", "-D_POSIX_C_SOURCE=200809L", "-fsyntax-only", "-I", inc,
+                           os.path.join(root, "tools", "bench_c_abi.c")])
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "only_header.c")
+        with open(src, "w") as f:
+            f.write('#include "csgpu.h"\nint main(void) { csgpu_stats_t s; (void)s; return (int)(CSGPU_ABI_VERSION == 0); }\n')
+        subprocess.check_call([gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, src])
