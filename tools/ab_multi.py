@@ -1,3 +1,11 @@
+#!/usr/bin/env python
+"""A/B of the multi-query scan kernels on ONE box: device time of csgpu_search_batch (scan route pinned with
+CSGPU_GEMM_MIN_BATCH) at 100k and 10M rows, for this build or for another library given as argv[1] — e.g. the same objects
+with an older scan_multi.o linked in (how profiles/r02_multi_tail_ab.txt was made):
+    nvcc ... -c <old>/scan_multi.cu -o /tmp/old/scan_multi.o
+    nvcc -shared -cudart static build/obj/{csgpu,scan_filtered,gemm_topk,snapshot,scan_i8}.o /tmp/old/scan_multi.o -o build/ab/libcsgpu_oldmulti.so
+    python tools/ab_multi.py build/ab/libcsgpu_oldmulti.so; python tools/ab_multi.py
+A diagnostic, not a benchmark line."""
 import sys, os, json, time
 sys.path.insert(0, os.getcwd())
 import numpy as np
