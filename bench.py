@@ -940,6 +940,15 @@ def extras_small(cs, _lib, lib, d, k):
             for i in range(100):
                 st.search_batch_ids(qs[:nv], k)
             variants[str(nv)] = round((time.perf_counter() - t0) / 100 * 1e3, 4)
+        # the reference's hybrid default: <= 9 query variants x retrieval limit 200, best distance per chunk id, one list
+        # (src/search/mod.rs:498-511, :513-590) = ONE csgpu_search_variants call
+        for i in range(5):
+            st.search_variants_ids(qs[:9], 200)
+        t0 = time.perf_counter()
+        for i in range(100):
+            st.search_variants_ids(qs[i % 8: i % 8 + 9], 200)
+        hybrid_ms = (time.perf_counter() - t0) / 100 * 1e3
+        variants["9_variants_x_limit_200_deduplicated (csgpu_search_variants)"] = round(hybrid_ms, 4)
         out[f"{rows}_rows"] = {"e2e_ms_per_query": round(dt * 1e3, 4), "qps": round(1 / dt, 1),
                                "device_us": round(float(np.median(dev)), 1), "top_ids_query0": [int(i) for i in st.search_ids(qs[0], k)[0]],
                                "e2e_ms_per_batch_of_query_variants": variants}
