@@ -92,6 +92,7 @@ SIGNATURES = {
     "csgpu_search_filtered": (ctypes.c_int, [_vp, _f32p, ctypes.c_uint32, ctypes.c_uint32, _u64p, ctypes.c_uint64, _u32p, _f32p, _u32p]),
     "csgpu_append_tagged": (ctypes.c_int, [_vp, _f32p, _u32p, _u32p, ctypes.c_uint64]),
     "csgpu_search_tagged": (ctypes.c_int, [_vp, _f32p, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(Predicate), _u32p, _f32p, _u32p]),
+    "csgpu_search_variants_tagged": (ctypes.c_int, [_vp, _f32p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(Predicate), _u32p, _f32p, _u32p]),
     "csgpu_get_tags": (ctypes.c_int, [_vp, _u32p, ctypes.c_uint64, _u32p]),
     "csgpu_search_tagged_keys_device": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.POINTER(Predicate), ctypes.c_uint32, _vp, _vp]),
     "csgpu_append_synthetic_tagged": (ctypes.c_int, [_vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32]),

@@ -369,7 +369,9 @@ static int enqueue_merge(const uint64_t *keys_dev, uint32_t n_lists, uint32_t nq
 
 // Enqueue one multi-query (nq <= 8) scan of `sh`. q_dev: [nq, dim_pad]; out_keys: [nq, k].
 static int enqueue_scan_multi(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const float *q_dev, uint32_t nq,
-                              uint32_t k, bool with_zero_ids, uint64_t *out_keys, cudaStream_t st)
+                              uint32_t k, bool with_zero_ids, uint64_t *out_keys, cudaStream_t st,
+                              const csgpu_predicate_t *pred = nullptr /* row-tag predicate */,
+                              const uint64_t *file_bitmap_dev = nullptr, uint64_t n_file_bits = 0)
 {
     MultiArgs a;
     a.rows = reinterpret_cast<const float4 *>(sh->rows);
@@ -381,6 +383,10 @@ static int enqueue_scan_multi(const csgpu_index *ix, const Shard *sh, SearchCtx 
     a.k = k;
     a.bitmap = nullptr;
     a.n_bits = 0;
+    if (pred) {
+        a.tags = sh->tags; a.lang_mask = pred->lang_mask; a.file_lo = pred->file_lo; a.file_hi = pred->file_hi;
+        a.bitmap = file_bitmap_dev; a.n_bits = n_file_bits;
+    }
     a.zero_ids = with_zero_ids ? ix->zero_ids_dev : nullptr;
     a.n_zero = with_zero_ids ? (uint32_t)ix->zero_ids.size() : 0;
     a.cand = c->cand;
@@ -1011,8 +1017,11 @@ static int search_multi(const csgpu_index *ix, const float *q, uint32_t nq, uint
 // by chunk id (best distance wins) and cut to the best k by dedup_variants_kernel. On a multi-device index every
 // shard does that for its own rows (a chunk id lives on exactly one shard, so per-shard dedup + a k-way merge of the
 // shards' lists on device 0 is the global dedup).
+// pred != nullptr (csgpu_search_variants_tagged): every variant is searched under the row-tag predicate. Small corpora
+// (<= 768 MB of rows per device: latency-bound) take the multi-query passes with the predicate applied to the results that
+// beat a threshold; larger ones one filtered scan per variant, which never reads a masked row — all lists stay on the device.
 static int search_variants(const csgpu_index *ix, const float *q, uint32_t b, uint32_t k,
-                           uint32_t *out_ids, float *out_dist, uint32_t *out_n)
+                           uint32_t *out_ids, float *out_dist, uint32_t *out_n, const csgpu_predicate_t *pred = nullptr)
 {
     MultiSlot slot(ix);
     const size_t G = ix->shards.size();
@@ -1024,25 +1033,42 @@ static int search_variants(const csgpu_index *ix, const float *q, uint32_t b, ui
     auto body = [&]() -> int {
         const size_t qbytes = (size_t)b * ix->dim_pad * sizeof(float);
         const uint32_t MQ = multi_scan_max_queries();
-        const bool multi_ok = multi_scan_supported(ix->dim4, k);
         const uint32_t total = b * k, npad = pow2_at_least(total, 64);
         const size_t smem = (size_t)npad * sizeof(uint64_t);
+        const uint64_t *file_bitmap = pred ? pred->file_bitmap : nullptr;
+        const uint64_t n_file_bits = file_bitmap ? pred->n_file_bits : 0;
+        const size_t bm_words = file_bitmap ? (size_t)((n_file_bits + 63) / 64) : 0;
         for (size_t g = 0; g < G; ++g) {
             Shard *sh = ix->shards[g];
             SearchCtx *c = ctx[g];
             DeviceGuard dg(sh->device);
+            const bool small_corpus = (uint64_t)sh->n_built * ix->dim4 * sizeof(float4) <= (768ull << 20);
+            const bool multi_ok = multi_scan_supported(ix->dim4, k) && (pred == nullptr || small_corpus);
             memset(c->q_pin, 0, qbytes);
             for (uint32_t j = 0; j < b; ++j) memcpy(c->q_pin + (size_t)j * ix->dim_pad, q + (size_t)j * ix->dim, (size_t)ix->dim * sizeof(float));
             CS_CUDA(cudaMemcpyAsync(c->q_dev, c->q_pin, qbytes, cudaMemcpyHostToDevice, c->stream));
+            const uint64_t *bm_dev = nullptr;
+            if (file_bitmap) {   // as in search_one: n_file_bits == 0 still needs a (never read) non-null pointer — it excludes every file
+                if (c->bitmap_dev == nullptr || c->bitmap_cap < bm_words) {
+                    CS_CUDA(cudaStreamSynchronize(c->stream));
+                    cudaFree(c->bitmap_dev); c->bitmap_dev = nullptr; c->bitmap_cap = 0;
+                    CS_CUDA(cudaMalloc(&c->bitmap_dev, std::max<size_t>(bm_words, 1) * sizeof(uint64_t)));
+                    c->bitmap_cap = std::max<size_t>(bm_words, 1);
+                }
+                if (bm_words) CS_CUDA(cudaMemcpyAsync(c->bitmap_dev, file_bitmap, bm_words * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+                bm_dev = c->bitmap_dev;
+            }
             if (g == 0) CS_CUDA(cudaEventRecord(c->ev0, c->stream));
             for (uint32_t j = 0; j < b;) {
                 const uint32_t nq = std::min(MQ, b - j);
                 int r;
                 if (multi_ok && nq >= 2) {
-                    r = enqueue_scan_multi(ix, sh, c, c->q_dev + (size_t)j * ix->dim_pad, nq, k, g == 0, c->out_dev + (size_t)j * k, c->stream);
+                    r = enqueue_scan_multi(ix, sh, c, c->q_dev + (size_t)j * ix->dim_pad, nq, k, g == 0, c->out_dev + (size_t)j * k, c->stream,
+                                           pred, bm_dev, n_file_bits);
                     j += nq;
                 } else {
-                    r = enqueue_scan(ix, sh, c, c->q_dev + (size_t)j * ix->dim_pad, k, nullptr, 0, g == 0, c->out_dev + (size_t)j * k, c->stream);
+                    r = enqueue_scan(ix, sh, c, c->q_dev + (size_t)j * ix->dim_pad, k, bm_dev, n_file_bits, g == 0, c->out_dev + (size_t)j * k, c->stream,
+                                     nullptr, 0, pred);
                     j += 1;
                 }
                 if (r) return r;
@@ -1718,6 +1744,24 @@ int csgpu_search_variants(const csgpu_index *ix, const float *q, uint32_t q_len,
     const bool tf32 = b >= 2 && batch_tf32_route(ix) && (env_s && *env_s ? b >= (uint32_t)atoi(env_s) : tf32_route_is_faster(ix, b, k));
     if (tf32) return search_variants_prefiltered(ix, q, b, k, out_ids, out_dist, out_n);
     return search_variants(ix, q, b, k, out_ids, out_dist, out_n);
+}
+
+int csgpu_search_variants_tagged(const csgpu_index *ix, const float *q, uint32_t q_len, uint32_t b, uint32_t k,
+                                 const csgpu_predicate_t *pred, uint32_t *out_ids, float *out_dist, uint32_t *out_n)
+{
+    if (out_n) *out_n = 0;
+    int rc = check_search_args(ix, q, q_len, k);
+    if (rc) return rc;
+    if (b == 0 || b > MAX_BATCH) return fail(CSGPU_ERR_ARG, "b must be in [1, 16] query variants");
+    if (ix->dtype != CSGPU_DTYPE_F32) return fail(CSGPU_ERR_ARG, "csgpu_search_variants_tagged needs an fp32 index");
+    if (!pred) return fail(CSGPU_ERR_ARG, "pred is null");
+    if (!pred->file_bitmap && pred->n_file_bits) return fail(CSGPU_ERR_ARG, "file_bitmap is null");
+    if (!all_finite(q, q_len * b)) return fail(CSGPU_ERR_ARG, "query contains NaN/Inf");
+    if (k == 0) return CSGPU_OK;
+    csgpu_predicate_t p = *pred;
+    static const uint64_t empty_word = 0;
+    if (p.file_bitmap && p.n_file_bits == 0) p.file_bitmap = &empty_word;   // an empty bitmap allows nothing
+    return search_variants(ix, q, b, k, out_ids, out_dist, out_n, &p);
 }
 
 int csgpu_search_keys_device(const csgpu_index *ix, const float *q_dev, uint32_t k, uint64_t *out_keys_dev, void *stream)

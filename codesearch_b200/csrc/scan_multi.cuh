@@ -34,7 +34,21 @@ struct MultiArgs {
     unsigned *ticket;      // [0] arrival ticket, [1] work counter of the dynamic row split, [2] finishers done (all self-resetting)
     uint64_t *out_keys;    // [nq][k]
     uint32_t static_split = 0;   // 1 = fixed-stride row split (CSGPU_SCAN_STATIC=1, A/B runs)
+    // row-tag predicate (csgpu_predicate_t; csgpu_search_variants_tagged): tags != nullptr switches it on, `bitmap` is then
+    // the optional per-FILE bitmap. Evaluated on the few (row, query) results that beat a threshold — every row is still
+    // read, which is the right trade for a handful of variants over a small corpus (the host routes by corpus size).
+    const uint32_t *tags = nullptr;
+    uint32_t lang_mask = 0, file_lo = 0, file_hi = 0;
 };
+
+// is row `row` (chunk id `id`) allowed under the launch's filter: id bitmap, or row-tag predicate (+ per-file bitmap)
+__device__ __forceinline__ bool multi_row_allowed(const MultiArgs &a, uint64_t row, uint32_t id)
+{
+    if (a.tags == nullptr) return id_allowed(a.bitmap, a.n_bits, id);
+    const uint32_t tag = __ldg(a.tags + row);
+    if (!tag_pass_static(tag, a.lang_mask, a.file_lo, a.file_hi)) return false;
+    return id_allowed(a.bitmap, a.n_bits, tag & 0x07FFFFFFu);
+}
 
 template <int NV, int O>
 __device__ __forceinline__ void butterfly_level(float (&v)[32], int lane)
@@ -235,7 +249,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, (E <= 4) ? 2 : 1) scan_multi_top
             if (my_active[g] && row < n && okey(dist) <= (uint32_t)(thr[g] >> 32)) {
                 const uint32_t id = a.ids[row];
                 const uint64_t kk = make_key(dist, id);
-                if (kk < thr[g] && id_allowed(a.bitmap, a.n_bits, id)) key = kk;
+                if (kk < thr[g] && multi_row_allowed(a, row, id)) key = kk;
             }
             unsigned m = __ballot_sync(FULL, key != KEY_EMPTY);
             if (m) {
@@ -310,10 +324,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, (E <= 4) ? 2 : 1) scan_multi_top
         for (uint32_t o = 0; o < a.n_zero && found < a.k; o += SCAN_WARPS * 32) {   // CTA-uniform loop; warp w sorts its 32 ids of the batch (the lists are merged across warps below)
             uint64_t key = KEY_EMPTY;
             const uint32_t i = o + threadIdx.x;
-            if (i < a.n_zero) {
-                const uint32_t id = a.zero_ids[i];
-                if (id_allowed(a.bitmap, a.n_bits, id)) key = make_key(0.f, id);
-            }
+            if (i < a.n_zero && zero_row_allowed(a.bitmap, a.n_bits, a.tags, a.lang_mask, a.file_lo, a.file_hi, a.zero_ids, a.n_zero, i))
+                key = make_key(0.f, a.zero_ids[i]);
             found += __syncthreads_count(key != KEY_EMPTY);
             zrun = warp_merge_low32(zrun, warp_sort32(key, lane), lane);
         }
@@ -453,7 +465,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_multi_cta_topk_kernel(co
             if (my_active[g] && row < n && okey(dist) <= (uint32_t)(thr[g] >> 32)) {
                 const uint32_t id = a.ids[row];
                 const uint64_t kk = make_key(dist, id);
-                if (kk < thr[g] && id_allowed(a.bitmap, a.n_bits, id))
+                if (kk < thr[g] && multi_row_allowed(a, row, id))
                     bufs[(size_t)(my_b + g * MQ) * cap + atomicAdd(&cnt_s[my_b + g * MQ], 1u)] = kk;
             }
         }
@@ -530,10 +542,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_multi_cta_topk_kernel(co
         uint32_t found = 0;   // zero-norm rows: distance 0.0, ascending id; the first k allowed ones suffice
         for (uint32_t o = 0; o < a.n_zero && found < k; o += blockDim.x) {
             uint64_t key = KEY_EMPTY;
-            if (o + threadIdx.x < a.n_zero) {
-                const uint32_t id = a.zero_ids[o + threadIdx.x];
-                if (id_allowed(a.bitmap, a.n_bits, id)) key = make_key(0.f, id);
-            }
+            if (o + threadIdx.x < a.n_zero &&
+                zero_row_allowed(a.bitmap, a.n_bits, a.tags, a.lang_mask, a.file_lo, a.file_hi, a.zero_ids, a.n_zero, o + threadIdx.x))
+                key = make_key(0.f, a.zero_ids[o + threadIdx.x]);
             found += __syncthreads_count(key != KEY_EMPTY);
             if (key < *thr_b) buf[atomicAdd(&cnt_s[b], 1u)] = key;
             if (__syncthreads_or(*reinterpret_cast<volatile unsigned *>(&cnt_s[b]) + blockDim.x > cap))

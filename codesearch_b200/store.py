@@ -357,6 +357,26 @@ class VectorStore:
     def search_variants(self, queries, limit: int) -> list[SearchResult]:
         return self._join(*self.search_variants_ids(queries, limit))
 
+    def search_variants_tagged_ids(self, queries, limit: int, pred: TagPredicate):
+        """search_variants_ids under a row-tag predicate (csgpu_search_variants_tagged): the reference's hybrid search with a
+        language / path filter (src/search/mod.rs:508-590 + the post-filters at :727-737) as one call."""
+        q = _f32(queries)
+        b, d = q.shape
+        k = int(limit)
+        oi = np.empty(max(k, 1), dtype=np.uint32)
+        od = np.empty(max(k, 1), dtype=np.float32)
+        on = ctypes.c_uint32(0)
+        cp = _lib.Predicate(pred.lang_mask & 0xFFFFFFFF, pred.file_lo, pred.file_hi & 0xFFFFFFFF, 0, None, 0)
+        bm = None
+        if pred.file_bitmap is not None:
+            bm = np.ascontiguousarray(pred.file_bitmap, dtype=np.uint64)
+            cp.file_bitmap = bm.ctypes.data
+            cp.n_file_bits = int(pred.n_file_bits)
+        _lib.check(self._lib.csgpu_search_variants_tagged(self._h, q.ctypes.data_as(_lib._f32p), d, b, k, ctypes.byref(cp),
+                                                          oi.ctypes.data_as(_lib._u32p), od.ctypes.data_as(_lib._f32p),
+                                                          ctypes.byref(on)))
+        return oi[: on.value].copy(), od[: on.value].copy()
+
     def set_tensor_prefilter(self, enabled: bool) -> None:
         """Opt-in (fp32 index): batches run on the tensor cores against a bf16 shadow as a filter, survivors are rescored
         in fp32 with the single-query kernel's arithmetic — results bit-identical to search() (csrc/rescore.cuh)."""

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define CSGPU_ABI_VERSION 7
+#define CSGPU_ABI_VERSION 8
 
 enum {
     CSGPU_OK            = 0,
@@ -230,6 +230,17 @@ int  csgpu_append_tagged(csgpu_index *ix, const float *rows, const uint32_t *ids
 int  csgpu_search_tagged(const csgpu_index *ix, const float *q, uint32_t q_len, uint32_t k,
                          const csgpu_predicate_t *pred,
                          uint32_t *out_ids, float *out_dist, uint32_t *out_n);
+
+/* csgpu_search_variants under a row-tag predicate: b (<= 16) query variants of one user query, each searched over the rows
+ * that pass `pred`, merged on the device (best distance per chunk id, then the best k, ascending (distance, id)); outputs [k].
+ * The reference's hybrid search with a language / path filter (src/search/mod.rs:508-590 followed by the post-filters at
+ * :727-737) as ONE call — and, unlike a post-filter, `k` results survive. Equals the dedup of b csgpu_search_tagged lists
+ * bit for bit. Small corpora (<= 768 MB of rows per device) take multi-query passes with the predicate applied to the
+ * results that beat a threshold (one launch per <= 16 variants); larger ones one filtered scan per variant (masked rows
+ * are never read); the lists stay on the device either way. file_bitmap is a HOST pointer. */
+int  csgpu_search_variants_tagged(const csgpu_index *ix, const float *q /*[b, dim]*/, uint32_t q_len, uint32_t b, uint32_t k,
+                                  const csgpu_predicate_t *pred,
+                                  uint32_t *out_ids /*[k]*/, float *out_dist /*[k]*/, uint32_t *out_n);
 
 /* Reads back the tags of `n` chunk ids (CSGPU_TAG_NONE for ids that are not live). Test/introspection helper. */
 int  csgpu_get_tags(const csgpu_index *ix, const uint32_t *ids, uint64_t n, uint32_t *out_tags);

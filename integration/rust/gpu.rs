@@ -18,7 +18,7 @@ use std::ffi::{CStr, CString};
 use std::os::raw::{c_char, c_int, c_void};
 use std::path::Path;
 
-pub const CSGPU_ABI_VERSION: u32 = 7;
+pub const CSGPU_ABI_VERSION: u32 = 8;
 pub const CSGPU_OK: c_int = 0;
 pub const CSGPU_ERR_DIM: c_int = 1; // "Query embedding dimension mismatch: expected {}, got {}"   store.rs:432-438
 pub const CSGPU_ERR_NOT_BUILT: c_int = 2; // "Index not built. Call build_index() after inserting chunks."   store.rs:440-444
@@ -105,6 +105,7 @@ extern "C" {
     pub fn csgpu_search_filtered(ix: *const CsgpuIndex, q: *const f32, q_len: u32, k: u32, id_bitmap: *const u64, n_bits: u64, out_ids: *mut u32, out_dist: *mut f32, out_n: *mut u32) -> c_int;
     pub fn csgpu_append_tagged(ix: *mut CsgpuIndex, rows: *const f32, ids: *const u32, tags: *const u32, n: u64) -> c_int;
     pub fn csgpu_search_tagged(ix: *const CsgpuIndex, q: *const f32, q_len: u32, k: u32, pred: *const CsgpuPredicate, out_ids: *mut u32, out_dist: *mut f32, out_n: *mut u32) -> c_int;
+    pub fn csgpu_search_variants_tagged(ix: *const CsgpuIndex, q: *const f32, q_len: u32, b: u32, k: u32, pred: *const CsgpuPredicate, out_ids: *mut u32, out_dist: *mut f32, out_n: *mut u32) -> c_int;
     pub fn csgpu_get_tags(ix: *const CsgpuIndex, ids: *const u32, n: u64, out_tags: *mut u32) -> c_int;
     pub fn csgpu_search_keys_device(ix: *const CsgpuIndex, q_dev: *const f32, k: u32, out_keys_dev: *mut u64, stream: *mut c_void) -> c_int;
     pub fn csgpu_merge_keys_device(ix: *const CsgpuIndex, keys_dev: *const u64, n_lists: u32, k: u32, out_keys_dev: *mut u64, stream: *mut c_void) -> c_int;
@@ -330,6 +331,29 @@ impl GpuIndex {
         let (mut ids, mut dist, mut n) = (vec![0u32; cap], vec![0f32; cap], 0u32);
         check(unsafe {
             csgpu_search_variants(self.raw, flat.as_ptr(), self.dim as u32, b as u32, limit as u32, ids.as_mut_ptr(), dist.as_mut_ptr(), &mut n)
+        })?;
+        Ok(Self::collect(ids, dist, n))
+    }
+
+    /// `search_variants` under a row-tag predicate: hybrid search with a language / path filter as ONE call
+    /// (src/search/mod.rs:508-590 + the post-filters at :727-737); `limit` results survive the filter.
+    pub fn search_variants_tagged(&self, queries: &[&[f32]], limit: usize, lang_mask: u32, file_lo: u32, file_hi: u32,
+                                  file_bitmap: Option<&[u64]>, n_file_bits: u64) -> Result<Vec<(u32, f32)>> {
+        let b = queries.len();
+        let mut flat = Vec::with_capacity(b * self.dim);
+        for q in queries {
+            flat.extend_from_slice(q);
+        }
+        let pred = CsgpuPredicate {
+            lang_mask, file_lo, file_hi, reserved: 0,
+            file_bitmap: file_bitmap.map_or(std::ptr::null(), |m| m.as_ptr()),
+            n_file_bits: if file_bitmap.is_some() { n_file_bits } else { 0 },
+        };
+        let cap = limit.max(1);
+        let (mut ids, mut dist, mut n) = (vec![0u32; cap], vec![0f32; cap], 0u32);
+        check(unsafe {
+            csgpu_search_variants_tagged(self.raw, flat.as_ptr(), self.dim as u32, b as u32, limit as u32, &pred,
+                                         ids.as_mut_ptr(), dist.as_mut_ptr(), &mut n)
         })?;
         Ok(Self::collect(ids, dist, n))
     }

@@ -24,7 +24,7 @@ def test_header_symbols_all_exported_and_bound():
         assert hasattr(lib, n), f"libcsgpu.so does not export {n}"
         assert n in _lib.SIGNATURES, f"{n} is declared in csgpu.h but not bound in _lib.SIGNATURES"
     assert set(_lib.SIGNATURES) == set(names)
-    assert lib.csgpu_abi_version() == 7
+    assert lib.csgpu_abi_version() == 8
 
 
 def test_stats_struct_layout_matches_header():

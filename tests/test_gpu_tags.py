@@ -80,6 +80,52 @@ def test_tagged_parity(cs, oracle, d):
             check_topk(gi, gd, oi, od, o64, k_eff)
 
 
+@pytest.mark.parametrize("n,d,devices", [(30_000, 384, None), (30_000, 100, None), (24_000, 384, [0, 0]), (700_000, 384, None)])
+def test_variants_under_a_tag_predicate(cs, oracle, n, d, devices):
+    """csgpu_search_variants_tagged = the reference's hybrid search with a language / path filter as ONE call: b variants,
+    each searched over the rows that pass the predicate, deduplicated by chunk id. Must equal the dedup of the b
+    csgpu_search_tagged lists bit for bit — on the multi-query route (small corpora: the predicate is applied to the results
+    that beat a threshold), on the per-variant filtered-scan route (700k x 384 = 1.08 GB > the 768 MB crossover; also
+    dim % 128 != 0), and on a two-shard index."""
+    rng = np.random.default_rng(n + d)
+    tags = oracle.synth_tags(0, n)
+    st = cs.VectorStore.new(None, d, devices=devices)
+    if n >= 500_000:
+        st.append_synthetic(55, 0, n, 0, tagged=True)
+    else:
+        rows = rng.standard_normal((n, d)).astype(np.float32)
+        rows[[7, 700, 7000]] = 0.0                                 # zero-norm rows keep their tags on the side list
+        tags[rng.random(n) < 0.02] = 0xFFFFFFFF                    # some untagged rows
+        st.append_rows(rows, np.arange(n, dtype=np.uint32), tags)
+    st.build_index()
+    n_files = n // 37 + 1
+    base = rng.standard_normal(d).astype(np.float32)
+    qs = np.stack([base] + [base + np.float32(0.3) * rng.standard_normal(d).astype(np.float32) for _ in range(15)])
+    qs[4] = 0.0                                                    # a zero-norm variant: distance 0.0 to every allowed row
+    lib = cs._lib.load()
+    for ci, p in enumerate(_cases(rng, n_files)):
+        for b, k in ((9, 200), (2, 10), (16, 32), (5, 33), (1, 10)):
+            l0 = lib.csgpu_kernel_launches()
+            gi, gd = st.search_variants_tagged_ids(qs[:b], k, p)
+            launches = lib.csgpu_kernel_launches() - l0
+            lists = [st.search_tagged_ids(q, k, p) for q in qs[:b]]
+            wi, wd = oracle.dedup_variants(lists, k)
+            assert np.array_equal(gi, wi) and np.array_equal(gd.view(np.uint32), wd.view(np.uint32)), (ci, b, k)
+            assert len(set(gi.tolist())) == len(gi)
+            if devices is None and d % 128 == 0 and n < 500_000 and b >= 2:
+                assert launches == 2, (launches, b, k)             # one multi-query pass + the dedup kernel
+    # no predicate restriction at all == the unfiltered variants call
+    from codesearch_b200.tags import TagPredicate
+    if n < 500_000:
+        ai, ad = st.search_variants_tagged_ids(qs[:9], 50, TagPredicate())
+        ui, ud = st.search_variants_ids(qs[:9], 50)
+        untagged_hit = (st.get_tags(ui) == 0xFFFFFFFF).any()
+        if not untagged_hit:                                       # (an untagged row passes no language mask)
+            assert np.array_equal(ai, ui) and np.array_equal(ad.view(np.uint32), ud.view(np.uint32))
+    with pytest.raises(cs.CsgpuError):
+        st.search_variants_tagged_ids(qs[:9, : d - 1], 10, TagPredicate())
+
+
 def test_tags_follow_rows_through_delete_and_rebuild(cs, oracle):
     rng = np.random.default_rng(77)
     n, d = 6000, 384

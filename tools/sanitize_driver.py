@@ -26,6 +26,9 @@ for k in (10, 100, 1000):                                   # single-query scan:
 st.search_ids(q, 50, cs.RowFilter.from_mask(rng.random(n) < 0.3))                      # id-bitmap filter
 st.search_tagged_ids(q, 50, TagPredicate(lang_mask=0x3F, file_lo=3, file_hi=120))     # row-tag predicate
 qs = rng.standard_normal((70, d)).astype(np.float32)
+for kk in (10, 100):                                        # variants under a tag predicate: multi-query kernels with the predicate
+    vt = st.search_variants_tagged_ids(qs[:9], kk, TagPredicate(lang_mask=0x3F, file_lo=3, file_hi=120))
+    assert len(set(vt[0].tolist())) == len(vt[0])
 st.search_batch_ids(qs[:8], 10)                             # multi-query scan, per-warp lists
 st.search_batch_ids(qs[:8], 100)                            # multi-query scan, CTA buffers
 st.search_variants_ids(qs[:5], 20)                          # device-side dedup of variants
