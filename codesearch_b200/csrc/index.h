@@ -173,6 +173,7 @@ int bf16_reserve_stage(const csgpu_index *ix, Shard *sh, uint64_t pending);
 int bf16_convert_pending(const csgpu_index *ix, Shard *sh);
 bool batch_f32_dim_supported(uint32_t dim_pad);
 int batch_after_build(const csgpu_index *ix, Shard *sh);
+int tag_stats_refresh(csgpu_index *ix);   // csgpu.cu
 int shadow_refresh(const csgpu_index *ix, Shard *sh);
 void batch_free_ctx(Shard *sh);
 bool batch_gemm_available(const csgpu_index *ix);
@@ -231,6 +232,11 @@ struct csgpu_index {
     mutable std::mutex multi_mu;
     mutable std::condition_variable multi_cv;
     mutable int multi_running = 0;
+    // Tag statistics of the built rows, refreshed at every build / load (tag_stats_refresh, csgpu.cu): rows per language id and
+    // the largest file id. Only used to ESTIMATE a predicate's density when a search has to pick a route.
+    uint64_t lang_rows[32] = {};
+    uint64_t tagged_rows = 0;
+    uint32_t max_file_id = 0;
     mutable std::atomic<uint32_t> batch_route{0};          // CSGPU_ROUTE_* of the last GEMM-shaped batch
     mutable std::atomic<float> filter_max_err{0.f};        // largest |d_filter - d_f32| its rescoring saw
     mutable std::atomic<uint64_t> prefilter_rescored{0};   // fp32 rows read by the last tensor-prefilter batch chunk
