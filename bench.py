@@ -1045,6 +1045,32 @@ def extras_c5(cs, _lib, lib, torch, dist, rank, world, local_rank, gather_obj, s
         out["densities"][str(dens)] = {"device_ms": round(ms, 4), "dense_GBps": round(N * (d * 4 + 4) / ms / 1e6, 1)}
         preds.append(pred)
         answers.append(searcher.search_keys_device(qd[0], k, pred).cpu().numpy().copy())
+    if world == 1:
+        # the caller shape of configs[4]: HYBRID search under the mask — 9 query variants x limit 200, each searched over the
+        # rows that pass the predicate, deduplicated by chunk id, as ONE csgpu_search_variants_tagged call (host buffers in and
+        # out); checked against the dedup of the nine single tagged searches
+        from codesearch_b200.tags import TagPredicate
+        hyb = {}
+        try:
+            for dens, pred in zip((1.0, 0.25, 0.01), preds):
+                tp = TagPredicate(lang_mask=int(pred.lang_mask), file_lo=int(pred.file_lo), file_hi=int(pred.file_hi))
+                for i in range(2):
+                    st.search_variants_tagged_ids(qs[:9], k, tp)
+                t0 = time.perf_counter()
+                for i in range(10):
+                    gi, gd = st.search_variants_tagged_ids(qs[i % 7: i % 7 + 9], k, tp)
+                ms = (time.perf_counter() - t0) / 10 * 1e3
+                gi, gd = st.search_variants_tagged_ids(qs[:9], k, tp)
+                best = {}
+                for q in qs[:9]:
+                    for i_, d_ in zip(*st.search_tagged_ids(q, k, tp)):
+                        if int(i_) not in best or d_ < best[int(i_)]:
+                            best[int(i_)] = d_
+                want_ids = [i_ for i_, _ in sorted(best.items(), key=lambda t: (t[1], t[0]))[:k]]
+                hyb[str(dens)] = {"e2e_ms": round(ms, 3), "equals_dedup_of_nine_tagged_searches": bool(gi.tolist() == want_ids)}
+        except Exception as e:  # noqa: BLE001
+            hyb = {"error": repr(e)[:200]}
+        out["hybrid_9_variants_limit200_under_the_mask"] = hyb
     # the same three searches with the opt-in byte prefilter (round 2: the int8 kernel's FILT instantiation streams only row
     # groups the predicate allows; survivors are rescored in fp32 in the same launch) — every answer must stay bit-identical
     st.set_byte_prefilter(True)
