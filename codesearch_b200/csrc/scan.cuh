@@ -70,6 +70,10 @@ struct ScanArgs {
     const unsigned *run_if = nullptr;   // non-null: the whole launch is a no-op unless *run_if != 0 (device-side fallback of
                                         // the byte prefilter: the host cannot look at the status without synchronising)
     uint32_t static_split = 0;          // filtered scans: 1 = fixed-stride block split instead of the work counter (CSGPU_SCAN_STATIC)
+    // device time of the launch without CUDA events (two event records cost a small-corpus query 8 us of its ~50): CTA 0 stamps
+    // %globaltimer into *t0_slot (device memory) when it starts, the CTA that writes the result stores now - t0 (ns) into
+    // *elapsed_out (mapped host memory). Both null: no stamps.
+    unsigned long long *t0_slot = nullptr, *elapsed_out = nullptr;
     unsigned long long *timing = nullptr;   // diagnostic (CSGPU_SCAN_TIMING=1): [gridDim.x + 1][4] globaltimer stamps — per CTA
                                             // start / streaming done / CTA list written; last CTA: ticket taken / merged / done
 };
@@ -512,6 +516,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const Scan
     if (a.run_if != nullptr && *reinterpret_cast<const volatile unsigned *>(a.run_if) == 0) return;   // CTA-uniform
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (a.timing && threadIdx.x == 0) a.timing[blockIdx.x * 4 + 0] = global_timer_ns();
+    if (a.t0_slot != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *a.t0_slot = global_timer_ns();
     // k <= 32: per-warp register selector. k > 32: ONE candidate buffer per CTA (a.kpad = its capacity) + threshold
     using Sel = typename ScanSelOf<BIG>::type;
     __shared__ unsigned cb_cnt;
@@ -712,6 +717,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, OCC) scan_topk_kernel(const Scan
     if (threadIdx.x == 0) {
         a.ticket[0] = 0; a.ticket[1] = 0;
         if (a.timing) a.timing[gridDim.x * 4 + 2] = global_timer_ns();
+        // CTA 0 stored t0 before its __threadfence() + ticket; this (last) CTA read every ticket after them
+        if (a.elapsed_out != nullptr) *a.elapsed_out = global_timer_ns() - *reinterpret_cast<volatile unsigned long long *>(a.t0_slot);
     }
 }
 

@@ -71,7 +71,8 @@ typedef struct csgpu_stats_t {
     uint32_t dtype;
     uint32_t n_devices;
     uint32_t built;            /* mirrors VectorStore::is_indexed()  store.rs:747              */
-    float    last_search_us;   /* device time of the most recent search (CUDA events)          */
+    float    last_search_us;   /* device time of the most recent search: CUDA events; a single-device fp32 scan stamps
+                                * %globaltimer in the kernel instead (first CTA started -> result written)              */
     uint32_t abi_version;
     uint64_t rows_per_device[8];
     uint64_t coalesced_passes;   /* micro-batcher: corpus passes launched ...                       */
