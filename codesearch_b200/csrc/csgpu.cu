@@ -377,9 +377,14 @@ static int enqueue_merge(const uint64_t *keys_dev, uint32_t n_lists, uint32_t nq
 static int enqueue_scan_multi(const csgpu_index *ix, const Shard *sh, SearchCtx *c, const float *q_dev, uint32_t nq,
                               uint32_t k, bool with_zero_ids, uint64_t *out_keys, cudaStream_t st,
                               const csgpu_predicate_t *pred = nullptr /* row-tag predicate */,
-                              const uint64_t *file_bitmap_dev = nullptr, uint64_t n_file_bits = 0)
+                              const uint64_t *file_bitmap_dev = nullptr, uint64_t n_file_bits = 0,
+                              bool stamp_time = false /* in-kernel device time -> c->out_pin[MAX_BATCH * CSGPU_MAX_K] (ns) */)
 {
     MultiArgs a;
+    if (stamp_time) {
+        a.t0_slot = reinterpret_cast<unsigned long long *>(c->ticket + 4);
+        a.elapsed_out = reinterpret_cast<unsigned long long *>(c->out_pin + (size_t)MAX_BATCH * CSGPU_MAX_K);
+    }
     a.rows = reinterpret_cast<const float4 *>(sh->rows);
     a.ids = sh->ids;
     a.n_rows = sh->n_built;
@@ -987,9 +992,9 @@ static int search_multi(const csgpu_index *ix, const float *q, uint32_t nq, uint
             memset(c->q_pin, 0, qbytes);
             for (uint32_t j = 0; j < nq; ++j) memcpy(c->q_pin + (size_t)j * ix->dim_pad, q + (size_t)j * ix->dim, (size_t)ix->dim * sizeof(float));
             CS_CUDA(cudaMemcpyAsync(c->q_dev, c->q_pin, qbytes, cudaMemcpyHostToDevice, c->stream));
-            if (g == 0) CS_CUDA(cudaEventRecord(c->ev0, c->stream));
+            if (g == 0 && G > 1) CS_CUDA(cudaEventRecord(c->ev0, c->stream));   // one device: the kernel times itself (see search_one)
             uint64_t *dst = (G == 1) ? c->out_pin : c->out_dev;
-            int r = enqueue_scan_multi(ix, sh, c, c->q_dev, nq, k, g == 0, dst, c->stream);
+            int r = enqueue_scan_multi(ix, sh, c, c->q_dev, nq, k, g == 0, dst, c->stream, nullptr, nullptr, 0, /*stamp_time=*/G == 1);
             if (r) return r;
         }
         SearchCtx *c0 = ctx[0];
@@ -1009,10 +1014,11 @@ static int search_multi(const csgpu_index *ix, const float *q, uint32_t nq, uint
         }
         {
             DeviceGuard dg(ix->shards[0]->device);
-            CS_CUDA(cudaEventRecord(c0->ev1, c0->stream));
+            if (G > 1) CS_CUDA(cudaEventRecord(c0->ev1, c0->stream));
             CS_CUDA(cudaStreamSynchronize(c0->stream));
             float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, c0->ev0, c0->ev1) == cudaSuccess) ix->last_search_us.store(ms * 1000.f);
+            if (G == 1) ix->last_search_us.store((float)c0->out_pin[(size_t)MAX_BATCH * CSGPU_MAX_K] * 1e-3f);
+            else if (cudaEventElapsedTime(&ms, c0->ev0, c0->ev1) == cudaSuccess) ix->last_search_us.store(ms * 1000.f);
         }
         for (uint32_t j = 0; j < nq; ++j)
             decode_keys(c0->out_pin + (size_t)j * k, k, out_ids + (size_t)j * k, out_dist + (size_t)j * k, out_n ? out_n + j : nullptr);

@@ -39,6 +39,9 @@ struct MultiArgs {
     // read, which is the right trade for a handful of variants over a small corpus (the host routes by corpus size).
     const uint32_t *tags = nullptr;
     uint32_t lang_mask = 0, file_lo = 0, file_hi = 0;
+    // in-kernel device time instead of CUDA events (see ScanArgs): CTA 0 stamps *t0_slot at its start, the last finisher
+    // stores now - t0 (ns) into *elapsed_out (mapped host memory)
+    unsigned long long *t0_slot = nullptr, *elapsed_out = nullptr;
 };
 
 // is row `row` (chunk id `id`) allowed under the launch's filter: id bitmap, or row-tag predicate (+ per-file bitmap)
@@ -154,6 +157,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, (E <= 4) ? 2 : 1) scan_multi_top
     __shared__ unsigned s_ticket;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t dim4 = a.dim4;
+    if (a.t0_slot != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *a.t0_slot = global_timer_ns();
 
     float4 *qs = reinterpret_cast<float4 *>(smem_raw);                                   // [MQT][dim4]
     uint64_t *keys0 = reinterpret_cast<uint64_t *>(smem_raw + (size_t)MQT * dim4 * sizeof(float4));
@@ -335,7 +339,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, (E <= 4) ? 2 : 1) scan_multi_top
         cta_topk_of_lists32(a.cand + (size_t)b * total, gridDim.x, a.k, zrun, keys0, a.out_keys + (size_t)b * a.k, warp, lane);
         __syncthreads();
     }
-    if (threadIdx.x == 0 && atomicAdd(a.ticket + 2, 1u) == n_fin - 1) { a.ticket[0] = 0; a.ticket[1] = 0; a.ticket[2] = 0; }
+    if (threadIdx.x == 0 && atomicAdd(a.ticket + 2, 1u) == n_fin - 1) {   // the last finisher to leave
+        a.ticket[0] = 0; a.ticket[1] = 0; a.ticket[2] = 0;
+        if (a.elapsed_out != nullptr) *a.elapsed_out = global_timer_ns() - *reinterpret_cast<volatile unsigned long long *>(a.t0_slot);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -358,6 +365,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_multi_cta_topk_kernel(co
     constexpr uint32_t SLACK = SYNC_IT * R * SCAN_WARPS;     // most keys one query can receive between two sync points
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned s_ticket;
+    if (a.t0_slot != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *a.t0_slot = global_timer_ns();
     __shared__ unsigned cnt_s[MQT];
     __shared__ uint64_t thr_s[MQT];
     __shared__ float qflag[MQT];
@@ -554,7 +562,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_multi_cta_topk_kernel(co
         for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) a.out_keys[(size_t)b * k + j] = buf[j];
         __syncthreads();
     }
-    if (threadIdx.x == 0 && atomicAdd(a.ticket + 2, 1u) == n_fin - 1) { a.ticket[0] = 0; a.ticket[1] = 0; a.ticket[2] = 0; }
+    if (threadIdx.x == 0 && atomicAdd(a.ticket + 2, 1u) == n_fin - 1) {   // the last finisher to leave
+        a.ticket[0] = 0; a.ticket[1] = 0; a.ticket[2] = 0;
+        if (a.elapsed_out != nullptr) *a.elapsed_out = global_timer_ns() - *reinterpret_cast<volatile unsigned long long *>(a.t0_slot);
+    }
 }
 
 
