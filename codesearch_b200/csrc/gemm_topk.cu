@@ -304,6 +304,8 @@ void batch_free_ctx(Shard *sh)
     DeviceGuard g(sh->device);
     BatchCtx *c = sh->batch;
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->e0) cudaEventDestroy(c->e0);
+    if (c->e1) cudaEventDestroy(c->e1);
     cudaFree(c->q_f32); cudaFree(c->q_prep); cudaFree(c->flags); cudaFree(c->thr); cudaFree(c->count); cudaFree(c->count_saved);
     cudaFree(c->cand); cudaFree(c->out); cudaFree(c->scalar); cudaFree(c->seg_count);
     cudaFreeHost(c->q_pin); cudaFreeHost(c->out_pin);
@@ -319,6 +321,8 @@ static int batch_ctx(const csgpu_index *ix, Shard *sh, BatchCtx **out)
     sh->batch = c;
     const size_t nq = (size_t)BF_MAX_QBLOCKS * GT_BLOCK_M;
     CS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CS_CUDA(cudaEventCreate(&c->e0));
+    CS_CUDA(cudaEventCreate(&c->e1));
     CS_CUDA(cudaMalloc(&c->q_f32, nq * ix->dim_pad * sizeof(float)));   // raw queries, row pitch dim_pad (zero-padded like the scan kernel's query)
     CS_CUDA(cudaMalloc(&c->q_prep, nq * ix->dim_pad * sizeof(float)));   // bf16 uses half of it
     CS_CUDA(cudaMalloc(&c->flags, nq));
@@ -690,8 +694,7 @@ int batch_search(const csgpu_index *ix, const float *q, uint32_t b, uint32_t k,
     BatchCtx *c0 = ctx[0];
     DeviceGuard g0(sh0->device);
     const uint32_t chunk = BF_MAX_QBLOCKS * GT_BLOCK_M;
-    cudaEvent_t e0, e1;
-    CS_CUDA(cudaEventCreate(&e0)); CS_CUDA(cudaEventCreate(&e1));
+    cudaEvent_t e0 = c0->e0, e1 = c0->e1;
     CS_CUDA(cudaEventRecord(e0, c0->stream));
     uint64_t *gather = nullptr;
     if (G > 1) CS_CUDA(cudaMalloc(&gather, G * (size_t)std::min(chunk, b) * k * sizeof(uint64_t)));
@@ -749,7 +752,6 @@ int batch_search(const csgpu_index *ix, const float *q, uint32_t b, uint32_t k,
     cudaStreamSynchronize(c0->stream);
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) ix->last_search_us.store(ms * 1000.f);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(gather);
     return rc;
 }

@@ -90,6 +90,7 @@ struct BatchCtx {
     unsigned *seg_count = nullptr;  // [1024][2 * 148] per-(query, segment) candidate counts of the tensor-core kernel
     float *q_pin = nullptr;
     uint64_t *out_pin = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;   // device time of a batch (created once: create + destroy per call cost ~10 us)
 };
 
 // Fused cross-GPU exchange state of a single-device index (scan.cuh: ExchangeDev). One cudaMalloc block:
