@@ -13,6 +13,7 @@
 //   build_index()                                               store.rs:386-430
 //   search(query_embedding, limit) -> vector<SearchResult>      store.rs:431-486   <- the CUDA path (csgpu_search)
 //   search_filtered / search_batch / search_tagged              additive
+//   search_variants / search_variants_tagged                    additive (§8f N3, N3 x N4): query variants -> one list
 //   get_chunk / get_chunk_as_result / get_chunks_by_file / stats / clear / is_indexed
 //
 // Chunk metadata (the LMDB "chunks" table, store.rs:97) stays on the host: here an ordered map keyed by chunk id,
@@ -282,8 +283,20 @@ class VectorStore {
         return out;
     }
 
-    // search() restricted by language / path BEFORE scoring (device-side row-tag predicate), so `limit` results survive
-    std::vector<SearchResult> search_tagged(const std::vector<float> &q, size_t limit, const TagFilter &f) const
+    // [b][dimensions] row-major, with the reference's guard message on a wrong length (store.rs:432-438)
+    std::vector<float> flatten(const std::vector<std::vector<float>> &queries) const
+    {
+        std::vector<float> q(queries.size() * dimensions);
+        for (size_t j = 0; j < queries.size(); ++j) {
+            if (queries[j].size() != dimensions)
+                throw Error(CSGPU_ERR_DIM, "Query embedding dimension mismatch: expected " + std::to_string(dimensions) + ", got " +
+                                               std::to_string(queries[j].size()));
+            std::memcpy(q.data() + j * dimensions, queries[j].data(), dimensions * sizeof(float));
+        }
+        return q;
+    }
+    // TagFilter -> csgpu_predicate_t; `bm` receives the per-file bitmap the predicate points into (keep it alive for the call)
+    csgpu_predicate_t predicate_of(const TagFilter &f, std::vector<uint64_t> &bm) const
     {
         csgpu_predicate_t p;
         std::memset(&p, 0, sizeof p);
@@ -294,7 +307,6 @@ class VectorStore {
             p.lang_mask = 0;
             for (Language l : f.languages) p.lang_mask |= 1u << (uint32_t)l;
         }
-        std::vector<uint64_t> bm;
         if (f.path_prefix || f.path_contains) {
             const std::string root = normalize_path_str(f.project_root);
             const std::string prefix = f.path_prefix ? normalize_path_str(*f.path_prefix) : std::string();
@@ -312,10 +324,44 @@ class VectorStore {
             p.file_bitmap = bm.data();
             p.n_file_bits = file_paths_.size();
         }
+        return p;
+    }
+
+    // search() restricted by language / path BEFORE scoring (device-side row-tag predicate), so `limit` results survive
+    std::vector<SearchResult> search_tagged(const std::vector<float> &q, size_t limit, const TagFilter &f) const
+    {
+        std::vector<uint64_t> bm;
+        const csgpu_predicate_t p = predicate_of(f, bm);
         std::vector<uint32_t> ids(std::max<size_t>(limit, 1));
         std::vector<float> dist(std::max<size_t>(limit, 1));
         uint32_t n = 0;
         check(csgpu_search_tagged(ix_.get(), q.data(), (uint32_t)q.size(), (uint32_t)limit, &p, ids.data(), dist.data(), &n));
+        return join(ids.data(), dist.data(), n);
+    }
+
+    // The <= 16 query variants of ONE user query -> one list: per chunk id the best distance, then the best `limit`
+    // (src/search/mod.rs:508-590: par_iter of searches + HashMap / BinaryHeap dedup) in one call.
+    std::vector<SearchResult> search_variants(const std::vector<std::vector<float>> &queries, size_t limit) const
+    {
+        const std::vector<float> q = flatten(queries);
+        std::vector<uint32_t> ids(std::max<size_t>(limit, 1));
+        std::vector<float> dist(std::max<size_t>(limit, 1));
+        uint32_t n = 0;
+        check(csgpu_search_variants(ix_.get(), q.data(), (uint32_t)dimensions, (uint32_t)queries.size(), (uint32_t)limit, ids.data(), dist.data(), &n));
+        return join(ids.data(), dist.data(), n);
+    }
+    // ... under a language / path filter: the hybrid search of src/search/mod.rs:508-590 with the post-filters of :727-737 applied
+    // BEFORE scoring, one call
+    std::vector<SearchResult> search_variants_tagged(const std::vector<std::vector<float>> &queries, size_t limit, const TagFilter &f) const
+    {
+        const std::vector<float> q = flatten(queries);
+        std::vector<uint64_t> bm;
+        const csgpu_predicate_t p = predicate_of(f, bm);
+        std::vector<uint32_t> ids(std::max<size_t>(limit, 1));
+        std::vector<float> dist(std::max<size_t>(limit, 1));
+        uint32_t n = 0;
+        check(csgpu_search_variants_tagged(ix_.get(), q.data(), (uint32_t)dimensions, (uint32_t)queries.size(), (uint32_t)limit, &p,
+                                           ids.data(), dist.data(), &n));
         return join(ids.data(), dist.data(), n);
     }
 

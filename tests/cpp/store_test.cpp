@@ -275,6 +275,37 @@ static void test_additive_methods()
         for (size_t i = 0; i < std::min(batch[j].size(), single.size()); ++i)
             CHECK(batch[j][i].id == single[i].id && batch[j][i].distance == single[i].distance);
     }
+    // query variants -> one list (src/search/mod.rs:508-590 restated on the host: best distance per id, then the best `limit`,
+    // ties by id), plain and under a filter: the mirror's one call must equal the dedup of its own per-variant searches
+    auto dedup = [&](const std::vector<std::vector<SearchResult>> &lists, size_t limit) {
+        std::map<uint32_t, float> best;
+        for (const auto &l : lists)
+            for (const auto &r : l) {
+                auto it = best.find(r.id);
+                if (it == best.end() || r.distance < it->second) best[r.id] = r.distance;
+            }
+        std::vector<std::pair<float, uint32_t>> order;
+        for (const auto &kv : best) order.emplace_back(kv.second, kv.first);
+        std::sort(order.begin(), order.end());
+        if (order.size() > limit) order.resize(limit);
+        return order;
+    };
+    {
+        auto got = store.search_variants(qs, 25);
+        auto want = dedup(batch, 25);
+        CHECK(got.size() == want.size());
+        for (size_t i = 0; i < std::min(got.size(), want.size()); ++i) CHECK(got[i].id == want[i].second && got[i].distance == want[i].first);
+        std::vector<std::vector<SearchResult>> tagged;
+        for (const auto &v : qs) tagged.push_back(store.search_tagged(v, 25, src));
+        auto got_t = store.search_variants_tagged(qs, 25, src);
+        auto want_t = dedup(tagged, 25);
+        CHECK(got_t.size() == want_t.size() && got_t.size() == 25);
+        for (size_t i = 0; i < std::min(got_t.size(), want_t.size()); ++i) {
+            CHECK(got_t[i].id == want_t[i].second && got_t[i].distance == want_t[i].first);
+            CHECK(got_t[i].path.rfind("/r/src/", 0) == 0);
+        }
+        CHECK(store.search_variants_tagged(qs, 25, go).empty());
+    }
     CHECK(language_from_path("main.rs") == Language::Rust);            // src/file/language.rs:145-166
     CHECK(language_from_path("a.pyi") == Language::Python && language_from_path("x.tsx") == Language::TypeScript);
     CHECK(language_from_path("Dockerfile") == Language::Shell && language_from_path(".env") == Language::Shell);
