@@ -357,6 +357,12 @@ class VectorStore:
     def search_variants(self, queries, limit: int) -> list[SearchResult]:
         return self._join(*self.search_variants_ids(queries, limit))
 
+    def search_variants_tagged(self, queries, limit: int, languages=None, path_prefix: str | None = None,
+                               path_contains: str | None = None, project_root: str = "") -> list[SearchResult]:
+        """search_variants() restricted by language / path BEFORE scoring (see search_tagged): hybrid search under a filter."""
+        pred = self.files.predicate(languages, path_prefix, path_contains, project_root)
+        return self._join(*self.search_variants_tagged_ids(queries, limit, pred))
+
     def search_variants_tagged_ids(self, queries, limit: int, pred: TagPredicate):
         """search_variants_ids under a row-tag predicate (csgpu_search_variants_tagged): the reference's hybrid search with a
         language / path filter (src/search/mod.rs:508-590 + the post-filters at :727-737) as one call."""

@@ -206,6 +206,19 @@ def test_search_tagged_by_path_and_language(cs):
     r = st.search_tagged(q, 500, languages=["Shell", "Markdown"])
     assert len(r) == 80
     assert st.search_tagged(q, 10, languages=["Go"]) == []
+    # hybrid search under the same filters: query variants -> one list, every hit inside the filter, `limit` of them survive
+    qs = np.stack([q] + [q + np.float32(0.3) * rng.standard_normal(d).astype(np.float32) for _ in range(8)])
+    r = st.search_variants_tagged(qs, 10, languages=["Rust"])
+    assert len(r) == 10 and all(x.path.endswith(".rs") for x in r) and len({x.id for x in r}) == 10
+    per_variant = [st.search_tagged(v, 10, languages=["Rust"]) for v in qs]
+    best = {}
+    for lst in per_variant:
+        for x in lst:
+            if x.id not in best or x.distance < best[x.id]:
+                best[x.id] = x.distance
+    want = sorted(best.items(), key=lambda t: (t[1], t[0]))[:10]
+    assert [(x.id, x.distance) for x in r] == want
+    assert st.search_variants_tagged(qs, 10, languages=["Go"]) == []
 
 
 @pytest.mark.parametrize("byte_prefilter", [False, True])
