@@ -1167,10 +1167,18 @@ static int search_variants(const csgpu_index *ix, const float *q, uint32_t b, ui
                 if (r) return r;
             }
             // always the ceiling (16 variants x k = 1024 keys): per-launch values from concurrent callers must not undercut each other
+            if (total <= 8192) {   // hash-table dedup: only the distinct ids are sorted (scan.cuh)
+                const uint32_t tbl = pow2_at_least(2 * total, 64), cpad = pow2_at_least(total, 32);
+                CS_CUDA(cudaFuncSetAttribute(dedup_variants_hash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)((size_t)(16384 + 8192) * sizeof(uint64_t))));   // the ceiling, never this launch's size
+                dedup_variants_hash_kernel<<<1, SCAN_THREADS, (size_t)(tbl + cpad) * sizeof(uint64_t), c->stream>>>(
+                    c->out_dev, total, tbl, cpad, k, G == 1 ? c->out_pin : c->cand);
+            } else {
             CS_CUDA(cudaFuncSetAttribute(dedup_variants_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)((size_t)MAX_BATCH * CSGPU_MAX_K * sizeof(uint64_t))));
             // one device: straight into the pinned result; several: the shard's deduplicated list parks in its scratch
             dedup_variants_kernel<<<1, SCAN_THREADS, smem, c->stream>>>(c->out_dev, total, npad, k, G == 1 ? c->out_pin : c->cand);
+            }
             count_launch();
             CS_CUDA(cudaGetLastError());
         }
