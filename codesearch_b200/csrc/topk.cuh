@@ -214,8 +214,14 @@ __device__ __forceinline__ void cta_buf_compact(uint64_t *buf, unsigned *cnt, vo
 {
     __syncthreads();
     const unsigned n = min(*cnt, cap);
-    for (uint32_t t = n + threadIdx.x; t < cap; t += blockDim.x) buf[t] = KEY_EMPTY;
-    cta_sort(buf, cap);   // leading + trailing __syncthreads inside
+    // sort only as many keys as there are (round 2): on a small corpus a CTA's buffer holds a few hundred keys when it finishes,
+    // and the last CTA's first compaction one key per list — a 512-key sort instead of a cap-sized (1024+) one. Slots up to k
+    // are padded so that buf[0..k) is always "best k ascending, KEY_EMPTY padded".
+    uint32_t spad = 32;
+    while (spad < n) spad <<= 1;                              // <= cap: cap is a power of two >= n
+    const uint32_t fill_to = max(spad, min(k, cap));
+    for (uint32_t t = n + threadIdx.x; t < fill_to; t += blockDim.x) buf[t] = KEY_EMPTY;
+    cta_sort(buf, spad);   // leading + trailing __syncthreads inside
     if (threadIdx.x == 0) {
         *cnt = min(n, k);
         if (n >= k) *thr = buf[k - 1];
